@@ -1,0 +1,173 @@
+/*
+ * bwq.h -- C ABI of the B200-native exact expectation-value engine ("blackwater-quantum").
+ *
+ * Drop-in boundary.  The reference (qiskit-community/ml-qem) reaches its
+ * simulator through the Qiskit Estimator primitive:
+ *     blackwater/data/utils.py:418-431   create_estimator_meas_data  (ideal + noisy AerEstimator)
+ *     blackwater/data/utils.py:434-444   create_meas_data_from_estimators
+ *     blackwater/library/learning/estimator.py:279-285  run(self, circuits=, observables=, ...)
+ * and the arithmetic behind it is qiskit-aer's C++ controller (pybind, not in tree).  The entry
+ * points below are what an FFI for that path binds: plain pointers and sizes, no torch / qiskit
+ * types.  ml_qem_b200/engine.py is the ctypes binding; INTEGRATION.md shows the reference-side
+ * stub.
+ *
+ * Conventions
+ *   - qubit 0 is the least-significant bit of a basis-state index (Qiskit little-endian);
+ *   - a Pauli term is (x_mask, z_mask, coeff): bit q of x_mask set for X or Y on qubit q, bit q
+ *     of z_mask set for Z or Y; the value of a term is coeff * Tr(rho P) (real part returned);
+ *   - the caller owns every host buffer for the duration of the call; the library owns all device
+ *     memory inside bwq_ctx; every function returns 0 (BWQ_OK) or a negative error code and the
+ *     message is available from bwq_last_error(); a ctx is not re-entrant (one per GPU);
+ *   - per-circuit failures (unsupported op, too many qubits) are reported in out_status[] and do
+ *     not void the rest of the batch.
+ */
+#ifndef BWQ_H_
+#define BWQ_H_
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define BWQ_VERSION 100 /* 0.1.0 */
+
+enum {
+  BWQ_OK = 0,
+  BWQ_ERR_ARG = -1,      /* malformed input */
+  BWQ_ERR_CUDA = -2,     /* CUDA runtime error (message has the CUDA string) */
+  BWQ_ERR_NOMEM = -3,    /* batch does not fit the device budget even one circuit at a time */
+  BWQ_ERR_UNSUPPORTED = -4,
+  BWQ_ERR_NO_DEVICE = -5 /* no CUDA device: there is NO CPU fallback */
+};
+
+/* per-circuit status */
+enum { BWQ_CIRC_OK = 0, BWQ_CIRC_BAD_OP = 1, BWQ_CIRC_TOO_WIDE = 2, BWQ_CIRC_BAD_QUBIT = 3 };
+
+/* Gate opcodes of the flat gate stream (Qiskit standard gates; names as in
+ * blackwater/data/utils.py:19-49 plus the backend basis id/rz/sx/x/cx/reset). */
+enum {
+  BWQ_G_ID = 0, BWQ_G_X, BWQ_G_Y, BWQ_G_Z, BWQ_G_H, BWQ_G_S, BWQ_G_SDG, BWQ_G_T, BWQ_G_TDG,
+  BWQ_G_SX, BWQ_G_SXDG, BWQ_G_RX, BWQ_G_RY, BWQ_G_RZ, BWQ_G_P, BWQ_G_U2, BWQ_G_U3,
+  BWQ_G_RESET,                                   /* 1-qubit, non-unitary                  */
+  BWQ_G_CX = 32, BWQ_G_CY, BWQ_G_CZ, BWQ_G_CH, BWQ_G_CRX, BWQ_G_CRY, BWQ_G_CRZ, BWQ_G_CP,
+  BWQ_G_CU3, BWQ_G_SWAP, BWQ_G_ISWAP, BWQ_G_RZZ, BWQ_G_RXX, BWQ_G_RYY, BWQ_G_RZX, BWQ_G_ECR,
+  BWQ_G_UNITARY1 = 64, /* params: 8 doubles, row-major 2x2 complex (re,im interleaved)   */
+  BWQ_G_UNITARY2 = 65, /* params: 32 doubles, row-major 4x4 complex, index i_q0 + 2 i_q1 */
+  BWQ_G_COUNT = 66
+};
+
+/* One gate of the stream.  q1 is ignored for 1-qubit gates.  param_idx indexes batch.params
+ * (first of up to 3 consecutive angles; 8 / 32 doubles for UNITARY1 / UNITARY2). */
+typedef struct {
+  uint16_t opcode;
+  uint8_t q0;
+  uint8_t q1;
+  uint32_t param_idx;
+} bwq_op;
+
+/* A batch of independent circuits with their observables, flat structure-of-arrays. */
+typedef struct {
+  int32_t n_circuits;
+  const int32_t* n_qubits;    /* [n_circuits] register width (<= 64)                         */
+  const int64_t* op_offsets;  /* [n_circuits+1] circuit c owns ops[op_offsets[c] .. [c+1])   */
+  const bwq_op* ops;
+  const double* params;
+  int64_t n_params;
+  const int64_t* obs_offsets; /* [n_circuits+1] circuit c owns observables [..)              */
+  const int64_t* term_offsets;/* [n_observables+1] observable o owns Pauli terms [..)        */
+  const uint64_t* term_x;
+  const uint64_t* term_z;
+  const double* term_coeff;   /* real coefficients                                           */
+} bwq_batch;
+
+/* Noise table: one error per (opcode, ordered physical qubits), the lookup Aer's
+ * NoiseModel.from_backend uses (reached from blackwater/data/utils.py:427).  Errors are given in
+ * the real Pauli-transfer-matrix form R[i][j] = Tr(P_i E(P_j)) / 2^k, P in {I,X,Y,Z}, index
+ * digit_q0 + 4*digit_q1.
+ *   kind BWQ_NOISE_DENSE1 : 16 doubles, row-major 4x4
+ *   kind BWQ_NOISE_DENSE2 : 256 doubles, row-major 16x16
+ *   kind BWQ_NOISE_RELAX2 : 25 doubles d[16], ca[4], cb[4], cab -- the closed form of
+ *        (thermal relaxation (x) thermal relaxation) o (any Pauli-diagonal channel):
+ *        out[i] = d[i] in[i];  out[Z,b] += ca[b] in[I,b];  out[a,Z] += cb[a] in[a,I];
+ *        out[Z,Z] += cab in[I,I]
+ *   q1 = 255 marks a 1-qubit entry; q0 = 255 marks an all-qubit default for the opcode. */
+enum { BWQ_NOISE_DENSE1 = 1, BWQ_NOISE_DENSE2 = 2, BWQ_NOISE_RELAX2 = 3 };
+typedef struct {
+  int32_t n_entries;
+  const uint16_t* opcode;   /* [n_entries] */
+  const uint8_t* q0;        /* [n_entries] */
+  const uint8_t* q1;        /* [n_entries] */
+  const uint8_t* kind;      /* [n_entries] */
+  const int64_t* data_off;  /* [n_entries] offset into data (doubles) */
+  const double* data;
+  int64_t n_data;
+} bwq_noise_table;
+
+/* Tunables (0 = library default). */
+typedef struct {
+  int32_t tile_qubits;      /* Pauli digits per shared-memory tile, 2..7 (default 6)          */
+  int32_t low_qubits;       /* lowest digits always resident in a tile (coalescing), default 2 */
+  int64_t max_state_bytes;  /* device budget for resident states (default: 80% of free)        */
+  int32_t chunk_circuits;   /* circuits simulated together (default: as many as fit)          */
+  int32_t host_threads;     /* lowering threads (default: hardware concurrency)               */
+} bwq_options;
+
+/* Counters of the last *_run call (for the roofline: bytes = sweeps x 16 B x 4^n). */
+typedef struct {
+  int64_t n_sweep_launches;    /* kernel launches of the density-matrix sweep kernel     */
+  int64_t n_state_sweeps;      /* (circuit, sweep) pairs executed = P of SURVEY 8(d)     */
+  int64_t n_passes;            /* register passes (2-qubit groups) executed              */
+  int64_t n_gates;             /* gates consumed from the stream                         */
+  int64_t state_bytes_swept;   /* sum over state sweeps of 2 * 8 B * 4^n_active          */
+  int64_t n_other_launches;    /* init / expectation / statevector launches              */
+  double lower_ms, h2d_ms, kernel_ms, d2h_ms; /* host wall / device-event times          */
+  double sweep_kernel_ms;      /* CUDA-event time of the sweep launches only             */
+} bwq_stats;
+
+typedef struct bwq_ctx bwq_ctx;
+
+int bwq_version(void);
+/* Creates the engine on CUDA device `device`.  Fails with BWQ_ERR_NO_DEVICE when no GPU. */
+int bwq_create(int device, bwq_ctx** out);
+int bwq_destroy(bwq_ctx* ctx);
+const char* bwq_last_error(const bwq_ctx* ctx); /* ctx may be NULL: last create() error */
+int bwq_set_options(bwq_ctx* ctx, const bwq_options* opt);
+/* Installs (copies) the noise table; NULL or n_entries == 0 => noise-free. */
+int bwq_set_noise_table(bwq_ctx* ctx, const bwq_noise_table* table);
+
+/* Noisy values: density-matrix evolution of every circuit under the installed noise table
+ * (Aer Estimator, method=density_matrix, approximation=True, shots=None).
+ * out_vals[n_observables] (order of term_offsets), out_status[n_circuits]. */
+int bwq_dm_run(bwq_ctx* ctx, const bwq_batch* batch, double* out_vals, int32_t* out_status);
+/* Ideal values: statevector evolution, noise table ignored (qiskit.primitives.Estimator,
+ * shots=None; docs/tutorials/h13_ising_data_gen_tomo.ipynb:811). */
+int bwq_sv_run(bwq_ctx* ctx, const bwq_batch* batch, double* out_vals, int32_t* out_status);
+/* Same as bwq_dm_run / bwq_sv_run but out_vals is a DEVICE pointer (e.g. a torch tensor's
+ * data_ptr()) -- zero-copy label hand-off; returns after the work is enqueued and synchronised. */
+int bwq_dm_run_device_out(bwq_ctx* ctx, const bwq_batch* batch, double* d_out_vals, int32_t* out_status);
+int bwq_get_stats(const bwq_ctx* ctx, bwq_stats* out);
+int bwq_sync(bwq_ctx* ctx);
+
+/* ---- host-only introspection of the lowering stage (no GPU needed; used by CPU tests) ---- */
+typedef struct bwq_program bwq_program;
+/* Lowers batch circuit `circuit` to its sweep program.  tile_qubits/low_qubits as in options. */
+int bwq_lower_dm(const bwq_noise_table* table, const bwq_batch* batch, int32_t circuit,
+                 int32_t tile_qubits, int32_t low_qubits, bwq_program** out);
+void bwq_program_free(bwq_program* p);
+/* Sizes: [0]=n_active, [1]=n_sweeps, [2]=n_passes, [3]=n_ops, [4]=n_mats (doubles), [5]=status,
+ * [6]=n_terms, [7]=n_gates */
+int bwq_program_sizes(const bwq_program* p, int64_t sizes[8]);
+/* Copies the program out.  active_qubits[n_active] (physical qubit of digit d);
+ * sweeps: per sweep 10 int32 {pass_begin, pos[0..7], pass_end}; passes: per pass 3 int32
+ * {slot_a, slot_b, op_end}; ops: per op 2 int64 {kind | (table_flag << 8), data_off};
+ * mats[n_mats]; term_index[n_terms] (element index, -1 = term vanishes); term_coeff. */
+int bwq_program_read(const bwq_program* p, int32_t* active_qubits, int32_t* sweeps,
+                     int32_t* passes, int64_t* ops, double* mats, int64_t* term_index,
+                     double* term_coeff);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* BWQ_H_ */

@@ -1,0 +1,34 @@
+"""Builds ml_qem_b200/lib/libbwq.so in-tree with nvcc for sm_100a (python -m ml_qem_b200.build)."""
+import os
+import shutil
+import subprocess
+import sys
+
+HERE = os.path.dirname(os.path.abspath(__file__))
+SRC = [os.path.join(HERE, "csrc", f) for f in ("api.cu", "lowering.cpp")]
+HDR = [os.path.join(HERE, "csrc", f) for f in ("kernels.cuh", "program.h")] + [os.path.join(HERE, "..", "include", "bwq.h")]
+OUT = os.path.join(HERE, "lib", "libbwq.so")
+
+
+def nvcc_path():
+    for cand in (shutil.which("nvcc"), "/usr/local/cuda/bin/nvcc"):
+        if cand and os.path.exists(cand):
+            return cand
+    raise RuntimeError("nvcc not found")
+
+
+def build_library(force=False, verbose=False):
+    os.makedirs(os.path.dirname(OUT), exist_ok=True)
+    if not force and os.path.exists(OUT) and all(os.path.getmtime(OUT) >= os.path.getmtime(f) for f in SRC + HDR):
+        return OUT
+    cmd = [nvcc_path(), "-O3", "-std=c++17", "-gencode", "arch=compute_100a,code=sm_100a", "-lineinfo",
+           "-Xcompiler", "-fPIC", "-shared", "-o", OUT] + SRC
+    if verbose:
+        cmd.insert(1, "-Xptxas=-v")
+        print(" ".join(cmd))
+    subprocess.run(cmd, check=True)
+    return OUT
+
+
+if __name__ == "__main__":
+    print(build_library(force="--force" in sys.argv, verbose="-v" in sys.argv))

@@ -1,0 +1,532 @@
+// K0 -- circuit lowering stage (host C++).
+//
+// Turns the flat gate stream of one circuit (bwq_batch) plus the per-backend noise table into a
+// "sweep program" for the density-matrix kernels:
+//   gate + attached error -> real Pauli-transfer matrices (error applied AFTER its gate, the
+//   density_matrix-method semantics of Aer reached from blackwater/data/utils.py:427-429),
+//   consecutive 1-qubit maps on a qubit are multiplied into one 4x4 and absorbed into the
+//   neighbouring 2-qubit register pass, qubits no instruction touches are truncated (Aer does
+//   the same), and passes are packed greedily into shared-memory tile sweeps so one HBM
+//   read+write of the state serves as many gates as the tile's qubit set allows.
+#include <algorithm>
+#include <cmath>
+#include <complex>
+#include <cstdio>
+#include <cstring>
+
+#include "program.h"
+
+namespace bwq {
+
+using cd = std::complex<double>;
+static const cd I_(0.0, 1.0);
+
+// ----------------------------------------------------------------------------- noise table
+int NoiseTable::set(const bwq_noise_table* t, char* err, size_t errlen) {
+  data.clear();
+  entries.clear();
+  if (!t || t->n_entries == 0) return BWQ_OK;
+  if (t->n_entries < 0 || !t->opcode || !t->q0 || !t->q1 || !t->kind || !t->data_off || !t->data) {
+    snprintf(err, errlen, "noise table: null array");
+    return BWQ_ERR_ARG;
+  }
+  // entries are re-packed 4-double aligned so the kernels may use 16-byte loads
+  for (int i = 0; i < t->n_entries; ++i) {
+    int need = t->kind[i] == BWQ_NOISE_DENSE1 ? 16 : t->kind[i] == BWQ_NOISE_DENSE2 ? 256
+             : t->kind[i] == BWQ_NOISE_RELAX2 ? 25 : -1;
+    if (need < 0 || t->data_off[i] < 0 || t->data_off[i] + need > t->n_data) {
+      snprintf(err, errlen, "noise table: entry %d has bad kind/offset", i);
+      return BWQ_ERR_ARG;
+    }
+    bool two = gate_is_2q(t->opcode[i]);
+    if (two != (t->kind[i] != BWQ_NOISE_DENSE1)) {
+      snprintf(err, errlen, "noise table: entry %d kind does not match gate arity", i);
+      return BWQ_ERR_ARG;
+    }
+    uint32_t key = (uint32_t(t->opcode[i]) << 16) | (uint32_t(t->q0[i]) << 8) | t->q1[i];
+    while (data.size() % 4) data.push_back(0.0);
+    entries.push_back({key, NoiseEntry{t->kind[i], (int64_t)data.size()}});
+    data.insert(data.end(), t->data + t->data_off[i], t->data + t->data_off[i] + need);
+  }
+  std::sort(entries.begin(), entries.end(),
+            [](const auto& a, const auto& b) { return a.first < b.first; });
+  return BWQ_OK;
+}
+
+const NoiseEntry* NoiseTable::find(uint16_t opcode, int q0, int q1) const {
+  if (entries.empty()) return nullptr;
+  auto look = [&](uint32_t key) -> const NoiseEntry* {
+    auto it = std::lower_bound(entries.begin(), entries.end(), key,
+                               [](const auto& a, uint32_t k) { return a.first < k; });
+    return (it != entries.end() && it->first == key) ? &it->second : nullptr;
+  };
+  // a local error for the exact ordered qubit tuple overrides the all-qubit default (Aer)
+  if (const NoiseEntry* e = look((uint32_t(opcode) << 16) | (uint32_t(q0) << 8) | uint32_t(q1 & 255)))
+    return e;
+  return look((uint32_t(opcode) << 16) | (255u << 8) | 255u);
+}
+
+// ----------------------------------------------------------------------------- gate library
+bool gate_is_2q(uint16_t op) { return (op >= BWQ_G_CX && op <= BWQ_G_ECR) || op == BWQ_G_UNITARY2; }
+
+int gate_num_params(uint16_t op) {
+  switch (op) {
+    case BWQ_G_RX: case BWQ_G_RY: case BWQ_G_RZ: case BWQ_G_P:
+    case BWQ_G_CRX: case BWQ_G_CRY: case BWQ_G_CRZ: case BWQ_G_CP:
+    case BWQ_G_RZZ: case BWQ_G_RXX: case BWQ_G_RYY: case BWQ_G_RZX: return 1;
+    case BWQ_G_U2: return 2;
+    case BWQ_G_U3: case BWQ_G_CU3: return 3;
+    case BWQ_G_UNITARY1: return 8;
+    case BWQ_G_UNITARY2: return 32;
+    default: return 0;
+  }
+}
+
+static void u3_mat(double th, double ph, double la, cd* m) {
+  double c = std::cos(th / 2), s = std::sin(th / 2);
+  m[0] = c;
+  m[1] = -std::exp(I_ * la) * s;
+  m[2] = std::exp(I_ * ph) * s;
+  m[3] = std::exp(I_ * (ph + la)) * c;
+}
+
+static bool unitary1(uint16_t op, const double* p, cd* m) {
+  const double r = std::sqrt(0.5);
+  switch (op) {
+    case BWQ_G_ID: m[0] = 1; m[1] = 0; m[2] = 0; m[3] = 1; return true;
+    case BWQ_G_X: m[0] = 0; m[1] = 1; m[2] = 1; m[3] = 0; return true;
+    case BWQ_G_Y: m[0] = 0; m[1] = -I_; m[2] = I_; m[3] = 0; return true;
+    case BWQ_G_Z: m[0] = 1; m[1] = 0; m[2] = 0; m[3] = -1; return true;
+    case BWQ_G_H: m[0] = r; m[1] = r; m[2] = r; m[3] = -r; return true;
+    case BWQ_G_S: m[0] = 1; m[1] = 0; m[2] = 0; m[3] = I_; return true;
+    case BWQ_G_SDG: m[0] = 1; m[1] = 0; m[2] = 0; m[3] = -I_; return true;
+    case BWQ_G_T: m[0] = 1; m[1] = 0; m[2] = 0; m[3] = std::exp(I_ * (M_PI / 4)); return true;
+    case BWQ_G_TDG: m[0] = 1; m[1] = 0; m[2] = 0; m[3] = std::exp(-I_ * (M_PI / 4)); return true;
+    case BWQ_G_SX: m[0] = cd(.5, .5); m[1] = cd(.5, -.5); m[2] = cd(.5, -.5); m[3] = cd(.5, .5); return true;
+    case BWQ_G_SXDG: m[0] = cd(.5, -.5); m[1] = cd(.5, .5); m[2] = cd(.5, .5); m[3] = cd(.5, -.5); return true;
+    case BWQ_G_RX: { double c = std::cos(p[0] / 2), s = std::sin(p[0] / 2);
+      m[0] = c; m[1] = -I_ * s; m[2] = -I_ * s; m[3] = c; return true; }
+    case BWQ_G_RY: { double c = std::cos(p[0] / 2), s = std::sin(p[0] / 2);
+      m[0] = c; m[1] = -s; m[2] = s; m[3] = c; return true; }
+    case BWQ_G_RZ: m[0] = std::exp(-I_ * (p[0] / 2)); m[1] = 0; m[2] = 0; m[3] = std::exp(I_ * (p[0] / 2)); return true;
+    case BWQ_G_P: m[0] = 1; m[1] = 0; m[2] = 0; m[3] = std::exp(I_ * p[0]); return true;
+    case BWQ_G_U2: u3_mat(M_PI / 2, p[0], p[1], m); return true;
+    case BWQ_G_U3: u3_mat(p[0], p[1], p[2], m); return true;
+    case BWQ_G_UNITARY1: for (int i = 0; i < 4; ++i) m[i] = cd(p[2 * i], p[2 * i + 1]); return true;
+    default: return false;
+  }
+}
+
+// local index = i_q0 + 2*i_q1; controlled gates: control = q0, target = q1
+static void controlled(const cd* u, cd* m) {
+  for (int i = 0; i < 16; ++i) m[i] = 0;
+  m[0 * 4 + 0] = 1;
+  m[2 * 4 + 2] = 1;
+  for (int tr = 0; tr < 2; ++tr)
+    for (int tc = 0; tc < 2; ++tc) m[(1 + 2 * tr) * 4 + (1 + 2 * tc)] = u[tr * 2 + tc];
+}
+
+// exp(-i th/2 * A(x)B) with A on q0, B on q1 (A, B Paulis: 1=X 2=Y 3=Z)
+static void pauli_rot2(int a, int b, double th, cd* m) {
+  static const cd P[4][4] = {{1, 0, 0, 1}, {0, 1, 1, 0}, {0, cd(0, -1), cd(0, 1), 0}, {1, 0, 0, -1}};
+  double c = std::cos(th / 2), s = std::sin(th / 2);
+  for (int r0 = 0; r0 < 2; ++r0) for (int r1 = 0; r1 < 2; ++r1)
+    for (int c0 = 0; c0 < 2; ++c0) for (int c1 = 0; c1 < 2; ++c1) {
+      cd pp = P[a][r0 * 2 + c0] * P[b][r1 * 2 + c1];
+      cd id = (r0 == c0 && r1 == c1) ? 1.0 : 0.0;
+      m[(r0 + 2 * r1) * 4 + (c0 + 2 * c1)] = c * id - I_ * s * pp;
+    }
+}
+
+static bool unitary2(uint16_t op, const double* p, cd* m) {
+  cd u[4];
+  switch (op) {
+    case BWQ_G_CX: unitary1(BWQ_G_X, p, u); controlled(u, m); return true;
+    case BWQ_G_CY: unitary1(BWQ_G_Y, p, u); controlled(u, m); return true;
+    case BWQ_G_CZ: unitary1(BWQ_G_Z, p, u); controlled(u, m); return true;
+    case BWQ_G_CH: unitary1(BWQ_G_H, p, u); controlled(u, m); return true;
+    case BWQ_G_CRX: unitary1(BWQ_G_RX, p, u); controlled(u, m); return true;
+    case BWQ_G_CRY: unitary1(BWQ_G_RY, p, u); controlled(u, m); return true;
+    case BWQ_G_CRZ: unitary1(BWQ_G_RZ, p, u); controlled(u, m); return true;
+    case BWQ_G_CP: unitary1(BWQ_G_P, p, u); controlled(u, m); return true;
+    case BWQ_G_CU3: unitary1(BWQ_G_U3, p, u); controlled(u, m); return true;
+    case BWQ_G_SWAP:
+      for (int i = 0; i < 16; ++i) m[i] = 0;
+      m[0] = 1; m[1 * 4 + 2] = 1; m[2 * 4 + 1] = 1; m[15] = 1; return true;
+    case BWQ_G_ISWAP:
+      for (int i = 0; i < 16; ++i) m[i] = 0;
+      m[0] = 1; m[1 * 4 + 2] = I_; m[2 * 4 + 1] = I_; m[15] = 1; return true;
+    case BWQ_G_RZZ: pauli_rot2(3, 3, p[0], m); return true;
+    case BWQ_G_RXX: pauli_rot2(1, 1, p[0], m); return true;
+    case BWQ_G_RYY: pauli_rot2(2, 2, p[0], m); return true;
+    case BWQ_G_RZX: pauli_rot2(3, 1, p[0], m); return true;  // Z on q0, X on q1 (qiskit RZXGate)
+    case BWQ_G_ECR: {
+      const double r = std::sqrt(0.5);
+      const cd e[16] = {0, 1, 0, I_, 1, 0, -I_, 0, 0, I_, 0, 1, -I_, 0, 1, 0};
+      for (int i = 0; i < 16; ++i) m[i] = r * e[i];
+      return true; }
+    case BWQ_G_UNITARY2: for (int i = 0; i < 16; ++i) m[i] = cd(p[2 * i], p[2 * i + 1]); return true;
+    default: return false;
+  }
+}
+
+bool gate_unitary(uint16_t op, const double* p, double* out) {
+  cd m[16];
+  if (gate_is_2q(op)) {
+    if (!unitary2(op, p, m)) return false;
+    for (int i = 0; i < 16; ++i) { out[2 * i] = m[i].real(); out[2 * i + 1] = m[i].imag(); }
+    return true;
+  }
+  if (!unitary1(op, p, m)) return false;
+  for (int i = 0; i < 4; ++i) { out[2 * i] = m[i].real(); out[2 * i + 1] = m[i].imag(); }
+  return true;
+}
+
+static const cd kPauli[4][4] = {{1, 0, 0, 1}, {0, 1, 1, 0}, {0, cd(0, -1), cd(0, 1), 0}, {1, 0, 0, -1}};
+
+// R[i][j] = 1/2 Tr(P_i U P_j U^dag)
+void ptm_from_unitary1(const double* uu, double* r) {
+  cd u[4];
+  for (int i = 0; i < 4; ++i) u[i] = cd(uu[2 * i], uu[2 * i + 1]);
+  for (int j = 0; j < 4; ++j) {
+    cd t[4], e[4];  // t = U P_j, e = t U^dag
+    for (int a = 0; a < 2; ++a) for (int b = 0; b < 2; ++b)
+      t[a * 2 + b] = u[a * 2 + 0] * kPauli[j][0 * 2 + b] + u[a * 2 + 1] * kPauli[j][1 * 2 + b];
+    for (int a = 0; a < 2; ++a) for (int b = 0; b < 2; ++b)
+      e[a * 2 + b] = t[a * 2 + 0] * std::conj(u[b * 2 + 0]) + t[a * 2 + 1] * std::conj(u[b * 2 + 1]);
+    for (int i = 0; i < 4; ++i) {
+      cd tr = 0;
+      for (int a = 0; a < 2; ++a) for (int b = 0; b < 2; ++b) tr += kPauli[i][a * 2 + b] * e[b * 2 + a];
+      r[i * 4 + j] = 0.5 * tr.real();
+    }
+  }
+}
+
+// 16x16: index = digit_q0 + 4*digit_q1, basis index = b_q0 + 2*b_q1
+void ptm_from_unitary2(const double* uu, double* r) {
+  cd u[16], P[16][16];
+  for (int i = 0; i < 16; ++i) u[i] = cd(uu[2 * i], uu[2 * i + 1]);
+  for (int d0 = 0; d0 < 4; ++d0) for (int d1 = 0; d1 < 4; ++d1)
+    for (int r0 = 0; r0 < 2; ++r0) for (int r1 = 0; r1 < 2; ++r1)
+      for (int c0 = 0; c0 < 2; ++c0) for (int c1 = 0; c1 < 2; ++c1)
+        P[d0 + 4 * d1][(r0 + 2 * r1) * 4 + (c0 + 2 * c1)] = kPauli[d0][r0 * 2 + c0] * kPauli[d1][r1 * 2 + c1];
+  for (int j = 0; j < 16; ++j) {
+    cd t[16], e[16];
+    for (int a = 0; a < 4; ++a) for (int b = 0; b < 4; ++b) {
+      cd s = 0;
+      for (int k = 0; k < 4; ++k) s += u[a * 4 + k] * P[j][k * 4 + b];
+      t[a * 4 + b] = s;
+    }
+    for (int a = 0; a < 4; ++a) for (int b = 0; b < 4; ++b) {
+      cd s = 0;
+      for (int k = 0; k < 4; ++k) s += t[a * 4 + k] * std::conj(u[b * 4 + k]);
+      e[a * 4 + b] = s;
+    }
+    for (int i = 0; i < 16; ++i) {
+      cd tr = 0;
+      for (int a = 0; a < 4; ++a) for (int b = 0; b < 4; ++b) tr += P[i][a * 4 + b] * e[b * 4 + a];
+      r[i * 16 + j] = 0.25 * tr.real();
+    }
+  }
+}
+
+// ----------------------------------------------------------------------------- 4x4 helpers
+static void mat4_identity(double* m) { for (int i = 0; i < 16; ++i) m[i] = (i % 5 == 0) ? 1.0 : 0.0; }
+static void mat4_mul(const double* a, const double* b, double* out) {  // out = a*b (out may alias b)
+  double t[16];
+  for (int i = 0; i < 4; ++i) for (int j = 0; j < 4; ++j) {
+    double s = 0;
+    for (int k = 0; k < 4; ++k) s += a[i * 4 + k] * b[k * 4 + j];
+    t[i * 4 + j] = s;
+  }
+  std::memcpy(out, t, sizeof t);
+}
+
+// PTM of a 1-qubit gate; closed forms for the backend basis (checked against the generic path
+// by tests/test_lowering.py).
+static bool gate_ptm1(uint16_t op, const double* p, double* r) {
+  switch (op) {
+    case BWQ_G_ID: mat4_identity(r); return true;
+    case BWQ_G_X: mat4_identity(r); r[10] = -1; r[15] = -1; return true;
+    case BWQ_G_Z: mat4_identity(r); r[5] = -1; r[10] = -1; return true;
+    case BWQ_G_RZ: case BWQ_G_P: {
+      double c = std::cos(p[0]), s = std::sin(p[0]);
+      mat4_identity(r); r[5] = c; r[6] = -s; r[9] = s; r[10] = c; return true; }
+    case BWQ_G_SX:  // rx(pi/2): Y -> Z, Z -> -Y
+      for (int i = 0; i < 16; ++i) r[i] = 0;
+      r[0] = 1; r[5] = 1; r[2 * 4 + 3] = -1; r[3 * 4 + 2] = 1; return true;
+    case BWQ_G_RESET:  // rho -> Tr(rho)|0><0|
+      for (int i = 0; i < 16; ++i) r[i] = 0;
+      r[0] = 1; r[3 * 4 + 0] = 1; return true;
+    default: {
+      double u[8];
+      if (!gate_unitary(op, p, u)) return false;
+      ptm_from_unitary1(u, r);
+      return true; }
+  }
+}
+
+// ----------------------------------------------------------------------------- DM lowering
+namespace {
+struct HostPass {
+  int qa, qb;
+  std::vector<DevOp> ops;
+};
+}  // namespace
+
+static int64_t push_mat(std::vector<double>& mats, const double* m, int n) {
+  int64_t off = (int64_t)mats.size();
+  mats.insert(mats.end(), m, m + n);
+  return off;
+}
+
+static void lower_terms(const bwq_batch& b, int c, const std::vector<int>& digit_of, int nq,
+                        CircuitProgram* out) {
+  int64_t o0 = b.obs_offsets[c], o1 = b.obs_offsets[c + 1];
+  int64_t t0 = b.term_offsets[o0], t1 = b.term_offsets[o1];
+  out->term_index.resize(t1 - t0);
+  out->term_coeff.resize(t1 - t0);
+  uint64_t valid = nq >= 64 ? ~0ull : ((1ull << nq) - 1);
+  for (int64_t t = t0; t < t1; ++t) {
+    uint64_t x = b.term_x[t], z = b.term_z[t];
+    int64_t idx = 0;
+    if ((x | z) & ~valid) { out->status = BWQ_CIRC_BAD_QUBIT; idx = -1; }
+    for (int q = 0; q < nq && idx >= 0; ++q) {
+      int xb = (x >> q) & 1, zb = (z >> q) & 1;
+      if (!xb && !zb) continue;
+      if (digit_of[q] < 0) {           // idle qubit stays |0>: <Z>=1, <X>=<Y>=0
+        if (xb) idx = -1;
+        continue;
+      }
+      int digit = xb ? (zb ? 2 : 1) : 3;
+      idx += (int64_t)digit << (2 * digit_of[q]);
+    }
+    out->term_index[t - t0] = idx;
+    out->term_coeff[t - t0] = b.term_coeff[t];
+  }
+}
+
+void lower_dm_circuit(const NoiseTable& noise, const bwq_batch& b, int c, const LowerOptions& opt,
+                      CircuitProgram* out) {
+  *out = CircuitProgram();
+  const int nq = b.n_qubits[c];
+  const int64_t g0 = b.op_offsets[c], g1 = b.op_offsets[c + 1];
+  out->n_gates = g1 - g0;
+  if (nq < 0 || nq > 64) { out->status = BWQ_CIRC_BAD_QUBIT; return; }
+
+  // active qubits -> digits (ascending physical order)
+  std::vector<int> digit_of(nq, -1);
+  {
+    std::vector<char> used(nq, 0);
+    for (int64_t g = g0; g < g1; ++g) {
+      const bwq_op& op = b.ops[g];
+      bool two = gate_is_2q(op.opcode);
+      if (op.q0 >= nq || (two && (op.q1 >= nq || op.q1 == op.q0))) { out->status = BWQ_CIRC_BAD_QUBIT; return; }
+      used[op.q0] = 1;
+      if (two) used[op.q1] = 1;
+    }
+    for (int q = 0; q < nq; ++q) if (used[q]) { digit_of[q] = (int)out->active.size(); out->active.push_back(q); }
+  }
+  while (out->active.size() < 2) out->active.push_back(-1);  // pad: idle digits stay I/Z = 1
+  const int nd = out->n_digits = (int)out->active.size();
+  if (nd > kMaxDmQubits) { out->status = BWQ_CIRC_TOO_WIDE; return; }
+  lower_terms(b, c, digit_of, nq, out);
+  if (out->status) return;
+
+  // ---- gates -> passes
+  std::vector<HostPass> passes;
+  std::vector<double> pend(16 * nd);
+  std::vector<char> has(nd, 0);
+  std::vector<int> last(nd, -1);
+  auto flush = [&](int d, HostPass& p) {
+    if (!has[d]) return;
+    p.ops.push_back(DevOp{d == p.qa ? K_DENSE1_A : K_DENSE1_B, 0, push_mat(out->mats, &pend[16 * d], 16)});
+    has[d] = 0;
+  };
+  for (int64_t g = g0; g < g1; ++g) {
+    const bwq_op& op = b.ops[g];
+    const int npar = gate_num_params(op.opcode);
+    if (npar && (int64_t)op.param_idx + npar > b.n_params) { out->status = BWQ_CIRC_BAD_OP; return; }
+    const double* par = npar ? b.params + op.param_idx : nullptr;
+    if (!gate_is_2q(op.opcode)) {
+      double r[16];
+      if (!gate_ptm1(op.opcode, par, r)) { out->status = BWQ_CIRC_BAD_OP; return; }
+      int d = digit_of[op.q0];
+      if (const NoiseEntry* ne = noise.find(op.opcode, op.q0, 255)) mat4_mul(&noise.data[ne->off], r, r);
+      if (has[d]) mat4_mul(r, &pend[16 * d], &pend[16 * d]);
+      else { std::memcpy(&pend[16 * d], r, sizeof r); has[d] = 1; }
+      continue;
+    }
+    int d0 = digit_of[op.q0], d1 = digit_of[op.q1];
+    int pi;
+    if (last[d0] >= 0 && last[d0] == last[d1]) pi = last[d0];
+    else {
+      pi = (int)passes.size();
+      passes.push_back(HostPass{d0, d1, {}});
+      last[d0] = last[d1] = pi;
+    }
+    HostPass& p = passes[pi];
+    flush(d0, p);
+    flush(d1, p);
+    const bool same = (d0 == p.qa);
+    if (op.opcode == BWQ_G_CX) p.ops.push_back(DevOp{same ? K_CX_AB : K_CX_BA, 0, 0});
+    else {
+      double u[32], r[256];
+      if (!gate_unitary(op.opcode, par, u)) { out->status = BWQ_CIRC_BAD_OP; return; }
+      ptm_from_unitary2(u, r);
+      p.ops.push_back(DevOp{same ? K_DENSE2 : K_DENSE2_SW, 0, push_mat(out->mats, r, 256)});
+    }
+    if (const NoiseEntry* ne = noise.find(op.opcode, op.q0, op.q1)) {
+      int k = ne->kind == BWQ_NOISE_RELAX2 ? (same ? K_RELAX2 : K_RELAX2_SW) : (same ? K_DENSE2 : K_DENSE2_SW);
+      p.ops.push_back(DevOp{k, 1, ne->off});
+    }
+  }
+  for (int d = 0; d < nd; ++d) {
+    if (!has[d]) continue;
+    if (last[d] < 0) {  // qubit with 1-qubit gates only: give it a pass with any partner
+      int partner = d == 0 ? 1 : 0;
+      passes.push_back(HostPass{d, partner, {}});
+      last[d] = (int)passes.size() - 1;
+    }
+    flush(d, passes[last[d]]);
+  }
+
+  // ---- passes -> sweeps (greedy in program order; a pass that does not fit blocks its qubits)
+  const int kq = std::min(std::max(opt.tile_qubits, 2), std::min(nd, kMaxTileQubits));
+  const int mlow = std::min(std::max(opt.low_qubits, 0), kq);
+  const int np = (int)passes.size();
+  std::vector<char> done(np, 0);
+  int first = 0, remaining = np;
+  std::vector<char> in_tile(nd), blocked(nd);
+  while (remaining > 0) {
+    std::fill(in_tile.begin(), in_tile.end(), 0);
+    std::fill(blocked.begin(), blocked.end(), 0);
+    int nt = 0, nblocked = 0;
+    for (int d = 0; d < mlow; ++d) { in_tile[d] = 1; ++nt; }
+    SweepDesc sw{};
+    sw.pass_begin = (int)out->passes.size();
+    while (first < np && done[first]) ++first;
+    for (int i = first; i < np && nblocked < nd; ++i) {
+      if (done[i]) continue;
+      const HostPass& p = passes[i];
+      auto block = [&](int d) { if (!blocked[d]) { blocked[d] = 1; ++nblocked; } };
+      if (blocked[p.qa] || blocked[p.qb]) { block(p.qa); block(p.qb); continue; }
+      int need = (!in_tile[p.qa]) + (!in_tile[p.qb]);
+      if (nt + need > kq) { block(p.qa); block(p.qb); continue; }
+      if (!in_tile[p.qa]) { in_tile[p.qa] = 1; ++nt; }
+      if (!in_tile[p.qb]) { in_tile[p.qb] = 1; ++nt; }
+      done[i] = 1;
+      --remaining;
+      PassDesc pd{};
+      pd.op_begin = (int)out->ops.size();
+      out->ops.insert(out->ops.end(), p.ops.begin(), p.ops.end());
+      pd.op_end = (int)out->ops.size();
+      pd.sa = (uint8_t)p.qa;  // digit for now; converted to slot below
+      pd.sb = (uint8_t)p.qb;
+      out->passes.push_back(pd);
+    }
+    for (int d = 0; d < nd && nt < kq; ++d) if (!in_tile[d]) { in_tile[d] = 1; ++nt; }
+    int slot_of[kMaxDmQubits];
+    int s = 0;
+    for (int d = 0; d < nd; ++d) if (in_tile[d]) { sw.pos[s] = (uint8_t)d; slot_of[d] = s++; }
+    sw.pass_end = (int)out->passes.size();
+    for (int i = sw.pass_begin; i < sw.pass_end; ++i) {
+      out->passes[i].sa = (uint8_t)slot_of[out->passes[i].sa];
+      out->passes[i].sb = (uint8_t)slot_of[out->passes[i].sb];
+    }
+    out->sweeps.push_back(sw);
+  }
+}
+
+// ----------------------------------------------------------------------------- SV lowering
+static void mat2c_mul(const cd* a, const cd* b, cd* out) {
+  cd t[4];
+  for (int i = 0; i < 2; ++i) for (int j = 0; j < 2; ++j) t[i * 2 + j] = a[i * 2] * b[j] + a[i * 2 + 1] * b[2 + j];
+  for (int i = 0; i < 4; ++i) out[i] = t[i];
+}
+
+void lower_sv_circuit(const bwq_batch& b, int c, SvProgram* out) {
+  *out = SvProgram();
+  const int nq = b.n_qubits[c];
+  const int64_t g0 = b.op_offsets[c], g1 = b.op_offsets[c + 1];
+  out->n_gates = g1 - g0;
+  if (nq < 0 || nq > 64) { out->status = BWQ_CIRC_BAD_QUBIT; return; }
+  std::vector<int> bit_of(nq, -1);
+  {
+    std::vector<char> used(nq, 0);
+    for (int64_t g = g0; g < g1; ++g) {
+      const bwq_op& op = b.ops[g];
+      bool two = gate_is_2q(op.opcode);
+      if (op.q0 >= nq || (two && (op.q1 >= nq || op.q1 == op.q0))) { out->status = BWQ_CIRC_BAD_QUBIT; return; }
+      if (op.opcode == BWQ_G_RESET) { out->status = BWQ_CIRC_BAD_OP; return; }
+      used[op.q0] = 1;
+      if (two) used[op.q1] = 1;
+    }
+    for (int q = 0; q < nq; ++q) if (used[q]) { bit_of[q] = (int)out->active.size(); out->active.push_back(q); }
+  }
+  if (out->active.empty()) out->active.push_back(-1);
+  const int nb = out->n_bits = (int)out->active.size();
+  if (nb > kMaxSvQubits) { out->status = BWQ_CIRC_TOO_WIDE; return; }
+
+  // terms
+  {
+    int64_t o0 = b.obs_offsets[c], o1 = b.obs_offsets[c + 1];
+    int64_t t0 = b.term_offsets[o0], t1 = b.term_offsets[o1];
+    uint64_t valid = nq >= 64 ? ~0ull : ((1ull << nq) - 1);
+    for (int64_t t = t0; t < t1; ++t) {
+      uint64_t x = b.term_x[t], z = b.term_z[t];
+      if ((x | z) & ~valid) { out->status = BWQ_CIRC_BAD_QUBIT; return; }
+      uint32_t cx = 0, cz = 0;
+      int ny = 0;
+      double coeff = b.term_coeff[t];
+      for (int q = 0; q < nq; ++q) {
+        int xb = (x >> q) & 1, zb = (z >> q) & 1;
+        if (!xb && !zb) continue;
+        if (bit_of[q] < 0) { if (xb) coeff = 0.0; continue; }
+        if (xb) cx |= 1u << bit_of[q];
+        if (zb) cz |= 1u << bit_of[q];
+        if (xb && zb) ++ny;
+      }
+      out->term_x.push_back(cx); out->term_z.push_back(cz); out->term_ny.push_back(ny);
+      out->term_coeff.push_back(coeff);
+    }
+  }
+
+  std::vector<cd> pend(4 * nb);
+  std::vector<char> has(nb, 0);
+  auto flush = [&](int q) {
+    if (!has[q]) return;
+    double m[8];
+    for (int i = 0; i < 4; ++i) { m[2 * i] = pend[4 * q + i].real(); m[2 * i + 1] = pend[4 * q + i].imag(); }
+    SvOp o{}; o.kind = SV_U1; o.q0 = (uint8_t)q; o.q1 = 0; o.off = push_mat(out->mats, m, 8);
+    out->ops.push_back(o);
+    has[q] = 0;
+  };
+  for (int64_t g = g0; g < g1; ++g) {
+    const bwq_op& op = b.ops[g];
+    const int npar = gate_num_params(op.opcode);
+    if (npar && (int64_t)op.param_idx + npar > b.n_params) { out->status = BWQ_CIRC_BAD_OP; return; }
+    const double* par = npar ? b.params + op.param_idx : nullptr;
+    if (!gate_is_2q(op.opcode)) {
+      cd u[4];
+      if (!unitary1(op.opcode, par, u)) { out->status = BWQ_CIRC_BAD_OP; return; }
+      int q = bit_of[op.q0];
+      if (has[q]) mat2c_mul(u, &pend[4 * q], &pend[4 * q]);
+      else { for (int i = 0; i < 4; ++i) pend[4 * q + i] = u[i]; has[q] = 1; }
+      continue;
+    }
+    int q0 = bit_of[op.q0], q1 = bit_of[op.q1];
+    flush(q0); flush(q1);
+    SvOp o{}; o.q0 = (uint8_t)q0; o.q1 = (uint8_t)q1;
+    if (op.opcode == BWQ_G_CX) { o.kind = SV_CX; o.off = 0; }
+    else {
+      double u[32];
+      if (!gate_unitary(op.opcode, par, u)) { out->status = BWQ_CIRC_BAD_OP; return; }
+      o.kind = SV_U2; o.off = push_mat(out->mats, u, 32);
+    }
+    out->ops.push_back(o);
+  }
+  for (int q = 0; q < nb; ++q) flush(q);
+}
+
+}  // namespace bwq

@@ -1,0 +1,310 @@
+"""ctypes binding of the C ABI (include/bwq.h) and the flat batch encoder.
+
+This is the only place Python talks to the CUDA library.  There is no CPU fallback: if
+``libbwq.so`` is missing or no GPU is present, ``Engine()`` raises.
+"""
+import ctypes as C
+import os
+import threading
+
+import numpy as np
+
+from . import circuit as circuit_mod
+from . import observable as observable_mod
+from .gateset import NUM_PARAMS, OPCODES
+
+_LIB_PATH = os.path.join(os.path.dirname(os.path.abspath(__file__)), "lib", "libbwq.so")
+_lib = None
+
+
+class EngineError(RuntimeError):
+    pass
+
+
+class _Op(C.Structure):
+    _fields_ = [("opcode", C.c_uint16), ("q0", C.c_uint8), ("q1", C.c_uint8), ("param_idx", C.c_uint32)]
+
+
+OP_DTYPE = np.dtype([("opcode", "<u2"), ("q0", "u1"), ("q1", "u1"), ("param_idx", "<u4")])
+
+
+class _Batch(C.Structure):
+    _fields_ = [
+        ("n_circuits", C.c_int32), ("n_qubits", C.c_void_p), ("op_offsets", C.c_void_p), ("ops", C.c_void_p),
+        ("params", C.c_void_p), ("n_params", C.c_int64), ("obs_offsets", C.c_void_p),
+        ("term_offsets", C.c_void_p), ("term_x", C.c_void_p), ("term_z", C.c_void_p), ("term_coeff", C.c_void_p),
+    ]
+
+
+class _NoiseTable(C.Structure):
+    _fields_ = [
+        ("n_entries", C.c_int32), ("opcode", C.c_void_p), ("q0", C.c_void_p), ("q1", C.c_void_p),
+        ("kind", C.c_void_p), ("data_off", C.c_void_p), ("data", C.c_void_p), ("n_data", C.c_int64),
+    ]
+
+
+class _Options(C.Structure):
+    _fields_ = [("tile_qubits", C.c_int32), ("low_qubits", C.c_int32), ("max_state_bytes", C.c_int64),
+                ("chunk_circuits", C.c_int32), ("host_threads", C.c_int32)]
+
+
+class _Stats(C.Structure):
+    _fields_ = [("n_sweep_launches", C.c_int64), ("n_state_sweeps", C.c_int64), ("n_passes", C.c_int64),
+                ("n_gates", C.c_int64), ("state_bytes_swept", C.c_int64), ("n_other_launches", C.c_int64),
+                ("lower_ms", C.c_double), ("h2d_ms", C.c_double), ("kernel_ms", C.c_double), ("d2h_ms", C.c_double),
+                ("sweep_kernel_ms", C.c_double)]
+
+
+EXPORTS = [
+    "bwq_version", "bwq_create", "bwq_destroy", "bwq_last_error", "bwq_set_options", "bwq_set_noise_table",
+    "bwq_dm_run", "bwq_sv_run", "bwq_dm_run_device_out", "bwq_get_stats", "bwq_sync", "bwq_lower_dm",
+    "bwq_program_free", "bwq_program_sizes", "bwq_program_read",
+]
+
+
+def load_library(path=None):
+    """Loads libbwq.so (built in-tree by ``python -m ml_qem_b200.build``); raises if absent."""
+    global _lib
+    if _lib is not None and path is None:
+        return _lib
+    p = path or _LIB_PATH
+    if not os.path.exists(p):
+        raise EngineError(f"{p} not found: build it with `python -m ml_qem_b200.build` (needs nvcc); "
+                          "this engine has no CPU fallback")
+    lib = C.CDLL(p)
+    lib.bwq_version.restype = C.c_int
+    lib.bwq_create.argtypes = [C.c_int, C.POINTER(C.c_void_p)]
+    lib.bwq_destroy.argtypes = [C.c_void_p]
+    lib.bwq_last_error.argtypes = [C.c_void_p]
+    lib.bwq_last_error.restype = C.c_char_p
+    lib.bwq_set_options.argtypes = [C.c_void_p, C.POINTER(_Options)]
+    lib.bwq_set_noise_table.argtypes = [C.c_void_p, C.POINTER(_NoiseTable)]
+    for f in (lib.bwq_dm_run, lib.bwq_sv_run, lib.bwq_dm_run_device_out):
+        f.argtypes = [C.c_void_p, C.POINTER(_Batch), C.c_void_p, C.c_void_p]
+    lib.bwq_get_stats.argtypes = [C.c_void_p, C.POINTER(_Stats)]
+    lib.bwq_sync.argtypes = [C.c_void_p]
+    lib.bwq_lower_dm.argtypes = [C.POINTER(_NoiseTable), C.POINTER(_Batch), C.c_int32, C.c_int32, C.c_int32,
+                                 C.POINTER(C.c_void_p)]
+    lib.bwq_program_free.argtypes = [C.c_void_p]
+    lib.bwq_program_free.restype = None
+    lib.bwq_program_sizes.argtypes = [C.c_void_p, C.c_void_p]
+    lib.bwq_program_read.argtypes = [C.c_void_p] + [C.c_void_p] * 7
+    if path is None:
+        _lib = lib
+    return lib
+
+
+def _ptr(a):
+    return a.ctypes.data_as(C.c_void_p) if a is not None and a.size else None
+
+
+class FlatBatch:
+    """Flat structure-of-arrays batch (bwq_batch).  Build with ``encode_batch`` or directly from
+    numpy arrays (the synthetic families in ml_qem_b200.families do the latter)."""
+
+    def __init__(self, n_qubits, op_offsets, ops, params, obs_offsets, term_offsets, term_x, term_z, term_coeff):
+        self.n_qubits = np.ascontiguousarray(n_qubits, dtype=np.int32)
+        self.op_offsets = np.ascontiguousarray(op_offsets, dtype=np.int64)
+        self.ops = np.ascontiguousarray(ops, dtype=OP_DTYPE)
+        self.params = np.ascontiguousarray(params, dtype=np.float64)
+        self.obs_offsets = np.ascontiguousarray(obs_offsets, dtype=np.int64)
+        self.term_offsets = np.ascontiguousarray(term_offsets, dtype=np.int64)
+        self.term_x = np.ascontiguousarray(term_x, dtype=np.uint64)
+        self.term_z = np.ascontiguousarray(term_z, dtype=np.uint64)
+        self.term_coeff = np.ascontiguousarray(term_coeff, dtype=np.float64)
+        self.n_circuits = len(self.n_qubits)
+        if len(self.op_offsets) != self.n_circuits + 1 or len(self.obs_offsets) != self.n_circuits + 1:
+            raise ValueError("offset arrays must have n_circuits + 1 entries")
+        self.n_observables = int(self.obs_offsets[-1]) if self.n_circuits else 0
+        if len(self.term_offsets) != self.n_observables + 1:
+            raise ValueError("term_offsets must have n_observables + 1 entries")
+
+    def c_struct(self):
+        return _Batch(self.n_circuits, _ptr(self.n_qubits), _ptr(self.op_offsets), _ptr(self.ops), _ptr(self.params),
+                      len(self.params), _ptr(self.obs_offsets), _ptr(self.term_offsets), _ptr(self.term_x),
+                      _ptr(self.term_z), _ptr(self.term_coeff))
+
+    def nbytes(self):
+        return sum(a.nbytes for a in (self.n_qubits, self.op_offsets, self.ops, self.params, self.obs_offsets,
+                                      self.term_offsets, self.term_x, self.term_z, self.term_coeff))
+
+    def select(self, idx):
+        """Sub-batch with the circuits ``idx`` (used to shard a batch across ranks)."""
+        idx = np.asarray(idx, dtype=np.int64)
+        ops, params, tx, tz, tc = [], [], [], [], []
+        op_off, obs_off, term_off = [0], [0], [0]
+        npar = 0
+        for c in idx:
+            o = self.ops[self.op_offsets[c]:self.op_offsets[c + 1]].copy()
+            if len(o):
+                lo = int(o["param_idx"].min())
+                hi = min(len(self.params), int(o["param_idx"].max()) + 32)
+                o["param_idx"] = o["param_idx"] - lo + npar
+                params.append(self.params[lo:hi])
+                npar += hi - lo
+            ops.append(o)
+            op_off.append(op_off[-1] + len(o))
+            for ob in range(self.obs_offsets[c], self.obs_offsets[c + 1]):
+                a, b = self.term_offsets[ob], self.term_offsets[ob + 1]
+                tx.append(self.term_x[a:b]); tz.append(self.term_z[a:b]); tc.append(self.term_coeff[a:b])
+                term_off.append(term_off[-1] + (b - a))
+            obs_off.append(obs_off[-1] + (self.obs_offsets[c + 1] - self.obs_offsets[c]))
+        cat = lambda xs, dt: np.concatenate(xs).astype(dt) if xs else np.zeros(0, dtype=dt)
+        return FlatBatch(self.n_qubits[idx], op_off, cat(ops, OP_DTYPE), cat(params, np.float64), obs_off, term_off,
+                         cat(tx, np.uint64), cat(tz, np.uint64), cat(tc, np.float64))
+
+
+def encode_batch(circuits, observables):
+    """circuits[i] with its list of observables observables[i] -> FlatBatch.
+
+    ``observables[i]`` is a list of Pauli observables evaluated on the SAME simulated state (the
+    reference re-simulates the circuit once per observable, e.g. docs/tutorials/zne_parallel.py:259
+    passes ``[circ] * 4``; here one evolution serves them all)."""
+    n_qubits, op_off, obs_off, term_off = [], [0], [0], [0]
+    opc, q0s, q1s, pidx, params = [], [], [], [], []
+    tx, tz, tc = [], [], []
+    for circ, obs_list in zip(circuits, observables):
+        circ = circuit_mod.from_any(circ)
+        n_qubits.append(circ.num_qubits)
+        for name, qubits, pr in circ.gate_ops():
+            opc.append(OPCODES[name])
+            q0s.append(qubits[0])
+            q1s.append(qubits[1] if len(qubits) > 1 else 0)
+            pidx.append(len(params))
+            if NUM_PARAMS.get(name, 0):
+                params.extend(float(p) for p in pr)
+        op_off.append(len(opc))
+        for ob in obs_list:
+            ob = observable_mod.from_any(ob)
+            if ob.num_qubits != circ.num_qubits and len(ob):
+                raise ValueError(f"observable acts on {ob.num_qubits} qubits, circuit has {circ.num_qubits}")
+            x, z, c = ob.masks()
+            tx.append(x); tz.append(z); tc.append(c)
+            term_off.append(term_off[-1] + len(c))
+        obs_off.append(obs_off[-1] + len(obs_list))
+    ops = np.zeros(len(opc), dtype=OP_DTYPE)
+    ops["opcode"], ops["q0"], ops["q1"], ops["param_idx"] = opc, q0s, q1s, pidx
+    cat = lambda xs, dt: np.concatenate(xs).astype(dt) if xs else np.zeros(0, dtype=dt)
+    return FlatBatch(n_qubits, op_off, ops, np.asarray(params, dtype=np.float64), obs_off, term_off,
+                     cat(tx, np.uint64), cat(tz, np.uint64), cat(tc, np.float64))
+
+
+def _noise_struct(table):
+    if table is None or len(table["opcode"]) == 0:
+        return None, None
+    keep = {k: np.ascontiguousarray(v) for k, v in table.items()}
+    st = _NoiseTable(len(keep["opcode"]), _ptr(keep["opcode"]), _ptr(keep["q0"]), _ptr(keep["q1"]), _ptr(keep["kind"]),
+                     _ptr(keep["data_off"]), _ptr(keep["data"]), len(keep["data"]))
+    return st, keep
+
+
+STATUS_TEXT = {0: "ok", 1: "unsupported or malformed operation", 2: "too many active qubits", 3: "qubit index out of range"}
+
+
+class Engine:
+    """One engine per GPU (bwq_ctx).  Not re-entrant: calls are serialised with a lock."""
+
+    def __init__(self, device=0, **options):
+        self._lib = load_library()
+        self._ctx = C.c_void_p()
+        rc = self._lib.bwq_create(int(device), C.byref(self._ctx))
+        if rc != 0:
+            msg = self._lib.bwq_last_error(None).decode()
+            self._ctx = None
+            raise EngineError(f"bwq_create failed ({rc}): {msg}")
+        self.device = int(device)
+        self._lock = threading.Lock()
+        self._noise_id = None
+        if options:
+            self.set_options(**options)
+
+    def close(self):
+        if getattr(self, "_ctx", None):
+            self._lib.bwq_destroy(self._ctx)
+            self._ctx = None
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+    def _check(self, rc, what):
+        if rc != 0:
+            raise EngineError(f"{what} failed ({rc}): {self._lib.bwq_last_error(self._ctx).decode()}")
+
+    def set_options(self, tile_qubits=0, low_qubits=0, max_state_bytes=0, chunk_circuits=0, host_threads=0):
+        o = _Options(tile_qubits, low_qubits, max_state_bytes, chunk_circuits, host_threads)
+        self._check(self._lib.bwq_set_options(self._ctx, C.byref(o)), "bwq_set_options")
+
+    def set_noise(self, model):
+        """model: ml_qem_b200.noise.NoiseModel or None (noise-free)."""
+        key = id(model) if model is not None else None
+        with self._lock:
+            st, keep = _noise_struct(model.to_table() if model is not None else None)
+            self._check(self._lib.bwq_set_noise_table(self._ctx, C.byref(st) if st is not None else None),
+                        "bwq_set_noise_table")
+            self._noise_id = key
+
+    def _run(self, fn, batch, what):
+        vals = np.empty(batch.n_observables, dtype=np.float64)
+        status = np.zeros(batch.n_circuits, dtype=np.int32)
+        st = batch.c_struct()
+        with self._lock:
+            self._check(fn(self._ctx, C.byref(st), vals.ctypes.data_as(C.c_void_p), status.ctypes.data_as(C.c_void_p)), what)
+        return vals, status
+
+    def run_dm(self, batch):
+        """Noisy values (density matrix under the installed noise table) -> (values, status)."""
+        return self._run(self._lib.bwq_dm_run, batch, "bwq_dm_run")
+
+    def run_sv(self, batch):
+        """Ideal values (statevector) -> (values, status)."""
+        return self._run(self._lib.bwq_sv_run, batch, "bwq_sv_run")
+
+    def run_dm_into(self, batch, device_ptr):
+        """Writes the values into device memory at ``device_ptr`` (e.g. torch ``tensor.data_ptr()``
+        of a float64 CUDA tensor with n_observables elements) -- zero-copy label hand-off."""
+        status = np.zeros(batch.n_circuits, dtype=np.int32)
+        st = batch.c_struct()
+        with self._lock:
+            self._check(self._lib.bwq_dm_run_device_out(self._ctx, C.byref(st), C.c_void_p(int(device_ptr)),
+                                                        status.ctypes.data_as(C.c_void_p)), "bwq_dm_run_device_out")
+        return status
+
+    def stats(self):
+        s = _Stats()
+        self._check(self._lib.bwq_get_stats(self._ctx, C.byref(s)), "bwq_get_stats")
+        return {f: getattr(s, f) for f, _ in _Stats._fields_}
+
+    def sync(self):
+        self._check(self._lib.bwq_sync(self._ctx), "bwq_sync")
+
+
+def lower_dm(batch, circuit, noise_model=None, tile_qubits=0, low_qubits=0):
+    """Host-only view of the lowering stage (no GPU): returns the sweep program of one circuit as a
+    dict of numpy arrays (see bwq_program_read in include/bwq.h)."""
+    lib = load_library()
+    st, keep = _noise_struct(noise_model.to_table() if noise_model is not None else None)
+    prog = C.c_void_p()
+    bs = batch.c_struct()
+    rc = lib.bwq_lower_dm(C.byref(st) if st is not None else None, C.byref(bs), circuit, tile_qubits, low_qubits,
+                          C.byref(prog))
+    if rc != 0:
+        raise EngineError(f"bwq_lower_dm failed ({rc}): {lib.bwq_last_error(None).decode()}")
+    try:
+        sizes = np.zeros(8, dtype=np.int64)
+        lib.bwq_program_sizes(prog, sizes.ctypes.data_as(C.c_void_p))
+        nd, nsw, nps, nops, nm, status, nt, ng = (int(x) for x in sizes)
+        out = {
+            "n_digits": nd, "status": status, "n_gates": ng,
+            "active": np.zeros(nd, dtype=np.int32), "sweeps": np.zeros((nsw, 10), dtype=np.int32),
+            "passes": np.zeros((nps, 3), dtype=np.int32), "ops": np.zeros((nops, 2), dtype=np.int64),
+            "mats": np.zeros(nm, dtype=np.float64), "term_index": np.zeros(nt, dtype=np.int64),
+            "term_coeff": np.zeros(nt, dtype=np.float64),
+        }
+        lib.bwq_program_read(prog, *[out[k].ctypes.data_as(C.c_void_p) for k in
+                                     ("active", "sweeps", "passes", "ops", "mats", "term_index", "term_coeff")])
+        return out
+    finally:
+        lib.bwq_program_free(prog)
