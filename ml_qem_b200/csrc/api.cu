@@ -137,8 +137,10 @@ extern "C" int bwq_create(int device, bwq_ctx** out) {
   if ((e = cudaGetDeviceProperties(&prop, device)) != cudaSuccess) return bail(e, "cudaGetDeviceProperties");
   ctx->smem_optin = prop.sharedMemPerBlockOptin;
   ctx->sm_count = prop.multiProcessorCount;
-  if ((e = cudaFuncSetAttribute(dm_sweep_kernel<7>, cudaFuncAttributeMaxDynamicSharedMemorySize, 8 << 14)) != cudaSuccess)
+  if ((e = cudaFuncSetAttribute(dm_sweep_kernel<7, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, 8 << 14)) != cudaSuccess)
     return bail(e, "cudaFuncSetAttribute(dm_sweep_kernel<7>) -- was the library built for this GPU (sm_100a)?");
+  if ((e = cudaFuncSetAttribute(dm_sweep_kernel<7, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, 8 << 14)) != cudaSuccess)
+    return bail(e, "cudaFuncSetAttribute(dm_sweep_kernel<7, full>)");
   if ((e = cudaFuncSetAttribute(sv_circuit_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 16 << 12)) != cudaSuccess)
     return bail(e, "cudaFuncSetAttribute(sv_circuit_kernel)");
   *out = ctx;
@@ -230,19 +232,19 @@ static int host_threads(const bwq_ctx* ctx) {
   return hc ? (int)std::min(hc, 32u) : 4;
 }
 
-template <int KQ> static cudaError_t launch_sweep(const DmLaunch& L, int sweep, int64_t n_cta, cudaStream_t s) {
-  dm_sweep_kernel<KQ><<<(unsigned)n_cta, SweepCfg<KQ>::kThreads, sizeof(double) << (2 * KQ), s>>>(L, sweep);
+template <int KQ, bool FULL> static cudaError_t launch_sweep(const DmLaunch& L, int sweep, int64_t n_cta, cudaStream_t s) {
+  dm_sweep_kernel<KQ, FULL><<<(unsigned)n_cta, SweepCfg<KQ>::kThreads, sizeof(double) << (2 * KQ), s>>>(L, sweep);
   return cudaGetLastError();
 }
 
-static cudaError_t launch_sweep_kq(int kq, const DmLaunch& L, int sweep, int64_t n_cta, cudaStream_t s) {
+template <bool FULL> static cudaError_t launch_sweep_kq(int kq, const DmLaunch& L, int sweep, int64_t n_cta, cudaStream_t s) {
   switch (kq) {
-    case 2: return launch_sweep<2>(L, sweep, n_cta, s);
-    case 3: return launch_sweep<3>(L, sweep, n_cta, s);
-    case 4: return launch_sweep<4>(L, sweep, n_cta, s);
-    case 5: return launch_sweep<5>(L, sweep, n_cta, s);
-    case 6: return launch_sweep<6>(L, sweep, n_cta, s);
-    case 7: return launch_sweep<7>(L, sweep, n_cta, s);
+    case 2: return launch_sweep<2, FULL>(L, sweep, n_cta, s);
+    case 3: return launch_sweep<3, FULL>(L, sweep, n_cta, s);
+    case 4: return launch_sweep<4, FULL>(L, sweep, n_cta, s);
+    case 5: return launch_sweep<5, FULL>(L, sweep, n_cta, s);
+    case 6: return launch_sweep<6, FULL>(L, sweep, n_cta, s);
+    case 7: return launch_sweep<7, FULL>(L, sweep, n_cta, s);
     default: return cudaErrorInvalidValue;
   }
 }
@@ -423,10 +425,12 @@ static int dm_run_impl(bwq_ctx* ctx, const bwq_batch* b, double* out_vals, bool 
     // circuits are sorted by sweep count (descending) inside a width group, so sweep s only needs
     // the leading circuits that still have an s-th sweep
     size_t max_sweeps = progs[order[ch.first]].sweeps.size();
+    bool full = false;
+    for (int i = ch.first; i < ch.first + ch.count; ++i) full = full || progs[order[i]].needs_dense;
     int live = ch.count;
     for (size_t s = 0; s < max_sweeps; ++s) {
       while (live > 0 && progs[order[ch.first + live - 1]].sweeps.size() <= s) --live;
-      CK(launch_sweep_kq(kq, L, (int)s, tiles * live, st));
+      CK(full ? launch_sweep_kq<true>(kq, L, (int)s, tiles * live, st) : launch_sweep_kq<false>(kq, L, (int)s, tiles * live, st));
       ctx->stats.n_sweep_launches++;
       ctx->stats.n_state_sweeps += live;
       ctx->stats.state_bytes_swept += 2 * (int64_t)sizeof(double) * L.stride * live;

@@ -32,25 +32,47 @@ struct DmLaunch {
 template <bool SW> __device__ __forceinline__ constexpr int idx2(int d0, int d1) {
   return SW ? (d1 + 4 * d0) : (d0 + 4 * d1);  // (q0,q1) digits -> register index
 }
+template <bool ON_B> __device__ __forceinline__ constexpr int idx1(int d, int other) {
+  return ON_B ? (other + 4 * d) : (d + 4 * other);
+}
 
+// general 4x4 (kept for channels that are not trace preserving)
 template <bool ON_B> __device__ __forceinline__ void op_dense1(double (&v)[16], const double* __restrict__ m) {
-  double a[16];
   const double2* m2 = reinterpret_cast<const double2*>(m);
 #pragma unroll
-  for (int i = 0; i < 8; ++i) { double2 t = __ldg(m2 + i); a[2 * i] = t.x; a[2 * i + 1] = t.y; }
-#pragma unroll
-  for (int o = 0; o < 4; ++o) {  // the other digit
-    double x[4];
-#pragma unroll
-    for (int j = 0; j < 4; ++j) x[j] = v[ON_B ? (o + 4 * j) : (j + 4 * o)];
+  for (int o = 0; o < 4; ++o) {
+    const double x0 = v[idx1<ON_B>(0, o)], x1 = v[idx1<ON_B>(1, o)], x2 = v[idx1<ON_B>(2, o)], x3 = v[idx1<ON_B>(3, o)];
 #pragma unroll
     for (int i = 0; i < 4; ++i) {
-      double s = a[i * 4] * x[0];
-      s = fma(a[i * 4 + 1], x[1], s);
-      s = fma(a[i * 4 + 2], x[2], s);
-      s = fma(a[i * 4 + 3], x[3], s);
-      v[ON_B ? (o + 4 * i) : (i + 4 * o)] = s;
+      const double2 a = __ldg(m2 + 2 * i), b = __ldg(m2 + 2 * i + 1);
+      v[idx1<ON_B>(i, o)] = fma(b.y, x3, fma(b.x, x2, fma(a.y, x1, a.x * x0)));
     }
+  }
+}
+
+// trace-preserving 1-qubit channel: row 0 of the transfer matrix is (1,0,0,0); m = rows 1..3
+template <bool ON_B> __device__ __forceinline__ void op_aff1(double (&v)[16], const double* __restrict__ m) {
+  const double2* m2 = reinterpret_cast<const double2*>(m);
+  double2 a[6];
+#pragma unroll
+  for (int i = 0; i < 6; ++i) a[i] = __ldg(m2 + i);
+#pragma unroll
+  for (int o = 0; o < 4; ++o) {
+    const double x0 = v[idx1<ON_B>(0, o)], x1 = v[idx1<ON_B>(1, o)], x2 = v[idx1<ON_B>(2, o)], x3 = v[idx1<ON_B>(3, o)];
+#pragma unroll
+    for (int i = 0; i < 3; ++i)
+      v[idx1<ON_B>(i + 1, o)] = fma(a[2 * i + 1].y, x3, fma(a[2 * i + 1].x, x2, fma(a[2 * i].y, x1, a[2 * i].x * x0)));
+  }
+}
+
+// rz / phase: X' = c X - s Y, Y' = s X + c Y
+template <bool ON_B> __device__ __forceinline__ void op_rotz(double (&v)[16], const double* __restrict__ m) {
+  const double2 cs = __ldg(reinterpret_cast<const double2*>(m));
+#pragma unroll
+  for (int o = 0; o < 4; ++o) {
+    const double x = v[idx1<ON_B>(1, o)], y = v[idx1<ON_B>(2, o)];
+    v[idx1<ON_B>(1, o)] = fma(-cs.y, y, cs.x * x);
+    v[idx1<ON_B>(2, o)] = fma(cs.y, x, cs.x * y);
   }
 }
 
@@ -73,19 +95,23 @@ template <bool CTRL_B> __device__ __forceinline__ void op_cx(double (&v)[16]) {
 }
 
 // out[i] = d[i] in[i]; out[Z,b] += ca[b] in[I,b]; out[a,Z] += cb[a] in[a,I]; out[Z,Z] += cab in[I,I]
+// evaluated in place: (Z,Z) first, then the Z row / Z column, then the plain scalings.
 template <bool SW> __device__ __forceinline__ void op_relax2(double (&v)[16], const double* __restrict__ m) {
-  double w[16];
+  const double2* m2 = reinterpret_cast<const double2*>(m);
+  double p[28];
 #pragma unroll
-  for (int i = 0; i < 16; ++i) w[i] = v[i];
+  for (int i = 0; i < 13; ++i) { const double2 t = __ldg(m2 + i); p[2 * i] = t.x; p[2 * i + 1] = t.y; }
+  // p[0..15] = d[d0 + 4 d1], p[16..19] = ca[b], p[20..23] = cb[a], p[24] = cab
+  v[idx2<SW>(3, 3)] = fma(p[24], v[idx2<SW>(0, 0)],
+                      fma(p[23], v[idx2<SW>(3, 0)], fma(p[19], v[idx2<SW>(0, 3)], p[15] * v[idx2<SW>(3, 3)])));
 #pragma unroll
-  for (int d1 = 0; d1 < 4; ++d1)
+  for (int b = 0; b < 3; ++b) v[idx2<SW>(3, b)] = fma(p[16 + b], v[idx2<SW>(0, b)], p[3 + 4 * b] * v[idx2<SW>(3, b)]);
 #pragma unroll
-    for (int d0 = 0; d0 < 4; ++d0) v[idx2<SW>(d0, d1)] = __ldg(m + d0 + 4 * d1) * w[idx2<SW>(d0, d1)];
+  for (int a = 0; a < 3; ++a) v[idx2<SW>(a, 3)] = fma(p[20 + a], v[idx2<SW>(a, 0)], p[a + 12] * v[idx2<SW>(a, 3)]);
 #pragma unroll
-  for (int b = 0; b < 4; ++b) v[idx2<SW>(3, b)] = fma(__ldg(m + 16 + b), w[idx2<SW>(0, b)], v[idx2<SW>(3, b)]);
+  for (int b = 0; b < 3; ++b)
 #pragma unroll
-  for (int a = 0; a < 4; ++a) v[idx2<SW>(a, 3)] = fma(__ldg(m + 20 + a), w[idx2<SW>(a, 0)], v[idx2<SW>(a, 3)]);
-  v[idx2<SW>(3, 3)] = fma(__ldg(m + 24), w[idx2<SW>(0, 0)], v[idx2<SW>(3, 3)]);
+    for (int a = 0; a < 3; ++a) v[idx2<SW>(a, b)] *= p[a + 4 * b];
 }
 
 template <bool SW> __device__ __forceinline__ void op_dense2(double (&v)[16], const double* __restrict__ m) {
@@ -110,6 +136,7 @@ template <bool SW> __device__ __forceinline__ void op_dense2(double (&v)[16], co
     }
 }
 
+template <bool FULL>
 __device__ __forceinline__ void run_ops(double (&v)[16], const DmLaunch& L, int op_begin, int op_end) {
   for (int o = op_begin; o < op_end; ++o) {
     const int4 raw = __ldg(reinterpret_cast<const int4*>(L.ops + o));
@@ -117,17 +144,39 @@ __device__ __forceinline__ void run_ops(double (&v)[16], const DmLaunch& L, int 
     const int64_t off = (int64_t(uint32_t(raw.w)) << 32) | uint32_t(raw.z);
     const double* m = (raw.y ? L.noise : L.mats) + off;
     switch (kind) {
-      case K_DENSE1_A: op_dense1<false>(v, m); break;
-      case K_DENSE1_B: op_dense1<true>(v, m); break;
+      case K_AFF1_A: op_aff1<false>(v, m); break;
+      case K_AFF1_B: op_aff1<true>(v, m); break;
+      case K_ROTZ_A: op_rotz<false>(v, m); break;
+      case K_ROTZ_B: op_rotz<true>(v, m); break;
       case K_CX_AB: op_cx<false>(v); break;
       case K_CX_BA: op_cx<true>(v); break;
       case K_RELAX2: op_relax2<false>(v, m); break;
       case K_RELAX2_SW: op_relax2<true>(v, m); break;
-      case K_DENSE2: op_dense2<false>(v, m); break;
-      case K_DENSE2_SW: op_dense2<true>(v, m); break;
+      case K_DENSE1_A: if constexpr (FULL) op_dense1<false>(v, m); break;
+      case K_DENSE1_B: if constexpr (FULL) op_dense1<true>(v, m); break;
+      case K_DENSE2: if constexpr (FULL) op_dense2<false>(v, m); break;
+      case K_DENSE2_SW: if constexpr (FULL) op_dense2<true>(v, m); break;
       default: break;
     }
   }
+}
+
+// ---------------------------------------------------------------------------------------------
+// shared-memory swizzle.  Tile element j (digits D0..D6, 2 bits each) lives at swz(j): the low
+// two digits are XOR-ed with GF(4)-linear combinations of the higher digits,
+//   digit0' = D0 + D2 + D3 + D4 + D5 + D6,   digit1' = D1 + D2 + w D3 + w^2 D4 + w^2 D5 + w D6,
+// i.e. D0..D4 sit on the five distinct points of the projective line over GF(4).  A half-warp of
+// a register pass varies the two lowest non-target digits (always among D0..D3), so its 16
+// 8-byte accesses hit 16 distinct bank pairs for EVERY choice of target slots; the linear
+// load/store phases stay conflict-free as well.  swz is XOR-linear: swz(a^b) = swz(a)^swz(b).
+// ---------------------------------------------------------------------------------------------
+__device__ __forceinline__ uint32_t gf4_mulw(uint32_t b) { return (((b >> 1) ^ b) & 1u) << 1 | (b >> 1); }
+__device__ __forceinline__ uint32_t swz(uint32_t j) {
+  const uint32_t d2 = (j >> 4) & 3u, d3 = (j >> 6) & 3u, d4 = (j >> 8) & 3u, d5 = (j >> 10) & 3u, d6 = (j >> 12) & 3u;
+  const uint32_t d45 = d4 ^ d5, d36 = d3 ^ d6;
+  const uint32_t x0 = d2 ^ d36 ^ d45;
+  const uint32_t x1 = d2 ^ gf4_mulw(d36) ^ gf4_mulw(d45) ^ d45;
+  return j ^ (x0 | (x1 << 2));
 }
 
 // ---------------------------------------------------------------------------------------------
@@ -137,10 +186,13 @@ template <int KQ> struct SweepCfg {
   static constexpr int kElems = 1 << (2 * KQ);
   static constexpr int kGroups = kElems / 16;
   static constexpr int kThreads = kGroups >= 256 ? 256 : (kGroups >= 32 ? kGroups : 32);
+  static constexpr int kMinBlocks = KQ >= 7 ? 1 : (KQ == 6 ? 3 : 4);
 };
 
-template <int KQ>
-__global__ void __launch_bounds__(SweepCfg<KQ>::kThreads)
+// FULL = also carries the dense 4x4 / 16x16 ops (coherent errors, non-basis 2-qubit gates); the
+// lean instantiation keeps the register budget at 3 CTAs per SM.
+template <int KQ, bool FULL>
+__global__ void __launch_bounds__(SweepCfg<KQ>::kThreads, FULL ? 1 : SweepCfg<KQ>::kMinBlocks)
 dm_sweep_kernel(const DmLaunch L, const int sweep_idx) {
   constexpr int E = SweepCfg<KQ>::kElems, G = SweepCfg<KQ>::kGroups, T = SweepCfg<KQ>::kThreads;
   extern __shared__ __align__(16) double tile[];
@@ -171,16 +223,19 @@ dm_sweep_kernel(const DmLaunch L, const int sweep_idx) {
     }
   }
   double* __restrict__ g = L.states + slot * L.stride + base;
+  double2* tile2 = reinterpret_cast<double2*>(tile);
 
   // ---- load (or synthesise |0..0><0..0| on the first sweep)
   if (sweep_idx == 0) {
     const bool tile_ok = ((t ^ (t >> 1)) & 0x55555555u) == 0u;  // all outside digits in {I,Z}
 #pragma unroll
     for (int u = tid; u < E / 2; u += T) {
-      const uint32_t j = 2u * u;
-      const bool ok0 = tile_ok && (((j ^ (j >> 1)) & 0x55555555u) == 0u);
-      const bool ok1 = tile_ok && ((((j + 1) ^ ((j + 1) >> 1)) & 0x55555555u) == 0u);
-      reinterpret_cast<double2*>(tile)[u] = make_double2(ok0 ? 1.0 : 0.0, ok1 ? 1.0 : 0.0);
+      const uint32_t j = 2u * u;  // D0 of j is 0 or 2 -> element j+1 has D0 = 1 or 3
+      const bool hi_ok = tile_ok && ((((j >> 2) ^ (j >> 3)) & 0x15555555u) == 0u);
+      const bool d0_is2 = (j & 2u) != 0u;
+      const uint32_t p = swz(j);
+      const double e0 = (hi_ok && !d0_is2) ? 1.0 : 0.0, e1 = (hi_ok && d0_is2) ? 1.0 : 0.0;
+      tile2[p >> 1] = (p & 1u) ? make_double2(e1, e0) : make_double2(e0, e1);
     }
   } else {
 #pragma unroll
@@ -189,7 +244,9 @@ dm_sweep_kernel(const DmLaunch L, const int sweep_idx) {
       int64_t off = 0;
 #pragma unroll
       for (int s = 0; s < KQ; ++s) off |= int64_t((j >> (2 * s)) & 3u) << (2 * pos[s]);
-      reinterpret_cast<double2*>(tile)[u] = *reinterpret_cast<const double2*>(g + off);
+      const double2 val = *reinterpret_cast<const double2*>(g + off);
+      const uint32_t p = swz(j);
+      tile2[p >> 1] = (p & 1u) ? make_double2(val.y, val.x) : val;
     }
   }
 
@@ -199,22 +256,24 @@ dm_sweep_kernel(const DmLaunch L, const int sweep_idx) {
     const int4 praw = __ldg(reinterpret_cast<const int4*>(L.passes + p));
     const int sa = praw.z & 0xff, sb = (praw.z >> 8) & 0xff;
     const int lo = min(sa, sb), hi = max(sa, sb);
-    const int stride_a = 1 << (2 * sa), stride_b = 1 << (2 * sb);
+    uint32_t oa[4], ob[4];
+#pragma unroll
+    for (int d = 0; d < 4; ++d) { oa[d] = swz(uint32_t(d) << (2 * sa)); ob[d] = swz(uint32_t(d) << (2 * sb)); }
     for (int grp = tid; grp < G; grp += T) {
       const uint32_t low = grp & ((1u << (2 * lo)) - 1u);
       const uint32_t mid = (grp >> (2 * lo)) & ((1u << (2 * (hi - lo - 1))) - 1u);
       const uint32_t high = grp >> (2 * (hi - 1));
-      const uint32_t b0 = low | (mid << (2 * lo + 2)) | (high << (2 * hi + 2));
+      const uint32_t b0 = swz(low | (mid << (2 * lo + 2)) | (high << (2 * hi + 2)));
       double v[16];
 #pragma unroll
       for (int db = 0; db < 4; ++db)
 #pragma unroll
-        for (int da = 0; da < 4; ++da) v[da + 4 * db] = tile[b0 + da * stride_a + db * stride_b];
-      run_ops(v, L, praw.x, praw.y);
+        for (int da = 0; da < 4; ++da) v[da + 4 * db] = tile[b0 ^ oa[da] ^ ob[db]];
+      run_ops<FULL>(v, L, praw.x, praw.y);
 #pragma unroll
       for (int db = 0; db < 4; ++db)
 #pragma unroll
-        for (int da = 0; da < 4; ++da) tile[b0 + da * stride_a + db * stride_b] = v[da + 4 * db];
+        for (int da = 0; da < 4; ++da) tile[b0 ^ oa[da] ^ ob[db]] = v[da + 4 * db];
     }
   }
   __syncthreads();
@@ -226,7 +285,9 @@ dm_sweep_kernel(const DmLaunch L, const int sweep_idx) {
     int64_t off = 0;
 #pragma unroll
     for (int s = 0; s < KQ; ++s) off |= int64_t((j >> (2 * s)) & 3u) << (2 * pos[s]);
-    *reinterpret_cast<double2*>(g + off) = reinterpret_cast<const double2*>(tile)[u];
+    const uint32_t p = swz(j);
+    const double2 val = tile2[p >> 1];
+    *reinterpret_cast<double2*>(g + off) = (p & 1u) ? make_double2(val.y, val.x) : val;
   }
 }
 

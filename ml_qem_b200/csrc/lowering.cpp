@@ -340,8 +340,23 @@ void lower_dm_circuit(const NoiseTable& noise, const bwq_batch& b, int c, const 
   std::vector<int> last(nd, -1);
   auto flush = [&](int d, HostPass& p) {
     if (!has[d]) return;
-    p.ops.push_back(DevOp{d == p.qa ? K_DENSE1_A : K_DENSE1_B, 0, push_mat(out->mats, &pend[16 * d], 16)});
     has[d] = 0;
+    const double* m = &pend[16 * d];
+    const bool on_a = d == p.qa;
+    const bool tp = m[0] == 1.0 && m[1] == 0.0 && m[2] == 0.0 && m[3] == 0.0;
+    if (!tp) {  // not trace preserving: general 4x4
+      p.ops.push_back(DevOp{on_a ? K_DENSE1_A : K_DENSE1_B, 0, push_mat(out->mats, m, 16)});
+      return;
+    }
+    const bool rot = m[4] == 0.0 && m[8] == 0.0 && m[12] == 0.0 && m[7] == 0.0 && m[11] == 0.0 &&
+                     m[13] == 0.0 && m[14] == 0.0 && m[15] == 1.0 && m[5] == m[10] && m[6] == -m[9];
+    if (rot) {
+      if (m[5] == 1.0 && m[9] == 0.0) return;  // identity
+      const double cs[4] = {m[5], m[9], 0.0, 0.0};
+      p.ops.push_back(DevOp{on_a ? K_ROTZ_A : K_ROTZ_B, 0, push_mat(out->mats, cs, 4)});
+      return;
+    }
+    p.ops.push_back(DevOp{on_a ? K_AFF1_A : K_AFF1_B, 0, push_mat(out->mats, m + 4, 12)});
   };
   for (int64_t g = g0; g < g1; ++g) {
     const bwq_op& op = b.ops[g];
@@ -393,7 +408,8 @@ void lower_dm_circuit(const NoiseTable& noise, const bwq_batch& b, int c, const 
 
   // ---- passes -> sweeps (greedy in program order; a pass that does not fit blocks its qubits)
   const int kq = std::min(std::max(opt.tile_qubits, 2), std::min(nd, kMaxTileQubits));
-  const int mlow = std::min(std::max(opt.low_qubits, 0), kq);
+  // always-resident low digits (coalescing); two slots must stay free for an arbitrary pass
+  const int mlow = (nd <= kq) ? 0 : std::min(std::max(opt.low_qubits, 0), kq - 2);
   const int np = (int)passes.size();
   std::vector<char> done(np, 0);
   int first = 0, remaining = np;
@@ -430,12 +446,15 @@ void lower_dm_circuit(const NoiseTable& noise, const bwq_batch& b, int c, const 
     int s = 0;
     for (int d = 0; d < nd; ++d) if (in_tile[d]) { sw.pos[s] = (uint8_t)d; slot_of[d] = s++; }
     sw.pass_end = (int)out->passes.size();
+    if (sw.pass_end == sw.pass_begin) { out->status = BWQ_CIRC_BAD_OP; return; }  // cannot happen
     for (int i = sw.pass_begin; i < sw.pass_end; ++i) {
       out->passes[i].sa = (uint8_t)slot_of[out->passes[i].sa];
       out->passes[i].sb = (uint8_t)slot_of[out->passes[i].sb];
     }
     out->sweeps.push_back(sw);
   }
+  for (const DevOp& o : out->ops)
+    if (o.kind == K_DENSE1_A || o.kind == K_DENSE1_B || o.kind == K_DENSE2 || o.kind == K_DENSE2_SW) out->needs_dense = true;
 }
 
 // ----------------------------------------------------------------------------- SV lowering

@@ -24,7 +24,11 @@ enum OpKind : int32_t {
   K_RELAX2_SW = 5, // same with (q0,q1)=(b,a)
   K_DENSE2 = 6,    // 16x16 real matrix, (q0,q1)=(a,b)    (256 doubles)
   K_DENSE2_SW = 7, // same with (q0,q1)=(b,a)
-  K_COUNT = 8
+  K_AFF1_A = 8,    // trace-preserving 1-qubit channel on digit a: rows 1..3 of its 4x4 (12 doubles)
+  K_AFF1_B = 9,
+  K_ROTZ_A = 10,   // rz / phase on digit a: (cos, sin) (2 doubles, padded to 4)
+  K_ROTZ_B = 11,
+  K_COUNT = 12
 };
 
 struct DevOp {      // 16 B
@@ -72,6 +76,7 @@ struct CircuitProgram {
   std::vector<int64_t> term_index;      // per Pauli term: element index or -1
   std::vector<double> term_coeff;
   int64_t n_gates = 0;
+  bool needs_dense = false;             // uses K_DENSE1_* / K_DENSE2_* (selects the FULL kernel)
 };
 
 struct LowerOptions {

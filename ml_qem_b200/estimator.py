@@ -1,0 +1,215 @@
+"""Estimator primitive surface backed by the B200 engine.
+
+Mirrors what the reference calls on its Aer-backed estimators:
+  blackwater/data/utils.py:422-430, 442-443   estimator.run(circuits, observables).result().values[0]
+  blackwater/library/learning/estimator.py:320-327  learning(): subclass + replace ``_run``; the
+      original is invoked as run(self, circuits=..., observables=..., parameter_values=..., **opts)
+      (:279-285) and the job must offer result()/job_id()/submit()/status()/cancel() (:215-256)
+  blackwater/library/ngem/estimator.py:101-157  ngem(): same contract
+  [3P] qiskit.primitives.BaseEstimator.run normalisation + validation
+
+Modes: a noise model / backend given -> density-matrix (noisy) values, as
+``AerEstimator(backend_options={"method": "density_matrix", "noise_model": NoiseModel.from_backend(b)},
+approximation=True, skip_transpilation=True)`` with shots=None; none given -> ideal statevector
+values, as ``qiskit.primitives.Estimator`` with shots=None.  When qiskit is importable the real
+``EstimatorResult`` class is returned; otherwise a dataclass with the same fields.
+"""
+import threading
+import uuid
+from dataclasses import dataclass
+
+import numpy as np
+
+from . import circuit as circuit_mod
+from . import noise as noise_mod
+from . import observable as observable_mod
+from .engine import Engine, STATUS_TEXT, encode_batch
+
+try:  # pragma: no cover - qiskit is not installed in the build image
+    from qiskit.primitives import EstimatorResult  # type: ignore
+except Exception:  # noqa: BLE001
+
+    @dataclass(frozen=True)
+    class EstimatorResult:
+        """Same fields as qiskit.primitives.EstimatorResult."""
+
+        values: np.ndarray
+        metadata: list
+
+
+class B200Job:
+    """Minimal JobV1-like handle (PrimitiveJob equivalent): runs eagerly on ``submit``."""
+
+    def __init__(self, fn):
+        self._fn = fn
+        self._id = str(uuid.uuid4())
+        self._result = None
+        self._error = None
+        self._done = threading.Event()
+
+    def job_id(self):
+        return self._id
+
+    def submit(self):
+        if self._done.is_set():
+            return
+        try:
+            self._result = self._fn()
+        except Exception as exc:  # noqa: BLE001 - re-raised from result()
+            self._error = exc
+        self._done.set()
+
+    def result(self):
+        self.submit()
+        if self._error is not None:
+            raise self._error
+        return self._result
+
+    def status(self):
+        if not self._done.is_set():
+            return "INITIALIZING"
+        return "ERROR" if self._error is not None else "DONE"
+
+    def done(self):
+        return self._done.is_set() and self._error is None
+
+    def running(self):
+        return False
+
+    def cancelled(self):
+        return False
+
+    def in_final_state(self):
+        return self._done.is_set()
+
+    def cancel(self):
+        return False
+
+
+_ENGINES = {}
+_ENGINES_LOCK = threading.Lock()
+
+
+def shared_engine(device=0):
+    with _ENGINES_LOCK:
+        if device not in _ENGINES:
+            _ENGINES[device] = Engine(device)
+        return _ENGINES[device]
+
+
+class B200Estimator:
+    """Exact (shots=None) Estimator on one B200.
+
+    Args:
+        backend: calibration source for the device noise model (BackendProps, properties dict,
+            get_backend_properties_v1 dict or a Qiskit backend); ``None`` => ideal statevector.
+        noise_model: explicit ml_qem_b200.noise.NoiseModel (overrides ``backend``).
+        device: CUDA device index.
+        options: default run options (kept and merged like BaseEstimator.options).
+    """
+
+    def __init__(self, backend=None, noise_model=None, device=0, options=None, engine=None, **engine_options):
+        self._noise = noise_model if noise_model is not None else (
+            noise_mod.from_backend(backend) if backend is not None else None)
+        self._backend = backend
+        self._device = device
+        self._engine = engine
+        self._engine_options = engine_options
+        self._options = dict(options or {})
+
+    # -- BaseEstimator surface
+    @property
+    def options(self):
+        return dict(self._options)
+
+    def set_options(self, **fields):
+        self._options.update(fields)
+
+    @property
+    def noise_model(self):
+        return self._noise
+
+    def run(self, circuits, observables, parameter_values=None, **run_options):
+        if not isinstance(circuits, (list, tuple)):
+            circuits = [circuits]
+        if isinstance(observables, (str,)) or not isinstance(observables, (list, tuple)) or (
+                observables and isinstance(observables[0], tuple) and isinstance(observables[0][0], str)):
+            observables = [observables]
+        circuits = tuple(circuits)
+        observables = tuple(observable_mod.from_any(o) for o in observables)
+        if parameter_values is None:
+            parameter_values = [()] * len(circuits)
+        else:
+            parameter_values = list(parameter_values)
+            if parameter_values and not isinstance(parameter_values[0], (list, tuple, np.ndarray)):
+                parameter_values = [parameter_values]
+        parameter_values = tuple(tuple(float(v) for v in pv) for pv in parameter_values)
+        if len(circuits) != len(observables):
+            raise ValueError(f"The number of circuits ({len(circuits)}) does not match the number of observables ({len(observables)}).")
+        if len(circuits) != len(parameter_values):
+            raise ValueError(f"The number of circuits ({len(circuits)}) does not match the number of parameter value sets ({len(parameter_values)}).")
+        for i, (c, o, pv) in enumerate(zip(circuits, observables, parameter_values)):
+            npar = getattr(c, "num_parameters", 0) if not isinstance(c, str) else 0
+            if len(pv) != npar:
+                raise ValueError(f"The number of values ({len(pv)}) does not match the number of parameters ({npar}) for the {i}-th circuit.")
+            nq = c.num_qubits if not isinstance(c, str) else circuit_mod.from_any(c).num_qubits
+            if len(o) and o.num_qubits != nq:
+                raise ValueError(f"The number of qubits of the {i}-th circuit ({nq}) does not match the number of qubits of the {i}-th observable ({o.num_qubits}).")
+        opts = dict(self._options)
+        opts.update(run_options)
+        return self._run(circuits, observables, parameter_values, **opts)
+
+    def _run(self, circuits, observables, parameter_values, **run_options):
+        job = B200Job(lambda: self._call(circuits, observables, parameter_values, **run_options))
+        job.submit()
+        return job
+
+    # -- the work
+    def _engine_handle(self):
+        if self._engine is None:
+            self._engine = shared_engine(self._device)
+        if self._engine_options:
+            self._engine.set_options(**self._engine_options)
+        return self._engine
+
+    def _call(self, circuits, observables, parameter_values, **run_options):
+        shots = run_options.get("shots")
+        if shots not in (None, 0):
+            raise ValueError("B200Estimator is exact: run with shots=None")
+        bound, keys = [], {}
+        groups = []  # unique (circuit, params) -> list of observable indices: one evolution serves all
+        for i, (c, pv) in enumerate(zip(circuits, parameter_values)):
+            key = (id(c), pv)
+            if key not in keys:
+                if pv:
+                    if hasattr(c, "assign_parameters"):
+                        b = c.assign_parameters(list(pv))
+                    else:
+                        b = c.bind_parameters(list(pv))
+                else:
+                    b = c
+                keys[key] = len(bound)
+                bound.append(circuit_mod.from_any(b))
+                groups.append([])
+            groups[keys[key]].append(i)
+        batch = encode_batch(bound, [[observables[i] for i in g] for g in groups])
+        eng = self._engine_handle()
+        if self._noise is not None and not self._noise.is_ideal():
+            eng.set_noise(self._noise)
+            vals, status = eng.run_dm(batch)
+            method = "density_matrix"
+        else:
+            vals, status = eng.run_sv(batch)
+            method = "statevector"
+        bad = np.nonzero(status)[0]
+        if len(bad):
+            c = int(bad[0])
+            raise ValueError(f"circuit {groups[c][0]}: {STATUS_TEXT.get(int(status[c]), 'error')}")
+        out = np.empty(len(circuits), dtype=float)
+        k = 0
+        for g in groups:
+            for i in g:
+                out[i] = vals[k]
+                k += 1
+        meta = [{"simulator_metadata": {"method": method, "device": f"cuda:{self._device}"}} for _ in circuits]
+        return EstimatorResult(np.real_if_close(out), meta)

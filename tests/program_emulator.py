@@ -9,7 +9,8 @@ import numpy as np
 
 CX_SRC = [0, 5, 6, 3, 4, 1, 2, 7, 11, 14, 13, 8, 15, 10, 9, 12]
 CX_SGN = [1, 1, 1, 1, 1, 1, 1, 1, 1, 1, -1, 1, 1, -1, 1, 1]
-K_DENSE1_A, K_DENSE1_B, K_CX_AB, K_CX_BA, K_RELAX2, K_RELAX2_SW, K_DENSE2, K_DENSE2_SW = range(8)
+(K_DENSE1_A, K_DENSE1_B, K_CX_AB, K_CX_BA, K_RELAX2, K_RELAX2_SW, K_DENSE2, K_DENSE2_SW,
+ K_AFF1_A, K_AFF1_B, K_ROTZ_A, K_ROTZ_B) = range(12)
 
 
 def _swap_view(v):  # v[da + 4 db] -> index with (q0,q1) = (b,a)
@@ -24,6 +25,13 @@ def apply_op(v, kind, m):
     if kind == K_DENSE1_B:
         a = m[:16].reshape(4, 4)
         return np.einsum("ij,jag->iag", a, v.reshape(4, 4, -1)).reshape(16, -1)
+    if kind in (K_AFF1_A, K_AFF1_B):
+        a = np.vstack([[1.0, 0.0, 0.0, 0.0], m[:12].reshape(3, 4)])
+        return apply_op(v, K_DENSE1_A if kind == K_AFF1_A else K_DENSE1_B, a.reshape(-1))
+    if kind in (K_ROTZ_A, K_ROTZ_B):
+        c, s = m[0], m[1]
+        a = np.array([[1, 0, 0, 0], [0, c, -s, 0], [0, s, c, 0], [0, 0, 0, 1.0]])
+        return apply_op(v, K_DENSE1_A if kind == K_ROTZ_A else K_DENSE1_B, a.reshape(-1))
     if kind in (K_CX_AB, K_CX_BA):
         w = v if kind == K_CX_AB else _swap_view(v)
         out = np.empty_like(w)

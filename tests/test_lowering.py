@@ -1,0 +1,122 @@
+"""CPU: lowering stage (host C++ in libbwq.so) + Pauli-transfer algebra against the oracle, by
+executing the lowered sweep program with the numpy emulator.  No GPU needed."""
+import numpy as np
+import pytest
+
+import helpers
+from program_emulator import expvals, run_program
+from ml_qem_b200 import backends, engine, families as F, noise
+
+TOL = 1e-12
+
+
+def _labels(rng, n, k):
+    return ["".join(rng.choice(list("IXYZ"), size=n)) for _ in range(k)]
+
+
+def _check(circ, obs, nm, on, tilings=((6, 2), (3, 1), (4, 2), (2, -1), (7, 2))):
+    fb = engine.encode_batch([circ], [obs])
+    if on is None:
+        cc, oo = helpers.compact(circ, obs)
+        ref = helpers.oracle_dm_values(cc, oo, None)
+    else:
+        cc, oo, on2 = helpers.compact(circ, obs, on)
+        ref = helpers.oracle_dm_values(cc, oo, on2)
+    for kq, low in tilings:
+        prog = engine.lower_dm(fb, 0, nm, kq, low)
+        assert prog["status"] == 0
+        got = expvals(prog, run_program(prog), [len(o) for o in obs])
+        assert np.max(np.abs(got - ref)) <= TOL, (kq, low)
+    return prog
+
+
+def test_lima_random_circuits(lib):
+    lima = backends.fake_lima()
+    nm = noise.from_backend(lima)
+    on = helpers.oracle_noise("fakelima")
+    rng = np.random.default_rng(1)
+    for _ in range(12):
+        c = F.random_basis_circuit(5, int(rng.integers(0, 60)), rng, lima.coupling_map)
+        obs = [[(l, float(rng.normal()))] for l in _labels(rng, 5, 6)] + [[("ZZIII", 0.5), ("IXXII", -1.5), ("IIIII", 2.0)]]
+        _check(c, obs, nm, on)
+
+
+def test_tfim_zne_fold_on_lima_chain(lib):
+    lima = backends.fake_lima()
+    nm = noise.from_backend(lima)
+    on = helpers.oracle_noise("fakelima")
+    for fold in (1, 3, 5):
+        c = F.tfim_circuit(4, 3, 0.37, basis="Y", layout=[0, 1, 3, 4], num_physical=5, fold=fold, random_init_prefix=True)
+        prog = _check(c, F.single_z_observables([0, 1, 3, 4], 5), nm, on)
+        assert prog["n_digits"] == 4 and len(prog["sweeps"]) == 1  # idle qubit 2 truncated, on-chip
+
+
+def test_coherent_cx_noise_uses_dense_op(lib):
+    lima = backends.fake_lima()
+    nm, thetas = noise.add_coherent_noise(lima, theta=0.04 * np.pi, seed=0)
+    from oracle import noise_model as onm
+    on = onm.add_coherent_noise(helpers.golden("backends.json")["fakelima"], theta=0.04 * np.pi, seed=0)
+    assert np.allclose(thetas, helpers.golden("kats.json")["coherent_thetas_8digits"], atol=1e-8)
+    rng = np.random.default_rng(3)
+    c = F.random_basis_circuit(5, 40, rng, lima.coupling_map)
+    prog = _check(c, [[(l, 1.0)] for l in _labels(rng, 5, 5)], nm, on, tilings=((6, 2), (3, 1)))
+    assert any((int(k) & 0xff) in (6, 7) for k, _ in prog["ops"])
+
+
+def test_non_basis_gates_and_reset(lib):
+    from ml_qem_b200 import Circuit
+    c = Circuit(4)
+    c.h(0); c.cz(0, 1); c.u3(0.3, 0.2, -0.7, 2); c.swap(1, 2); c.rzz(0.4, 2, 3); c.ecr(3, 0); c.t(1); c.sdg(2)
+    c.crx(0.9, 1, 3); c.reset(0); c.ry(0.5, 0); c.cp(1.1, 0, 2); c.y(3); c.rzx(0.6, 1, 2); c.iswap(0, 3); c.cy(2, 0)
+    rng = np.random.default_rng(5)
+    obs = [[(l, 1.0)] for l in _labels(rng, 4, 8)]
+    fb = engine.encode_batch([c], [obs])
+    ref = helpers.oracle_dm_values(c, obs, None)
+    for kq, low in ((6, 2), (2, -1), (3, 2)):
+        prog = engine.lower_dm(fb, 0, None, kq, low)
+        got = expvals(prog, run_program(prog), [1] * len(obs))
+        assert np.max(np.abs(got - ref)) <= TOL
+
+
+def test_idle_qubits_and_empty_circuit(lib):
+    from ml_qem_b200 import Circuit
+    c = Circuit(6)
+    c.sx(4)
+    obs = [[("IZIIII", 1.0)], [("IYIIII", 1.0)], [("ZIIIII", 1.0)], [("XIIIII", 1.0)], [("IIIIII", 3.0)]]
+    fb = engine.encode_batch([c], [obs])
+    prog = engine.lower_dm(fb, 0, None, 6, 2)
+    got = expvals(prog, run_program(prog), [1] * 5)
+    assert np.allclose(got, [0.0, -1.0, 1.0, 0.0, 3.0], atol=1e-15)
+    empty = engine.lower_dm(engine.encode_batch([Circuit(3)], [[[("ZZZ", 1.0)]]]), 0, None, 6, 2)
+    assert len(empty["sweeps"]) == 0 and empty["status"] == 0
+
+
+def test_bad_input_sets_status(lib):
+    import numpy as np
+    from ml_qem_b200.engine import FlatBatch, OP_DTYPE
+    ops = np.zeros(1, dtype=OP_DTYPE)
+    ops["opcode"], ops["q0"] = 20, 0  # unknown opcode
+    fb = FlatBatch([2], [0, 1], ops, [], [0, 0], [0], [], [], [])
+    assert engine.lower_dm(fb, 0, None, 6, 2)["status"] == 1
+    ops["opcode"], ops["q0"] = 1, 7  # qubit out of range
+    fb = FlatBatch([2], [0, 1], ops, [], [0, 0], [0], [], [], [])
+    assert engine.lower_dm(fb, 0, None, 6, 2)["status"] == 3
+
+
+def test_sweep_packing_respects_tile_and_order(lib):
+    be = backends.synthetic_chain(10, seed=1)
+    nm = noise.from_backend(be)
+    c = F.tfim_circuit(10, 3, 0.5)
+    fb = engine.encode_batch([c], [F.single_z_observables(range(10), 10)])
+    for kq, low in ((6, 2), (6, 1), (7, 2), (4, 2)):
+        prog = engine.lower_dm(fb, 0, nm, kq, low)
+        assert prog["n_digits"] == 10
+        pb = 0
+        for sw in prog["sweeps"]:
+            pos = list(sw[1:1 + kq])
+            m = min(max(low, 0), kq - 2)
+            assert pos == sorted(set(pos)) and pos[:m] == list(range(m))
+            for sa, sb, _ in prog["passes"][pb:sw[9]]:
+                assert sa < kq and sb < kq and sa != sb
+            pb = sw[9]
+        assert pb == len(prog["passes"])
