@@ -1,0 +1,357 @@
+#!/usr/bin/env python
+"""bench.py -- noisy+ideal circuits/sec (exact <O>) of the expectation-value hot path.
+
+    python bench.py [--gpus N] [--steps K] [--warmup W] [--impl ours|reference] [--workload NAME]
+    python -m torch.distributed.run --nnodes=1 --nproc-per-node N ... bench.py --gpus N ...
+
+One "step" = one pass of the hot path over one batch of synthetic circuits of the named workload:
+every circuit is evolved twice -- density matrix under the backend-derived noise table (noisy
+values) and statevector (ideal values) -- and all its Pauli observables are evaluated.
+
+Default workload `brick10_guadalupe_twirl` = BASELINE.json configs[1]: 10-qubit random brickwork
+circuits (steps 1..5) on a 16-qubit heavy-hex-like chain table, 100 Pauli twirls per base circuit
+(20 base circuits -> 2000 circuit instances per rank), 10 single-Z observables each.
+
+JSON keys: see the contract in the task statement; `value` is timed with the lowered programs
+resident in HBM (bwq_dm_execute + bwq_sv_execute), `e2e` through the C ABI with HOST buffers
+(bwq_dm_run + bwq_sv_run: lowering, H2D of the programs, kernels, D2H of the values).
+`--impl reference` times the Aer-style CPU restatement (oracle/cpu_ref.cpp; qiskit-aer itself is
+not installable here) on the host cores, on a bounded sample of the same workload.
+"""
+import argparse
+import json
+import os
+import subprocess
+import sys
+import tempfile
+import time
+
+import numpy as np
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, ROOT)
+
+METRIC = "noisy+ideal circuits/sec (exact <O>)"
+UNIT = "circuits/s"
+
+
+# ----------------------------------------------------------------------------------------------
+# workloads (synthetic, seeded)
+# ----------------------------------------------------------------------------------------------
+def build_workload(name, rank, scale=1.0):
+    """-> dict(circuits, observables, backend, desc).  Seeds depend on the rank (weak scaling: every
+    rank owns its own batch of the same shape)."""
+    from ml_qem_b200 import backends, families as F
+
+    if name == "brick10_guadalupe_twirl":
+        n_base = max(1, int(round(20 * scale)))
+        circs, _, obs = F.config_brick10_twirl(n_base=n_base, n_twirls=100, seed=1 + 1000 * rank)
+        be = backends.synthetic_chain(16, seed=2, name="synthetic_guadalupe_like_16q")
+        desc = {"workload": name, "n_qubits": 10, "register": 16, "base_circuits": n_base, "twirls": 100,
+                "circuits_per_rank": len(circs), "observables_per_circuit": len(obs), "trotter_steps": "1..5"}
+    elif name == "tfim4_lima_zne":
+        n_base = max(1, int(round(2000 * scale)))
+        circs, _, obs = F.config_tfim4_lima_zne(n_base=n_base, seed=1000 * rank)
+        be = backends.fake_lima()
+        desc = {"workload": name, "n_qubits": 4, "register": 5, "base_circuits": n_base, "zne_factors": [1, 3, 5],
+                "circuits_per_rank": len(circs), "observables_per_circuit": len(obs)}
+    elif name.startswith("tfim") and name.endswith("_dm"):
+        n = int(name[4:-3])
+        n_c = max(1, int(round(8 * scale)))
+        circs, obs = F.config_tfim_dm(n=n, n_circuits=n_c, seed=2 + 1000 * rank)
+        be = backends.synthetic_chain(n, seed=n, name=f"synthetic_chain_{n}q")
+        desc = {"workload": name, "n_qubits": n, "register": n, "circuits_per_rank": len(circs),
+                "observables_per_circuit": len(obs), "trotter_steps": "1..10"}
+    else:
+        raise SystemExit(f"unknown workload {name!r}")
+    return {"circuits": circs, "observables": [obs] * len(circs), "backend": be, "desc": desc}
+
+
+# ----------------------------------------------------------------------------------------------
+# clocks sampling (nvidia-smi in the background during the timed region)
+# ----------------------------------------------------------------------------------------------
+class ClockSampler:
+    Q = ("index,clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.active,clocks_event_reasons.hw_slowdown,"
+         "clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap")
+
+    def __init__(self, device):
+        self.device = device
+        self.proc = None
+        self.path = None
+
+    def start(self):
+        try:
+            fd, self.path = tempfile.mkstemp(suffix=".csv")
+            os.close(fd)
+            self.proc = subprocess.Popen(["nvidia-smi", f"--query-gpu={self.Q}", "--format=csv,noheader,nounits",
+                                          "-i", str(self.device), "-lms", "100"], stdout=open(self.path, "w"),
+                                         stderr=subprocess.DEVNULL)
+        except Exception:  # noqa: BLE001
+            self.proc = None
+
+    def stop(self):
+        out = {"sm_mhz": None, "sm_max_mhz": None, "reasons": []}
+        if self.proc is None:
+            return out
+        self.proc.terminate()
+        try:
+            self.proc.wait(timeout=5)
+        except Exception:  # noqa: BLE001
+            self.proc.kill()
+        sm, mx, reasons, power = [], [], set(), []
+        try:
+            for line in open(self.path):
+                f = [x.strip() for x in line.split(",")]
+                if len(f) < 9:
+                    continue
+                try:
+                    sm.append(float(f[1])); mx.append(float(f[2])); power.append(float(f[3]))
+                except ValueError:
+                    continue
+                for name, val in zip(("hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"), f[5:9]):
+                    if val.lower().startswith("active"):
+                        reasons.add(name)
+            os.unlink(self.path)
+        except Exception:  # noqa: BLE001
+            pass
+        if sm:
+            out = {"sm_mhz": float(np.median(sm)), "sm_max_mhz": float(max(mx)), "reasons": sorted(reasons),
+                   "power_w_max": float(max(power)), "samples": len(sm)}
+        return out
+
+
+# ----------------------------------------------------------------------------------------------
+# CPU arm: Aer-style restatement (oracle/cpu_ref.cpp) on a bounded sample
+# ----------------------------------------------------------------------------------------------
+def cpu_reference_rate(workload_name, budget_s=12.0, max_circuits=64):
+    """Times noisy (density matrix) + ideal (statevector) evaluation of the first circuits of the
+    rank-0 workload on all host cores.  Returns (circuits/s, cores, sample description)."""
+    from ml_qem_b200 import engine
+    from ml_qem_b200.gateset import OPCODES
+    from oracle import cpu_ref, noise_model as onm
+
+    cpu_ref.build()
+    wl = build_workload(workload_name, 0, scale=0.05 if workload_name != "tfim4_lima_zne" else 0.02)
+    onoise = cpu_ref.noise_arrays(onm.from_backend(wl["backend"].to_dict()), OPCODES)
+    cores = cpu_ref.max_threads()
+    # size the sample: time one circuit, then as many as fit the budget
+    fb1 = engine.encode_batch(wl["circuits"][:1], wl["observables"][:1])
+    t = time.perf_counter()
+    cpu_ref.run_dm(fb1, onoise)
+    cpu_ref.run_sv(fb1)
+    t1 = max(time.perf_counter() - t, 1e-4)
+    # small states run circuit-parallel (one circuit per core), large ones amplitude-parallel
+    est_rate = (cores if wl["desc"]["n_qubits"] < 7 else 1.0) / t1
+    cap = max_circuits if wl["desc"]["n_qubits"] >= 7 else 4096
+    n = int(max(1, min(cap, len(wl["circuits"]), budget_s * est_rate)))
+    fb = engine.encode_batch(wl["circuits"][:n], wl["observables"][:n])
+    t = time.perf_counter()
+    v_dm, s1 = cpu_ref.run_dm(fb, onoise)
+    v_sv, s2 = cpu_ref.run_sv(fb)
+    dt = time.perf_counter() - t
+    assert not s1.any() and not s2.any()
+    return n / dt, cores, f"first {n} circuits of {workload_name} (rank-0 seed), noisy DM + ideal SV, {dt:.2f} s", (fb, v_dm, v_sv)
+
+
+# ----------------------------------------------------------------------------------------------
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=5)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
+    ap.add_argument("--workload", default="brick10_guadalupe_twirl")
+    ap.add_argument("--scale", type=float, default=1.0, help="fraction of the named batch size (debug)")
+    ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--tile-qubits", type=int, default=0)
+    ap.add_argument("--low-qubits", type=int, default=0)
+    ap.add_argument("--chunk-circuits", type=int, default=0)
+    args = ap.parse_args()
+
+    rank = int(os.environ.get("RANK", "0"))
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    local_rank = int(os.environ.get("LOCAL_RANK", "0"))
+    steps, warmup = args.steps, max(args.warmup, 0)
+
+    # ------------------------------------------------------------------ reference arm (CPU)
+    if args.impl == "reference":
+        if rank != 0:
+            return 0
+        t_all = time.perf_counter()
+        rates = []
+        for i in range(warmup + steps):
+            # each step = one bounded sample; budget so that the whole run ends within minutes
+            rate, cores, sample, _ = cpu_reference_rate(args.workload, budget_s=8.0)
+            if i >= warmup:
+                rates.append(rate)
+        value = float(np.mean(rates))
+        line = {
+            "impl": "reference", "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": args.gpus, "steps": steps,
+            "warmup": warmup, "ms_per_step": 1e3 * (time.perf_counter() - t_all) / max(1, warmup + steps),
+            "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f64", "data": "synthetic",
+            "config": {"workload": args.workload, "note": "Aer-style C++/OpenMP restatement (oracle/cpu_ref.cpp); "
+                       "qiskit-aer is not installable offline"},
+            "cpu_baseline": {"value": value, "unit": UNIT, "cores": cores, "kind": "port", "sample": sample},
+            "e2e": {"value": value, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+            "gpu_launches": 0,
+        }
+        print(json.dumps(line))
+        return 0
+
+    # ------------------------------------------------------------------ our arm (B200)
+    import torch
+
+    if not torch.cuda.is_available():
+        raise SystemExit("bench.py: no CUDA device -- the engine has no CPU fallback (use --impl reference for the CPU arm)")
+    torch.cuda.set_device(local_rank)
+    dist = None
+    if world > 1:
+        import torch.distributed as dist_mod
+
+        dist = dist_mod
+        dist.init_process_group("nccl", device_id=torch.device("cuda", local_rank))
+    from ml_qem_b200 import engine, noise
+
+    wl = build_workload(args.workload, rank, args.scale)
+    batch = engine.encode_batch(wl["circuits"], wl["observables"])
+    n_circ = batch.n_circuits
+    eng = engine.Engine(local_rank)
+    eng.set_options(tile_qubits=args.tile_qubits, low_qubits=args.low_qubits, chunk_circuits=args.chunk_circuits)
+    eng.set_noise(noise.from_backend(wl["backend"]))
+
+    def barrier():
+        if dist is not None:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    def max_over_ranks(x):
+        if dist is None:
+            return x
+        t = torch.tensor([x], dtype=torch.float64, device="cuda")
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        return float(t.item())
+
+    def sum_over_ranks(x):
+        if dist is None:
+            return x
+        t = torch.tensor([x], dtype=torch.float64, device="cuda")
+        dist.all_reduce(t, op=dist.ReduceOp.SUM)
+        return float(t.item())
+
+    # ---- resident-program throughput (`value`)
+    st = eng.prepare_dm(batch)
+    assert not st.any(), "lowering failed"
+    st = eng.prepare_sv(batch)
+    assert not st.any()
+    for _ in range(warmup):
+        noisy = eng.execute_dm()
+        ideal = eng.execute_sv()
+    sampler = ClockSampler(local_rank)
+    if rank == 0:
+        sampler.start()
+    barrier()
+    t0 = time.perf_counter()
+    dev_ms = sweep_ms = 0.0
+    launches = swept = sweeps = 0
+    for _ in range(steps):
+        noisy = eng.execute_dm()
+        s = eng.stats()
+        dev_ms += s["kernel_ms"]; sweep_ms += s["sweep_kernel_ms"]
+        launches += s["n_sweep_launches"] + s["n_other_launches"]
+        swept += s["state_bytes_swept"]; sweeps += s["n_state_sweeps"]
+        n_sweep_launches = s["n_sweep_launches"]; n_passes = s["n_passes"]
+        ideal = eng.execute_sv()
+        s = eng.stats()
+        dev_ms += s["kernel_ms"]
+        launches += s["n_other_launches"]
+    barrier()
+    wall_s = time.perf_counter() - t0
+    clocks = sampler.stop() if rank == 0 else None
+    # device time (CUDA events on the engine's stream, summed over the K steps), max over ranks
+    t_dev = max_over_ranks(dev_ms / 1e3)
+    t_wall = max_over_ranks(wall_s)
+    total_circ = sum_over_ranks(float(n_circ)) * steps
+    value = total_circ / t_dev
+
+    # ---- end to end through the C ABI with host buffers (`e2e`)
+    for _ in range(min(warmup, 2)):
+        eng.run_dm(batch); eng.run_sv(batch)
+    barrier()
+    t0 = time.perf_counter()
+    h2d = d2h = 0
+    for _ in range(steps):
+        noisy_e, st1 = eng.run_dm(batch)
+        s = eng.stats(); h2d += s["h2d_bytes"]; d2h += s["d2h_bytes"]
+        ideal_e, st2 = eng.run_sv(batch)
+        s = eng.stats(); h2d += s["h2d_bytes"]; d2h += s["d2h_bytes"]
+    barrier()
+    e2e_s = max_over_ranks(time.perf_counter() - t0)
+    e2e_value = total_circ / e2e_s
+    assert np.array_equal(noisy_e, noisy) and np.array_equal(ideal_e, ideal), "resident and host-buffer paths differ"
+
+    # ---- final gather of the labels (the only collective of the density-matrix path)
+    if dist is not None:
+        mine = torch.from_numpy(np.stack([noisy, ideal])).cuda()
+        parts = [torch.empty_like(mine) for _ in range(world)] if rank == 0 else None
+        dist.gather(mine, parts, dst=0)
+
+    if rank != 0:
+        if dist is not None:
+            dist.destroy_process_group()
+        return 0
+
+    # ---- roofline of the dominant kernel (dm_sweep_kernel): algorithmic bytes = 2 x 8 B x 4^n per
+    # state sweep (one read + one write of every Pauli-basis element), time = CUDA events around
+    # the sweep launches (rank 0)
+    peaks_path = os.path.join(ROOT, "MEASURED_PEAKS.json")
+    if os.path.exists(peaks_path):
+        peak, peak_src = float(json.load(open(peaks_path))["hbm_gbs"]), "measured (MEASURED_PEAKS.json)"
+    else:
+        peak, peak_src = 6650.0, "fallback (B200_PROFILING.md)"
+    achieved = swept / (sweep_ms / 1e3) / 1e9 if sweep_ms > 0 else 0.0
+    roofline = {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
+                "traffic": None, "kernel": "dm_sweep_kernel<6,false>", "peak_source": peak_src,
+                "bytes_per_launch": swept / max(1, steps * n_sweep_launches),
+                "launches_per_step": n_sweep_launches, "state_sweeps_per_step": sweeps // steps,
+                "register_passes_per_step": n_passes,
+                "sweep_share_of_step": sweep_ms / dev_ms if dev_ms else None}
+    traffic_path = os.path.join(ROOT, "profiles", "traffic.json")
+    if os.path.exists(traffic_path):
+        try:
+            roofline["traffic"] = json.load(open(traffic_path)).get(args.workload)
+        except Exception:  # noqa: BLE001
+            pass
+
+    cpu = None
+    if not args.no_cpu_baseline and world == 1:
+        rate, cores, sample, (fb_s, v_dm, v_sv) = cpu_reference_rate(args.workload)
+        # the CPU sample doubles as a parity check of this very run
+        k = fb_s.n_observables
+        err = max(float(np.max(np.abs(noisy[:k] - v_dm))), float(np.max(np.abs(ideal[:k] - v_sv))))
+        cpu = {"value": rate, "unit": UNIT, "cores": cores, "kind": "port", "sample": sample,
+               "max_abs_diff_vs_gpu": err}
+
+    line = {
+        "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": steps, "warmup": warmup,
+        "ms_per_step": 1e3 * t_dev / steps, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
+        "dtype": "f64", "data": "synthetic",
+        "config": dict(wl["desc"], parallelism=f"circuit-sharded x{world}", state_layout="Pauli-basis density matrix, 8 B/element",
+                       l2="per-rank working set %.1f GiB of resident states >> 126 MB L2 (no flush needed)" %
+                          (n_circ * 8 * 4 ** wl["desc"]["n_qubits"] / 2 ** 30),
+                       timing="CUDA events on the engine stream summed over steps (max over ranks); wall %.1f ms/step" %
+                              (1e3 * t_wall / steps)),
+        "e2e": {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": h2d // steps, "d2h_bytes_per_step": d2h // steps,
+                "ms_per_step": 1e3 * e2e_s / steps},
+        "gpu_launches": int(launches),
+        "roofline": roofline,
+        "cpu_baseline": cpu,
+        "clocks": clocks,
+    }
+    print(json.dumps(line))
+    if dist is not None:
+        dist.destroy_process_group()
+    return 0
+
+
+if __name__ == "__main__":
+    sys.exit(main())

@@ -124,6 +124,7 @@ typedef struct {
   int64_t n_other_launches;    /* init / expectation / statevector launches              */
   double lower_ms, h2d_ms, kernel_ms, d2h_ms; /* host wall / device-event times          */
   double sweep_kernel_ms;      /* CUDA-event time of the sweep launches only             */
+  int64_t h2d_bytes, d2h_bytes;/* program upload / value download of the last run          */
 } bwq_stats;
 
 typedef struct bwq_ctx bwq_ctx;
@@ -141,9 +142,17 @@ int bwq_set_noise_table(bwq_ctx* ctx, const bwq_noise_table* table);
  * (Aer Estimator, method=density_matrix, approximation=True, shots=None).
  * out_vals[n_observables] (order of term_offsets), out_status[n_circuits]. */
 int bwq_dm_run(bwq_ctx* ctx, const bwq_batch* batch, double* out_vals, int32_t* out_status);
+/* Split form of bwq_dm_run: prepare lowers the batch on the host and uploads the program (it
+ * stays resident in HBM inside the ctx); execute runs the kernels and returns the values, and may
+ * be repeated.  bwq_dm_run == prepare + execute. */
+int bwq_dm_prepare(bwq_ctx* ctx, const bwq_batch* batch, int32_t* out_status);
+int bwq_dm_execute(bwq_ctx* ctx, double* out_vals);
+int bwq_dm_execute_device_out(bwq_ctx* ctx, double* d_out_vals);
 /* Ideal values: statevector evolution, noise table ignored (qiskit.primitives.Estimator,
  * shots=None; docs/tutorials/h13_ising_data_gen_tomo.ipynb:811). */
 int bwq_sv_run(bwq_ctx* ctx, const bwq_batch* batch, double* out_vals, int32_t* out_status);
+int bwq_sv_prepare(bwq_ctx* ctx, const bwq_batch* batch, int32_t* out_status);
+int bwq_sv_execute(bwq_ctx* ctx, double* out_vals);
 /* Same as bwq_dm_run / bwq_sv_run but out_vals is a DEVICE pointer (e.g. a torch tensor's
  * data_ptr()) -- zero-copy label hand-off; returns after the work is enqueued and synchronised. */
 int bwq_dm_run_device_out(bwq_ctx* ctx, const bwq_batch* batch, double* d_out_vals, int32_t* out_status);
@@ -161,7 +170,8 @@ void bwq_program_free(bwq_program* p);
 int bwq_program_sizes(const bwq_program* p, int64_t sizes[8]);
 /* Copies the program out.  active_qubits[n_active] (physical qubit of digit d);
  * sweeps: per sweep 10 int32 {pass_begin, pos[0..7], pass_end}; passes: per pass 3 int32
- * {slot_a, slot_b, op_end}; ops: per op 2 int64 {kind | (table_flag << 8), data_off};
+ * {slot_a, slot_b, op_end}; ops: per macro-op 6 int64 {pre_a, pre_b, twoq, off_a, off_b, off_2}
+ * (kinds: ml_qem_b200/csrc/program.h);
  * mats[n_mats]; term_index[n_terms] (element index, -1 = term vanishes); term_coeff. */
 int bwq_program_read(const bwq_program* p, int32_t* active_qubits, int32_t* sweeps,
                      int32_t* passes, int64_t* ops, double* mats, int64_t* term_index,

@@ -73,6 +73,37 @@ struct Blob {
 
 }  // namespace
 
+struct DmChunk {
+  int first = 0, count = 0, nd = 0, kq = 0;
+  bool full = false;
+  std::vector<int> live;  // circuits that still have a sweep s, per sweep index
+};
+struct DmPlan {
+  bool valid = false;
+  int tile_qubits = 6;
+  int64_t n_obs = 0;
+  size_t o_range = 0, o_sweeps = 0, o_passes = 0, o_ops = 0, o_mats = 0, o_tidx = 0, o_tcoef = 0, o_obs = 0, blob_bytes = 0;
+  std::vector<int64_t> ob_off;
+  std::vector<DmChunk> chunks;
+  std::vector<std::pair<int64_t, double>> host_fix;
+  int64_t max_chunk_bytes = 0, n_gates = 0, n_passes = 0;
+  double lower_ms = 0, h2d_ms = 0;
+};
+
+struct SvGroup {
+  int first = 0, count = 0, nb = 0, per_launch = 0;
+  size_t smem = 0;
+  int64_t stride = 0;
+};
+struct SvPlan {
+  bool valid = false;
+  int64_t n_obs = 0, n_gates = 0;
+  size_t o_cd = 0, o_ops = 0, o_mats = 0, o_obs = 0, o_tx = 0, o_tz = 0, o_tny = 0, o_tc = 0, blob_bytes = 0;
+  std::vector<SvGroup> groups;
+  std::vector<int64_t> nan_obs;
+  double lower_ms = 0, h2d_ms = 0;
+};
+
 struct bwq_ctx {
   int device = 0;
   cudaStream_t stream = nullptr;
@@ -80,9 +111,12 @@ struct bwq_ctx {
   std::string error;
   bwq_options opt{};
   NoiseTable noise;
-  DevBuf d_noise, d_prog, d_states, d_out, d_scratch;
-  PinBuf h_prog, h_out;
+  DevBuf d_noise, d_prog, d_sv_prog, d_states, d_out, d_scratch;
+  PinBuf h_prog, h_sv_prog, h_out;
   bwq_stats stats{};
+  DmPlan plan;
+  SvPlan sv_plan;
+  std::vector<cudaEvent_t> chunk_ev;  // begin/end of each chunk's sweep launches
   size_t smem_optin = 0;
   int sm_count = 0;
 };
@@ -133,6 +167,9 @@ extern "C" int bwq_create(int device, bwq_ctx** out) {
   if ((e = cudaStreamCreateWithFlags(&ctx->stream, cudaStreamNonBlocking)) != cudaSuccess) return bail(e, "cudaStreamCreate");
   for (auto& ev : ctx->ev)
     if ((e = cudaEventCreate(&ev)) != cudaSuccess) return bail(e, "cudaEventCreate");
+  ctx->chunk_ev.resize(128);
+  for (auto& ev : ctx->chunk_ev)
+    if ((e = cudaEventCreate(&ev)) != cudaSuccess) return bail(e, "cudaEventCreate");
   cudaDeviceProp prop;
   if ((e = cudaGetDeviceProperties(&prop, device)) != cudaSuccess) return bail(e, "cudaGetDeviceProperties");
   ctx->smem_optin = prop.sharedMemPerBlockOptin;
@@ -153,7 +190,9 @@ extern "C" int bwq_destroy(bwq_ctx* ctx) {
   cudaStreamSynchronize(ctx->stream);
   ctx->d_noise.release(); ctx->d_prog.release(); ctx->d_states.release(); ctx->d_out.release();
   ctx->d_scratch.release(); ctx->h_prog.release(); ctx->h_out.release();
+  ctx->d_sv_prog.release(); ctx->h_sv_prog.release();
   for (auto& ev : ctx->ev) if (ev) cudaEventDestroy(ev);
+  for (auto& ev : ctx->chunk_ev) if (ev) cudaEventDestroy(ev);
   if (ctx->stream) cudaStreamDestroy(ctx->stream);
   delete ctx;
   return BWQ_OK;
@@ -250,36 +289,39 @@ template <bool FULL> static cudaError_t launch_sweep_kq(int kq, const DmLaunch& 
 }
 
 // ------------------------------------------------------------------------------------------------
-// density-matrix run
+// density-matrix run = prepare (K0 lowering on host threads + one H2D of the program) + execute
+// (sweeps, expectation values, D2H of the values).  The prepared plan stays in the ctx so that
+// bwq_dm_execute can be repeated with the program resident in HBM.
 // ------------------------------------------------------------------------------------------------
-static int dm_run_impl(bwq_ctx* ctx, const bwq_batch* b, double* out_vals, bool out_on_device, int32_t* out_status) {
+static int dm_prepare_impl(bwq_ctx* ctx, const bwq_batch* b, int32_t* out_status) {
   if (!ctx) return BWQ_ERR_ARG;
-  int rc = check_batch(ctx, b, out_vals, out_status);
+  int rc = check_batch(ctx, b, out_status, out_status);
   if (rc) return rc;
+  DmPlan& P = ctx->plan;
+  P = DmPlan();
   ctx->stats = bwq_stats{};
   const int N = b->n_circuits;
+  P.n_obs = N ? b->obs_offsets[N] : 0;
+  P.valid = true;
   if (N == 0) return BWQ_OK;
   CK(cudaSetDevice(ctx->device));
-  const int64_t n_obs = b->obs_offsets[N];
 
   // ---- K0: lowering (host threads)
   double t0 = now_ms();
   LowerOptions lo;
   lo.tile_qubits = ctx->opt.tile_qubits ? ctx->opt.tile_qubits : 6;
-  lo.low_qubits = ctx->opt.low_qubits ? ctx->opt.low_qubits : 2;
-  if (ctx->opt.low_qubits < 0) lo.low_qubits = 0;
+  lo.low_qubits = ctx->opt.low_qubits > 0 ? ctx->opt.low_qubits : 2;
+  P.tile_qubits = lo.tile_qubits;
   std::vector<CircuitProgram> progs(N);
   parallel_for(N, host_threads(ctx), [&](int c) { lower_dm_circuit(ctx->noise, *b, c, lo, &progs[c]); });
 
-  // host-evaluated circuits: failures, and circuits without any gate (state stays |0..0>)
-  std::vector<double> host_vals;  // only used for those
   std::vector<int> order;
   order.reserve(N);
   for (int c = 0; c < N; ++c) {
     out_status[c] = progs[c].status;
     if (progs[c].status == 0 && !progs[c].sweeps.empty()) order.push_back(c);
   }
-  // sort: wide first, then by sweep count (so a chunk's circuits finish together)
+  // wide first, then by sweep count (so the circuits of a chunk finish together)
   std::sort(order.begin(), order.end(), [&](int a, int c) {
     if (progs[a].n_digits != progs[c].n_digits) return progs[a].n_digits > progs[c].n_digits;
     if (progs[a].sweeps.size() != progs[c].sweeps.size()) return progs[a].sweeps.size() > progs[c].sweeps.size();
@@ -287,8 +329,9 @@ static int dm_run_impl(bwq_ctx* ctx, const bwq_batch* b, double* out_vals, bool 
   });
   const int M = (int)order.size();
 
-  // ---- merge programs into one blob (sorted order)
-  std::vector<int64_t> sw_off(M + 1, 0), ps_off(M + 1, 0), op_off(M + 1, 0), mt_off(M + 1, 0), tm_off(M + 1, 0), ob_off(M + 1, 0);
+  // ---- merge the programs into one blob (sorted order)
+  std::vector<int64_t> sw_off(M + 1, 0), ps_off(M + 1, 0), op_off(M + 1, 0), mt_off(M + 1, 0), tm_off(M + 1, 0);
+  P.ob_off.assign(M + 1, 0);
   for (int i = 0; i < M; ++i) {
     const CircuitProgram& p = progs[order[i]];
     sw_off[i + 1] = sw_off[i] + (int64_t)p.sweeps.size();
@@ -296,19 +339,23 @@ static int dm_run_impl(bwq_ctx* ctx, const bwq_batch* b, double* out_vals, bool 
     op_off[i + 1] = op_off[i] + (int64_t)p.ops.size();
     mt_off[i + 1] = mt_off[i] + (int64_t)p.mats.size();
     tm_off[i + 1] = tm_off[i] + (int64_t)p.term_index.size();
-    ob_off[i + 1] = ob_off[i] + (b->obs_offsets[order[i] + 1] - b->obs_offsets[order[i]]);
+    P.ob_off[i + 1] = P.ob_off[i] + (b->obs_offsets[order[i] + 1] - b->obs_offsets[order[i]]);
   }
   if (ps_off[M] > INT32_MAX || op_off[M] > INT32_MAX || sw_off[M] > INT32_MAX)
     return fail(ctx, BWQ_ERR_ARG, "batch too large for 32-bit program indices; split the batch");
+  // matrix buffer = [noise table | per-circuit matrices], one base pointer for the kernels
+  const int64_t noise_n = ((int64_t)ctx->noise.data.size() + 31) & ~int64_t(31);
+  if (noise_n + mt_off[M] >= (int64_t(1) << 31)) return fail(ctx, BWQ_ERR_ARG, "batch matrices exceed 2^31 doubles; split the batch");
   Blob blob;
-  const size_t o_range = blob.add(sizeof(int32_t) * 2 * (size_t)M);
-  const size_t o_sweeps = blob.add(sizeof(SweepDesc) * (size_t)sw_off[M]);
-  const size_t o_passes = blob.add(sizeof(PassDesc) * (size_t)ps_off[M]);
-  const size_t o_ops = blob.add(sizeof(DevOp) * (size_t)op_off[M]);
-  const size_t o_mats = blob.add(sizeof(double) * (size_t)mt_off[M]);
-  const size_t o_tidx = blob.add(sizeof(int64_t) * (size_t)tm_off[M]);
-  const size_t o_tcoef = blob.add(sizeof(double) * (size_t)tm_off[M]);
-  const size_t o_obs = blob.add(sizeof(int64_t) * 4 * (size_t)ob_off[M]);
+  P.o_range = blob.add(sizeof(int32_t) * 2 * (size_t)M);
+  P.o_sweeps = blob.add(sizeof(SweepDesc) * (size_t)sw_off[M]);
+  P.o_passes = blob.add(sizeof(PassDesc) * (size_t)ps_off[M]);
+  P.o_ops = blob.add(sizeof(MacroOp) * (size_t)op_off[M]);
+  P.o_mats = blob.add(sizeof(double) * (size_t)(noise_n + mt_off[M]));
+  P.o_tidx = blob.add(sizeof(int64_t) * (size_t)tm_off[M]);
+  P.o_tcoef = blob.add(sizeof(double) * (size_t)tm_off[M]);
+  P.o_obs = blob.add(sizeof(int64_t) * 4 * (size_t)P.ob_off[M]);
+  P.blob_bytes = blob.total;
   if (M > 0) {
     CK(ctx->h_prog.reserve(blob.total));
     CK(ctx->d_prog.reserve(blob.total));
@@ -317,53 +364,53 @@ static int dm_run_impl(bwq_ctx* ctx, const bwq_batch* b, double* out_vals, bool 
   parallel_for(M, host_threads(ctx), [&](int i) {
     const int c = order[i];
     const CircuitProgram& p = progs[c];
-    int32_t* range = (int32_t*)(hb + o_range) + 2 * i;
+    int32_t* range = (int32_t*)(hb + P.o_range) + 2 * i;
     range[0] = (int32_t)sw_off[i];
     range[1] = (int32_t)sw_off[i + 1];
-    SweepDesc* sw = (SweepDesc*)(hb + o_sweeps) + sw_off[i];
+    SweepDesc* sw = (SweepDesc*)(hb + P.o_sweeps) + sw_off[i];
     for (size_t k = 0; k < p.sweeps.size(); ++k) {
       sw[k] = p.sweeps[k];
       sw[k].pass_begin += (int32_t)ps_off[i];
       sw[k].pass_end += (int32_t)ps_off[i];
     }
-    PassDesc* ps = (PassDesc*)(hb + o_passes) + ps_off[i];
+    PassDesc* ps = (PassDesc*)(hb + P.o_passes) + ps_off[i];
     for (size_t k = 0; k < p.passes.size(); ++k) {
       ps[k] = p.passes[k];
       ps[k].op_begin += (int32_t)op_off[i];
       ps[k].op_end += (int32_t)op_off[i];
     }
-    DevOp* ops = (DevOp*)(hb + o_ops) + op_off[i];
+    MacroOp* ops = (MacroOp*)(hb + P.o_ops) + op_off[i];
+    const uint32_t rel = (uint32_t)(noise_n + mt_off[i]);
+    auto fix = [&](uint32_t off) { return (off & kLocalMat) ? (off & ~kLocalMat) + rel : off; };
     for (size_t k = 0; k < p.ops.size(); ++k) {
       ops[k] = p.ops[k];
-      if (ops[k].src == 0) ops[k].off += mt_off[i];
+      ops[k].off_a = fix(ops[k].off_a); ops[k].off_b = fix(ops[k].off_b); ops[k].off_2 = fix(ops[k].off_2);
     }
-    if (!p.mats.empty()) std::memcpy((double*)(hb + o_mats) + mt_off[i], p.mats.data(), p.mats.size() * sizeof(double));
+    if (!p.mats.empty()) std::memcpy((double*)(hb + P.o_mats) + noise_n + mt_off[i], p.mats.data(), p.mats.size() * sizeof(double));
     if (!p.term_index.empty()) {
-      std::memcpy((int64_t*)(hb + o_tidx) + tm_off[i], p.term_index.data(), p.term_index.size() * sizeof(int64_t));
-      std::memcpy((double*)(hb + o_tcoef) + tm_off[i], p.term_coeff.data(), p.term_coeff.size() * sizeof(double));
+      std::memcpy((int64_t*)(hb + P.o_tidx) + tm_off[i], p.term_index.data(), p.term_index.size() * sizeof(int64_t));
+      std::memcpy((double*)(hb + P.o_tcoef) + tm_off[i], p.term_coeff.data(), p.term_coeff.size() * sizeof(double));
     }
-    // observables: {term_begin, term_end, slot (filled per chunk = sorted index), out_index}
-    int64_t* od = (int64_t*)(hb + o_obs) + 4 * ob_off[i];
+    // observables: {term_begin, term_end, chunk-local slot (filled below), out_index}
+    int64_t* od = (int64_t*)(hb + P.o_obs) + 4 * P.ob_off[i];
     const int64_t ob0 = b->obs_offsets[c], ob1 = b->obs_offsets[c + 1];
     const int64_t tb = b->term_offsets[ob0];
     for (int64_t o = ob0; o < ob1; ++o) {
       int64_t* d = od + 4 * (o - ob0);
       d[0] = tm_off[i] + (b->term_offsets[o] - tb);
       d[1] = tm_off[i] + (b->term_offsets[o + 1] - tb);
-      d[2] = i;  // rewritten to the chunk-local slot below
+      d[2] = i;
       d[3] = o;
     }
   });
-  for (int i = 0; i < M; ++i) { ctx->stats.n_gates += progs[order[i]].n_gates; ctx->stats.n_passes += (int64_t)progs[order[i]].passes.size(); }
-  ctx->stats.lower_ms = now_ms() - t0;
+  if (M > 0 && !ctx->noise.data.empty()) std::memcpy(hb + P.o_mats, ctx->noise.data.data(), ctx->noise.data.size() * sizeof(double));
+  for (int i = 0; i < M; ++i) { P.n_gates += progs[order[i]].n_gates; P.n_passes += (int64_t)progs[order[i]].passes.size(); }
 
   // ---- chunk plan: circuits of equal width, as many resident states as the budget allows
   size_t free_b = 0, total_b = 0;
   CK(cudaMemGetInfo(&free_b, &total_b));
   int64_t budget = ctx->opt.max_state_bytes > 0 ? ctx->opt.max_state_bytes
                                                  : (int64_t)((free_b + ctx->d_states.cap) * 0.8);
-  struct Chunk { int first, count, nd; };
-  std::vector<Chunk> chunks;
   for (int i = 0; i < M;) {
     const int nd = progs[order[i]].n_digits;
     const int64_t sbytes = (int64_t)sizeof(double) << (2 * nd);
@@ -375,135 +422,185 @@ static int dm_run_impl(bwq_ctx* ctx, const bwq_batch* b, double* out_vals, bool 
       continue;
     }
     if (ctx->opt.chunk_circuits > 0) fit = std::min<int64_t>(fit, ctx->opt.chunk_circuits);
-    const int kq = std::min(std::min(nd, lo.tile_qubits), kMaxTileQubits);
+    const int kq = std::min(std::min(nd, std::max(lo.tile_qubits, 3)), kMaxTileQubits);
     const int64_t tiles = int64_t(1) << (2 * (nd - kq));
     fit = std::min<int64_t>(fit, (int64_t(1) << 30) / tiles);  // grid.x limit
     int j = i;
     while (j < M && progs[order[j]].n_digits == nd && j - i < fit) ++j;
-    chunks.push_back({i, j - i, nd});
+    DmChunk ch;
+    ch.first = i; ch.count = j - i; ch.nd = nd; ch.kq = kq;
+    // circuits are sorted by sweep count (descending) inside a width group, so sweep s only needs
+    // the leading circuits that still have an s-th sweep
+    const size_t max_sweeps = progs[order[i]].sweeps.size();
+    int live = ch.count;
+    for (size_t sidx = 0; sidx < max_sweeps; ++sidx) {
+      while (live > 0 && progs[order[i + live - 1]].sweeps.size() <= sidx) --live;
+      ch.live.push_back(live);
+    }
+    for (int k = i; k < j; ++k) ch.full = ch.full || progs[order[k]].needs_dense;
+    P.chunks.push_back(std::move(ch));
     i = j;
   }
-  int64_t max_chunk_bytes = 0;
-  for (auto& ch : chunks) max_chunk_bytes = std::max(max_chunk_bytes, ((int64_t)sizeof(double) << (2 * ch.nd)) * ch.count);
-  // chunk-local slots for the observables
-  for (auto& ch : chunks)
+  for (auto& ch : P.chunks) {
+    P.max_chunk_bytes = std::max(P.max_chunk_bytes, ((int64_t)sizeof(double) << (2 * ch.nd)) * ch.count);
     for (int i = ch.first; i < ch.first + ch.count; ++i) {
-      int64_t* od = (int64_t*)(hb + o_obs) + 4 * ob_off[i];
-      for (int64_t k = 0; k < ob_off[i + 1] - ob_off[i]; ++k) od[4 * k + 2] = i - ch.first;
+      int64_t* od = (int64_t*)(hb + P.o_obs) + 4 * P.ob_off[i];
+      for (int64_t k = 0; k < P.ob_off[i + 1] - P.ob_off[i]; ++k) od[4 * k + 2] = i - ch.first;
     }
-
-  // ---- device: upload, sweeps, expectation values
-  double* d_out = nullptr;
-  if (out_on_device) d_out = out_vals;
-  else if (n_obs > 0) {
-    CK(ctx->d_out.reserve(sizeof(double) * (size_t)n_obs));
-    CK(ctx->h_out.reserve(sizeof(double) * (size_t)n_obs));
-    d_out = (double*)ctx->d_out.p;
   }
-  if (max_chunk_bytes > 0) CK(ctx->d_states.reserve((size_t)max_chunk_bytes));
+  // circuits the GPU does not touch: failures (NaN) and circuits without any gate (state stays
+  // |0..0>: <P> = 1 for I/Z strings, 0 otherwise)
+  for (int c = 0; c < N; ++c) {
+    const bool gpu = out_status[c] == 0 && !progs[c].sweeps.empty();
+    if (gpu) continue;
+    for (int64_t o = b->obs_offsets[c]; o < b->obs_offsets[c + 1]; ++o) {
+      double v = 0.0;
+      if (out_status[c] == 0)
+        for (int64_t t = b->term_offsets[o]; t < b->term_offsets[o + 1]; ++t)
+          if (b->term_x[t] == 0) v += b->term_coeff[t];
+      P.host_fix.push_back({o, out_status[c] == 0 ? v : std::nan("")});
+    }
+  }
+  P.lower_ms = now_ms() - t0;
+
+  // ---- upload
+  if (P.max_chunk_bytes > 0) CK(ctx->d_states.reserve((size_t)P.max_chunk_bytes));
+  if (P.n_obs > 0) {
+    CK(ctx->d_out.reserve(sizeof(double) * (size_t)P.n_obs));
+    CK(ctx->h_out.reserve(sizeof(double) * (size_t)P.n_obs));
+  }
   cudaStream_t st = ctx->stream;
   CK(cudaEventRecord(ctx->ev[0], st));
   if (M > 0) CK(cudaMemcpyAsync(ctx->d_prog.p, hb, blob.total, cudaMemcpyHostToDevice, st));
-  if (n_obs > 0) CK(cudaMemsetAsync(d_out, 0, sizeof(double) * (size_t)n_obs, st));
   CK(cudaEventRecord(ctx->ev[1], st));
+  CK(cudaStreamSynchronize(st));
+  float ms = 0.f;
+  CK(cudaEventElapsedTime(&ms, ctx->ev[0], ctx->ev[1]));
+  P.h2d_ms = ms;
+  ctx->stats.lower_ms = P.lower_ms;
+  ctx->stats.h2d_ms = P.h2d_ms;
+  ctx->stats.h2d_bytes = (int64_t)P.blob_bytes;
+  ctx->stats.n_gates = P.n_gates;
+  ctx->stats.n_passes = P.n_passes;
+  return BWQ_OK;
+}
+
+static int dm_execute_impl(bwq_ctx* ctx, double* out_vals, bool out_on_device) {
+  if (!ctx || !out_vals) return BWQ_ERR_ARG;
+  DmPlan& P = ctx->plan;
+  if (!P.valid) return fail(ctx, BWQ_ERR_ARG, "bwq_dm_execute: no prepared batch (call bwq_dm_prepare first)");
+  CK(cudaSetDevice(ctx->device));
+  bwq_stats& S = ctx->stats;
+  S = bwq_stats{};
+  S.lower_ms = P.lower_ms; S.h2d_ms = P.h2d_ms; S.h2d_bytes = (int64_t)P.blob_bytes;
+  S.n_gates = P.n_gates; S.n_passes = P.n_passes;
+  cudaStream_t st = ctx->stream;
+  double* d_out = out_on_device ? out_vals : (double*)ctx->d_out.p;
   const char* db = (const char*)ctx->d_prog.p;
-  float sweep_ms_total = 0.f;
-  for (auto& ch : chunks) {
-    const int kq = std::min(std::min(ch.nd, lo.tile_qubits), kMaxTileQubits);
+  CK(cudaEventRecord(ctx->ev[1], st));
+  if (P.n_obs > 0) CK(cudaMemsetAsync(d_out, 0, sizeof(double) * (size_t)P.n_obs, st));
+  const size_t n_ev = std::min(P.chunks.size(), ctx->chunk_ev.size() / 2);
+  for (size_t ci = 0; ci < P.chunks.size(); ++ci) {
+    const DmChunk& ch = P.chunks[ci];
     DmLaunch L;
     L.states = (double*)ctx->d_states.p;
     L.stride = int64_t(1) << (2 * ch.nd);
     L.n_digits = ch.nd;
     L.first_circuit = ch.first;
-    L.sweep_range = (const int32_t*)(db + o_range);
-    L.sweeps = (const SweepDesc*)(db + o_sweeps);
-    L.passes = (const PassDesc*)(db + o_passes);
-    L.ops = (const DevOp*)(db + o_ops);
-    L.mats = (const double*)(db + o_mats);
-    L.noise = (const double*)ctx->d_noise.p;
-    const int64_t tiles = int64_t(1) << (2 * (ch.nd - kq));
-    // circuits are sorted by sweep count (descending) inside a width group, so sweep s only needs
-    // the leading circuits that still have an s-th sweep
-    size_t max_sweeps = progs[order[ch.first]].sweeps.size();
-    bool full = false;
-    for (int i = ch.first; i < ch.first + ch.count; ++i) full = full || progs[order[i]].needs_dense;
-    int live = ch.count;
-    for (size_t s = 0; s < max_sweeps; ++s) {
-      while (live > 0 && progs[order[ch.first + live - 1]].sweeps.size() <= s) --live;
-      CK(full ? launch_sweep_kq<true>(kq, L, (int)s, tiles * live, st) : launch_sweep_kq<false>(kq, L, (int)s, tiles * live, st));
-      ctx->stats.n_sweep_launches++;
-      ctx->stats.n_state_sweeps += live;
-      ctx->stats.state_bytes_swept += 2 * (int64_t)sizeof(double) * L.stride * live;
+    L.sweep_range = (const int32_t*)(db + P.o_range);
+    L.sweeps = (const SweepDesc*)(db + P.o_sweeps);
+    L.passes = (const PassDesc*)(db + P.o_passes);
+    L.ops = (const MacroOp*)(db + P.o_ops);
+    L.mats = (const double*)(db + P.o_mats);
+    const int64_t tiles = int64_t(1) << (2 * (ch.nd - ch.kq));
+    if (ci < n_ev) CK(cudaEventRecord(ctx->chunk_ev[2 * ci], st));
+    for (size_t sidx = 0; sidx < ch.live.size(); ++sidx) {
+      const int live = ch.live[sidx];
+      CK(ch.full ? launch_sweep_kq<true>(ch.kq, L, (int)sidx, tiles * live, st)
+                 : launch_sweep_kq<false>(ch.kq, L, (int)sidx, tiles * live, st));
+      S.n_sweep_launches++;
+      S.n_state_sweeps += live;
+      S.state_bytes_swept += 2 * (int64_t)sizeof(double) * L.stride * live;
     }
-    const int64_t nob = ob_off[ch.first + ch.count] - ob_off[ch.first];
+    if (ci < n_ev) CK(cudaEventRecord(ctx->chunk_ev[2 * ci + 1], st));
+    const int64_t nob = P.ob_off[ch.first + ch.count] - P.ob_off[ch.first];
     if (nob > 0) {
       ExpvalLaunch E;
       E.states = L.states;
       E.stride = L.stride;
       E.n_obs = (int32_t)nob;
-      E.obs_desc = (const int64_t*)(db + o_obs) + 4 * ob_off[ch.first];
-      E.term_index = (const int64_t*)(db + o_tidx);
-      E.term_coeff = (const double*)(db + o_tcoef);
+      E.obs_desc = (const int64_t*)(db + P.o_obs) + 4 * P.ob_off[ch.first];
+      E.term_index = (const int64_t*)(db + P.o_tidx);
+      E.term_coeff = (const double*)(db + P.o_tcoef);
       E.out = d_out;
       const int wpb = 8;
       dm_expval_kernel<<<(unsigned)((nob + wpb - 1) / wpb), wpb * 32, 0, st>>>(E);
       CK(cudaGetLastError());
-      ctx->stats.n_other_launches++;
+      S.n_other_launches++;
     }
   }
   CK(cudaEventRecord(ctx->ev[2], st));
-  if (!out_on_device && n_obs > 0)
-    CK(cudaMemcpyAsync(ctx->h_out.p, d_out, sizeof(double) * (size_t)n_obs, cudaMemcpyDeviceToHost, st));
+  if (!out_on_device && P.n_obs > 0) {
+    CK(cudaMemcpyAsync(ctx->h_out.p, d_out, sizeof(double) * (size_t)P.n_obs, cudaMemcpyDeviceToHost, st));
+    S.d2h_bytes = (int64_t)sizeof(double) * P.n_obs;
+  }
   CK(cudaEventRecord(ctx->ev[3], st));
   CK(cudaStreamSynchronize(st));
   float ms = 0.f;
-  CK(cudaEventElapsedTime(&ms, ctx->ev[0], ctx->ev[1])); ctx->stats.h2d_ms = ms;
-  CK(cudaEventElapsedTime(&ms, ctx->ev[1], ctx->ev[2])); ctx->stats.kernel_ms = ms;
-  CK(cudaEventElapsedTime(&ms, ctx->ev[2], ctx->ev[3])); ctx->stats.d2h_ms = ms;
-  ctx->stats.sweep_kernel_ms = sweep_ms_total > 0 ? sweep_ms_total : ctx->stats.kernel_ms;
-
-  // ---- host-evaluated circuits: no gates at all => |0..0>: <P> = 1 for I/Z strings else 0
-  std::vector<std::pair<int64_t, double>> host_fix;
-  for (int c = 0; c < N; ++c) {
-    const bool gpu = out_status[c] == 0 && !progs[c].sweeps.empty();
-    if (gpu) continue;
-    const int64_t ob0 = b->obs_offsets[c], ob1 = b->obs_offsets[c + 1];
-    for (int64_t o = ob0; o < ob1; ++o) {
-      double v = 0.0;
-      if (out_status[c] == 0)
-        for (int64_t t = b->term_offsets[o]; t < b->term_offsets[o + 1]; ++t)
-          if (b->term_x[t] == 0) v += b->term_coeff[t];
-      host_fix.push_back({o, out_status[c] == 0 ? v : std::nan("")});
+  CK(cudaEventElapsedTime(&ms, ctx->ev[1], ctx->ev[2])); S.kernel_ms = ms;
+  CK(cudaEventElapsedTime(&ms, ctx->ev[2], ctx->ev[3])); S.d2h_ms = ms;
+  if (n_ev == P.chunks.size()) {
+    double tot = 0;
+    for (size_t ci = 0; ci < n_ev; ++ci) {
+      CK(cudaEventElapsedTime(&ms, ctx->chunk_ev[2 * ci], ctx->chunk_ev[2 * ci + 1]));
+      tot += ms;
     }
+    S.sweep_kernel_ms = tot;
+  } else {
+    S.sweep_kernel_ms = S.kernel_ms;
   }
   if (!out_on_device) {
-    if (n_obs > 0) std::memcpy(out_vals, ctx->h_out.p, sizeof(double) * (size_t)n_obs);
-    for (auto& f : host_fix) out_vals[f.first] = f.second;
+    if (P.n_obs > 0) std::memcpy(out_vals, ctx->h_out.p, sizeof(double) * (size_t)P.n_obs);
+    for (auto& f : P.host_fix) out_vals[f.first] = f.second;
   } else {
-    for (auto& f : host_fix) CK(cudaMemcpy(out_vals + f.first, &f.second, sizeof(double), cudaMemcpyHostToDevice));
+    for (auto& f : P.host_fix) CK(cudaMemcpy(out_vals + f.first, &f.second, sizeof(double), cudaMemcpyHostToDevice));
   }
   return BWQ_OK;
 }
 
+extern "C" int bwq_dm_prepare(bwq_ctx* ctx, const bwq_batch* b, int32_t* out_status) {
+  if (!out_status) return fail(ctx, BWQ_ERR_ARG, "null status");
+  return dm_prepare_impl(ctx, b, out_status);
+}
+extern "C" int bwq_dm_execute(bwq_ctx* ctx, double* out_vals) { return dm_execute_impl(ctx, out_vals, false); }
+extern "C" int bwq_dm_execute_device_out(bwq_ctx* ctx, double* d_out_vals) { return dm_execute_impl(ctx, d_out_vals, true); }
+
 extern "C" int bwq_dm_run(bwq_ctx* ctx, const bwq_batch* b, double* out_vals, int32_t* out_status) {
-  return dm_run_impl(ctx, b, out_vals, false, out_status);
+  if (!out_vals || !out_status) return fail(ctx, BWQ_ERR_ARG, "null out/status");
+  int rc = dm_prepare_impl(ctx, b, out_status);
+  return rc ? rc : dm_execute_impl(ctx, out_vals, false);
 }
 extern "C" int bwq_dm_run_device_out(bwq_ctx* ctx, const bwq_batch* b, double* d_out_vals, int32_t* out_status) {
-  return dm_run_impl(ctx, b, d_out_vals, true, out_status);
+  if (!d_out_vals || !out_status) return fail(ctx, BWQ_ERR_ARG, "null out/status");
+  int rc = dm_prepare_impl(ctx, b, out_status);
+  return rc ? rc : dm_execute_impl(ctx, d_out_vals, true);
 }
 
 // ------------------------------------------------------------------------------------------------
 // statevector run (ideal labels)
 // ------------------------------------------------------------------------------------------------
-extern "C" int bwq_sv_run(bwq_ctx* ctx, const bwq_batch* b, double* out_vals, int32_t* out_status) {
+static int sv_prepare_impl(bwq_ctx* ctx, const bwq_batch* b, int32_t* out_status) {
   if (!ctx) return BWQ_ERR_ARG;
-  int rc = check_batch(ctx, b, out_vals, out_status);
+  int rc = check_batch(ctx, b, out_status, out_status);
   if (rc) return rc;
+  SvPlan& P = ctx->sv_plan;
+  P = SvPlan();
   ctx->stats = bwq_stats{};
   const int N = b->n_circuits;
+  P.n_obs = N ? b->obs_offsets[N] : 0;
+  P.valid = true;
   if (N == 0) return BWQ_OK;
   CK(cudaSetDevice(ctx->device));
-  const int64_t n_obs = b->obs_offsets[N];
   double t0 = now_ms();
   std::vector<SvProgram> progs(N);
   parallel_for(N, host_threads(ctx), [&](int c) { lower_sv_circuit(*b, c, &progs[c]); });
@@ -513,6 +610,7 @@ extern "C" int bwq_sv_run(bwq_ctx* ctx, const bwq_batch* b, double* out_vals, in
     if (progs[c].status == 0 && progs[c].n_bits > kSimpleMaxBits) progs[c].status = BWQ_CIRC_TOO_WIDE;
     out_status[c] = progs[c].status;
     if (progs[c].status == 0) order.push_back(c);
+    else for (int64_t o = b->obs_offsets[c]; o < b->obs_offsets[c + 1]; ++o) P.nan_obs.push_back(o);
   }
   std::sort(order.begin(), order.end(), [&](int a, int c) {
     if (progs[a].n_bits != progs[c].n_bits) return progs[a].n_bits > progs[c].n_bits;
@@ -526,40 +624,41 @@ extern "C" int bwq_sv_run(bwq_ctx* ctx, const bwq_batch* b, double* out_vals, in
     mt_off[i + 1] = mt_off[i] + (int64_t)p.mats.size();
     tm_off[i + 1] = tm_off[i] + (int64_t)p.term_coeff.size();
     ob_off[i + 1] = ob_off[i] + (b->obs_offsets[order[i] + 1] - b->obs_offsets[order[i]]);
-    ctx->stats.n_gates += p.n_gates;
+    P.n_gates += p.n_gates;
   }
   if (op_off[M] > INT32_MAX || ob_off[M] > INT32_MAX) return fail(ctx, BWQ_ERR_ARG, "batch too large; split it");
   Blob blob;
-  const size_t o_cd = blob.add(sizeof(int32_t) * 8 * (size_t)M);
-  const size_t o_ops = blob.add(sizeof(SvOp) * (size_t)op_off[M]);
-  const size_t o_mats = blob.add(sizeof(double) * (size_t)mt_off[M]);
-  const size_t o_obs = blob.add(sizeof(int64_t) * 4 * (size_t)ob_off[M]);
-  const size_t o_tx = blob.add(sizeof(uint32_t) * (size_t)tm_off[M]);
-  const size_t o_tz = blob.add(sizeof(uint32_t) * (size_t)tm_off[M]);
-  const size_t o_tny = blob.add(sizeof(int32_t) * (size_t)tm_off[M]);
-  const size_t o_tc = blob.add(sizeof(double) * (size_t)tm_off[M]);
+  P.o_cd = blob.add(sizeof(int32_t) * 8 * (size_t)M);
+  P.o_ops = blob.add(sizeof(SvOp) * (size_t)op_off[M]);
+  P.o_mats = blob.add(sizeof(double) * (size_t)mt_off[M]);
+  P.o_obs = blob.add(sizeof(int64_t) * 4 * (size_t)ob_off[M]);
+  P.o_tx = blob.add(sizeof(uint32_t) * (size_t)tm_off[M]);
+  P.o_tz = blob.add(sizeof(uint32_t) * (size_t)tm_off[M]);
+  P.o_tny = blob.add(sizeof(int32_t) * (size_t)tm_off[M]);
+  P.o_tc = blob.add(sizeof(double) * (size_t)tm_off[M]);
+  P.blob_bytes = blob.total;
   if (M > 0) {
-    CK(ctx->h_prog.reserve(blob.total));
-    CK(ctx->d_prog.reserve(blob.total));
+    CK(ctx->h_sv_prog.reserve(blob.total));
+    CK(ctx->d_sv_prog.reserve(blob.total));
   }
-  char* hb = (char*)ctx->h_prog.p;
+  char* hb = (char*)ctx->h_sv_prog.p;
   parallel_for(M, host_threads(ctx), [&](int i) {
     const int c = order[i];
     const SvProgram& p = progs[c];
-    int32_t* cd = (int32_t*)(hb + o_cd) + 8 * i;
+    int32_t* cd = (int32_t*)(hb + P.o_cd) + 8 * i;
     cd[0] = p.n_bits; cd[1] = (int32_t)op_off[i]; cd[2] = (int32_t)op_off[i + 1];
     cd[3] = (int32_t)ob_off[i]; cd[4] = (int32_t)ob_off[i + 1]; cd[5] = cd[6] = cd[7] = 0;
-    SvOp* ops = (SvOp*)(hb + o_ops) + op_off[i];
+    SvOp* ops = (SvOp*)(hb + P.o_ops) + op_off[i];
     for (size_t k = 0; k < p.ops.size(); ++k) { ops[k] = p.ops[k]; ops[k].off += mt_off[i]; }
-    if (!p.mats.empty()) std::memcpy((double*)(hb + o_mats) + mt_off[i], p.mats.data(), p.mats.size() * sizeof(double));
+    if (!p.mats.empty()) std::memcpy((double*)(hb + P.o_mats) + mt_off[i], p.mats.data(), p.mats.size() * sizeof(double));
     const size_t nt = p.term_coeff.size();
     if (nt) {
-      std::memcpy((uint32_t*)(hb + o_tx) + tm_off[i], p.term_x.data(), nt * sizeof(uint32_t));
-      std::memcpy((uint32_t*)(hb + o_tz) + tm_off[i], p.term_z.data(), nt * sizeof(uint32_t));
-      std::memcpy((int32_t*)(hb + o_tny) + tm_off[i], p.term_ny.data(), nt * sizeof(int32_t));
-      std::memcpy((double*)(hb + o_tc) + tm_off[i], p.term_coeff.data(), nt * sizeof(double));
+      std::memcpy((uint32_t*)(hb + P.o_tx) + tm_off[i], p.term_x.data(), nt * sizeof(uint32_t));
+      std::memcpy((uint32_t*)(hb + P.o_tz) + tm_off[i], p.term_z.data(), nt * sizeof(uint32_t));
+      std::memcpy((int32_t*)(hb + P.o_tny) + tm_off[i], p.term_ny.data(), nt * sizeof(int32_t));
+      std::memcpy((double*)(hb + P.o_tc) + tm_off[i], p.term_coeff.data(), nt * sizeof(double));
     }
-    int64_t* od = (int64_t*)(hb + o_obs) + 4 * ob_off[i];
+    int64_t* od = (int64_t*)(hb + P.o_obs) + 4 * ob_off[i];
     const int64_t ob0 = b->obs_offsets[c], ob1 = b->obs_offsets[c + 1];
     const int64_t tb = b->term_offsets[ob0];
     for (int64_t o = ob0; o < ob1; ++o) {
@@ -570,68 +669,102 @@ extern "C" int bwq_sv_run(bwq_ctx* ctx, const bwq_batch* b, double* out_vals, in
       d[3] = 0;
     }
   });
-  ctx->stats.lower_ms = now_ms() - t0;
-
-  if (n_obs > 0) {
-    CK(ctx->d_out.reserve(sizeof(double) * (size_t)n_obs));
-    CK(ctx->h_out.reserve(sizeof(double) * (size_t)n_obs));
-  }
-  double* d_out = (double*)ctx->d_out.p;
-  cudaStream_t st = ctx->stream;
-  CK(cudaEventRecord(ctx->ev[0], st));
-  if (M > 0) CK(cudaMemcpyAsync(ctx->d_prog.p, hb, blob.total, cudaMemcpyHostToDevice, st));
-  if (n_obs > 0) CK(cudaMemsetAsync(d_out, 0, sizeof(double) * (size_t)n_obs, st));
-  CK(cudaEventRecord(ctx->ev[1], st));
-  const char* db = (const char*)ctx->d_prog.p;
+  // launch groups: circuits of equal width
   constexpr int kSmemBits = 12;
+  int64_t scratch = 0;
   for (int i = 0; i < M;) {
     const int nb = progs[order[i]].n_bits;
     int j = i;
     while (j < M && progs[order[j]].n_bits == nb) ++j;
-    int per_launch = j - i;
-    size_t smem = 0;
-    int64_t stride = 0;
-    if (nb <= kSmemBits) smem = sizeof(double2) << nb;
+    SvGroup g;
+    g.first = i; g.count = j - i; g.nb = nb; g.per_launch = j - i;
+    if (nb <= kSmemBits) g.smem = sizeof(double2) << nb;
     else {
-      stride = int64_t(1) << nb;
-      per_launch = std::min(per_launch, std::max(1, std::min(4 * ctx->sm_count, (int)((int64_t(8) << 30) / (stride * 16)))));
-      CK(ctx->d_scratch.reserve(sizeof(double2) * (size_t)stride * per_launch));
+      g.stride = int64_t(1) << nb;
+      g.per_launch = std::min(g.per_launch, std::max(1, std::min(4 * ctx->sm_count, (int)((int64_t(8) << 30) / (g.stride * 16)))));
+      scratch = std::max(scratch, (int64_t)sizeof(double2) * g.stride * g.per_launch);
     }
-    for (int f = i; f < j; f += per_launch) {
-      SvLaunch L;
-      L.first_circuit = f;
-      L.n_circuits = std::min(per_launch, j - f);
-      L.circ_desc = (const int32_t*)(db + o_cd);
-      L.ops = (const SvOp*)(db + o_ops);
-      L.mats = (const double*)(db + o_mats);
-      L.obs_desc = (const int64_t*)(db + o_obs);
-      L.term_x = (const uint32_t*)(db + o_tx);
-      L.term_z = (const uint32_t*)(db + o_tz);
-      L.term_ny = (const int32_t*)(db + o_tny);
-      L.term_coeff = (const double*)(db + o_tc);
-      L.out = d_out;
-      L.scratch = (double2*)ctx->d_scratch.p;
-      L.scratch_stride = stride;
-      L.smem_bits = kSmemBits;
-      sv_circuit_kernel<<<L.n_circuits, kSvThreads, smem, st>>>(L);
-      CK(cudaGetLastError());
-      ctx->stats.n_other_launches++;
-    }
+    P.groups.push_back(g);
     i = j;
   }
+  P.lower_ms = now_ms() - t0;
+  if (scratch > 0) CK(ctx->d_scratch.reserve((size_t)scratch));
+  if (P.n_obs > 0) {
+    CK(ctx->d_out.reserve(sizeof(double) * (size_t)P.n_obs));
+    CK(ctx->h_out.reserve(sizeof(double) * (size_t)P.n_obs));
+  }
+  cudaStream_t st = ctx->stream;
+  CK(cudaEventRecord(ctx->ev[0], st));
+  if (M > 0) CK(cudaMemcpyAsync(ctx->d_sv_prog.p, hb, blob.total, cudaMemcpyHostToDevice, st));
+  CK(cudaEventRecord(ctx->ev[1], st));
+  CK(cudaStreamSynchronize(st));
+  float ms = 0.f;
+  CK(cudaEventElapsedTime(&ms, ctx->ev[0], ctx->ev[1]));
+  P.h2d_ms = ms;
+  ctx->stats.lower_ms = P.lower_ms; ctx->stats.h2d_ms = ms; ctx->stats.h2d_bytes = (int64_t)P.blob_bytes;
+  ctx->stats.n_gates = P.n_gates;
+  return BWQ_OK;
+}
+
+static int sv_execute_impl(bwq_ctx* ctx, double* out_vals) {
+  if (!ctx || !out_vals) return BWQ_ERR_ARG;
+  SvPlan& P = ctx->sv_plan;
+  if (!P.valid) return fail(ctx, BWQ_ERR_ARG, "bwq_sv_execute: no prepared batch (call bwq_sv_prepare first)");
+  CK(cudaSetDevice(ctx->device));
+  bwq_stats& S = ctx->stats;
+  S = bwq_stats{};
+  S.lower_ms = P.lower_ms; S.h2d_ms = P.h2d_ms; S.h2d_bytes = (int64_t)P.blob_bytes; S.n_gates = P.n_gates;
+  double* d_out = (double*)ctx->d_out.p;
+  cudaStream_t st = ctx->stream;
+  const char* db = (const char*)ctx->d_sv_prog.p;
+  CK(cudaEventRecord(ctx->ev[1], st));
+  if (P.n_obs > 0) CK(cudaMemsetAsync(d_out, 0, sizeof(double) * (size_t)P.n_obs, st));
+  for (const SvGroup& g : P.groups) {
+    for (int f = g.first; f < g.first + g.count; f += g.per_launch) {
+      SvLaunch L;
+      L.first_circuit = f;
+      L.n_circuits = std::min(g.per_launch, g.first + g.count - f);
+      L.circ_desc = (const int32_t*)(db + P.o_cd);
+      L.ops = (const SvOp*)(db + P.o_ops);
+      L.mats = (const double*)(db + P.o_mats);
+      L.obs_desc = (const int64_t*)(db + P.o_obs);
+      L.term_x = (const uint32_t*)(db + P.o_tx);
+      L.term_z = (const uint32_t*)(db + P.o_tz);
+      L.term_ny = (const int32_t*)(db + P.o_tny);
+      L.term_coeff = (const double*)(db + P.o_tc);
+      L.out = d_out;
+      L.scratch = (double2*)ctx->d_scratch.p;
+      L.scratch_stride = g.stride;
+      L.smem_bits = 12;
+      sv_circuit_kernel<<<L.n_circuits, kSvThreads, g.smem, st>>>(L);
+      CK(cudaGetLastError());
+      S.n_other_launches++;
+    }
+  }
   CK(cudaEventRecord(ctx->ev[2], st));
-  if (n_obs > 0) CK(cudaMemcpyAsync(ctx->h_out.p, d_out, sizeof(double) * (size_t)n_obs, cudaMemcpyDeviceToHost, st));
+  if (P.n_obs > 0) {
+    CK(cudaMemcpyAsync(ctx->h_out.p, d_out, sizeof(double) * (size_t)P.n_obs, cudaMemcpyDeviceToHost, st));
+    S.d2h_bytes = (int64_t)sizeof(double) * P.n_obs;
+  }
   CK(cudaEventRecord(ctx->ev[3], st));
   CK(cudaStreamSynchronize(st));
   float ms = 0.f;
-  CK(cudaEventElapsedTime(&ms, ctx->ev[0], ctx->ev[1])); ctx->stats.h2d_ms = ms;
-  CK(cudaEventElapsedTime(&ms, ctx->ev[1], ctx->ev[2])); ctx->stats.kernel_ms = ms;
-  CK(cudaEventElapsedTime(&ms, ctx->ev[2], ctx->ev[3])); ctx->stats.d2h_ms = ms;
-  if (n_obs > 0) std::memcpy(out_vals, ctx->h_out.p, sizeof(double) * (size_t)n_obs);
-  for (int c = 0; c < N; ++c)
-    if (out_status[c] != 0)
-      for (int64_t o = b->obs_offsets[c]; o < b->obs_offsets[c + 1]; ++o) out_vals[o] = std::nan("");
+  CK(cudaEventElapsedTime(&ms, ctx->ev[1], ctx->ev[2])); S.kernel_ms = ms;
+  CK(cudaEventElapsedTime(&ms, ctx->ev[2], ctx->ev[3])); S.d2h_ms = ms;
+  if (P.n_obs > 0) std::memcpy(out_vals, ctx->h_out.p, sizeof(double) * (size_t)P.n_obs);
+  for (int64_t o : P.nan_obs) out_vals[o] = std::nan("");
   return BWQ_OK;
+}
+
+extern "C" int bwq_sv_prepare(bwq_ctx* ctx, const bwq_batch* b, int32_t* out_status) {
+  if (!out_status) return fail(ctx, BWQ_ERR_ARG, "null status");
+  return sv_prepare_impl(ctx, b, out_status);
+}
+extern "C" int bwq_sv_execute(bwq_ctx* ctx, double* out_vals) { return sv_execute_impl(ctx, out_vals); }
+extern "C" int bwq_sv_run(bwq_ctx* ctx, const bwq_batch* b, double* out_vals, int32_t* out_status) {
+  if (!out_vals || !out_status) return fail(ctx, BWQ_ERR_ARG, "null out/status");
+  int rc = sv_prepare_impl(ctx, b, out_status);
+  return rc ? rc : sv_execute_impl(ctx, out_vals);
 }
 
 // ------------------------------------------------------------------------------------------------
@@ -649,15 +782,15 @@ extern "C" int bwq_lower_dm(const bwq_noise_table* table, const bwq_batch* batch
   lo.low_qubits = low_qubits < 0 ? 0 : (low_qubits ? low_qubits : 2);
   bwq_program* p = new bwq_program();
   lower_dm_circuit(nt, *batch, circuit, lo, &p->p);
-  // table-sourced ops reference the (re-packed) table: export them as batch matrices instead
-  for (auto& op : p->p.ops) {
-    if (op.src != 1) continue;
-    int n = (op.kind == K_RELAX2 || op.kind == K_RELAX2_SW) ? 25 : 256;
-    int64_t off = (int64_t)p->p.mats.size();
-    p->p.mats.insert(p->p.mats.end(), nt.data.begin() + op.off, nt.data.begin() + op.off + n);
-    while (p->p.mats.size() % 4) p->p.mats.push_back(0.0);
-    op.src = 0;
-    op.off = off;
+  // same matrix-buffer layout as a run: [noise table | circuit matrices]
+  {
+    const int64_t noise_n = ((int64_t)nt.data.size() + 31) & ~int64_t(31);
+    std::vector<double> all((size_t)noise_n, 0.0);
+    std::copy(nt.data.begin(), nt.data.end(), all.begin());
+    all.insert(all.end(), p->p.mats.begin(), p->p.mats.end());
+    p->p.mats.swap(all);
+    auto fix = [&](uint32_t off) { return (off & kLocalMat) ? (off & ~kLocalMat) + (uint32_t)noise_n : off; };
+    for (auto& op : p->p.ops) { op.off_a = fix(op.off_a); op.off_b = fix(op.off_b); op.off_2 = fix(op.off_2); }
   }
   *out = p;
   return BWQ_OK;
@@ -692,7 +825,11 @@ extern "C" int bwq_program_read(const bwq_program* p, int32_t* active, int32_t* 
       passes[3 * i] = q.passes[i].sa; passes[3 * i + 1] = q.passes[i].sb; passes[3 * i + 2] = q.passes[i].op_end;
     }
   if (ops)
-    for (size_t i = 0; i < q.ops.size(); ++i) { ops[2 * i] = q.ops[i].kind | (int64_t(q.ops[i].src) << 8); ops[2 * i + 1] = q.ops[i].off; }
+    for (size_t i = 0; i < q.ops.size(); ++i) {
+      int64_t* o = ops + 6 * i;
+      o[0] = q.ops[i].pre_a; o[1] = q.ops[i].pre_b; o[2] = q.ops[i].twoq;
+      o[3] = q.ops[i].off_a; o[4] = q.ops[i].off_b; o[5] = q.ops[i].off_2;
+    }
   if (mats && !q.mats.empty()) std::memcpy(mats, q.mats.data(), q.mats.size() * sizeof(double));
   if (term_index && !q.term_index.empty()) std::memcpy(term_index, q.term_index.data(), q.term_index.size() * sizeof(int64_t));
   if (term_coeff && !q.term_coeff.empty()) std::memcpy(term_coeff, q.term_coeff.data(), q.term_coeff.size() * sizeof(double));

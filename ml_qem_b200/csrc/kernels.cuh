@@ -21,9 +21,8 @@ struct DmLaunch {
   const int32_t* sweep_range;  // [2 * n_circuits] absolute {begin, end} per sorted circuit
   const SweepDesc* sweeps;
   const PassDesc* passes;
-  const DevOp* ops;
-  const double* mats;
-  const double* noise;
+  const MacroOp* ops;
+  const double* mats;          // [noise table copy | per-circuit matrices]
 };
 
 // ---------------------------------------------------------------------------------------------
@@ -50,7 +49,8 @@ template <bool ON_B> __device__ __forceinline__ void op_dense1(double (&v)[16], 
   }
 }
 
-// trace-preserving 1-qubit channel: row 0 of the transfer matrix is (1,0,0,0); m = rows 1..3
+// trace-preserving 1-qubit channel: row 0 of the transfer matrix is (1,0,0,0); m = rows 1..3.
+// The last FMA of each row consumes x3, so results can land in the registers of x1..x3.
 template <bool ON_B> __device__ __forceinline__ void op_aff1(double (&v)[16], const double* __restrict__ m) {
   const double2* m2 = reinterpret_cast<const double2*>(m);
   double2 a[6];
@@ -59,59 +59,82 @@ template <bool ON_B> __device__ __forceinline__ void op_aff1(double (&v)[16], co
 #pragma unroll
   for (int o = 0; o < 4; ++o) {
     const double x0 = v[idx1<ON_B>(0, o)], x1 = v[idx1<ON_B>(1, o)], x2 = v[idx1<ON_B>(2, o)], x3 = v[idx1<ON_B>(3, o)];
-#pragma unroll
-    for (int i = 0; i < 3; ++i)
-      v[idx1<ON_B>(i + 1, o)] = fma(a[2 * i + 1].y, x3, fma(a[2 * i + 1].x, x2, fma(a[2 * i].y, x1, a[2 * i].x * x0)));
+    const double p1 = fma(a[1].x, x2, fma(a[0].y, x1, a[0].x * x0));
+    const double p2 = fma(a[3].x, x2, fma(a[2].y, x1, a[2].x * x0));
+    const double p3 = fma(a[5].x, x2, fma(a[4].y, x1, a[4].x * x0));
+    v[idx1<ON_B>(1, o)] = fma(a[1].y, x3, p1);
+    v[idx1<ON_B>(2, o)] = fma(a[3].y, x3, p2);
+    v[idx1<ON_B>(3, o)] = fma(a[5].y, x3, p3);
   }
 }
 
-// rz / phase: X' = c X - s Y, Y' = s X + c Y
-template <bool ON_B> __device__ __forceinline__ void op_rotz(double (&v)[16], const double* __restrict__ m) {
-  const double2 cs = __ldg(reinterpret_cast<const double2*>(m));
+// rz / phase as three in-place shears: x -= t y; y += s x; x -= t y; then the optional sign
+template <bool ON_B> __device__ __forceinline__ void op_rot(double (&v)[16], const double* __restrict__ m) {
+  const double2 ts = __ldg(reinterpret_cast<const double2*>(m));
+  const double sign = __ldg(m + 2);
 #pragma unroll
   for (int o = 0; o < 4; ++o) {
-    const double x = v[idx1<ON_B>(1, o)], y = v[idx1<ON_B>(2, o)];
-    v[idx1<ON_B>(1, o)] = fma(-cs.y, y, cs.x * x);
-    v[idx1<ON_B>(2, o)] = fma(cs.y, x, cs.x * y);
+    double x = v[idx1<ON_B>(1, o)], y = v[idx1<ON_B>(2, o)];
+    x = fma(-ts.x, y, x);
+    y = fma(ts.y, x, y);
+    x = fma(-ts.x, y, x);
+    v[idx1<ON_B>(1, o)] = x;
+    v[idx1<ON_B>(2, o)] = y;
+  }
+  if (sign < 0.0) {
+#pragma unroll
+    for (int o = 0; o < 4; ++o) { v[idx1<ON_B>(1, o)] = -v[idx1<ON_B>(1, o)]; v[idx1<ON_B>(2, o)] = -v[idx1<ON_B>(2, o)]; }
   }
 }
 
-// CX Pauli-transfer matrix = signed permutation; index = d_control + 4 * d_target
+// CX Pauli-transfer matrix = signed permutation (an involution: six transpositions);
+// index = d_control + 4 * d_target:  y[i] = sgn[i] * v[src[i]]
+__device__ constexpr int kCxSrc[16] = {0, 5, 6, 3, 4, 1, 2, 7, 11, 14, 13, 8, 15, 10, 9, 12};
+__device__ constexpr int kCxSgn[16] = {1, 1, 1, 1, 1, 1, 1, 1, 1, 1, -1, 1, 1, -1, 1, 1};
+
 template <bool CTRL_B> __device__ __forceinline__ void op_cx(double (&v)[16]) {
-  constexpr int src[16] = {0, 5, 6, 3, 4, 1, 2, 7, 11, 14, 13, 8, 15, 10, 9, 12};
-  constexpr int sgn[16] = {1, 1, 1, 1, 1, 1, 1, 1, 1, 1, -1, 1, 1, -1, 1, 1};
   double w[16];
 #pragma unroll
   for (int i = 0; i < 16; ++i) w[i] = v[i];
 #pragma unroll
-  for (int dc = 0; dc < 4; ++dc)
-#pragma unroll
-    for (int dt = 0; dt < 4; ++dt) {
-      const int i = dc + 4 * dt, j = src[i];
-      const int jc = j & 3, jt = j >> 2;
-      const double x = w[CTRL_B ? (jt + 4 * jc) : (jc + 4 * jt)];
-      v[CTRL_B ? (dt + 4 * dc) : (dc + 4 * dt)] = sgn[i] > 0 ? x : -x;
-    }
+  for (int i = 0; i < 16; ++i) {
+    const int j = kCxSrc[i];
+    const double x = w[idx2<CTRL_B>(j & 3, j >> 2)];
+    v[idx2<CTRL_B>(i & 3, i >> 2)] = kCxSgn[i] > 0 ? x : -x;
+  }
 }
 
 // out[i] = d[i] in[i]; out[Z,b] += ca[b] in[I,b]; out[a,Z] += cb[a] in[a,I]; out[Z,Z] += cab in[I,I]
-// evaluated in place: (Z,Z) first, then the Z row / Z column, then the plain scalings.
-template <bool SW> __device__ __forceinline__ void op_relax2(double (&v)[16], const double* __restrict__ m) {
+// with (d0,d1) = digits of the error's (q0,q1).  WITH_CX: in = CX(v) first, control = q0 (the
+// noise of a cx is keyed by (control, target)); the permutation and signs fold into operand
+// selection, so the fused op costs the 25 multiply-adds of the noise alone.
+template <bool SW, bool WITH_CX> __device__ __forceinline__ void op_relax2(double (&v)[16], const double* __restrict__ m) {
   const double2* m2 = reinterpret_cast<const double2*>(m);
-  double p[28];
+  double p[26];
 #pragma unroll
   for (int i = 0; i < 13; ++i) { const double2 t = __ldg(m2 + i); p[2 * i] = t.x; p[2 * i + 1] = t.y; }
+  double y[16];  // input in (q0,q1) index order, after the optional CX
+#pragma unroll
+  for (int i = 0; i < 16; ++i) {
+    if (WITH_CX) {
+      const int j = kCxSrc[i];
+      const double x = v[idx2<SW>(j & 3, j >> 2)];
+      y[i] = kCxSgn[i] > 0 ? x : -x;
+    } else {
+      y[i] = v[idx2<SW>(i & 3, i >> 2)];
+    }
+  }
   // p[0..15] = d[d0 + 4 d1], p[16..19] = ca[b], p[20..23] = cb[a], p[24] = cab
-  v[idx2<SW>(3, 3)] = fma(p[24], v[idx2<SW>(0, 0)],
-                      fma(p[23], v[idx2<SW>(3, 0)], fma(p[19], v[idx2<SW>(0, 3)], p[15] * v[idx2<SW>(3, 3)])));
 #pragma unroll
-  for (int b = 0; b < 3; ++b) v[idx2<SW>(3, b)] = fma(p[16 + b], v[idx2<SW>(0, b)], p[3 + 4 * b] * v[idx2<SW>(3, b)]);
+  for (int b = 0; b < 4; ++b)
 #pragma unroll
-  for (int a = 0; a < 3; ++a) v[idx2<SW>(a, 3)] = fma(p[20 + a], v[idx2<SW>(a, 0)], p[a + 12] * v[idx2<SW>(a, 3)]);
-#pragma unroll
-  for (int b = 0; b < 3; ++b)
-#pragma unroll
-    for (int a = 0; a < 3; ++a) v[idx2<SW>(a, b)] *= p[a + 4 * b];
+    for (int a = 0; a < 4; ++a) {
+      double r = p[a + 4 * b] * y[a + 4 * b];
+      if (a == 3) r = fma(p[16 + b], y[0 + 4 * b], r);
+      if (b == 3) r = fma(p[20 + a], y[a + 0], r);
+      if (a == 3 && b == 3) r = fma(p[24], y[0], r);
+      v[idx2<SW>(a, b)] = r;
+    }
 }
 
 template <bool SW> __device__ __forceinline__ void op_dense2(double (&v)[16], const double* __restrict__ m) {
@@ -138,24 +161,26 @@ template <bool SW> __device__ __forceinline__ void op_dense2(double (&v)[16], co
 
 template <bool FULL>
 __device__ __forceinline__ void run_ops(double (&v)[16], const DmLaunch& L, int op_begin, int op_end) {
+  const double* __restrict__ mats = L.mats;
   for (int o = op_begin; o < op_end; ++o) {
-    const int4 raw = __ldg(reinterpret_cast<const int4*>(L.ops + o));
-    const int kind = raw.x;
-    const int64_t off = (int64_t(uint32_t(raw.w)) << 32) | uint32_t(raw.z);
-    const double* m = (raw.y ? L.noise : L.mats) + off;
-    switch (kind) {
-      case K_AFF1_A: op_aff1<false>(v, m); break;
-      case K_AFF1_B: op_aff1<true>(v, m); break;
-      case K_ROTZ_A: op_rotz<false>(v, m); break;
-      case K_ROTZ_B: op_rotz<true>(v, m); break;
-      case K_CX_AB: op_cx<false>(v); break;
-      case K_CX_BA: op_cx<true>(v); break;
-      case K_RELAX2: op_relax2<false>(v, m); break;
-      case K_RELAX2_SW: op_relax2<true>(v, m); break;
-      case K_DENSE1_A: if constexpr (FULL) op_dense1<false>(v, m); break;
-      case K_DENSE1_B: if constexpr (FULL) op_dense1<true>(v, m); break;
-      case K_DENSE2: if constexpr (FULL) op_dense2<false>(v, m); break;
-      case K_DENSE2_SW: if constexpr (FULL) op_dense2<true>(v, m); break;
+    const uint4 raw = __ldg(reinterpret_cast<const uint4*>(L.ops + o));
+    const uint32_t pre_a = raw.x & 0xffu, pre_b = (raw.x >> 8) & 0xffu, twoq = (raw.x >> 16) & 0xffu;
+    if (pre_a == P_AFF) op_aff1<false>(v, mats + raw.y);
+    else if (pre_a == P_ROT) op_rot<false>(v, mats + raw.y);
+    else if (FULL && pre_a == P_DENSE) op_dense1<false>(v, mats + raw.y);
+    if (pre_b == P_AFF) op_aff1<true>(v, mats + raw.z);
+    else if (pre_b == P_ROT) op_rot<true>(v, mats + raw.z);
+    else if (FULL && pre_b == P_DENSE) op_dense1<true>(v, mats + raw.z);
+    const double* m2q = mats + raw.w;
+    switch (twoq) {
+      case Q_CXN_AB: op_relax2<false, true>(v, m2q); break;
+      case Q_CXN_BA: op_relax2<true, true>(v, m2q); break;
+      case Q_CX_AB: op_cx<false>(v); break;
+      case Q_CX_BA: op_cx<true>(v); break;
+      case Q_RELAX: op_relax2<false, false>(v, m2q); break;
+      case Q_RELAX_SW: op_relax2<true, false>(v, m2q); break;
+      case Q_DENSE: if constexpr (FULL) op_dense2<false>(v, m2q); break;
+      case Q_DENSE_SW: if constexpr (FULL) op_dense2<true>(v, m2q); break;
       default: break;
     }
   }
@@ -170,14 +195,20 @@ __device__ __forceinline__ void run_ops(double (&v)[16], const DmLaunch& L, int 
 // 8-byte accesses hit 16 distinct bank pairs for EVERY choice of target slots; the linear
 // load/store phases stay conflict-free as well.  swz is XOR-linear: swz(a^b) = swz(a)^swz(b).
 // ---------------------------------------------------------------------------------------------
-__device__ __forceinline__ uint32_t gf4_mulw(uint32_t b) { return (((b >> 1) ^ b) & 1u) << 1 | (b >> 1); }
-__device__ __forceinline__ uint32_t swz(uint32_t j) {
+__host__ __device__ constexpr uint32_t gf4_mulw(uint32_t b) { return ((((b >> 1) ^ b) & 1u) << 1) | (b >> 1); }
+__host__ __device__ constexpr uint32_t swz(uint32_t j) {
   const uint32_t d2 = (j >> 4) & 3u, d3 = (j >> 6) & 3u, d4 = (j >> 8) & 3u, d5 = (j >> 10) & 3u, d6 = (j >> 12) & 3u;
   const uint32_t d45 = d4 ^ d5, d36 = d3 ^ d6;
   const uint32_t x0 = d2 ^ d36 ^ d45;
   const uint32_t x1 = d2 ^ gf4_mulw(d36) ^ gf4_mulw(d45) ^ d45;
   return j ^ (x0 | (x1 << 2));
 }
+// swz(d << 2s) for a single digit d in slot s (uniform lookup for the register-pass offsets)
+__constant__ const uint16_t kSwzDigit[7][4] = {
+    {0, 1, 2, 3},          {0, 4, 8, 12},         {0, 21, 42, 63},        {0, 73, 142, 199},
+    {0, 269, 518, 779},    {0, 1037, 2054, 3083}, {0, 4105, 8206, 12295}};
+static_assert(swz(1u << 4) == 21 && swz(2u << 6) == 142 && swz(3u << 8) == 779 && swz(1u << 10) == 1037 &&
+              swz(3u << 12) == 12295 && swz(2u << 4) == 42 && swz(3u << 6) == 199, "swizzle table");
 
 // ---------------------------------------------------------------------------------------------
 // K1/K2/K3: tile sweep
@@ -189,12 +220,22 @@ template <int KQ> struct SweepCfg {
   static constexpr int kMinBlocks = KQ >= 7 ? 1 : (KQ == 6 ? 3 : 4);
 };
 
+// tile-local index j (2 bits per slot) -> offset in the state (2 bits per digit position)
+template <int KQ> __device__ __forceinline__ int64_t deposit(uint32_t j, const int (&pos)[KQ]) {
+  int64_t off = 0;
+#pragma unroll
+  for (int s = 0; s < KQ; ++s) off |= int64_t((j >> (2 * s)) & 3u) << (2 * pos[s]);
+  return off;
+}
+
 // FULL = also carries the dense 4x4 / 16x16 ops (coherent errors, non-basis 2-qubit gates); the
 // lean instantiation keeps the register budget at 3 CTAs per SM.
 template <int KQ, bool FULL>
 __global__ void __launch_bounds__(SweepCfg<KQ>::kThreads, FULL ? 1 : SweepCfg<KQ>::kMinBlocks)
 dm_sweep_kernel(const DmLaunch L, const int sweep_idx) {
   constexpr int E = SweepCfg<KQ>::kElems, G = SweepCfg<KQ>::kGroups, T = SweepCfg<KQ>::kThreads;
+  constexpr int U = E / 2;                       // double2 units per tile
+  constexpr int NIT = (U + T - 1) / T;           // load/store iterations per thread
   extern __shared__ __align__(16) double tile[];
   const int tid = threadIdx.x;
   const int tiles_log2 = 2 * (L.n_digits - KQ);
@@ -211,42 +252,57 @@ dm_sweep_kernel(const DmLaunch L, const int sweep_idx) {
 #pragma unroll
     for (int s = 0; s < KQ; ++s) pos[s] = int((pk >> (8 * s)) & 0xff);
   }
-  // scatter the tile id over the digit positions that are NOT resident in the tile
+  // scatter the tile id over the digit positions that are NOT resident in the tile: the bits of t
+  // fill the gaps between consecutive resident positions (pos[] ascending)
   int64_t base = 0;
   {
-    uint32_t rest = t;
-    int s = 0;
-    for (int d = 0; d < L.n_digits; ++d) {
-      if (s < KQ && pos[s] == d) { ++s; continue; }
-      base |= int64_t(rest & 3u) << (2 * d);
-      rest >>= 2;
+    uint64_t rest = t;
+    int next = 0;  // next free digit position
+#pragma unroll
+    for (int s = 0; s < KQ; ++s) {
+      const int gap = pos[s] - next;  // digits in [next, pos[s]) come from t
+      base |= int64_t(rest & ((1ull << (2 * gap)) - 1ull)) << (2 * next);
+      rest >>= 2 * gap;
+      next = pos[s] + 1;
     }
+    base |= int64_t(rest) << (2 * next);
   }
   double* __restrict__ g = L.states + slot * L.stride + base;
   double2* tile2 = reinterpret_cast<double2*>(tile);
+
+  // Unit u = tid + k*T covers tile elements j = 2u, 2u+1.  deposit() and swz() are bitwise
+  // linear, so the per-thread part (tid) is computed once and the per-iteration part (k*T) is
+  // uniform / compile-time.
+  const uint32_t j_thr = 2u * uint32_t(tid);
+  const int64_t off_thr = deposit<KQ>(j_thr, pos);
+  const uint32_t p_thr = swz(j_thr);
 
   // ---- load (or synthesise |0..0><0..0| on the first sweep)
   if (sweep_idx == 0) {
     const bool tile_ok = ((t ^ (t >> 1)) & 0x55555555u) == 0u;  // all outside digits in {I,Z}
 #pragma unroll
-    for (int u = tid; u < E / 2; u += T) {
-      const uint32_t j = 2u * u;  // D0 of j is 0 or 2 -> element j+1 has D0 = 1 or 3
+    for (int k = 0; k < NIT; ++k) {
+      if (NIT * T != U && tid + k * T >= U) break;
+      const uint32_t j = j_thr + 2u * uint32_t(k * T);  // D0 of j is 0 or 2
       const bool hi_ok = tile_ok && ((((j >> 2) ^ (j >> 3)) & 0x15555555u) == 0u);
       const bool d0_is2 = (j & 2u) != 0u;
-      const uint32_t p = swz(j);
+      const uint32_t p = p_thr ^ swz(2u * uint32_t(k * T));
       const double e0 = (hi_ok && !d0_is2) ? 1.0 : 0.0, e1 = (hi_ok && d0_is2) ? 1.0 : 0.0;
       tile2[p >> 1] = (p & 1u) ? make_double2(e1, e0) : make_double2(e0, e1);
     }
   } else {
+    double2 val[NIT];
 #pragma unroll
-    for (int u = tid; u < E / 2; u += T) {
-      const uint32_t j = 2u * u;
-      int64_t off = 0;
+    for (int k = 0; k < NIT; ++k) {
+      if (NIT * T != U && tid + k * T >= U) break;
+      const int64_t off = off_thr | deposit<KQ>(2u * uint32_t(k * T), pos);
+      val[k] = *reinterpret_cast<const double2*>(g + off);
+    }
 #pragma unroll
-      for (int s = 0; s < KQ; ++s) off |= int64_t((j >> (2 * s)) & 3u) << (2 * pos[s]);
-      const double2 val = *reinterpret_cast<const double2*>(g + off);
-      const uint32_t p = swz(j);
-      tile2[p >> 1] = (p & 1u) ? make_double2(val.y, val.x) : val;
+    for (int k = 0; k < NIT; ++k) {
+      if (NIT * T != U && tid + k * T >= U) break;
+      const uint32_t p = p_thr ^ swz(2u * uint32_t(k * T));
+      tile2[p >> 1] = (p & 1u) ? make_double2(val[k].y, val[k].x) : val[k];
     }
   }
 
@@ -258,7 +314,7 @@ dm_sweep_kernel(const DmLaunch L, const int sweep_idx) {
     const int lo = min(sa, sb), hi = max(sa, sb);
     uint32_t oa[4], ob[4];
 #pragma unroll
-    for (int d = 0; d < 4; ++d) { oa[d] = swz(uint32_t(d) << (2 * sa)); ob[d] = swz(uint32_t(d) << (2 * sb)); }
+    for (int d = 0; d < 4; ++d) { oa[d] = kSwzDigit[sa][d]; ob[d] = kSwzDigit[sb][d]; }
     for (int grp = tid; grp < G; grp += T) {
       const uint32_t low = grp & ((1u << (2 * lo)) - 1u);
       const uint32_t mid = (grp >> (2 * lo)) & ((1u << (2 * (hi - lo - 1))) - 1u);
@@ -280,12 +336,10 @@ dm_sweep_kernel(const DmLaunch L, const int sweep_idx) {
 
   // ---- store
 #pragma unroll
-  for (int u = tid; u < E / 2; u += T) {
-    const uint32_t j = 2u * u;
-    int64_t off = 0;
-#pragma unroll
-    for (int s = 0; s < KQ; ++s) off |= int64_t((j >> (2 * s)) & 3u) << (2 * pos[s]);
-    const uint32_t p = swz(j);
+  for (int k = 0; k < NIT; ++k) {
+    if (NIT * T != U && tid + k * T >= U) break;
+    const int64_t off = off_thr | deposit<KQ>(2u * uint32_t(k * T), pos);
+    const uint32_t p = p_thr ^ swz(2u * uint32_t(k * T));
     const double2 val = tile2[p >> 1];
     *reinterpret_cast<double2*>(g + off) = (p & 1u) ? make_double2(val.y, val.x) : val;
   }

@@ -270,7 +270,7 @@ static bool gate_ptm1(uint16_t op, const double* p, double* r) {
 namespace {
 struct HostPass {
   int qa, qb;
-  std::vector<DevOp> ops;
+  std::vector<MacroOp> ops;
 };
 }  // namespace
 
@@ -338,25 +338,43 @@ void lower_dm_circuit(const NoiseTable& noise, const bwq_batch& b, int c, const 
   std::vector<double> pend(16 * nd);
   std::vector<char> has(nd, 0);
   std::vector<int> last(nd, -1);
+  auto local = [&](const double* m, int n) { return kLocalMat | (uint32_t)push_mat(out->mats, m, n); };
+  // the macro-op a 1-qubit map on slot a/b (or a 2-qubit op) goes into
+  auto slot_for_pre = [&](HostPass& p, bool on_a) -> MacroOp& {
+    if (p.ops.empty() || p.ops.back().twoq != Q_NONE || (on_a ? p.ops.back().pre_a : p.ops.back().pre_b) != P_NONE)
+      p.ops.push_back(MacroOp{});
+    return p.ops.back();
+  };
+  auto slot_for_two = [&](HostPass& p) -> MacroOp& {
+    if (p.ops.empty() || p.ops.back().twoq != Q_NONE) p.ops.push_back(MacroOp{});
+    return p.ops.back();
+  };
   auto flush = [&](int d, HostPass& p) {
     if (!has[d]) return;
     has[d] = 0;
     const double* m = &pend[16 * d];
     const bool on_a = d == p.qa;
+    uint8_t kind;
+    uint32_t off;
     const bool tp = m[0] == 1.0 && m[1] == 0.0 && m[2] == 0.0 && m[3] == 0.0;
-    if (!tp) {  // not trace preserving: general 4x4
-      p.ops.push_back(DevOp{on_a ? K_DENSE1_A : K_DENSE1_B, 0, push_mat(out->mats, m, 16)});
-      return;
-    }
-    const bool rot = m[4] == 0.0 && m[8] == 0.0 && m[12] == 0.0 && m[7] == 0.0 && m[11] == 0.0 &&
+    const bool rot = tp && m[4] == 0.0 && m[8] == 0.0 && m[12] == 0.0 && m[7] == 0.0 && m[11] == 0.0 &&
                      m[13] == 0.0 && m[14] == 0.0 && m[15] == 1.0 && m[5] == m[10] && m[6] == -m[9];
-    if (rot) {
-      if (m[5] == 1.0 && m[9] == 0.0) return;  // identity
-      const double cs[4] = {m[5], m[9], 0.0, 0.0};
-      p.ops.push_back(DevOp{on_a ? K_ROTZ_A : K_ROTZ_B, 0, push_mat(out->mats, cs, 4)});
-      return;
+    if (!tp) {  // not trace preserving: general 4x4
+      kind = P_DENSE; off = local(m, 16);
+    } else if (rot) {
+      double c = m[5], sn = m[9];
+      if (c == 1.0 && sn == 0.0) return;  // identity
+      // R(theta) = sign * Shear_x(-t) Shear_y(s) Shear_x(-t), theta' = theta (-/+ pi when cos < 0)
+      double sign = 1.0;
+      if (c < 0.0) { c = -c; sn = -sn; sign = -1.0; }
+      const double t = sn / (1.0 + c);  // tan(theta'/2), |t| <= 1
+      const double sh[4] = {t, sn, sign, 0.0};
+      kind = P_ROT; off = local(sh, 4);
+    } else {
+      kind = P_AFF; off = local(m + 4, 12);
     }
-    p.ops.push_back(DevOp{on_a ? K_AFF1_A : K_AFF1_B, 0, push_mat(out->mats, m + 4, 12)});
+    MacroOp& mo = slot_for_pre(p, on_a);
+    if (on_a) { mo.pre_a = kind; mo.off_a = off; } else { mo.pre_b = kind; mo.off_b = off; }
   };
   for (int64_t g = g0; g < g1; ++g) {
     const bwq_op& op = b.ops[g];
@@ -384,16 +402,26 @@ void lower_dm_circuit(const NoiseTable& noise, const bwq_batch& b, int c, const 
     flush(d0, p);
     flush(d1, p);
     const bool same = (d0 == p.qa);
-    if (op.opcode == BWQ_G_CX) p.ops.push_back(DevOp{same ? K_CX_AB : K_CX_BA, 0, 0});
-    else {
+    const NoiseEntry* ne = noise.find(op.opcode, op.q0, op.q1);
+    if (op.opcode == BWQ_G_CX) {
+      MacroOp& mo = slot_for_two(p);
+      if (ne && ne->kind == BWQ_NOISE_RELAX2) {  // CX + its relaxation/depolarizing error: one fused op
+        mo.twoq = same ? Q_CXN_AB : Q_CXN_BA; mo.off_2 = (uint32_t)ne->off;
+        ne = nullptr;
+      } else {
+        mo.twoq = same ? Q_CX_AB : Q_CX_BA;
+      }
+    } else {
       double u[32], r[256];
       if (!gate_unitary(op.opcode, par, u)) { out->status = BWQ_CIRC_BAD_OP; return; }
       ptm_from_unitary2(u, r);
-      p.ops.push_back(DevOp{same ? K_DENSE2 : K_DENSE2_SW, 0, push_mat(out->mats, r, 256)});
+      MacroOp& mo = slot_for_two(p);
+      mo.twoq = same ? Q_DENSE : Q_DENSE_SW; mo.off_2 = local(r, 256);
     }
-    if (const NoiseEntry* ne = noise.find(op.opcode, op.q0, op.q1)) {
-      int k = ne->kind == BWQ_NOISE_RELAX2 ? (same ? K_RELAX2 : K_RELAX2_SW) : (same ? K_DENSE2 : K_DENSE2_SW);
-      p.ops.push_back(DevOp{k, 1, ne->off});
+    if (ne) {
+      MacroOp& mo = slot_for_two(p);
+      mo.twoq = ne->kind == BWQ_NOISE_RELAX2 ? (same ? Q_RELAX : Q_RELAX_SW) : (same ? Q_DENSE : Q_DENSE_SW);
+      mo.off_2 = (uint32_t)ne->off;
     }
   }
   for (int d = 0; d < nd; ++d) {
@@ -407,9 +435,10 @@ void lower_dm_circuit(const NoiseTable& noise, const bwq_batch& b, int c, const 
   }
 
   // ---- passes -> sweeps (greedy in program order; a pass that does not fit blocks its qubits)
-  const int kq = std::min(std::max(opt.tile_qubits, 2), std::min(nd, kMaxTileQubits));
-  // always-resident low digits (coalescing); two slots must stay free for an arbitrary pass
-  const int mlow = (nd <= kq) ? 0 : std::min(std::max(opt.low_qubits, 0), kq - 2);
+  // tile = min(tile_qubits, n) digits, at least 3 when the state is larger than the tile so that
+  // digit 0 (always resident: 16-byte global accesses) leaves two free slots for any pass
+  const int kq = std::min(std::max(opt.tile_qubits, 3), std::min(nd, kMaxTileQubits));
+  const int mlow = (nd <= kq) ? 0 : std::min(std::max(opt.low_qubits, 1), kq - 2);
   const int np = (int)passes.size();
   std::vector<char> done(np, 0);
   int first = 0, remaining = np;
@@ -453,8 +482,8 @@ void lower_dm_circuit(const NoiseTable& noise, const bwq_batch& b, int c, const 
     }
     out->sweeps.push_back(sw);
   }
-  for (const DevOp& o : out->ops)
-    if (o.kind == K_DENSE1_A || o.kind == K_DENSE1_B || o.kind == K_DENSE2 || o.kind == K_DENSE2_SW) out->needs_dense = true;
+  for (const MacroOp& o : out->ops)
+    if (o.pre_a == P_DENSE || o.pre_b == P_DENSE || o.twoq == Q_DENSE || o.twoq == Q_DENSE_SW) out->needs_dense = true;
 }
 
 // ----------------------------------------------------------------------------- SV lowering

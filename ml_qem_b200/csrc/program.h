@@ -13,29 +13,33 @@
 
 namespace bwq {
 
-// Register-pass op kinds.  A pass owns two tile slots (a, b); every thread holds the 16 elements
-// v[da + 4*db] of one (a, b) group in registers and runs the pass's op list on them.
-enum OpKind : int32_t {
-  K_DENSE1_A = 0,  // 4x4 real matrix on digit a          (16 doubles)
-  K_DENSE1_B = 1,  // 4x4 real matrix on digit b          (16 doubles)
-  K_CX_AB = 2,     // CX, control a, target b             (signed permutation, no data)
-  K_CX_BA = 3,     // CX, control b, target a
-  K_RELAX2 = 4,    // diag + affine noise, (q0,q1)=(a,b)  (25 doubles)
-  K_RELAX2_SW = 5, // same with (q0,q1)=(b,a)
-  K_DENSE2 = 6,    // 16x16 real matrix, (q0,q1)=(a,b)    (256 doubles)
-  K_DENSE2_SW = 7, // same with (q0,q1)=(b,a)
-  K_AFF1_A = 8,    // trace-preserving 1-qubit channel on digit a: rows 1..3 of its 4x4 (12 doubles)
-  K_AFF1_B = 9,
-  K_ROTZ_A = 10,   // rz / phase on digit a: (cos, sin) (2 doubles, padded to 4)
-  K_ROTZ_B = 11,
-  K_COUNT = 12
+// Register-pass macro-ops.  A pass owns two tile slots (a, b); every thread holds the 16 elements
+// v[da + 4*db] of one (a, b) group in registers and runs the pass's macro-op list on them.  One
+// macro-op = optional 1-qubit map on a, optional 1-qubit map on b, then an optional 2-qubit op.
+enum PreKind : uint8_t {
+  P_NONE = 0,
+  P_ROT = 1,    // rz / phase as three shears: (tan(theta'/2), sin(theta'), sign)      4 doubles
+  P_AFF = 2,    // trace-preserving 1-qubit channel: rows 1..3 of its 4x4 transfer matrix 12 doubles
+  P_DENSE = 3   // general 4x4 (not trace preserving)                                   16 doubles
+};
+enum TwoKind : uint8_t {
+  Q_NONE = 0,
+  Q_CXN_AB = 1,   // CX (control a) fused with its diag+affine noise                   28 doubles
+  Q_CXN_BA = 2,   // CX (control b) fused with its noise
+  Q_CX_AB = 3,    // bare CX: signed permutation, no data
+  Q_CX_BA = 4,
+  Q_RELAX = 5,    // diag + affine noise alone, (q0,q1) = (a,b)                        28 doubles
+  Q_RELAX_SW = 6, // (q0,q1) = (b,a)
+  Q_DENSE = 7,    // 16x16 real matrix, (q0,q1) = (a,b)                               256 doubles
+  Q_DENSE_SW = 8
 };
 
-struct DevOp {      // 16 B
-  int32_t kind;
-  int32_t src;      // 0: batch matrix buffer, 1: ctx noise table
-  int64_t off;      // offset in doubles
+struct MacroOp {    // 16 B
+  uint8_t pre_a, pre_b, twoq, pad;
+  uint32_t off_a, off_b, off_2;   // offsets (doubles) into the batch matrix buffer, whose head is
+                                  // a copy of the noise table
 };
+constexpr uint32_t kLocalMat = 0x80000000u;  // in CircuitProgram: offset is circuit-local
 struct PassDesc {   // 16 B
   int32_t op_begin, op_end;
   uint8_t sa, sb;   // tile slots of digits a and b
@@ -71,12 +75,12 @@ struct CircuitProgram {
   std::vector<int32_t> active;          // physical qubit of each digit (-1 = padding)
   std::vector<SweepDesc> sweeps;
   std::vector<PassDesc> passes;
-  std::vector<DevOp> ops;
+  std::vector<MacroOp> ops;
   std::vector<double> mats;
   std::vector<int64_t> term_index;      // per Pauli term: element index or -1
   std::vector<double> term_coeff;
   int64_t n_gates = 0;
-  bool needs_dense = false;             // uses K_DENSE1_* / K_DENSE2_* (selects the FULL kernel)
+  bool needs_dense = false;             // uses P_DENSE / Q_DENSE* (selects the FULL kernel)
 };
 
 struct LowerOptions {

@@ -52,12 +52,12 @@ class _Stats(C.Structure):
     _fields_ = [("n_sweep_launches", C.c_int64), ("n_state_sweeps", C.c_int64), ("n_passes", C.c_int64),
                 ("n_gates", C.c_int64), ("state_bytes_swept", C.c_int64), ("n_other_launches", C.c_int64),
                 ("lower_ms", C.c_double), ("h2d_ms", C.c_double), ("kernel_ms", C.c_double), ("d2h_ms", C.c_double),
-                ("sweep_kernel_ms", C.c_double)]
+                ("sweep_kernel_ms", C.c_double), ("h2d_bytes", C.c_int64), ("d2h_bytes", C.c_int64)]
 
 
 EXPORTS = [
     "bwq_version", "bwq_create", "bwq_destroy", "bwq_last_error", "bwq_set_options", "bwq_set_noise_table",
-    "bwq_dm_run", "bwq_sv_run", "bwq_dm_run_device_out", "bwq_get_stats", "bwq_sync", "bwq_lower_dm",
+    "bwq_dm_run", "bwq_sv_run", "bwq_dm_run_device_out", "bwq_dm_prepare", "bwq_dm_execute", "bwq_dm_execute_device_out", "bwq_sv_prepare", "bwq_sv_execute", "bwq_get_stats", "bwq_sync", "bwq_lower_dm",
     "bwq_program_free", "bwq_program_sizes", "bwq_program_read",
 ]
 
@@ -81,6 +81,11 @@ def load_library(path=None):
     lib.bwq_set_noise_table.argtypes = [C.c_void_p, C.POINTER(_NoiseTable)]
     for f in (lib.bwq_dm_run, lib.bwq_sv_run, lib.bwq_dm_run_device_out):
         f.argtypes = [C.c_void_p, C.POINTER(_Batch), C.c_void_p, C.c_void_p]
+    lib.bwq_dm_prepare.argtypes = [C.c_void_p, C.POINTER(_Batch), C.c_void_p]
+    lib.bwq_dm_execute.argtypes = [C.c_void_p, C.c_void_p]
+    lib.bwq_sv_prepare.argtypes = [C.c_void_p, C.POINTER(_Batch), C.c_void_p]
+    lib.bwq_sv_execute.argtypes = [C.c_void_p, C.c_void_p]
+    lib.bwq_dm_execute_device_out.argtypes = [C.c_void_p, C.c_void_p]
     lib.bwq_get_stats.argtypes = [C.c_void_p, C.POINTER(_Stats)]
     lib.bwq_sync.argtypes = [C.c_void_p]
     lib.bwq_lower_dm.argtypes = [C.POINTER(_NoiseTable), C.POINTER(_Batch), C.c_int32, C.c_int32, C.c_int32,
@@ -258,6 +263,36 @@ class Engine:
         """Noisy values (density matrix under the installed noise table) -> (values, status)."""
         return self._run(self._lib.bwq_dm_run, batch, "bwq_dm_run")
 
+    def prepare_dm(self, batch):
+        """Lowers + uploads the batch; the program stays resident on the device.  -> status"""
+        status = np.zeros(batch.n_circuits, dtype=np.int32)
+        st = batch.c_struct()
+        with self._lock:
+            self._check(self._lib.bwq_dm_prepare(self._ctx, C.byref(st), status.ctypes.data_as(C.c_void_p)), "bwq_dm_prepare")
+        self._prepared_obs = batch.n_observables
+        return status
+
+    def execute_dm(self):
+        """Runs the prepared batch (kernels + D2H of the values) -> values."""
+        vals = np.empty(self._prepared_obs, dtype=np.float64)
+        with self._lock:
+            self._check(self._lib.bwq_dm_execute(self._ctx, vals.ctypes.data_as(C.c_void_p)), "bwq_dm_execute")
+        return vals
+
+    def prepare_sv(self, batch):
+        status = np.zeros(batch.n_circuits, dtype=np.int32)
+        st = batch.c_struct()
+        with self._lock:
+            self._check(self._lib.bwq_sv_prepare(self._ctx, C.byref(st), status.ctypes.data_as(C.c_void_p)), "bwq_sv_prepare")
+        self._prepared_sv_obs = batch.n_observables
+        return status
+
+    def execute_sv(self):
+        vals = np.empty(self._prepared_sv_obs, dtype=np.float64)
+        with self._lock:
+            self._check(self._lib.bwq_sv_execute(self._ctx, vals.ctypes.data_as(C.c_void_p)), "bwq_sv_execute")
+        return vals
+
     def run_sv(self, batch):
         """Ideal values (statevector) -> (values, status)."""
         return self._run(self._lib.bwq_sv_run, batch, "bwq_sv_run")
@@ -299,7 +334,7 @@ def lower_dm(batch, circuit, noise_model=None, tile_qubits=0, low_qubits=0):
         out = {
             "n_digits": nd, "status": status, "n_gates": ng,
             "active": np.zeros(nd, dtype=np.int32), "sweeps": np.zeros((nsw, 10), dtype=np.int32),
-            "passes": np.zeros((nps, 3), dtype=np.int32), "ops": np.zeros((nops, 2), dtype=np.int64),
+            "passes": np.zeros((nps, 3), dtype=np.int32), "ops": np.zeros((nops, 6), dtype=np.int64),
             "mats": np.zeros(nm, dtype=np.float64), "term_index": np.zeros(nt, dtype=np.int64),
             "term_coeff": np.zeros(nt, dtype=np.float64),
         }

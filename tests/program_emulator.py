@@ -9,49 +9,73 @@ import numpy as np
 
 CX_SRC = [0, 5, 6, 3, 4, 1, 2, 7, 11, 14, 13, 8, 15, 10, 9, 12]
 CX_SGN = [1, 1, 1, 1, 1, 1, 1, 1, 1, 1, -1, 1, 1, -1, 1, 1]
-(K_DENSE1_A, K_DENSE1_B, K_CX_AB, K_CX_BA, K_RELAX2, K_RELAX2_SW, K_DENSE2, K_DENSE2_SW,
- K_AFF1_A, K_AFF1_B, K_ROTZ_A, K_ROTZ_B) = range(12)
+P_NONE, P_ROT, P_AFF, P_DENSE = range(4)
+Q_NONE, Q_CXN_AB, Q_CXN_BA, Q_CX_AB, Q_CX_BA, Q_RELAX, Q_RELAX_SW, Q_DENSE, Q_DENSE_SW = range(9)
 
 
 def _swap_view(v):  # v[da + 4 db] -> index with (q0,q1) = (b,a)
     return v.reshape(4, 4, -1).transpose(1, 0, 2).reshape(16, -1)
 
 
-def apply_op(v, kind, m):
-    """v: (16, G) array, row index da + 4*db."""
-    if kind == K_DENSE1_A:
-        a = m[:16].reshape(4, 4)
-        return np.einsum("ij,bjg->big", a, v.reshape(4, 4, -1)).reshape(16, -1)
-    if kind == K_DENSE1_B:
-        a = m[:16].reshape(4, 4)
-        return np.einsum("ij,jag->iag", a, v.reshape(4, 4, -1)).reshape(16, -1)
-    if kind in (K_AFF1_A, K_AFF1_B):
-        a = np.vstack([[1.0, 0.0, 0.0, 0.0], m[:12].reshape(3, 4)])
-        return apply_op(v, K_DENSE1_A if kind == K_AFF1_A else K_DENSE1_B, a.reshape(-1))
-    if kind in (K_ROTZ_A, K_ROTZ_B):
-        c, s = m[0], m[1]
-        a = np.array([[1, 0, 0, 0], [0, c, -s, 0], [0, s, c, 0], [0, 0, 0, 1.0]])
-        return apply_op(v, K_DENSE1_A if kind == K_ROTZ_A else K_DENSE1_B, a.reshape(-1))
-    if kind in (K_CX_AB, K_CX_BA):
-        w = v if kind == K_CX_AB else _swap_view(v)
-        out = np.empty_like(w)
-        for i in range(16):
-            out[i] = CX_SGN[i] * w[CX_SRC[i]]
-        return out if kind == K_CX_AB else _swap_view(out)
-    if kind in (K_RELAX2, K_RELAX2_SW):
-        w = v if kind == K_RELAX2 else _swap_view(v)
-        out = m[:16, None] * w
-        for b in range(4):
-            out[3 + 4 * b] += m[16 + b] * w[4 * b]
-        for a in range(4):
-            out[a + 12] += m[20 + a] * w[a]
-        out[15] += m[24] * w[0]
-        return out if kind == K_RELAX2 else _swap_view(out)
-    if kind in (K_DENSE2, K_DENSE2_SW):
-        w = v if kind == K_DENSE2 else _swap_view(v)
-        out = m[:256].reshape(16, 16) @ w
-        return out if kind == K_DENSE2 else _swap_view(out)
+def _one_qubit(v, a, on_b):
+    t = v.reshape(4, 4, -1)  # [db, da, g]
+    if on_b:
+        return np.einsum("ij,jag->iag", a, t).reshape(16, -1)
+    return np.einsum("ij,bjg->big", a, t).reshape(16, -1)
+
+
+def apply_pre(v, kind, m, on_b):
+    if kind == P_NONE:
+        return v
+    if kind == P_ROT:  # three shears + sign, exactly as the kernel evaluates it
+        t, s, sign = m[0], m[1], m[2]
+        sh_x = np.array([[1, 0, 0, 0], [0, 1, -t, 0], [0, 0, 1, 0], [0, 0, 0, 1.0]])
+        sh_y = np.array([[1, 0, 0, 0], [0, 1, 0, 0], [0, s, 1, 0], [0, 0, 0, 1.0]])
+        a = sh_x @ sh_y @ sh_x
+        if sign < 0:
+            a[1:3] *= -1.0
+        return _one_qubit(v, a, on_b)
+    if kind == P_AFF:
+        return _one_qubit(v, np.vstack([[1.0, 0.0, 0.0, 0.0], m[:12].reshape(3, 4)]), on_b)
+    if kind == P_DENSE:
+        return _one_qubit(v, m[:16].reshape(4, 4), on_b)
     raise ValueError(kind)
+
+
+def _cx(w):
+    out = np.empty_like(w)
+    for i in range(16):
+        out[i] = CX_SGN[i] * w[CX_SRC[i]]
+    return out
+
+
+def _relax(w, m):
+    out = m[:16, None] * w
+    for b in range(4):
+        out[3 + 4 * b] += m[16 + b] * w[4 * b]
+    for a in range(4):
+        out[a + 12] += m[20 + a] * w[a]
+    out[15] += m[24] * w[0]
+    return out
+
+
+def apply_two(v, kind, m):
+    """v: (16, G) array, row index da + 4*db."""
+    if kind == Q_NONE:
+        return v
+    sw = kind in (Q_CXN_BA, Q_CX_BA, Q_RELAX_SW, Q_DENSE_SW)
+    w = _swap_view(v) if sw else v
+    if kind in (Q_CXN_AB, Q_CXN_BA):
+        out = _relax(_cx(w), m)
+    elif kind in (Q_CX_AB, Q_CX_BA):
+        out = _cx(w)
+    elif kind in (Q_RELAX, Q_RELAX_SW):
+        out = _relax(w, m)
+    elif kind in (Q_DENSE, Q_DENSE_SW):
+        out = m[:256].reshape(16, 16) @ w
+    else:
+        raise ValueError(kind)
+    return _swap_view(out) if sw else out
 
 
 def run_program(prog):
@@ -86,9 +110,10 @@ def run_program(prog):
             shp = tt.shape
             v = tt.reshape(16, -1)  # index db*4 + da  == da + 4 db
             for o in range(op_begin, op_end):
-                kind = int(prog["ops"][o][0]) & 0xff
-                off = int(prog["ops"][o][1])
-                v = apply_op(v, kind, mats[off:off + 256])
+                pre_a, pre_b, twoq, off_a, off_b, off_2 = (int(x) for x in prog["ops"][o])
+                v = apply_pre(v, pre_a, mats[off_a:off_a + 16], False)
+                v = apply_pre(v, pre_b, mats[off_b:off_b + 16], True)
+                v = apply_two(v, twoq, mats[off_2:off_2 + 256])
             t = np.moveaxis(v.reshape(shp), [0, 1], axes)
             op_begin = op_end
         pass_begin = pass_end

@@ -60,7 +60,7 @@ def test_coherent_cx_noise_uses_dense_op(lib):
     rng = np.random.default_rng(3)
     c = F.random_basis_circuit(5, 40, rng, lima.coupling_map)
     prog = _check(c, [[(l, 1.0)] for l in _labels(rng, 5, 5)], nm, on, tilings=((6, 2), (3, 1)))
-    assert any((int(k) & 0xff) in (6, 7) for k, _ in prog["ops"])
+    assert any(int(op[2]) in (7, 8) for op in prog["ops"])  # Q_DENSE / Q_DENSE_SW
 
 
 def test_non_basis_gates_and_reset(lib):
@@ -114,7 +114,7 @@ def test_sweep_packing_respects_tile_and_order(lib):
         pb = 0
         for sw in prog["sweeps"]:
             pos = list(sw[1:1 + kq])
-            m = min(max(low, 0), kq - 2)
+            m = min(max(low, 1), kq - 2)
             assert pos == sorted(set(pos)) and pos[:m] == list(range(m))
             for sa, sb, _ in prog["passes"][pb:sw[9]]:
                 assert sa < kq and sb < kq and sa != sb

@@ -1,0 +1,171 @@
+"""Pins the CPU oracle to the known answers stored in the reference (tests/golden/*.json, made by
+tests/golden/make_golden.py from docs/demos/fake_backend_info.ipynb, docs/tutorials/device_params,
+docs/tutorials/data/mbd_datasets2 and docs/tutorials/h2-hamiltonian-qubit-params.txt)."""
+import numpy as np
+import pytest
+
+import helpers
+from oracle import dm, gates as G, noise_model as onm, sv
+
+
+@pytest.fixture(scope="module")
+def lima_props():
+    return helpers.golden("backends.json")["fakelima"]
+
+
+def _dump_superop(entry):
+    """Superoperator of one entry of Aer's noise_model.to_dict()['errors'] dump."""
+    k = len(entry["gate_qubits"][0])
+    total = np.zeros((4 ** k, 4 ** k), dtype=complex)
+    for prob, circ in zip(entry["probabilities"], entry["instructions"]):
+        s = np.eye(4 ** k, dtype=complex)
+        for op in circ:
+            name, qs = op["name"], op["qubits"]
+            if name == "kraus":
+                step = onm.kraus_to_superop([np.array(m["re"]) + 1j * np.array(m["im"]) for m in op["params"]])
+            elif name == "pauli":
+                label = op["params"][0]  # qiskit label: right-most char acts on qubits[0]
+                u = np.array([[1.0]], dtype=complex)
+                for ch in label:
+                    u = np.kron(u, G.PAULI[ch])
+                step = onm.unitary_superop(u)
+                qs = list(range(len(label)))
+            elif name == "reset":
+                step = onm.RESET_SUPEROP
+            else:
+                step = onm.unitary_superop(G.gate_matrix(name))
+            if k == 2 and len(qs) == 1:
+                step = onm.embed_1q_in_2q(step, qs[0])
+            s = step @ s
+        total += prob * s
+    return total
+
+
+def test_aer_noise_dump_channels(lima_props):
+    """Every quantum error Aer built for FakeLima (docs/demos/fake_backend_info.ipynb:135) equals the
+    oracle's channel; Kraus operators are printed with 8 digits, hence 5e-8."""
+    model = onm.from_backend(lima_props)
+    dump = [e for e in helpers.golden("aer_noise_lima.json") if e["type"] == "qerror"]
+    assert len(dump) == 28
+    seen = 0
+    for e in dump:
+        name, qubits = e["operations"][0], tuple(e["gate_qubits"][0])
+        ours = model.get(name, qubits)
+        assert ours is not None, (name, qubits)
+        assert np.max(np.abs(ours - _dump_superop(e))) < 5e-8, (name, qubits)
+        seen += 1
+    assert seen == len(model.local)  # nothing extra (rz carries no error: gate_length 0)
+
+
+def test_aer_noise_dump_probabilities_full_precision(lima_props):
+    """Mixture probabilities are printed in full precision: depolarizing {p_I, p_other} and the
+    thermal-relaxation {I, Z, reset} mixture (T2 <= T1 qubits)."""
+    model = onm.from_backend(lima_props)
+    dump = {(e["operations"][0], tuple(e["gate_qubits"][0])): e for e in helpers.golden("aer_noise_lima.json")
+            if e["type"] == "qerror"}
+    # cx(4,3): no depolarizing term, qubit 4 relaxes as a mixture -> probabilities are the mixture's
+    info = model.info[("cx", (4, 3))]
+    assert "depol_param" not in info
+    assert np.allclose(info["relax_mixtures"][0], dump[("cx", (4, 3))]["probabilities"], rtol=0, atol=1e-16)
+    assert dump[("cx", (4, 3))]["probabilities"] == [0.9719154155349994, 0.000898479654052871, 0.027186104810947742]
+    # cx(0,1): depolarizing o (kraus (x) kraus) -> 16 Pauli probabilities
+    info = model.info[("cx", (0, 1))]
+    assert np.allclose(info["depol_probabilities"], dump[("cx", (0, 1))]["probabilities"], rtol=0, atol=5e-15)
+    # sx(1): 1-qubit depolarizing o kraus
+    assert np.allclose(model.info[("sx", (1,))]["depol_probabilities"], dump[("sx", (1,))]["probabilities"], rtol=0, atol=1e-15)
+    # sx(2): T2 <= T1 and no depolarizing: pure {I, Z, reset} mixture
+    assert np.allclose(model.info[("sx", (2,))]["relax_mixtures"][0], dump[("sx", (2,))]["probabilities"], rtol=0, atol=1e-16)
+    # cx(2,1): depolarizing x mixture(qubit 2) -> 48 products
+    info = model.info[("cx", (2, 1))]
+    prod = np.outer(info["depol_probabilities"], info["relax_mixtures"][0]).reshape(-1)
+    assert np.allclose(prod, dump[("cx", (2, 1))]["probabilities"], rtol=0, atol=5e-15)
+
+
+def test_readout_matrices(lima_props):
+    model = onm.from_backend(lima_props)
+    assert np.allclose(model.readout[0], [[0.9882, 0.0118], [0.0404, 0.9596]], atol=1e-12)
+    assert np.allclose(model.readout[4], [[0.9808, 0.0192], [0.0958, 0.9042]], atol=1e-12)
+
+
+@pytest.mark.parametrize("backend,key", [("fakelima", "lima"), ("fakebelem", "belem")])
+def test_average_gate_infidelities(backend, key):
+    """mean / (std/len) of 1-average_gate_fidelity over the model's errors, as printed by
+    docs/demos/fake_backend_info.ipynb:202-204,233 (16 digits)."""
+    props = helpers.golden("backends.json")[backend]
+    kats = helpers.golden("kats.json")
+    model = onm.from_backend(props)
+    for gi, g in enumerate(("cx", "x", "sx")):
+        inf = [1 - onm.average_gate_fidelity(s) for (n, _), s in model.local.items() if n == g]
+        mean, sem = kats[f"{key}_infidelity_cx_x_sx"][gi]
+        assert abs(np.mean(inf) - mean) < 1e-15
+        assert abs(np.std(inf) / len(inf) - sem) < 1e-15
+    coh = onm.add_coherent_noise(props, theta=np.pi * 0.04, seed=0)
+    assert np.allclose(coh.info["thetas"], kats["coherent_thetas_8digits"], atol=5e-9)
+    inf = [1 - onm.average_gate_fidelity(s) for (n, _), s in coh.local.items() if n == "cx"]
+    mean, sem = kats[f"{key}_coherent_infidelity_cx_x_sx"][0]
+    assert abs(np.mean(inf) - mean) < 1e-15 and abs(np.std(inf) / len(inf) - sem) < 1e-15
+
+
+def test_h2_hamiltonians_fci():
+    """docs/tutorials/h2-hamiltonian-qubit-params.txt: min eigenvalue of the 2-qubit Hamiltonian =
+    FCI energy, and Tr(rho H) through the oracle's Pauli expectation equals <psi|H|psi>."""
+    for entry in helpers.golden("h2.json"):
+        obs = []
+        for coeff, ops in entry["terms"]:
+            chars = {int(o[1:]): o[0] for o in ops}
+            obs.append(("".join(chars.get(q, "I") for q in (1, 0)), coeff))
+        h = sum(c * np.kron(G.PAULI[l[0]], G.PAULI[l[1]]) for l, c in obs)
+        w, vecs = np.linalg.eigh(h)
+        assert abs(w[0] - entry["fci"]) < 1e-9
+        psi = vecs[:, 0]
+        rho_vec = np.outer(psi, psi.conj()).T.reshape(-1)
+        assert abs(dm.expval(rho_vec, 2, obs) - w[0]) < 1e-12
+        assert abs(sv.expval(psi, 2, obs) - w[0]) < 1e-12
+
+
+def test_pauli_expectation_matches_dense_kron():
+    rng = np.random.default_rng(0)
+    n = 4
+    a = rng.normal(size=(16, 16)) + 1j * rng.normal(size=(16, 16))
+    rho = a @ a.conj().T
+    rho /= np.trace(rho)
+    v = rho.T.reshape(-1)
+    for _ in range(40):
+        label = "".join(rng.choice(list("IXYZ"), size=n))
+        assert abs(dm.expval_pauli(v, n, label) - dm.expval_pauli_dense(v, n, label)) < 1e-13
+
+
+def test_stored_dataset_statistics(lima_props):
+    """docs/tutorials/data/mbd_datasets2/theta_0.05pi/val/step_{1,2}.json: 10k-shot ideal / noisy
+    single-Z values of FakeLima-transpiled circuits.  The exact oracle (density matrix + analytic
+    readout confusion) must agree within shot noise; stored value = -<Z>, index 0 <-> highest clbit
+    (docs/tutorials/mbd_utils.py:328-350)."""
+    from ml_qem_b200.circuit import parse_qasm
+
+    model = onm.from_backend(lima_props)
+    ideal_res, noisy_res, bare_res = [], [], []
+    for e in helpers.golden("mbd_sample.json"):
+        circ = parse_qasm(e["qasm"])
+        meas = [q for name, (q,), _ in [(o[0], o[1], o[2]) for o in circ.ops if o[0] == "measure"]]
+        ops = circ.gate_ops()
+        n = circ.num_qubits
+        psi = sv.simulate(n, ops)
+        rho = dm.simulate(n, ops, model)
+        rho0 = dm.simulate(n, ops, None)
+        for k, q in enumerate(meas):  # clbit k <- qubit q; stored index = len-1-k
+            label = "".join("Z" if (n - 1 - i) == q else "I" for i in range(n))
+            z_ideal = sv.expval_pauli(psi, n, label).real
+            z_noisy = dm.expval_pauli(rho, n, label).real
+            a, b = model.readout[q][0, 1], model.readout[q][1, 0]  # P(1|0), P(0|1)
+            z_meas = (1 - a - b) * z_noisy + (b - a)
+            idx = len(meas) - 1 - k
+            ideal_res.append(-z_ideal - e["ideal_exp_value"][idx])
+            noisy_res.append(-z_meas - e["noisy_exp_values"][0][idx])
+            bare_res.append(-((1 - a - b) * dm.expval_pauli(rho0, n, label).real + (b - a)) - e["noisy_exp_values"][0][idx])
+    ideal_res, noisy_res, bare_res = map(np.array, (ideal_res, noisy_res, bare_res))
+    shot = 1.0 / np.sqrt(10000)
+    assert np.sqrt(np.mean(ideal_res ** 2)) < shot and np.max(np.abs(ideal_res)) < 5 * shot
+    assert np.sqrt(np.mean(noisy_res ** 2)) < shot and abs(np.mean(noisy_res)) < 1.5e-3
+    assert np.max(np.abs(noisy_res)) < 5 * shot
+    # the gate noise matters: without it the residual is several times shot noise
+    assert np.sqrt(np.mean(bare_res ** 2)) > 2.5 * np.sqrt(np.mean(noisy_res ** 2))
