@@ -165,17 +165,15 @@ typedef struct bwq_program bwq_program;
 int bwq_lower_dm(const bwq_noise_table* table, const bwq_batch* batch, int32_t circuit,
                  int32_t tile_qubits, int32_t low_qubits, bwq_program** out);
 void bwq_program_free(bwq_program* p);
-/* Sizes: [0]=n_active, [1]=n_sweeps, [2]=n_passes, [3]=n_ops, [4]=n_mats (doubles), [5]=status,
- * [6]=n_terms, [7]=n_gates */
+/* Sizes: [0]=n_active, [1]=n_sweeps, [2]=n_passes, [3]=n_prog (8-byte words), [4]=needs_dense,
+ * [5]=status, [6]=n_terms, [7]=n_gates */
 int bwq_program_sizes(const bwq_program* p, int64_t sizes[8]);
-/* Copies the program out.  active_qubits[n_active] (physical qubit of digit d);
- * sweeps: per sweep 10 int32 {pass_begin, pos[0..7], pass_end}; passes: per pass 3 int32
- * {slot_a, slot_b, op_end}; ops: per macro-op 6 int64 {pre_a, pre_b, twoq, off_a, off_b, off_2}
- * (kinds: ml_qem_b200/csrc/program.h);
- * mats[n_mats]; term_index[n_terms] (element index, -1 = term vanishes); term_coeff. */
-int bwq_program_read(const bwq_program* p, int32_t* active_qubits, int32_t* sweeps,
-                     int32_t* passes, int64_t* ops, double* mats, int64_t* term_index,
-                     double* term_coeff);
+/* Copies the program out.  active_qubits[n_active] (physical qubit of digit d, -1 = padding);
+ * sweeps: per sweep 10 int32 {block offset (16-byte units into prog), pos[0..7], block length
+ * (16-byte units)}; prog[n_prog]: the sweep blocks (layout: ml_qem_b200/csrc/program.h);
+ * term_index[n_terms] (element index, -1 = term vanishes); term_coeff. */
+int bwq_program_read(const bwq_program* p, int32_t* active_qubits, int32_t* sweeps, uint64_t* prog,
+                     int64_t* term_index, double* term_coeff);
 
 #ifdef __cplusplus
 }

@@ -82,7 +82,7 @@ struct DmPlan {
   bool valid = false;
   int tile_qubits = 6;
   int64_t n_obs = 0;
-  size_t o_range = 0, o_sweeps = 0, o_passes = 0, o_ops = 0, o_mats = 0, o_tidx = 0, o_tcoef = 0, o_obs = 0, blob_bytes = 0;
+  size_t o_range = 0, o_sweeps = 0, o_prog = 0, o_tidx = 0, o_tcoef = 0, o_obs = 0, blob_bytes = 0;
   std::vector<int64_t> ob_off;
   std::vector<DmChunk> chunks;
   std::vector<std::pair<int64_t, double>> host_fix;
@@ -174,9 +174,9 @@ extern "C" int bwq_create(int device, bwq_ctx** out) {
   if ((e = cudaGetDeviceProperties(&prop, device)) != cudaSuccess) return bail(e, "cudaGetDeviceProperties");
   ctx->smem_optin = prop.sharedMemPerBlockOptin;
   ctx->sm_count = prop.multiProcessorCount;
-  if ((e = cudaFuncSetAttribute(dm_sweep_kernel<7, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, 8 << 14)) != cudaSuccess)
+  if ((e = cudaFuncSetAttribute(dm_sweep_kernel<7, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (8 << 14) + kBlockBytes)) != cudaSuccess)
     return bail(e, "cudaFuncSetAttribute(dm_sweep_kernel<7>) -- was the library built for this GPU (sm_100a)?");
-  if ((e = cudaFuncSetAttribute(dm_sweep_kernel<7, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, 8 << 14)) != cudaSuccess)
+  if ((e = cudaFuncSetAttribute(dm_sweep_kernel<7, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (8 << 14) + kBlockBytes)) != cudaSuccess)
     return bail(e, "cudaFuncSetAttribute(dm_sweep_kernel<7, full>)");
   if ((e = cudaFuncSetAttribute(sv_circuit_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 16 << 12)) != cudaSuccess)
     return bail(e, "cudaFuncSetAttribute(sv_circuit_kernel)");
@@ -272,7 +272,7 @@ static int host_threads(const bwq_ctx* ctx) {
 }
 
 template <int KQ, bool FULL> static cudaError_t launch_sweep(const DmLaunch& L, int sweep, int64_t n_cta, cudaStream_t s) {
-  dm_sweep_kernel<KQ, FULL><<<(unsigned)n_cta, SweepCfg<KQ>::kThreads, sizeof(double) << (2 * KQ), s>>>(L, sweep);
+  dm_sweep_kernel<KQ, FULL><<<(unsigned)n_cta, SweepCfg<KQ>::kThreads, (sizeof(double) << (2 * KQ)) + kBlockBytes, s>>>(L, sweep);
   return cudaGetLastError();
 }
 
@@ -330,28 +330,21 @@ static int dm_prepare_impl(bwq_ctx* ctx, const bwq_batch* b, int32_t* out_status
   const int M = (int)order.size();
 
   // ---- merge the programs into one blob (sorted order)
-  std::vector<int64_t> sw_off(M + 1, 0), ps_off(M + 1, 0), op_off(M + 1, 0), mt_off(M + 1, 0), tm_off(M + 1, 0);
+  std::vector<int64_t> sw_off(M + 1, 0), pg_off(M + 1, 0), tm_off(M + 1, 0);
   P.ob_off.assign(M + 1, 0);
   for (int i = 0; i < M; ++i) {
     const CircuitProgram& p = progs[order[i]];
     sw_off[i + 1] = sw_off[i] + (int64_t)p.sweeps.size();
-    ps_off[i + 1] = ps_off[i] + (int64_t)p.passes.size();
-    op_off[i + 1] = op_off[i] + (int64_t)p.ops.size();
-    mt_off[i + 1] = mt_off[i] + (int64_t)p.mats.size();
+    pg_off[i + 1] = pg_off[i] + (int64_t)p.prog.size();
     tm_off[i + 1] = tm_off[i] + (int64_t)p.term_index.size();
     P.ob_off[i + 1] = P.ob_off[i] + (b->obs_offsets[order[i] + 1] - b->obs_offsets[order[i]]);
   }
-  if (ps_off[M] > INT32_MAX || op_off[M] > INT32_MAX || sw_off[M] > INT32_MAX)
+  if (sw_off[M] > INT32_MAX || pg_off[M] / 2 >= (int64_t(1) << 32))
     return fail(ctx, BWQ_ERR_ARG, "batch too large for 32-bit program indices; split the batch");
-  // matrix buffer = [noise table | per-circuit matrices], one base pointer for the kernels
-  const int64_t noise_n = ((int64_t)ctx->noise.data.size() + 31) & ~int64_t(31);
-  if (noise_n + mt_off[M] >= (int64_t(1) << 31)) return fail(ctx, BWQ_ERR_ARG, "batch matrices exceed 2^31 doubles; split the batch");
   Blob blob;
   P.o_range = blob.add(sizeof(int32_t) * 2 * (size_t)M);
   P.o_sweeps = blob.add(sizeof(SweepDesc) * (size_t)sw_off[M]);
-  P.o_passes = blob.add(sizeof(PassDesc) * (size_t)ps_off[M]);
-  P.o_ops = blob.add(sizeof(MacroOp) * (size_t)op_off[M]);
-  P.o_mats = blob.add(sizeof(double) * (size_t)(noise_n + mt_off[M]));
+  P.o_prog = blob.add(sizeof(uint64_t) * (size_t)pg_off[M]);
   P.o_tidx = blob.add(sizeof(int64_t) * (size_t)tm_off[M]);
   P.o_tcoef = blob.add(sizeof(double) * (size_t)tm_off[M]);
   P.o_obs = blob.add(sizeof(int64_t) * 4 * (size_t)P.ob_off[M]);
@@ -370,23 +363,9 @@ static int dm_prepare_impl(bwq_ctx* ctx, const bwq_batch* b, int32_t* out_status
     SweepDesc* sw = (SweepDesc*)(hb + P.o_sweeps) + sw_off[i];
     for (size_t k = 0; k < p.sweeps.size(); ++k) {
       sw[k] = p.sweeps[k];
-      sw[k].pass_begin += (int32_t)ps_off[i];
-      sw[k].pass_end += (int32_t)ps_off[i];
+      sw[k].blk_q16 += (uint32_t)(pg_off[i] / 2);
     }
-    PassDesc* ps = (PassDesc*)(hb + P.o_passes) + ps_off[i];
-    for (size_t k = 0; k < p.passes.size(); ++k) {
-      ps[k] = p.passes[k];
-      ps[k].op_begin += (int32_t)op_off[i];
-      ps[k].op_end += (int32_t)op_off[i];
-    }
-    MacroOp* ops = (MacroOp*)(hb + P.o_ops) + op_off[i];
-    const uint32_t rel = (uint32_t)(noise_n + mt_off[i]);
-    auto fix = [&](uint32_t off) { return (off & kLocalMat) ? (off & ~kLocalMat) + rel : off; };
-    for (size_t k = 0; k < p.ops.size(); ++k) {
-      ops[k] = p.ops[k];
-      ops[k].off_a = fix(ops[k].off_a); ops[k].off_b = fix(ops[k].off_b); ops[k].off_2 = fix(ops[k].off_2);
-    }
-    if (!p.mats.empty()) std::memcpy((double*)(hb + P.o_mats) + noise_n + mt_off[i], p.mats.data(), p.mats.size() * sizeof(double));
+    if (!p.prog.empty()) std::memcpy((uint64_t*)(hb + P.o_prog) + pg_off[i], p.prog.data(), p.prog.size() * sizeof(uint64_t));
     if (!p.term_index.empty()) {
       std::memcpy((int64_t*)(hb + P.o_tidx) + tm_off[i], p.term_index.data(), p.term_index.size() * sizeof(int64_t));
       std::memcpy((double*)(hb + P.o_tcoef) + tm_off[i], p.term_coeff.data(), p.term_coeff.size() * sizeof(double));
@@ -403,8 +382,7 @@ static int dm_prepare_impl(bwq_ctx* ctx, const bwq_batch* b, int32_t* out_status
       d[3] = o;
     }
   });
-  if (M > 0 && !ctx->noise.data.empty()) std::memcpy(hb + P.o_mats, ctx->noise.data.data(), ctx->noise.data.size() * sizeof(double));
-  for (int i = 0; i < M; ++i) { P.n_gates += progs[order[i]].n_gates; P.n_passes += (int64_t)progs[order[i]].passes.size(); }
+  for (int i = 0; i < M; ++i) { P.n_gates += progs[order[i]].n_gates; P.n_passes += progs[order[i]].n_passes; }
 
   // ---- chunk plan: circuits of equal width, as many resident states as the budget allows
   size_t free_b = 0, total_b = 0;
@@ -509,9 +487,7 @@ static int dm_execute_impl(bwq_ctx* ctx, double* out_vals, bool out_on_device) {
     L.first_circuit = ch.first;
     L.sweep_range = (const int32_t*)(db + P.o_range);
     L.sweeps = (const SweepDesc*)(db + P.o_sweeps);
-    L.passes = (const PassDesc*)(db + P.o_passes);
-    L.ops = (const MacroOp*)(db + P.o_ops);
-    L.mats = (const double*)(db + P.o_mats);
+    L.prog = (const uint4*)(db + P.o_prog);
     const int64_t tiles = int64_t(1) << (2 * (ch.nd - ch.kq));
     if (ci < n_ev) CK(cudaEventRecord(ctx->chunk_ev[2 * ci], st));
     for (size_t sidx = 0; sidx < ch.live.size(); ++sidx) {
@@ -782,16 +758,6 @@ extern "C" int bwq_lower_dm(const bwq_noise_table* table, const bwq_batch* batch
   lo.low_qubits = low_qubits < 0 ? 0 : (low_qubits ? low_qubits : 2);
   bwq_program* p = new bwq_program();
   lower_dm_circuit(nt, *batch, circuit, lo, &p->p);
-  // same matrix-buffer layout as a run: [noise table | circuit matrices]
-  {
-    const int64_t noise_n = ((int64_t)nt.data.size() + 31) & ~int64_t(31);
-    std::vector<double> all((size_t)noise_n, 0.0);
-    std::copy(nt.data.begin(), nt.data.end(), all.begin());
-    all.insert(all.end(), p->p.mats.begin(), p->p.mats.end());
-    p->p.mats.swap(all);
-    auto fix = [&](uint32_t off) { return (off & kLocalMat) ? (off & ~kLocalMat) + (uint32_t)noise_n : off; };
-    for (auto& op : p->p.ops) { op.off_a = fix(op.off_a); op.off_b = fix(op.off_b); op.off_2 = fix(op.off_2); }
-  }
   *out = p;
   return BWQ_OK;
 }
@@ -800,37 +766,25 @@ extern "C" void bwq_program_free(bwq_program* p) { delete p; }
 
 extern "C" int bwq_program_sizes(const bwq_program* p, int64_t s[8]) {
   if (!p || !s) return BWQ_ERR_ARG;
-  s[0] = p->p.n_digits; s[1] = (int64_t)p->p.sweeps.size(); s[2] = (int64_t)p->p.passes.size();
-  s[3] = (int64_t)p->p.ops.size(); s[4] = (int64_t)p->p.mats.size(); s[5] = p->p.status;
+  s[0] = p->p.n_digits; s[1] = (int64_t)p->p.sweeps.size(); s[2] = p->p.n_passes;
+  s[3] = (int64_t)p->p.prog.size(); s[4] = p->p.needs_dense ? 1 : 0; s[5] = p->p.status;
   s[6] = (int64_t)p->p.term_index.size(); s[7] = p->p.n_gates;
   return BWQ_OK;
 }
 
-extern "C" int bwq_program_read(const bwq_program* p, int32_t* active, int32_t* sweeps, int32_t* passes,
-                                int64_t* ops, double* mats, int64_t* term_index, double* term_coeff) {
+extern "C" int bwq_program_read(const bwq_program* p, int32_t* active, int32_t* sweeps, uint64_t* prog,
+                                int64_t* term_index, double* term_coeff) {
   if (!p) return BWQ_ERR_ARG;
   const CircuitProgram& q = p->p;
-  const int kq = q.sweeps.empty() ? 0 : 0;
-  (void)kq;
   if (active) for (size_t i = 0; i < q.active.size(); ++i) active[i] = q.active[i];
   if (sweeps)
     for (size_t i = 0; i < q.sweeps.size(); ++i) {
       int32_t* s = sweeps + 10 * i;
-      s[0] = q.sweeps[i].pass_begin;
+      s[0] = (int32_t)q.sweeps[i].blk_q16;
       for (int k = 0; k < 8; ++k) s[1 + k] = q.sweeps[i].pos[k];
-      s[9] = q.sweeps[i].pass_end;
+      s[9] = (int32_t)q.sweeps[i].blk_len_q16;
     }
-  if (passes)
-    for (size_t i = 0; i < q.passes.size(); ++i) {
-      passes[3 * i] = q.passes[i].sa; passes[3 * i + 1] = q.passes[i].sb; passes[3 * i + 2] = q.passes[i].op_end;
-    }
-  if (ops)
-    for (size_t i = 0; i < q.ops.size(); ++i) {
-      int64_t* o = ops + 6 * i;
-      o[0] = q.ops[i].pre_a; o[1] = q.ops[i].pre_b; o[2] = q.ops[i].twoq;
-      o[3] = q.ops[i].off_a; o[4] = q.ops[i].off_b; o[5] = q.ops[i].off_2;
-    }
-  if (mats && !q.mats.empty()) std::memcpy(mats, q.mats.data(), q.mats.size() * sizeof(double));
+  if (prog && !q.prog.empty()) std::memcpy(prog, q.prog.data(), q.prog.size() * sizeof(uint64_t));
   if (term_index && !q.term_index.empty()) std::memcpy(term_index, q.term_index.data(), q.term_index.size() * sizeof(int64_t));
   if (term_coeff && !q.term_coeff.empty()) std::memcpy(term_coeff, q.term_coeff.data(), q.term_coeff.size() * sizeof(double));
   return BWQ_OK;

@@ -20,9 +20,7 @@ struct DmLaunch {
   int32_t first_circuit;       // index (sorted order) of slot 0
   const int32_t* sweep_range;  // [2 * n_circuits] absolute {begin, end} per sorted circuit
   const SweepDesc* sweeps;
-  const PassDesc* passes;
-  const MacroOp* ops;
-  const double* mats;          // [noise table copy | per-circuit matrices]
+  const uint4* prog;           // sweep blocks (16-byte units)
 };
 
 // ---------------------------------------------------------------------------------------------
@@ -43,7 +41,7 @@ template <bool ON_B> __device__ __forceinline__ void op_dense1(double (&v)[16], 
     const double x0 = v[idx1<ON_B>(0, o)], x1 = v[idx1<ON_B>(1, o)], x2 = v[idx1<ON_B>(2, o)], x3 = v[idx1<ON_B>(3, o)];
 #pragma unroll
     for (int i = 0; i < 4; ++i) {
-      const double2 a = __ldg(m2 + 2 * i), b = __ldg(m2 + 2 * i + 1);
+      const double2 a = m2[2 * i], b = m2[2 * i + 1];
       v[idx1<ON_B>(i, o)] = fma(b.y, x3, fma(b.x, x2, fma(a.y, x1, a.x * x0)));
     }
   }
@@ -55,7 +53,7 @@ template <bool ON_B> __device__ __forceinline__ void op_aff1(double (&v)[16], co
   const double2* m2 = reinterpret_cast<const double2*>(m);
   double2 a[6];
 #pragma unroll
-  for (int i = 0; i < 6; ++i) a[i] = __ldg(m2 + i);
+  for (int i = 0; i < 6; ++i) a[i] = m2[i];
 #pragma unroll
   for (int o = 0; o < 4; ++o) {
     const double x0 = v[idx1<ON_B>(0, o)], x1 = v[idx1<ON_B>(1, o)], x2 = v[idx1<ON_B>(2, o)], x3 = v[idx1<ON_B>(3, o)];
@@ -70,8 +68,8 @@ template <bool ON_B> __device__ __forceinline__ void op_aff1(double (&v)[16], co
 
 // rz / phase as three in-place shears: x -= t y; y += s x; x -= t y; then the optional sign
 template <bool ON_B> __device__ __forceinline__ void op_rot(double (&v)[16], const double* __restrict__ m) {
-  const double2 ts = __ldg(reinterpret_cast<const double2*>(m));
-  const double sign = __ldg(m + 2);
+  const double2 ts = *reinterpret_cast<const double2*>(m);
+  const double sign = m[2];
 #pragma unroll
   for (int o = 0; o < 4; ++o) {
     double x = v[idx1<ON_B>(1, o)], y = v[idx1<ON_B>(2, o)];
@@ -112,7 +110,7 @@ template <bool SW, bool WITH_CX> __device__ __forceinline__ void op_relax2(doubl
   const double2* m2 = reinterpret_cast<const double2*>(m);
   double p[26];
 #pragma unroll
-  for (int i = 0; i < 13; ++i) { const double2 t = __ldg(m2 + i); p[2 * i] = t.x; p[2 * i + 1] = t.y; }
+  for (int i = 0; i < 13; ++i) { const double2 t = m2[i]; p[2 * i] = t.x; p[2 * i + 1] = t.y; }
   double y[16];  // input in (q0,q1) index order, after the optional CX
 #pragma unroll
   for (int i = 0; i < 16; ++i) {
@@ -150,7 +148,7 @@ template <bool SW> __device__ __forceinline__ void op_dense2(double (&v)[16], co
       double s = 0.0;
 #pragma unroll
       for (int jj = 0; jj < 8; ++jj) {
-        const double2 t = __ldg(m2 + row * 8 + jj);
+        const double2 t = m2[row * 8 + jj];
         const int j = 2 * jj;
         s = fma(t.x, w[idx2<SW>(j & 3, j >> 2)], s);
         s = fma(t.y, w[idx2<SW>((j + 1) & 3, (j + 1) >> 2)], s);
@@ -159,19 +157,22 @@ template <bool SW> __device__ __forceinline__ void op_dense2(double (&v)[16], co
     }
 }
 
+// ops and parameters of a pass, read from the sweep block staged in shared memory
 template <bool FULL>
-__device__ __forceinline__ void run_ops(double (&v)[16], const DmLaunch& L, int op_begin, int op_end) {
-  const double* __restrict__ mats = L.mats;
-  for (int o = op_begin; o < op_end; ++o) {
-    const uint4 raw = __ldg(reinterpret_cast<const uint4*>(L.ops + o));
+__device__ __forceinline__ void run_ops(double (&v)[16], const double* __restrict__ blk, int ops_q16, int n_ops) {
+  const uint4* ops = reinterpret_cast<const uint4*>(blk) + ops_q16;
+  for (int o = 0; o < n_ops; ++o) {
+    const uint4 raw = ops[o];
     const uint32_t pre_a = raw.x & 0xffu, pre_b = (raw.x >> 8) & 0xffu, twoq = (raw.x >> 16) & 0xffu;
-    if (pre_a == P_AFF) op_aff1<false>(v, mats + raw.y);
-    else if (pre_a == P_ROT) op_rot<false>(v, mats + raw.y);
-    else if (FULL && pre_a == P_DENSE) op_dense1<false>(v, mats + raw.y);
-    if (pre_b == P_AFF) op_aff1<true>(v, mats + raw.z);
-    else if (pre_b == P_ROT) op_rot<true>(v, mats + raw.z);
-    else if (FULL && pre_b == P_DENSE) op_dense1<true>(v, mats + raw.z);
-    const double* m2q = mats + raw.w;
+    const double* ma = blk + (raw.y & 0xffffu);
+    const double* mb = blk + (raw.y >> 16);
+    const double* m2q = blk + (raw.z & 0xffffu);
+    if (pre_a == P_AFF) op_aff1<false>(v, ma);
+    else if (pre_a == P_ROT) op_rot<false>(v, ma);
+    else if (FULL && pre_a == P_DENSE) op_dense1<false>(v, ma);
+    if (pre_b == P_AFF) op_aff1<true>(v, mb);
+    else if (pre_b == P_ROT) op_rot<true>(v, mb);
+    else if (FULL && pre_b == P_DENSE) op_dense1<true>(v, mb);
     switch (twoq) {
       case Q_CXN_AB: op_relax2<false, true>(v, m2q); break;
       case Q_CXN_BA: op_relax2<true, true>(v, m2q); break;
@@ -185,6 +186,12 @@ __device__ __forceinline__ void run_ops(double (&v)[16], const DmLaunch& L, int 
     }
   }
 }
+
+__device__ __forceinline__ void cp_async16(void* smem_dst, const void* gmem_src) {
+  const uint32_t d = static_cast<uint32_t>(__cvta_generic_to_shared(smem_dst));
+  asm volatile("cp.async.cg.shared.global [%0], [%1], 16;\n" ::"r"(d), "l"(gmem_src) : "memory");
+}
+__device__ __forceinline__ void cp_async_wait_all() { asm volatile("cp.async.wait_all;\n" ::: "memory"); }
 
 // ---------------------------------------------------------------------------------------------
 // shared-memory swizzle.  Tile element j (digits D0..D6, 2 bits each) lives at swz(j): the low
@@ -245,10 +252,16 @@ dm_sweep_kernel(const DmLaunch L, const int sweep_idx) {
   const int sw_i = __ldg(L.sweep_range + 2 * circ) + sweep_idx;
   if (sw_i >= __ldg(L.sweep_range + 2 * circ + 1)) return;  // this circuit has fewer sweeps
   const int4 swraw = __ldg(reinterpret_cast<const int4*>(L.sweeps + sw_i));
-  const int pass_begin = swraw.x, pass_end = swraw.y;
+  // stage the sweep's program block (descriptors + parameters) while the tile streams in
+  double* pbuf = tile + E;
+  {
+    const uint4* src = L.prog + uint32_t(swraw.x);
+    const int len = swraw.y;
+    for (int i = tid; i < len; i += T) cp_async16(reinterpret_cast<uint4*>(pbuf) + i, src + i);
+  }
   int pos[KQ];
   {
-    const uint64_t pk = (uint64_t(uint32_t(swraw.w)) << 32) | uint32_t(swraw.z);
+    const uint64_t pk = (uint64_t(uint32_t(swraw.w)) << 32) | uint32_t(swraw.z);  // pos[0..7]
 #pragma unroll
     for (int s = 0; s < KQ; ++s) pos[s] = int((pk >> (8 * s)) & 0xff);
   }
@@ -296,7 +309,7 @@ dm_sweep_kernel(const DmLaunch L, const int sweep_idx) {
     for (int k = 0; k < NIT; ++k) {
       if (NIT * T != U && tid + k * T >= U) break;
       const int64_t off = off_thr | deposit<KQ>(2u * uint32_t(k * T), pos);
-      val[k] = *reinterpret_cast<const double2*>(g + off);
+      val[k] = __ldcg(reinterpret_cast<const double2*>(g + off));  // stream past L1
     }
 #pragma unroll
     for (int k = 0; k < NIT; ++k) {
@@ -307,10 +320,14 @@ dm_sweep_kernel(const DmLaunch L, const int sweep_idx) {
   }
 
   // ---- register passes
-  for (int p = pass_begin; p < pass_end; ++p) {
-    __syncthreads();
-    const int4 praw = __ldg(reinterpret_cast<const int4*>(L.passes + p));
-    const int sa = praw.z & 0xff, sb = (praw.z >> 8) & 0xff;
+  cp_async_wait_all();
+  __syncthreads();
+  const int n_passes = reinterpret_cast<const int*>(pbuf)[0];
+  for (int p = 0; p < n_passes; ++p) {
+    if (p) __syncthreads();
+    const uint2 praw = *reinterpret_cast<const uint2*>(pbuf + 2 * (1 + p));
+    const int ops_q16 = praw.x & 0xffffu, n_ops = praw.x >> 16;
+    const int sa = praw.y & 0xffu, sb = (praw.y >> 8) & 0xffu;
     const int lo = min(sa, sb), hi = max(sa, sb);
     uint32_t oa[4], ob[4];
 #pragma unroll
@@ -325,7 +342,7 @@ dm_sweep_kernel(const DmLaunch L, const int sweep_idx) {
       for (int db = 0; db < 4; ++db)
 #pragma unroll
         for (int da = 0; da < 4; ++da) v[da + 4 * db] = tile[b0 ^ oa[da] ^ ob[db]];
-      run_ops<FULL>(v, L, praw.x, praw.y);
+      run_ops<FULL>(v, pbuf, ops_q16, n_ops);
 #pragma unroll
       for (int db = 0; db < 4; ++db)
 #pragma unroll

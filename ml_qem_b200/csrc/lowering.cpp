@@ -434,56 +434,144 @@ void lower_dm_circuit(const NoiseTable& noise, const bwq_batch& b, int c, const 
     flush(d, passes[last[d]]);
   }
 
+  // ---- parameter sizes (8-byte words) and sources
+  auto pre_words = [](uint8_t k) { return k == P_ROT ? 4 : k == P_AFF ? 12 : k == P_DENSE ? 16 : 0; };
+  auto two_words = [](uint8_t k) {
+    return (k == Q_CXN_AB || k == Q_CXN_BA || k == Q_RELAX || k == Q_RELAX_SW) ? 26 : (k == Q_DENSE || k == Q_DENSE_SW) ? 256 : 0;
+  };
+  auto src_ptr = [&](uint32_t off) -> const double* {
+    return (off & kLocalMat) ? &out->mats[off & ~kLocalMat] : &noise.data[off];
+  };
+  // bytes a pass adds to a sweep block; parameters already present (same source) are shared
+  struct Seen { uint32_t key; uint16_t off; };
+  auto pass_bytes = [&](const HostPass& p, const std::vector<Seen>& seen) {
+    int bytes = (int)sizeof(PassHdr) + (int)sizeof(BlockOp) * (int)p.ops.size();
+    std::vector<uint32_t> mine;
+    auto add = [&](uint32_t key, int words) {
+      if (!words) return;
+      for (const Seen& sn : seen) if (sn.key == key) return;
+      for (uint32_t k : mine) if (k == key) return;
+      mine.push_back(key);
+      bytes += ((words + 1) & ~1) * 8;
+    };
+    for (const MacroOp& o : p.ops) { add(o.off_a, pre_words(o.pre_a)); add(o.off_b, pre_words(o.pre_b)); add(o.off_2, two_words(o.twoq)); }
+    return bytes;
+  };
+  // split passes whose block alone would not fit the shared-memory program buffer
+  {
+    const int cap = kBlockBytes - (int)sizeof(BlockHdr);
+    std::vector<HostPass> split;
+    for (HostPass& p : passes) {
+      if (pass_bytes(p, {}) <= cap) { split.push_back(std::move(p)); continue; }
+      HostPass cur{p.qa, p.qb, {}};
+      for (const MacroOp& o : p.ops) {
+        cur.ops.push_back(o);
+        if (pass_bytes(cur, {}) > cap) {
+          cur.ops.pop_back();
+          if (cur.ops.empty()) { out->status = BWQ_CIRC_BAD_OP; return; }  // a single op always fits
+          split.push_back(cur);
+          cur.ops.assign(1, o);
+        }
+      }
+      if (!cur.ops.empty()) split.push_back(cur);
+    }
+    passes.swap(split);
+  }
+
   // ---- passes -> sweeps (greedy in program order; a pass that does not fit blocks its qubits)
   // tile = min(tile_qubits, n) digits, at least 3 when the state is larger than the tile so that
   // digit 0 (always resident: 16-byte global accesses) leaves two free slots for any pass
   const int kq = std::min(std::max(opt.tile_qubits, 3), std::min(nd, kMaxTileQubits));
   const int mlow = (nd <= kq) ? 0 : std::min(std::max(opt.low_qubits, 1), kq - 2);
   const int np = (int)passes.size();
+  out->n_passes = np;
   std::vector<char> done(np, 0);
   int first = 0, remaining = np;
   std::vector<char> in_tile(nd), blocked(nd);
+  std::vector<int> sel;
+  std::vector<Seen> seen;
   while (remaining > 0) {
     std::fill(in_tile.begin(), in_tile.end(), 0);
     std::fill(blocked.begin(), blocked.end(), 0);
     int nt = 0, nblocked = 0;
     for (int d = 0; d < mlow; ++d) { in_tile[d] = 1; ++nt; }
-    SweepDesc sw{};
-    sw.pass_begin = (int)out->passes.size();
+    sel.clear();
+    seen.clear();
+    int bytes = (int)sizeof(BlockHdr);
     while (first < np && done[first]) ++first;
     for (int i = first; i < np && nblocked < nd; ++i) {
       if (done[i]) continue;
       const HostPass& p = passes[i];
       auto block = [&](int d) { if (!blocked[d]) { blocked[d] = 1; ++nblocked; } };
       if (blocked[p.qa] || blocked[p.qb]) { block(p.qa); block(p.qb); continue; }
-      int need = (!in_tile[p.qa]) + (!in_tile[p.qb]);
-      if (nt + need > kq) { block(p.qa); block(p.qb); continue; }
+      const int need = (!in_tile[p.qa]) + (!in_tile[p.qb]);
+      const int add = pass_bytes(p, seen);
+      if (nt + need > kq || bytes + add > kBlockBytes) { block(p.qa); block(p.qb); continue; }
       if (!in_tile[p.qa]) { in_tile[p.qa] = 1; ++nt; }
       if (!in_tile[p.qb]) { in_tile[p.qb] = 1; ++nt; }
       done[i] = 1;
       --remaining;
-      PassDesc pd{};
-      pd.op_begin = (int)out->ops.size();
-      out->ops.insert(out->ops.end(), p.ops.begin(), p.ops.end());
-      pd.op_end = (int)out->ops.size();
-      pd.sa = (uint8_t)p.qa;  // digit for now; converted to slot below
-      pd.sb = (uint8_t)p.qb;
-      out->passes.push_back(pd);
+      sel.push_back(i);
+      bytes += add;
+      // remember the parameters this pass brings (offsets are assigned at emission)
+      for (const MacroOp& o : p.ops) {
+        auto note = [&](uint32_t key, int words) {
+          if (!words) return;
+          for (const Seen& sn : seen) if (sn.key == key) return;
+          seen.push_back(Seen{key, 0});
+        };
+        note(o.off_a, pre_words(o.pre_a)); note(o.off_b, pre_words(o.pre_b)); note(o.off_2, two_words(o.twoq));
+      }
     }
+    if (sel.empty()) { out->status = BWQ_CIRC_BAD_OP; return; }  // cannot happen
     for (int d = 0; d < nd && nt < kq; ++d) if (!in_tile[d]) { in_tile[d] = 1; ++nt; }
     int slot_of[kMaxDmQubits];
+    SweepDesc sw{};
     int s = 0;
     for (int d = 0; d < nd; ++d) if (in_tile[d]) { sw.pos[s] = (uint8_t)d; slot_of[d] = s++; }
-    sw.pass_end = (int)out->passes.size();
-    if (sw.pass_end == sw.pass_begin) { out->status = BWQ_CIRC_BAD_OP; return; }  // cannot happen
-    for (int i = sw.pass_begin; i < sw.pass_end; ++i) {
-      out->passes[i].sa = (uint8_t)slot_of[out->passes[i].sa];
-      out->passes[i].sb = (uint8_t)slot_of[out->passes[i].sb];
+
+    // ---- emit the block
+    size_t n_ops_total = 0;
+    for (int i : sel) n_ops_total += passes[i].ops.size();
+    const size_t hdr_words = (sizeof(BlockHdr) + sizeof(PassHdr) * sel.size() + sizeof(BlockOp) * n_ops_total) / 8;
+    const size_t blk_begin = out->prog.size();
+    out->prog.resize(blk_begin + (size_t)bytes / 8, 0);
+    uint64_t* blk = out->prog.data() + blk_begin;
+    BlockHdr* bh = reinterpret_cast<BlockHdr*>(blk);
+    bh->n_passes = (int32_t)sel.size();
+    PassHdr* ph = reinterpret_cast<PassHdr*>(blk + sizeof(BlockHdr) / 8);
+    BlockOp* bo = reinterpret_cast<BlockOp*>(blk + (sizeof(BlockHdr) + sizeof(PassHdr) * sel.size()) / 8);
+    size_t op_cursor = 0, par_cursor = hdr_words;
+    seen.clear();
+    auto place = [&](uint32_t key, int words) -> uint16_t {
+      if (!words) return 0;
+      for (const Seen& sn : seen) if (sn.key == key) return sn.off;
+      const uint16_t off = (uint16_t)par_cursor;
+      std::memcpy(blk + par_cursor, src_ptr(key), (size_t)words * 8);
+      par_cursor += (size_t)((words + 1) & ~1);
+      seen.push_back(Seen{key, off});
+      return off;
+    };
+    for (size_t k = 0; k < sel.size(); ++k) {
+      const HostPass& p = passes[sel[k]];
+      ph[k].ops_q16 = (uint16_t)((sizeof(BlockHdr) + sizeof(PassHdr) * sel.size() + sizeof(BlockOp) * op_cursor) / 16);
+      ph[k].n_ops = (uint16_t)p.ops.size();
+      ph[k].sa = (uint8_t)slot_of[p.qa];
+      ph[k].sb = (uint8_t)slot_of[p.qb];
+      for (const MacroOp& o : p.ops) {
+        BlockOp& d = bo[op_cursor++];
+        d.pre_a = o.pre_a; d.pre_b = o.pre_b; d.twoq = o.twoq;
+        d.off_a = place(o.off_a, pre_words(o.pre_a));
+        d.off_b = place(o.off_b, pre_words(o.pre_b));
+        d.off_2 = place(o.off_2, two_words(o.twoq));
+        if (o.pre_a == P_DENSE || o.pre_b == P_DENSE || o.twoq == Q_DENSE || o.twoq == Q_DENSE_SW) out->needs_dense = true;
+      }
     }
+    if (par_cursor * 8 != (size_t)bytes) { out->status = BWQ_CIRC_BAD_OP; return; }  // accounting bug guard
+    sw.blk_q16 = (uint32_t)(blk_begin / 2);
+    sw.blk_len_q16 = (uint32_t)(bytes / 16);
     out->sweeps.push_back(sw);
   }
-  for (const MacroOp& o : out->ops)
-    if (o.pre_a == P_DENSE || o.pre_b == P_DENSE || o.twoq == Q_DENSE || o.twoq == Q_DENSE_SW) out->needs_dense = true;
 }
 
 // ----------------------------------------------------------------------------- SV lowering

@@ -34,21 +34,39 @@ enum TwoKind : uint8_t {
   Q_DENSE_SW = 8
 };
 
-struct MacroOp {    // 16 B
+// Host-side macro-op (lowering scratch): parameter offsets point into the noise table or, with
+// kLocalMat set, into the circuit's own matrix scratch.
+struct MacroOp {
   uint8_t pre_a, pre_b, twoq, pad;
-  uint32_t off_a, off_b, off_2;   // offsets (doubles) into the batch matrix buffer, whose head is
-                                  // a copy of the noise table
+  uint32_t off_a, off_b, off_2;
 };
-constexpr uint32_t kLocalMat = 0x80000000u;  // in CircuitProgram: offset is circuit-local
-struct PassDesc {   // 16 B
-  int32_t op_begin, op_end;
+constexpr uint32_t kLocalMat = 0x80000000u;
+
+// ---- device program: one contiguous, self-contained block per sweep -----------------------
+// A CTA copies its sweep's block into shared memory (cp.async) while the tile streams in, so
+// every descriptor and parameter the register passes need is one LDS away.
+//   block := BlockHdr | PassHdr[n_passes] | BlockOp[...] | parameters (16-byte aligned)
+struct BlockHdr {   // 16 B
+  int32_t n_passes;
+  int32_t pad[3];
+};
+struct PassHdr {    // 16 B
+  uint16_t ops_q16; // offset of the pass's first BlockOp, in 16-byte units from the block start
+  uint16_t n_ops;
   uint8_t sa, sb;   // tile slots of digits a and b
-  uint8_t pad[6];
+  uint8_t pad[10];
+};
+struct BlockOp {    // 16 B
+  uint8_t pre_a, pre_b, twoq, pad0;
+  uint16_t off_a, off_b, off_2;  // parameter offsets in 8-byte units from the block start
+  uint16_t pad1[3];
 };
 struct SweepDesc {  // 16 B
-  int32_t pass_begin, pass_end;
-  uint8_t pos[8];   // digit positions resident in the tile, ascending; first n_tile valid
+  uint32_t blk_q16;     // block offset in 16-byte units from the program buffer base
+  uint32_t blk_len_q16; // block length in 16-byte units
+  uint8_t pos[8];       // digit positions resident in the tile, ascending; first n_tile valid
 };
+constexpr int kBlockBytes = 8192;  // shared-memory program buffer per CTA
 
 constexpr int kMaxTileQubits = 7;
 constexpr int kMaxDmQubits = 16;   // 4^16 doubles = 34 GB
@@ -73,10 +91,10 @@ struct CircuitProgram {
   int32_t status = 0;
   int32_t n_digits = 0;                 // active qubits (>= 2, padded with idle digits)
   std::vector<int32_t> active;          // physical qubit of each digit (-1 = padding)
-  std::vector<SweepDesc> sweeps;
-  std::vector<PassDesc> passes;
-  std::vector<MacroOp> ops;
-  std::vector<double> mats;
+  std::vector<SweepDesc> sweeps;        // blk_q16 relative to this circuit's prog
+  std::vector<uint64_t> prog;           // sweep blocks, 8-byte words (16-byte aligned blocks)
+  int64_t n_passes = 0;
+  std::vector<double> mats;             // lowering scratch (not uploaded)
   std::vector<int64_t> term_index;      // per Pauli term: element index or -1
   std::vector<double> term_coeff;
   int64_t n_gates = 0;

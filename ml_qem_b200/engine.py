@@ -93,7 +93,7 @@ def load_library(path=None):
     lib.bwq_program_free.argtypes = [C.c_void_p]
     lib.bwq_program_free.restype = None
     lib.bwq_program_sizes.argtypes = [C.c_void_p, C.c_void_p]
-    lib.bwq_program_read.argtypes = [C.c_void_p] + [C.c_void_p] * 7
+    lib.bwq_program_read.argtypes = [C.c_void_p] + [C.c_void_p] * 5
     if path is None:
         _lib = lib
     return lib
@@ -330,16 +330,15 @@ def lower_dm(batch, circuit, noise_model=None, tile_qubits=0, low_qubits=0):
     try:
         sizes = np.zeros(8, dtype=np.int64)
         lib.bwq_program_sizes(prog, sizes.ctypes.data_as(C.c_void_p))
-        nd, nsw, nps, nops, nm, status, nt, ng = (int(x) for x in sizes)
+        nd, nsw, nps, nprog, dense, status, nt, ng = (int(x) for x in sizes)
         out = {
-            "n_digits": nd, "status": status, "n_gates": ng,
+            "n_digits": nd, "status": status, "n_gates": ng, "n_passes": nps, "needs_dense": bool(dense),
             "active": np.zeros(nd, dtype=np.int32), "sweeps": np.zeros((nsw, 10), dtype=np.int32),
-            "passes": np.zeros((nps, 3), dtype=np.int32), "ops": np.zeros((nops, 6), dtype=np.int64),
-            "mats": np.zeros(nm, dtype=np.float64), "term_index": np.zeros(nt, dtype=np.int64),
+            "prog": np.zeros(nprog, dtype=np.uint64), "term_index": np.zeros(nt, dtype=np.int64),
             "term_coeff": np.zeros(nt, dtype=np.float64),
         }
         lib.bwq_program_read(prog, *[out[k].ctypes.data_as(C.c_void_p) for k in
-                                     ("active", "sweeps", "passes", "ops", "mats", "term_index", "term_coeff")])
+                                     ("active", "sweeps", "prog", "term_index", "term_coeff")])
         return out
     finally:
         lib.bwq_program_free(prog)

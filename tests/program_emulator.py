@@ -78,6 +78,27 @@ def apply_two(v, kind, m):
     return _swap_view(out) if sw else out
 
 
+def decode_block(prog, sw):
+    """Decodes one sweep block (layout: ml_qem_b200/csrc/program.h) -> list of passes
+    [(sa, sb, [(pre_a, pre_b, twoq, off_a, off_b, off_2), ...])] and the block as doubles."""
+    words = prog["prog"]
+    blk = words[2 * int(sw[0]): 2 * (int(sw[0]) + int(sw[9]))]
+    b = blk.view(np.uint8)
+    n_passes = int(blk[:1].view(np.int32)[0])
+    passes = []
+    for p in range(n_passes):
+        h = b[16 * (1 + p): 16 * (2 + p)]
+        ops_q16, n_ops = int(h[:2].view(np.uint16)[0]), int(h[2:4].view(np.uint16)[0])
+        sa, sb = int(h[4]), int(h[5])
+        ops = []
+        for o in range(n_ops):
+            r = b[16 * (ops_q16 + o): 16 * (ops_q16 + o + 1)]
+            offs = r[4:10].view(np.uint16)
+            ops.append((int(r[0]), int(r[1]), int(r[2]), int(offs[0]), int(offs[1]), int(offs[2])))
+        passes.append((sa, sb, ops))
+    return passes, blk.view(np.float64)
+
+
 def run_program(prog):
     """Returns the final Pauli-basis state r (4^n doubles) of a lowered program (engine.lower_dm)."""
     nd = prog["n_digits"]
@@ -88,35 +109,25 @@ def run_program(prog):
         dig = (idx >> (2 * d)) & 3
         ok &= (dig == 0) | (dig == 3)
     state[ok] = 1.0
-    mats = prog["mats"]
-    op_begin = 0
-    pass_begin = 0
     t = state.reshape((4,) * nd)  # axis k <-> digit nd-1-k
     for sw in prog["sweeps"]:
-        assert sw[0] == pass_begin
         pos = list(sw[1:9])
-        pass_end = sw[9]
-        # number of tile slots = positions strictly ascending prefix
         kq = 1
         while kq < 8 and kq < nd and pos[kq] > pos[kq - 1]:
             kq += 1
         pos = pos[:kq]
-        for p in range(pass_begin, pass_end):
-            sa, sb, op_end = prog["passes"][p]
+        passes, mats = decode_block(prog, sw)
+        for sa, sb, ops in passes:
             da, db = pos[sa], pos[sb]
-            # gather: rows da + 4 db
             axes = [nd - 1 - db, nd - 1 - da]
             tt = np.moveaxis(t, axes, [0, 1])
             shp = tt.shape
-            v = tt.reshape(16, -1)  # index db*4 + da  == da + 4 db
-            for o in range(op_begin, op_end):
-                pre_a, pre_b, twoq, off_a, off_b, off_2 = (int(x) for x in prog["ops"][o])
+            v = tt.reshape(16, -1)  # index db*4 + da == da + 4 db
+            for pre_a, pre_b, twoq, off_a, off_b, off_2 in ops:
                 v = apply_pre(v, pre_a, mats[off_a:off_a + 16], False)
                 v = apply_pre(v, pre_b, mats[off_b:off_b + 16], True)
                 v = apply_two(v, twoq, mats[off_2:off_2 + 256])
             t = np.moveaxis(v.reshape(shp), [0, 1], axes)
-            op_begin = op_end
-        pass_begin = pass_end
     return np.ascontiguousarray(t).reshape(-1)
 
 

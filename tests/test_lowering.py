@@ -60,7 +60,7 @@ def test_coherent_cx_noise_uses_dense_op(lib):
     rng = np.random.default_rng(3)
     c = F.random_basis_circuit(5, 40, rng, lima.coupling_map)
     prog = _check(c, [[(l, 1.0)] for l in _labels(rng, 5, 5)], nm, on, tilings=((6, 2), (3, 1)))
-    assert any(int(op[2]) in (7, 8) for op in prog["ops"])  # Q_DENSE / Q_DENSE_SW
+    assert prog["needs_dense"]
 
 
 def test_non_basis_gates_and_reset(lib):
@@ -111,12 +111,15 @@ def test_sweep_packing_respects_tile_and_order(lib):
     for kq, low in ((6, 2), (6, 1), (7, 2), (4, 2)):
         prog = engine.lower_dm(fb, 0, nm, kq, low)
         assert prog["n_digits"] == 10
-        pb = 0
+        from program_emulator import decode_block
+        total = 0
         for sw in prog["sweeps"]:
             pos = list(sw[1:1 + kq])
             m = min(max(low, 1), kq - 2)
             assert pos == sorted(set(pos)) and pos[:m] == list(range(m))
-            for sa, sb, _ in prog["passes"][pb:sw[9]]:
-                assert sa < kq and sb < kq and sa != sb
-            pb = sw[9]
-        assert pb == len(prog["passes"])
+            assert sw[9] * 16 <= 8192
+            passes, _ = decode_block(prog, sw)
+            for sa, sb, ops in passes:
+                assert sa < kq and sb < kq and sa != sb and len(ops) > 0
+            total += len(passes)
+        assert total == prog["n_passes"]
