@@ -112,6 +112,8 @@ typedef struct {
   int64_t max_state_bytes;  /* device budget for resident states (default: 80% of free)        */
   int32_t chunk_circuits;   /* circuits simulated together (default: as many as fit)          */
   int32_t host_threads;     /* lowering threads (default: hardware concurrency)               */
+  int32_t sv_tile_bits;     /* amplitudes per statevector tile = 2^this, 2..12 (default 11)    */
+  int32_t reserved;
 } bwq_options;
 
 /* Counters of the last *_run call (for the roofline: bytes = sweeps x 16 B x 4^n). */
@@ -125,6 +127,8 @@ typedef struct {
   double lower_ms, h2d_ms, kernel_ms, d2h_ms; /* host wall / device-event times          */
   double sweep_kernel_ms;      /* CUDA-event time of the sweep launches only             */
   int64_t h2d_bytes, d2h_bytes;/* program upload / value download of the last run          */
+  int64_t sv_state_bytes_swept;/* statevector sweeps: sum of 2 * 16 B * 2^n (+ 16 B * 2^n per
+                                  expectation pass) of the last bwq_sv_* call                  */
 } bwq_stats;
 
 typedef struct bwq_ctx bwq_ctx;
@@ -174,6 +178,37 @@ int bwq_program_sizes(const bwq_program* p, int64_t sizes[8]);
  * term_index[n_terms] (element index, -1 = term vanishes); term_coeff. */
 int bwq_program_read(const bwq_program* p, int32_t* active_qubits, int32_t* sweeps, uint64_t* prog,
                      int64_t* term_index, double* term_coeff);
+
+/* ---- wide and amplitude-sharded statevector (ideal labels beyond 12 qubits) ----
+ * Replaces qiskit.primitives.Estimator / Statevector.evolve for wide registers
+ * (docs/tutorials/h13_ising_data_gen_tomo.ipynb:811 runs it at 16 qubits).  bwq_sv_run uses this
+ * path internally for circuits wider than 12 active qubits; the entry points below expose it for
+ * ONE circuit whose 2^n amplitudes are sharded over 2^n_global_bits GPUs (one process per GPU):
+ * the program is a list of segments -- local tile sweeps, EXCHANGE (the caller swaps the top
+ * n_global_bits local index bits with the rank bits: one all-to-all of 2^g contiguous blocks,
+ * NCCL over NVLink), and EXPVAL (signed |amplitude|^2 sums accumulated into n_observables
+ * partial values the caller all-reduces).  Device buffers are caller-owned. */
+typedef struct bwq_svx_program bwq_svx_program;
+/* Host-only planner.  tile_bits 0 = default (11). */
+int bwq_svx_lower(const bwq_batch* batch, int32_t circuit, int32_t tile_bits, int32_t n_global_bits,
+                  bwq_svx_program** out);
+void bwq_svx_free(bwq_svx_program* p);
+/* sizes: [0]=status [1]=n_bits [2]=n_local [3]=n_global [4]=tile_bits [5]=n_sweeps [6]=n_prog
+ * (8-byte words) [7]=n_segments [8]=n_zterms [9]=n_passes [10]=n_exchanges [11]=n_observables */
+int bwq_svx_sizes(const bwq_svx_program* p, int64_t sizes[12]);
+/* active[n_bits]; sweeps: 10 int32 each {block offset, pos[0..7], block length} (16-byte units);
+ * segs: 4 int32 each {kind (0 sweeps, 1 exchange, 2 expval), first, count, 0}. */
+int bwq_svx_read(const bwq_svx_program* p, int32_t* active, int32_t* sweeps, uint64_t* prog, int32_t* segs,
+                 uint32_t* zt_mask, double* zt_coeff, int32_t* zt_obs);
+/* Uploads the program to ctx's device (kept inside the handle). */
+int bwq_svx_upload(bwq_ctx* ctx, bwq_svx_program* p);
+/* Runs segment `segment` on this rank's shard d_state (2^n_local complex128, device memory).
+ * SWEEPS segments update the shard in place (the first sweep of the program initialises
+ * |0...0>); EXPVAL segments add this shard's contribution into d_obs[n_observables] (device);
+ * EXCHANGE segments are the caller's job and are rejected here.  Work is enqueued on `stream`
+ * (a cudaStream_t, 0 = the ctx's own stream) and not synchronised. */
+int bwq_svx_run_segment(bwq_ctx* ctx, const bwq_svx_program* p, int32_t segment, double* d_state,
+                        int32_t rank, double* d_obs, void* stream);
 
 #ifdef __cplusplus
 }

@@ -12,6 +12,7 @@
 #include <vector>
 
 #include "kernels.cuh"
+#include "sv_kernels.cuh"
 
 using namespace bwq;
 
@@ -95,12 +96,33 @@ struct SvGroup {
   size_t smem = 0;
   int64_t stride = 0;
 };
+// wide circuits (> kSvSmallBits active qubits): tile-sweep path, batched per chunk of equal width
+struct SvWideStage {
+  int max_sweeps = 0;       // sweep launches of this stage
+  size_t range_off = 0;     // int32 index of the chunk's {begin,end} array for this stage
+  int group_first = 0, n_groups = 0;  // index into the group_desc array
+  int cdesc_first = 0, n_cdesc = 0;   // circuits that evaluate terms in this stage
+};
+struct SvWideChunk {
+  int first = 0, count = 0, nb = 0, tile_bits = 0, low_bits = 0;
+  std::vector<SvWideStage> stages;
+  size_t init_off = 0;      // int32 index of the slots that need an explicit |0..0>
+  int n_init = 0;
+};
+struct SvWidePlan {
+  size_t o_range = 0, o_sweeps = 0, o_prog = 0, o_ztm = 0, o_ztc = 0, o_zto = 0, o_gdesc = 0, o_cdesc = 0, o_init = 0;
+  size_t blob_bytes = 0;
+  std::vector<SvWideChunk> chunks;
+  int64_t max_state_bytes = 0, n_passes = 0;
+  bool any = false;
+};
 struct SvPlan {
   bool valid = false;
   int64_t n_obs = 0, n_gates = 0;
   size_t o_cd = 0, o_ops = 0, o_mats = 0, o_obs = 0, o_tx = 0, o_tz = 0, o_tny = 0, o_tc = 0, blob_bytes = 0;
   std::vector<SvGroup> groups;
   std::vector<int64_t> nan_obs;
+  SvWidePlan wide;
   double lower_ms = 0, h2d_ms = 0;
 };
 
@@ -111,8 +133,8 @@ struct bwq_ctx {
   std::string error;
   bwq_options opt{};
   NoiseTable noise;
-  DevBuf d_noise, d_prog, d_sv_prog, d_states, d_out, d_scratch;
-  PinBuf h_prog, h_sv_prog, h_out;
+  DevBuf d_noise, d_prog, d_sv_prog, d_states, d_out, d_scratch, d_wide_prog, d_partial;
+  PinBuf h_prog, h_sv_prog, h_out, h_wide_prog;
   bwq_stats stats{};
   DmPlan plan;
   SvPlan sv_plan;
@@ -180,6 +202,8 @@ extern "C" int bwq_create(int device, bwq_ctx** out) {
     return bail(e, "cudaFuncSetAttribute(dm_sweep_kernel<7, full>)");
   if ((e = cudaFuncSetAttribute(sv_circuit_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 16 << 12)) != cudaSuccess)
     return bail(e, "cudaFuncSetAttribute(sv_circuit_kernel)");
+  if ((e = cudaFuncSetAttribute(sv_sweep_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (16 << kSvTileBitsMax) + kBlockBytes)) != cudaSuccess)
+    return bail(e, "cudaFuncSetAttribute(sv_sweep_kernel)");
   *out = ctx;
   return BWQ_OK;
 }
@@ -191,6 +215,7 @@ extern "C" int bwq_destroy(bwq_ctx* ctx) {
   ctx->d_noise.release(); ctx->d_prog.release(); ctx->d_states.release(); ctx->d_out.release();
   ctx->d_scratch.release(); ctx->h_prog.release(); ctx->h_out.release();
   ctx->d_sv_prog.release(); ctx->h_sv_prog.release();
+  ctx->d_wide_prog.release(); ctx->h_wide_prog.release(); ctx->d_partial.release();
   for (auto& ev : ctx->ev) if (ev) cudaEventDestroy(ev);
   for (auto& ev : ctx->chunk_ev) if (ev) cudaEventDestroy(ev);
   if (ctx->stream) cudaStreamDestroy(ctx->stream);
@@ -563,6 +588,217 @@ extern "C" int bwq_dm_run_device_out(bwq_ctx* ctx, const bwq_batch* b, double* d
 }
 
 // ------------------------------------------------------------------------------------------------
+// wide statevectors (13..31 active qubits on one GPU): tile sweeps, batched per chunk of equal width
+// ------------------------------------------------------------------------------------------------
+static cudaError_t launch_sv_sweep(const SvxLaunch& L, int sweep, int64_t n_cta, cudaStream_t s) {
+  const size_t smem = (sizeof(double2) << L.tile_bits) + kBlockBytes;
+  sv_sweep_kernel<<<(unsigned)n_cta, kSvxThreads, smem, s>>>(L, sweep);
+  return cudaGetLastError();
+}
+
+static int zexp_splits(const bwq_ctx* ctx, int n_groups, int n_local) {
+  const int64_t amps = int64_t(1) << n_local;
+  int64_t want = (4 * (int64_t)ctx->sm_count + n_groups - 1) / std::max(1, n_groups);
+  want = std::min<int64_t>(want, std::max<int64_t>(1, amps / 8192));
+  return (int)std::max<int64_t>(1, want);
+}
+
+static int sv_wide_prepare(bwq_ctx* ctx, const bwq_batch* b, const std::vector<int>& wide, int32_t* out_status) {
+  SvPlan& SP = ctx->sv_plan;
+  SvWidePlan& W = SP.wide;
+  const int NW = (int)wide.size();
+  std::vector<SvxProgram> progs(NW);
+  SvxOptions so;
+  so.tile_bits = ctx->opt.sv_tile_bits > 0 ? ctx->opt.sv_tile_bits : kSvTileBitsDefault;
+  parallel_for(NW, host_threads(ctx), [&](int i) { lower_svx_circuit(*b, wide[i], so, &progs[i]); });
+  size_t free_b = 0, total_b = 0;
+  CK(cudaMemGetInfo(&free_b, &total_b));
+  const int64_t budget = ctx->opt.max_state_bytes > 0 ? ctx->opt.max_state_bytes
+                                                       : (int64_t)((free_b + ctx->d_states.cap) * 0.8);
+  std::vector<int> order;
+  for (int i = 0; i < NW; ++i) {
+    const int c = wide[i];
+    if (progs[i].status == 0 && ((int64_t)sizeof(double2) << progs[i].n_bits) > budget) progs[i].status = BWQ_CIRC_TOO_WIDE;
+    out_status[c] = progs[i].status;
+    if (progs[i].status == 0) order.push_back(i);
+    else for (int64_t o = b->obs_offsets[c]; o < b->obs_offsets[c + 1]; ++o) SP.nan_obs.push_back(o);
+  }
+  std::sort(order.begin(), order.end(), [&](int a, int c) {
+    if (progs[a].n_bits != progs[c].n_bits) return progs[a].n_bits > progs[c].n_bits;
+    return a < c;
+  });
+  const int M = (int)order.size();
+  if (M == 0) return BWQ_OK;
+  // per circuit: stages = (optional sweep segment, expval segment)
+  struct Stage { int sw_first = 0, sw_count = 0, zt_first = 0, zt_count = 0; };
+  std::vector<std::vector<Stage>> stages(M);
+  std::vector<int64_t> sw_off(M + 1, 0), pg_off(M + 1, 0), zt_off(M + 1, 0);
+  for (int i = 0; i < M; ++i) {
+    const SvxProgram& p = progs[order[i]];
+    Stage cur;
+    for (const SvxSegment& sg : p.segs) {
+      if (sg.kind == SVSEG_SWEEPS) {  // consecutive sweep segments are contiguous
+        if (cur.sw_count == 0) cur.sw_first = sg.first;
+        cur.sw_count = sg.first + sg.count - cur.sw_first;
+      }
+      else if (sg.kind == SVSEG_EXPVAL) { cur.zt_first = sg.first; cur.zt_count = sg.count; stages[i].push_back(cur); cur = Stage(); }
+    }
+    sw_off[i + 1] = sw_off[i] + (int64_t)p.sweeps.size();
+    pg_off[i + 1] = pg_off[i] + (int64_t)p.prog.size();
+    zt_off[i + 1] = zt_off[i] + (int64_t)p.zt_mask.size();
+    SP.n_gates += p.n_gates;
+    W.n_passes += p.n_passes;
+  }
+  if (sw_off[M] > INT32_MAX || pg_off[M] / 2 >= (int64_t(1) << 32) || zt_off[M] > INT32_MAX)
+    return fail(ctx, BWQ_ERR_ARG, "statevector batch too large for 32-bit program indices; split the batch");
+  // chunks + per-stage tables
+  std::vector<int32_t> ranges, gdesc, cdesc, inits;
+  for (int i = 0; i < M;) {
+    const int nb = progs[order[i]].n_bits;
+    const int64_t sbytes = (int64_t)sizeof(double2) << nb;
+    int64_t fit = std::max<int64_t>(1, budget / sbytes);
+    if (ctx->opt.chunk_circuits > 0) fit = std::min<int64_t>(fit, ctx->opt.chunk_circuits);
+    const int tb = progs[order[i]].tile_bits;
+    fit = std::min<int64_t>(fit, (int64_t(1) << 30) >> (nb - tb));
+    int j = i;
+    while (j < M && progs[order[j]].n_bits == nb && j - i < fit) ++j;
+    SvWideChunk ch;
+    ch.first = i; ch.count = j - i; ch.nb = nb; ch.tile_bits = tb; ch.low_bits = std::max(0, tb - kSvFreeSlots);
+    size_t n_st = 0;
+    for (int k = i; k < j; ++k) n_st = std::max(n_st, stages[k].size());
+    ch.init_off = inits.size();
+    for (int k = i; k < j; ++k)
+      if (stages[k].empty() || stages[k][0].sw_count == 0) inits.push_back(k - i);
+    ch.n_init = (int)(inits.size() - ch.init_off);
+    for (size_t f = 0; f < n_st; ++f) {
+      SvWideStage st;
+      st.range_off = ranges.size();
+      st.group_first = (int)(gdesc.size() / 4);
+      st.cdesc_first = (int)(cdesc.size() / 4);
+      for (int k = i; k < j; ++k) {
+        Stage sg = f < stages[k].size() ? stages[k][f] : Stage();
+        ranges.push_back((int32_t)(sw_off[k] + sg.sw_first));
+        ranges.push_back((int32_t)(sw_off[k] + sg.sw_first + sg.sw_count));
+        st.max_sweeps = std::max(st.max_sweeps, sg.sw_count);
+        if (sg.zt_count > 0) {
+          const int g_first = (int)(gdesc.size() / 4) - st.group_first;
+          int ng = 0;
+          for (int t0 = 0; t0 < sg.zt_count; t0 += kZexpTerms, ++ng) {
+            gdesc.push_back(k - i);
+            gdesc.push_back((int32_t)(zt_off[k] + sg.zt_first + t0));
+            gdesc.push_back(std::min(kZexpTerms, sg.zt_count - t0));
+            gdesc.push_back(0);
+          }
+          cdesc.push_back(g_first); cdesc.push_back(ng);
+          cdesc.push_back((int32_t)b->obs_offsets[wide[order[k]]]); cdesc.push_back(0);
+        }
+      }
+      st.n_groups = (int)(gdesc.size() / 4) - st.group_first;
+      st.n_cdesc = (int)(cdesc.size() / 4) - st.cdesc_first;
+      ch.stages.push_back(st);
+    }
+    W.max_state_bytes = std::max(W.max_state_bytes, sbytes * ch.count);
+    W.chunks.push_back(std::move(ch));
+    i = j;
+  }
+  if (b->obs_offsets[b->n_circuits] > INT32_MAX) return fail(ctx, BWQ_ERR_ARG, "too many observables");
+  Blob blob;
+  W.o_range = blob.add(sizeof(int32_t) * ranges.size());
+  W.o_sweeps = blob.add(sizeof(SweepDesc) * (size_t)sw_off[M]);
+  W.o_prog = blob.add(sizeof(uint64_t) * (size_t)pg_off[M]);
+  W.o_ztm = blob.add(sizeof(uint32_t) * (size_t)zt_off[M]);
+  W.o_ztc = blob.add(sizeof(double) * (size_t)zt_off[M]);
+  W.o_zto = blob.add(sizeof(int32_t) * (size_t)zt_off[M]);
+  W.o_gdesc = blob.add(sizeof(int32_t) * gdesc.size());
+  W.o_cdesc = blob.add(sizeof(int32_t) * cdesc.size());
+  W.o_init = blob.add(sizeof(int32_t) * inits.size());
+  W.blob_bytes = blob.total;
+  CK(ctx->h_wide_prog.reserve(blob.total));
+  CK(ctx->d_wide_prog.reserve(blob.total));
+  char* hb = (char*)ctx->h_wide_prog.p;
+  if (!ranges.empty()) std::memcpy(hb + W.o_range, ranges.data(), sizeof(int32_t) * ranges.size());
+  if (!gdesc.empty()) std::memcpy(hb + W.o_gdesc, gdesc.data(), sizeof(int32_t) * gdesc.size());
+  if (!cdesc.empty()) std::memcpy(hb + W.o_cdesc, cdesc.data(), sizeof(int32_t) * cdesc.size());
+  if (!inits.empty()) std::memcpy(hb + W.o_init, inits.data(), sizeof(int32_t) * inits.size());
+  parallel_for(M, host_threads(ctx), [&](int i) {
+    const SvxProgram& p = progs[order[i]];
+    SweepDesc* sw = (SweepDesc*)(hb + W.o_sweeps) + sw_off[i];
+    for (size_t k = 0; k < p.sweeps.size(); ++k) { sw[k] = p.sweeps[k]; sw[k].blk_q16 += (uint32_t)(pg_off[i] / 2); }
+    if (!p.prog.empty()) std::memcpy((uint64_t*)(hb + W.o_prog) + pg_off[i], p.prog.data(), p.prog.size() * sizeof(uint64_t));
+    const size_t nt = p.zt_mask.size();
+    if (nt) {
+      std::memcpy((uint32_t*)(hb + W.o_ztm) + zt_off[i], p.zt_mask.data(), nt * sizeof(uint32_t));
+      std::memcpy((double*)(hb + W.o_ztc) + zt_off[i], p.zt_coeff.data(), nt * sizeof(double));
+      std::memcpy((int32_t*)(hb + W.o_zto) + zt_off[i], p.zt_obs.data(), nt * sizeof(int32_t));
+    }
+  });
+  CK(ctx->d_states.reserve((size_t)W.max_state_bytes));
+  // per-CTA partials of the largest expectation launch
+  int64_t max_partial = 0;
+  for (const SvWideChunk& ch : W.chunks)
+    for (const SvWideStage& st : ch.stages)
+      max_partial = std::max<int64_t>(max_partial, (int64_t)st.n_groups * zexp_splits(ctx, st.n_groups, ch.nb) * kZexpTerms);
+  if (max_partial > 0) CK(ctx->d_partial.reserve(sizeof(double) * (size_t)max_partial));
+  W.any = true;
+  return BWQ_OK;
+}
+
+static int sv_wide_execute(bwq_ctx* ctx, double* d_out) {
+  SvWidePlan& W = ctx->sv_plan.wide;
+  bwq_stats& S = ctx->stats;
+  cudaStream_t st = ctx->stream;
+  const char* db = (const char*)ctx->d_wide_prog.p;
+  for (const SvWideChunk& ch : W.chunks) {
+    SvxLaunch L;
+    L.states = (double2*)ctx->d_states.p;
+    L.stride = int64_t(1) << ch.nb;
+    L.n_local = ch.nb; L.tile_bits = ch.tile_bits; L.low_bits = ch.low_bits;
+    L.first_circuit = 0;
+    L.sweeps = (const SweepDesc*)(db + W.o_sweeps);
+    L.prog = (const uint4*)(db + W.o_prog);
+    L.hi_bits = 0;
+    if (ch.n_init > 0) {
+      dim3 grid((unsigned)((L.stride + 255) / 256), (unsigned)ch.n_init);
+      sv_init_kernel<<<grid, 256, 0, st>>>(L.states, L.stride, (const int32_t*)(db + W.o_init) + ch.init_off, ch.n_init, 0u);
+      CK(cudaGetLastError());
+      S.n_other_launches++;
+    }
+    const int64_t tiles = int64_t(1) << (ch.nb - ch.tile_bits);
+    for (size_t f = 0; f < ch.stages.size(); ++f) {
+      const SvWideStage& sg = ch.stages[f];
+      L.sweep_range = (const int32_t*)(db + W.o_range) + sg.range_off;
+      L.init = f == 0 ? 1 : 0;
+      for (int sidx = 0; sidx < sg.max_sweeps; ++sidx) {
+        CK(launch_sv_sweep(L, sidx, tiles * ch.count, st));
+        S.n_other_launches++;
+        S.sv_state_bytes_swept += 2 * (int64_t)sizeof(double2) * L.stride * ch.count;
+      }
+      if (sg.n_groups > 0) {
+        ZexpLaunch Z;
+        Z.states = L.states; Z.stride = L.stride; Z.hi_bits = 0;
+        Z.splits = zexp_splits(ctx, sg.n_groups, ch.nb);
+        Z.group_desc = (const int32_t*)(db + W.o_gdesc) + 4 * (size_t)sg.group_first;
+        Z.zt_mask = (const uint32_t*)(db + W.o_ztm);
+        Z.partial = (double*)ctx->d_partial.p;
+        sv_zexp_kernel<<<(unsigned)(sg.n_groups * Z.splits), kZexpThreads, 0, st>>>(Z);
+        CK(cudaGetLastError());
+        ZexpFinalize F;
+        F.circ_desc = (const int32_t*)(db + W.o_cdesc) + 4 * (size_t)sg.cdesc_first;
+        F.group_desc = Z.group_desc;
+        F.zt_coeff = (const double*)(db + W.o_ztc);
+        F.zt_obs = (const int32_t*)(db + W.o_zto);
+        F.partial = Z.partial; F.splits = Z.splits; F.out = d_out;
+        sv_zexp_finalize<<<(unsigned)sg.n_cdesc, 128, 0, st>>>(F);
+        CK(cudaGetLastError());
+        S.n_other_launches += 2;
+        S.sv_state_bytes_swept += (int64_t)sizeof(double2) * L.stride * sg.n_groups;
+      }
+    }
+  }
+  return BWQ_OK;
+}
+
+// ------------------------------------------------------------------------------------------------
 // statevector run (ideal labels)
 // ------------------------------------------------------------------------------------------------
 static int sv_prepare_impl(bwq_ctx* ctx, const bwq_batch* b, int32_t* out_status) {
@@ -580,13 +816,17 @@ static int sv_prepare_impl(bwq_ctx* ctx, const bwq_batch* b, int32_t* out_status
   double t0 = now_ms();
   std::vector<SvProgram> progs(N);
   parallel_for(N, host_threads(ctx), [&](int c) { lower_sv_circuit(*b, c, &progs[c]); });
-  constexpr int kSimpleMaxBits = 24;  // one-CTA-per-circuit kernel; wider needs the sharded path
-  std::vector<int> order;
+  // <= kSvSmallBits active qubits: one CTA per circuit, state in shared memory; wider: tile sweeps
+  std::vector<int> order, wide;
   for (int c = 0; c < N; ++c) {
-    if (progs[c].status == 0 && progs[c].n_bits > kSimpleMaxBits) progs[c].status = BWQ_CIRC_TOO_WIDE;
+    if (progs[c].status == 0 && progs[c].n_bits > kSvSmallBits) { wide.push_back(c); continue; }
     out_status[c] = progs[c].status;
     if (progs[c].status == 0) order.push_back(c);
     else for (int64_t o = b->obs_offsets[c]; o < b->obs_offsets[c + 1]; ++o) P.nan_obs.push_back(o);
+  }
+  if (!wide.empty()) {
+    int rc2 = sv_wide_prepare(ctx, b, wide, out_status);
+    if (rc2) return rc2;
   }
   std::sort(order.begin(), order.end(), [&](int a, int c) {
     if (progs[a].n_bits != progs[c].n_bits) return progs[a].n_bits > progs[c].n_bits;
@@ -646,7 +886,7 @@ static int sv_prepare_impl(bwq_ctx* ctx, const bwq_batch* b, int32_t* out_status
     }
   });
   // launch groups: circuits of equal width
-  constexpr int kSmemBits = 12;
+  constexpr int kSmemBits = kSvSmallBits;
   int64_t scratch = 0;
   for (int i = 0; i < M;) {
     const int nb = progs[order[i]].n_bits;
@@ -672,11 +912,13 @@ static int sv_prepare_impl(bwq_ctx* ctx, const bwq_batch* b, int32_t* out_status
   cudaStream_t st = ctx->stream;
   CK(cudaEventRecord(ctx->ev[0], st));
   if (M > 0) CK(cudaMemcpyAsync(ctx->d_sv_prog.p, hb, blob.total, cudaMemcpyHostToDevice, st));
+  if (P.wide.any) CK(cudaMemcpyAsync(ctx->d_wide_prog.p, ctx->h_wide_prog.p, P.wide.blob_bytes, cudaMemcpyHostToDevice, st));
   CK(cudaEventRecord(ctx->ev[1], st));
   CK(cudaStreamSynchronize(st));
   float ms = 0.f;
   CK(cudaEventElapsedTime(&ms, ctx->ev[0], ctx->ev[1]));
   P.h2d_ms = ms;
+  P.blob_bytes += P.wide.blob_bytes;
   ctx->stats.lower_ms = P.lower_ms; ctx->stats.h2d_ms = ms; ctx->stats.h2d_bytes = (int64_t)P.blob_bytes;
   ctx->stats.n_gates = P.n_gates;
   return BWQ_OK;
@@ -716,6 +958,10 @@ static int sv_execute_impl(bwq_ctx* ctx, double* out_vals) {
       CK(cudaGetLastError());
       S.n_other_launches++;
     }
+  }
+  if (P.wide.any) {
+    int rc2 = sv_wide_execute(ctx, d_out);
+    if (rc2) return rc2;
   }
   CK(cudaEventRecord(ctx->ev[2], st));
   if (P.n_obs > 0) {
@@ -787,5 +1033,173 @@ extern "C" int bwq_program_read(const bwq_program* p, int32_t* active, int32_t* 
   if (prog && !q.prog.empty()) std::memcpy(prog, q.prog.data(), q.prog.size() * sizeof(uint64_t));
   if (term_index && !q.term_index.empty()) std::memcpy(term_index, q.term_index.data(), q.term_index.size() * sizeof(int64_t));
   if (term_coeff && !q.term_coeff.empty()) std::memcpy(term_coeff, q.term_coeff.data(), q.term_coeff.size() * sizeof(double));
+  return BWQ_OK;
+}
+
+// ------------------------------------------------------------------------------------------------
+// wide / amplitude-sharded statevector of ONE circuit on caller-owned device memory
+// ------------------------------------------------------------------------------------------------
+struct bwq_svx_program {
+  SvxProgram p;
+  int64_t n_obs = 0;
+  int device = -1;
+  DevBuf d_blob, d_partial;
+  size_t o_sweeps = 0, o_prog = 0, o_ztm = 0, o_ztc = 0, o_zto = 0, o_gdesc = 0, o_cdesc = 0;
+  std::vector<int> seg_group_first, seg_n_groups;  // per segment (EXPVAL only)
+  bool uploaded = false;
+};
+
+extern "C" int bwq_svx_lower(const bwq_batch* batch, int32_t circuit, int32_t tile_bits, int32_t n_global_bits,
+                             bwq_svx_program** out) {
+  if (!batch || !out || circuit < 0 || circuit >= batch->n_circuits || n_global_bits < 0 || n_global_bits > 8)
+    return fail(nullptr, BWQ_ERR_ARG, "bwq_svx_lower: bad arguments");
+  bwq_svx_program* h = new bwq_svx_program();
+  SvxOptions so;
+  so.tile_bits = tile_bits > 0 ? tile_bits : kSvTileBitsDefault;
+  so.n_global = n_global_bits;
+  lower_svx_circuit(*batch, circuit, so, &h->p);
+  h->n_obs = batch->obs_offsets[circuit + 1] - batch->obs_offsets[circuit];
+  *out = h;
+  return BWQ_OK;
+}
+
+extern "C" void bwq_svx_free(bwq_svx_program* h) {
+  if (!h) return;
+  if (h->uploaded) { cudaSetDevice(h->device); h->d_blob.release(); h->d_partial.release(); }
+  delete h;
+}
+
+extern "C" int bwq_svx_sizes(const bwq_svx_program* h, int64_t s[12]) {
+  if (!h || !s) return BWQ_ERR_ARG;
+  const SvxProgram& p = h->p;
+  s[0] = p.status; s[1] = p.n_bits; s[2] = p.n_local; s[3] = p.n_global; s[4] = p.tile_bits;
+  s[5] = (int64_t)p.sweeps.size(); s[6] = (int64_t)p.prog.size(); s[7] = (int64_t)p.segs.size();
+  s[8] = (int64_t)p.zt_mask.size(); s[9] = p.n_passes; s[10] = p.n_exchanges; s[11] = h->n_obs;
+  return BWQ_OK;
+}
+
+extern "C" int bwq_svx_read(const bwq_svx_program* h, int32_t* active, int32_t* sweeps, uint64_t* prog, int32_t* segs,
+                            uint32_t* zt_mask, double* zt_coeff, int32_t* zt_obs) {
+  if (!h) return BWQ_ERR_ARG;
+  const SvxProgram& q = h->p;
+  if (active) for (size_t i = 0; i < q.active.size(); ++i) active[i] = q.active[i];
+  if (sweeps)
+    for (size_t i = 0; i < q.sweeps.size(); ++i) {
+      int32_t* s = sweeps + 10 * i;
+      s[0] = (int32_t)q.sweeps[i].blk_q16;
+      for (int k = 0; k < 8; ++k) s[1 + k] = q.sweeps[i].pos[k];
+      s[9] = (int32_t)q.sweeps[i].blk_len_q16;
+    }
+  if (prog && !q.prog.empty()) std::memcpy(prog, q.prog.data(), q.prog.size() * sizeof(uint64_t));
+  if (segs)
+    for (size_t i = 0; i < q.segs.size(); ++i) {
+      segs[4 * i] = q.segs[i].kind; segs[4 * i + 1] = q.segs[i].first; segs[4 * i + 2] = q.segs[i].count; segs[4 * i + 3] = 0;
+    }
+  if (zt_mask && !q.zt_mask.empty()) std::memcpy(zt_mask, q.zt_mask.data(), q.zt_mask.size() * sizeof(uint32_t));
+  if (zt_coeff && !q.zt_coeff.empty()) std::memcpy(zt_coeff, q.zt_coeff.data(), q.zt_coeff.size() * sizeof(double));
+  if (zt_obs && !q.zt_obs.empty()) std::memcpy(zt_obs, q.zt_obs.data(), q.zt_obs.size() * sizeof(int32_t));
+  return BWQ_OK;
+}
+
+extern "C" int bwq_svx_upload(bwq_ctx* ctx, bwq_svx_program* h) {
+  if (!ctx || !h) return BWQ_ERR_ARG;
+  const SvxProgram& p = h->p;
+  if (p.status != 0) return fail(ctx, BWQ_ERR_ARG, "bwq_svx_upload: program status %d", p.status);
+  CK(cudaSetDevice(ctx->device));
+  std::vector<int32_t> gdesc, cdesc;
+  h->seg_group_first.assign(p.segs.size(), 0);
+  h->seg_n_groups.assign(p.segs.size(), 0);
+  int max_groups = 0;
+  for (size_t i = 0; i < p.segs.size(); ++i) {
+    if (p.segs[i].kind != SVSEG_EXPVAL) continue;
+    h->seg_group_first[i] = (int)(gdesc.size() / 4);
+    int ng = 0;
+    for (int t0 = 0; t0 < p.segs[i].count; t0 += kZexpTerms, ++ng) {
+      gdesc.push_back(0); gdesc.push_back(p.segs[i].first + t0);
+      gdesc.push_back(std::min(kZexpTerms, p.segs[i].count - t0)); gdesc.push_back(0);
+    }
+    h->seg_n_groups[i] = ng;
+    max_groups = std::max(max_groups, ng);
+    cdesc.push_back(0); cdesc.push_back(ng); cdesc.push_back(0); cdesc.push_back(0);  // one per EXPVAL segment
+  }
+  Blob blob;
+  h->o_sweeps = blob.add(sizeof(SweepDesc) * p.sweeps.size());
+  h->o_prog = blob.add(sizeof(uint64_t) * p.prog.size());
+  h->o_ztm = blob.add(sizeof(uint32_t) * p.zt_mask.size());
+  h->o_ztc = blob.add(sizeof(double) * p.zt_coeff.size());
+  h->o_zto = blob.add(sizeof(int32_t) * p.zt_obs.size());
+  h->o_gdesc = blob.add(sizeof(int32_t) * gdesc.size());
+  h->o_cdesc = blob.add(sizeof(int32_t) * 4);
+  std::vector<char> hb(blob.total + 256, 0);
+  auto put = [&](size_t off, const void* src, size_t n) { if (n) std::memcpy(hb.data() + off, src, n); };
+  put(h->o_sweeps, p.sweeps.data(), sizeof(SweepDesc) * p.sweeps.size());
+  put(h->o_prog, p.prog.data(), sizeof(uint64_t) * p.prog.size());
+  put(h->o_ztm, p.zt_mask.data(), sizeof(uint32_t) * p.zt_mask.size());
+  put(h->o_ztc, p.zt_coeff.data(), sizeof(double) * p.zt_coeff.size());
+  put(h->o_zto, p.zt_obs.data(), sizeof(int32_t) * p.zt_obs.size());
+  put(h->o_gdesc, gdesc.data(), sizeof(int32_t) * gdesc.size());
+  h->device = ctx->device;
+  CK(h->d_blob.reserve(hb.size()));
+  CK(cudaMemcpy(h->d_blob.p, hb.data(), hb.size(), cudaMemcpyHostToDevice));
+  if (max_groups > 0)
+    CK(h->d_partial.reserve(sizeof(double) * (size_t)max_groups * zexp_splits(ctx, 1, p.n_local) * kZexpTerms));
+  h->uploaded = true;
+  return BWQ_OK;
+}
+
+extern "C" int bwq_svx_run_segment(bwq_ctx* ctx, const bwq_svx_program* h, int32_t segment, double* d_state,
+                                   int32_t rank, double* d_obs, void* stream) {
+  if (!ctx || !h || !d_state) return BWQ_ERR_ARG;
+  if (!h->uploaded) return fail(ctx, BWQ_ERR_ARG, "bwq_svx_run_segment: call bwq_svx_upload first");
+  const SvxProgram& p = h->p;
+  if (segment < 0 || segment >= (int)p.segs.size()) return fail(ctx, BWQ_ERR_ARG, "segment out of range");
+  if (rank < 0 || rank >= (1 << p.n_global)) return fail(ctx, BWQ_ERR_ARG, "rank out of range");
+  CK(cudaSetDevice(ctx->device));
+  cudaStream_t st = stream ? (cudaStream_t)stream : ctx->stream;
+  const SvxSegment& sg = p.segs[segment];
+  const char* db = (const char*)h->d_blob.p;
+  const uint32_t hi = uint32_t(rank) << p.n_local;
+  const int64_t stride = int64_t(1) << p.n_local;
+  // a program that starts with an expectation value (no gates) still needs |0...0>
+  if (segment == 0 && sg.kind != SVSEG_SWEEPS) {
+    sv_init_kernel<<<dim3((unsigned)((stride + 255) / 256), 1), 256, 0, st>>>((double2*)d_state, stride, nullptr, 1, hi);
+    CK(cudaGetLastError());
+  }
+  if (sg.kind == SVSEG_EXCHANGE)
+    return fail(ctx, BWQ_ERR_UNSUPPORTED, "EXCHANGE segments are executed by the caller (all-to-all of the top local bits)");
+  if (sg.kind == SVSEG_SWEEPS) {
+    SvxLaunch L;
+    L.states = (double2*)d_state; L.stride = stride;
+    L.n_local = p.n_local; L.tile_bits = p.tile_bits; L.low_bits = std::max(0, p.tile_bits - kSvFreeSlots);
+    L.first_circuit = 0; L.sweep_range = nullptr;
+    L.sweeps = (const SweepDesc*)(db + h->o_sweeps);
+    L.prog = (const uint4*)(db + h->o_prog);
+    L.hi_bits = hi; L.init = 1;
+    const int64_t tiles = int64_t(1) << (p.n_local - p.tile_bits);
+    for (int s = sg.first; s < sg.first + sg.count; ++s) CK(launch_sv_sweep(L, s, tiles, st));
+    return BWQ_OK;
+  }
+  if (!d_obs) return fail(ctx, BWQ_ERR_ARG, "EXPVAL segment needs d_obs");
+  const int ng = h->seg_n_groups[segment];
+  if (ng == 0) return BWQ_OK;
+  ZexpLaunch Z;
+  Z.states = (const double2*)d_state; Z.stride = stride; Z.hi_bits = hi;
+  Z.splits = zexp_splits(ctx, ng, p.n_local);
+  Z.group_desc = (const int32_t*)(db + h->o_gdesc) + 4 * (size_t)h->seg_group_first[segment];
+  Z.zt_mask = (const uint32_t*)(db + h->o_ztm);
+  Z.partial = (double*)h->d_partial.p;
+  sv_zexp_kernel<<<(unsigned)(ng * Z.splits), kZexpThreads, 0, st>>>(Z);
+  CK(cudaGetLastError());
+  // circ_desc {0, ng, 0, 0}: passed through a small device constant written at upload time
+  int32_t cd[4] = {0, ng, 0, 0};
+  CK(cudaMemcpyAsync((void*)(db + h->o_cdesc), cd, sizeof cd, cudaMemcpyHostToDevice, st));
+  ZexpFinalize F;
+  F.circ_desc = (const int32_t*)(db + h->o_cdesc);
+  F.group_desc = Z.group_desc;
+  F.zt_coeff = (const double*)(db + h->o_ztc);
+  F.zt_obs = (const int32_t*)(db + h->o_zto);
+  F.partial = Z.partial; F.splits = Z.splits; F.out = d_obs;
+  sv_zexp_finalize<<<1, 128, 0, st>>>(F);
+  CK(cudaGetLastError());
   return BWQ_OK;
 }

@@ -140,4 +140,71 @@ bool gate_unitary(uint16_t opcode, const double* params, double* u);
 void ptm_from_unitary1(const double* u, double* r /*16*/);
 void ptm_from_unitary2(const double* u, double* r /*256*/);
 
+// ============================================================================================
+// Statevector SWEEP program (wide circuits, batched or amplitude-sharded across GPUs).
+//
+// State: 2^n_local complex128 per GPU; with n_global > 0 the rank supplies the top index bits
+// (physical bit n_local + i = bit i of the rank).  A sweep stages a tile of 2^K amplitudes in
+// shared memory (the lowest L = max(0, K-8) physical bits always resident, plus up to 8 others)
+// and runs register passes on slot pairs, like the density-matrix path.  Diagonal operations
+// read the bits of the full physical index and therefore never need their qubits resident (or
+// even local); controlled operations only need their TARGET resident (the control is a bit
+// test).  Non-diagonal work on a global qubit is preceded by an EXCHANGE segment: physical bits
+// [n_local-g, n_local) <-> [n_local, n_local+g), i.e. one all-to-all of 2^g contiguous blocks.
+// Expectation values are always evaluated on Z-type strings: X/Y terms are grouped into
+// qubit-wise commuting families and the planner appends the basis rotation as ordinary gates.
+// ============================================================================================
+enum SvOpKind : uint8_t {
+  SVO_U1 = 1,    // 2x2 on the target slot                      8 doubles
+  SVO_X = 2,     // Pauli X on the target slot (cx = conditional X)
+  SVO_U2 = 3,    // 4x4 on (a,b), local index i_a + 2 i_b       32 doubles
+  SVO_SWAP = 4,  // exchange slots a and b
+  SVO_D1 = 5,    // phases by physical bit qa                    4 doubles (p0, p1)
+  SVO_D2 = 6     // phases by physical bits (qa,qb), b_qa+2b_qb  8 doubles
+};
+enum : uint8_t { SVF_ON_B = 1, SVF_COND = 2, SVF_COND_VAL = 4 };
+struct SvBlockOp {   // 8 B
+  uint8_t kind, flags;
+  uint8_t qa, qb;    // D1/D2: physical bit positions
+  uint16_t off;      // parameter offset, 8-byte units from the block start
+  uint8_t cond_bit;  // SVF_COND: physical bit tested against SVF_COND_VAL
+  uint8_t pad;
+};
+struct SvPassHdr {   // 8 B
+  uint16_t ops_q8;   // first SvBlockOp, 8-byte units from the block start
+  uint16_t n_ops;
+  uint8_t sa, sb;    // tile slots
+  uint8_t needs_index;  // some op reads the physical index (diagonal / conditional)
+  uint8_t pad;
+};
+constexpr int kSvTileBitsDefault = 11;
+constexpr int kSvTileBitsMax = 12;
+constexpr int kSvFreeSlots = 8;       // SweepDesc::pos holds the positions of slots L..K-1
+constexpr int kSvSmallBits = 12;      // <= this: one CTA per circuit, state in shared memory
+
+enum : int32_t { SVSEG_SWEEPS = 0, SVSEG_EXCHANGE = 1, SVSEG_EXPVAL = 2 };
+struct SvxSegment {
+  int32_t kind;
+  int32_t first, count;  // SWEEPS: sweep range; EXPVAL: z-term range
+  int32_t pad;
+};
+struct SvxProgram {
+  int32_t status = 0;
+  int32_t n_bits = 0;      // active qubits (padded so that n_local >= 2 + n_global)
+  int32_t n_local = 0, n_global = 0, tile_bits = 0;
+  std::vector<int32_t> active;     // physical (register) qubit of each logical bit, -1 = padding
+  std::vector<SweepDesc> sweeps;
+  std::vector<uint64_t> prog;
+  std::vector<SvxSegment> segs;
+  std::vector<uint32_t> zt_mask;   // Z-type terms, physical masks under the mapping at that point
+  std::vector<double> zt_coeff;    // coefficient (0 = vanishing term)
+  std::vector<int32_t> zt_obs;     // observable index within the circuit
+  int64_t n_gates = 0, n_passes = 0, n_exchanges = 0;
+};
+struct SvxOptions {
+  int tile_bits = kSvTileBitsDefault;
+  int n_global = 0;
+};
+void lower_svx_circuit(const bwq_batch& b, int c, const SvxOptions& o, SvxProgram* out);
+
 }  // namespace bwq

@@ -45,20 +45,23 @@ class _NoiseTable(C.Structure):
 
 class _Options(C.Structure):
     _fields_ = [("tile_qubits", C.c_int32), ("low_qubits", C.c_int32), ("max_state_bytes", C.c_int64),
-                ("chunk_circuits", C.c_int32), ("host_threads", C.c_int32)]
+                ("chunk_circuits", C.c_int32), ("host_threads", C.c_int32), ("sv_tile_bits", C.c_int32),
+                ("reserved", C.c_int32)]
 
 
 class _Stats(C.Structure):
     _fields_ = [("n_sweep_launches", C.c_int64), ("n_state_sweeps", C.c_int64), ("n_passes", C.c_int64),
                 ("n_gates", C.c_int64), ("state_bytes_swept", C.c_int64), ("n_other_launches", C.c_int64),
                 ("lower_ms", C.c_double), ("h2d_ms", C.c_double), ("kernel_ms", C.c_double), ("d2h_ms", C.c_double),
-                ("sweep_kernel_ms", C.c_double), ("h2d_bytes", C.c_int64), ("d2h_bytes", C.c_int64)]
+                ("sweep_kernel_ms", C.c_double), ("h2d_bytes", C.c_int64), ("d2h_bytes", C.c_int64),
+                ("sv_state_bytes_swept", C.c_int64)]
 
 
 EXPORTS = [
     "bwq_version", "bwq_create", "bwq_destroy", "bwq_last_error", "bwq_set_options", "bwq_set_noise_table",
     "bwq_dm_run", "bwq_sv_run", "bwq_dm_run_device_out", "bwq_dm_prepare", "bwq_dm_execute", "bwq_dm_execute_device_out", "bwq_sv_prepare", "bwq_sv_execute", "bwq_get_stats", "bwq_sync", "bwq_lower_dm",
     "bwq_program_free", "bwq_program_sizes", "bwq_program_read",
+    "bwq_svx_lower", "bwq_svx_free", "bwq_svx_sizes", "bwq_svx_read", "bwq_svx_upload", "bwq_svx_run_segment",
 ]
 
 
@@ -94,6 +97,13 @@ def load_library(path=None):
     lib.bwq_program_free.restype = None
     lib.bwq_program_sizes.argtypes = [C.c_void_p, C.c_void_p]
     lib.bwq_program_read.argtypes = [C.c_void_p] + [C.c_void_p] * 5
+    lib.bwq_svx_lower.argtypes = [C.POINTER(_Batch), C.c_int32, C.c_int32, C.c_int32, C.POINTER(C.c_void_p)]
+    lib.bwq_svx_free.argtypes = [C.c_void_p]
+    lib.bwq_svx_free.restype = None
+    lib.bwq_svx_sizes.argtypes = [C.c_void_p, C.c_void_p]
+    lib.bwq_svx_read.argtypes = [C.c_void_p] + [C.c_void_p] * 7
+    lib.bwq_svx_upload.argtypes = [C.c_void_p, C.c_void_p]
+    lib.bwq_svx_run_segment.argtypes = [C.c_void_p, C.c_void_p, C.c_int32, C.c_void_p, C.c_int32, C.c_void_p, C.c_void_p]
     if path is None:
         _lib = lib
     return lib
@@ -238,8 +248,9 @@ class Engine:
         if rc != 0:
             raise EngineError(f"{what} failed ({rc}): {self._lib.bwq_last_error(self._ctx).decode()}")
 
-    def set_options(self, tile_qubits=0, low_qubits=0, max_state_bytes=0, chunk_circuits=0, host_threads=0):
-        o = _Options(tile_qubits, low_qubits, max_state_bytes, chunk_circuits, host_threads)
+    def set_options(self, tile_qubits=0, low_qubits=0, max_state_bytes=0, chunk_circuits=0, host_threads=0,
+                    sv_tile_bits=0):
+        o = _Options(tile_qubits, low_qubits, max_state_bytes, chunk_circuits, host_threads, sv_tile_bits, 0)
         self._check(self._lib.bwq_set_options(self._ctx, C.byref(o)), "bwq_set_options")
 
     def set_noise(self, model):
@@ -342,3 +353,52 @@ def lower_dm(batch, circuit, noise_model=None, tile_qubits=0, low_qubits=0):
         return out
     finally:
         lib.bwq_program_free(prog)
+
+
+SEG_SWEEPS, SEG_EXCHANGE, SEG_EXPVAL = 0, 1, 2
+
+
+class SvxProgram:
+    """Handle of a lowered wide/sharded statevector program (bwq_svx_program).  ``info`` holds the
+    host-side view (no GPU needed): segments, sweeps, program words, Z-type terms."""
+
+    def __init__(self, batch, circuit=0, tile_bits=0, n_global_bits=0):
+        self._lib = load_library()
+        self._h = C.c_void_p()
+        bs = batch.c_struct()
+        rc = self._lib.bwq_svx_lower(C.byref(bs), circuit, tile_bits, n_global_bits, C.byref(self._h))
+        if rc != 0:
+            raise EngineError(f"bwq_svx_lower failed ({rc}): {self._lib.bwq_last_error(None).decode()}")
+        sizes = np.zeros(12, dtype=np.int64)
+        self._lib.bwq_svx_sizes(self._h, sizes.ctypes.data_as(C.c_void_p))
+        (status, n_bits, n_local, n_global, tile, nsw, nprog, nseg, nzt, npass, nex, nobs) = (int(x) for x in sizes)
+        self.info = {
+            "status": status, "n_bits": n_bits, "n_local": n_local, "n_global": n_global, "tile_bits": tile,
+            "n_passes": npass, "n_exchanges": nex, "n_observables": nobs,
+            "active": np.zeros(n_bits, dtype=np.int32), "sweeps": np.zeros((nsw, 10), dtype=np.int32),
+            "prog": np.zeros(nprog, dtype=np.uint64), "segs": np.zeros((nseg, 4), dtype=np.int32),
+            "zt_mask": np.zeros(nzt, dtype=np.uint32), "zt_coeff": np.zeros(nzt, dtype=np.float64),
+            "zt_obs": np.zeros(nzt, dtype=np.int32),
+        }
+        self._lib.bwq_svx_read(self._h, *[self.info[k].ctypes.data_as(C.c_void_p) for k in
+                                          ("active", "sweeps", "prog", "segs", "zt_mask", "zt_coeff", "zt_obs")])
+
+    def close(self):
+        if getattr(self, "_h", None):
+            self._lib.bwq_svx_free(self._h)
+            self._h = None
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+    def upload(self, engine):
+        engine._check(self._lib.bwq_svx_upload(engine._ctx, self._h), "bwq_svx_upload")
+
+    def run_segment(self, engine, segment, state_ptr, rank=0, obs_ptr=0, stream=0):
+        engine._check(self._lib.bwq_svx_run_segment(engine._ctx, self._h, int(segment), C.c_void_p(int(state_ptr)),
+                                                    int(rank), C.c_void_p(int(obs_ptr)) if obs_ptr else None,
+                                                    C.c_void_p(int(stream)) if stream else None),
+                      "bwq_svx_run_segment")

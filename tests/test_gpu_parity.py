@@ -111,3 +111,112 @@ def test_dm_equals_sv_without_noise(engine_gpu):
     v_dm, _ = engine_gpu.run_dm(b)
     v_sv, _ = engine_gpu.run_sv(b)
     assert np.max(np.abs(v_dm - v_sv)) <= TOL
+
+
+# ---------------------------------------------------------------------------------------------
+# wide statevectors (tile-sweep path, > 12 active qubits)
+# ---------------------------------------------------------------------------------------------
+def _chain(n):
+    return [(i, i + 1) for i in range(n - 1)] + [(i + 1, i) for i in range(n - 1)]
+
+
+@pytest.mark.parametrize("tile_bits", [0, 12, 7])
+def test_sv_wide_vs_oracle(engine_gpu, tile_bits):
+    rng = np.random.default_rng(40 + tile_bits)
+    circs, obs = [], []
+    for n in (13, 14, 16, 13):
+        circs.append(F.random_basis_circuit(n, 150, rng, _chain(n)))
+        obs.append([[(l, float(rng.normal()))] for l in _labels(rng, n, 6)] + [[("Z" * n, 1.0), ("I" * n, 0.5)]])
+    circs.append(F.tfim_circuit(15, 3, 0.4, basis="Y"))
+    obs.append(F.tfim_observables(list(range(15)), 15))
+    circs.append(F.brickwork_circuit(14, 2, np.random.default_rng(3)))
+    obs.append(F.single_z_observables(list(range(14)), 14))
+    # a narrow circuit in the same batch goes through the one-CTA kernel
+    circs.append(F.tfim_circuit(6, 2, 0.3))
+    obs.append(F.tfim_observables(list(range(6)), 6))
+    ref = np.concatenate([helpers.oracle_sv_values(c, o) for c, o in zip(circs, obs)])
+    engine_gpu.set_options(sv_tile_bits=tile_bits)
+    vals, status = engine_gpu.run_sv(engine.encode_batch(circs, obs))
+    engine_gpu.set_options()
+    assert not status.any()
+    assert np.max(np.abs(vals - ref)) <= TOL
+
+
+def test_sv_wide_general_gates(engine_gpu):
+    from ml_qem_b200.circuit import Circuit
+    rng = np.random.default_rng(6)
+    n = 13
+    c = Circuit(n)
+    for _ in range(120):
+        a, b = (int(x) for x in rng.choice(n, size=2, replace=False))
+        k = int(rng.integers(0, 8))
+        th = float(rng.uniform(-3, 3))
+        if k == 0: c.append("cz", (a, b))
+        elif k == 1: c.append("swap", (a, b))
+        elif k == 2: c.append("crx", (a, b), (th,))
+        elif k == 3: c.append("rzz", (a, b), (th,))
+        elif k == 4: c.append("rxx", (a, b), (th,))
+        elif k == 5: c.append("ecr", (a, b))
+        elif k == 6: c.append("u3", (a,), (th, 0.3, -1.1))
+        else: c.append("cx", (a, b))
+    obs = [[(l, 1.0)] for l in _labels(rng, n, 8)]
+    ref = helpers.oracle_sv_values(c, obs)
+    vals, status = engine_gpu.run_sv(engine.encode_batch([c], [obs]))
+    assert not status.any()
+    assert np.max(np.abs(vals - ref)) <= TOL
+
+
+def test_sharded_statevector_single_rank_gpu(engine_gpu):
+    """ShardedStatevector on one GPU (no exchange): torch-owned state, segments through the C ABI."""
+    from ml_qem_b200.statevector import GpuExecutor, ShardedStatevector
+    sv = ShardedStatevector(GpuExecutor(engine_gpu))
+    n = 18
+    c = F.tfim_circuit(n, 3, 0.6, basis="X")
+    obs = F.tfim_observables(list(range(n)), n)
+    vals = sv.estimate(c, obs)
+    ref = helpers.oracle_sv_values(c, obs)
+    assert np.max(np.abs(vals - ref)) <= TOL
+    e = F.tfim_circuit(3, 0, 0.1)  # no gates at all
+    vals = sv.estimate(e, [[("ZZZ", 1.0)], [("XII", 1.0)]])
+    assert np.allclose(vals, [1.0, 0.0], atol=TOL)
+
+
+def test_sv_26q_product_state_and_light_cone(engine_gpu):
+    """Size-independent properties at a width the oracle cannot reach (26 qubits = 1 GiB):
+    J = 0 gives a product state with <Z> = cos(2 h dt steps); with J != 0 the bulk of a long
+    chain equals the bulk of a short chain (light cone of 2 steps)."""
+    n, steps, h, dt = 26, 3, 1.0, 0.5
+    c = F.tfim_circuit(n, steps, 0.0, h=h, dt=dt)
+    obs = F.tfim_observables(list(range(n)), n)
+    vals, status = engine_gpu.run_sv(engine.encode_batch([c], [obs]))
+    assert not status.any()
+    z = np.cos(2 * h * dt * steps)
+    assert np.max(np.abs(vals[:n] - z)) <= TOL
+    assert np.max(np.abs(vals[n:2 * n - 1] - z * z)) <= TOL
+    assert np.max(np.abs(vals[2 * n - 1:3 * n - 2])) <= TOL
+    assert abs(vals[-1] - z ** n) <= TOL
+    c = F.tfim_circuit(n, 2, 0.8)
+    small = F.tfim_circuit(12, 2, 0.8)
+    pick = lambda w, q: [[(F.pad_label({q: "Z"}, w), 1.0)], [(F.pad_label({q: "Z", q + 1: "Z"}, w), 1.0)],
+                         [(F.pad_label({q: "X", q + 1: "X"}, w), 1.0)]]
+    v_big, _ = engine_gpu.run_sv(engine.encode_batch([c], [pick(n, 13)]))
+    ref = helpers.oracle_sv_values(small, pick(12, 5))
+    assert np.max(np.abs(v_big - ref)) <= TOL
+
+
+def _n_gpus():
+    import torch
+    return torch.cuda.device_count()
+
+
+def test_sharded_statevector_two_gpus(lib):
+    """Amplitude-sharded over 2 GPUs (torchrun, NCCL all_to_all exchange) against the oracle."""
+    import subprocess, sys, os
+    if _n_gpus() < 2:
+        pytest.skip("needs 2 GPUs")
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    for world in [w for w in (2, 4, 8) if w <= _n_gpus()]:
+        r = subprocess.run([sys.executable, "-m", "torch.distributed.run", "--nnodes=1", f"--nproc-per-node={world}",
+                            "--master-addr", "127.0.0.1", "--master-port", str(29500 + world),
+                            os.path.join(root, "tests", "svx_multi_gpu.py"), "--check"], capture_output=True, text=True, timeout=600)
+        assert r.returncode == 0, r.stdout[-2000:] + r.stderr[-2000:]
