@@ -17,18 +17,23 @@ def nvcc_path():
     raise RuntimeError("nvcc not found")
 
 
-def build_library(force=False, verbose=False):
-    os.makedirs(os.path.dirname(OUT), exist_ok=True)
-    if not force and os.path.exists(OUT) and all(os.path.getmtime(OUT) >= os.path.getmtime(f) for f in SRC + HDR):
-        return OUT
+def build_library(force=False, verbose=False, out=None, defines=()):
+    """out/defines: alternative builds for kernel experiments (e.g. defines=["BWQ_KQ6_BLOCKS=3"])."""
+    out = out or OUT
+    os.makedirs(os.path.dirname(out), exist_ok=True)
+    if not force and os.path.exists(out) and all(os.path.getmtime(out) >= os.path.getmtime(f) for f in SRC + HDR):
+        return out
     cmd = [nvcc_path(), "-O3", "-std=c++17", "-gencode", "arch=compute_100a,code=sm_100a", "-lineinfo",
-           "-Xcompiler", "-fPIC", "-shared", "-o", OUT] + SRC
+           "-Xcompiler", "-fPIC", "-shared", "-o", out] + [f"-D{d}" for d in defines] + SRC
     if verbose:
         cmd.insert(1, "-Xptxas=-v")
         print(" ".join(cmd))
     subprocess.run(cmd, check=True)
-    return OUT
+    return out
 
 
 if __name__ == "__main__":
-    print(build_library(force="--force" in sys.argv, verbose="-v" in sys.argv))
+    defs = [a[2:] for a in sys.argv if a.startswith("-D")]
+    outs = [a[6:] for a in sys.argv if a.startswith("--out=")]
+    print(build_library(force="--force" in sys.argv or bool(defs), verbose="-v" in sys.argv, out=outs[0] if outs else None,
+                        defines=defs))

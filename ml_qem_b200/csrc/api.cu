@@ -133,7 +133,7 @@ struct bwq_ctx {
   std::string error;
   bwq_options opt{};
   NoiseTable noise;
-  DevBuf d_noise, d_prog, d_sv_prog, d_states, d_out, d_scratch, d_wide_prog, d_partial;
+  DevBuf d_b0, d_noise, d_prog, d_sv_prog, d_states, d_out, d_scratch, d_wide_prog, d_partial;
   PinBuf h_prog, h_sv_prog, h_out, h_wide_prog;
   bwq_stats stats{};
   DmPlan plan;
@@ -202,8 +202,15 @@ extern "C" int bwq_create(int device, bwq_ctx** out) {
     return bail(e, "cudaFuncSetAttribute(dm_sweep_kernel<7, full>)");
   if ((e = cudaFuncSetAttribute(sv_circuit_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 16 << 12)) != cudaSuccess)
     return bail(e, "cudaFuncSetAttribute(sv_circuit_kernel)");
-  if ((e = cudaFuncSetAttribute(sv_sweep_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (16 << kSvTileBitsMax) + kBlockBytes)) != cudaSuccess)
+  if ((e = cudaFuncSetAttribute(sv_sweep_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (16 << kSvTileBitsMax) + kBlockBytes + 1024)) != cudaSuccess)
     return bail(e, "cudaFuncSetAttribute(sv_sweep_kernel)");
+  {
+    std::vector<uint32_t> tab((size_t)kB0Pairs * kB0Groups);
+    fill_b0_table(tab.data());
+    if ((e = ctx->d_b0.reserve(tab.size() * sizeof(uint32_t))) != cudaSuccess) return bail(e, "cudaMalloc(b0 table)");
+    if ((e = cudaMemcpy(ctx->d_b0.p, tab.data(), tab.size() * sizeof(uint32_t), cudaMemcpyHostToDevice)) != cudaSuccess)
+      return bail(e, "cudaMemcpy(b0 table)");
+  }
   *out = ctx;
   return BWQ_OK;
 }
@@ -212,7 +219,7 @@ extern "C" int bwq_destroy(bwq_ctx* ctx) {
   if (!ctx) return BWQ_OK;
   cudaSetDevice(ctx->device);
   cudaStreamSynchronize(ctx->stream);
-  ctx->d_noise.release(); ctx->d_prog.release(); ctx->d_states.release(); ctx->d_out.release();
+  ctx->d_b0.release(); ctx->d_noise.release(); ctx->d_prog.release(); ctx->d_states.release(); ctx->d_out.release();
   ctx->d_scratch.release(); ctx->h_prog.release(); ctx->h_out.release();
   ctx->d_sv_prog.release(); ctx->h_sv_prog.release();
   ctx->d_wide_prog.release(); ctx->h_wide_prog.release(); ctx->d_partial.release();
@@ -297,7 +304,8 @@ static int host_threads(const bwq_ctx* ctx) {
 }
 
 template <int KQ, bool FULL> static cudaError_t launch_sweep(const DmLaunch& L, int sweep, int64_t n_cta, cudaStream_t s) {
-  dm_sweep_kernel<KQ, FULL><<<(unsigned)n_cta, SweepCfg<KQ>::kThreads, (sizeof(double) << (2 * KQ)) + kBlockBytes, s>>>(L, sweep);
+  const size_t dyn = KQ <= 6 ? 0 : (sizeof(double) << (2 * KQ)) + kBlockBytes;  // KQ <= 6: static shared memory
+  dm_sweep_kernel<KQ, FULL><<<(unsigned)n_cta, SweepCfg<KQ>::kThreads, dyn, s>>>(L, sweep);
   return cudaGetLastError();
 }
 
@@ -513,6 +521,7 @@ static int dm_execute_impl(bwq_ctx* ctx, double* out_vals, bool out_on_device) {
     L.sweep_range = (const int32_t*)(db + P.o_range);
     L.sweeps = (const SweepDesc*)(db + P.o_sweeps);
     L.prog = (const uint4*)(db + P.o_prog);
+    L.b0_table = (const uint32_t*)ctx->d_b0.p;
     const int64_t tiles = int64_t(1) << (2 * (ch.nd - ch.kq));
     if (ci < n_ev) CK(cudaEventRecord(ctx->chunk_ev[2 * ci], st));
     for (size_t sidx = 0; sidx < ch.live.size(); ++sidx) {
@@ -591,7 +600,7 @@ extern "C" int bwq_dm_run_device_out(bwq_ctx* ctx, const bwq_batch* b, double* d
 // wide statevectors (13..31 active qubits on one GPU): tile sweeps, batched per chunk of equal width
 // ------------------------------------------------------------------------------------------------
 static cudaError_t launch_sv_sweep(const SvxLaunch& L, int sweep, int64_t n_cta, cudaStream_t s) {
-  const size_t smem = (sizeof(double2) << L.tile_bits) + kBlockBytes;
+  const size_t smem = (sizeof(double2) << L.tile_bits) + kBlockBytes + 1024;  // tile | program | deposit table
   sv_sweep_kernel<<<(unsigned)n_cta, kSvxThreads, smem, s>>>(L, sweep);
   return cudaGetLastError();
 }

@@ -21,6 +21,7 @@ struct DmLaunch {
   const int32_t* sweep_range;  // [2 * n_circuits] absolute {begin, end} per sorted circuit
   const SweepDesc* sweeps;
   const uint4* prog;           // sweep blocks (16-byte units)
+  const uint32_t* b0_table;    // [21][1024] group bases (bytes) of the register passes (fill_b0_table)
 };
 
 // ---------------------------------------------------------------------------------------------
@@ -33,56 +34,68 @@ template <bool ON_B> __device__ __forceinline__ constexpr int idx1(int d, int ot
   return ON_B ? (other + 4 * d) : (d + 4 * other);
 }
 
+// Every op runs on NG register groups at once (v[g][da + 4*db]): the parameters -- uniform
+// shared-memory loads, one wavefront each -- and the op decode are paid once per NG groups.
+
 // general 4x4 (kept for channels that are not trace preserving)
-template <bool ON_B> __device__ __forceinline__ void op_dense1(double (&v)[16], const double* __restrict__ m) {
+template <bool ON_B, int NG> __device__ __forceinline__ void op_dense1(double (&v)[NG][16], const double* __restrict__ m) {
   const double2* m2 = reinterpret_cast<const double2*>(m);
 #pragma unroll
-  for (int o = 0; o < 4; ++o) {
-    const double x0 = v[idx1<ON_B>(0, o)], x1 = v[idx1<ON_B>(1, o)], x2 = v[idx1<ON_B>(2, o)], x3 = v[idx1<ON_B>(3, o)];
+  for (int i4 = 0; i4 < 1; ++i4) {
+    double x[NG][4][4];
+#pragma unroll
+    for (int g = 0; g < NG; ++g)
+#pragma unroll
+      for (int o = 0; o < 4; ++o)
+#pragma unroll
+        for (int d = 0; d < 4; ++d) x[g][o][d] = v[g][idx1<ON_B>(d, o)];
 #pragma unroll
     for (int i = 0; i < 4; ++i) {
       const double2 a = m2[2 * i], b = m2[2 * i + 1];
-      v[idx1<ON_B>(i, o)] = fma(b.y, x3, fma(b.x, x2, fma(a.y, x1, a.x * x0)));
+#pragma unroll
+      for (int g = 0; g < NG; ++g)
+#pragma unroll
+        for (int o = 0; o < 4; ++o)
+          v[g][idx1<ON_B>(i, o)] = fma(b.y, x[g][o][3], fma(b.x, x[g][o][2], fma(a.y, x[g][o][1], a.x * x[g][o][0])));
     }
   }
 }
 
 // trace-preserving 1-qubit channel: row 0 of the transfer matrix is (1,0,0,0); m = rows 1..3.
-// The last FMA of each row consumes x3, so results can land in the registers of x1..x3.
-template <bool ON_B> __device__ __forceinline__ void op_aff1(double (&v)[16], const double* __restrict__ m) {
+template <bool ON_B, int NG> __device__ __forceinline__ void op_aff1(double (&v)[NG][16], const double* __restrict__ m) {
   const double2* m2 = reinterpret_cast<const double2*>(m);
   double2 a[6];
 #pragma unroll
   for (int i = 0; i < 6; ++i) a[i] = m2[i];
 #pragma unroll
-  for (int o = 0; o < 4; ++o) {
-    const double x0 = v[idx1<ON_B>(0, o)], x1 = v[idx1<ON_B>(1, o)], x2 = v[idx1<ON_B>(2, o)], x3 = v[idx1<ON_B>(3, o)];
-    const double p1 = fma(a[1].x, x2, fma(a[0].y, x1, a[0].x * x0));
-    const double p2 = fma(a[3].x, x2, fma(a[2].y, x1, a[2].x * x0));
-    const double p3 = fma(a[5].x, x2, fma(a[4].y, x1, a[4].x * x0));
-    v[idx1<ON_B>(1, o)] = fma(a[1].y, x3, p1);
-    v[idx1<ON_B>(2, o)] = fma(a[3].y, x3, p2);
-    v[idx1<ON_B>(3, o)] = fma(a[5].y, x3, p3);
-  }
+  for (int g = 0; g < NG; ++g)
+#pragma unroll
+    for (int o = 0; o < 4; ++o) {
+      const double x0 = v[g][idx1<ON_B>(0, o)], x1 = v[g][idx1<ON_B>(1, o)], x2 = v[g][idx1<ON_B>(2, o)], x3 = v[g][idx1<ON_B>(3, o)];
+      const double p1 = fma(a[1].x, x2, fma(a[0].y, x1, a[0].x * x0));
+      const double p2 = fma(a[3].x, x2, fma(a[2].y, x1, a[2].x * x0));
+      const double p3 = fma(a[5].x, x2, fma(a[4].y, x1, a[4].x * x0));
+      v[g][idx1<ON_B>(1, o)] = fma(a[1].y, x3, p1);
+      v[g][idx1<ON_B>(2, o)] = fma(a[3].y, x3, p2);
+      v[g][idx1<ON_B>(3, o)] = fma(a[5].y, x3, p3);
+    }
 }
 
 // rz / phase as three in-place shears: x -= t y; y += s x; x -= t y; then the optional sign
-template <bool ON_B> __device__ __forceinline__ void op_rot(double (&v)[16], const double* __restrict__ m) {
+template <bool ON_B, int NG> __device__ __forceinline__ void op_rot(double (&v)[NG][16], const double* __restrict__ m) {
   const double2 ts = *reinterpret_cast<const double2*>(m);
   const double sign = m[2];
 #pragma unroll
-  for (int o = 0; o < 4; ++o) {
-    double x = v[idx1<ON_B>(1, o)], y = v[idx1<ON_B>(2, o)];
-    x = fma(-ts.x, y, x);
-    y = fma(ts.y, x, y);
-    x = fma(-ts.x, y, x);
-    v[idx1<ON_B>(1, o)] = x;
-    v[idx1<ON_B>(2, o)] = y;
-  }
-  if (sign < 0.0) {
+  for (int g = 0; g < NG; ++g)
 #pragma unroll
-    for (int o = 0; o < 4; ++o) { v[idx1<ON_B>(1, o)] = -v[idx1<ON_B>(1, o)]; v[idx1<ON_B>(2, o)] = -v[idx1<ON_B>(2, o)]; }
-  }
+    for (int o = 0; o < 4; ++o) {
+      double x = v[g][idx1<ON_B>(1, o)], y = v[g][idx1<ON_B>(2, o)];
+      x = fma(-ts.x, y, x);
+      y = fma(ts.y, x, y);
+      x = fma(-ts.x, y, x);
+      v[g][idx1<ON_B>(1, o)] = sign < 0.0 ? -x : x;
+      v[g][idx1<ON_B>(2, o)] = sign < 0.0 ? -y : y;
+    }
 }
 
 // CX Pauli-transfer matrix = signed permutation (an involution: six transpositions);
@@ -90,15 +103,18 @@ template <bool ON_B> __device__ __forceinline__ void op_rot(double (&v)[16], con
 __device__ constexpr int kCxSrc[16] = {0, 5, 6, 3, 4, 1, 2, 7, 11, 14, 13, 8, 15, 10, 9, 12};
 __device__ constexpr int kCxSgn[16] = {1, 1, 1, 1, 1, 1, 1, 1, 1, 1, -1, 1, 1, -1, 1, 1};
 
-template <bool CTRL_B> __device__ __forceinline__ void op_cx(double (&v)[16]) {
-  double w[16];
+template <bool CTRL_B, int NG> __device__ __forceinline__ void op_cx(double (&v)[NG][16]) {
 #pragma unroll
-  for (int i = 0; i < 16; ++i) w[i] = v[i];
+  for (int g = 0; g < NG; ++g) {
+    double w[16];
 #pragma unroll
-  for (int i = 0; i < 16; ++i) {
-    const int j = kCxSrc[i];
-    const double x = w[idx2<CTRL_B>(j & 3, j >> 2)];
-    v[idx2<CTRL_B>(i & 3, i >> 2)] = kCxSgn[i] > 0 ? x : -x;
+    for (int i = 0; i < 16; ++i) w[i] = v[g][i];
+#pragma unroll
+    for (int i = 0; i < 16; ++i) {
+      const int j = kCxSrc[i];
+      const double x = w[idx2<CTRL_B>(j & 3, j >> 2)];
+      v[g][idx2<CTRL_B>(i & 3, i >> 2)] = kCxSgn[i] > 0 ? x : -x;
+    }
   }
 }
 
@@ -106,60 +122,72 @@ template <bool CTRL_B> __device__ __forceinline__ void op_cx(double (&v)[16]) {
 // with (d0,d1) = digits of the error's (q0,q1).  WITH_CX: in = CX(v) first, control = q0 (the
 // noise of a cx is keyed by (control, target)); the permutation and signs fold into operand
 // selection, so the fused op costs the 25 multiply-adds of the noise alone.
-template <bool SW, bool WITH_CX> __device__ __forceinline__ void op_relax2(double (&v)[16], const double* __restrict__ m) {
+// m: d[16] (index d0 + 4 d1), ca[4], cb[4], cab, pad -- 26 doubles, read as 16-byte uniform loads
+template <bool SW, bool WITH_CX, int NG> __device__ __forceinline__ void op_relax2(double (&v)[NG][16], const double* __restrict__ m) {
   const double2* m2 = reinterpret_cast<const double2*>(m);
-  double p[26];
+  double y[NG][16];  // input in (q0,q1) index order, after the optional CX
 #pragma unroll
-  for (int i = 0; i < 13; ++i) { const double2 t = m2[i]; p[2 * i] = t.x; p[2 * i + 1] = t.y; }
-  double y[16];  // input in (q0,q1) index order, after the optional CX
+  for (int g = 0; g < NG; ++g)
 #pragma unroll
-  for (int i = 0; i < 16; ++i) {
-    if (WITH_CX) {
-      const int j = kCxSrc[i];
-      const double x = v[idx2<SW>(j & 3, j >> 2)];
-      y[i] = kCxSgn[i] > 0 ? x : -x;
-    } else {
-      y[i] = v[idx2<SW>(i & 3, i >> 2)];
+    for (int i = 0; i < 16; ++i) {
+      const int j = WITH_CX ? kCxSrc[i] : i;
+      const double x = v[g][idx2<SW>(j & 3, j >> 2)];
+      y[g][i] = (WITH_CX && kCxSgn[i] < 0) ? -x : x;
     }
+  const double2 cb01 = m2[10], cb23 = m2[11], cabp = m2[12];
+  const double cb[4] = {cb01.x, cb01.y, cb23.x, cb23.y};
+#pragma unroll
+  for (int b = 0; b < 4; ++b) {
+    const double2 d01 = m2[2 * b], d23 = m2[2 * b + 1];
+    const double2 ca2 = m2[8 + (b >> 1)];
+    const double ca = (b & 1) ? ca2.y : ca2.x;
+    const double d[4] = {d01.x, d01.y, d23.x, d23.y};
+#pragma unroll
+    for (int g = 0; g < NG; ++g)
+#pragma unroll
+      for (int a = 0; a < 4; ++a) {
+        double r = d[a] * y[g][a + 4 * b];
+        if (a == 3) r = fma(ca, y[g][0 + 4 * b], r);
+        if (b == 3) r = fma(cb[a], y[g][a + 0], r);
+        if (a == 3 && b == 3) r = fma(cabp.x, y[g][0], r);
+        v[g][idx2<SW>(a, b)] = r;
+      }
   }
-  // p[0..15] = d[d0 + 4 d1], p[16..19] = ca[b], p[20..23] = cb[a], p[24] = cab
-#pragma unroll
-  for (int b = 0; b < 4; ++b)
-#pragma unroll
-    for (int a = 0; a < 4; ++a) {
-      double r = p[a + 4 * b] * y[a + 4 * b];
-      if (a == 3) r = fma(p[16 + b], y[0 + 4 * b], r);
-      if (b == 3) r = fma(p[20 + a], y[a + 0], r);
-      if (a == 3 && b == 3) r = fma(p[24], y[0], r);
-      v[idx2<SW>(a, b)] = r;
-    }
 }
 
-template <bool SW> __device__ __forceinline__ void op_dense2(double (&v)[16], const double* __restrict__ m) {
-  double w[16];
+template <bool SW, int NG> __device__ __forceinline__ void op_dense2(double (&v)[NG][16], const double* __restrict__ m) {
+  double w[NG][16];
 #pragma unroll
-  for (int i = 0; i < 16; ++i) w[i] = v[i];
+  for (int g = 0; g < NG; ++g)
+#pragma unroll
+    for (int i = 0; i < 16; ++i) w[g][i] = v[g][i];
   const double2* m2 = reinterpret_cast<const double2*>(m);
 #pragma unroll
   for (int i1 = 0; i1 < 4; ++i1)
 #pragma unroll
     for (int i0 = 0; i0 < 4; ++i0) {
       const int row = i0 + 4 * i1;
-      double s = 0.0;
+      double s[NG];
+#pragma unroll
+      for (int g = 0; g < NG; ++g) s[g] = 0.0;
 #pragma unroll
       for (int jj = 0; jj < 8; ++jj) {
         const double2 t = m2[row * 8 + jj];
         const int j = 2 * jj;
-        s = fma(t.x, w[idx2<SW>(j & 3, j >> 2)], s);
-        s = fma(t.y, w[idx2<SW>((j + 1) & 3, (j + 1) >> 2)], s);
+#pragma unroll
+        for (int g = 0; g < NG; ++g) {
+          s[g] = fma(t.x, w[g][idx2<SW>(j & 3, j >> 2)], s[g]);
+          s[g] = fma(t.y, w[g][idx2<SW>((j + 1) & 3, (j + 1) >> 2)], s[g]);
+        }
       }
-      v[idx2<SW>(i0, i1)] = s;
+#pragma unroll
+      for (int g = 0; g < NG; ++g) v[g][idx2<SW>(i0, i1)] = s[g];
     }
 }
 
 // ops and parameters of a pass, read from the sweep block staged in shared memory
-template <bool FULL>
-__device__ __forceinline__ void run_ops(double (&v)[16], const double* __restrict__ blk, int ops_q16, int n_ops) {
+template <bool FULL, int NG>
+__device__ __forceinline__ void run_ops(double (&v)[NG][16], const double* __restrict__ blk, int ops_q16, int n_ops) {
   const uint4* ops = reinterpret_cast<const uint4*>(blk) + ops_q16;
   for (int o = 0; o < n_ops; ++o) {
     const uint4 raw = ops[o];
@@ -167,21 +195,21 @@ __device__ __forceinline__ void run_ops(double (&v)[16], const double* __restric
     const double* ma = blk + (raw.y & 0xffffu);
     const double* mb = blk + (raw.y >> 16);
     const double* m2q = blk + (raw.z & 0xffffu);
-    if (pre_a == P_AFF) op_aff1<false>(v, ma);
-    else if (pre_a == P_ROT) op_rot<false>(v, ma);
-    else if (FULL && pre_a == P_DENSE) op_dense1<false>(v, ma);
-    if (pre_b == P_AFF) op_aff1<true>(v, mb);
-    else if (pre_b == P_ROT) op_rot<true>(v, mb);
-    else if (FULL && pre_b == P_DENSE) op_dense1<true>(v, mb);
+    if (pre_a == P_AFF) op_aff1<false, NG>(v, ma);
+    else if (pre_a == P_ROT) op_rot<false, NG>(v, ma);
+    else if (FULL && pre_a == P_DENSE) op_dense1<false, NG>(v, ma);
+    if (pre_b == P_AFF) op_aff1<true, NG>(v, mb);
+    else if (pre_b == P_ROT) op_rot<true, NG>(v, mb);
+    else if (FULL && pre_b == P_DENSE) op_dense1<true, NG>(v, mb);
     switch (twoq) {
-      case Q_CXN_AB: op_relax2<false, true>(v, m2q); break;
-      case Q_CXN_BA: op_relax2<true, true>(v, m2q); break;
-      case Q_CX_AB: op_cx<false>(v); break;
-      case Q_CX_BA: op_cx<true>(v); break;
-      case Q_RELAX: op_relax2<false, false>(v, m2q); break;
-      case Q_RELAX_SW: op_relax2<true, false>(v, m2q); break;
-      case Q_DENSE: if constexpr (FULL) op_dense2<false>(v, m2q); break;
-      case Q_DENSE_SW: if constexpr (FULL) op_dense2<true>(v, m2q); break;
+      case Q_CXN_AB: op_relax2<false, true, NG>(v, m2q); break;
+      case Q_CXN_BA: op_relax2<true, true, NG>(v, m2q); break;
+      case Q_CX_AB: op_cx<false, NG>(v); break;
+      case Q_CX_BA: op_cx<true, NG>(v); break;
+      case Q_RELAX: op_relax2<false, false, NG>(v, m2q); break;
+      case Q_RELAX_SW: op_relax2<true, false, NG>(v, m2q); break;
+      case Q_DENSE: if constexpr (FULL) op_dense2<false, NG>(v, m2q); break;
+      case Q_DENSE_SW: if constexpr (FULL) op_dense2<true, NG>(v, m2q); break;
       default: break;
     }
   }
@@ -214,6 +242,10 @@ __host__ __device__ constexpr uint32_t swz(uint32_t j) {
 __constant__ const uint16_t kSwzDigit[7][4] = {
     {0, 1, 2, 3},          {0, 4, 8, 12},         {0, 21, 42, 63},        {0, 73, 142, 199},
     {0, 269, 518, 779},    {0, 1037, 2054, 3083}, {0, 4105, 8206, 12295}};
+// the same offsets in bytes (8-byte elements)
+__constant__ const uint32_t kSwzDigit8[7][4] = {
+    {0, 8, 16, 24},          {0, 32, 64, 96},         {0, 168, 336, 504},        {0, 584, 1136, 1592},
+    {0, 2152, 4144, 6232},   {0, 8296, 16432, 24664}, {0, 32840, 65648, 98360}};
 static_assert(swz(1u << 4) == 21 && swz(2u << 6) == 142 && swz(3u << 8) == 779 && swz(1u << 10) == 1037 &&
               swz(3u << 12) == 12295 && swz(2u << 4) == 42 && swz(3u << 6) == 199, "swizzle table");
 
@@ -223,8 +255,12 @@ static_assert(swz(1u << 4) == 21 && swz(2u << 6) == 142 && swz(3u << 8) == 779 &
 template <int KQ> struct SweepCfg {
   static constexpr int kElems = 1 << (2 * KQ);
   static constexpr int kGroups = kElems / 16;
-  static constexpr int kThreads = kGroups >= 256 ? 256 : (kGroups >= 32 ? kGroups : 32);
-  static constexpr int kMinBlocks = KQ >= 7 ? 1 : (KQ == 6 ? 3 : 4);
+  static constexpr int kNG = kGroups >= 64 ? 2 : 1;   // register groups per thread
+  static constexpr int kThreads = kGroups / kNG >= 256 ? 256 : (kGroups / kNG >= 32 ? kGroups / kNG : 32);
+#ifndef BWQ_KQ6_BLOCKS
+#define BWQ_KQ6_BLOCKS 3
+#endif
+  static constexpr int kMinBlocks = KQ >= 7 ? 1 : (KQ == 6 ? BWQ_KQ6_BLOCKS : 4);
 };
 
 // tile-local index j (2 bits per slot) -> offset in the state (2 bits per digit position)
@@ -235,15 +271,60 @@ template <int KQ> __device__ __forceinline__ int64_t deposit(uint32_t j, const i
   return off;
 }
 
+// all register passes of one sweep block on the tile staged in shared memory
+template <int KQ, bool FULL>
+__device__ __forceinline__ void run_passes(double* __restrict__ tile, const double* __restrict__ pbuf,
+                                           const uint32_t* __restrict__ b0_table, const int tid) {
+  constexpr int G = SweepCfg<KQ>::kGroups, T = SweepCfg<KQ>::kThreads, NG = SweepCfg<KQ>::kNG;
+  const int n_passes = reinterpret_cast<const int*>(pbuf)[0];
+  char* const tile_b = reinterpret_cast<char*>(tile);
+  for (int p = 0; p < n_passes; ++p) {
+    if (p) __syncthreads();
+    const uint2 praw = *reinterpret_cast<const uint2*>(pbuf + 2 * (1 + p));
+    const int ops_q16 = praw.x & 0xffffu, n_ops = praw.x >> 16;
+    const int sa = praw.y & 0xffu, sb = (praw.y >> 8) & 0xffu;
+    const int lo = min(sa, sb), hi = max(sa, sb);
+    // swizzled byte offsets of the 16 (da, db) corners (uniform) and of the thread's group base
+    // (table built on the host: index = swz(grp with zero digits inserted at lo and hi))
+    uint32_t oab[16];
+#pragma unroll
+    for (int db = 0; db < 4; ++db)
+#pragma unroll
+      for (int da = 0; da < 4; ++da) oab[da + 4 * db] = kSwzDigit8[sa][da] ^ kSwzDigit8[sb][db];
+    const uint32_t* __restrict__ b0row = b0_table + ((hi * (hi - 1) / 2 + lo) << 10);
+    for (int grp = tid; grp < G; grp += T * NG) {
+      uint32_t b0[NG];
+      double v[NG][16];
+#pragma unroll
+      for (int g = 0; g < NG; ++g) b0[g] = __ldg(b0row + min(grp + g * T, G - 1));
+#pragma unroll
+      for (int g = 0; g < NG; ++g)
+#pragma unroll
+        for (int i = 0; i < 16; ++i) v[g][i] = *reinterpret_cast<const double*>(tile_b + (b0[g] ^ oab[i]));
+      run_ops<FULL, NG>(v, pbuf, ops_q16, n_ops);
+#pragma unroll
+      for (int g = 0; g < NG; ++g)
+        if (NG == 1 || grp + g * T < G) {
+#pragma unroll
+          for (int i = 0; i < 16; ++i) *reinterpret_cast<double*>(tile_b + (b0[g] ^ oab[i])) = v[g][i];
+        }
+    }
+  }
+}
+
 // FULL = also carries the dense 4x4 / 16x16 ops (coherent errors, non-basis 2-qubit gates); the
 // lean instantiation keeps the register budget at 3 CTAs per SM.
 template <int KQ, bool FULL>
 __global__ void __launch_bounds__(SweepCfg<KQ>::kThreads, FULL ? 1 : SweepCfg<KQ>::kMinBlocks)
 dm_sweep_kernel(const DmLaunch L, const int sweep_idx) {
-  constexpr int E = SweepCfg<KQ>::kElems, G = SweepCfg<KQ>::kGroups, T = SweepCfg<KQ>::kThreads;
+  constexpr int E = SweepCfg<KQ>::kElems, G = SweepCfg<KQ>::kGroups, T = SweepCfg<KQ>::kThreads, NG = SweepCfg<KQ>::kNG;
   constexpr int U = E / 2;                       // double2 units per tile
   constexpr int NIT = (U + T - 1) / T;           // load/store iterations per thread
-  extern __shared__ __align__(16) double tile[];
+  // KQ <= 6: static shared memory, so the tile base is a compile-time constant and the pass
+  // gather is one XOR + LDS [reg + imm] per element; KQ = 7 (128 KiB) needs the dynamic window
+  extern __shared__ __align__(16) double dyn_tile[];
+  __shared__ __align__(16) double st_tile[KQ <= 6 ? E + kBlockBytes / 8 : 2];
+  double* const tile = KQ <= 6 ? st_tile : dyn_tile;
   const int tid = threadIdx.x;
   const int tiles_log2 = 2 * (L.n_digits - KQ);
   const int64_t slot = int64_t(blockIdx.x) >> tiles_log2;
@@ -281,11 +362,11 @@ dm_sweep_kernel(const DmLaunch L, const int sweep_idx) {
     base |= int64_t(rest) << (2 * next);
   }
   double* __restrict__ g = L.states + slot * L.stride + base;
-  double2* tile2 = reinterpret_cast<double2*>(tile);
 
   // Unit u = tid + k*T covers tile elements j = 2u, 2u+1.  deposit() and swz() are bitwise
   // linear, so the per-thread part (tid) is computed once and the per-iteration part (k*T) is
-  // uniform / compile-time.
+  // uniform / compile-time.  swz(j + 1) = swz(j) ^ 1: the pair goes to shared memory as two
+  // 8-byte accesses (same bank traffic as one 16-byte access, no select on the swizzle parity).
   const uint32_t j_thr = 2u * uint32_t(tid);
   const int64_t off_thr = deposit<KQ>(j_thr, pos);
   const uint32_t p_thr = swz(j_thr);
@@ -300,8 +381,8 @@ dm_sweep_kernel(const DmLaunch L, const int sweep_idx) {
       const bool hi_ok = tile_ok && ((((j >> 2) ^ (j >> 3)) & 0x15555555u) == 0u);
       const bool d0_is2 = (j & 2u) != 0u;
       const uint32_t p = p_thr ^ swz(2u * uint32_t(k * T));
-      const double e0 = (hi_ok && !d0_is2) ? 1.0 : 0.0, e1 = (hi_ok && d0_is2) ? 1.0 : 0.0;
-      tile2[p >> 1] = (p & 1u) ? make_double2(e1, e0) : make_double2(e0, e1);
+      tile[p] = (hi_ok && !d0_is2) ? 1.0 : 0.0;
+      tile[p ^ 1u] = (hi_ok && d0_is2) ? 1.0 : 0.0;
     }
   } else {
     double2 val[NIT];
@@ -315,40 +396,15 @@ dm_sweep_kernel(const DmLaunch L, const int sweep_idx) {
     for (int k = 0; k < NIT; ++k) {
       if (NIT * T != U && tid + k * T >= U) break;
       const uint32_t p = p_thr ^ swz(2u * uint32_t(k * T));
-      tile2[p >> 1] = (p & 1u) ? make_double2(val[k].y, val[k].x) : val[k];
+      tile[p] = val[k].x;
+      tile[p ^ 1u] = val[k].y;
     }
   }
 
   // ---- register passes
   cp_async_wait_all();
   __syncthreads();
-  const int n_passes = reinterpret_cast<const int*>(pbuf)[0];
-  for (int p = 0; p < n_passes; ++p) {
-    if (p) __syncthreads();
-    const uint2 praw = *reinterpret_cast<const uint2*>(pbuf + 2 * (1 + p));
-    const int ops_q16 = praw.x & 0xffffu, n_ops = praw.x >> 16;
-    const int sa = praw.y & 0xffu, sb = (praw.y >> 8) & 0xffu;
-    const int lo = min(sa, sb), hi = max(sa, sb);
-    uint32_t oa[4], ob[4];
-#pragma unroll
-    for (int d = 0; d < 4; ++d) { oa[d] = kSwzDigit[sa][d]; ob[d] = kSwzDigit[sb][d]; }
-    for (int grp = tid; grp < G; grp += T) {
-      const uint32_t low = grp & ((1u << (2 * lo)) - 1u);
-      const uint32_t mid = (grp >> (2 * lo)) & ((1u << (2 * (hi - lo - 1))) - 1u);
-      const uint32_t high = grp >> (2 * (hi - 1));
-      const uint32_t b0 = swz(low | (mid << (2 * lo + 2)) | (high << (2 * hi + 2)));
-      double v[16];
-#pragma unroll
-      for (int db = 0; db < 4; ++db)
-#pragma unroll
-        for (int da = 0; da < 4; ++da) v[da + 4 * db] = tile[b0 ^ oa[da] ^ ob[db]];
-      run_ops<FULL>(v, pbuf, ops_q16, n_ops);
-#pragma unroll
-      for (int db = 0; db < 4; ++db)
-#pragma unroll
-        for (int da = 0; da < 4; ++da) tile[b0 ^ oa[da] ^ ob[db]] = v[da + 4 * db];
-    }
-  }
+  run_passes<KQ, FULL>(tile, pbuf, L.b0_table, tid);
   __syncthreads();
 
   // ---- store
@@ -357,9 +413,23 @@ dm_sweep_kernel(const DmLaunch L, const int sweep_idx) {
     if (NIT * T != U && tid + k * T >= U) break;
     const int64_t off = off_thr | deposit<KQ>(2u * uint32_t(k * T), pos);
     const uint32_t p = p_thr ^ swz(2u * uint32_t(k * T));
-    const double2 val = tile2[p >> 1];
-    *reinterpret_cast<double2*>(g + off) = (p & 1u) ? make_double2(val.y, val.x) : val;
+    *reinterpret_cast<double2*>(g + off) = make_double2(tile[p], tile[p ^ 1u]);
   }
+}
+
+// group-base table of the register passes: row (lo, hi) -> swz(grp with zero digits at slots lo
+// and hi) in bytes, grp < 1024 (KQ = 7); filled once per context
+constexpr int kB0Pairs = 21, kB0Groups = 1024;
+inline void fill_b0_table(uint32_t* t) {
+  for (int hi = 1; hi < 7; ++hi)
+    for (int lo = 0; lo < hi; ++lo)
+      for (uint32_t grp = 0; grp < (uint32_t)kB0Groups; ++grp) {
+        const uint32_t low = grp & ((1u << (2 * lo)) - 1u);
+        const uint32_t mid = (grp >> (2 * lo)) & ((1u << (2 * (hi - lo - 1))) - 1u);
+        const uint32_t high = grp >> (2 * (hi - 1));
+        t[((hi * (hi - 1) / 2 + lo) << 10) + grp] =
+            8u * swz(low | (mid << (2 * lo + 2)) | (high << (2 * hi + 2)));
+      }
 }
 
 // ---------------------------------------------------------------------------------------------

@@ -457,9 +457,10 @@ void lower_dm_circuit(const NoiseTable& noise, const bwq_batch& b, int c, const 
     for (const MacroOp& o : p.ops) { add(o.off_a, pre_words(o.pre_a)); add(o.off_b, pre_words(o.pre_b)); add(o.off_2, two_words(o.twoq)); }
     return bytes;
   };
+  const int block_bytes = kBlockBytes;
   // split passes whose block alone would not fit the shared-memory program buffer
   {
-    const int cap = kBlockBytes - (int)sizeof(BlockHdr);
+    const int cap = block_bytes - (int)sizeof(BlockHdr);
     std::vector<HostPass> split;
     for (HostPass& p : passes) {
       if (pass_bytes(p, {}) <= cap) { split.push_back(std::move(p)); continue; }
@@ -506,7 +507,7 @@ void lower_dm_circuit(const NoiseTable& noise, const bwq_batch& b, int c, const 
       if (blocked[p.qa] || blocked[p.qb]) { block(p.qa); block(p.qb); continue; }
       const int need = (!in_tile[p.qa]) + (!in_tile[p.qb]);
       const int add = pass_bytes(p, seen);
-      if (nt + need > kq || bytes + add > kBlockBytes) { block(p.qa); block(p.qb); continue; }
+      if (nt + need > kq || bytes + add > block_bytes) { block(p.qa); block(p.qb); continue; }
       if (!in_tile[p.qa]) { in_tile[p.qa] = 1; ++nt; }
       if (!in_tile[p.qb]) { in_tile[p.qb] = 1; ++nt; }
       done[i] = 1;

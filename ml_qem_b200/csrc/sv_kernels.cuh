@@ -46,12 +46,12 @@ __device__ __forceinline__ double2 cfma_d(double2 a, double2 b, double2 c) {
   return make_double2(fma(a.x, b.x, fma(-a.y, b.y, c.x)), fma(a.x, b.y, fma(a.y, b.x, c.y)));
 }
 
-// tile-local index (low bits + 8 free slots) -> offset inside the shard
-__device__ __forceinline__ uint32_t svx_deposit(uint32_t j, int low_bits, const int (&pos)[8]) {
-  uint32_t off = j & ((1u << low_bits) - 1u);
-  const uint32_t up = j >> low_bits;
+// tile-local index (low bits + 8 free slots) -> offset inside the shard.  pk = the 8 slot
+// positions, one byte each.
+__device__ __forceinline__ uint32_t svx_deposit_hi(uint32_t up, uint64_t pk) {
+  uint32_t off = 0;
 #pragma unroll
-  for (int s = 0; s < 8; ++s) off |= ((up >> s) & 1u) << pos[s];
+  for (int s = 0; s < 8; ++s) off |= ((up >> s) & 1u) << (uint32_t(pk >> (8 * s)) & 0xffu);
   return off;
 }
 
@@ -76,12 +76,7 @@ __global__ void __launch_bounds__(kSvxThreads, 3) sv_sweep_kernel(const SvxLaunc
     const int len = swraw.y;
     for (int i = tid; i < len; i += kSvxThreads) cp_async16(reinterpret_cast<uint4*>(pbuf) + i, src + i);
   }
-  int pos[8];
-  {
-    const uint64_t pk = (uint64_t(uint32_t(swraw.w)) << 32) | uint32_t(swraw.z);
-#pragma unroll
-    for (int s = 0; s < 8; ++s) pos[s] = int((pk >> (8 * s)) & 0xff);
-  }
+  const uint64_t pk = (uint64_t(uint32_t(swraw.w)) << 32) | uint32_t(swraw.z);  // slot positions
   // tile id -> the physical bits that are not resident
   uint32_t base = 0;
   {
@@ -90,18 +85,24 @@ __global__ void __launch_bounds__(kSvxThreads, 3) sv_sweep_kernel(const SvxLaunc
 #pragma unroll
     for (int s = 0; s < 8; ++s) {
       if (s < K - LB) {
-        const int gap = pos[s] - next;
+        const int ps = int((pk >> (8 * s)) & 0xff);
+        const int gap = ps - next;
         base |= (rest & ((1u << gap) - 1u)) << next;
         rest >>= gap;
-        next = pos[s] + 1;
+        next = ps + 1;
       }
     }
     base |= rest << next;
   }
   const uint32_t gbase = L.hi_bits | base;
   double2* __restrict__ g = L.states + slot * L.stride + base;
+  // deposit table of the 8 free slots (one entry per thread), after the program block
+  uint32_t* dep = reinterpret_cast<uint32_t*>(pbuf + kBlockBytes / 8);
+  dep[tid] = svx_deposit_hi(uint32_t(tid), pk);
+  __syncthreads();
+  const uint32_t lowmask = (1u << LB) - 1u;
+#define SVX_DEPOSIT(j) (((j) & lowmask) | dep[(j) >> LB])
 
-  const uint32_t off_thr = svx_deposit(uint32_t(tid), LB, pos);
   const uint32_t p_thr = svz(uint32_t(tid));
   if (L.init && sweep_idx == 0) {
     for (uint32_t u0 = 0; u0 < E; u0 += kSvxThreads) {
@@ -113,8 +114,8 @@ __global__ void __launch_bounds__(kSvxThreads, 3) sv_sweep_kernel(const SvxLaunc
       double2 val[4];
 #pragma unroll
       for (int k = 0; k < 4; ++k) {
-        const uint32_t uk = u0 + k * kSvxThreads;
-        if (uk + tid < E) val[k] = __ldcg(g + (off_thr | svx_deposit(uk, LB, pos)));
+        const uint32_t u = u0 + k * kSvxThreads + tid;
+        if (u < E) val[k] = __ldcg(g + SVX_DEPOSIT(u));
       }
 #pragma unroll
       for (int k = 0; k < 4; ++k) {
@@ -137,87 +138,80 @@ __global__ void __launch_bounds__(kSvxThreads, 3) sv_sweep_kernel(const SvxLaunc
     const int lo = min(sa, sb), hi = max(sa, sb);
     const uint32_t ma = 1u << sa, mb = 1u << sb;
     // physical positions of the two slots
-    const int pa = sa < LB ? sa : pos[sa - LB], pb = sb < LB ? sb : pos[sb - LB];
+    const uint32_t pa = sa < LB ? uint32_t(sa) : (uint32_t(pk >> (8 * (sa - LB))) & 0xffu);
+    const uint32_t pb = sb < LB ? uint32_t(sb) : (uint32_t(pk >> (8 * (sb - LB))) & 0xffu);
     const uint2* ops = reinterpret_cast<const uint2*>(pbuf) + ops_q8;
     for (uint32_t grp = tid; grp < (E >> 2); grp += kSvxThreads) {
       uint32_t b0 = (grp & ((1u << lo) - 1u)) | ((grp >> lo) << (lo + 1));
       b0 = (b0 & ((1u << hi) - 1u)) | ((b0 >> hi) << (hi + 1));
       const uint32_t i0 = svz(b0), i1 = svz(b0 | ma), i2 = svz(b0 | mb), i3 = svz(b0 | ma | mb);
       double2 v0 = sv_tile[i0], v1 = sv_tile[i1], v2 = sv_tile[i2], v3 = sv_tile[i3];  // v[ka + 2 kb]
-      const uint32_t gidx0 = needs_index ? (gbase | svx_deposit(b0, LB, pos)) : 0u;
+      const uint32_t gidx0 = needs_index ? (gbase | SVX_DEPOSIT(b0)) : 0u;
       for (int o = 0; o < n_ops; ++o) {
         const uint2 raw = ops[o];
         const uint32_t kind = raw.x & 0xffu, flags = (raw.x >> 8) & 0xffu;
         const uint32_t qa = (raw.x >> 16) & 0xffu, qb = raw.x >> 24;
         const double2* m = reinterpret_cast<const double2*>(pbuf + (raw.y & 0xffffu));
-        const uint32_t cbit = (raw.y >> 16) & 0xffu;
+        if (kind == SVO_D2) {
+          // phase index b_qa + 2 b_qb; gidx0 has zeros at pa and pb, so the slot bits OR in
+          const uint32_t s0 = ((gidx0 >> qa) & 1u) | (((gidx0 >> qb) & 1u) << 1);
+          const uint32_t da = uint32_t(pa == qa) | (uint32_t(pa == qb) << 1);
+          const uint32_t db = uint32_t(pb == qa) | (uint32_t(pb == qb) << 1);
+          v0 = cmul_d(m[s0], v0);
+          v1 = cmul_d(m[s0 | da], v1);
+          v2 = cmul_d(m[s0 | db], v2);
+          v3 = cmul_d(m[s0 | da | db], v3);
+          continue;
+        }
+        if (kind == SVO_D1) {
+          const uint32_t s0 = (gidx0 >> qa) & 1u;
+          const uint32_t da = uint32_t(pa == qa), db = uint32_t(pb == qa);
+          v0 = cmul_d(m[s0], v0);
+          v1 = cmul_d(m[s0 | da], v1);
+          v2 = cmul_d(m[s0 | db], v2);
+          v3 = cmul_d(m[s0 | da | db], v3);
+          continue;
+        }
         const bool on_b = (flags & SVF_ON_B) != 0u;
         // conditional ops: does the pair with the OTHER slot's bit = k qualify?
         bool c0 = true, c1 = true;
         if (flags & SVF_COND) {
+          const uint32_t cbit = (raw.y >> 16) & 0xffu;
           const uint32_t want = (flags & SVF_COND_VAL) ? 1u : 0u;
-          const int po = on_b ? pa : pb;  // position of the non-target slot
+          const uint32_t po = on_b ? pa : pb;  // position of the non-target slot
           c0 = ((gidx0 >> cbit) & 1u) == want;
           c1 = (((gidx0 | (1u << po)) >> cbit) & 1u) == want;
         }
-        switch (kind) {
-          case SVO_U1: {
-            const double2 u00 = m[0], u01 = m[1], u10 = m[2], u11 = m[3];
-            if (!on_b) {
-              if (c0) { const double2 a = v0, b = v1; v0 = cfma_d(u01, b, cmul_d(u00, a)); v1 = cfma_d(u11, b, cmul_d(u10, a)); }
-              if (c1) { const double2 a = v2, b = v3; v2 = cfma_d(u01, b, cmul_d(u00, a)); v3 = cfma_d(u11, b, cmul_d(u10, a)); }
-            } else {
-              if (c0) { const double2 a = v0, b = v2; v0 = cfma_d(u01, b, cmul_d(u00, a)); v2 = cfma_d(u11, b, cmul_d(u10, a)); }
-              if (c1) { const double2 a = v1, b = v3; v1 = cfma_d(u01, b, cmul_d(u00, a)); v3 = cfma_d(u11, b, cmul_d(u10, a)); }
-            }
-            break;
-          }
-          case SVO_X: {
-            if (!on_b) {
-              if (c0) { const double2 a = v0; v0 = v1; v1 = a; }
-              if (c1) { const double2 a = v2; v2 = v3; v3 = a; }
-            } else {
-              if (c0) { const double2 a = v0; v0 = v2; v2 = a; }
-              if (c1) { const double2 a = v1; v1 = v3; v3 = a; }
-            }
-            break;
-          }
-          case SVO_U2: {
-            // matrix index i_first + 2 i_second; on_b: (first, second) = (slot b, slot a)
-            const double2 x0 = v0, x1 = on_b ? v2 : v1, x2 = on_b ? v1 : v2, x3 = v3;
-            double2 y[4];
+        if (kind == SVO_U1) {
+          const double2 u00 = m[0], u01 = m[1], u10 = m[2], u11 = m[3];
+          // pairs along the target slot: (x0,x1) and (y0,y1)
+          double2 x0 = v0, x1 = on_b ? v2 : v1, y0 = on_b ? v1 : v2, y1 = v3;
+          if (c0) { const double2 a = x0, b = x1; x0 = cfma_d(u01, b, cmul_d(u00, a)); x1 = cfma_d(u11, b, cmul_d(u10, a)); }
+          if (c1) { const double2 a = y0, b = y1; y0 = cfma_d(u01, b, cmul_d(u00, a)); y1 = cfma_d(u11, b, cmul_d(u10, a)); }
+          v0 = x0; v3 = y1;
+          if (on_b) { v2 = x1; v1 = y0; } else { v1 = x1; v2 = y0; }
+        } else if (kind == SVO_X) {
+          double2 x0 = v0, x1 = on_b ? v2 : v1, y0 = on_b ? v1 : v2, y1 = v3;
+          if (c0) { const double2 a = x0; x0 = x1; x1 = a; }
+          if (c1) { const double2 a = y0; y0 = y1; y1 = a; }
+          v0 = x0; v3 = y1;
+          if (on_b) { v2 = x1; v1 = y0; } else { v1 = x1; v2 = y0; }
+        } else if (kind == SVO_U2) {
+          // matrix index i_first + 2 i_second; on_b: (first, second) = (slot b, slot a)
+          const double2 x0 = v0, x1 = on_b ? v2 : v1, x2 = on_b ? v1 : v2, x3 = v3;
+          double2 y[4];
 #pragma unroll
-            for (int r = 0; r < 4; ++r) {
-              double2 s = cmul_d(m[4 * r], x0);
-              s = cfma_d(m[4 * r + 1], x1, s);
-              s = cfma_d(m[4 * r + 2], x2, s);
-              s = cfma_d(m[4 * r + 3], x3, s);
-              y[r] = s;
-            }
-            v0 = y[0]; v3 = y[3];
-            if (on_b) { v2 = y[1]; v1 = y[2]; } else { v1 = y[1]; v2 = y[2]; }
-            break;
+          for (int r = 0; r < 4; ++r) {
+            double2 s = cmul_d(m[4 * r], x0);
+            s = cfma_d(m[4 * r + 1], x1, s);
+            s = cfma_d(m[4 * r + 2], x2, s);
+            s = cfma_d(m[4 * r + 3], x3, s);
+            y[r] = s;
           }
-          case SVO_SWAP: { const double2 a = v1; v1 = v2; v2 = a; break; }
-          case SVO_D1: {
-            const double2 ph0 = m[0], ph1 = m[1];
-            const uint32_t ga = 1u << pa, gb = 1u << pb;
-            v0 = cmul_d(((gidx0 >> qa) & 1u) ? ph1 : ph0, v0);
-            v1 = cmul_d((((gidx0 | ga) >> qa) & 1u) ? ph1 : ph0, v1);
-            v2 = cmul_d((((gidx0 | gb) >> qa) & 1u) ? ph1 : ph0, v2);
-            v3 = cmul_d((((gidx0 | ga | gb) >> qa) & 1u) ? ph1 : ph0, v3);
-            break;
-          }
-          case SVO_D2: {
-            const uint32_t ga = 1u << pa, gb = 1u << pb;
-            const uint32_t g1 = gidx0 | ga, g2 = gidx0 | gb, g3 = gidx0 | ga | gb;
-            v0 = cmul_d(m[((gidx0 >> qa) & 1u) | (((gidx0 >> qb) & 1u) << 1)], v0);
-            v1 = cmul_d(m[((g1 >> qa) & 1u) | (((g1 >> qb) & 1u) << 1)], v1);
-            v2 = cmul_d(m[((g2 >> qa) & 1u) | (((g2 >> qb) & 1u) << 1)], v2);
-            v3 = cmul_d(m[((g3 >> qa) & 1u) | (((g3 >> qb) & 1u) << 1)], v3);
-            break;
-          }
-          default: break;
+          v0 = y[0]; v3 = y[3];
+          if (on_b) { v2 = y[1]; v1 = y[2]; } else { v1 = y[1]; v2 = y[2]; }
+        } else if (kind == SVO_SWAP) {
+          const double2 a = v1; v1 = v2; v2 = a;
         }
       }
       sv_tile[i0] = v0; sv_tile[i1] = v1; sv_tile[i2] = v2; sv_tile[i3] = v3;
@@ -226,8 +220,10 @@ __global__ void __launch_bounds__(kSvxThreads, 3) sv_sweep_kernel(const SvxLaunc
   __syncthreads();
 
   for (uint32_t u0 = 0; u0 < E; u0 += kSvxThreads) {
-    if (u0 + tid < E) g[off_thr | svx_deposit(u0, LB, pos)] = sv_tile[p_thr ^ svz(u0)];
+    const uint32_t u = u0 + tid;
+    if (u < E) g[SVX_DEPOSIT(u)] = sv_tile[p_thr ^ svz(u0)];
   }
+#undef SVX_DEPOSIT
 }
 
 // |0...0> for circuits whose first stage has no sweep (slot list)

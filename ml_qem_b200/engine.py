@@ -70,7 +70,7 @@ def load_library(path=None):
     global _lib
     if _lib is not None and path is None:
         return _lib
-    p = path or _LIB_PATH
+    p = path or os.environ.get("BWQ_LIB") or _LIB_PATH  # BWQ_LIB: alternative build (kernel experiments)
     if not os.path.exists(p):
         raise EngineError(f"{p} not found: build it with `python -m ml_qem_b200.build` (needs nvcc); "
                           "this engine has no CPU fallback")

@@ -43,7 +43,7 @@ def test_dm_tfim_chain_vs_oracle(engine_gpu, n):
     obs = [F.tfim_observables(list(range(n)), n) for _ in circs]
     ref = np.concatenate([helpers.oracle_dm_values(c, o, on) for c, o in zip(circs, obs)])
     engine_gpu.set_noise(nm)
-    for kq in (6, 7, 4):
+    for kq in (6, 7, 5, 4):
         engine_gpu.set_options(tile_qubits=kq)
         vals, status = engine_gpu.run_dm(engine.encode_batch(circs, obs))
         assert not status.any()

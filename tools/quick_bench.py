@@ -6,7 +6,7 @@ eng=engine.Engine(0)
 be=backends.synthetic_chain(16, seed=2); nm=noise.from_backend(be); eng.set_noise(nm)
 tw,base,obs=F.config_brick10_twirl(n_base=4,n_twirls=50)
 b=engine.encode_batch(tw,[obs]*len(tw))
-for kq,low,chunk in ((6,2,0),(6,1,0),(7,2,0),(6,2,8),(6,2,32)):
+for kq,low,chunk in ((6,2,0),(6,1,0),(7,2,0),(5,2,0)):
     eng.set_options(tile_qubits=kq,low_qubits=low,chunk_circuits=chunk)
     for _ in range(3):
         t=time.time(); v,s=eng.run_dm(b); dt=time.time()-t
@@ -17,7 +17,7 @@ for n in (12,13):
     be=backends.synthetic_chain(n, seed=n); eng.set_noise(noise.from_backend(be))
     circs,obs=F.config_tfim_dm(n=n,n_circuits=4,max_steps=4)
     b=engine.encode_batch(circs,[obs]*len(circs))
-    for kq,low in ((6,2),(6,1),(7,2),(7,1)):
+    for kq,low in ((6,2),(6,1),(7,2),(5,2)):
         eng.set_options(tile_qubits=kq,low_qubits=low)
         for _ in range(2):
             t=time.time(); v,s=eng.run_dm(b); dt=time.time()-t
