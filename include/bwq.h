@@ -206,7 +206,8 @@ int bwq_svx_upload(bwq_ctx* ctx, bwq_svx_program* p);
  * SWEEPS segments update the shard in place (the first sweep of the program initialises
  * |0...0>); EXPVAL segments add this shard's contribution into d_obs[n_observables] (device);
  * EXCHANGE segments are the caller's job and are rejected here.  Work is enqueued on `stream`
- * (a cudaStream_t, 0 = the ctx's own stream) and not synchronised. */
+ * (a cudaStream_t; 0 = the ctx's own non-blocking stream, (void*)1 = cudaStreamLegacy, i.e. the
+ * default stream torch uses) and not synchronised. */
 int bwq_svx_run_segment(bwq_ctx* ctx, const bwq_svx_program* p, int32_t segment, double* d_state,
                         int32_t rank, double* d_obs, void* stream);
 

@@ -37,7 +37,10 @@ class GpuExecutor:
     def run_segment(self, program, seg, state, rank, obs):
         import torch
 
-        stream = torch.cuda.current_stream(self.device).cuda_stream
+        # run on torch's current stream so the segments are ordered with the NCCL exchange; the
+        # C ABI reads 0 as "the engine's own stream", so torch's default stream (handle 0) is
+        # passed as cudaStreamLegacy (0x1)
+        stream = torch.cuda.current_stream(self.device).cuda_stream or 1
         program.run_segment(self.engine, seg, state.data_ptr(), rank, obs.data_ptr(), stream)
 
 

@@ -220,3 +220,43 @@ def test_sharded_statevector_two_gpus(lib):
                             "--master-addr", "127.0.0.1", "--master-port", str(29500 + world),
                             os.path.join(root, "tests", "svx_multi_gpu.py"), "--check"], capture_output=True, text=True, timeout=600)
         assert r.returncode == 0, r.stdout[-2000:] + r.stderr[-2000:]
+
+
+@pytest.mark.parametrize("g", [1, 2, 3])
+def test_svx_simulated_ranks_on_one_gpu(engine_gpu, g):
+    """The amplitude-sharded program with all 2^g shards on ONE GPU: every local segment goes
+    through the C ABI with its rank, the EXCHANGE is done with tensor copies (what
+    all_to_all_single does between GPUs)."""
+    import torch
+    n = 15
+    rng = np.random.default_rng(70 + g)
+    cases = [(F.tfim_circuit(n, 3, 0.45, basis="Y"), F.tfim_observables(list(range(n)), n)),
+             (F.random_basis_circuit(n, 200, rng, _chain(n)),
+              [[("XYZ" * 5, 0.7), ("Z" * n, 1.0)], [("IIIIXIIIIIIIIII", 1.0)], [("Y" * n, 1.0)]])]
+    G = 1 << g
+    dev = torch.device("cuda", 0)
+    for circ, obs in cases:
+        prog = engine.SvxProgram(engine.encode_batch([circ], [obs]), 0, 0, g)
+        info = prog.info
+        assert info["status"] == 0 and info["n_exchanges"] >= 1
+        prog.upload(engine_gpu)
+        nl = info["n_local"]
+        shards = [torch.empty(1 << nl, dtype=torch.complex128, device=dev) for _ in range(G)]
+        vals = torch.zeros(info["n_observables"], dtype=torch.float64, device=dev)
+        blk = 1 << (nl - g)
+        for seg, (kind, first, count, _) in enumerate(info["segs"]):
+            if kind == engine.SEG_EXCHANGE:
+                torch.cuda.synchronize()
+                new = [torch.empty_like(s) for s in shards]
+                for s in range(G):
+                    for v in range(G):
+                        new[v][s * blk:(s + 1) * blk] = shards[s][v * blk:(v + 1) * blk]
+                shards = new
+                torch.cuda.synchronize()
+            else:
+                for r in range(G):
+                    prog.run_segment(engine_gpu, seg, shards[r].data_ptr(), r, vals.data_ptr())
+                engine_gpu.sync()
+        ref = helpers.oracle_sv_values(circ, obs)
+        assert np.max(np.abs(vals.cpu().numpy() - ref)) <= TOL
+        prog.close()
