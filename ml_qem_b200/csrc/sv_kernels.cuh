@@ -55,6 +55,128 @@ __device__ __forceinline__ uint32_t svx_deposit_hi(uint32_t up, uint64_t pk) {
   return off;
 }
 
+// 2x2 (or X) on the target slot; pairs along it: indices (0,1),(2,3) for slot a, (0,2),(1,3) for b
+template <int NG, bool ON_B, bool COND>
+__device__ __forceinline__ void sv_op_1q(double2 (&v)[NG][4], const double2* __restrict__ m, const bool isx,
+                                         const uint32_t (&gidx0)[NG], const uint32_t cbit, const uint32_t want,
+                                         const uint32_t po) {
+  constexpr int P0 = 0, P1 = ON_B ? 2 : 1, Q0 = ON_B ? 1 : 2, Q1 = 3;
+  if (isx) {
+#pragma unroll
+    for (int k = 0; k < NG; ++k) {
+      if (!COND || ((gidx0[k] >> cbit) & 1u) == want) { const double2 a = v[k][P0]; v[k][P0] = v[k][P1]; v[k][P1] = a; }
+      if (!COND || (((gidx0[k] | po) >> cbit) & 1u) == want) { const double2 a = v[k][Q0]; v[k][Q0] = v[k][Q1]; v[k][Q1] = a; }
+    }
+    return;
+  }
+  const double2 u00 = m[0], u01 = m[1], u10 = m[2], u11 = m[3];
+#pragma unroll
+  for (int k = 0; k < NG; ++k) {
+    if (!COND || ((gidx0[k] >> cbit) & 1u) == want) {
+      const double2 a = v[k][P0], b = v[k][P1];
+      v[k][P0] = cfma_d(u01, b, cmul_d(u00, a));
+      v[k][P1] = cfma_d(u11, b, cmul_d(u10, a));
+    }
+    if (!COND || (((gidx0[k] | po) >> cbit) & 1u) == want) {
+      const double2 a = v[k][Q0], b = v[k][Q1];
+      v[k][Q0] = cfma_d(u01, b, cmul_d(u00, a));
+      v[k][Q1] = cfma_d(u11, b, cmul_d(u10, a));
+    }
+  }
+}
+
+// 4x4, matrix index i_first + 2 i_second; ON_B: (first, second) = (slot b, slot a)
+template <int NG, bool ON_B>
+__device__ __forceinline__ void sv_op_u2(double2 (&v)[NG][4], const double2* __restrict__ m) {
+  constexpr int I1 = ON_B ? 2 : 1, I2 = ON_B ? 1 : 2;
+  double2 y[NG][4];
+#pragma unroll
+  for (int r = 0; r < 4; ++r) {
+    const double2 m0 = m[4 * r], m1 = m[4 * r + 1], m2 = m[4 * r + 2], m3 = m[4 * r + 3];
+#pragma unroll
+    for (int k = 0; k < NG; ++k) {
+      double2 s = cmul_d(m0, v[k][0]);
+      s = cfma_d(m1, v[k][I1], s);
+      s = cfma_d(m2, v[k][I2], s);
+      y[k][r] = cfma_d(m3, v[k][3], s);
+    }
+  }
+#pragma unroll
+  for (int k = 0; k < NG; ++k) { v[k][0] = y[k][0]; v[k][I1] = y[k][1]; v[k][I2] = y[k][2]; v[k][3] = y[k][3]; }
+}
+
+// One register pass on NG groups per thread (groups grp0 + k * kSvxThreads).  Every thread keeps
+// the 4 amplitudes v[k][ka + 2 kb] of its groups in registers and walks the op list once, so the
+// op decode and the (uniform) parameter loads are shared by the NG groups.
+template <int NG>
+__device__ __forceinline__ void sv_run_pass(double2* __restrict__ tile, const double* __restrict__ pbuf,
+                                            const uint32_t* __restrict__ dep, const uint2* __restrict__ ops, const int n_ops,
+                                            const uint32_t grp0, const uint32_t n_grp, const int lo, const int hi,
+                                            const uint32_t ma, const uint32_t mb, const uint32_t pa, const uint32_t pb,
+                                            const uint32_t gbase, const int LB, const bool needs_index) {
+  uint32_t idx[NG][4], gidx0[NG];
+  double2 v[NG][4];
+  const uint32_t lowmask = (1u << LB) - 1u;
+#pragma unroll
+  for (int k = 0; k < NG; ++k) {
+    const uint32_t grp = min(grp0 + k * kSvxThreads, n_grp - 1u);
+    uint32_t b0 = (grp & ((1u << lo) - 1u)) | ((grp >> lo) << (lo + 1));
+    b0 = (b0 & ((1u << hi) - 1u)) | ((b0 >> hi) << (hi + 1));
+    idx[k][0] = svz(b0); idx[k][1] = svz(b0 | ma); idx[k][2] = svz(b0 | mb); idx[k][3] = svz(b0 | ma | mb);
+    gidx0[k] = needs_index ? (gbase | (b0 & lowmask) | dep[b0 >> LB]) : 0u;
+#pragma unroll
+    for (int c = 0; c < 4; ++c) v[k][c] = tile[idx[k][c]];
+  }
+  for (int o = 0; o < n_ops; ++o) {
+    const uint2 raw = ops[o];
+    const uint32_t kind = raw.x & 0xffu, flags = (raw.x >> 8) & 0xffu;
+    const uint32_t qa = (raw.x >> 16) & 0xffu, qb = raw.x >> 24;
+    const double2* m = reinterpret_cast<const double2*>(pbuf + (raw.y & 0xffffu));
+    if (kind == SVO_D2 || kind == SVO_D1) {
+      // phase index b_qa (+ 2 b_qb); gidx0 has zeros at pa and pb, so the slot bits OR in
+      const bool two = kind == SVO_D2;
+      const uint32_t da = uint32_t(pa == qa) | (two ? (uint32_t(pa == qb) << 1) : 0u);
+      const uint32_t db = uint32_t(pb == qa) | (two ? (uint32_t(pb == qb) << 1) : 0u);
+#pragma unroll
+      for (int k = 0; k < NG; ++k) {
+        const uint32_t s0 = ((gidx0[k] >> qa) & 1u) | (two ? (((gidx0[k] >> qb) & 1u) << 1) : 0u);
+        v[k][0] = cmul_d(m[s0], v[k][0]);
+        v[k][1] = cmul_d(m[s0 | da], v[k][1]);
+        v[k][2] = cmul_d(m[s0 | db], v[k][2]);
+        v[k][3] = cmul_d(m[s0 | da | db], v[k][3]);
+      }
+      continue;
+    }
+    const bool on_b = (flags & SVF_ON_B) != 0u;
+    const uint32_t cbit = (raw.y >> 16) & 0xffu;
+    const uint32_t want = (flags & SVF_COND_VAL) ? 1u : 0u;
+    const uint32_t po = 1u << (on_b ? pa : pb);  // bit of the non-target slot
+    // uniform branches select straight-line variants (no per-element selects)
+    if (kind == SVO_U1 || kind == SVO_X) {
+      const bool isx = kind == SVO_X;
+      if (flags & SVF_COND) {
+        if (on_b) sv_op_1q<NG, true, true>(v, m, isx, gidx0, cbit, want, po);
+        else sv_op_1q<NG, false, true>(v, m, isx, gidx0, cbit, want, po);
+      } else {
+        if (on_b) sv_op_1q<NG, true, false>(v, m, isx, gidx0, cbit, want, po);
+        else sv_op_1q<NG, false, false>(v, m, isx, gidx0, cbit, want, po);
+      }
+    } else if (kind == SVO_U2) {
+      if (on_b) sv_op_u2<NG, true>(v, m);
+      else sv_op_u2<NG, false>(v, m);
+    } else if (kind == SVO_SWAP) {
+#pragma unroll
+      for (int k = 0; k < NG; ++k) { const double2 a = v[k][1]; v[k][1] = v[k][2]; v[k][2] = a; }
+    }
+  }
+#pragma unroll
+  for (int k = 0; k < NG; ++k)
+    if (NG == 1 ? (grp0 < n_grp) : true) {
+#pragma unroll
+      for (int c = 0; c < 4; ++c) tile[idx[k][c]] = v[k][c];
+    }
+}
+
 __global__ void __launch_bounds__(kSvxThreads, 3) sv_sweep_kernel(const SvxLaunch L, const int sweep_idx) {
   extern __shared__ __align__(16) double2 sv_tile[];
   const int tid = threadIdx.x;
@@ -141,81 +263,13 @@ __global__ void __launch_bounds__(kSvxThreads, 3) sv_sweep_kernel(const SvxLaunc
     const uint32_t pa = sa < LB ? uint32_t(sa) : (uint32_t(pk >> (8 * (sa - LB))) & 0xffu);
     const uint32_t pb = sb < LB ? uint32_t(sb) : (uint32_t(pk >> (8 * (sb - LB))) & 0xffu);
     const uint2* ops = reinterpret_cast<const uint2*>(pbuf) + ops_q8;
-    for (uint32_t grp = tid; grp < (E >> 2); grp += kSvxThreads) {
-      uint32_t b0 = (grp & ((1u << lo) - 1u)) | ((grp >> lo) << (lo + 1));
-      b0 = (b0 & ((1u << hi) - 1u)) | ((b0 >> hi) << (hi + 1));
-      const uint32_t i0 = svz(b0), i1 = svz(b0 | ma), i2 = svz(b0 | mb), i3 = svz(b0 | ma | mb);
-      double2 v0 = sv_tile[i0], v1 = sv_tile[i1], v2 = sv_tile[i2], v3 = sv_tile[i3];  // v[ka + 2 kb]
-      const uint32_t gidx0 = needs_index ? (gbase | SVX_DEPOSIT(b0)) : 0u;
-      for (int o = 0; o < n_ops; ++o) {
-        const uint2 raw = ops[o];
-        const uint32_t kind = raw.x & 0xffu, flags = (raw.x >> 8) & 0xffu;
-        const uint32_t qa = (raw.x >> 16) & 0xffu, qb = raw.x >> 24;
-        const double2* m = reinterpret_cast<const double2*>(pbuf + (raw.y & 0xffffu));
-        if (kind == SVO_D2) {
-          // phase index b_qa + 2 b_qb; gidx0 has zeros at pa and pb, so the slot bits OR in
-          const uint32_t s0 = ((gidx0 >> qa) & 1u) | (((gidx0 >> qb) & 1u) << 1);
-          const uint32_t da = uint32_t(pa == qa) | (uint32_t(pa == qb) << 1);
-          const uint32_t db = uint32_t(pb == qa) | (uint32_t(pb == qb) << 1);
-          v0 = cmul_d(m[s0], v0);
-          v1 = cmul_d(m[s0 | da], v1);
-          v2 = cmul_d(m[s0 | db], v2);
-          v3 = cmul_d(m[s0 | da | db], v3);
-          continue;
-        }
-        if (kind == SVO_D1) {
-          const uint32_t s0 = (gidx0 >> qa) & 1u;
-          const uint32_t da = uint32_t(pa == qa), db = uint32_t(pb == qa);
-          v0 = cmul_d(m[s0], v0);
-          v1 = cmul_d(m[s0 | da], v1);
-          v2 = cmul_d(m[s0 | db], v2);
-          v3 = cmul_d(m[s0 | da | db], v3);
-          continue;
-        }
-        const bool on_b = (flags & SVF_ON_B) != 0u;
-        // conditional ops: does the pair with the OTHER slot's bit = k qualify?
-        bool c0 = true, c1 = true;
-        if (flags & SVF_COND) {
-          const uint32_t cbit = (raw.y >> 16) & 0xffu;
-          const uint32_t want = (flags & SVF_COND_VAL) ? 1u : 0u;
-          const uint32_t po = on_b ? pa : pb;  // position of the non-target slot
-          c0 = ((gidx0 >> cbit) & 1u) == want;
-          c1 = (((gidx0 | (1u << po)) >> cbit) & 1u) == want;
-        }
-        if (kind == SVO_U1) {
-          const double2 u00 = m[0], u01 = m[1], u10 = m[2], u11 = m[3];
-          // pairs along the target slot: (x0,x1) and (y0,y1)
-          double2 x0 = v0, x1 = on_b ? v2 : v1, y0 = on_b ? v1 : v2, y1 = v3;
-          if (c0) { const double2 a = x0, b = x1; x0 = cfma_d(u01, b, cmul_d(u00, a)); x1 = cfma_d(u11, b, cmul_d(u10, a)); }
-          if (c1) { const double2 a = y0, b = y1; y0 = cfma_d(u01, b, cmul_d(u00, a)); y1 = cfma_d(u11, b, cmul_d(u10, a)); }
-          v0 = x0; v3 = y1;
-          if (on_b) { v2 = x1; v1 = y0; } else { v1 = x1; v2 = y0; }
-        } else if (kind == SVO_X) {
-          double2 x0 = v0, x1 = on_b ? v2 : v1, y0 = on_b ? v1 : v2, y1 = v3;
-          if (c0) { const double2 a = x0; x0 = x1; x1 = a; }
-          if (c1) { const double2 a = y0; y0 = y1; y1 = a; }
-          v0 = x0; v3 = y1;
-          if (on_b) { v2 = x1; v1 = y0; } else { v1 = x1; v2 = y0; }
-        } else if (kind == SVO_U2) {
-          // matrix index i_first + 2 i_second; on_b: (first, second) = (slot b, slot a)
-          const double2 x0 = v0, x1 = on_b ? v2 : v1, x2 = on_b ? v1 : v2, x3 = v3;
-          double2 y[4];
-#pragma unroll
-          for (int r = 0; r < 4; ++r) {
-            double2 s = cmul_d(m[4 * r], x0);
-            s = cfma_d(m[4 * r + 1], x1, s);
-            s = cfma_d(m[4 * r + 2], x2, s);
-            s = cfma_d(m[4 * r + 3], x3, s);
-            y[r] = s;
-          }
-          v0 = y[0]; v3 = y[3];
-          if (on_b) { v2 = y[1]; v1 = y[2]; } else { v1 = y[1]; v2 = y[2]; }
-        } else if (kind == SVO_SWAP) {
-          const double2 a = v1; v1 = v2; v2 = a;
-        }
-      }
-      sv_tile[i0] = v0; sv_tile[i1] = v1; sv_tile[i2] = v2; sv_tile[i3] = v3;
-    }
+    const uint32_t n_grp = E >> 2;
+    if (n_grp % (2u * kSvxThreads) == 0u)
+      for (uint32_t g0 = 0; g0 < n_grp; g0 += 2u * kSvxThreads)
+        sv_run_pass<2>(sv_tile, pbuf, dep, ops, n_ops, tid + g0, n_grp, lo, hi, ma, mb, pa, pb, gbase, LB, needs_index);
+    else
+      for (uint32_t g0 = 0; g0 < n_grp; g0 += kSvxThreads)
+        sv_run_pass<1>(sv_tile, pbuf, dep, ops, n_ops, tid + g0, n_grp, lo, hi, ma, mb, pa, pb, gbase, LB, needs_index);
   }
   __syncthreads();
 

@@ -194,22 +194,37 @@ class B200Estimator:
             groups[keys[key]].append(i)
         batch = encode_batch(bound, [[observables[i] for i in g] for g in groups])
         eng = self._engine_handle()
-        if self._noise is not None and not self._noise.is_ideal():
+        noisy = self._noise is not None and not self._noise.is_ideal()
+        method = "density_matrix" if noisy else "statevector"
+        if noisy:
             eng.set_noise(self._noise)
-            vals, status = eng.run_dm(batch)
-            method = "density_matrix"
-        else:
-            vals, status = eng.run_sv(batch)
-            method = "statevector"
-        bad = np.nonzero(status)[0]
-        if len(bad):
-            c = int(bad[0])
-            raise ValueError(f"circuit {groups[c][0]}: {STATUS_TEXT.get(int(status[c]), 'error')}")
-        out = np.empty(len(circuits), dtype=float)
-        k = 0
-        for g in groups:
-            for i in g:
-                out[i] = vals[k]
-                k += 1
+
+        def evaluate(b):
+            vals, status = eng.run_dm(b) if noisy else eng.run_sv(b)
+            bad = np.nonzero(status)[0]
+            if len(bad):
+                c = int(bad[0])
+                raise ValueError(f"circuit {groups[c][0]}: {STATUS_TEXT.get(int(status[c]), 'error')}")
+            out = np.empty(len(circuits), dtype=float)
+            k = 0
+            for g in groups:
+                for i in g:
+                    out[i] = vals[k]
+                    k += 1
+            return out
+
         meta = [{"simulator_metadata": {"method": method, "device": f"cuda:{self._device}"}} for _ in circuits]
+        strategy = run_options.get("zne_strategy")
+        if strategy is None:
+            return EstimatorResult(np.real_if_close(evaluate(batch)), meta)
+        # digital ZNE (docs/tutorials/zne_parallel.py:168-189): every noise factor is the same
+        # encoded batch with its 2-qubit gates folded on the flat gate stream
+        from . import zne as zne_mod
+
+        factors = tuple(int(f) for f in strategy.noise_factors)
+        vals = np.stack([evaluate(zne_mod.fold_batch(batch, f)) for f in factors], axis=-1)
+        out = strategy.extrapolator(vals, factors)
+        for m, v in zip(meta, vals):
+            m["zne"] = {"noise_amplification": {"noise_factors": factors, "values": tuple(float(x) for x in v)},
+                        "extrapolation": {"degree": getattr(strategy.extrapolator, "degree", None)}}
         return EstimatorResult(np.real_if_close(out), meta)

@@ -60,7 +60,9 @@ class ShardedStatevector:
         self.n_global = self.world.bit_length() - 1
         self.last_plan = None
 
-    def estimate(self, circuit, observables, tile_bits=0):
+    def estimate(self, circuit, observables, tile_bits=0, profile=False):
+        """profile=True additionally records CUDA-event times per segment kind in ``last_plan``
+        (GPU executor only; adds a synchronisation at the end)."""
         import torch
 
         batch = encode_batch([circuit], [observables])
@@ -76,21 +78,41 @@ class ShardedStatevector:
         obs = torch.zeros(max(1, info["n_observables"]), dtype=torch.float64, device=dev)
         self.ex.init_state(state, self.rank)
         exchanged_bytes = 0
+        profile = profile and dev != "cpu"
+        marks = []
+
+        def mark(kind):
+            if profile:
+                ev = torch.cuda.Event(enable_timing=True)
+                ev.record()
+                marks.append((kind, ev))
+
+        mark("begin")
         for seg, (kind, first, count, _) in enumerate(info["segs"]):
             if kind == SEG_EXCHANGE:
                 # block v of rank s <-> block s of rank v: top g local bits swap with the rank bits
                 self.dist.all_to_all_single(spare, state)
                 state, spare = spare, state
                 exchanged_bytes += state.numel() * 16 * (self.world - 1) // self.world
+                mark("exchange")
             elif kind in (SEG_SWEEPS, SEG_EXPVAL):
                 self.ex.run_segment(prog, seg, state, self.rank, obs)
+                mark("sweeps" if kind == SEG_SWEEPS else "expval")
         if self.dist:
             self.dist.all_reduce(obs)
+            mark("allreduce")
         self.last_plan = {"n_bits": info["n_bits"], "n_local": info["n_local"], "n_sweeps": len(info["sweeps"]),
                           "n_passes": info["n_passes"], "n_exchanges": info["n_exchanges"],
                           "exchanged_bytes_per_rank": exchanged_bytes,
                           "n_expval_passes": int(sum(-(-int(c) // 32) for k, _, c, _ in info["segs"] if k == SEG_EXPVAL))}
         vals = obs[:info["n_observables"]].cpu().numpy()
+        if profile:
+            torch.cuda.synchronize()
+            ms = {}
+            for (_, e0), (kind, e1) in zip(marks[:-1], marks[1:]):
+                ms[kind] = ms.get(kind, 0.0) + e0.elapsed_time(e1)
+            self.last_plan["ms"] = ms
+            self.last_plan["ms_total"] = marks[0][1].elapsed_time(marks[-1][1])
         if dev != "cpu":
             prog.close()
         return vals
