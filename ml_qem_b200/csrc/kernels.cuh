@@ -317,7 +317,7 @@ __device__ __forceinline__ void run_passes(double* __restrict__ tile, const doub
 template <int KQ, bool FULL>
 __global__ void __launch_bounds__(SweepCfg<KQ>::kThreads, FULL ? 1 : SweepCfg<KQ>::kMinBlocks)
 dm_sweep_kernel(const DmLaunch L, const int sweep_idx) {
-  constexpr int E = SweepCfg<KQ>::kElems, G = SweepCfg<KQ>::kGroups, T = SweepCfg<KQ>::kThreads, NG = SweepCfg<KQ>::kNG;
+  constexpr int E = SweepCfg<KQ>::kElems, T = SweepCfg<KQ>::kThreads;
   constexpr int U = E / 2;                       // double2 units per tile
   constexpr int NIT = (U + T - 1) / T;           // load/store iterations per thread
   // KQ <= 6: static shared memory, so the tile base is a compile-time constant and the pass
