@@ -302,7 +302,9 @@ def main():
     batch = engine.encode_batch(wl["circuits"], wl["observables"])
     n_circ = batch.n_circuits
     eng = engine.Engine(local_rank)
-    eng.set_options(tile_qubits=args.tile_qubits, low_qubits=args.low_qubits, chunk_circuits=args.chunk_circuits)
+    # lowering threads: the ranks of one box share its host cores
+    eng.set_options(tile_qubits=args.tile_qubits, low_qubits=args.low_qubits, chunk_circuits=args.chunk_circuits,
+                    host_threads=max(1, (os.cpu_count() or 8) // world) if world > 1 else 0)
     eng.set_noise(noise.from_backend(wl["backend"]))
 
     def barrier():
