@@ -122,7 +122,8 @@ typedef struct {
   int64_t n_state_sweeps;      /* (circuit, sweep) pairs executed = P of SURVEY 8(d)     */
   int64_t n_passes;            /* register passes (2-qubit groups) executed              */
   int64_t n_gates;             /* gates consumed from the stream                         */
-  int64_t state_bytes_swept;   /* sum over state sweeps of 2 * 8 B * 4^n_active          */
+  int64_t state_bytes_swept;   /* sum over state sweeps of 2 * 8 B * 4^n_active (the first
+                                  sweep of a circuit only writes: 1 * 8 B * 4^n)           */
   int64_t n_other_launches;    /* init / expectation / statevector launches              */
   double lower_ms, h2d_ms, kernel_ms, d2h_ms; /* host wall / device-event times          */
   double sweep_kernel_ms;      /* CUDA-event time of the sweep launches only             */

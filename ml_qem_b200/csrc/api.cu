@@ -78,6 +78,7 @@ struct DmChunk {
   int first = 0, count = 0, nd = 0, kq = 0;
   bool full = false;
   std::vector<int> live;  // circuits that still have a sweep s, per sweep index
+  std::vector<int64_t> bytes;  // algorithmic bytes of launch s: tiles that are not provably zero
 };
 struct DmPlan {
   bool valid = false;
@@ -449,6 +450,19 @@ static int dm_prepare_impl(bwq_ctx* ctx, const bwq_batch* b, int32_t* out_status
       ch.live.push_back(live);
     }
     for (int k = i; k < j; ++k) ch.full = ch.full || progs[order[k]].needs_dense;
+    // bytes per launch: a tile with X/Y on an outside digit no pass has touched yet is all zero
+    // (kernels.cuh): the first sweep stores it (8 B/element, no read), later sweeps skip it
+    ch.bytes.assign(max_sweeps, 0);
+    for (int k = i; k < j; ++k) {
+      const CircuitProgram& p = progs[order[k]];
+      for (size_t sidx = 0; sidx < p.sweeps.size(); ++sidx) {
+        uint32_t outside = (nd >= 32 ? ~0u : ((1u << nd) - 1u));
+        for (int s2 = 0; s2 < kq; ++s2) outside &= ~(1u << p.sweeps[sidx].pos[s2]);
+        const int u = __builtin_popcount(outside & (p.sweeps[sidx].blk_len_q16 >> 16));
+        const int64_t full = (int64_t)sizeof(double) << (2 * nd);
+        ch.bytes[sidx] += sidx == 0 ? full + (full >> u) * 0 : 2 * (full >> u);
+      }
+    }
     P.chunks.push_back(std::move(ch));
     i = j;
   }
@@ -530,7 +544,7 @@ static int dm_execute_impl(bwq_ctx* ctx, double* out_vals, bool out_on_device) {
                  : launch_sweep_kq<false>(ch.kq, L, (int)sidx, tiles * live, st));
       S.n_sweep_launches++;
       S.n_state_sweeps += live;
-      S.state_bytes_swept += 2 * (int64_t)sizeof(double) * L.stride * live;
+      S.state_bytes_swept += ch.bytes[sidx];
     }
     if (ci < n_ev) CK(cudaEventRecord(ctx->chunk_ev[2 * ci + 1], st));
     const int64_t nob = P.ob_off[ch.first + ch.count] - P.ob_off[ch.first];
@@ -780,7 +794,7 @@ static int sv_wide_execute(bwq_ctx* ctx, double* d_out) {
       for (int sidx = 0; sidx < sg.max_sweeps; ++sidx) {
         CK(launch_sv_sweep(L, sidx, tiles * ch.count, st));
         S.n_other_launches++;
-        S.sv_state_bytes_swept += 2 * (int64_t)sizeof(double2) * L.stride * ch.count;
+        S.sv_state_bytes_swept += ((f == 0 && sidx == 0) ? 1 : 2) * (int64_t)sizeof(double2) * L.stride * ch.count;
       }
       if (sg.n_groups > 0) {
         ZexpLaunch Z;
@@ -1037,7 +1051,7 @@ extern "C" int bwq_program_read(const bwq_program* p, int32_t* active, int32_t* 
       int32_t* s = sweeps + 10 * i;
       s[0] = (int32_t)q.sweeps[i].blk_q16;
       for (int k = 0; k < 8; ++k) s[1 + k] = q.sweeps[i].pos[k];
-      s[9] = (int32_t)q.sweeps[i].blk_len_q16;
+      s[9] = (int32_t)(q.sweeps[i].blk_len_q16 & 0xffffu);
     }
   if (prog && !q.prog.empty()) std::memcpy(prog, q.prog.data(), q.prog.size() * sizeof(uint64_t));
   if (term_index && !q.term_index.empty()) std::memcpy(term_index, q.term_index.data(), q.term_index.size() * sizeof(int64_t));

@@ -488,6 +488,7 @@ void lower_dm_circuit(const NoiseTable& noise, const bwq_batch& b, int c, const 
   out->n_passes = np;
   std::vector<char> done(np, 0);
   int first = 0, remaining = np;
+  uint32_t touched_mask = 0;  // digits acted on so far (the others still hold |0><0|: I/Z only)
   std::vector<char> in_tile(nd), blocked(nd);
   std::vector<int> sel;
   std::vector<Seen> seen;
@@ -570,7 +571,8 @@ void lower_dm_circuit(const NoiseTable& noise, const bwq_batch& b, int c, const 
     }
     if (par_cursor * 8 != (size_t)bytes) { out->status = BWQ_CIRC_BAD_OP; return; }  // accounting bug guard
     sw.blk_q16 = (uint32_t)(blk_begin / 2);
-    sw.blk_len_q16 = (uint32_t)(bytes / 16);
+    for (int i : sel) { touched_mask |= 1u << passes[i].qa; touched_mask |= 1u << passes[i].qb; }
+    sw.blk_len_q16 = (uint32_t)(bytes / 16) | ((~touched_mask & ((1u << nd) - 1u)) << 16);
     out->sweeps.push_back(sw);
   }
 }

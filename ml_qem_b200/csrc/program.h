@@ -63,7 +63,9 @@ struct BlockOp {    // 16 B
 };
 struct SweepDesc {  // 16 B
   uint32_t blk_q16;     // block offset in 16-byte units from the program buffer base
-  uint32_t blk_len_q16; // block length in 16-byte units
+  uint32_t blk_len_q16; // low 16 bits: block length in 16-byte units; high 16 bits (density
+                        // matrix only): digit positions no pass has touched up to and including
+                        // this sweep -- a tile with X or Y on such an outside digit is all zero
   uint8_t pos[8];       // digit positions resident in the tile, ascending; first n_tile valid
 };
 constexpr int kBlockBytes = 8192;  // shared-memory program buffer per CTA
