@@ -195,7 +195,7 @@ def bench_sharded_sv(args, rank, world, local_rank, dist, steps, warmup):
         vals = sv.estimate(c, obs, profile=True)
         pl = sv.last_plan
         dev_ms += pl["ms_total"]; sweep_ms += pl["ms"].get("sweeps", 0.0); exch_ms += pl["ms"].get("exchange", 0.0)
-        swept += 16 * (1 << pl["n_local"]) * (2 * pl["n_sweeps"] - 1)  # the first sweep only writes
+        swept += pl["kernel_bytes"] - 16 * (1 << pl["n_local"]) * pl["n_expval_passes"]  # sweeps only, live tiles
         exch_bytes += pl["exchanged_bytes_per_rank"]
         launches += pl["n_sweeps"] + 2 * pl["n_expval_passes"]
     barrier()

@@ -201,6 +201,10 @@ int bwq_svx_sizes(const bwq_svx_program* p, int64_t sizes[12]);
  * segs: 4 int32 each {kind (0 sweeps, 1 exchange, 2 expval), first, count, 0}. */
 int bwq_svx_read(const bwq_svx_program* p, int32_t* active, int32_t* sweeps, uint64_t* prog, int32_t* segs,
                  uint32_t* zt_mask, double* zt_coeff, int32_t* zt_obs);
+/* Algorithmic bytes this rank's kernels move for the whole program: 2 x 16 B per amplitude of
+ * every live tile of every sweep (the first sweep only writes; tiles that are provably zero are
+ * skipped) + 16 B per amplitude per expectation pass.  For the roofline. */
+int64_t bwq_svx_bytes(const bwq_svx_program* p, int32_t rank);
 /* Uploads the program to ctx's device (kept inside the handle). */
 int bwq_svx_upload(bwq_ctx* ctx, bwq_svx_program* p);
 /* Runs segment `segment` on this rank's shard d_state (2^n_local complex128, device memory).

@@ -111,8 +111,9 @@ struct SvWideChunk {
   int n_init = 0;
 };
 struct SvWidePlan {
-  size_t o_range = 0, o_sweeps = 0, o_prog = 0, o_ztm = 0, o_ztc = 0, o_zto = 0, o_gdesc = 0, o_cdesc = 0, o_init = 0;
+  size_t o_range = 0, o_sweeps = 0, o_unt = 0, o_prog = 0, o_ztm = 0, o_ztc = 0, o_zto = 0, o_gdesc = 0, o_cdesc = 0, o_init = 0;
   size_t blob_bytes = 0;
+  int64_t bytes_per_exec = 0;   // algorithmic bytes of one execute (live tiles only)
   std::vector<SvWideChunk> chunks;
   int64_t max_state_bytes = 0, n_passes = 0;
   bool any = false;
@@ -671,6 +672,19 @@ static int sv_wide_prepare(bwq_ctx* ctx, const bwq_batch* b, const std::vector<i
     zt_off[i + 1] = zt_off[i] + (int64_t)p.zt_mask.size();
     SP.n_gates += p.n_gates;
     W.n_passes += p.n_passes;
+    {  // algorithmic bytes: live tiles only; the first sweep writes every tile and reads none
+      const int K = p.tile_bits, LBk = std::max(0, K - kSvFreeSlots);
+      const int64_t full = (int64_t)sizeof(double2) << p.n_bits;
+      for (size_t k = 0; k < p.sweeps.size(); ++k) {
+        uint32_t outside = p.n_bits >= 32 ? ~0u : ((1u << p.n_bits) - 1u);
+        outside &= ~((1u << LBk) - 1u);
+        for (int s2 = 0; s2 < K - LBk; ++s2) outside &= ~(1u << p.sweeps[k].pos[s2]);
+        const int u = __builtin_popcount(outside & p.sweep_untouched[k]);
+        W.bytes_per_exec += k == 0 ? full : 2 * (full >> u);
+      }
+      for (const SvxSegment& sg : p.segs)
+        if (sg.kind == SVSEG_EXPVAL) W.bytes_per_exec += full * ((sg.count + kZexpTerms - 1) / kZexpTerms);
+    }
   }
   if (sw_off[M] > INT32_MAX || pg_off[M] / 2 >= (int64_t(1) << 32) || zt_off[M] > INT32_MAX)
     return fail(ctx, BWQ_ERR_ARG, "statevector batch too large for 32-bit program indices; split the batch");
@@ -728,6 +742,7 @@ static int sv_wide_prepare(bwq_ctx* ctx, const bwq_batch* b, const std::vector<i
   Blob blob;
   W.o_range = blob.add(sizeof(int32_t) * ranges.size());
   W.o_sweeps = blob.add(sizeof(SweepDesc) * (size_t)sw_off[M]);
+  W.o_unt = blob.add(sizeof(uint32_t) * (size_t)sw_off[M]);
   W.o_prog = blob.add(sizeof(uint64_t) * (size_t)pg_off[M]);
   W.o_ztm = blob.add(sizeof(uint32_t) * (size_t)zt_off[M]);
   W.o_ztc = blob.add(sizeof(double) * (size_t)zt_off[M]);
@@ -747,6 +762,7 @@ static int sv_wide_prepare(bwq_ctx* ctx, const bwq_batch* b, const std::vector<i
     const SvxProgram& p = progs[order[i]];
     SweepDesc* sw = (SweepDesc*)(hb + W.o_sweeps) + sw_off[i];
     for (size_t k = 0; k < p.sweeps.size(); ++k) { sw[k] = p.sweeps[k]; sw[k].blk_q16 += (uint32_t)(pg_off[i] / 2); }
+    if (!p.sweeps.empty()) std::memcpy((uint32_t*)(hb + W.o_unt) + sw_off[i], p.sweep_untouched.data(), p.sweeps.size() * sizeof(uint32_t));
     if (!p.prog.empty()) std::memcpy((uint64_t*)(hb + W.o_prog) + pg_off[i], p.prog.data(), p.prog.size() * sizeof(uint64_t));
     const size_t nt = p.zt_mask.size();
     if (nt) {
@@ -769,6 +785,7 @@ static int sv_wide_prepare(bwq_ctx* ctx, const bwq_batch* b, const std::vector<i
 static int sv_wide_execute(bwq_ctx* ctx, double* d_out) {
   SvWidePlan& W = ctx->sv_plan.wide;
   bwq_stats& S = ctx->stats;
+  S.sv_state_bytes_swept = W.bytes_per_exec;
   cudaStream_t st = ctx->stream;
   const char* db = (const char*)ctx->d_wide_prog.p;
   for (const SvWideChunk& ch : W.chunks) {
@@ -778,6 +795,7 @@ static int sv_wide_execute(bwq_ctx* ctx, double* d_out) {
     L.n_local = ch.nb; L.tile_bits = ch.tile_bits; L.low_bits = ch.low_bits;
     L.first_circuit = 0;
     L.sweeps = (const SweepDesc*)(db + W.o_sweeps);
+    L.sweep_untouched = (const uint32_t*)(db + W.o_unt);
     L.prog = (const uint4*)(db + W.o_prog);
     L.hi_bits = 0;
     if (ch.n_init > 0) {
@@ -794,7 +812,6 @@ static int sv_wide_execute(bwq_ctx* ctx, double* d_out) {
       for (int sidx = 0; sidx < sg.max_sweeps; ++sidx) {
         CK(launch_sv_sweep(L, sidx, tiles * ch.count, st));
         S.n_other_launches++;
-        S.sv_state_bytes_swept += ((f == 0 && sidx == 0) ? 1 : 2) * (int64_t)sizeof(double2) * L.stride * ch.count;
       }
       if (sg.n_groups > 0) {
         ZexpLaunch Z;
@@ -814,7 +831,6 @@ static int sv_wide_execute(bwq_ctx* ctx, double* d_out) {
         sv_zexp_finalize<<<(unsigned)sg.n_cdesc, 128, 0, st>>>(F);
         CK(cudaGetLastError());
         S.n_other_launches += 2;
-        S.sv_state_bytes_swept += (int64_t)sizeof(double2) * L.stride * sg.n_groups;
       }
     }
   }
@@ -1067,7 +1083,7 @@ struct bwq_svx_program {
   int64_t n_obs = 0;
   int device = -1;
   DevBuf d_blob, d_partial;
-  size_t o_sweeps = 0, o_prog = 0, o_ztm = 0, o_ztc = 0, o_zto = 0, o_gdesc = 0, o_cdesc = 0;
+  size_t o_sweeps = 0, o_unt = 0, o_prog = 0, o_ztm = 0, o_ztc = 0, o_zto = 0, o_gdesc = 0, o_cdesc = 0;
   std::vector<int> seg_group_first, seg_n_groups;  // per segment (EXPVAL only)
   bool uploaded = false;
 };
@@ -1124,6 +1140,26 @@ extern "C" int bwq_svx_read(const bwq_svx_program* h, int32_t* active, int32_t* 
   return BWQ_OK;
 }
 
+extern "C" int64_t bwq_svx_bytes(const bwq_svx_program* h, int32_t rank) {
+  if (!h) return -1;
+  const SvxProgram& p = h->p;
+  const int K = p.tile_bits, LBk = std::max(0, K - kSvFreeSlots);
+  const int64_t full = (int64_t)sizeof(double2) << p.n_local;
+  const uint32_t hi = uint32_t(rank) << p.n_local;
+  int64_t bytes = 0;
+  for (size_t k = 0; k < p.sweeps.size(); ++k) {
+    if (k > 0 && (hi & p.sweep_untouched[k])) continue;  // the whole shard is still zero
+    uint32_t outside = (1u << p.n_local) - 1u;
+    outside &= ~((1u << LBk) - 1u);
+    for (int s2 = 0; s2 < K - LBk; ++s2) outside &= ~(1u << p.sweeps[k].pos[s2]);
+    const int u = __builtin_popcount(outside & p.sweep_untouched[k]);
+    bytes += k == 0 ? full : 2 * (full >> u);
+  }
+  for (const SvxSegment& sg : p.segs)
+    if (sg.kind == SVSEG_EXPVAL) bytes += full * ((sg.count + kZexpTerms - 1) / kZexpTerms);
+  return bytes;
+}
+
 extern "C" int bwq_svx_upload(bwq_ctx* ctx, bwq_svx_program* h) {
   if (!ctx || !h) return BWQ_ERR_ARG;
   const SvxProgram& p = h->p;
@@ -1147,6 +1183,7 @@ extern "C" int bwq_svx_upload(bwq_ctx* ctx, bwq_svx_program* h) {
   }
   Blob blob;
   h->o_sweeps = blob.add(sizeof(SweepDesc) * p.sweeps.size());
+  h->o_unt = blob.add(sizeof(uint32_t) * p.sweeps.size());
   h->o_prog = blob.add(sizeof(uint64_t) * p.prog.size());
   h->o_ztm = blob.add(sizeof(uint32_t) * p.zt_mask.size());
   h->o_ztc = blob.add(sizeof(double) * p.zt_coeff.size());
@@ -1156,6 +1193,7 @@ extern "C" int bwq_svx_upload(bwq_ctx* ctx, bwq_svx_program* h) {
   std::vector<char> hb(blob.total + 256, 0);
   auto put = [&](size_t off, const void* src, size_t n) { if (n) std::memcpy(hb.data() + off, src, n); };
   put(h->o_sweeps, p.sweeps.data(), sizeof(SweepDesc) * p.sweeps.size());
+  put(h->o_unt, p.sweep_untouched.data(), sizeof(uint32_t) * p.sweeps.size());
   put(h->o_prog, p.prog.data(), sizeof(uint64_t) * p.prog.size());
   put(h->o_ztm, p.zt_mask.data(), sizeof(uint32_t) * p.zt_mask.size());
   put(h->o_ztc, p.zt_coeff.data(), sizeof(double) * p.zt_coeff.size());
@@ -1196,6 +1234,7 @@ extern "C" int bwq_svx_run_segment(bwq_ctx* ctx, const bwq_svx_program* h, int32
     L.n_local = p.n_local; L.tile_bits = p.tile_bits; L.low_bits = std::max(0, p.tile_bits - kSvFreeSlots);
     L.first_circuit = 0; L.sweep_range = nullptr;
     L.sweeps = (const SweepDesc*)(db + h->o_sweeps);
+    L.sweep_untouched = (const uint32_t*)(db + h->o_unt);
     L.prog = (const uint4*)(db + h->o_prog);
     L.hi_bits = hi; L.init = 1;
     const int64_t tiles = int64_t(1) << (p.n_local - p.tile_bits);

@@ -196,6 +196,7 @@ struct SvxProgram {
   int32_t n_local = 0, n_global = 0, tile_bits = 0;
   std::vector<int32_t> active;     // physical (register) qubit of each logical bit, -1 = padding
   std::vector<SweepDesc> sweeps;
+  std::vector<uint32_t> sweep_untouched;  // per sweep: physical bits no non-diagonal op has touched yet
   std::vector<uint64_t> prog;
   std::vector<SvxSegment> segs;
   std::vector<uint32_t> zt_mask;   // Z-type terms, physical masks under the mapping at that point

@@ -23,6 +23,7 @@ struct SvxLaunch {
   int32_t first_circuit;
   const int32_t* sweep_range;  // per circuit {begin, end} of this stage; nullptr: sweep_idx is absolute
   const SweepDesc* sweeps;
+  const uint32_t* sweep_untouched;  // per sweep: physical bits still |0> (see sv_lowering.cpp)
   const uint4* prog;
   uint32_t hi_bits;            // rank << n_local: the global part of the physical index
   int32_t init;                // sweep_idx == 0 synthesises |0...0> instead of reading
@@ -192,12 +193,8 @@ __global__ void __launch_bounds__(kSvxThreads, 3) sv_sweep_kernel(const SvxLaunc
     if (sw_i >= __ldg(L.sweep_range + 2 * circ + 1)) return;
   }
   const int4 swraw = __ldg(reinterpret_cast<const int4*>(L.sweeps + sw_i));
+  const uint32_t untouched = __ldg(L.sweep_untouched + sw_i);
   double* pbuf = reinterpret_cast<double*>(sv_tile + E);
-  {
-    const uint4* src = L.prog + uint32_t(swraw.x);
-    const int len = swraw.y;
-    for (int i = tid; i < len; i += kSvxThreads) cp_async16(reinterpret_cast<uint4*>(pbuf) + i, src + i);
-  }
   const uint64_t pk = (uint64_t(uint32_t(swraw.w)) << 32) | uint32_t(swraw.z);  // slot positions
   // tile id -> the physical bits that are not resident
   uint32_t base = 0;
@@ -218,15 +215,29 @@ __global__ void __launch_bounds__(kSvxThreads, 3) sv_sweep_kernel(const SvxLaunc
   }
   const uint32_t gbase = L.hi_bits | base;
   double2* __restrict__ g = L.states + slot * L.stride + base;
+  // early-state sparsity: an outside bit set on a qubit that is still |0> means the tile is all
+  // zero and stays zero -- nothing to do, except that the very first sweep has to store the zeros
+  const bool first = L.init && sweep_idx == 0;
+  const bool dead = (gbase & untouched) != 0u;
+  if (dead && !first) return;
   // deposit table of the 8 free slots (one entry per thread), after the program block
   uint32_t* dep = reinterpret_cast<uint32_t*>(pbuf + kBlockBytes / 8);
   dep[tid] = svx_deposit_hi(uint32_t(tid), pk);
   __syncthreads();
   const uint32_t lowmask = (1u << LB) - 1u;
 #define SVX_DEPOSIT(j) (((j) & lowmask) | dep[(j) >> LB])
+  if (dead) {
+    for (uint32_t u = tid; u < E; u += kSvxThreads) __stcg(g + SVX_DEPOSIT(u), make_double2(0.0, 0.0));
+    return;
+  }
+  {
+    const uint4* src = L.prog + uint32_t(swraw.x);
+    const int len = swraw.y;
+    for (int i = tid; i < len; i += kSvxThreads) cp_async16(reinterpret_cast<uint4*>(pbuf) + i, src + i);
+  }
 
   const uint32_t p_thr = svz(uint32_t(tid));
-  if (L.init && sweep_idx == 0) {
+  if (first) {
     for (uint32_t u0 = 0; u0 < E; u0 += kSvxThreads) {
       const uint32_t u = u0 + tid;
       if (u < E) sv_tile[p_thr ^ svz(u0)] = make_double2((gbase == 0u && u == 0u) ? 1.0 : 0.0, 0.0);

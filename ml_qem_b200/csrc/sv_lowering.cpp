@@ -50,6 +50,7 @@ struct Planner {
   SvxProgram* out;
   int n = 0, nl = 0, g = 0, K = 0, L = 0;
   std::vector<int> phys, logical_at;   // logical <-> physical bit position
+  uint64_t touched = 0;                // logical qubits a non-diagonal op has acted on so far
   std::vector<double> mats;
   // stage state
   std::vector<HPass> passes;
@@ -339,6 +340,15 @@ struct Planner {
     sw.blk_q16 = (uint32_t)(blk_begin / 2);
     sw.blk_len_q16 = (uint32_t)(bytes / 16);
     out->sweeps.push_back(sw);
+    // a qubit only diagonal ops / control tests have seen is still |0>: amplitudes with a 1 on its
+    // bit are zero, so tiles (or whole shards) with such an outside bit set can be skipped
+    for (int i : sel) {
+      if (passes[i].qa >= 0) touched |= 1ull << passes[i].qa;
+      if (passes[i].qb >= 0) touched |= 1ull << passes[i].qb;
+    }
+    uint32_t um = 0;
+    for (int q = 0; q < n; ++q) if (!((touched >> q) & 1)) um |= 1u << phys[q];
+    out->sweep_untouched.push_back(um);
     out->n_passes += (int64_t)sel.size();
   }
 

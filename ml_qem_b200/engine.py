@@ -62,6 +62,7 @@ EXPORTS = [
     "bwq_dm_run", "bwq_sv_run", "bwq_dm_run_device_out", "bwq_dm_prepare", "bwq_dm_execute", "bwq_dm_execute_device_out", "bwq_sv_prepare", "bwq_sv_execute", "bwq_get_stats", "bwq_sync", "bwq_lower_dm",
     "bwq_program_free", "bwq_program_sizes", "bwq_program_read",
     "bwq_svx_lower", "bwq_svx_free", "bwq_svx_sizes", "bwq_svx_read", "bwq_svx_upload", "bwq_svx_run_segment",
+    "bwq_svx_bytes",
 ]
 
 
@@ -103,6 +104,8 @@ def load_library(path=None):
     lib.bwq_svx_sizes.argtypes = [C.c_void_p, C.c_void_p]
     lib.bwq_svx_read.argtypes = [C.c_void_p] + [C.c_void_p] * 7
     lib.bwq_svx_upload.argtypes = [C.c_void_p, C.c_void_p]
+    lib.bwq_svx_bytes.argtypes = [C.c_void_p, C.c_int32]
+    lib.bwq_svx_bytes.restype = C.c_int64
     lib.bwq_svx_run_segment.argtypes = [C.c_void_p, C.c_void_p, C.c_int32, C.c_void_p, C.c_int32, C.c_void_p, C.c_void_p]
     if path is None:
         _lib = lib
@@ -393,6 +396,9 @@ class SvxProgram:
             self.close()
         except Exception:
             pass
+
+    def algorithmic_bytes(self, rank=0):
+        return int(self._lib.bwq_svx_bytes(self._h, int(rank)))
 
     def upload(self, engine):
         engine._check(self._lib.bwq_svx_upload(engine._ctx, self._h), "bwq_svx_upload")

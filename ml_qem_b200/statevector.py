@@ -103,7 +103,7 @@ class ShardedStatevector:
             mark("allreduce")
         self.last_plan = {"n_bits": info["n_bits"], "n_local": info["n_local"], "n_sweeps": len(info["sweeps"]),
                           "n_passes": info["n_passes"], "n_exchanges": info["n_exchanges"],
-                          "exchanged_bytes_per_rank": exchanged_bytes,
+                          "exchanged_bytes_per_rank": exchanged_bytes, "kernel_bytes": prog.algorithmic_bytes(self.rank),
                           "n_expval_passes": int(sum(-(-int(c) // 32) for k, _, c, _ in info["segs"] if k == SEG_EXPVAL))}
         vals = obs[:info["n_observables"]].cpu().numpy()
         if profile:

@@ -15,7 +15,7 @@ ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 
 def test_library_exports_every_declared_symbol(lib):
     hdr = open(os.path.join(ROOT, "include", "bwq.h")).read()
-    declared = set(re.findall(r"^\s*(?:int|void|const char\*)\s+(bwq_[a-z_0-9]+)\s*\(", hdr, re.M))
+    declared = set(re.findall(r"^\s*(?:int|int64_t|void|const char\*)\s+(bwq_[a-z_0-9]+)\s*\(", hdr, re.M))
     assert declared >= {"bwq_create", "bwq_dm_run", "bwq_sv_run", "bwq_set_noise_table", "bwq_lower_dm"}
     for name in declared:
         assert getattr(lib, name) is not None, name
