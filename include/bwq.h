@@ -113,8 +113,11 @@ typedef struct {
   int32_t chunk_circuits;   /* circuits simulated together (default: as many as fit)          */
   int32_t host_threads;     /* lowering threads (default: hardware concurrency)               */
   int32_t sv_tile_bits;     /* amplitudes per statevector tile = 2^this, 2..12 (default 11)    */
-  int32_t reserved;
+  int32_t flags;            /* BWQ_OPT_* bits (0 = defaults)                                  */
 } bwq_options;
+/* planner switches for kernel experiments: keep the first / last pass of a sweep on the staged path */
+#define BWQ_OPT_NO_DIRECT_LOAD 1
+#define BWQ_OPT_NO_DIRECT_STORE 2
 
 /* Counters of the last *_run call (for the roofline: bytes = sweeps x 16 B x 4^n). */
 typedef struct {

@@ -346,6 +346,7 @@ static int dm_prepare_impl(bwq_ctx* ctx, const bwq_batch* b, int32_t* out_status
   LowerOptions lo;
   lo.tile_qubits = ctx->opt.tile_qubits ? ctx->opt.tile_qubits : 6;
   lo.low_qubits = ctx->opt.low_qubits > 0 ? ctx->opt.low_qubits : 2;
+  lo.direct = (ctx->opt.flags & BWQ_OPT_NO_DIRECT_LOAD ? 0 : kPassLoadDirect) | (ctx->opt.flags & BWQ_OPT_NO_DIRECT_STORE ? 0 : kPassStoreDirect);
   P.tile_qubits = lo.tile_qubits;
   std::vector<CircuitProgram> progs(N);
   parallel_for(N, host_threads(ctx), [&](int c) { lower_dm_circuit(ctx->noise, *b, c, lo, &progs[c]); });

@@ -271,18 +271,87 @@ template <int KQ> __device__ __forceinline__ int64_t deposit(uint32_t j, const i
   return off;
 }
 
-// all register passes of one sweep block on the tile staged in shared memory
+// tile-local index of register group grp of a pass on slots (lo, hi): zero digits inserted at lo, hi
+__device__ __forceinline__ uint32_t group_tile_index(uint32_t grp, int lo, int hi) {
+  const uint32_t low = grp & ((1u << (2 * lo)) - 1u);
+  const uint32_t mid = (grp >> (2 * lo)) & ((1u << (2 * (hi - lo - 1))) - 1u);
+  const uint32_t high = grp >> (2 * (hi - 1));
+  return low | (mid << (2 * lo + 2)) | (high << (2 * hi + 2));
+}
+
+// Direct pass <-> HBM transfers.  The first pass of a sweep may take its register groups straight
+// from global memory and the last one may store them straight back, which removes the staging
+// hop through shared memory (2 of the 2P+2 tile traversals each).  The lowering stage requests it
+// only when neither target slot is one of the two lowest slots: consecutive lanes then walk the
+// 16 contiguous elements of slots 0 and 1, i.e. every 8-byte warp access covers two full 128-byte
+// lines.  synth: first sweep of a circuit, the tile of |0..0><0..0| is generated instead of read.
+template <int KQ, int NG>
+__device__ __forceinline__ void group_load_global(double (&v)[NG][16], const double* __restrict__ gtile, const int (&pos)[KQ],
+                                                  const uint64_t pk, const int sa, const int sb, const int grp, const bool synth) {
+  constexpr int G = SweepCfg<KQ>::kGroups, T = SweepCfg<KQ>::kThreads;
+  const int lo = min(sa, sb), hi = max(sa, sb);
+  const int sha = 2 * int((pk >> (8 * sa)) & 0xffu), shb = 2 * int((pk >> (8 * sb)) & 0xffu);
+#pragma unroll
+  for (int g = 0; g < NG; ++g) {
+    const uint32_t j0 = group_tile_index(uint32_t(min(grp + g * T, G - 1)), lo, hi);
+    if (synth) {
+      const bool ok = ((j0 ^ (j0 >> 1)) & 0x55555555u) == 0u;  // every other digit of the group is I or Z
+#pragma unroll
+      for (int i = 0; i < 16; ++i) v[g][i] = (ok && (i == 0 || i == 3 || i == 12 || i == 15)) ? 1.0 : 0.0;
+    } else {
+      const double* __restrict__ base = gtile + deposit<KQ>(j0, pos);
+#pragma unroll
+      for (int db = 0; db < 4; ++db)
+#pragma unroll
+        for (int da = 0; da < 4; ++da)
+          v[g][da + 4 * db] = __ldcg(base + ((int64_t(da) << sha) + (int64_t(db) << shb)));
+    }
+  }
+}
+template <int KQ, int NG>
+__device__ __forceinline__ void group_store_global(const double (&v)[NG][16], double* __restrict__ gtile, const int (&pos)[KQ],
+                                                   const uint64_t pk, const int sa, const int sb, const int grp) {
+  constexpr int G = SweepCfg<KQ>::kGroups, T = SweepCfg<KQ>::kThreads;
+  const int lo = min(sa, sb), hi = max(sa, sb);
+  const int sha = 2 * int((pk >> (8 * sa)) & 0xffu), shb = 2 * int((pk >> (8 * sb)) & 0xffu);
+#pragma unroll
+  for (int g = 0; g < NG; ++g) {
+    if (NG > 1 && grp + g * T >= G) break;
+    double* __restrict__ base = gtile + deposit<KQ>(group_tile_index(uint32_t(grp + g * T), lo, hi), pos);
+#pragma unroll
+    for (int db = 0; db < 4; ++db)
+#pragma unroll
+      for (int da = 0; da < 4; ++da) base[(int64_t(da) << sha) + (int64_t(db) << shb)] = v[g][da + 4 * db];
+  }
+}
+
+// All register passes of one sweep block.  The tile is staged in shared memory unless the first
+// pass loads directly (first_desc, from SweepDesc::pos[7]: known before the program block lands,
+// so the loads are issued ahead of the block wait).  Returns true when the last pass already
+// stored the tile to global memory.
 template <int KQ, bool FULL>
-__device__ __forceinline__ void run_passes(double* __restrict__ tile, const double* __restrict__ pbuf,
-                                           const uint32_t* __restrict__ b0_table, const int tid) {
+__device__ __forceinline__ bool run_passes(double* __restrict__ tile, const double* __restrict__ pbuf,
+                                           const uint32_t* __restrict__ b0_table, const int tid,
+                                           double* __restrict__ gtile, const int (&pos)[KQ], const uint64_t pk,
+                                           const uint32_t first_desc, const bool synth) {
   constexpr int G = SweepCfg<KQ>::kGroups, T = SweepCfg<KQ>::kThreads, NG = SweepCfg<KQ>::kNG;
-  const int n_passes = reinterpret_cast<const int*>(pbuf)[0];
+  static_assert(NG == 1 || G % (T * NG) == 0, "two-group configurations cover the tile exactly");
   char* const tile_b = reinterpret_cast<char*>(tile);
+  double v[NG][16];
+  const bool first_direct = (first_desc & 0x80u) != 0u;
+  if (first_direct && tid < G)
+    group_load_global<KQ, NG>(v, gtile, pos, pk, int(first_desc & 7u), int((first_desc >> 3) & 7u), tid, synth);
+  cp_async_wait_all();
+  __syncthreads();
+  const int n_passes = reinterpret_cast<const int*>(pbuf)[0];
+  bool stored = false;
   for (int p = 0; p < n_passes; ++p) {
     if (p) __syncthreads();
     const uint2 praw = *reinterpret_cast<const uint2*>(pbuf + 2 * (1 + p));
     const int ops_q16 = praw.x & 0xffffu, n_ops = praw.x >> 16;
     const int sa = praw.y & 0xffu, sb = (praw.y >> 8) & 0xffu;
+    const bool ld_g = p == 0 && first_direct;
+    const bool st_g = ((praw.y >> 16) & kPassStoreDirect) != 0u;
     const int lo = min(sa, sb), hi = max(sa, sb);
     // swizzled byte offsets of the 16 (da, db) corners (uniform) and of the thread's group base
     // (table built on the host: index = swz(grp with zero digits inserted at lo and hi))
@@ -294,22 +363,31 @@ __device__ __forceinline__ void run_passes(double* __restrict__ tile, const doub
     const uint32_t* __restrict__ b0row = b0_table + ((hi * (hi - 1) / 2 + lo) << 10);
     for (int grp = tid; grp < G; grp += T * NG) {
       uint32_t b0[NG];
-      double v[NG][16];
 #pragma unroll
       for (int g = 0; g < NG; ++g) b0[g] = __ldg(b0row + min(grp + g * T, G - 1));
+      if (ld_g) {
+        if (grp != tid) group_load_global<KQ, NG>(v, gtile, pos, pk, sa, sb, grp, synth);
+      } else {
 #pragma unroll
-      for (int g = 0; g < NG; ++g)
+        for (int g = 0; g < NG; ++g)
 #pragma unroll
-        for (int i = 0; i < 16; ++i) v[g][i] = *reinterpret_cast<const double*>(tile_b + (b0[g] ^ oab[i]));
+          for (int i = 0; i < 16; ++i) v[g][i] = *reinterpret_cast<const double*>(tile_b + (b0[g] ^ oab[i]));
+      }
       run_ops<FULL, NG>(v, pbuf, ops_q16, n_ops);
+      if (st_g) {
+        group_store_global<KQ, NG>(v, gtile, pos, pk, sa, sb, grp);
+      } else {
 #pragma unroll
-      for (int g = 0; g < NG; ++g)
-        if (NG == 1 || grp + g * T < G) {
+        for (int g = 0; g < NG; ++g)
+          if (NG == 1 || grp + g * T < G) {
 #pragma unroll
-          for (int i = 0; i < 16; ++i) *reinterpret_cast<double*>(tile_b + (b0[g] ^ oab[i])) = v[g][i];
-        }
+            for (int i = 0; i < 16; ++i) *reinterpret_cast<double*>(tile_b + (b0[g] ^ oab[i])) = v[g][i];
+          }
+      }
     }
+    stored = st_g;
   }
+  return stored;
 }
 
 // FULL = also carries the dense 4x4 / 16x16 ops (coherent errors, non-basis 2-qubit gates); the
@@ -335,11 +413,11 @@ dm_sweep_kernel(const DmLaunch L, const int sweep_idx) {
   const int4 swraw = __ldg(reinterpret_cast<const int4*>(L.sweeps + sw_i));
   double* pbuf = tile + E;
   int pos[KQ];
-  {
-    const uint64_t pk = (uint64_t(uint32_t(swraw.w)) << 32) | uint32_t(swraw.z);  // pos[0..7]
+  const uint64_t pk = (uint64_t(uint32_t(swraw.w)) << 32) | uint32_t(swraw.z);  // pos[0..7]
 #pragma unroll
-    for (int s = 0; s < KQ; ++s) pos[s] = int((pk >> (8 * s)) & 0xff);
-  }
+  for (int s = 0; s < KQ; ++s) pos[s] = int((pk >> (8 * s)) & 0xff);
+  const uint32_t first_desc = uint32_t(swraw.w) >> 24;  // pos[7]: kFirstDirect | sa | sb << 3
+  const bool first_direct = (first_desc & 0x80u) != 0u;
   // scatter the tile id over the digit positions that are NOT resident in the tile: the bits of t
   // fill the gaps between consecutive resident positions (pos[] ascending)
   int64_t base = 0;
@@ -395,8 +473,10 @@ dm_sweep_kernel(const DmLaunch L, const int sweep_idx) {
     for (int i = tid; i < len; i += T) cp_async16(reinterpret_cast<uint4*>(pbuf) + i, src + i);
   }
 
-  // ---- load (or synthesise |0..0><0..0| on the first sweep)
-  if (sweep_idx == 0) {
+  // ---- load (or synthesise |0..0><0..0| on the first sweep); skipped when the first pass reads
+  //      its register groups straight from global memory
+  if (first_direct) {
+  } else if (sweep_idx == 0) {
 #pragma unroll
     for (int k = 0; k < NIT; ++k) {
       if (NIT * T != U && tid + k * T >= U) break;
@@ -424,10 +504,8 @@ dm_sweep_kernel(const DmLaunch L, const int sweep_idx) {
     }
   }
 
-  // ---- register passes
-  cp_async_wait_all();
-  __syncthreads();
-  run_passes<KQ, FULL>(tile, pbuf, L.b0_table, tid);
+  // ---- register passes (waits for the program block; the last pass may store the tile itself)
+  if (run_passes<KQ, FULL>(tile, pbuf, L.b0_table, tid, g, pos, pk, first_desc, sweep_idx == 0)) return;
   __syncthreads();
 
   // ---- store

@@ -532,6 +532,36 @@ void lower_dm_circuit(const NoiseTable& noise, const bwq_batch& b, int c, const 
     int s = 0;
     for (int d = 0; d < nd; ++d) if (in_tile[d]) { sw.pos[s] = (uint8_t)d; slot_of[d] = s++; }
 
+    // ---- direct passes: passes on disjoint qubits commute, so an eligible pass (neither target in
+    // the two lowest slots) with no predecessor / successor on its qubits inside this sweep is
+    // moved to the front / back and exchanges its register groups with global memory directly
+    auto eligible = [&](int i) { return slot_of[passes[i].qa] >= 2 && slot_of[passes[i].qb] >= 2; };
+    auto shares = [&](int i, int j) {
+      return passes[i].qa == passes[j].qa || passes[i].qa == passes[j].qb || passes[i].qb == passes[j].qa || passes[i].qb == passes[j].qb;
+    };
+    bool first_direct = false, last_direct = false;
+    if (opt.direct & kPassLoadDirect) {
+      for (size_t k = 0; k < sel.size() && !first_direct; ++k) {
+        if (!eligible(sel[k])) continue;
+        bool free_ = true;
+        for (size_t e = 0; e < k && free_; ++e) free_ = !shares(sel[e], sel[k]);
+        if (!free_) continue;
+        std::rotate(sel.begin(), sel.begin() + k, sel.begin() + k + 1);
+        first_direct = true;
+      }
+    }
+    if (opt.direct & kPassStoreDirect) {
+      const size_t stop = (first_direct && sel.size() > 1) ? 1 : 0;  // the front pass stays in front
+      for (size_t k = sel.size(); k-- > stop && !last_direct;) {
+        if (!eligible(sel[k])) continue;
+        bool free_ = true;
+        for (size_t l = k + 1; l < sel.size() && free_; ++l) free_ = !shares(sel[l], sel[k]);
+        if (!free_) continue;
+        std::rotate(sel.begin() + k, sel.begin() + k + 1, sel.end());
+        last_direct = true;
+      }
+    }
+
     // ---- emit the block
     size_t n_ops_total = 0;
     for (int i : sel) n_ops_total += passes[i].ops.size();
@@ -560,6 +590,11 @@ void lower_dm_circuit(const NoiseTable& noise, const bwq_batch& b, int c, const 
       ph[k].n_ops = (uint16_t)p.ops.size();
       ph[k].sa = (uint8_t)slot_of[p.qa];
       ph[k].sb = (uint8_t)slot_of[p.qb];
+      if (k == 0 && first_direct) {
+        ph[k].flags |= kPassLoadDirect;
+        sw.pos[7] = (uint8_t)(kFirstDirect | ph[k].sa | (ph[k].sb << 3));
+      }
+      if (k + 1 == sel.size() && last_direct) ph[k].flags |= kPassStoreDirect;
       for (const MacroOp& o : p.ops) {
         BlockOp& d = bo[op_cursor++];
         d.pre_a = o.pre_a; d.pre_b = o.pre_b; d.twoq = o.twoq;

@@ -54,8 +54,14 @@ struct PassHdr {    // 16 B
   uint16_t ops_q16; // offset of the pass's first BlockOp, in 16-byte units from the block start
   uint16_t n_ops;
   uint8_t sa, sb;   // tile slots of digits a and b
-  uint8_t pad[10];
+  uint8_t flags;    // kPassLoadDirect (first pass; mirrored in SweepDesc::pos[7]) | kPassStoreDirect (last pass)
+  uint8_t pad[9];
 };
+// Direct passes: the first pass of a sweep reads its register groups from global memory and the
+// last one writes them back, instead of staging the tile through shared memory.  Requested when
+// neither target slot is one of the two lowest slots (full 128-byte lines per warp access).
+constexpr uint8_t kPassLoadDirect = 1, kPassStoreDirect = 2;
+constexpr uint8_t kFirstDirect = 0x80;  // SweepDesc::pos[7] = kFirstDirect | sa | sb << 3 of the first pass
 struct BlockOp {    // 16 B
   uint8_t pre_a, pre_b, twoq, pad0;
   uint16_t off_a, off_b, off_2;  // parameter offsets in 8-byte units from the block start
@@ -66,7 +72,8 @@ struct SweepDesc {  // 16 B
   uint32_t blk_len_q16; // low 16 bits: block length in 16-byte units; high 16 bits (density
                         // matrix only): digit positions no pass has touched up to and including
                         // this sweep -- a tile with X or Y on such an outside digit is all zero
-  uint8_t pos[8];       // digit positions resident in the tile, ascending; first n_tile valid
+  uint8_t pos[8];       // digit positions resident in the tile, ascending; first n_tile (<= 7) valid;
+                        // pos[7] (density matrix): first-pass descriptor, see kFirstDirect
 };
 constexpr int kBlockBytes = 8192;  // shared-memory program buffer per CTA
 
@@ -106,6 +113,7 @@ struct CircuitProgram {
 struct LowerOptions {
   int tile_qubits = 6;
   int low_qubits = 2;
+  int direct = kPassLoadDirect | kPassStoreDirect;  // which direct passes the planner may request
 };
 
 // Lowers circuit c of the batch.  Never throws; sets status on per-circuit failure.

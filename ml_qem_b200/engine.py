@@ -46,7 +46,7 @@ class _NoiseTable(C.Structure):
 class _Options(C.Structure):
     _fields_ = [("tile_qubits", C.c_int32), ("low_qubits", C.c_int32), ("max_state_bytes", C.c_int64),
                 ("chunk_circuits", C.c_int32), ("host_threads", C.c_int32), ("sv_tile_bits", C.c_int32),
-                ("reserved", C.c_int32)]
+                ("flags", C.c_int32)]
 
 
 class _Stats(C.Structure):
@@ -252,8 +252,9 @@ class Engine:
             raise EngineError(f"{what} failed ({rc}): {self._lib.bwq_last_error(self._ctx).decode()}")
 
     def set_options(self, tile_qubits=0, low_qubits=0, max_state_bytes=0, chunk_circuits=0, host_threads=0,
-                    sv_tile_bits=0):
-        o = _Options(tile_qubits, low_qubits, max_state_bytes, chunk_circuits, host_threads, sv_tile_bits, 0)
+                    sv_tile_bits=0, flags=0):
+        """flags: BWQ_OPT_* bits of include/bwq.h (1 = no direct load pass, 2 = no direct store pass)."""
+        o = _Options(tile_qubits, low_qubits, max_state_bytes, chunk_circuits, host_threads, sv_tile_bits, flags)
         self._check(self._lib.bwq_set_options(self._ctx, C.byref(o)), "bwq_set_options")
 
     def set_noise(self, model):

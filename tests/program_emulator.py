@@ -113,7 +113,7 @@ def run_program(prog):
     for sw in prog["sweeps"]:
         pos = list(sw[1:9])
         kq = 1
-        while kq < 8 and kq < nd and pos[kq] > pos[kq - 1]:
+        while kq < 7 and kq < nd and pos[kq] > pos[kq - 1]:  # pos[7] is the first-pass descriptor
             kq += 1
         pos = pos[:kq]
         passes, mats = decode_block(prog, sw)
