@@ -78,13 +78,14 @@ struct DmChunk {
   int first = 0, count = 0, nd = 0, kq = 0;
   bool full = false;
   std::vector<int> live;  // circuits that still have a sweep s, per sweep index
+  std::vector<int64_t> desc_off;  // per sweep index: first descriptor of the launch (sweep-major table)
   std::vector<int64_t> bytes;  // algorithmic bytes of launch s: tiles that are not provably zero
 };
 struct DmPlan {
   bool valid = false;
   int tile_qubits = 6;
   int64_t n_obs = 0;
-  size_t o_range = 0, o_sweeps = 0, o_prog = 0, o_tidx = 0, o_tcoef = 0, o_obs = 0, blob_bytes = 0;
+  size_t o_sweeps = 0, o_prog = 0, o_tidx = 0, o_tcoef = 0, o_obs = 0, blob_bytes = 0;
   std::vector<int64_t> ob_off;
   std::vector<DmChunk> chunks;
   std::vector<std::pair<int64_t, double>> host_fix;
@@ -378,7 +379,6 @@ static int dm_prepare_impl(bwq_ctx* ctx, const bwq_batch* b, int32_t* out_status
   if (sw_off[M] > INT32_MAX || pg_off[M] / 2 >= (int64_t(1) << 32))
     return fail(ctx, BWQ_ERR_ARG, "batch too large for 32-bit program indices; split the batch");
   Blob blob;
-  P.o_range = blob.add(sizeof(int32_t) * 2 * (size_t)M);
   P.o_sweeps = blob.add(sizeof(SweepDesc) * (size_t)sw_off[M]);
   P.o_prog = blob.add(sizeof(uint64_t) * (size_t)pg_off[M]);
   P.o_tidx = blob.add(sizeof(int64_t) * (size_t)tm_off[M]);
@@ -393,9 +393,6 @@ static int dm_prepare_impl(bwq_ctx* ctx, const bwq_batch* b, int32_t* out_status
   parallel_for(M, host_threads(ctx), [&](int i) {
     const int c = order[i];
     const CircuitProgram& p = progs[c];
-    int32_t* range = (int32_t*)(hb + P.o_range) + 2 * i;
-    range[0] = (int32_t)sw_off[i];
-    range[1] = (int32_t)sw_off[i + 1];
     SweepDesc* sw = (SweepDesc*)(hb + P.o_sweeps) + sw_off[i];
     for (size_t k = 0; k < p.sweeps.size(); ++k) {
       sw[k] = p.sweeps[k];
@@ -463,6 +460,18 @@ static int dm_prepare_impl(bwq_ctx* ctx, const bwq_batch* b, int32_t* out_status
         const int u = __builtin_popcount(outside & (p.sweeps[sidx].blk_len_q16 >> 16));
         const int64_t full = (int64_t)sizeof(double) << (2 * nd);
         ch.bytes[sidx] += sidx == 0 ? full + (full >> u) * 0 : 2 * (full >> u);
+      }
+    }
+    // sweep-major descriptor table of the chunk: launch s reads one descriptor per circuit slot
+    // (circuits with an s-th sweep are the leading `live[s]` slots), a single lookup per CTA
+    {
+      SweepDesc* all = (SweepDesc*)(hb + P.o_sweeps);
+      const int64_t base = sw_off[i];
+      std::vector<SweepDesc> tmp(all + base, all + sw_off[j]);
+      int64_t off = base;
+      for (size_t sidx = 0; sidx < max_sweeps; ++sidx) {
+        ch.desc_off.push_back(off);
+        for (int slot = 0; slot < ch.live[sidx]; ++slot) all[off++] = tmp[(sw_off[i + slot] - base) + (int64_t)sidx];
       }
     }
     P.chunks.push_back(std::move(ch));
@@ -533,15 +542,16 @@ static int dm_execute_impl(bwq_ctx* ctx, double* out_vals, bool out_on_device) {
     L.states = (double*)ctx->d_states.p;
     L.stride = int64_t(1) << (2 * ch.nd);
     L.n_digits = ch.nd;
-    L.first_circuit = ch.first;
-    L.sweep_range = (const int32_t*)(db + P.o_range);
-    L.sweeps = (const SweepDesc*)(db + P.o_sweeps);
+    const int pf_opt = (ctx->opt.flags >> 8) & 0xffff;  // kernel experiments: prefetch distance, 0xffff = off
+    const int pf_dist = (ch.nd <= ch.kq || pf_opt == 0xffff) ? 0 : (pf_opt ? pf_opt : kDmPrefetchDist);
     L.prog = (const uint4*)(db + P.o_prog);
     L.b0_table = (const uint32_t*)ctx->d_b0.p;
     const int64_t tiles = int64_t(1) << (2 * (ch.nd - ch.kq));
     if (ci < n_ev) CK(cudaEventRecord(ctx->chunk_ev[2 * ci], st));
     for (size_t sidx = 0; sidx < ch.live.size(); ++sidx) {
       const int live = ch.live[sidx];
+      L.sweeps = (const SweepDesc*)(db + P.o_sweeps) + ch.desc_off[sidx];
+      L.prefetch_dist = sidx == 0 ? 0 : pf_dist;  // the first sweep synthesises |0..0><0..0|, nothing to read
       CK(ch.full ? launch_sweep_kq<true>(ch.kq, L, (int)sidx, tiles * live, st)
                  : launch_sweep_kq<false>(ch.kq, L, (int)sidx, tiles * live, st));
       S.n_sweep_launches++;

@@ -17,9 +17,8 @@ struct DmLaunch {
   double* states;              // chunk base; circuit slot s owns [s * stride, (s+1) * stride)
   int64_t stride;              // 4^n doubles
   int32_t n_digits;
-  int32_t first_circuit;       // index (sorted order) of slot 0
-  const int32_t* sweep_range;  // [2 * n_circuits] absolute {begin, end} per sorted circuit
-  const SweepDesc* sweeps;
+  int32_t prefetch_dist;       // CTA b prefetches the tile of CTA b + prefetch_dist into L2 (0 = off)
+  const SweepDesc* sweeps;     // THIS launch: one descriptor per circuit slot (sweep-major table)
   const uint4* prog;           // sweep blocks (16-byte units)
   const uint32_t* b0_table;    // [21][1024] group bases (bytes) of the register passes (fill_b0_table)
 };
@@ -255,20 +254,57 @@ static_assert(swz(1u << 4) == 21 && swz(2u << 6) == 142 && swz(3u << 8) == 779 &
 template <int KQ> struct SweepCfg {
   static constexpr int kElems = 1 << (2 * KQ);
   static constexpr int kGroups = kElems / 16;
-  static constexpr int kNG = kGroups >= 64 ? 2 : 1;   // register groups per thread
-  static constexpr int kThreads = kGroups / kNG >= 256 ? 256 : (kGroups / kNG >= 32 ? kGroups / kNG : 32);
+#ifndef BWQ_KQ6_NG
+#define BWQ_KQ6_NG 2
+#endif
+#ifndef BWQ_KQ6_THREADS
+#define BWQ_KQ6_THREADS (256 / BWQ_KQ6_NG)
+#endif
+  static constexpr int kNG = KQ == 6 ? BWQ_KQ6_NG : (kGroups >= 64 ? 2 : 1);   // register groups per thread
+  static constexpr int kThreads = KQ == 6 ? BWQ_KQ6_THREADS : (kGroups / kNG >= 256 ? 256 : (kGroups / kNG >= 32 ? kGroups / kNG : 32));
 #ifndef BWQ_KQ6_BLOCKS
 #define BWQ_KQ6_BLOCKS 3
 #endif
   static constexpr int kMinBlocks = KQ >= 7 ? 1 : (KQ == 6 ? BWQ_KQ6_BLOCKS : 4);
 };
 
+// default distance of the L2 tile prefetch: 2/3 of the 148 x 3 resident CTAs (KQ = 6); measured
+// on tfim13: off 4262 GB/s, 148: 4436, 296: 4460, 444: 4417, 888: 4317
+constexpr int kDmPrefetchDist = 296;
+
 // tile-local index j (2 bits per slot) -> offset in the state (2 bits per digit position)
-template <int KQ> __device__ __forceinline__ int64_t deposit(uint32_t j, const int (&pos)[KQ]) {
-  int64_t off = 0;
+// (element offsets fit 32 bits: kMaxDmQubits = 16 digits)
+template <int KQ> __device__ __forceinline__ uint32_t deposit(uint32_t j, const int (&pos)[KQ]) {
+  uint32_t off = 0;
 #pragma unroll
-  for (int s = 0; s < KQ; ++s) off |= int64_t((j >> (2 * s)) & 3u) << (2 * pos[s]);
+  for (int s = 0; s < KQ; ++s) off |= ((j >> (2 * s)) & 3u) << (2 * pos[s]);
   return off;
+}
+static_assert(kMaxDmQubits <= 16, "32-bit element offsets");
+
+// tile id -> offset of the tile's first element: the bits of t fill the digit positions that are
+// NOT resident in the tile, i.e. the gaps between consecutive resident positions (pos[] ascending)
+template <int KQ> __device__ __forceinline__ uint32_t tile_base(uint32_t t, const int (&pos)[KQ]) {
+  uint32_t base = 0, rest = t;
+  int next = 0;  // next free digit position
+#pragma unroll
+  for (int s = 0; s < KQ; ++s) {
+    const int gap = pos[s] - next;  // digits in [next, pos[s]) come from t
+    base |= (rest & ((1u << (2 * gap)) - 1u)) << (2 * next);
+    rest = gap >= 16 ? 0u : rest >> (2 * gap);
+    next = pos[s] + 1;
+  }
+  return next >= 16 ? base : (base | (rest << (2 * next)));
+}
+
+// one bit per digit position (d -> bit 2d) whose digit is X or Y
+__device__ __forceinline__ uint32_t xy_mask(uint32_t elem) { return (elem ^ (elem >> 1)) & 0x55555555u; }
+// 16-bit set of digit positions -> bits 2d
+__device__ __forceinline__ uint32_t spread_digits(uint32_t m) {
+  m = (m | (m << 8)) & 0x00ff00ffu;
+  m = (m | (m << 4)) & 0x0f0f0f0fu;
+  m = (m | (m << 2)) & 0x33333333u;
+  return (m | (m << 1)) & 0x55555555u;
 }
 
 // tile-local index of register group grp of a pass on slots (lo, hi): zero digits inserted at lo, hi
@@ -299,12 +335,12 @@ __device__ __forceinline__ void group_load_global(double (&v)[NG][16], const dou
 #pragma unroll
       for (int i = 0; i < 16; ++i) v[g][i] = (ok && (i == 0 || i == 3 || i == 12 || i == 15)) ? 1.0 : 0.0;
     } else {
-      const double* __restrict__ base = gtile + deposit<KQ>(j0, pos);
+      const uint32_t e0 = deposit<KQ>(j0, pos);  // the corner offsets occupy digit positions e0 leaves zero
 #pragma unroll
       for (int db = 0; db < 4; ++db)
 #pragma unroll
         for (int da = 0; da < 4; ++da)
-          v[g][da + 4 * db] = __ldcg(base + ((int64_t(da) << sha) + (int64_t(db) << shb)));
+          v[g][da + 4 * db] = __ldcg(gtile + (e0 | (uint32_t(da) << sha) | (uint32_t(db) << shb)));
     }
   }
 }
@@ -317,12 +353,38 @@ __device__ __forceinline__ void group_store_global(const double (&v)[NG][16], do
 #pragma unroll
   for (int g = 0; g < NG; ++g) {
     if (NG > 1 && grp + g * T >= G) break;
-    double* __restrict__ base = gtile + deposit<KQ>(group_tile_index(uint32_t(grp + g * T), lo, hi), pos);
+    const uint32_t e0 = deposit<KQ>(group_tile_index(uint32_t(grp + g * T), lo, hi), pos);
 #pragma unroll
     for (int db = 0; db < 4; ++db)
 #pragma unroll
-      for (int da = 0; da < 4; ++da) base[(int64_t(da) << sha) + (int64_t(db) << shb)] = v[g][da + 4 * db];
+      for (int da = 0; da < 4; ++da) gtile[e0 | (uint32_t(da) << sha) | (uint32_t(db) << shb)] = v[g][da + 4 * db];
   }
+}
+
+// L2 prefetch of the tile CTA (blockIdx.x + prefetch_dist) will sweep: CTAs are dispatched in index
+// order, so that CTA starts about one CTA lifetime from now and finds its 32 KiB in L2 instead of
+// HBM (the load phase is latency bound: 12 warps per SM).  One warp issues the 4^(KQ-2) line
+// prefetches; tiles that are provably zero or whose two lowest slots are not contiguous are skipped.
+template <int KQ>
+__device__ __forceinline__ void prefetch_next_tile(const DmLaunch& L, const int tid) {
+  if (L.prefetch_dist == 0 || tid >= 32) return;
+  const uint32_t nb = blockIdx.x + uint32_t(L.prefetch_dist);
+  if (nb >= gridDim.x) return;
+  const int tiles_log2 = 2 * (L.n_digits - KQ);
+  const uint32_t slot = nb >> tiles_log2;
+  const int4 d = __ldg(reinterpret_cast<const int4*>(L.sweeps + slot));
+  const uint64_t pk = (uint64_t(uint32_t(d.w)) << 32) | uint32_t(d.z);
+  int pos[KQ];
+#pragma unroll
+  for (int s = 0; s < KQ; ++s) pos[s] = int((pk >> (8 * s)) & 0xff);
+  if (pos[0] != 0 || pos[1] != 1) return;
+  const uint32_t base = tile_base<KQ>(nb & ((1u << tiles_log2) - 1u), pos);
+  if (xy_mask(base) & spread_digits(uint32_t(d.y) >> 16)) return;
+  const double* g = L.states + int64_t(slot) * L.stride + base;
+  constexpr int kRuns = 1 << (2 * KQ - 4);  // 128-byte runs (slots 0 and 1) per tile
+#pragma unroll 4
+  for (int r = tid; r < kRuns; r += 32)
+    asm volatile("prefetch.global.L2 [%0];" ::"l"(g + deposit<KQ>(uint32_t(r) << 4, pos)));
 }
 
 // All register passes of one sweep block.  The tile is staged in shared memory unless the first
@@ -333,7 +395,7 @@ template <int KQ, bool FULL>
 __device__ __forceinline__ bool run_passes(double* __restrict__ tile, const double* __restrict__ pbuf,
                                            const uint32_t* __restrict__ b0_table, const int tid,
                                            double* __restrict__ gtile, const int (&pos)[KQ], const uint64_t pk,
-                                           const uint32_t first_desc, const bool synth) {
+                                           const uint32_t first_desc, const bool synth, const DmLaunch& L) {
   constexpr int G = SweepCfg<KQ>::kGroups, T = SweepCfg<KQ>::kThreads, NG = SweepCfg<KQ>::kNG;
   static_assert(NG == 1 || G % (T * NG) == 0, "two-group configurations cover the tile exactly");
   char* const tile_b = reinterpret_cast<char*>(tile);
@@ -341,6 +403,7 @@ __device__ __forceinline__ bool run_passes(double* __restrict__ tile, const doub
   const bool first_direct = (first_desc & 0x80u) != 0u;
   if (first_direct && tid < G)
     group_load_global<KQ, NG>(v, gtile, pos, pk, int(first_desc & 7u), int((first_desc >> 3) & 7u), tid, synth);
+  if (first_direct) prefetch_next_tile<KQ>(L, tid);
   cp_async_wait_all();
   __syncthreads();
   const int n_passes = reinterpret_cast<const int*>(pbuf)[0];
@@ -405,12 +468,9 @@ dm_sweep_kernel(const DmLaunch L, const int sweep_idx) {
   double* const tile = KQ <= 6 ? st_tile : dyn_tile;
   const int tid = threadIdx.x;
   const int tiles_log2 = 2 * (L.n_digits - KQ);
-  const int64_t slot = int64_t(blockIdx.x) >> tiles_log2;
-  const uint32_t t = uint32_t(blockIdx.x) & ((1u << tiles_log2) - 1u);
-  const int circ = L.first_circuit + int(slot);
-  const int sw_i = __ldg(L.sweep_range + 2 * circ) + sweep_idx;
-  if (sw_i >= __ldg(L.sweep_range + 2 * circ + 1)) return;  // this circuit has fewer sweeps
-  const int4 swraw = __ldg(reinterpret_cast<const int4*>(L.sweeps + sw_i));
+  const uint32_t tile_mask = (1u << tiles_log2) - 1u;
+  const uint32_t slot = blockIdx.x >> tiles_log2;
+  const int4 swraw = __ldg(reinterpret_cast<const int4*>(L.sweeps + slot));
   double* pbuf = tile + E;
   int pos[KQ];
   const uint64_t pk = (uint64_t(uint32_t(swraw.w)) << 32) | uint32_t(swraw.z);  // pos[0..7]
@@ -418,29 +478,15 @@ dm_sweep_kernel(const DmLaunch L, const int sweep_idx) {
   for (int s = 0; s < KQ; ++s) pos[s] = int((pk >> (8 * s)) & 0xff);
   const uint32_t first_desc = uint32_t(swraw.w) >> 24;  // pos[7]: kFirstDirect | sa | sb << 3
   const bool first_direct = (first_desc & 0x80u) != 0u;
-  // scatter the tile id over the digit positions that are NOT resident in the tile: the bits of t
-  // fill the gaps between consecutive resident positions (pos[] ascending)
-  int64_t base = 0;
-  {
-    uint64_t rest = t;
-    int next = 0;  // next free digit position
-#pragma unroll
-    for (int s = 0; s < KQ; ++s) {
-      const int gap = pos[s] - next;  // digits in [next, pos[s]) come from t
-      base |= int64_t(rest & ((1ull << (2 * gap)) - 1ull)) << (2 * next);
-      rest >>= 2 * gap;
-      next = pos[s] + 1;
-    }
-    base |= int64_t(rest) << (2 * next);
-  }
-  double* __restrict__ g = L.states + slot * L.stride + base;
+  const uint32_t base = tile_base<KQ>(blockIdx.x & tile_mask, pos);
+  double* __restrict__ g = L.states + int64_t(slot) * L.stride + base;
 
   // Unit u = tid + k*T covers tile elements j = 2u, 2u+1.  deposit() and swz() are bitwise
   // linear, so the per-thread part (tid) is computed once and the per-iteration part (k*T) is
   // uniform / compile-time.  swz(j + 1) = swz(j) ^ 1: the pair goes to shared memory as two
   // 8-byte accesses (same bank traffic as one 16-byte access, no select on the swizzle parity).
   const uint32_t j_thr = 2u * uint32_t(tid);
-  const int64_t off_thr = deposit<KQ>(j_thr, pos);
+  const uint32_t off_thr = deposit<KQ>(j_thr, pos);
   const uint32_t p_thr = swz(j_thr);
 
   // Sparsity of the early state: |0..0><0..0| is 1 on the {I,Z}^n strings and 0 elsewhere, and a
@@ -448,20 +494,14 @@ dm_sweep_kernel(const DmLaunch L, const int sweep_idx) {
   // is all zero and stays zero under the linear passes (the affine parts act through the tile's
   // own I-component).  First sweep: plain zero store -- only 2^-(n-KQ) of its tiles run passes,
   // the rest is write-bandwidth bound; later sweeps: nothing to read, compute or write.
-  const uint32_t untouched = uint32_t(swraw.y) >> 16;          // digit positions, one bit each
-  uint32_t xy_digits = 0;                                        // positions whose digit is X or Y
-  {
-    const uint64_t b = uint64_t(base);
-#pragma unroll
-    for (int d = 0; d < kMaxDmQubits; ++d) xy_digits |= uint32_t(((b >> (2 * d)) ^ (b >> (2 * d + 1))) & 1ull) << d;
-  }
-  const bool tile_ok = (xy_digits & untouched) == 0u;
+  const uint32_t untouched = spread_digits(uint32_t(swraw.y) >> 16);  // digit positions d -> bit 2d
+  const bool tile_ok = (xy_mask(base) & untouched) == 0u;
   if (sweep_idx > 0 && !tile_ok) return;
   if (sweep_idx == 0 && !tile_ok) {
 #pragma unroll
     for (int k = 0; k < NIT; ++k) {
       if (NIT * T != U && tid + k * T >= U) break;
-      const int64_t off = off_thr | deposit<KQ>(2u * uint32_t(k * T), pos);
+      const uint32_t off = off_thr | deposit<KQ>(2u * uint32_t(k * T), pos);
       __stcg(reinterpret_cast<double2*>(g + off), make_double2(0.0, 0.0));
     }
     return;
@@ -492,9 +532,10 @@ dm_sweep_kernel(const DmLaunch L, const int sweep_idx) {
 #pragma unroll
     for (int k = 0; k < NIT; ++k) {
       if (NIT * T != U && tid + k * T >= U) break;
-      const int64_t off = off_thr | deposit<KQ>(2u * uint32_t(k * T), pos);
+      const uint32_t off = off_thr | deposit<KQ>(2u * uint32_t(k * T), pos);
       val[k] = __ldcg(reinterpret_cast<const double2*>(g + off));  // stream past L1
     }
+    prefetch_next_tile<KQ>(L, tid);
 #pragma unroll
     for (int k = 0; k < NIT; ++k) {
       if (NIT * T != U && tid + k * T >= U) break;
@@ -505,14 +546,14 @@ dm_sweep_kernel(const DmLaunch L, const int sweep_idx) {
   }
 
   // ---- register passes (waits for the program block; the last pass may store the tile itself)
-  if (run_passes<KQ, FULL>(tile, pbuf, L.b0_table, tid, g, pos, pk, first_desc, sweep_idx == 0)) return;
+  if (run_passes<KQ, FULL>(tile, pbuf, L.b0_table, tid, g, pos, pk, first_desc, sweep_idx == 0, L)) return;
   __syncthreads();
 
   // ---- store
 #pragma unroll
   for (int k = 0; k < NIT; ++k) {
     if (NIT * T != U && tid + k * T >= U) break;
-    const int64_t off = off_thr | deposit<KQ>(2u * uint32_t(k * T), pos);
+    const uint32_t off = off_thr | deposit<KQ>(2u * uint32_t(k * T), pos);
     const uint32_t p = p_thr ^ swz(2u * uint32_t(k * T));
     *reinterpret_cast<double2*>(g + off) = make_double2(tile[p], tile[p ^ 1u]);
   }
