@@ -335,12 +335,16 @@ __device__ __forceinline__ void group_load_global(double (&v)[NG][16], const dou
 #pragma unroll
       for (int i = 0; i < 16; ++i) v[g][i] = (ok && (i == 0 || i == 3 || i == 12 || i == 15)) ? 1.0 : 0.0;
     } else {
-      const uint32_t e0 = deposit<KQ>(j0, pos);  // the corner offsets occupy digit positions e0 leaves zero
+      // one 64-bit pointer per group and row; the corner offsets occupy digit positions the group
+      // base leaves zero, so they add (uniform byte strides) instead of being OR-ed per element
+      const char* const base = reinterpret_cast<const char*>(gtile + deposit<KQ>(j0, pos));
+      const uint64_t stra = uint64_t(8) << sha, strb = uint64_t(8) << shb;
 #pragma unroll
-      for (int db = 0; db < 4; ++db)
+      for (int db = 0; db < 4; ++db) {
+        const char* const row = base + db * strb;
 #pragma unroll
-        for (int da = 0; da < 4; ++da)
-          v[g][da + 4 * db] = __ldcg(gtile + (e0 | (uint32_t(da) << sha) | (uint32_t(db) << shb)));
+        for (int da = 0; da < 4; ++da) v[g][da + 4 * db] = __ldcg(reinterpret_cast<const double*>(row + da * stra));
+      }
     }
   }
 }
@@ -353,11 +357,14 @@ __device__ __forceinline__ void group_store_global(const double (&v)[NG][16], do
 #pragma unroll
   for (int g = 0; g < NG; ++g) {
     if (NG > 1 && grp + g * T >= G) break;
-    const uint32_t e0 = deposit<KQ>(group_tile_index(uint32_t(grp + g * T), lo, hi), pos);
+    char* const base = reinterpret_cast<char*>(gtile + deposit<KQ>(group_tile_index(uint32_t(grp + g * T), lo, hi), pos));
+    const uint64_t stra = uint64_t(8) << sha, strb = uint64_t(8) << shb;
 #pragma unroll
-    for (int db = 0; db < 4; ++db)
+    for (int db = 0; db < 4; ++db) {
+      char* const row = base + db * strb;
 #pragma unroll
-      for (int da = 0; da < 4; ++da) gtile[e0 | (uint32_t(da) << sha) | (uint32_t(db) << shb)] = v[g][da + 4 * db];
+      for (int da = 0; da < 4; ++da) *reinterpret_cast<double*>(row + da * stra) = v[g][da + 4 * db];
+    }
   }
 }
 
