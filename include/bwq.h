@@ -118,6 +118,7 @@ typedef struct {
 /* planner switches for kernel experiments: keep the first / last pass of a sweep on the staged path */
 #define BWQ_OPT_NO_DIRECT_LOAD 1
 #define BWQ_OPT_NO_DIRECT_STORE 2
+#define BWQ_OPT_NO_PIPELINE 4   /* bwq_dm_run: lower the whole batch before the first launch */
 
 /* Counters of the last *_run call (for the roofline: bytes = sweeps x 16 B x 4^n). */
 typedef struct {

@@ -136,10 +136,13 @@ struct bwq_ctx {
   std::string error;
   bwq_options opt{};
   NoiseTable noise;
-  DevBuf d_b0, d_noise, d_prog, d_sv_prog, d_states, d_out, d_scratch, d_wide_prog, d_partial;
-  PinBuf h_prog, h_sv_prog, h_out, h_wide_prog;
+  DevBuf d_b0, d_noise, d_sv_prog, d_states, d_out, d_scratch, d_wide_prog, d_partial;
+  PinBuf h_sv_prog, h_out, h_wide_prog;
   bwq_stats stats{};
-  DmPlan plan;
+  // density-matrix program slots: slot 0 is the prepared batch of bwq_dm_prepare / bwq_dm_execute;
+  // bwq_dm_run alternates between both so that segment k+1 is lowered on the host threads while
+  // the GPU executes segment k
+  struct DmSlot { DmPlan plan; PinBuf h_prog; DevBuf d_prog; } dm[2];
   SvPlan sv_plan;
   std::vector<cudaEvent_t> chunk_ev;  // begin/end of each chunk's sweep launches
   size_t smem_optin = 0;
@@ -222,8 +225,9 @@ extern "C" int bwq_destroy(bwq_ctx* ctx) {
   if (!ctx) return BWQ_OK;
   cudaSetDevice(ctx->device);
   cudaStreamSynchronize(ctx->stream);
-  ctx->d_b0.release(); ctx->d_noise.release(); ctx->d_prog.release(); ctx->d_states.release(); ctx->d_out.release();
-  ctx->d_scratch.release(); ctx->h_prog.release(); ctx->h_out.release();
+  ctx->d_b0.release(); ctx->d_noise.release(); ctx->d_states.release(); ctx->d_out.release();
+  for (auto& sl : ctx->dm) { sl.d_prog.release(); sl.h_prog.release(); }
+  ctx->d_scratch.release(); ctx->h_out.release();
   ctx->d_sv_prog.release(); ctx->h_sv_prog.release();
   ctx->d_wide_prog.release(); ctx->h_wide_prog.release(); ctx->d_partial.release();
   for (auto& ev : ctx->ev) if (ev) cudaEventDestroy(ev);
@@ -329,15 +333,16 @@ template <bool FULL> static cudaError_t launch_sweep_kq(int kq, const DmLaunch& 
 // (sweeps, expectation values, D2H of the values).  The prepared plan stays in the ctx so that
 // bwq_dm_execute can be repeated with the program resident in HBM.
 // ------------------------------------------------------------------------------------------------
-static int dm_prepare_impl(bwq_ctx* ctx, const bwq_batch* b, int32_t* out_status) {
-  if (!ctx) return BWQ_ERR_ARG;
-  int rc = check_batch(ctx, b, out_status, out_status);
-  if (rc) return rc;
-  DmPlan& P = ctx->plan;
+// Host part: lowers circuits [c0, c1) of the batch into slot `sl` (program blob in pinned memory,
+// chunk plan).  Output indices are relative to the first observable of c0.  Touches only the slot,
+// so it may run on a helper thread while the GPU executes the other slot.
+static int dm_lower_impl(bwq_ctx* ctx, bwq_ctx::DmSlot& sl, const bwq_batch* b, int c0, int c1, int32_t* out_status,
+                         int64_t budget) {
+  DmPlan& P = sl.plan;
   P = DmPlan();
-  ctx->stats = bwq_stats{};
-  const int N = b->n_circuits;
-  P.n_obs = N ? b->obs_offsets[N] : 0;
+  const int N = c1 - c0;
+  const int64_t obs0 = N > 0 ? b->obs_offsets[c0] : 0;
+  P.n_obs = N > 0 ? b->obs_offsets[c1] - obs0 : 0;
   P.valid = true;
   if (N == 0) return BWQ_OK;
   CK(cudaSetDevice(ctx->device));
@@ -349,13 +354,13 @@ static int dm_prepare_impl(bwq_ctx* ctx, const bwq_batch* b, int32_t* out_status
   lo.low_qubits = ctx->opt.low_qubits > 0 ? ctx->opt.low_qubits : 2;
   lo.direct = (ctx->opt.flags & BWQ_OPT_NO_DIRECT_LOAD ? 0 : kPassLoadDirect) | (ctx->opt.flags & BWQ_OPT_NO_DIRECT_STORE ? 0 : kPassStoreDirect);
   P.tile_qubits = lo.tile_qubits;
-  std::vector<CircuitProgram> progs(N);
-  parallel_for(N, host_threads(ctx), [&](int c) { lower_dm_circuit(ctx->noise, *b, c, lo, &progs[c]); });
+  std::vector<CircuitProgram> progs(N);  // progs[c] <-> batch circuit c0 + c
+  parallel_for(N, host_threads(ctx), [&](int c) { lower_dm_circuit(ctx->noise, *b, c0 + c, lo, &progs[c]); });
 
   std::vector<int> order;
   order.reserve(N);
   for (int c = 0; c < N; ++c) {
-    out_status[c] = progs[c].status;
+    out_status[c0 + c] = progs[c].status;
     if (progs[c].status == 0 && !progs[c].sweeps.empty()) order.push_back(c);
   }
   // wide first, then by sweep count (so the circuits of a chunk finish together)
@@ -374,7 +379,7 @@ static int dm_prepare_impl(bwq_ctx* ctx, const bwq_batch* b, int32_t* out_status
     sw_off[i + 1] = sw_off[i] + (int64_t)p.sweeps.size();
     pg_off[i + 1] = pg_off[i] + (int64_t)p.prog.size();
     tm_off[i + 1] = tm_off[i] + (int64_t)p.term_index.size();
-    P.ob_off[i + 1] = P.ob_off[i] + (b->obs_offsets[order[i] + 1] - b->obs_offsets[order[i]]);
+    P.ob_off[i + 1] = P.ob_off[i] + (b->obs_offsets[c0 + order[i] + 1] - b->obs_offsets[c0 + order[i]]);
   }
   if (sw_off[M] > INT32_MAX || pg_off[M] / 2 >= (int64_t(1) << 32))
     return fail(ctx, BWQ_ERR_ARG, "batch too large for 32-bit program indices; split the batch");
@@ -385,11 +390,8 @@ static int dm_prepare_impl(bwq_ctx* ctx, const bwq_batch* b, int32_t* out_status
   P.o_tcoef = blob.add(sizeof(double) * (size_t)tm_off[M]);
   P.o_obs = blob.add(sizeof(int64_t) * 4 * (size_t)P.ob_off[M]);
   P.blob_bytes = blob.total;
-  if (M > 0) {
-    CK(ctx->h_prog.reserve(blob.total));
-    CK(ctx->d_prog.reserve(blob.total));
-  }
-  char* hb = (char*)ctx->h_prog.p;
+  if (M > 0) CK(sl.h_prog.reserve(blob.total));
+  char* hb = (char*)sl.h_prog.p;
   parallel_for(M, host_threads(ctx), [&](int i) {
     const int c = order[i];
     const CircuitProgram& p = progs[c];
@@ -405,30 +407,26 @@ static int dm_prepare_impl(bwq_ctx* ctx, const bwq_batch* b, int32_t* out_status
     }
     // observables: {term_begin, term_end, chunk-local slot (filled below), out_index}
     int64_t* od = (int64_t*)(hb + P.o_obs) + 4 * P.ob_off[i];
-    const int64_t ob0 = b->obs_offsets[c], ob1 = b->obs_offsets[c + 1];
+    const int64_t ob0 = b->obs_offsets[c0 + c], ob1 = b->obs_offsets[c0 + c + 1];
     const int64_t tb = b->term_offsets[ob0];
     for (int64_t o = ob0; o < ob1; ++o) {
       int64_t* d = od + 4 * (o - ob0);
       d[0] = tm_off[i] + (b->term_offsets[o] - tb);
       d[1] = tm_off[i] + (b->term_offsets[o + 1] - tb);
       d[2] = i;
-      d[3] = o;
+      d[3] = o - obs0;
     }
   });
   for (int i = 0; i < M; ++i) { P.n_gates += progs[order[i]].n_gates; P.n_passes += progs[order[i]].n_passes; }
 
   // ---- chunk plan: circuits of equal width, as many resident states as the budget allows
-  size_t free_b = 0, total_b = 0;
-  CK(cudaMemGetInfo(&free_b, &total_b));
-  int64_t budget = ctx->opt.max_state_bytes > 0 ? ctx->opt.max_state_bytes
-                                                 : (int64_t)((free_b + ctx->d_states.cap) * 0.8);
   for (int i = 0; i < M;) {
     const int nd = progs[order[i]].n_digits;
     const int64_t sbytes = (int64_t)sizeof(double) << (2 * nd);
     int64_t fit = budget / sbytes;
     if (fit < 1) {
       int j = i;
-      while (j < M && progs[order[j]].n_digits == nd) out_status[order[j++]] = BWQ_CIRC_TOO_WIDE;
+      while (j < M && progs[order[j]].n_digits == nd) out_status[c0 + order[j++]] = BWQ_CIRC_TOO_WIDE;
       i = j;
       continue;
     }
@@ -487,19 +485,27 @@ static int dm_prepare_impl(bwq_ctx* ctx, const bwq_batch* b, int32_t* out_status
   // circuits the GPU does not touch: failures (NaN) and circuits without any gate (state stays
   // |0..0>: <P> = 1 for I/Z strings, 0 otherwise)
   for (int c = 0; c < N; ++c) {
-    const bool gpu = out_status[c] == 0 && !progs[c].sweeps.empty();
+    const bool gpu = out_status[c0 + c] == 0 && !progs[c].sweeps.empty();
     if (gpu) continue;
-    for (int64_t o = b->obs_offsets[c]; o < b->obs_offsets[c + 1]; ++o) {
+    for (int64_t o = b->obs_offsets[c0 + c]; o < b->obs_offsets[c0 + c + 1]; ++o) {
       double v = 0.0;
-      if (out_status[c] == 0)
+      if (out_status[c0 + c] == 0)
         for (int64_t t = b->term_offsets[o]; t < b->term_offsets[o + 1]; ++t)
           if (b->term_x[t] == 0) v += b->term_coeff[t];
-      P.host_fix.push_back({o, out_status[c] == 0 ? v : std::nan("")});
+      P.host_fix.push_back({o - obs0, out_status[c0 + c] == 0 ? v : std::nan("")});
     }
   }
   P.lower_ms = now_ms() - t0;
+  return BWQ_OK;
+}
 
-  // ---- upload
+// Device part of the preparation: buffers + one H2D copy of the slot's program blob.
+static int dm_upload_impl(bwq_ctx* ctx, bwq_ctx::DmSlot& sl, bool sync) {
+  DmPlan& P = sl.plan;
+  const size_t blob_total = P.blob_bytes;
+  const char* hb = (const char*)sl.h_prog.p;
+  const bool have = !P.chunks.empty();
+  if (have) CK(sl.d_prog.reserve(blob_total));
   if (P.max_chunk_bytes > 0) CK(ctx->d_states.reserve((size_t)P.max_chunk_bytes));
   if (P.n_obs > 0) {
     CK(ctx->d_out.reserve(sizeof(double) * (size_t)P.n_obs));
@@ -507,12 +513,37 @@ static int dm_prepare_impl(bwq_ctx* ctx, const bwq_batch* b, int32_t* out_status
   }
   cudaStream_t st = ctx->stream;
   CK(cudaEventRecord(ctx->ev[0], st));
-  if (M > 0) CK(cudaMemcpyAsync(ctx->d_prog.p, hb, blob.total, cudaMemcpyHostToDevice, st));
+  if (have) CK(cudaMemcpyAsync(sl.d_prog.p, hb, blob_total, cudaMemcpyHostToDevice, st));
   CK(cudaEventRecord(ctx->ev[1], st));
-  CK(cudaStreamSynchronize(st));
-  float ms = 0.f;
-  CK(cudaEventElapsedTime(&ms, ctx->ev[0], ctx->ev[1]));
-  P.h2d_ms = ms;
+  if (sync) {
+    CK(cudaStreamSynchronize(st));
+    float ms = 0.f;
+    CK(cudaEventElapsedTime(&ms, ctx->ev[0], ctx->ev[1]));
+    P.h2d_ms = ms;
+  }
+  return BWQ_OK;
+}
+
+static int64_t dm_state_budget(bwq_ctx* ctx, int64_t* out) {
+  if (ctx->opt.max_state_bytes > 0) { *out = ctx->opt.max_state_bytes; return BWQ_OK; }
+  size_t free_b = 0, total_b = 0;
+  CK(cudaSetDevice(ctx->device));
+  CK(cudaMemGetInfo(&free_b, &total_b));
+  *out = (int64_t)((free_b + ctx->d_states.cap) * 0.8);
+  return BWQ_OK;
+}
+
+static int dm_prepare_impl(bwq_ctx* ctx, const bwq_batch* b, int32_t* out_status) {
+  if (!ctx) return BWQ_ERR_ARG;
+  int rc = check_batch(ctx, b, out_status, out_status);
+  if (rc) return rc;
+  ctx->stats = bwq_stats{};
+  int64_t budget = 0;
+  if ((rc = (int)dm_state_budget(ctx, &budget))) return rc;
+  bwq_ctx::DmSlot& sl = ctx->dm[0];
+  if ((rc = dm_lower_impl(ctx, sl, b, 0, b->n_circuits, out_status, budget))) return rc;
+  if (b->n_circuits > 0 && (rc = dm_upload_impl(ctx, sl, true))) return rc;
+  const DmPlan& P = sl.plan;
   ctx->stats.lower_ms = P.lower_ms;
   ctx->stats.h2d_ms = P.h2d_ms;
   ctx->stats.h2d_bytes = (int64_t)P.blob_bytes;
@@ -521,9 +552,9 @@ static int dm_prepare_impl(bwq_ctx* ctx, const bwq_batch* b, int32_t* out_status
   return BWQ_OK;
 }
 
-static int dm_execute_impl(bwq_ctx* ctx, double* out_vals, bool out_on_device) {
+static int dm_execute_impl(bwq_ctx* ctx, bwq_ctx::DmSlot& sl, double* out_vals, bool out_on_device) {
   if (!ctx || !out_vals) return BWQ_ERR_ARG;
-  DmPlan& P = ctx->plan;
+  DmPlan& P = sl.plan;
   if (!P.valid) return fail(ctx, BWQ_ERR_ARG, "bwq_dm_execute: no prepared batch (call bwq_dm_prepare first)");
   CK(cudaSetDevice(ctx->device));
   bwq_stats& S = ctx->stats;
@@ -532,7 +563,7 @@ static int dm_execute_impl(bwq_ctx* ctx, double* out_vals, bool out_on_device) {
   S.n_gates = P.n_gates; S.n_passes = P.n_passes;
   cudaStream_t st = ctx->stream;
   double* d_out = out_on_device ? out_vals : (double*)ctx->d_out.p;
-  const char* db = (const char*)ctx->d_prog.p;
+  const char* db = (const char*)sl.d_prog.p;
   CK(cudaEventRecord(ctx->ev[1], st));
   if (P.n_obs > 0) CK(cudaMemsetAsync(d_out, 0, sizeof(double) * (size_t)P.n_obs, st));
   const size_t n_ev = std::min(P.chunks.size(), ctx->chunk_ev.size() / 2);
@@ -608,18 +639,61 @@ extern "C" int bwq_dm_prepare(bwq_ctx* ctx, const bwq_batch* b, int32_t* out_sta
   if (!out_status) return fail(ctx, BWQ_ERR_ARG, "null status");
   return dm_prepare_impl(ctx, b, out_status);
 }
-extern "C" int bwq_dm_execute(bwq_ctx* ctx, double* out_vals) { return dm_execute_impl(ctx, out_vals, false); }
-extern "C" int bwq_dm_execute_device_out(bwq_ctx* ctx, double* d_out_vals) { return dm_execute_impl(ctx, d_out_vals, true); }
+extern "C" int bwq_dm_execute(bwq_ctx* ctx, double* out_vals) { return ctx ? dm_execute_impl(ctx, ctx->dm[0], out_vals, false) : BWQ_ERR_ARG; }
+extern "C" int bwq_dm_execute_device_out(bwq_ctx* ctx, double* d_out_vals) { return ctx ? dm_execute_impl(ctx, ctx->dm[0], d_out_vals, true) : BWQ_ERR_ARG; }
+
+// Whole-batch run from host buffers.  Large batches are cut into segments of consecutive circuits
+// and software-pipelined over the two program slots: while the GPU sweeps segment k, the host
+// threads lower segment k+1 (K0 is otherwise 20-25 % of the call for 10-qubit circuits).  The
+// values do not depend on the segmentation (circuits are independent).
+static int dm_run_impl(bwq_ctx* ctx, const bwq_batch* b, double* out_vals, int32_t* out_status, bool out_on_device) {
+  if (!ctx) return BWQ_ERR_ARG;
+  int rc = check_batch(ctx, b, out_status, out_status);
+  if (rc) return rc;
+  ctx->stats = bwq_stats{};
+  const int N = b->n_circuits;
+  int64_t budget = 0;
+  if ((rc = (int)dm_state_budget(ctx, &budget))) return rc;
+  // segments: at least kMinSeg circuits each, at most kMaxSegs of them
+  constexpr int kMinSeg = 128, kMaxSegs = 16;
+  const int n_seg = (ctx->opt.flags & BWQ_OPT_NO_PIPELINE) ? 1 : std::max(1, std::min(kMaxSegs, N / kMinSeg));
+  auto seg_begin = [&](int k) { return (int)((int64_t)N * k / n_seg); };
+  bwq_stats total{};
+  int lower_rc = dm_lower_impl(ctx, ctx->dm[0], b, seg_begin(0), seg_begin(1), out_status, budget);
+  if (lower_rc) return lower_rc;
+  for (int k = 0; k < n_seg; ++k) {
+    bwq_ctx::DmSlot& cur = ctx->dm[k & 1];
+    std::thread helper;
+    int next_rc = BWQ_OK;
+    if (k + 1 < n_seg)
+      helper = std::thread([&, k] {
+        next_rc = dm_lower_impl(ctx, ctx->dm[(k + 1) & 1], b, seg_begin(k + 1), seg_begin(k + 2), out_status, budget);
+      });
+    const int64_t obs0 = N > 0 ? b->obs_offsets[seg_begin(k)] : 0;
+    rc = seg_begin(k + 1) > seg_begin(k) ? dm_upload_impl(ctx, cur, n_seg == 1) : BWQ_OK;
+    if (!rc) rc = dm_execute_impl(ctx, cur, out_vals + obs0, out_on_device);
+    if (helper.joinable()) helper.join();
+    if (rc) return rc;
+    if (next_rc) return next_rc;
+    const bwq_stats& S = ctx->stats;
+    total.n_sweep_launches += S.n_sweep_launches; total.n_state_sweeps += S.n_state_sweeps;
+    total.n_passes += S.n_passes; total.n_gates += S.n_gates; total.state_bytes_swept += S.state_bytes_swept;
+    total.n_other_launches += S.n_other_launches; total.lower_ms += cur.plan.lower_ms; total.h2d_ms += cur.plan.h2d_ms;
+    total.kernel_ms += S.kernel_ms; total.d2h_ms += S.d2h_ms; total.sweep_kernel_ms += S.sweep_kernel_ms;
+    total.h2d_bytes += S.h2d_bytes; total.d2h_bytes += S.d2h_bytes;
+  }
+  ctx->stats = total;
+  if (n_seg > 1) ctx->dm[0].plan.valid = false;  // slot 0 no longer holds a whole prepared batch
+  return BWQ_OK;
+}
 
 extern "C" int bwq_dm_run(bwq_ctx* ctx, const bwq_batch* b, double* out_vals, int32_t* out_status) {
   if (!out_vals || !out_status) return fail(ctx, BWQ_ERR_ARG, "null out/status");
-  int rc = dm_prepare_impl(ctx, b, out_status);
-  return rc ? rc : dm_execute_impl(ctx, out_vals, false);
+  return dm_run_impl(ctx, b, out_vals, out_status, false);
 }
 extern "C" int bwq_dm_run_device_out(bwq_ctx* ctx, const bwq_batch* b, double* d_out_vals, int32_t* out_status) {
   if (!d_out_vals || !out_status) return fail(ctx, BWQ_ERR_ARG, "null out/status");
-  int rc = dm_prepare_impl(ctx, b, out_status);
-  return rc ? rc : dm_execute_impl(ctx, d_out_vals, true);
+  return dm_run_impl(ctx, b, d_out_vals, out_status, true);
 }
 
 // ------------------------------------------------------------------------------------------------
