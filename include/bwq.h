@@ -149,7 +149,9 @@ int bwq_set_noise_table(bwq_ctx* ctx, const bwq_noise_table* table);
 
 /* Noisy values: density-matrix evolution of every circuit under the installed noise table
  * (Aer Estimator, method=density_matrix, approximation=True, shots=None).
- * out_vals[n_observables] (order of term_offsets), out_status[n_circuits]. */
+ * out_vals[n_observables] (order of term_offsets), out_status[n_circuits].  Batches of >= 256
+ * circuits are cut into segments and pipelined: the host lowers segment k+1 while the GPU sweeps
+ * segment k (BWQ_OPT_NO_PIPELINE turns this off). */
 int bwq_dm_run(bwq_ctx* ctx, const bwq_batch* batch, double* out_vals, int32_t* out_status);
 /* Split form of bwq_dm_run: prepare lowers the batch on the host and uploads the program (it
  * stays resident in HBM inside the ctx); execute runs the kernels and returns the values, and may
@@ -165,6 +167,14 @@ int bwq_sv_execute(bwq_ctx* ctx, double* out_vals);
 /* Same as bwq_dm_run / bwq_sv_run but out_vals is a DEVICE pointer (e.g. a torch tensor's
  * data_ptr()) -- zero-copy label hand-off; returns after the work is enqueued and synchronised. */
 int bwq_dm_run_device_out(bwq_ctx* ctx, const bwq_batch* batch, double* d_out_vals, int32_t* out_status);
+/* Ideal AND noisy values of every circuit in one call: what create_estimator_meas_data
+ * (blackwater/data/utils.py:418-431) returns per circuit, for the whole batch.  The statevector
+ * side runs on a companion context (own stream and buffers) concurrently with the density-matrix
+ * pipeline, so its lowering and launches hide behind the sweeps.  Equivalent to bwq_sv_run into
+ * out_ideal / status_ideal and bwq_dm_run into out_noisy / status_noisy; bwq_get_stats reports the
+ * density-matrix side. */
+int bwq_meas_data_run(bwq_ctx* ctx, const bwq_batch* batch, double* out_ideal, double* out_noisy,
+                      int32_t* status_ideal, int32_t* status_noisy);
 int bwq_get_stats(const bwq_ctx* ctx, bwq_stats* out);
 int bwq_sync(bwq_ctx* ctx);
 

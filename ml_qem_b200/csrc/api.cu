@@ -145,6 +145,7 @@ struct bwq_ctx {
   struct DmSlot { DmPlan plan; PinBuf h_prog; DevBuf d_prog; } dm[2];
   SvPlan sv_plan;
   std::vector<cudaEvent_t> chunk_ev;  // begin/end of each chunk's sweep launches
+  bwq_ctx* companion = nullptr;       // statevector side of bwq_meas_data_run (created on first use)
   size_t smem_optin = 0;
   int sm_count = 0;
 };
@@ -655,7 +656,7 @@ static int dm_run_impl(bwq_ctx* ctx, const bwq_batch* b, double* out_vals, int32
   int64_t budget = 0;
   if ((rc = (int)dm_state_budget(ctx, &budget))) return rc;
   // segments: at least kMinSeg circuits each, at most kMaxSegs of them
-  constexpr int kMinSeg = 128, kMaxSegs = 16;
+  constexpr int kMinSeg = 128, kMaxSegs = 8;
   const int n_seg = (ctx->opt.flags & BWQ_OPT_NO_PIPELINE) ? 1 : std::max(1, std::min(kMaxSegs, N / kMinSeg));
   auto seg_begin = [&](int k) { return (int)((int64_t)N * k / n_seg); };
   bwq_stats total{};
@@ -1111,6 +1112,24 @@ extern "C" int bwq_sv_run(bwq_ctx* ctx, const bwq_batch* b, double* out_vals, in
   if (!out_vals || !out_status) return fail(ctx, BWQ_ERR_ARG, "null out/status");
   int rc = sv_prepare_impl(ctx, b, out_status);
   return rc ? rc : sv_execute_impl(ctx, out_vals);
+}
+
+extern "C" int bwq_meas_data_run(bwq_ctx* ctx, const bwq_batch* b, double* out_ideal, double* out_noisy,
+                                 int32_t* status_ideal, int32_t* status_noisy) {
+  if (!ctx) return BWQ_ERR_ARG;
+  if (!out_ideal || !out_noisy || !status_ideal || !status_noisy) return fail(ctx, BWQ_ERR_ARG, "null out/status");
+  if (!ctx->companion) {
+    int rc = bwq_create(ctx->device, &ctx->companion);
+    if (rc) return fail(ctx, rc, "companion context: %s", bwq_last_error(nullptr));
+  }
+  ctx->companion->opt = ctx->opt;
+  int rc_sv = BWQ_OK;
+  std::thread ideal([&] { rc_sv = bwq_sv_run(ctx->companion, b, out_ideal, status_ideal); });
+  const int rc_dm = bwq_dm_run(ctx, b, out_noisy, status_noisy);
+  ideal.join();
+  if (rc_dm) return rc_dm;
+  if (rc_sv) return fail(ctx, rc_sv, "statevector side: %s", bwq_last_error(ctx->companion));
+  return BWQ_OK;
 }
 
 // ------------------------------------------------------------------------------------------------

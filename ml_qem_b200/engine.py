@@ -59,7 +59,7 @@ class _Stats(C.Structure):
 
 EXPORTS = [
     "bwq_version", "bwq_create", "bwq_destroy", "bwq_last_error", "bwq_set_options", "bwq_set_noise_table",
-    "bwq_dm_run", "bwq_sv_run", "bwq_dm_run_device_out", "bwq_dm_prepare", "bwq_dm_execute", "bwq_dm_execute_device_out", "bwq_sv_prepare", "bwq_sv_execute", "bwq_get_stats", "bwq_sync", "bwq_lower_dm",
+    "bwq_dm_run", "bwq_sv_run", "bwq_meas_data_run", "bwq_dm_run_device_out", "bwq_dm_prepare", "bwq_dm_execute", "bwq_dm_execute_device_out", "bwq_sv_prepare", "bwq_sv_execute", "bwq_get_stats", "bwq_sync", "bwq_lower_dm",
     "bwq_program_free", "bwq_program_sizes", "bwq_program_read",
     "bwq_svx_lower", "bwq_svx_free", "bwq_svx_sizes", "bwq_svx_read", "bwq_svx_upload", "bwq_svx_run_segment",
     "bwq_svx_bytes",
@@ -85,6 +85,7 @@ def load_library(path=None):
     lib.bwq_set_noise_table.argtypes = [C.c_void_p, C.POINTER(_NoiseTable)]
     for f in (lib.bwq_dm_run, lib.bwq_sv_run, lib.bwq_dm_run_device_out):
         f.argtypes = [C.c_void_p, C.POINTER(_Batch), C.c_void_p, C.c_void_p]
+    lib.bwq_meas_data_run.argtypes = [C.c_void_p, C.POINTER(_Batch), C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p]
     lib.bwq_dm_prepare.argtypes = [C.c_void_p, C.POINTER(_Batch), C.c_void_p]
     lib.bwq_dm_execute.argtypes = [C.c_void_p, C.c_void_p]
     lib.bwq_sv_prepare.argtypes = [C.c_void_p, C.POINTER(_Batch), C.c_void_p]
@@ -311,6 +312,21 @@ class Engine:
     def run_sv(self, batch):
         """Ideal values (statevector) -> (values, status)."""
         return self._run(self._lib.bwq_sv_run, batch, "bwq_sv_run")
+
+    def run_meas_data(self, batch):
+        """(ideal, noisy) values of every circuit in one call -- the batch form of the reference's
+        ``create_estimator_meas_data`` (blackwater/data/utils.py:418-431); the statevector side
+        runs concurrently with the density-matrix pipeline.  -> (ideal, noisy, status_ideal, status_noisy)"""
+        ideal = np.empty(batch.n_observables, dtype=np.float64)
+        noisy = np.empty(batch.n_observables, dtype=np.float64)
+        st_i = np.zeros(batch.n_circuits, dtype=np.int32)
+        st_n = np.zeros(batch.n_circuits, dtype=np.int32)
+        st = batch.c_struct()
+        with self._lock:
+            self._check(self._lib.bwq_meas_data_run(self._ctx, C.byref(st), ideal.ctypes.data_as(C.c_void_p),
+                                                    noisy.ctypes.data_as(C.c_void_p), st_i.ctypes.data_as(C.c_void_p),
+                                                    st_n.ctypes.data_as(C.c_void_p)), "bwq_meas_data_run")
+        return ideal, noisy, st_i, st_n
 
     def run_dm_into(self, batch, device_ptr):
         """Writes the values into device memory at ``device_ptr`` (e.g. torch ``tensor.data_ptr()``

@@ -260,3 +260,42 @@ def test_svx_simulated_ranks_on_one_gpu(engine_gpu, g):
         ref = helpers.oracle_sv_values(circ, obs)
         assert np.max(np.abs(vals.cpu().numpy() - ref)) <= TOL
         prog.close()
+
+
+def test_pipelined_run_and_meas_data_call(engine_gpu):
+    """bwq_dm_run cuts batches of >= 256 circuits into pipelined segments (mixed widths, an empty
+    circuit and a failing circuit inside): the values must be bit-identical to the unsegmented run
+    and to the prepared/resident path, and bwq_meas_data_run == (bwq_sv_run, bwq_dm_run).
+    A sample is checked against the oracle."""
+    lima = backends.fake_lima()
+    nm = noise.from_backend(lima)
+    on = helpers.oracle_noise("fakelima")
+    rng = np.random.default_rng(23)
+    circs, obs = [], []
+    for i in range(600):
+        if i == 301:
+            c = F.random_basis_circuit(5, 0, rng, lima.coupling_map)  # no gate at all: host-side value
+        else:
+            c = F.random_basis_circuit(5, int(rng.integers(1, 40)), rng, lima.coupling_map)
+        circs.append(c)
+        obs.append([[(l, float(rng.normal()))] for l in _labels(rng, 5, int(rng.integers(1, 4)))])
+    batch = engine.encode_batch(circs, obs)
+    engine_gpu.set_noise(nm)
+    engine_gpu.set_options()
+    v_pipe, st_pipe = engine_gpu.run_dm(batch)
+    assert engine_gpu.stats()["n_sweep_launches"] > 0
+    engine_gpu.set_options(flags=4)  # BWQ_OPT_NO_PIPELINE
+    v_one, st_one = engine_gpu.run_dm(batch)
+    engine_gpu.set_options()
+    assert not st_pipe.any() and not st_one.any()
+    assert np.array_equal(v_pipe, v_one)
+    assert not engine_gpu.prepare_dm(batch).any()
+    assert np.array_equal(engine_gpu.execute_dm(), v_pipe)
+    v_sv, st_sv = engine_gpu.run_sv(batch)
+    ideal, noisy, st_i, st_n = engine_gpu.run_meas_data(batch)
+    assert not st_i.any() and not st_n.any()
+    assert np.array_equal(ideal, v_sv) and np.array_equal(noisy, v_pipe)
+    offs = np.cumsum([0] + [len(o) for o in obs])
+    for i in (0, 150, 299, 300, 301, 302, 450, 599):
+        ref = helpers.oracle_dm_values(circs[i], obs[i], on)
+        assert np.max(np.abs(v_pipe[offs[i]:offs[i + 1]] - ref)) <= TOL, i
