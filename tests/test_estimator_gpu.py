@@ -106,6 +106,31 @@ def test_learning_style_decorator_wraps_the_estimator(lib):
     assert all(m["simulator_metadata"]["method"] == "density_matrix" for m in res.metadata)
 
 
+def test_learning_module_on_the_engine_estimator(lib):
+    """ml_qem_b200.learning.learning() on the real engine estimator: the mitigated values are the
+    model applied to the engine's noisy values, term by term (estimator.py:128-148), computed with
+    one batched model call."""
+    from sklearn.linear_model import Ridge
+
+    from ml_qem_b200 import learning as L
+    from ml_qem_b200.features import backend_properties_v1, encode_data
+
+    lima = backends.fake_lima()
+    props = backend_properties_v1(lima)
+    rng = np.random.default_rng(2)
+    circs = [F.tfim_circuit(4, s, 0.3 + 0.1 * s, layout=[0, 1, 3, 4], num_physical=5) for s in (1, 2, 3)]
+    obs = [[("IIIIZ", 1.0), ("IIIZI", -0.5)], "ZIIII", [("ZIIIZ", 2.0)]]
+    width = encode_data([circs[0]], props, [[0.0]], [[0.0]], 1, L.encode_pauli_sum_op("IIIIZ"))[0].shape[1]
+    model = Ridge().fit(rng.normal(size=(40, width)), rng.normal(size=40))
+    proc = L.ScikitLearningModelProcessor(model, lima)
+    est = L.learning(B200Estimator, proc, skip_transpile=True, backend=lima)(backend=lima)
+    res = est.run(circs, obs).result()
+    base = B200Estimator(backend=lima).run(circs, obs).result().values
+    want = [proc.process(v, c, o, ()) for v, c, o in zip(base, circs, obs)]
+    assert np.allclose(res.values, want, atol=1e-12)
+    assert [m["original_value"] for m in res.metadata] == list(base)
+
+
 def test_zne_strategy_matches_folded_circuits_and_extrapolates(lib):
     lima = backends.fake_lima()
     ZNEEstimator = zne(B200Estimator)

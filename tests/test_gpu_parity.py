@@ -299,3 +299,57 @@ def test_pipelined_run_and_meas_data_call(engine_gpu):
     for i in (0, 150, 299, 300, 301, 302, 450, 599):
         ref = helpers.oracle_dm_values(circs[i], obs[i], on)
         assert np.max(np.abs(v_pipe[offs[i]:offs[i + 1]] - ref)) <= TOL, i
+
+
+def test_dm_14q_full_size_factorised(engine_gpu):
+    """BASELINE cfg3 size (14 qubits, 2.15 GB Pauli-basis state; the numpy oracle stops near 9).
+    Size-independent property: a circuit acting only inside the pairs (0,1), (2,3), ... leaves a
+    product state, so Tr(rho P) is the product of the pair expectations -- each one computed by the
+    oracle on the 2-qubit sub-circuit with the device noise of those physical qubits."""
+    from ml_qem_b200.circuit import Circuit
+
+    n = 14
+    be = backends.synthetic_chain(n, seed=14)
+    nm = noise.from_backend(be)
+    from oracle import noise_model as onm
+    on = onm.from_backend(be.to_dict())
+    rng = np.random.default_rng(14)
+    full = Circuit(n)
+    blocks = []
+    for k in range(n // 2):
+        a, b = 2 * k, 2 * k + 1
+        sub = Circuit(n)
+        for _ in range(int(rng.integers(6, 14))):
+            r = int(rng.integers(0, 4))
+            if r == 0:
+                op = ("rz", (int(rng.choice([a, b])),), (float(rng.uniform(-3, 3)),))
+            elif r == 1:
+                op = ("sx", (int(rng.choice([a, b])),), ())
+            else:
+                op = ("cx", (a, b) if rng.integers(0, 2) else (b, a), ())
+            sub.ops.append(op)
+        blocks.append(sub)
+    # interleave the blocks' gates (program order inside a block is kept)
+    cursors = [0] * len(blocks)
+    while any(c < len(bk.ops) for c, bk in zip(cursors, blocks)):
+        k = int(rng.integers(0, len(blocks)))
+        if cursors[k] < len(blocks[k].ops):
+            full.ops.append(blocks[k].ops[cursors[k]])
+            cursors[k] += 1
+    labels = _labels(rng, n, 12) + ["Z" * n, "I" * n]
+    obs = [[(l, 1.0)] for l in labels]
+    engine_gpu.set_noise(nm)
+    engine_gpu.set_options()
+    vals, status = engine_gpu.run_dm(engine.encode_batch([full], [obs]))
+    assert not status.any()
+    ref = np.ones(len(labels))
+    for k, sub in enumerate(blocks):
+        a, b = 2 * k, 2 * k + 1
+        sub_obs = []
+        for l in labels:
+            chars = ["I"] * n
+            chars[n - 1 - a], chars[n - 1 - b] = l[n - 1 - a], l[n - 1 - b]
+            sub_obs.append([("".join(chars), 1.0)])
+        c2, o2, n2 = helpers.compact(sub, sub_obs, on)
+        ref *= helpers.oracle_dm_values(c2, o2, n2)
+    assert np.max(np.abs(vals - ref)) <= TOL
