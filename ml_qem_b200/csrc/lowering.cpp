@@ -232,18 +232,25 @@ void ptm_from_unitary2(const double* uu, double* r) {
 
 // ----------------------------------------------------------------------------- 4x4 helpers
 static void mat4_identity(double* m) { for (int i = 0; i < 16; ++i) m[i] = (i % 5 == 0) ? 1.0 : 0.0; }
-static void mat4_mul(const double* a, const double* b, double* out) {  // out = a*b (out may alias b)
-  double t[16];
-  for (int i = 0; i < 4; ++i) for (int j = 0; j < 4; ++j) {
-    double s = 0;
-    for (int k = 0; k < 4; ++k) s += a[i * 4 + k] * b[k * 4 + j];
-    t[i * 4 + j] = s;
-  }
-  std::memcpy(out, t, sizeof t);
+// out = a*b (out may alias a or b).  Row i of the product is a linear combination of the rows of
+// b, evaluated 4 wide in the order ((a0 b0 + a1 b1) + a2 b2) + a3 b3 -- the summation order of
+// the scalar triple loop, so the programs stay bit-identical.  K0 spends most of its time here
+// (two products per 1-qubit gate).
+typedef double v4d __attribute__((vector_size(32), aligned(8)));
+static inline void mat4_mul(const double* a, const double* b, double* out) {
+  v4d b0, b1, b2, b3, r[4];
+  std::memcpy(&b0, b, 32); std::memcpy(&b1, b + 4, 32); std::memcpy(&b2, b + 8, 32); std::memcpy(&b3, b + 12, 32);
+  for (int i = 0; i < 4; ++i) r[i] = ((a[4 * i] * b0 + a[4 * i + 1] * b1) + a[4 * i + 2] * b2) + a[4 * i + 3] * b3;
+  std::memcpy(out, r, sizeof r);
 }
-
-// PTM of a 1-qubit gate; closed forms for the backend basis (checked against the generic path
-// by tests/test_lowering.py).
+// out = R * b for R = identity outside rows/columns 1, 2 (rz, p, z, s, t: a rotation of X, Y)
+static inline void mat4_rot_mul(double c, double sn, const double* b, double* out) {
+  v4d b1, b2;
+  std::memcpy(&b1, b + 4, 32); std::memcpy(&b2, b + 8, 32);
+  const v4d r1 = c * b1 + (-sn) * b2, r2 = sn * b1 + c * b2;
+  if (out != b) { std::memcpy(out, b, 32); std::memcpy(out + 12, b + 12, 32); }
+  std::memcpy(out + 4, &r1, 32); std::memcpy(out + 8, &r2, 32);
+}
 static bool gate_ptm1(uint16_t op, const double* p, double* r) {
   switch (op) {
     case BWQ_G_ID: mat4_identity(r); return true;
@@ -383,9 +390,14 @@ void lower_dm_circuit(const NoiseTable& noise, const bwq_batch& b, int c, const 
     const double* par = npar ? b.params + op.param_idx : nullptr;
     if (!gate_is_2q(op.opcode)) {
       double r[16];
-      if (!gate_ptm1(op.opcode, par, r)) { out->status = BWQ_CIRC_BAD_OP; return; }
       int d = digit_of[op.q0];
-      if (const NoiseEntry* ne = noise.find(op.opcode, op.q0, 255)) mat4_mul(&noise.data[ne->off], r, r);
+      const NoiseEntry* ne = noise.find(op.opcode, op.q0, 255);
+      if (!ne && has[d] && (op.opcode == BWQ_G_RZ || op.opcode == BWQ_G_P)) {  // noise-free virtual rotation
+        mat4_rot_mul(std::cos(par[0]), std::sin(par[0]), &pend[16 * d], &pend[16 * d]);
+        continue;
+      }
+      if (!gate_ptm1(op.opcode, par, r)) { out->status = BWQ_CIRC_BAD_OP; return; }
+      if (ne) mat4_mul(&noise.data[ne->off], r, r);
       if (has[d]) mat4_mul(r, &pend[16 * d], &pend[16 * d]);
       else { std::memcpy(&pend[16 * d], r, sizeof r); has[d] = 1; }
       continue;
