@@ -315,8 +315,15 @@ struct ZexpLaunch {
   double* partial;             // [group][split][32]
 };
 
+// A thread owns 8 amplitudes per unit of 2048 (index = unit base | warp << 8 | j << 5 | lane, so
+// every load instruction of a warp covers 512 contiguous bytes).  Their probabilities go through an
+// 8-point Walsh-Hadamard transform over j (24 adds): w[c] = sum_j (-1)^popc(j & c) p_j is the
+// thread's signed sum for every term whose mask has c on index bits 5..7.  A term then costs one
+// parity of the remaining bits, one shared-memory read of w[c] (uniform c: conflict free) and one
+// add per EIGHT amplitudes instead of a parity, select and add per amplitude.
 __global__ void __launch_bounds__(kZexpThreads) sv_zexp_kernel(const ZexpLaunch L) {
   __shared__ double red[kZexpThreads / 32][kZexpTerms];
+  __shared__ double wsm[8][kZexpThreads];
   const int grp = blockIdx.x / L.splits, sp = blockIdx.x % L.splits;
   const int4 d = __ldg(reinterpret_cast<const int4*>(L.group_desc) + grp);
   const int nt = d.z;
@@ -327,15 +334,45 @@ __global__ void __launch_bounds__(kZexpThreads) sv_zexp_kernel(const ZexpLaunch 
 #pragma unroll
   for (int t = 0; t < kZexpTerms; ++t) acc[t] = 0.0;
   const double2* st = L.states + int64_t(d.x) * L.stride;
-  const int64_t chunk = (L.stride + L.splits - 1) / L.splits;
-  const int64_t i0 = chunk * sp, i1 = min(L.stride, i0 + chunk);
-  for (int64_t i = i0 + threadIdx.x; i < i1; i += kZexpThreads) {
-    const double2 a = __ldcs(st + i);
-    const double p = fma(a.x, a.x, a.y * a.y);
-    const uint32_t gi = L.hi_bits | uint32_t(i);
+  if ((L.stride & 2047) == 0) {
+    const int tid = threadIdx.x;
+    const int64_t units = L.stride >> 11;
+    const int64_t u0 = units * sp / L.splits, u1 = units * (sp + 1) / L.splits;
+    const uint32_t in_unit = (uint32_t(tid >> 5) << 8) | uint32_t(tid & 31);  // bits 5..7 = j = 0
+    for (int64_t u = u0; u < u1; ++u) {
+      const double2* src = st + (u << 11) + in_unit;
+      double w[8];
 #pragma unroll
-    for (int t = 0; t < kZexpTerms; ++t)
-      if (t < nt) acc[t] += (__popc(gi & mask[t]) & 1) ? -p : p;
+      for (int j = 0; j < 8; ++j) {
+        const double2 a = __ldcs(src + 32 * j);
+        w[j] = fma(a.x, a.x, a.y * a.y);
+      }
+#pragma unroll
+      for (int h = 1; h < 8; h <<= 1)
+#pragma unroll
+        for (int j = 0; j < 8; ++j)
+          if (!(j & h)) { const double x = w[j], y = w[j | h]; w[j] = x + y; w[j | h] = x - y; }
+#pragma unroll
+      for (int c = 0; c < 8; ++c) wsm[c][tid] = w[c];
+      const uint32_t gi = L.hi_bits | uint32_t(u << 11) | in_unit;
+#pragma unroll
+      for (int t = 0; t < kZexpTerms; ++t)
+        if (t < nt) {
+          const double x = wsm[(mask[t] >> 5) & 7u][tid];
+          acc[t] += (__popc(gi & mask[t] & ~0xe0u) & 1) ? -x : x;
+        }
+    }
+  } else {  // shards smaller than one unit (tests, simulated ranks)
+    const int64_t chunk = (L.stride + L.splits - 1) / L.splits;
+    const int64_t i0 = chunk * sp, i1 = min(L.stride, i0 + chunk);
+    for (int64_t i = i0 + threadIdx.x; i < i1; i += kZexpThreads) {
+      const double2 a = __ldcs(st + i);
+      const double p = fma(a.x, a.x, a.y * a.y);
+      const uint32_t gi = L.hi_bits | uint32_t(i);
+#pragma unroll
+      for (int t = 0; t < kZexpTerms; ++t)
+        if (t < nt) acc[t] += (__popc(gi & mask[t]) & 1) ? -p : p;
+    }
   }
 #pragma unroll
   for (int t = 0; t < kZexpTerms; ++t) {
