@@ -62,6 +62,16 @@ def build_workload(name, rank, scale=1.0):
         be = backends.synthetic_chain(n, seed=n, name=f"synthetic_chain_{n}q")
         desc = {"workload": name, "n_qubits": n, "register": n, "circuits_per_rank": len(circs),
                 "observables_per_circuit": len(obs), "trotter_steps": "1..10"}
+    elif name == "mixed6_12_dataset":
+        n_c = max(3, int(round(5000 * scale)))
+        circs, obs_each = F.config_mixed_dataset(n_circuits=n_c, seed=5 + 1000 * rank)
+        be = backends.synthetic_chain(12, seed=12, name="synthetic_chain_12q")
+        desc = {"workload": name, "n_qubits": 12, "active_qubits": "6..12 uniform", "register": 12, "circuits_per_rank": len(circs),
+                "families": "tfim / brickwork / random basis layers, equal parts",
+                "observables_per_circuit": "one single-Z per active qubit",
+                "note": "generation part of BASELINE configs[4] (50k circuits = 10 steps of this batch)",
+                "resident_state_bytes": int(sum(8 * 4 ** len({q for _, qs, _ in c.gate_ops() for q in qs}) for c in circs))}
+        return {"circuits": circs, "observables": obs_each, "backend": be, "desc": desc}
     else:
         raise SystemExit(f"unknown workload {name!r}")
     return {"circuits": circs, "observables": [obs] * len(circs), "backend": be, "desc": desc}
@@ -433,7 +443,7 @@ def main():
         "dtype": "f64", "data": "synthetic",
         "config": dict(wl["desc"], parallelism=f"circuit-sharded x{world}", state_layout="Pauli-basis density matrix, 8 B/element",
                        l2="per-rank working set %.1f GiB of resident states >> 126 MB L2 (no flush needed)" %
-                          (n_circ * 8 * 4 ** wl["desc"]["n_qubits"] / 2 ** 30),
+                          (wl["desc"].get("resident_state_bytes", n_circ * 8 * 4 ** wl["desc"]["n_qubits"]) / 2 ** 30),
                        timing="CUDA events on the engine stream summed over steps (max over ranks); wall %.1f ms/step" %
                               (1e3 * t_wall / steps)),
         "e2e": {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": h2d // steps, "d2h_bytes_per_step": d2h // steps,

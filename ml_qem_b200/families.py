@@ -243,3 +243,25 @@ def config_tfim_dm(n=14, n_circuits=8, seed=2, max_steps=10):
     layout = list(range(n))
     circs = [tfim_circuit(n, 1 + i % max_steps, float(rng.uniform(0, 1)), dt=0.25, layout=layout) for i in range(n_circuits)]
     return circs, tfim_observables(layout, n)
+
+
+def config_mixed_dataset(n_circuits=5000, seed=5, n_min=6, n_max=12, width=12):
+    """cfg5 (generation part): circuits of n ~ U{n_min..n_max} active qubits on a ``width``-qubit
+    chain table, families TFIM / brickwork / random basis layers in equal parts (SURVEY.md 8(d)
+    `e2e50k`), single-Z observables on the active qubits.  Returns (circuits, observables per circuit)."""
+    rng = np.random.default_rng(seed)
+    coupling = [(i, i + 1) for i in range(width - 1)] + [(i + 1, i) for i in range(width - 1)]
+    circs, obs = [], []
+    for i in range(n_circuits):
+        n = int(rng.integers(n_min, n_max + 1))
+        layout = list(range(n))
+        fam = i % 3
+        if fam == 0:
+            c = tfim_circuit(n, 1 + int(rng.integers(0, 6)), float(rng.uniform(0, 1)), dt=0.25, layout=layout, num_physical=width)
+        elif fam == 1:
+            c = brickwork_circuit(n, 1 + int(rng.integers(0, 5)), np.random.default_rng(int(rng.integers(0, 2 ** 31))), layout, width)
+        else:
+            c = random_basis_circuit(n, int(rng.integers(8 * n, 20 * n)), rng, [p for p in coupling if p[0] < n and p[1] < n], width)
+        circs.append(c)
+        obs.append(single_z_observables(layout, width))
+    return circs, obs
