@@ -3,7 +3,9 @@ import os, sys, time
 sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
 from ml_qem_b200 import backends, engine, families as F, noise
 eng = engine.Engine(0)
-out = [os.path.basename(os.environ.get("BWQ_LIB", "default"))]
+FLAGS = int(os.environ.get("BWQ_FLAGS", "0"), 0)
+eng.set_options(flags=FLAGS)
+out = [os.path.basename(os.environ.get("BWQ_LIB", "default")) + " flags=%#x" % FLAGS]
 be = backends.synthetic_chain(16, seed=2); eng.set_noise(noise.from_backend(be))
 tw, base, obs = F.config_brick10_twirl(n_base=4, n_twirls=50)
 b = engine.encode_batch(tw, [obs] * len(tw))
