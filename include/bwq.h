@@ -230,6 +230,21 @@ int bwq_svx_upload(bwq_ctx* ctx, bwq_svx_program* p);
 int bwq_svx_run_segment(bwq_ctx* ctx, const bwq_svx_program* p, int32_t segment, double* d_state,
                         int32_t rank, double* d_obs, void* stream);
 
+/* EXCHANGE segment over NVLink peer memory (the engine's own replacement for the NCCL
+ * all_to_all): the top log2(world) local index bits swap with the rank bits, so block b of the
+ * new shard d_dst is block `rank` of rank b's old shard.  peer_src[w] = device pointer to rank
+ * w's OLD shard as mapped into this process (symmetric memory / CUDA IPC; peer_src[rank] is the
+ * local one).  The kernel pulls all 2^g blocks with P2P loads on `stream` (same convention as
+ * bwq_svx_run_segment) and does not synchronise; the caller places a cross-rank barrier before
+ * it (every peer has finished writing its old shard) and before the old shard is overwritten. */
+int bwq_svx_exchange_pull(bwq_ctx* ctx, double* d_dst, const uint64_t* peer_src, int32_t world, int32_t rank,
+                          int64_t n_local_amps, void* stream);
+/* Same exchange with P2P stores: block b of the local OLD shard d_src is written into block `rank`
+ * of rank b's NEW shard peer_dst[b].  The caller places the cross-rank barrier AFTER it (all
+ * blocks have landed before anyone sweeps its new shard). */
+int bwq_svx_exchange_push(bwq_ctx* ctx, const double* d_src, const uint64_t* peer_dst, int32_t world, int32_t rank,
+                          int64_t n_local_amps, void* stream);
+
 #ifdef __cplusplus
 }
 #endif

@@ -1312,6 +1312,36 @@ extern "C" int bwq_svx_upload(bwq_ctx* ctx, bwq_svx_program* h) {
   return BWQ_OK;
 }
 
+static int svx_exchange_impl(bwq_ctx* ctx, double* d_local, const uint64_t* peers, int32_t world, int32_t rank,
+                             int64_t n_local_amps, void* stream, bool push) {
+  if (!ctx || !d_local || !peers) return BWQ_ERR_ARG;
+  if (world < 2 || world > kSvxMaxWorld || (world & (world - 1)) || rank < 0 || rank >= world)
+    return fail(ctx, BWQ_ERR_ARG, "bwq_svx_exchange: world must be a power of two in [2,%d], rank inside it", kSvxMaxWorld);
+  if (n_local_amps < world || n_local_amps % world) return fail(ctx, BWQ_ERR_ARG, "shard size must be a multiple of world");
+  CK(cudaSetDevice(ctx->device));
+  cudaStream_t st = stream ? (cudaStream_t)stream : ctx->stream;
+  SvxPeers P{};
+  for (int w = 0; w < world; ++w) {
+    if (!peers[w]) return fail(ctx, BWQ_ERR_ARG, "peer pointer %d is NULL", w);
+    P.ptr[w] = reinterpret_cast<double2*>(peers[w]);
+  }
+  const int64_t blk = n_local_amps / world;
+  // CTAs per partner rank: enough 16-byte accesses in flight for the NVLink round trip, about two waves
+  const int64_t per = std::max<int64_t>(1, std::min<int64_t>((blk + 256 * 8 - 1) / (256 * 8), 2 * (int64_t)ctx->sm_count * 8 / world));
+  if (push) svx_exchange_kernel<true><<<(unsigned)(per * world), 256, 0, st>>>((double2*)d_local, P, world, rank, blk);
+  else svx_exchange_kernel<false><<<(unsigned)(per * world), 256, 0, st>>>((double2*)d_local, P, world, rank, blk);
+  CK(cudaGetLastError());
+  return BWQ_OK;
+}
+extern "C" int bwq_svx_exchange_pull(bwq_ctx* ctx, double* d_dst, const uint64_t* peer_src, int32_t world, int32_t rank,
+                                     int64_t n_local_amps, void* stream) {
+  return svx_exchange_impl(ctx, d_dst, peer_src, world, rank, n_local_amps, stream, false);
+}
+extern "C" int bwq_svx_exchange_push(bwq_ctx* ctx, const double* d_src, const uint64_t* peer_dst, int32_t world, int32_t rank,
+                                     int64_t n_local_amps, void* stream) {
+  return svx_exchange_impl(ctx, const_cast<double*>(d_src), peer_dst, world, rank, n_local_amps, stream, true);
+}
+
 extern "C" int bwq_svx_run_segment(bwq_ctx* ctx, const bwq_svx_program* h, int32_t segment, double* d_state,
                                    int32_t rank, double* d_obs, void* stream) {
   if (!ctx || !h || !d_state) return BWQ_ERR_ARG;

@@ -291,6 +291,43 @@ __global__ void __launch_bounds__(kSvxThreads, 3) sv_sweep_kernel(const SvxLaunc
 #undef SVX_DEPOSIT
 }
 
+// ---------------------------------------------------------------------------------------------
+// EXCHANGE over NVLink peer memory: the top g local index bits swap with the rank bits, i.e.
+// block b of this rank's new shard is block `rank` of rank b's old shard.  Every rank moves its
+// 2^g blocks straight between the shards (P2P loads or stores through NVSwitch; symmetric-memory
+// mappings supplied by the caller) -- no staging buffers, no send/recv channels.  CTA c serves
+// partner rank (rank + 1 + c) mod world, so at any moment the traffic is spread over all peers
+// (every link carries 1/world of each rank) instead of all ranks hitting rank 0 first.
+// ---------------------------------------------------------------------------------------------
+constexpr int kSvxMaxWorld = 16;
+struct SvxPeers { double2* ptr[kSvxMaxWorld]; };
+
+// PUSH = false: ptr[w] = rank w's OLD shard, `local` = this rank's new shard (P2P loads);
+// PUSH = true:  ptr[w] = rank w's NEW shard, `local` = this rank's old shard (P2P stores: block b
+//               of the old shard becomes block `rank` of rank b's new shard).
+template <bool PUSH>
+__global__ void __launch_bounds__(256) svx_exchange_kernel(double2* __restrict__ local, const SvxPeers peers, const int world,
+                                                           const int rank, const int64_t blk) {
+  const int b = (rank + 1 + int(blockIdx.x % world)) % world;          // partner rank of this CTA
+  const int64_t cta = blockIdx.x / world, n_cta = gridDim.x / world;    // CTAs sharing the block
+  const double2* __restrict__ src = PUSH ? local + int64_t(b) * blk : peers.ptr[b] + int64_t(rank) * blk;
+  double2* __restrict__ out = PUSH ? peers.ptr[b] + int64_t(rank) * blk : local + int64_t(b) * blk;
+  constexpr int U = 8;                                                  // 16-byte accesses in flight per thread
+  for (int64_t i0 = (cta * 256 + threadIdx.x); i0 < blk; i0 += n_cta * 256 * U) {
+    double2 v[U];
+#pragma unroll
+    for (int u = 0; u < U; ++u) {
+      const int64_t i = i0 + int64_t(u) * n_cta * 256;
+      if (i < blk) v[u] = __ldcg(src + i);
+    }
+#pragma unroll
+    for (int u = 0; u < U; ++u) {
+      const int64_t i = i0 + int64_t(u) * n_cta * 256;
+      if (i < blk) out[i] = v[u];
+    }
+  }
+}
+
 // |0...0> for circuits whose first stage has no sweep (slot list)
 __global__ void sv_init_kernel(double2* states, int64_t stride, const int32_t* slots, int n_slots, uint32_t hi_bits) {
   const int64_t i = int64_t(blockIdx.x) * blockDim.x + threadIdx.x;

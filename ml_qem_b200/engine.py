@@ -62,7 +62,7 @@ EXPORTS = [
     "bwq_dm_run", "bwq_sv_run", "bwq_meas_data_run", "bwq_dm_run_device_out", "bwq_dm_prepare", "bwq_dm_execute", "bwq_dm_execute_device_out", "bwq_sv_prepare", "bwq_sv_execute", "bwq_get_stats", "bwq_sync", "bwq_lower_dm",
     "bwq_program_free", "bwq_program_sizes", "bwq_program_read",
     "bwq_svx_lower", "bwq_svx_free", "bwq_svx_sizes", "bwq_svx_read", "bwq_svx_upload", "bwq_svx_run_segment",
-    "bwq_svx_bytes",
+    "bwq_svx_bytes", "bwq_svx_exchange_pull", "bwq_svx_exchange_push",
 ]
 
 
@@ -108,6 +108,8 @@ def load_library(path=None):
     lib.bwq_svx_bytes.argtypes = [C.c_void_p, C.c_int32]
     lib.bwq_svx_bytes.restype = C.c_int64
     lib.bwq_svx_run_segment.argtypes = [C.c_void_p, C.c_void_p, C.c_int32, C.c_void_p, C.c_int32, C.c_void_p, C.c_void_p]
+    for f in (lib.bwq_svx_exchange_pull, lib.bwq_svx_exchange_push):
+        f.argtypes = [C.c_void_p, C.c_void_p, C.c_void_p, C.c_int32, C.c_int32, C.c_int64, C.c_void_p]
     if path is None:
         _lib = lib
     return lib
@@ -327,6 +329,14 @@ class Engine:
                                                     noisy.ctypes.data_as(C.c_void_p), st_i.ctypes.data_as(C.c_void_p),
                                                     st_n.ctypes.data_as(C.c_void_p)), "bwq_meas_data_run")
         return ideal, noisy, st_i, st_n
+
+    def svx_exchange(self, local_ptr, peer_ptrs, rank, n_local_amps, stream=0, push=False):
+        """EXCHANGE of the sharded statevector through peer memory: pull (local = new shard,
+        peers = old shards) or push (local = old shard, peers = new shards)."""
+        peers = np.asarray(peer_ptrs, dtype=np.uint64)
+        fn = self._lib.bwq_svx_exchange_push if push else self._lib.bwq_svx_exchange_pull
+        self._check(fn(self._ctx, C.c_void_p(int(local_ptr)), peers.ctypes.data_as(C.c_void_p), len(peers), int(rank),
+                       int(n_local_amps), C.c_void_p(int(stream)) if stream else None), "bwq_svx_exchange")
 
     def run_dm_into(self, batch, device_ptr):
         """Writes the values into device memory at ``device_ptr`` (e.g. torch ``tensor.data_ptr()``

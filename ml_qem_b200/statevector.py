@@ -11,8 +11,12 @@ expectation passes.  Rank r owns the amplitudes whose top log2(world) index bits
 Diagonal gates (every TFIM bond: cx rz cx = exp(-i t ZZ)) and controlled gates with a global
 control never communicate; a non-diagonal gate on a global qubit is preceded by an EXCHANGE = the
 top log2(world) local index bits swap with the rank bits: one ``all_to_all_single`` of 2^g
-contiguous blocks (NCCL over NVLink), 1 - 1/world of the shard leaves the GPU.  Values are reduced
-with one ``all_reduce`` of n_observables doubles.
+contiguous blocks, 1 - 1/world of the shard leaves the GPU.  The exchange is the engine's own
+kernel: the shards live in symmetric memory and every rank pulls its blocks straight out of the
+peers' shards over NVLink (bwq_svx_exchange_push, P2P stores, 705 GB/s per rank on 2 GPUs;
+bwq_svx_exchange_pull, P2P loads, 670 GB/s; NCCL all_to_all: 424 GB/s); NCCL ``all_to_all_single`` is the fallback
+(BWQ_SVX_EXCHANGE=nccl, or no symmetric memory).  Values are reduced with one ``all_reduce`` of
+n_observables doubles.
 """
 import numpy as np
 
@@ -34,14 +38,60 @@ class GpuExecutor:
     def init_state(self, state, rank):
         pass  # the first sweep synthesises |0...0>
 
-    def run_segment(self, program, seg, state, rank, obs):
+    def _stream(self):
         import torch
 
-        # run on torch's current stream so the segments are ordered with the NCCL exchange; the
+        # run on torch's current stream so the segments are ordered with the exchange; the
         # C ABI reads 0 as "the engine's own stream", so torch's default stream (handle 0) is
         # passed as cudaStreamLegacy (0x1)
-        stream = torch.cuda.current_stream(self.device).cuda_stream or 1
-        program.run_segment(self.engine, seg, state.data_ptr(), rank, obs.data_ptr(), stream)
+        return torch.cuda.current_stream(self.device).cuda_stream or 1
+
+    def run_segment(self, program, seg, state, rank, obs):
+        program.run_segment(self.engine, seg, state.data_ptr(), rank, obs.data_ptr(), self._stream())
+
+    # ---- EXCHANGE through NVLink peer memory (the engine's own kernel instead of NCCL) -------
+    def exchange_buffers(self, n_amp, dist):
+        """Two shard buffers in symmetric memory (every rank maps the peers' copies), cached per
+        shard size.  Returns None when symmetric memory is unavailable or BWQ_SVX_EXCHANGE=nccl:
+        the caller then falls back to ``all_to_all_single``."""
+        import os
+
+        import torch
+
+        if os.environ.get("BWQ_SVX_EXCHANGE", "push").lower() == "nccl":  # push (default) | pull | nccl
+            return None
+        cache = self.__dict__.setdefault("_xbuf", {})
+        if n_amp in cache:
+            return cache[n_amp]
+        try:
+            import torch.distributed._symmetric_memory as symm
+
+            group = dist.group.WORLD
+            bufs = []
+            for _ in range(2):
+                raw = symm.empty(2 * n_amp, dtype=torch.float64, device=self.device)
+                hdl = symm.rendezvous(raw, group)
+                bufs.append((torch.view_as_complex(raw.view(n_amp, 2)), hdl, [int(p) for p in hdl.buffer_ptrs]))
+            cache[n_amp] = bufs
+        except Exception as exc:  # noqa: BLE001
+            import warnings
+
+            warnings.warn(f"symmetric memory unavailable ({exc!r}): EXCHANGE falls back to NCCL all_to_all")
+            cache[n_amp] = None
+        return cache[n_amp]
+
+    def exchange(self, src, dst, rank, world):
+        """src/dst: entries of exchange_buffers().  Cross-rank barrier (every peer has finished
+        writing its old shard; it also fences the previous pull out of ``dst``), then the pull."""
+        import os
+
+        if os.environ.get("BWQ_SVX_EXCHANGE", "push").lower() != "pull":
+            # P2P stores into the peers' new shards, barrier after: all blocks have landed
+            self.engine.svx_exchange(src[0].data_ptr(), dst[2], rank, src[0].numel(), self._stream(), push=True)
+            dst[1].barrier(channel=0)
+            return
+        src[1].barrier(channel=0)
+        self.engine.svx_exchange(dst[0].data_ptr(), src[2], rank, dst[0].numel(), self._stream())
 
 
 class ShardedStatevector:
@@ -73,8 +123,15 @@ class ShardedStatevector:
         self.ex.prepare(prog)
         n_amp = 1 << info["n_local"]
         dev = self.ex.device
-        state = torch.empty(n_amp, dtype=torch.complex128, device=dev)
-        spare = torch.empty(n_amp, dtype=torch.complex128, device=dev) if info["n_exchanges"] else None
+        xbuf = None
+        if self.dist and info["n_exchanges"] and hasattr(self.ex, "exchange_buffers"):
+            xbuf = self.ex.exchange_buffers(n_amp, self.dist)
+        if xbuf is not None:
+            cur, other = xbuf
+            state, spare = cur[0], other[0]
+        else:
+            state = torch.empty(n_amp, dtype=torch.complex128, device=dev)
+            spare = torch.empty(n_amp, dtype=torch.complex128, device=dev) if info["n_exchanges"] else None
         obs = torch.zeros(max(1, info["n_observables"]), dtype=torch.float64, device=dev)
         self.ex.init_state(state, self.rank)
         exchanged_bytes = 0
@@ -91,7 +148,11 @@ class ShardedStatevector:
         for seg, (kind, first, count, _) in enumerate(info["segs"]):
             if kind == SEG_EXCHANGE:
                 # block v of rank s <-> block s of rank v: top g local bits swap with the rank bits
-                self.dist.all_to_all_single(spare, state)
+                if xbuf is not None:
+                    self.ex.exchange(cur, other, self.rank, self.world)
+                    cur, other = other, cur
+                else:
+                    self.dist.all_to_all_single(spare, state)
                 state, spare = spare, state
                 exchanged_bytes += state.numel() * 16 * (self.world - 1) // self.world
                 mark("exchange")
@@ -103,7 +164,9 @@ class ShardedStatevector:
             mark("allreduce")
         self.last_plan = {"n_bits": info["n_bits"], "n_local": info["n_local"], "n_sweeps": len(info["sweeps"]),
                           "n_passes": info["n_passes"], "n_exchanges": info["n_exchanges"],
-                          "exchanged_bytes_per_rank": exchanged_bytes, "kernel_bytes": prog.algorithmic_bytes(self.rank),
+                          "exchanged_bytes_per_rank": exchanged_bytes,
+                          "exchange_impl": "own P2P kernel over symmetric memory (bwq_svx_exchange_push/pull)" if xbuf is not None else "nccl all_to_all",
+                          "kernel_bytes": prog.algorithmic_bytes(self.rank),
                           "n_expval_passes": int(sum(-(-int(c) // 32) for k, _, c, _ in info["segs"] if k == SEG_EXPVAL))}
         vals = obs[:info["n_observables"]].cpu().numpy()
         if profile:
