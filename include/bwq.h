@@ -119,6 +119,7 @@ typedef struct {
 #define BWQ_OPT_NO_DIRECT_LOAD 1
 #define BWQ_OPT_NO_DIRECT_STORE 2
 #define BWQ_OPT_NO_PIPELINE 4   /* bwq_dm_run: lower the whole batch before the first launch */
+#define BWQ_OPT_FORCE_PIPELINE 8 /* bwq_dm_run: pipeline segments even when the sweeps look too short to matter */
 
 /* Counters of the last *_run call (for the roofline: bytes = sweeps x 16 B x 4^n). */
 typedef struct {
@@ -150,8 +151,9 @@ int bwq_set_noise_table(bwq_ctx* ctx, const bwq_noise_table* table);
 /* Noisy values: density-matrix evolution of every circuit under the installed noise table
  * (Aer Estimator, method=density_matrix, approximation=True, shots=None).
  * out_vals[n_observables] (order of term_offsets), out_status[n_circuits].  Batches of >= 256
- * circuits are cut into segments and pipelined: the host lowers segment k+1 while the GPU sweeps
- * segment k (BWQ_OPT_NO_PIPELINE turns this off). */
+ * circuits with enough sweep work (about 5 ms by a gate-count estimate) are cut into segments and
+ * pipelined: the host lowers segment k+1 while the GPU sweeps segment k (BWQ_OPT_NO_PIPELINE /
+ * BWQ_OPT_FORCE_PIPELINE override the choice). */
 int bwq_dm_run(bwq_ctx* ctx, const bwq_batch* batch, double* out_vals, int32_t* out_status);
 /* Split form of bwq_dm_run: prepare lowers the batch on the host and uploads the program (it
  * stays resident in HBM inside the ctx); execute runs the kernels and returns the values, and may

@@ -655,9 +655,28 @@ static int dm_run_impl(bwq_ctx* ctx, const bwq_batch* b, double* out_vals, int32
   const int N = b->n_circuits;
   int64_t budget = 0;
   if ((rc = (int)dm_state_budget(ctx, &budget))) return rc;
-  // segments: at least kMinSeg circuits each, at most kMaxSegs of them
+  // segments: at least kMinSeg circuits each, at most kMaxSegs of them -- but only when the sweeps
+  // are worth hiding behind: a rough estimate of the HBM traffic (8 B x 4^active qubits per sweep,
+  // about one sweep per four 2-qubit gates) must reach a few milliseconds of GPU time; batches of
+  // tiny circuits (cfg1: 4 qubits, on chip) are lowered in one piece (the per-segment thread and
+  // launch overhead would exceed the kernel time)
   constexpr int kMinSeg = 128, kMaxSegs = 8;
-  const int n_seg = (ctx->opt.flags & BWQ_OPT_NO_PIPELINE) ? 1 : std::max(1, std::min(kMaxSegs, N / kMinSeg));
+  int n_seg = (ctx->opt.flags & BWQ_OPT_NO_PIPELINE) ? 1 : std::max(1, std::min(kMaxSegs, N / kMinSeg));
+  if (n_seg > 1 && !(ctx->opt.flags & BWQ_OPT_FORCE_PIPELINE)) {
+    double est_bytes = 0.0;
+    for (int c = 0; c < N && est_bytes < 2e10; ++c) {
+      uint64_t used = 0;
+      int64_t n2 = 0;
+      for (int64_t g = b->op_offsets[c]; g < b->op_offsets[c + 1]; ++g) {
+        const bwq_op& op = b->ops[g];
+        used |= 1ull << (op.q0 & 63);
+        if (gate_is_2q(op.opcode)) { used |= 1ull << (op.q1 & 63); ++n2; }
+      }
+      const int na = std::min(__builtin_popcountll(used), kMaxDmQubits);
+      if (na > 6) est_bytes += 16.0 * std::ldexp(1.0, 2 * na) * (1.0 + 0.25 * (double)n2);
+    }
+    if (est_bytes < 2e10) n_seg = 1;  // < ~5 ms of sweeps
+  }
   auto seg_begin = [&](int k) { return (int)((int64_t)N * k / n_seg); };
   bwq_stats total{};
   int lower_rc = dm_lower_impl(ctx, ctx->dm[0], b, seg_begin(0), seg_begin(1), out_status, budget);

@@ -14,3 +14,7 @@ for fl in (0, 4):
 for rep in range(3):
     t = time.perf_counter(); eng.run_sv(batch); w = 1e3 * (time.perf_counter() - t); s = eng.stats()
     print("run_sv wall %.1f ms | lower %.1f h2d %.2f kernel %.1f d2h %.2f" % (w, s["lower_ms"], s["h2d_ms"], s["kernel_ms"], s["d2h_ms"]))
+eng.set_options()
+for rep in range(4):
+    t = time.perf_counter(); eng.run_meas_data(batch); w = 1e3 * (time.perf_counter() - t); s = eng.stats()
+    print("run_meas_data wall %.1f ms | dm side: lower %.1f h2d %.2f kernel %.1f d2h %.2f | circuits %d" % (w, s["lower_ms"], s["h2d_ms"], s["kernel_ms"], s["d2h_ms"], batch.n_circuits))
