@@ -142,7 +142,7 @@ struct bwq_ctx {
   // density-matrix program slots: slot 0 is the prepared batch of bwq_dm_prepare / bwq_dm_execute;
   // bwq_dm_run alternates between both so that segment k+1 is lowered on the host threads while
   // the GPU executes segment k
-  struct DmSlot { DmPlan plan; PinBuf h_prog; DevBuf d_prog; } dm[2];
+  struct DmSlot { DmPlan plan; PinBuf h_prog; DevBuf d_prog; cudaEvent_t h2d_done = nullptr; } dm[2];
   SvPlan sv_plan;
   std::vector<cudaEvent_t> chunk_ev;  // begin/end of each chunk's sweep launches
   bwq_ctx* companion = nullptr;       // statevector side of bwq_meas_data_run (created on first use)
@@ -196,6 +196,8 @@ extern "C" int bwq_create(int device, bwq_ctx** out) {
   if ((e = cudaStreamCreateWithFlags(&ctx->stream, cudaStreamNonBlocking)) != cudaSuccess) return bail(e, "cudaStreamCreate");
   for (auto& ev : ctx->ev)
     if ((e = cudaEventCreate(&ev)) != cudaSuccess) return bail(e, "cudaEventCreate");
+  for (auto& sl : ctx->dm)
+    if ((e = cudaEventCreateWithFlags(&sl.h2d_done, cudaEventDisableTiming)) != cudaSuccess) return bail(e, "cudaEventCreate");
   ctx->chunk_ev.resize(128);
   for (auto& ev : ctx->chunk_ev)
     if ((e = cudaEventCreate(&ev)) != cudaSuccess) return bail(e, "cudaEventCreate");
@@ -227,7 +229,7 @@ extern "C" int bwq_destroy(bwq_ctx* ctx) {
   cudaSetDevice(ctx->device);
   cudaStreamSynchronize(ctx->stream);
   ctx->d_b0.release(); ctx->d_noise.release(); ctx->d_states.release(); ctx->d_out.release();
-  for (auto& sl : ctx->dm) { sl.d_prog.release(); sl.h_prog.release(); }
+  for (auto& sl : ctx->dm) { sl.d_prog.release(); sl.h_prog.release(); if (sl.h2d_done) cudaEventDestroy(sl.h2d_done); }
   ctx->d_scratch.release(); ctx->h_out.release();
   ctx->d_sv_prog.release(); ctx->h_sv_prog.release();
   ctx->d_wide_prog.release(); ctx->h_wide_prog.release(); ctx->d_partial.release();
@@ -501,6 +503,8 @@ static int dm_lower_impl(bwq_ctx* ctx, bwq_ctx::DmSlot& sl, const bwq_batch* b, 
 }
 
 // Device part of the preparation: buffers + one H2D copy of the slot's program blob.
+// sync = false (pipelined run): the value buffers were sized for the whole batch by the caller and
+// the copy is only enqueued; sl.h2d_done tells the lowering thread when the pinned blob is free.
 static int dm_upload_impl(bwq_ctx* ctx, bwq_ctx::DmSlot& sl, bool sync) {
   DmPlan& P = sl.plan;
   const size_t blob_total = P.blob_bytes;
@@ -508,14 +512,14 @@ static int dm_upload_impl(bwq_ctx* ctx, bwq_ctx::DmSlot& sl, bool sync) {
   const bool have = !P.chunks.empty();
   if (have) CK(sl.d_prog.reserve(blob_total));
   if (P.max_chunk_bytes > 0) CK(ctx->d_states.reserve((size_t)P.max_chunk_bytes));
-  if (P.n_obs > 0) {
+  if (sync && P.n_obs > 0) {
     CK(ctx->d_out.reserve(sizeof(double) * (size_t)P.n_obs));
     CK(ctx->h_out.reserve(sizeof(double) * (size_t)P.n_obs));
   }
   cudaStream_t st = ctx->stream;
-  CK(cudaEventRecord(ctx->ev[0], st));
+  if (sync) CK(cudaEventRecord(ctx->ev[0], st));
   if (have) CK(cudaMemcpyAsync(sl.d_prog.p, hb, blob_total, cudaMemcpyHostToDevice, st));
-  CK(cudaEventRecord(ctx->ev[1], st));
+  CK(cudaEventRecord(sync ? ctx->ev[1] : sl.h2d_done, st));
   if (sync) {
     CK(cudaStreamSynchronize(st));
     float ms = 0.f;
@@ -553,7 +557,10 @@ static int dm_prepare_impl(bwq_ctx* ctx, const bwq_batch* b, int32_t* out_status
   return BWQ_OK;
 }
 
-static int dm_execute_impl(bwq_ctx* ctx, bwq_ctx::DmSlot& sl, double* out_vals, bool out_on_device) {
+// deferred = true (pipelined run): segment values go to offset obs_off of the batch-sized buffers,
+// nothing is synchronised, timed or copied to the caller here (dm_run_impl does that once).
+static int dm_execute_impl(bwq_ctx* ctx, bwq_ctx::DmSlot& sl, double* out_vals, bool out_on_device, bool deferred = false,
+                           int64_t obs_off = 0) {
   if (!ctx || !out_vals) return BWQ_ERR_ARG;
   DmPlan& P = sl.plan;
   if (!P.valid) return fail(ctx, BWQ_ERR_ARG, "bwq_dm_execute: no prepared batch (call bwq_dm_prepare first)");
@@ -563,11 +570,11 @@ static int dm_execute_impl(bwq_ctx* ctx, bwq_ctx::DmSlot& sl, double* out_vals, 
   S.lower_ms = P.lower_ms; S.h2d_ms = P.h2d_ms; S.h2d_bytes = (int64_t)P.blob_bytes;
   S.n_gates = P.n_gates; S.n_passes = P.n_passes;
   cudaStream_t st = ctx->stream;
-  double* d_out = out_on_device ? out_vals : (double*)ctx->d_out.p;
+  double* d_out = out_on_device ? out_vals : (double*)ctx->d_out.p + obs_off;
   const char* db = (const char*)sl.d_prog.p;
-  CK(cudaEventRecord(ctx->ev[1], st));
+  if (!deferred) CK(cudaEventRecord(ctx->ev[1], st));
   if (P.n_obs > 0) CK(cudaMemsetAsync(d_out, 0, sizeof(double) * (size_t)P.n_obs, st));
-  const size_t n_ev = std::min(P.chunks.size(), ctx->chunk_ev.size() / 2);
+  const size_t n_ev = deferred ? 0 : std::min(P.chunks.size(), ctx->chunk_ev.size() / 2);
   for (size_t ci = 0; ci < P.chunks.size(); ++ci) {
     const DmChunk& ch = P.chunks[ci];
     DmLaunch L;
@@ -607,11 +614,12 @@ static int dm_execute_impl(bwq_ctx* ctx, bwq_ctx::DmSlot& sl, double* out_vals, 
       S.n_other_launches++;
     }
   }
-  CK(cudaEventRecord(ctx->ev[2], st));
+  if (!deferred) CK(cudaEventRecord(ctx->ev[2], st));
   if (!out_on_device && P.n_obs > 0) {
-    CK(cudaMemcpyAsync(ctx->h_out.p, d_out, sizeof(double) * (size_t)P.n_obs, cudaMemcpyDeviceToHost, st));
+    CK(cudaMemcpyAsync((double*)ctx->h_out.p + obs_off, d_out, sizeof(double) * (size_t)P.n_obs, cudaMemcpyDeviceToHost, st));
     S.d2h_bytes = (int64_t)sizeof(double) * P.n_obs;
   }
+  if (deferred) return BWQ_OK;
   CK(cudaEventRecord(ctx->ev[3], st));
   CK(cudaStreamSynchronize(st));
   float ms = 0.f;
@@ -678,32 +686,61 @@ static int dm_run_impl(bwq_ctx* ctx, const bwq_batch* b, double* out_vals, int32
     if (est_bytes < 2e10) n_seg = 1;  // < ~5 ms of sweeps
   }
   auto seg_begin = [&](int k) { return (int)((int64_t)N * k / n_seg); };
+  if (n_seg == 1) {
+    if ((rc = dm_lower_impl(ctx, ctx->dm[0], b, 0, N, out_status, budget))) return rc;
+    if (N > 0 && (rc = dm_upload_impl(ctx, ctx->dm[0], true))) return rc;
+    return dm_execute_impl(ctx, ctx->dm[0], out_vals, out_on_device);
+  }
+  // pipelined: nothing is synchronised between the segments -- upload, sweeps and the D2H of the
+  // values of segment k are enqueued behind segment k-1 while the helper thread lowers segment k+1
+  CK(cudaSetDevice(ctx->device));
+  cudaStream_t st = ctx->stream;
+  const int64_t n_obs = b->obs_offsets[N];
+  if (!out_on_device && n_obs > 0) {
+    CK(ctx->d_out.reserve(sizeof(double) * (size_t)n_obs));
+    CK(ctx->h_out.reserve(sizeof(double) * (size_t)n_obs));
+  }
   bwq_stats total{};
-  int lower_rc = dm_lower_impl(ctx, ctx->dm[0], b, seg_begin(0), seg_begin(1), out_status, budget);
-  if (lower_rc) return lower_rc;
+  std::vector<std::pair<int64_t, double>> fixes;
+  if ((rc = dm_lower_impl(ctx, ctx->dm[0], b, seg_begin(0), seg_begin(1), out_status, budget))) return rc;
+  CK(cudaEventRecord(ctx->ev[1], st));
   for (int k = 0; k < n_seg; ++k) {
     bwq_ctx::DmSlot& cur = ctx->dm[k & 1];
     std::thread helper;
     int next_rc = BWQ_OK;
     if (k + 1 < n_seg)
       helper = std::thread([&, k] {
-        next_rc = dm_lower_impl(ctx, ctx->dm[(k + 1) & 1], b, seg_begin(k + 1), seg_begin(k + 2), out_status, budget);
+        bwq_ctx::DmSlot& nxt = ctx->dm[(k + 1) & 1];
+        cudaSetDevice(ctx->device);
+        cudaEventSynchronize(nxt.h2d_done);  // the blob of segment k-1 has left the pinned buffer
+        next_rc = dm_lower_impl(ctx, nxt, b, seg_begin(k + 1), seg_begin(k + 2), out_status, budget);
       });
-    const int64_t obs0 = N > 0 ? b->obs_offsets[seg_begin(k)] : 0;
-    rc = seg_begin(k + 1) > seg_begin(k) ? dm_upload_impl(ctx, cur, n_seg == 1) : BWQ_OK;
-    if (!rc) rc = dm_execute_impl(ctx, cur, out_vals + obs0, out_on_device);
+    const int64_t obs0 = b->obs_offsets[seg_begin(k)];
+    rc = dm_upload_impl(ctx, cur, false);
+    if (!rc) rc = dm_execute_impl(ctx, cur, out_on_device ? out_vals + obs0 : out_vals, out_on_device, true, obs0);
+    for (auto& f : cur.plan.host_fix) fixes.push_back({obs0 + f.first, f.second});
+    const bwq_stats S = ctx->stats;
+    const double seg_lower_ms = cur.plan.lower_ms;
     if (helper.joinable()) helper.join();
-    if (rc) return rc;
-    if (next_rc) return next_rc;
-    const bwq_stats& S = ctx->stats;
+    if (rc || next_rc) { cudaStreamSynchronize(st); return rc ? rc : next_rc; }
     total.n_sweep_launches += S.n_sweep_launches; total.n_state_sweeps += S.n_state_sweeps;
     total.n_passes += S.n_passes; total.n_gates += S.n_gates; total.state_bytes_swept += S.state_bytes_swept;
-    total.n_other_launches += S.n_other_launches; total.lower_ms += cur.plan.lower_ms; total.h2d_ms += cur.plan.h2d_ms;
-    total.kernel_ms += S.kernel_ms; total.d2h_ms += S.d2h_ms; total.sweep_kernel_ms += S.sweep_kernel_ms;
+    total.n_other_launches += S.n_other_launches; total.lower_ms += seg_lower_ms;
     total.h2d_bytes += S.h2d_bytes; total.d2h_bytes += S.d2h_bytes;
   }
+  CK(cudaEventRecord(ctx->ev[2], st));
+  CK(cudaStreamSynchronize(st));
+  float ms = 0.f;
+  CK(cudaEventElapsedTime(&ms, ctx->ev[1], ctx->ev[2]));
+  total.kernel_ms = total.sweep_kernel_ms = ms;  // uploads and value copies of the segments included
+  if (!out_on_device) {
+    if (n_obs > 0) std::memcpy(out_vals, ctx->h_out.p, sizeof(double) * (size_t)n_obs);
+    for (auto& f : fixes) out_vals[f.first] = f.second;
+  } else {
+    for (auto& f : fixes) CK(cudaMemcpy(out_vals + f.first, &f.second, sizeof(double), cudaMemcpyHostToDevice));
+  }
   ctx->stats = total;
-  if (n_seg > 1) ctx->dm[0].plan.valid = false;  // slot 0 no longer holds a whole prepared batch
+  ctx->dm[0].plan.valid = false;  // slot 0 no longer holds a whole prepared batch
   return BWQ_OK;
 }
 
