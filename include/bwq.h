@@ -112,7 +112,7 @@ typedef struct {
   int64_t max_state_bytes;  /* device budget for resident states (default: 80% of free)        */
   int32_t chunk_circuits;   /* circuits simulated together (default: as many as fit)          */
   int32_t host_threads;     /* lowering threads (default: hardware concurrency)               */
-  int32_t sv_tile_bits;     /* amplitudes per statevector tile = 2^this, 2..12 (default 11)    */
+  int32_t sv_tile_bits;     /* amplitudes per statevector tile = 2^this, 2..12 (default 12)    */
   int32_t flags;            /* BWQ_OPT_* bits (0 = defaults)                                  */
 } bwq_options;
 /* planner switches for kernel experiments: keep the first / last pass of a sweep on the staged path */
@@ -206,7 +206,7 @@ int bwq_program_read(const bwq_program* p, int32_t* active_qubits, int32_t* swee
  * NCCL over NVLink), and EXPVAL (signed |amplitude|^2 sums accumulated into n_observables
  * partial values the caller all-reduces).  Device buffers are caller-owned. */
 typedef struct bwq_svx_program bwq_svx_program;
-/* Host-only planner.  tile_bits 0 = default (11). */
+/* Host-only planner.  tile_bits 0 = default (12). */
 int bwq_svx_lower(const bwq_batch* batch, int32_t circuit, int32_t tile_bits, int32_t n_global_bits,
                   bwq_svx_program** out);
 void bwq_svx_free(bwq_svx_program* p);

@@ -123,3 +123,42 @@ def test_sweep_packing_respects_tile_and_order(lib):
                 assert sa < kq and sb < kq and sa != sb and len(ops) > 0
             total += len(passes)
         assert total == prog["n_passes"]
+
+
+def test_direct_pass_flags_are_consistent(lib):
+    """Direct passes (kernels.cuh): the planner may move a commuting pass to the front / back of a
+    sweep and flag it to exchange its register groups with global memory.  The flagged passes must
+    avoid the two lowest tile slots, the first-pass descriptor in SweepDesc::pos[7] must repeat the
+    first pass header, and the reordered program must still match the oracle (run by the emulator
+    in emitted order)."""
+    from program_emulator import decode_block
+
+    n = 9
+    be = backends.synthetic_chain(n, seed=9)
+    nm = noise.from_backend(be)
+    from oracle import noise_model as onm
+    on = onm.from_backend(be.to_dict())
+    rng = np.random.default_rng(9)
+    circ = F.brickwork_circuit(n, 3, rng, list(range(n)), n)
+    obs = [[(l, 1.0)] for l in _labels(rng, n, 5)]
+    prog = _check(circ, obs, nm, on, tilings=((6, 2),))
+    n_first = n_last = 0
+    for sw in prog["sweeps"]:
+        passes, _ = decode_block(prog, sw)
+        blk = prog["prog"][2 * int(sw[0]): 2 * (int(sw[0]) + int(sw[9]))].view(np.uint8)
+        flags = [int(blk[16 * (1 + p) + 6]) for p in range(len(passes))]
+        desc = int(sw[8])  # pos[7]
+        assert all(f == 0 for f in flags[1:-1])
+        if flags[0] & 1:
+            sa, sb, _ = passes[0]
+            assert min(sa, sb) >= 2 and desc == (0x80 | sa | (sb << 3))
+            n_first += 1
+        else:
+            assert desc & 0x80 == 0
+        if flags[-1] & 2:
+            sa, sb, _ = passes[-1]
+            assert min(sa, sb) >= 2
+            n_last += 1
+        if len(passes) > 1:
+            assert not (flags[0] & 2) and not (flags[-1] & 1)
+    assert n_first > 0 and n_last > 0
