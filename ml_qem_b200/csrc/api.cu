@@ -498,6 +498,8 @@ static int dm_lower_impl(bwq_ctx* ctx, bwq_ctx::DmSlot& sl, const bwq_batch* b, 
       P.host_fix.push_back({o - obs0, out_status[c0 + c] == 0 ? v : std::nan("")});
     }
   }
+  // thousands of small circuits leave ~10 heap blocks each: release them on the host threads too
+  if (N >= 1024) parallel_for(N, host_threads(ctx), [&](int c) { progs[c] = CircuitProgram(); });
   P.lower_ms = now_ms() - t0;
   return BWQ_OK;
 }
@@ -1177,6 +1179,14 @@ extern "C" int bwq_meas_data_run(bwq_ctx* ctx, const bwq_batch* b, double* out_i
   if (!ctx->companion) {
     int rc = bwq_create(ctx->device, &ctx->companion);
     if (rc) return fail(ctx, rc, "companion context: %s", bwq_last_error(nullptr));
+    // the statevector side is a chain of short dependent launches: on a high-priority stream its
+    // CTAs are placed ahead of the queued density-matrix tiles instead of waiting for a whole sweep
+    int least = 0, greatest = 0;
+    CK(cudaDeviceGetStreamPriorityRange(&least, &greatest));
+    cudaStream_t hp = nullptr;
+    CK(cudaStreamCreateWithPriority(&hp, cudaStreamNonBlocking, greatest));
+    cudaStreamDestroy(ctx->companion->stream);
+    ctx->companion->stream = hp;
   }
   ctx->companion->opt = ctx->opt;
   int rc_sv = BWQ_OK;
