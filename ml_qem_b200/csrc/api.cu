@@ -1188,11 +1188,17 @@ extern "C" int bwq_meas_data_run(bwq_ctx* ctx, const bwq_batch* b, double* out_i
     cudaStreamDestroy(ctx->companion->stream);
     ctx->companion->stream = hp;
   }
+  // both lowering stages run at once: split the host threads (statevector lowering is the cheaper
+  // one) instead of oversubscribing the cores, which shows up as multi-millisecond join tails
+  const int all_threads = host_threads(ctx), saved_threads = ctx->opt.host_threads;
   ctx->companion->opt = ctx->opt;
+  ctx->companion->opt.host_threads = std::max(1, all_threads / 4);
+  ctx->opt.host_threads = std::max(1, all_threads - ctx->companion->opt.host_threads);
   int rc_sv = BWQ_OK;
   std::thread ideal([&] { rc_sv = bwq_sv_run(ctx->companion, b, out_ideal, status_ideal); });
   const int rc_dm = bwq_dm_run(ctx, b, out_noisy, status_noisy);
   ideal.join();
+  ctx->opt.host_threads = saved_threads;
   if (rc_dm) return rc_dm;
   if (rc_sv) return fail(ctx, rc_sv, "statevector side: %s", bwq_last_error(ctx->companion));
   return BWQ_OK;
