@@ -184,7 +184,10 @@ def bench_sharded_sv(args, rank, world, local_rank, dist, steps, warmup):
     sv = ShardedStatevector(GpuExecutor(eng), dist)
     rng = np.random.default_rng(4)
     obs = F.tfim_observables(list(range(n)), n)
-    circs = [F.tfim_circuit(n, 1 + i % 10, float(rng.uniform(0, 1)), dt=0.25) for i in range(warmup + steps)]
+    # timed circuit i has 1 + (i mod 10) Trotter steps whatever the warm-up count (the warm-up reuses
+    # the first timed circuits), so runs with equal --steps are comparable across GPU counts
+    timed = [F.tfim_circuit(n, 1 + i % 10, float(rng.uniform(0, 1)), dt=0.25) for i in range(steps)]
+    circs = [timed[i % steps] for i in range(warmup)] + timed
 
     def barrier():
         if dist is not None:
@@ -226,7 +229,8 @@ def bench_sharded_sv(args, rank, world, local_rank, dist, steps, warmup):
         "metric": METRIC, "value": steps / t_dev, "unit": UNIT, "n_gpus": world, "steps": steps, "warmup": warmup,
         "ms_per_step": 1e3 * t_dev / steps, "higher_is_better": True, "scaling": "strong", "vs_baseline": None,
         "dtype": "f64", "data": "synthetic",
-        "config": {"workload": args.workload, "n_qubits": n, "observables_per_circuit": len(obs), "trotter_steps": "1..10",
+        "config": {"workload": args.workload, "n_qubits": n, "observables_per_circuit": len(obs),
+                   "trotter_steps": "timed circuit i has 1 + (i mod 10) steps: " + ",".join(str(1 + i % 10) for i in range(steps)),
                    "parallelism": f"amplitude-sharded x{world} (rank = top {world.bit_length() - 1} index bits)",
                    "l2": "shard of %.2f GiB >> 126 MB L2 (no flush needed)" % (16 * 2 ** n / world / 2 ** 30),
                    "timing": "CUDA events on torch's stream, first segment to all_reduce (max over ranks)"},
