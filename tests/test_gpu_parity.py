@@ -355,3 +355,43 @@ def test_dm_14q_full_size_factorised(engine_gpu):
         c2, o2, n2 = helpers.compact(sub, sub_obs, on)
         ref *= helpers.oracle_dm_values(c2, o2, n2)
     assert np.max(np.abs(vals - ref)) <= TOL
+
+
+def test_mixed_widths_failing_circuit_and_empty_batch(engine_gpu):
+    """One batch with widths 3..9 (chunks of different tile sizes, forced pipelining), a circuit the
+    density-matrix path must reject (17 active qubits > 16) without voiding the batch, and the
+    empty batch.  Values against the oracle on the active qubits."""
+    from oracle import noise_model as onm
+
+    width = 17
+    be = backends.synthetic_chain(width, seed=17)
+    nm = noise.from_backend(be)
+    on = onm.from_backend(be.to_dict())
+    rng = np.random.default_rng(31)
+    cm = [(i, i + 1) for i in range(width - 1)] + [(i + 1, i) for i in range(width - 1)]
+    circs, obs = [], []
+    for i in range(280):
+        n = 3 + i % 7
+        circs.append(F.random_basis_circuit(n, int(rng.integers(2 * n, 8 * n)), rng, [p for p in cm if max(p) < n], width))
+        obs.append([[("I" * (width - n) + "".join(rng.choice(list("IXYZ"), size=n)), float(rng.normal()))] for _ in range(2)])
+    wide = F.tfim_circuit(width, 1, 0.3)
+    bad = 137
+    circs[bad], obs[bad] = wide, [[("Z" * width, 1.0)], [("I" * (width - 1) + "Z", 1.0)]]
+    batch = engine.encode_batch(circs, obs)
+    engine_gpu.set_noise(nm)
+    engine_gpu.set_options(flags=8)
+    ideal, noisy, st_i, st_n = engine_gpu.run_meas_data(batch)
+    engine_gpu.set_options()
+    assert not st_i.any()
+    assert st_n[bad] != 0 and not np.delete(st_n, bad).any()
+    offs = np.cumsum([0] + [len(o) for o in obs])
+    assert np.isnan(noisy[offs[bad]:offs[bad + 1]]).all() and not np.isnan(np.delete(noisy, range(offs[bad], offs[bad + 1]))).any()
+    for i in (0, 6, 69, 136, 138, 139, 279):
+        c2, o2, n2 = helpers.compact(circs[i], obs[i], on)
+        assert np.max(np.abs(noisy[offs[i]:offs[i + 1]] - helpers.oracle_dm_values(c2, o2, n2))) <= TOL, i
+        assert np.max(np.abs(ideal[offs[i]:offs[i + 1]] - helpers.oracle_sv_values(c2, o2))) <= TOL, i
+    empty = engine.encode_batch([], [])
+    v, s = engine_gpu.run_dm(empty)
+    assert len(v) == 0 and len(s) == 0
+    i2, n2_, s1, s2 = engine_gpu.run_meas_data(empty)
+    assert len(i2) == 0 and len(n2_) == 0
