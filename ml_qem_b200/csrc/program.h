@@ -185,8 +185,13 @@ struct SvPassHdr {   // 8 B
   uint16_t n_ops;
   uint8_t sa, sb;    // tile slots
   uint8_t needs_index;  // some op reads the physical index (diagonal / conditional)
-  uint8_t pad;
+  uint8_t flags;     // kPassLoadDirect (first pass of the sweep) | kPassStoreDirect (last pass)
 };
+// Statevector sweeps mirror the first-pass descriptor in the high half of SweepDesc::blk_len_q16:
+// kSvFirstDirect | sa | sb << 4 (the block length keeps the low 16 bits).  A pass is eligible when
+// both slots are free slots (>= the always-resident low bits): lanes then walk the contiguous low
+// bits, i.e. whole 256-byte runs.
+constexpr uint32_t kSvFirstDirect = 0x8000u;
 constexpr int kSvTileBitsDefault = 12;  // 64 KiB tiles: 9 instead of 8 free slots' worth of passes per sweep, 7-9 % faster than 11
 constexpr int kSvTileBitsMax = 12;
 constexpr int kSvFreeSlots = 8;       // SweepDesc::pos holds the positions of slots L..K-1
@@ -215,6 +220,7 @@ struct SvxProgram {
 struct SvxOptions {
   int tile_bits = kSvTileBitsDefault;
   int n_global = 0;
+  int direct = 1;  // let the planner request direct first / last passes
 };
 void lower_svx_circuit(const bwq_batch& b, int c, const SvxOptions& o, SvxProgram* out);
 

@@ -109,24 +109,40 @@ __device__ __forceinline__ void sv_op_u2(double2 (&v)[NG][4], const double2* __r
 // One register pass on NG groups per thread (groups grp0 + k * kSvxThreads).  Every thread keeps
 // the 4 amplitudes v[k][ka + 2 kb] of its groups in registers and walks the op list once, so the
 // op decode and the (uniform) parameter loads are shared by the NG groups.
+// ld_g / st_g: direct pass -- the groups come from / go to global memory (gt = the tile's base in
+// the shard; the offset of a group is the deposit of its tile index, the 4 corners add the slot
+// bits 1 << pa, 1 << pb) instead of the shared-memory tile; synth: first sweep, |0...0> is generated.
 template <int NG>
 __device__ __forceinline__ void sv_run_pass(double2* __restrict__ tile, const double* __restrict__ pbuf,
                                             const uint32_t* __restrict__ dep, const uint2* __restrict__ ops, const int n_ops,
                                             const uint32_t grp0, const uint32_t n_grp, const int lo, const int hi,
                                             const uint32_t ma, const uint32_t mb, const uint32_t pa, const uint32_t pb,
-                                            const uint32_t gbase, const int LB, const bool needs_index) {
-  uint32_t idx[NG][4], gidx0[NG];
+                                            const uint32_t gbase, const int LB, const bool needs_index,
+                                            double2* __restrict__ gt, const bool ld_g, const bool st_g, const bool synth) {
+  uint32_t idx[NG][4], gidx0[NG], goff[NG];
   double2 v[NG][4];
   const uint32_t lowmask = (1u << LB) - 1u;
+  const uint32_t ca = 1u << pa, cb = 1u << pb;
 #pragma unroll
   for (int k = 0; k < NG; ++k) {
     const uint32_t grp = min(grp0 + k * kSvxThreads, n_grp - 1u);
     uint32_t b0 = (grp & ((1u << lo) - 1u)) | ((grp >> lo) << (lo + 1));
     b0 = (b0 & ((1u << hi) - 1u)) | ((b0 >> hi) << (hi + 1));
     idx[k][0] = svz(b0); idx[k][1] = svz(b0 | ma); idx[k][2] = svz(b0 | mb); idx[k][3] = svz(b0 | ma | mb);
-    gidx0[k] = needs_index ? (gbase | (b0 & lowmask) | dep[b0 >> LB]) : 0u;
+    goff[k] = (needs_index || ld_g || st_g) ? ((b0 & lowmask) | dep[b0 >> LB]) : 0u;
+    gidx0[k] = gbase | goff[k];
+    if (ld_g) {
+      if (synth) {
+        v[k][0] = make_double2(gidx0[k] == 0u ? 1.0 : 0.0, 0.0);
+        v[k][1] = v[k][2] = v[k][3] = make_double2(0.0, 0.0);
+      } else {
+        const double2* __restrict__ src = gt + goff[k];
+        v[k][0] = __ldcg(src); v[k][1] = __ldcg(src + ca); v[k][2] = __ldcg(src + cb); v[k][3] = __ldcg(src + (ca | cb));
+      }
+    } else {
 #pragma unroll
-    for (int c = 0; c < 4; ++c) v[k][c] = tile[idx[k][c]];
+      for (int c = 0; c < 4; ++c) v[k][c] = tile[idx[k][c]];
+    }
   }
   for (int o = 0; o < n_ops; ++o) {
     const uint2 raw = ops[o];
@@ -173,8 +189,13 @@ __device__ __forceinline__ void sv_run_pass(double2* __restrict__ tile, const do
 #pragma unroll
   for (int k = 0; k < NG; ++k)
     if (NG == 1 ? (grp0 < n_grp) : true) {
+      if (st_g) {
+        double2* __restrict__ dst = gt + goff[k];
+        dst[0] = v[k][0]; dst[ca] = v[k][1]; dst[cb] = v[k][2]; dst[ca | cb] = v[k][3];
+      } else {
 #pragma unroll
-      for (int c = 0; c < 4; ++c) tile[idx[k][c]] = v[k][c];
+        for (int c = 0; c < 4; ++c) tile[idx[k][c]] = v[k][c];
+      }
     }
 }
 
@@ -232,12 +253,19 @@ __global__ void __launch_bounds__(kSvxThreads, 3) sv_sweep_kernel(const SvxLaunc
   }
   {
     const uint4* src = L.prog + uint32_t(swraw.x);
-    const int len = swraw.y;
+    const int len = swraw.y & 0xffff;
     for (int i = tid; i < len; i += kSvxThreads) cp_async16(reinterpret_cast<uint4*>(pbuf) + i, src + i);
   }
+  // first pass direct (descriptor in the high half of blk_len): no staging of the tile; its lines
+  // are prefetched into L2 while the program block is in flight
+  const bool first_direct = ((uint32_t(swraw.y) >> 16) & kSvFirstDirect) != 0u;
 
   const uint32_t p_thr = svz(uint32_t(tid));
-  if (first) {
+  if (first_direct) {
+    if (!first)
+      for (uint32_t u = 8u * tid; u < E; u += 8u * kSvxThreads)   // one 128-byte line = 8 amplitudes
+        asm volatile("prefetch.global.L2 [%0];" ::"l"(g + SVX_DEPOSIT(u)));
+  } else if (first) {
     for (uint32_t u0 = 0; u0 < E; u0 += kSvxThreads) {
       const uint32_t u = u0 + tid;
       if (u < E) sv_tile[p_thr ^ svz(u0)] = make_double2((gbase == 0u && u == 0u) ? 1.0 : 0.0, 0.0);
@@ -262,12 +290,16 @@ __global__ void __launch_bounds__(kSvxThreads, 3) sv_sweep_kernel(const SvxLaunc
 
   const int n_passes = reinterpret_cast<const int*>(pbuf)[0];
   const uint2* phdr = reinterpret_cast<const uint2*>(pbuf + 2);
+  bool stored = false;  // the last pass wrote the tile back itself
   for (int p = 0; p < n_passes; ++p) {
     if (p) __syncthreads();
     const uint2 praw = phdr[p];
     const int ops_q8 = praw.x & 0xffffu, n_ops = praw.x >> 16;
     const int sa = praw.y & 0xffu, sb = (praw.y >> 8) & 0xffu;
     const bool needs_index = ((praw.y >> 16) & 0xffu) != 0u;
+    const bool ld_g = p == 0 && first_direct;
+    const bool st_g = ((praw.y >> 24) & kPassStoreDirect) != 0u;
+    stored = st_g;
     const int lo = min(sa, sb), hi = max(sa, sb);
     const uint32_t ma = 1u << sa, mb = 1u << sb;
     // physical positions of the two slots
@@ -277,11 +309,14 @@ __global__ void __launch_bounds__(kSvxThreads, 3) sv_sweep_kernel(const SvxLaunc
     const uint32_t n_grp = E >> 2;
     if (n_grp % (2u * kSvxThreads) == 0u)
       for (uint32_t g0 = 0; g0 < n_grp; g0 += 2u * kSvxThreads)
-        sv_run_pass<2>(sv_tile, pbuf, dep, ops, n_ops, tid + g0, n_grp, lo, hi, ma, mb, pa, pb, gbase, LB, needs_index);
+        sv_run_pass<2>(sv_tile, pbuf, dep, ops, n_ops, tid + g0, n_grp, lo, hi, ma, mb, pa, pb, gbase, LB, needs_index,
+                       g, ld_g, st_g, first);
     else
       for (uint32_t g0 = 0; g0 < n_grp; g0 += kSvxThreads)
-        sv_run_pass<1>(sv_tile, pbuf, dep, ops, n_ops, tid + g0, n_grp, lo, hi, ma, mb, pa, pb, gbase, LB, needs_index);
+        sv_run_pass<1>(sv_tile, pbuf, dep, ops, n_ops, tid + g0, n_grp, lo, hi, ma, mb, pa, pb, gbase, LB, needs_index,
+                       g, ld_g, st_g, first);
   }
+  if (stored) return;
   __syncthreads();
 
   for (uint32_t u0 = 0; u0 < E; u0 += kSvxThreads) {

@@ -19,6 +19,7 @@
 #include <algorithm>
 #include <cmath>
 #include <complex>
+#include <cstdlib>
 #include <cstring>
 #include <vector>
 
@@ -51,6 +52,7 @@ struct Planner {
   int n = 0, nl = 0, g = 0, K = 0, L = 0;
   std::vector<int> phys, logical_at;   // logical <-> physical bit position
   uint64_t touched = 0;                // logical qubits a non-diagonal op has acted on so far
+  bool direct_passes = true;           // SvxOptions::direct
   std::vector<double> mats;
   // stage state
   std::vector<HPass> passes;
@@ -273,7 +275,8 @@ struct Planner {
     return b;
   }
 
-  void emit_sweep(const std::vector<int>& sel, std::vector<char>& in_tile) {
+  void emit_sweep(const std::vector<int>& sel_in, std::vector<char>& in_tile) {
+    std::vector<int> sel(sel_in);
     int nt = 0;
     for (int p = 0; p < nl; ++p) nt += in_tile[p];
     for (int p = 0; p < nl && nt < K; ++p) if (!in_tile[p]) { in_tile[p] = 1; ++nt; }
@@ -287,6 +290,35 @@ struct Planner {
         ++s;
       }
     for (int i = K - L; i < 8; ++i) sw.pos[i] = 31;  // unused slots
+    // direct passes: a pass that commutes with everything before / after it in this sweep (no
+    // shared touched qubit) and whose slots are free slots moves to the front / back and exchanges
+    // its register groups with global memory itself (sv_kernels.cuh)
+    auto slots_of = [&](const HPass& p, int& sa, int& sb) {
+      sa = p.qa >= 0 ? slot_of[phys[p.qa]] : -1; sb = p.qb >= 0 ? slot_of[phys[p.qb]] : -1;
+      if (sa < 0) sa = (sb == 0) ? 1 : 0;
+      if (sb < 0) sb = (sa == 0) ? 1 : 0;
+    };
+    auto eligible = [&](int i) { int sa, sb; slots_of(passes[i], sa, sb); return sa >= L && sb >= L && L >= 3; };
+    bool first_direct = false, last_direct = false;
+    if (direct_passes) {
+      for (size_t k = 0; k < sel.size() && !first_direct; ++k) {
+        if (!eligible(sel[k])) continue;
+        bool free_ = true;
+        for (size_t e = 0; e < k && free_; ++e) free_ = !(passes[sel[e]].touch & passes[sel[k]].touch);
+        if (!free_) continue;
+        std::rotate(sel.begin(), sel.begin() + k, sel.begin() + k + 1);
+        first_direct = true;
+      }
+      const size_t stop = (first_direct && sel.size() > 1) ? 1 : 0;
+      for (size_t k = sel.size(); k-- > stop && !last_direct;) {
+        if (!eligible(sel[k])) continue;
+        bool free_ = true;
+        for (size_t l = k + 1; l < sel.size() && free_; ++l) free_ = !(passes[sel[l]].touch & passes[sel[k]].touch);
+        if (!free_) continue;
+        std::rotate(sel.begin() + k, sel.begin() + k + 1, sel.end());
+        last_direct = true;
+      }
+    }
     size_t n_ops = 0;
     for (int i : sel) n_ops += passes[i].ops.size();
     auto al16 = [](size_t x) { return (x + 15) & ~size_t(15); };
@@ -304,9 +336,10 @@ struct Planner {
     size_t oc = 0, pc = o_par;
     for (size_t k = 0; k < sel.size(); ++k) {
       const HPass& p = passes[sel[k]];
-      int sa = p.qa >= 0 ? slot_of[phys[p.qa]] : -1, sb = p.qb >= 0 ? slot_of[phys[p.qb]] : -1;
-      if (sa < 0) sa = (sb == 0) ? 1 : 0;
-      if (sb < 0) sb = (sa == 0) ? 1 : 0;
+      int sa, sb;
+      slots_of(p, sa, sb);
+      if (k == 0 && first_direct) ph[k].flags |= kPassLoadDirect;
+      if (k + 1 == sel.size() && last_direct) ph[k].flags |= kPassStoreDirect;
       ph[k].ops_q8 = (uint16_t)((o_ops + sizeof(SvBlockOp) * oc) / 8);
       ph[k].n_ops = (uint16_t)p.ops.size();
       ph[k].sa = (uint8_t)sa; ph[k].sb = (uint8_t)sb;
@@ -339,6 +372,7 @@ struct Planner {
     }
     sw.blk_q16 = (uint32_t)(blk_begin / 2);
     sw.blk_len_q16 = (uint32_t)(bytes / 16);
+    if (first_direct) sw.blk_len_q16 |= (kSvFirstDirect | (uint32_t)ph[0].sa | ((uint32_t)ph[0].sb << 4)) << 16;
     out->sweeps.push_back(sw);
     // a qubit only diagonal ops / control tests have seen is still |0>: amplitudes with a 1 on its
     // bit are zero, so tiles (or whole shards) with such an outside bit set can be skipped
@@ -435,6 +469,7 @@ struct Planner {
         if (!in_tile[pb]) { in_tile[pb] = 1; ++nt; }
         HPass p;
         p.qa = swaps[j].first; p.qb = swaps[j].second;
+        p.touch = (1ull << p.qa) | (1ull << p.qb);
         HOp op; op.kind = SVO_SWAP; op.qa = (int8_t)p.qa; op.qb = (int8_t)p.qb;
         p.ops.push_back(op);
         sel.push_back((int)passes.size());
@@ -512,6 +547,7 @@ void lower_svx_circuit(const bwq_batch& b, int c, const SvxOptions& opt, SvxProg
   if (n > kMaxSvQubits + 1) { out->status = BWQ_CIRC_TOO_WIDE; return; }
   Planner P;
   P.out = out;
+  P.direct_passes = opt.direct != 0 && std::getenv("BWQ_SVX_NO_DIRECT") == nullptr;  // env: kernel experiments
   P.n = n; P.g = gl; P.nl = n - gl;
   P.K = std::min(std::min(std::max(opt.tile_bits, 2), kSvTileBitsMax), P.nl);
   P.L = std::max(0, P.K - kSvFreeSlots);

@@ -10,7 +10,7 @@ SVF_ON_B, SVF_COND, SVF_COND_VAL = 1, 2, 4
 
 def decode_block(info, sw):
     words = info["prog"]
-    blk = words[2 * int(sw[0]): 2 * (int(sw[0]) + int(sw[9]))]
+    blk = words[2 * int(sw[0]): 2 * (int(sw[0]) + (int(sw[9]) & 0xffff))]  # high half: first-pass descriptor
     b = blk.view(np.uint8)
     n_passes = int(blk[:1].view(np.int32)[0])
     passes = []
