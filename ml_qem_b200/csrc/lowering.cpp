@@ -25,6 +25,7 @@ static const cd I_(0.0, 1.0);
 int NoiseTable::set(const bwq_noise_table* t, char* err, size_t errlen) {
   data.clear();
   entries.clear();
+  one_q.clear();
   if (!t || t->n_entries == 0) return BWQ_OK;
   if (t->n_entries < 0 || !t->opcode || !t->q0 || !t->q1 || !t->kind || !t->data_off || !t->data) {
     snprintf(err, errlen, "noise table: null array");
@@ -50,11 +51,25 @@ int NoiseTable::set(const bwq_noise_table* t, char* err, size_t errlen) {
   }
   std::sort(entries.begin(), entries.end(),
             [](const auto& a, const auto& b) { return a.first < b.first; });
+  one_q.clear();  // find() below searches while the table is being filled
+  std::vector<int32_t> tab(32 * 64, -1);
+  for (int op = 0; op < 32; ++op)
+    for (int q = 0; q < 64; ++q) {
+      const NoiseEntry* e = find((uint16_t)op, q, 255);
+      if (!e) continue;
+      for (size_t i = 0; i < entries.size(); ++i)
+        if (&entries[i].second == e) { tab[op * 64 + q] = (int32_t)i; break; }
+    }
+  one_q.swap(tab);
   return BWQ_OK;
 }
 
 const NoiseEntry* NoiseTable::find(uint16_t opcode, int q0, int q1) const {
   if (entries.empty()) return nullptr;
+  if (q1 == 255 && opcode < 32 && q0 >= 0 && q0 < 64 && !one_q.empty()) {
+    const int32_t i = one_q[opcode * 64 + q0];
+    return i < 0 ? nullptr : &entries[(size_t)i].second;
+  }
   auto look = [&](uint32_t key) -> const NoiseEntry* {
     auto it = std::lower_bound(entries.begin(), entries.end(), key,
                                [](const auto& a, uint32_t k) { return a.first < k; });
@@ -341,7 +356,9 @@ void lower_dm_circuit(const NoiseTable& noise, const bwq_batch& b, int c, const 
   if (out->status) return;
 
   // ---- gates -> passes
+  out->mats.reserve((size_t)(g1 - g0) * 6 + 64);
   std::vector<HostPass> passes;
+  passes.reserve(64);
   std::vector<double> pend(16 * nd);
   std::vector<char> has(nd, 0);
   std::vector<int> last(nd, -1);
@@ -461,9 +478,11 @@ void lower_dm_circuit(const NoiseTable& noise, const bwq_batch& b, int c, const 
     std::vector<uint32_t> mine;
     auto add = [&](uint32_t key, int words) {
       if (!words) return;
-      for (const Seen& sn : seen) if (sn.key == key) return;
-      for (uint32_t k : mine) if (k == key) return;
-      mine.push_back(key);
+      if (!(key & kLocalMat)) {  // circuit-local matrices are unique per use: only noise-table entries are shared
+        for (const Seen& sn : seen) if (sn.key == key) return;
+        for (uint32_t k : mine) if (k == key) return;
+        mine.push_back(key);
+      }
       bytes += ((words + 1) & ~1) * 8;
     };
     for (const MacroOp& o : p.ops) { add(o.off_a, pre_words(o.pre_a)); add(o.off_b, pre_words(o.pre_b)); add(o.off_2, two_words(o.twoq)); }
@@ -530,7 +549,7 @@ void lower_dm_circuit(const NoiseTable& noise, const bwq_batch& b, int c, const 
       // remember the parameters this pass brings (offsets are assigned at emission)
       for (const MacroOp& o : p.ops) {
         auto note = [&](uint32_t key, int words) {
-          if (!words) return;
+          if (!words || (key & kLocalMat)) return;
           for (const Seen& sn : seen) if (sn.key == key) return;
           seen.push_back(Seen{key, 0});
         };
@@ -589,11 +608,12 @@ void lower_dm_circuit(const NoiseTable& noise, const bwq_batch& b, int c, const 
     seen.clear();
     auto place = [&](uint32_t key, int words) -> uint16_t {
       if (!words) return 0;
-      for (const Seen& sn : seen) if (sn.key == key) return sn.off;
+      const bool shared = !(key & kLocalMat);
+      if (shared) for (const Seen& sn : seen) if (sn.key == key) return sn.off;
       const uint16_t off = (uint16_t)par_cursor;
       std::memcpy(blk + par_cursor, src_ptr(key), (size_t)words * 8);
       par_cursor += (size_t)((words + 1) & ~1);
-      seen.push_back(Seen{key, off});
+      if (shared) seen.push_back(Seen{key, off});
       return off;
     };
     for (size_t k = 0; k < sel.size(); ++k) {

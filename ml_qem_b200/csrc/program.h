@@ -90,6 +90,9 @@ struct NoiseTable {
   std::vector<double> data;
   // key = opcode << 16 | q0 << 8 | q1   (q1 = 255 for 1-qubit, q0 = 255 for all-qubit default)
   std::vector<std::pair<uint32_t, NoiseEntry>> entries;  // sorted by key
+  // 1-qubit gates (most of a transpiled circuit): resolved entry per (opcode < 32, qubit < 64),
+  // all-qubit default included; -1 = no error, -2 = not tabulated (fall back to the search)
+  std::vector<int32_t> one_q;
   int set(const bwq_noise_table* t, char* err, size_t errlen);
   const NoiseEntry* find(uint16_t opcode, int q0, int q1) const;
   bool empty() const { return entries.empty(); }
