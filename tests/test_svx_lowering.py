@@ -103,3 +103,35 @@ def test_exchange_count_tfim_chain_30q_plan(lib):
     info = prog.info
     assert info["status"] == 0 and info["n_local"] == 27 and info["n_global"] == 3
     assert 1 <= info["n_exchanges"] <= 12
+
+
+def test_direct_pass_flags_of_statevector_sweeps(lib):
+    """sv_sweep_kernel direct passes: the flagged first / last pass of a sweep uses free slots
+    only (>= the always-resident low bits) and the first-pass descriptor in the high half of the
+    sweep's block length repeats the first pass header.  (The reordered programs are run by the
+    emulator in the other tests of this file.)"""
+    from ml_qem_b200.engine import SvxProgram
+    from svx_emulator import decode_block
+
+    n = 20
+    circ = F.tfim_circuit(n, 3, 0.4)
+    prog = SvxProgram(engine.encode_batch([circ], [F.tfim_observables(list(range(n)), n)]), 0, 12, 0)
+    info = prog.info
+    LB = max(0, info["tile_bits"] - 8)
+    n_first = n_last = 0
+    for sw in info["sweeps"]:
+        desc = (int(sw[9]) >> 16) & 0xffff
+        passes, _ = decode_block(info, sw)
+        words = info["prog"][2 * int(sw[0]): 2 * (int(sw[0]) + (int(sw[9]) & 0xffff))].view(np.uint8)
+        flags = [int(words[16 + 8 * p + 7]) for p in range(len(passes))]
+        assert all(f == 0 for f in flags[1:-1])
+        if flags[0] & 1:
+            sa, sb = passes[0][0], passes[0][1]
+            assert sa >= LB and sb >= LB and desc == (0x8000 | sa | (sb << 4))
+            n_first += 1
+        else:
+            assert desc & 0x8000 == 0
+        if flags[-1] & 2:
+            assert passes[-1][0] >= LB and passes[-1][1] >= LB
+            n_last += 1
+    assert n_first > 0 and n_last > 0
