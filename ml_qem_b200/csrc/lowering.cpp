@@ -26,6 +26,8 @@ int NoiseTable::set(const bwq_noise_table* t, char* err, size_t errlen) {
   data.clear();
   entries.clear();
   one_q.clear();
+  fixed_ptm.clear();
+  fixed_ok.clear();
   if (!t || t->n_entries == 0) return BWQ_OK;
   if (t->n_entries < 0 || !t->opcode || !t->q0 || !t->q1 || !t->kind || !t->data_off || !t->data) {
     snprintf(err, errlen, "noise table: null array");
@@ -61,6 +63,7 @@ int NoiseTable::set(const bwq_noise_table* t, char* err, size_t errlen) {
         if (&entries[i].second == e) { tab[op * 64 + q] = (int32_t)i; break; }
     }
   one_q.swap(tab);
+  build_fixed();
   return BWQ_OK;
 }
 
@@ -288,6 +291,21 @@ static bool gate_ptm1(uint16_t op, const double* p, double* r) {
   }
 }
 
+void NoiseTable::build_fixed() {
+  fixed_ptm.assign((size_t)32 * 64 * 16, 0.0);
+  fixed_ok.assign((size_t)32 * 64, 0);
+  for (int op = 0; op < 32; ++op) {
+    if (gate_num_params((uint16_t)op) != 0 || op == BWQ_G_RESET) continue;
+    for (int q = 0; q < 64; ++q) {
+      const NoiseEntry* ne = find((uint16_t)op, q, 255);
+      double r[16];
+      if (!ne || !gate_ptm1((uint16_t)op, nullptr, r)) continue;
+      mat4_mul(&data[ne->off], r, &fixed_ptm[(size_t)(op * 64 + q) * 16]);  // same product as the gate loop
+      fixed_ok[op * 64 + q] = 1;
+    }
+  }
+}
+
 // ----------------------------------------------------------------------------- DM lowering
 namespace {
 struct HostPass {
@@ -413,10 +431,15 @@ void lower_dm_circuit(const NoiseTable& noise, const bwq_batch& b, int c, const 
         mat4_rot_mul(std::cos(par[0]), std::sin(par[0]), &pend[16 * d], &pend[16 * d]);
         continue;
       }
-      if (!gate_ptm1(op.opcode, par, r)) { out->status = BWQ_CIRC_BAD_OP; return; }
-      if (ne) mat4_mul(&noise.data[ne->off], r, r);
-      if (has[d]) mat4_mul(r, &pend[16 * d], &pend[16 * d]);
-      else { std::memcpy(&pend[16 * d], r, sizeof r); has[d] = 1; }
+      const double* gm = r;
+      if (ne && op.opcode < 32 && op.q0 < 64 && !noise.fixed_ok.empty() && noise.fixed_ok[op.opcode * 64 + op.q0]) {
+        gm = &noise.fixed_ptm[(size_t)(op.opcode * 64 + op.q0) * 16];  // error x gate, precomputed
+      } else {
+        if (!gate_ptm1(op.opcode, par, r)) { out->status = BWQ_CIRC_BAD_OP; return; }
+        if (ne) mat4_mul(&noise.data[ne->off], r, r);
+      }
+      if (has[d]) mat4_mul(gm, &pend[16 * d], &pend[16 * d]);
+      else { std::memcpy(&pend[16 * d], gm, sizeof r); has[d] = 1; }
       continue;
     }
     int d0 = digit_of[op.q0], d1 = digit_of[op.q1];

@@ -93,6 +93,11 @@ struct NoiseTable {
   // 1-qubit gates (most of a transpiled circuit): resolved entry per (opcode < 32, qubit < 64),
   // all-qubit default included; -1 = no error, -2 = not tabulated (fall back to the search)
   std::vector<int32_t> one_q;
+  // noisy transfer matrix (error x gate, 16 doubles) of every parameter-free 1-qubit gate that has
+  // an error: index (opcode * 64 + qubit) * 16, valid where fixed_ok is set
+  std::vector<double> fixed_ptm;
+  std::vector<char> fixed_ok;
+  void build_fixed();
   int set(const bwq_noise_table* t, char* err, size_t errlen);
   const NoiseEntry* find(uint16_t opcode, int q0, int q1) const;
   bool empty() const { return entries.empty(); }
