@@ -126,8 +126,10 @@ static bool unitary1(uint16_t op, const double* p, cd* m) {
       m[0] = c; m[1] = -I_ * s; m[2] = -I_ * s; m[3] = c; return true; }
     case BWQ_G_RY: { double c = std::cos(p[0] / 2), s = std::sin(p[0] / 2);
       m[0] = c; m[1] = -s; m[2] = s; m[3] = c; return true; }
-    case BWQ_G_RZ: m[0] = std::exp(-I_ * (p[0] / 2)); m[1] = 0; m[2] = 0; m[3] = std::exp(I_ * (p[0] / 2)); return true;
-    case BWQ_G_P: m[0] = 1; m[1] = 0; m[2] = 0; m[3] = std::exp(I_ * p[0]); return true;
+    // exp(+-i t) written as (cos t, +-sin t): what std::exp(complex) returns, without its overhead
+    case BWQ_G_RZ: { const double c = std::cos(p[0] / 2), sn = std::sin(p[0] / 2);
+      m[0] = cd(c, -sn); m[1] = 0; m[2] = 0; m[3] = cd(c, sn); return true; }
+    case BWQ_G_P: m[0] = 1; m[1] = 0; m[2] = 0; m[3] = cd(std::cos(p[0]), std::sin(p[0])); return true;
     case BWQ_G_U2: u3_mat(M_PI / 2, p[0], p[1], m); return true;
     case BWQ_G_U3: u3_mat(p[0], p[1], p[2], m); return true;
     case BWQ_G_UNITARY1: for (int i = 0; i < 4; ++i) m[i] = cd(p[2 * i], p[2 * i + 1]); return true;
@@ -668,9 +670,14 @@ void lower_dm_circuit(const NoiseTable& noise, const bwq_batch& b, int c, const 
 }
 
 // ----------------------------------------------------------------------------- SV lowering
+// 2x2 complex product in plain real arithmetic: the (ac - bd, ad + bc) of std::complex without
+// its NaN recovery path (identical for finite values)
+static inline cd cmulf(const cd& x, const cd& y) {
+  return cd(x.real() * y.real() - x.imag() * y.imag(), x.real() * y.imag() + x.imag() * y.real());
+}
 static void mat2c_mul(const cd* a, const cd* b, cd* out) {
   cd t[4];
-  for (int i = 0; i < 2; ++i) for (int j = 0; j < 2; ++j) t[i * 2 + j] = a[i * 2] * b[j] + a[i * 2 + 1] * b[2 + j];
+  for (int i = 0; i < 2; ++i) for (int j = 0; j < 2; ++j) t[i * 2 + j] = cmulf(a[i * 2], b[j]) + cmulf(a[i * 2 + 1], b[2 + j]);
   for (int i = 0; i < 4; ++i) out[i] = t[i];
 }
 
