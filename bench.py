@@ -14,7 +14,9 @@ circuits (steps 1..5) on a 16-qubit heavy-hex-like chain table, 100 Pauli twirls
 
 JSON keys: see the contract in the task statement; `value` is timed with the lowered programs
 resident in HBM (bwq_dm_execute + bwq_sv_execute), `e2e` through the C ABI with HOST buffers
-(bwq_dm_run + bwq_sv_run: lowering, H2D of the programs, kernels, D2H of the values).
+(one bwq_meas_data_run per step = ideal + noisy values of the batch: lowering, H2D of the programs,
+kernels, D2H of the values; the density-matrix side is pipelined in segments, the statevector side
+runs concurrently on a companion context).
 `--impl reference` times the Aer-style CPU restatement (oracle/cpu_ref.cpp; qiskit-aer itself is
 not installable here) on the host cores, on a bounded sample of the same workload.
 """
