@@ -335,17 +335,19 @@ def from_any(obj):
             if canonical(name) == "measure":
                 circ.ops.append(("measure", (qs[0],), ()))
                 continue
+            if canonical(name) == "unitary":  # UnitaryGate: its parameter is the matrix, not an angle
+                mat = np.asarray(op.to_matrix() if hasattr(op, "to_matrix") else op.params[0], dtype=complex)
+                if mat.shape not in ((2, 2), (4, 4)):
+                    raise ValueError(f"unitary on {len(qs)} qubits: only 1- and 2-qubit unitaries are supported")
+                flat = np.stack([mat.real, mat.imag], -1).reshape(-1)
+                circ.ops.append(("unitary1" if mat.shape[0] == 2 else "unitary2", tuple(qs), tuple(flat)))
+                continue
             params = []
             for p in op.params:
                 try:
                     params.append(float(p))
                 except TypeError as exc:
                     raise ValueError("unbound parameters: bind them (parameter_values) before lowering") from exc
-            if canonical(name) == "unitary":
-                mat = np.asarray(op.to_matrix() if hasattr(op, "to_matrix") else op.params[0], dtype=complex)
-                flat = np.stack([mat.real, mat.imag], -1).reshape(-1)
-                circ.ops.append(("unitary1" if mat.shape[0] == 2 else "unitary2", tuple(qs), tuple(flat)))
-                continue
             circ.append(name, qs, params)
         return circ
     raise TypeError(f"cannot interpret {type(obj).__name__} as a circuit")

@@ -150,29 +150,55 @@ class FlatBatch:
                                       self.term_offsets, self.term_x, self.term_z, self.term_coeff))
 
     def select(self, idx):
-        """Sub-batch with the circuits ``idx`` (used to shard a batch across ranks)."""
+        """Sub-batch with the circuits ``idx`` (used to shard a batch across ranks).  Only the
+        parameters the selected gates reference are copied (compacted per circuit), so batches whose
+        variants share parameter slots at the end of the array (zne.twirl_batch / fold_batch) do not
+        blow up."""
         idx = np.asarray(idx, dtype=np.int64)
-        ops, params, tx, tz, tc = [], [], [], [], []
-        op_off, obs_off, term_off = [0], [0], [0]
-        npar = 0
-        for c in idx:
-            o = self.ops[self.op_offsets[c]:self.op_offsets[c + 1]].copy()
-            if len(o):
-                lo = int(o["param_idx"].min())
-                hi = min(len(self.params), int(o["param_idx"].max()) + 32)
-                o["param_idx"] = o["param_idx"] - lo + npar
-                params.append(self.params[lo:hi])
-                npar += hi - lo
-            ops.append(o)
-            op_off.append(op_off[-1] + len(o))
-            for ob in range(self.obs_offsets[c], self.obs_offsets[c + 1]):
-                a, b = self.term_offsets[ob], self.term_offsets[ob + 1]
-                tx.append(self.term_x[a:b]); tz.append(self.term_z[a:b]); tc.append(self.term_coeff[a:b])
-                term_off.append(term_off[-1] + (b - a))
-            obs_off.append(obs_off[-1] + (self.obs_offsets[c + 1] - self.obs_offsets[c]))
-        cat = lambda xs, dt: np.concatenate(xs).astype(dt) if xs else np.zeros(0, dtype=dt)
-        return FlatBatch(self.n_qubits[idx], op_off, cat(ops, OP_DTYPE), cat(params, np.float64), obs_off, term_off,
-                         cat(tx, np.uint64), cat(tz, np.uint64), cat(tc, np.float64))
+        npar_of = _num_params_table()
+        op_lo, op_hi = self.op_offsets[idx], self.op_offsets[idx + 1]
+        op_off = np.concatenate([[0], np.cumsum(op_hi - op_lo)])
+        gather = _ranges(op_lo, op_hi)
+        ops = self.ops[gather].copy()
+        # parameters: one run [param_idx, param_idx + n_params(opcode)) per gate, re-packed in gate order
+        npar = npar_of[ops["opcode"]].astype(np.int64)
+        new_idx = np.concatenate([[0], np.cumsum(npar)])
+        params = self.params[_ranges(ops["param_idx"].astype(np.int64), ops["param_idx"].astype(np.int64) + npar)]
+        if new_idx[-1] >= 2 ** 32:
+            raise ValueError("sub-batch has too many parameters for 32-bit indices")
+        ops["param_idx"] = new_idx[:-1].astype(np.uint32)
+        ob_lo, ob_hi = self.obs_offsets[idx], self.obs_offsets[idx + 1]
+        obs_off = np.concatenate([[0], np.cumsum(ob_hi - ob_lo)])
+        obs = _ranges(ob_lo, ob_hi)
+        t_lo, t_hi = self.term_offsets[obs], self.term_offsets[obs + 1]
+        term_off = np.concatenate([[0], np.cumsum(t_hi - t_lo)])
+        terms = _ranges(t_lo, t_hi)
+        return FlatBatch(self.n_qubits[idx], op_off, ops, params, obs_off, term_off,
+                         self.term_x[terms], self.term_z[terms], self.term_coeff[terms])
+
+
+def _ranges(lo, hi):
+    """Concatenation of arange(lo[i], hi[i]) for all i (vectorised)."""
+    lo = np.asarray(lo, dtype=np.int64)
+    n = np.asarray(hi, dtype=np.int64) - lo
+    total = int(n.sum())
+    if total == 0:
+        return np.zeros(0, dtype=np.int64)
+    starts = np.repeat(lo - np.concatenate([[0], np.cumsum(n)[:-1]]), n)
+    return starts + np.arange(total, dtype=np.int64)
+
+
+_NPAR_TABLE = None
+
+
+def _num_params_table():
+    global _NPAR_TABLE
+    if _NPAR_TABLE is None:
+        t = np.zeros(max(OPCODES.values()) + 1, dtype=np.int32)
+        for name, code in OPCODES.items():
+            t[code] = NUM_PARAMS.get(name, 0)
+        _NPAR_TABLE = t
+    return _NPAR_TABLE
 
 
 def encode_batch(circuits, observables):
@@ -219,6 +245,8 @@ def _noise_struct(table):
     return st, keep
 
 
+_KEEP_NOISE = object()  # run_dm(noise=...) default: keep the installed table
+
 STATUS_TEXT = {0: "ok", 1: "unsupported or malformed operation", 2: "too many active qubits", 3: "qubit index out of range"}
 
 
@@ -234,8 +262,9 @@ class Engine:
             self._ctx = None
             raise EngineError(f"bwq_create failed ({rc}): {msg}")
         self.device = int(device)
-        self._lock = threading.Lock()
+        self._lock = threading.RLock()
         self._noise_id = None
+        self._noise_ref = self._noise_table_ref = None
         if options:
             self.set_options(**options)
 
@@ -264,22 +293,38 @@ class Engine:
         """model: ml_qem_b200.noise.NoiseModel or None (noise-free)."""
         key = id(model) if model is not None else None
         with self._lock:
-            st, keep = _noise_struct(model.to_table() if model is not None else None)
+            table = model.to_table() if model is not None else None
+            st, keep = _noise_struct(table)
             self._check(self._lib.bwq_set_noise_table(self._ctx, C.byref(st) if st is not None else None),
                         "bwq_set_noise_table")
             self._noise_id = key
+            # the installed table: the model object and the table it was built from (a model edited
+            # afterwards rebuilds its table, so it is installed again)
+            self._noise_ref, self._noise_table_ref = model, table
 
-    def _run(self, fn, batch, what):
+    def _ensure_noise(self, model):
+        """Installs ``model`` unless it already is the installed table (caller holds the lock)."""
+        if model is _KEEP_NOISE:
+            return
+        table = model.to_table() if model is not None else None
+        if model is not self._noise_ref or table is not self._noise_table_ref:
+            self.set_noise(model)
+
+    def _run(self, fn, batch, what, noise=None):
         vals = np.empty(batch.n_observables, dtype=np.float64)
         status = np.zeros(batch.n_circuits, dtype=np.int32)
         st = batch.c_struct()
         with self._lock:
+            self._ensure_noise(_KEEP_NOISE if noise is None else noise[0])
             self._check(fn(self._ctx, C.byref(st), vals.ctypes.data_as(C.c_void_p), status.ctypes.data_as(C.c_void_p)), what)
         return vals, status
 
-    def run_dm(self, batch):
-        """Noisy values (density matrix under the installed noise table) -> (values, status)."""
-        return self._run(self._lib.bwq_dm_run, batch, "bwq_dm_run")
+    def run_dm(self, batch, noise=_KEEP_NOISE):
+        """Noisy values (density matrix) -> (values, status).  ``noise``: the NoiseModel the batch
+        must run under -- installed (only if it is not the installed table already) and used
+        under ONE lock, so engines shared between estimators / threads never mix tables; default:
+        whatever ``set_noise`` installed last."""
+        return self._run(self._lib.bwq_dm_run, batch, "bwq_dm_run", None if noise is _KEEP_NOISE else (noise,))
 
     def prepare_dm(self, batch):
         """Lowers + uploads the batch; the program stays resident on the device.  -> status"""
@@ -315,7 +360,7 @@ class Engine:
         """Ideal values (statevector) -> (values, status)."""
         return self._run(self._lib.bwq_sv_run, batch, "bwq_sv_run")
 
-    def run_meas_data(self, batch):
+    def run_meas_data(self, batch, noise=_KEEP_NOISE):
         """(ideal, noisy) values of every circuit in one call -- the batch form of the reference's
         ``create_estimator_meas_data`` (blackwater/data/utils.py:418-431); the statevector side
         runs concurrently with the density-matrix pipeline.  -> (ideal, noisy, status_ideal, status_noisy)"""
@@ -325,6 +370,7 @@ class Engine:
         st_n = np.zeros(batch.n_circuits, dtype=np.int32)
         st = batch.c_struct()
         with self._lock:
+            self._ensure_noise(noise)
             self._check(self._lib.bwq_meas_data_run(self._ctx, C.byref(st), ideal.ctypes.data_as(C.c_void_p),
                                                     noisy.ctypes.data_as(C.c_void_p), st_i.ctypes.data_as(C.c_void_p),
                                                     st_n.ctypes.data_as(C.c_void_p)), "bwq_meas_data_run")
@@ -338,12 +384,13 @@ class Engine:
         self._check(fn(self._ctx, C.c_void_p(int(local_ptr)), peers.ctypes.data_as(C.c_void_p), len(peers), int(rank),
                        int(n_local_amps), C.c_void_p(int(stream)) if stream else None), "bwq_svx_exchange")
 
-    def run_dm_into(self, batch, device_ptr):
+    def run_dm_into(self, batch, device_ptr, noise=_KEEP_NOISE):
         """Writes the values into device memory at ``device_ptr`` (e.g. torch ``tensor.data_ptr()``
         of a float64 CUDA tensor with n_observables elements) -- zero-copy label hand-off."""
         status = np.zeros(batch.n_circuits, dtype=np.int32)
         st = batch.c_struct()
         with self._lock:
+            self._ensure_noise(noise)
             self._check(self._lib.bwq_dm_run_device_out(self._ctx, C.byref(st), C.c_void_p(int(device_ptr)),
                                                         status.ctypes.data_as(C.c_void_p)), "bwq_dm_run_device_out")
         return status

@@ -166,10 +166,10 @@ class B200Estimator:
 
     # -- the work
     def _engine_handle(self):
+        """The engine of this estimator: the per-device shared one, or -- when engine options were
+        given -- a private one, so the options never leak into other estimators."""
         if self._engine is None:
-            self._engine = shared_engine(self._device)
-        if self._engine_options:
-            self._engine.set_options(**self._engine_options)
+            self._engine = Engine(self._device, **self._engine_options) if self._engine_options else shared_engine(self._device)
         return self._engine
 
     def _call(self, circuits, observables, parameter_values, **run_options):
@@ -192,25 +192,33 @@ class B200Estimator:
                 bound.append(circuit_mod.from_any(b))
                 groups.append([])
             groups[keys[key]].append(i)
-        batch = encode_batch(bound, [[observables[i] for i in g] for g in groups])
+        # complex coefficients (Aer returns np.real_if_close of the complex sum): the C ABI takes
+        # real coefficients, so such an observable is evaluated as <Re O> + i <Im O>
+        cplx = [i for i, o in enumerate(observables) if o.is_complex()]
+        obs_lists = [[observables[i].real_part() if observables[i].is_complex() else observables[i] for i in g] +
+                     [observables[i].imag_part() for i in g if observables[i].is_complex()] for g in groups]
+        batch = encode_batch(bound, obs_lists)
         eng = self._engine_handle()
         noisy = self._noise is not None and not self._noise.is_ideal()
         method = "density_matrix" if noisy else "statevector"
-        if noisy:
-            eng.set_noise(self._noise)
 
         def evaluate(b):
-            vals, status = eng.run_dm(b) if noisy else eng.run_sv(b)
+            # the noise table is installed and used under one engine lock (shared engines)
+            vals, status = eng.run_dm(b, noise=self._noise) if noisy else eng.run_sv(b)
             bad = np.nonzero(status)[0]
             if len(bad):
                 c = int(bad[0])
                 raise ValueError(f"circuit {groups[c][0]}: {STATUS_TEXT.get(int(status[c]), 'error')}")
-            out = np.empty(len(circuits), dtype=float)
+            out = np.empty(len(circuits), dtype=complex if cplx else float)
             k = 0
             for g in groups:
                 for i in g:
                     out[i] = vals[k]
                     k += 1
+                for i in g:
+                    if observables[i].is_complex():
+                        out[i] += 1j * vals[k]
+                        k += 1
             return out
 
         meta = [{"simulator_metadata": {"method": method, "device": f"cuda:{self._device}"}} for _ in circuits]

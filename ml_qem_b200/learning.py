@@ -159,6 +159,8 @@ class PostProcessedJob:
     def result(self):
         result = self._base_job.result()
         bound = [_bind(c, p) for c, p in zip(self._circuits, self._parameter_values)]
+        if not self._skip_transpile:
+            bound = _transpile_or_warn(bound, self._backend)
         for obs in self._observables:
             try:
                 observable_mod.from_any(obs)
@@ -179,6 +181,22 @@ class PostProcessedJob:
 
     def __repr__(self):
         return f"<LearningJob: {self._base_job.job_id()}>"
+
+
+def _transpile_or_warn(circuits, backend):
+    """skip_transpile=False (the reference's default, estimator.py:233-238: transpile at
+    optimization_level=3 before encoding).  Uses qiskit's transpiler when it is importable;
+    otherwise the circuits are encoded as given and the caller is told so."""
+    try:
+        from qiskit import transpile  # type: ignore
+    except Exception:  # noqa: BLE001
+        import warnings
+
+        warnings.warn("learning(skip_transpile=False): qiskit is not importable, so no transpiler is available; "
+                      "the circuits are encoded as given (pass circuits already in the backend basis)",
+                      RuntimeWarning, stacklevel=3)
+        return circuits
+    return [transpile(c, backend, optimization_level=3) if not hasattr(c, "gate_ops") else c for c in circuits]
 
 
 def patch_run(run, processor, skip_transpile=True, backend=None, options=None):

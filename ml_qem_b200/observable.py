@@ -24,8 +24,21 @@ class PauliObservable:
     def __iter__(self):
         return iter(self.terms)
 
+    def is_complex(self):
+        """True when some coefficient has a non-zero imaginary part (the expectation value is then
+        complex, as Aer's ``np.real_if_close`` of the complex sum would return it)."""
+        return any(c.imag != 0.0 for _, c in self.terms)
+
+    def imag_part(self):
+        """Observable with the imaginary parts of the coefficients: <O> = <Re O> + i <Im O>."""
+        return PauliObservable([(l, c.imag) for l, c in self.terms])
+
     def masks(self):
-        """(x_mask, z_mask, real coeff) arrays; complex coefficients keep their real part."""
+        """(x_mask, z_mask, real coeff) arrays.  The C ABI takes real coefficients: a complex
+        observable is evaluated as its real part here plus ``imag_part()`` (the estimator does
+        that); calling this directly on a complex observable drops nothing silently -- it raises."""
+        if self.is_complex() and not getattr(self, "_real_only_ok", False):
+            raise ValueError("complex Pauli coefficients: evaluate real_part() and imag_part() separately")
         n = len(self.terms)
         x = np.zeros(n, dtype=np.uint64)
         z = np.zeros(n, dtype=np.uint64)
@@ -42,23 +55,44 @@ class PauliObservable:
             x[k], z[k], c[k] = xm, zm, coeff.real
         return x, z, c
 
+    def real_part(self):
+        return PauliObservable([(l, c.real) for l, c in self.terms])
+
     def __repr__(self):
         return f"PauliObservable({self.terms!r})"
+
+
+_PAULI_PHASE = {"": 1.0, "+": 1.0, "-": -1.0, "i": 1j, "+i": 1j, "-i": -1j}
+
+
+def _split_phase(label):
+    """'-iXZ' -> ('XZ', -1j): a qiskit Pauli label with its group phase prefix."""
+    body = label.lstrip("+-i")
+    prefix = label[:len(label) - len(body)]
+    if prefix not in _PAULI_PHASE:
+        raise ValueError(f"bad Pauli phase prefix {prefix!r}")
+    return body, _PAULI_PHASE[prefix]
 
 
 def from_any(obj):
     if isinstance(obj, PauliObservable):
         return obj
     if isinstance(obj, str):
-        return PauliObservable([(obj, 1.0)])
+        body, phase = _split_phase(obj)
+        return PauliObservable([(body, phase)])
     if hasattr(obj, "primitive"):  # opflow PauliSumOp
         coeff = complex(getattr(obj, "coeff", 1.0))
         inner = from_any(obj.primitive)
         return PauliObservable([(l, c * coeff) for l, c in inner.terms])
     if hasattr(obj, "paulis") and hasattr(obj, "coeffs"):  # SparsePauliOp
-        return PauliObservable(list(zip(obj.paulis.to_labels(), np.asarray(obj.coeffs))))
-    if hasattr(obj, "to_label"):  # Pauli
-        return PauliObservable([(obj.to_label().lstrip("+-i"), 1.0)])
+        terms = []
+        for label, c in zip(obj.paulis.to_labels(), np.asarray(obj.coeffs)):
+            body, phase = _split_phase(label)
+            terms.append((body, complex(c) * phase))
+        return PauliObservable(terms)
+    if hasattr(obj, "to_label"):  # Pauli: its phase is the coefficient (as SparsePauliOp(Pauli) keeps it)
+        body, phase = _split_phase(obj.to_label())
+        return PauliObservable([(body, phase)])
     if isinstance(obj, (list, tuple)):
         if obj and isinstance(obj[0], str):
             return PauliObservable([(l, 1.0) for l in obj])
