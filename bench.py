@@ -133,214 +133,257 @@ class ClockSampler:
 
 
 # ----------------------------------------------------------------------------------------------
-# CPU arm: Aer-style restatement (oracle/cpu_ref.cpp) on a bounded sample
+# CPU arm: real qiskit-aer when the box has it, else the Aer-style restatement (oracle/cpu_ref.cpp)
 # ----------------------------------------------------------------------------------------------
-def cpu_reference_rate(workload_name, budget_s=15.0, max_circuits=512):
+def host_threads():
+    """All host cores of the box.  torchrun exports OMP_NUM_THREADS=1 to its workers; the CPU arm
+    (rank 0 only) must not inherit that, so the thread count is passed to the library explicitly."""
+    try:
+        return max(1, len(os.sched_getaffinity(0)))
+    except AttributeError:
+        return max(1, os.cpu_count() or 1)
+
+
+def probe_qiskit_aer():
+    """SURVEY 8(c) run-time probe (oracle/aer_probe.py): the reference's own simulator, if this box
+    has it (also under a driver-provided baseline/_ref).  Nothing in the image ships it; when it is
+    absent the CPU arm is the C++ restatement and says so (kind = "port")."""
+    from oracle import aer_probe
+
+    return aer_probe.find()
+
+
+def aer_reference_rate(wl, n, cores):
+    """Real Aer through the reference's own call sequence (blackwater/data/utils.py:422-430) on the
+    first n circuits of the workload.  Returns (circuits/s, noisy values, ideal values)."""
+    from oracle import aer_probe
+
+    props = wl["backend"].to_dict()
+    t = time.perf_counter()
+    noisy, ideal = [], []
+    for c, obs in zip(wl["circuits"][:n], wl["observables"][:n]):
+        noisy.append(aer_probe.estimate(c.num_qubits, c.gate_ops(), obs, props, threads=cores))
+        ideal.append(aer_probe.estimate(c.num_qubits, c.gate_ops(), obs, None))
+    dt = time.perf_counter() - t
+    return n / dt, np.concatenate(noisy), np.concatenate(ideal), dt
+
+
+def cpu_reference_rate(workload_name, budget_s=15.0, max_circuits=512, wl=None, first=None):
     """Times noisy (density matrix) + ideal (statevector) evaluation of the first circuits of the
-    rank-0 workload on all host cores.  Returns (circuits/s, cores, sample description)."""
+    rank-0 workload on all host cores.  Returns (circuits/s, cores, sample description, parity data)."""
     from ml_qem_b200 import engine
     from ml_qem_b200.gateset import OPCODES
     from oracle import cpu_ref, noise_model as onm
 
     cpu_ref.build()
-    wl = build_workload(workload_name, 0, scale=0.3)
+    if wl is None:
+        wl = build_workload(workload_name, 0, scale=0.3)
+    if probe_qiskit_aer() is not None:
+        try:  # the genuine reference: small bounded sample, the reference's per-circuit calls
+            n = int(first or 4)
+            rate, v_dm, v_sv, dt = aer_reference_rate(wl, n, host_threads())
+            fb = engine.encode_batch(wl["circuits"][:n], wl["observables"][:n])
+            return (rate, host_threads(), f"REAL qiskit-aer: first {n} circuits of {workload_name}, AerEstimator density_matrix "
+                    f"(approximation=True, shots=None) + qiskit Estimator, {dt:.2f} s", (fb, v_dm, v_sv), "reference")
+        except Exception as exc:  # noqa: BLE001
+            print(f"bench.py: qiskit-aer present but unusable ({exc!r}); using the C++ restatement", file=sys.stderr)
     onoise = cpu_ref.noise_arrays(onm.from_backend(wl["backend"].to_dict()), OPCODES)
-    cores = cpu_ref.max_threads()
+    cores = host_threads()
     # size the sample: time one circuit, then as many as fit the budget
     fb1 = engine.encode_batch(wl["circuits"][:1], wl["observables"][:1])
     t = time.perf_counter()
-    cpu_ref.run_dm(fb1, onoise)
-    cpu_ref.run_sv(fb1)
+    cpu_ref.run_dm(fb1, onoise, threads=cores)
+    cpu_ref.run_sv(fb1, threads=cores)
     t1 = max(time.perf_counter() - t, 1e-4)
     # small states run circuit-parallel (one circuit per core), large ones amplitude-parallel
     est_rate = (cores if wl["desc"]["n_qubits"] < 7 else 1.0) / t1
     cap = max_circuits if wl["desc"]["n_qubits"] >= 7 else 4096
     n = int(max(1, min(cap, len(wl["circuits"]), budget_s * est_rate)))
+    if first is not None:
+        n = min(n, first)
     fb = engine.encode_batch(wl["circuits"][:n], wl["observables"][:n])
     reps, dt = 0, 0.0
     while True:  # small circuits: repeat the sample until it amounts to ~10 s of CPU work
         t = time.perf_counter()
-        v_dm, s1 = cpu_ref.run_dm(fb, onoise)
-        v_sv, s2 = cpu_ref.run_sv(fb)
+        v_dm, s1 = cpu_ref.run_dm(fb, onoise, threads=cores)
+        v_sv, s2 = cpu_ref.run_sv(fb, threads=cores)
         dt += time.perf_counter() - t
         reps += 1
         if dt >= min(10.0, budget_s) or dt * (reps + 1) / reps > budget_s:
             break
     assert not s1.any() and not s2.any()
     return (n * reps / dt, cores, f"first {n} circuits of {workload_name} (rank-0 seed) x {reps} pass(es), noisy DM + ideal SV, "
-            f"{dt:.2f} s on {cores} threads", (fb, v_dm, v_sv))
+            f"{dt:.2f} s on {cores} threads", (fb, v_dm, v_sv), "port")
+
+
+# ----------------------------------------------------------------------------------------------
+class Ctx:
+    """One rank of the run: engine, process group, helpers for the max/sum over ranks."""
+
+    def __init__(self, args):
+        import torch
+
+        self.args = args
+        self.rank = int(os.environ.get("RANK", "0"))
+        self.world = int(os.environ.get("WORLD_SIZE", "1"))
+        self.local_rank = int(os.environ.get("LOCAL_RANK", "0"))
+        self.torch = torch
+        torch.cuda.set_device(self.local_rank)
+        self.dist = None
+        if self.world > 1:
+            import torch.distributed as dist_mod
+
+            self.dist = dist_mod
+            self.dist.init_process_group("nccl", device_id=torch.device("cuda", self.local_rank))
+        from ml_qem_b200 import engine
+
+        self.eng = engine.Engine(self.local_rank)
+        peaks_path = os.path.join(ROOT, "MEASURED_PEAKS.json")
+        if os.path.exists(peaks_path):
+            self.peak, self.peak_src = float(json.load(open(peaks_path))["hbm_gbs"]), "measured (MEASURED_PEAKS.json)"
+        else:
+            self.peak, self.peak_src = 6650.0, "fallback (B200_PROFILING.md)"
+
+    def barrier(self):
+        if self.dist is not None:
+            self.dist.barrier()
+        self.torch.cuda.synchronize()
+
+    def _reduce(self, x, op):
+        if self.dist is None:
+            return x
+        t = self.torch.tensor([x], dtype=self.torch.float64, device="cuda")
+        self.dist.all_reduce(t, op=op)
+        return float(t.item())
+
+    def max(self, x):
+        return self._reduce(x, self.dist.ReduceOp.MAX) if self.dist else x
+
+    def sum(self, x):
+        return self._reduce(x, self.dist.ReduceOp.SUM) if self.dist else x
+
+    def close(self):
+        if self.dist is not None:
+            self.dist.destroy_process_group()
 
 
 # ----------------------------------------------------------------------------------------------
 # BASELINE configs[3]: ideal-label statevector of ONE wide TFIM circuit, amplitudes sharded over
-# all ranks (NCCL all_to_all for the global-qubit exchanges).  Strong scaling: the circuit is fixed.
+# all ranks (the engine's P2P exchange kernel / NCCL all_to_all for the global-qubit swaps).
+# Strong scaling: the circuit is fixed.
 # ----------------------------------------------------------------------------------------------
-def bench_sharded_sv(args, rank, world, local_rank, dist, steps, warmup):
+def bench_sharded_sv(ctx, name, steps, warmup, first_trotter=1, cpu_check=True, clocks=False):
     import torch
 
     from ml_qem_b200 import engine, families as F
     from ml_qem_b200.statevector import GpuExecutor, ShardedStatevector
 
-    n = int(args.workload[4:-3])
-    eng = engine.Engine(local_rank)
+    n = int(name[4:-3])
+    rank, world, dist, eng = ctx.rank, ctx.world, ctx.dist, ctx.eng
     sv = ShardedStatevector(GpuExecutor(eng), dist)
     rng = np.random.default_rng(4)
     obs = F.tfim_observables(list(range(n)), n)
-    # timed circuit i has 1 + (i mod 10) Trotter steps whatever the warm-up count (the warm-up reuses
-    # the first timed circuits), so runs with equal --steps are comparable across GPU counts
-    timed = [F.tfim_circuit(n, 1 + i % 10, float(rng.uniform(0, 1)), dt=0.25) for i in range(steps)]
+    # timed circuit i has first_trotter + (i mod 10) Trotter steps whatever the warm-up count (the
+    # warm-up reuses the first timed circuits), so runs with equal --steps are comparable across GPU counts
+    Js = [float(rng.uniform(0, 1)) for _ in range(steps)]
+    trot = [first_trotter + i % 10 for i in range(steps)]
+    timed = [F.tfim_circuit(n, trot[i], Js[i], dt=0.25) for i in range(steps)]
     circs = [timed[i % steps] for i in range(warmup)] + timed
-
-    def barrier():
-        if dist is not None:
-            dist.barrier()
-        torch.cuda.synchronize()
 
     for c in circs[:warmup]:
         sv.estimate(c, obs)
-    sampler = ClockSampler(local_rank)
-    if rank == 0:
+    sampler = ClockSampler(ctx.local_rank)
+    if rank == 0 and clocks:
         sampler.start()
-    barrier()
+    ctx.barrier()
     t0 = time.perf_counter()
     dev_ms = sweep_ms = exch_ms = 0.0
-    swept = exch_bytes = launches = 0
-    vals = None
+    swept = exch_bytes = launches = n_exch = 0
+    all_vals = []
     for c in circs[warmup:]:
         vals = sv.estimate(c, obs, profile=True)
+        all_vals.append(vals)
         pl = sv.last_plan
         dev_ms += pl["ms_total"]; sweep_ms += pl["ms"].get("sweeps", 0.0); exch_ms += pl["ms"].get("exchange", 0.0)
         swept += pl["kernel_bytes"] - 16 * (1 << pl["n_local"]) * pl["n_expval_passes"]  # sweeps only, live tiles
-        exch_bytes += pl["exchanged_bytes_per_rank"]
-        launches += pl["n_sweeps"] + 2 * pl["n_expval_passes"]
-    barrier()
+        exch_bytes += pl["exchanged_bytes_per_rank"]; n_exch += pl["n_exchanges"]
+        launches += pl["n_sweeps"] + 2 * pl["n_expval_passes"] + pl["n_exchanges"]
+    ctx.barrier()
     wall_s = time.perf_counter() - t0
-    clocks = sampler.stop() if rank == 0 else None
-    t = torch.tensor([dev_ms / 1e3, wall_s], dtype=torch.float64, device="cuda")
-    if dist is not None:
-        dist.all_reduce(t, op=dist.ReduceOp.MAX)
-    t_dev, t_wall = float(t[0]), float(t[1])
+    clk = sampler.stop() if (rank == 0 and clocks) else None
+    t_dev, t_wall = ctx.max(dev_ms / 1e3), ctx.max(wall_s)
+    # sharded == unsharded: rank 0 re-runs the first timed circuit on ONE GPU (the batched wide
+    # path of bwq_sv_run: 16 B x 2^n state on this GPU) and compares the values
+    diff_1rank = None
+    if world > 1:
+        if rank == 0:
+            v1, st = eng.run_sv(engine.encode_batch([timed[0]], [obs]))
+            diff_1rank = float(np.max(np.abs(v1 - all_vals[0]))) if not st.any() else None
+        ctx.barrier()
     if rank != 0:
-        if dist is not None:
-            dist.destroy_process_group()
-        return 0
-    peaks_path = os.path.join(ROOT, "MEASURED_PEAKS.json")
-    peak = float(json.load(open(peaks_path))["hbm_gbs"]) if os.path.exists(peaks_path) else 6650.0
+        return None
     achieved = swept / (sweep_ms / 1e3) / 1e9 if sweep_ms > 0 else 0.0
-    line = {
-        "metric": METRIC, "value": steps / t_dev, "unit": UNIT, "n_gpus": world, "steps": steps, "warmup": warmup,
-        "ms_per_step": 1e3 * t_dev / steps, "higher_is_better": True, "scaling": "strong", "vs_baseline": None,
-        "dtype": "f64", "data": "synthetic",
-        "config": {"workload": args.workload, "n_qubits": n, "observables_per_circuit": len(obs),
-                   "trotter_steps": "timed circuit i has 1 + (i mod 10) steps: " + ",".join(str(1 + i % 10) for i in range(steps)),
+    out = {
+        "value": steps / t_dev, "unit": UNIT, "ms_per_step": 1e3 * t_dev / steps, "scaling": "strong", "steps": steps, "warmup": warmup,
+        "config": {"workload": name, "n_qubits": n, "observables_per_circuit": len(obs),
+                   "trotter_steps": "timed circuit i has %d + (i mod 10) steps: " % first_trotter + ",".join(map(str, trot)),
                    "parallelism": f"amplitude-sharded x{world} (rank = top {world.bit_length() - 1} index bits)",
                    "l2": "shard of %.2f GiB >> 126 MB L2 (no flush needed)" % (16 * 2 ** n / world / 2 ** 30),
                    "timing": "CUDA events on torch's stream, first segment to all_reduce (max over ranks)"},
         "e2e": {"value": steps / t_wall, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 8 * len(obs),
                 "ms_per_step": 1e3 * t_wall / steps, "note": "circuit object -> plan -> upload -> run -> values on host"},
         "gpu_launches": int(launches),
-        "roofline": {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak, "traffic": None,
+        "roofline": {"bound": "hbm", "achieved": achieved, "peak": ctx.peak, "unit": "GB/s", "frac": achieved / ctx.peak, "traffic": None,
                      "kernel": "sv_sweep_kernel", "bytes_per_launch": 2 * 16 * 2 ** n / world,
                      "sweep_share_of_step": sweep_ms / dev_ms if dev_ms else None},
-        "exchange": {"bytes_per_rank_per_step": exch_bytes // steps, "ms_per_step": exch_ms / steps,
-                     "GBps_per_rank": (exch_bytes / (exch_ms / 1e3) / 1e9) if exch_ms > 0 else None},
-        "cpu_baseline": None, "clocks": clocks, "last_values_head": [float(x) for x in vals[:3]],
+        "exchange": {"exchanges_per_circuit": n_exch / steps, "bytes_per_rank_per_step": exch_bytes // steps, "ms_per_step": exch_ms / steps,
+                     "share_of_step": exch_ms / dev_ms if dev_ms else None,
+                     "GBps_per_rank": (exch_bytes / (exch_ms / 1e3) / 1e9) if exch_ms > 0 else None,
+                     "nvlink_reference_GBps": 770.0, "impl": sv.last_plan["exchange_impl"] if world > 1 else None},
+        "max_abs_diff_vs_1rank": diff_1rank, "last_values_head": [float(x) for x in all_vals[-1][:3]],
     }
-    print(json.dumps(line))
-    if dist is not None:
-        dist.destroy_process_group()
-    return 0
+    if clk is not None:
+        out["clocks"] = clk
+    if cpu_check and world == 1:
+        # CPU parity + rate at a width the host finishes in seconds: the same circuit family through
+        # the same wide-statevector kernels at 22 qubits against the C++ restatement
+        from oracle import cpu_ref
+
+        cpu_ref.build()
+        m = 22
+        c_small = [F.tfim_circuit(m, trot[i], Js[i], dt=0.25) for i in range(min(2, steps))]
+        fb = engine.encode_batch(c_small, [F.tfim_observables(list(range(m)), m)] * len(c_small))
+        cores = host_threads()
+        t = time.perf_counter()
+        ref, st = cpu_ref.run_sv(fb, threads=cores)
+        dt = time.perf_counter() - t
+        got, st2 = eng.run_sv(fb)
+        out["cpu_baseline"] = {"value": len(c_small) / dt, "unit": UNIT, "cores": cores, "kind": "port",
+                               "sample": f"{len(c_small)} circuits of the same family at {m} qubits (2^-{n - m} of the amplitudes; "
+                                         f"a {n}-qubit state does not fit the CPU budget), ideal SV, {dt:.2f} s on {cores} threads",
+                               "max_abs_diff_vs_gpu": float(np.max(np.abs(got - ref))) if not (st.any() or st2.any()) else None}
+        out["max_abs_diff_vs_cpu"] = out["cpu_baseline"]["max_abs_diff_vs_gpu"]
+    return out
 
 
 # ----------------------------------------------------------------------------------------------
-def main():
-    ap = argparse.ArgumentParser()
-    ap.add_argument("--gpus", type=int, default=1)
-    ap.add_argument("--steps", type=int, default=5)
-    ap.add_argument("--warmup", type=int, default=3)
-    ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
-    ap.add_argument("--workload", default="brick10_guadalupe_twirl")
-    ap.add_argument("--scale", type=float, default=1.0, help="fraction of the named batch size (debug)")
-    ap.add_argument("--no-cpu-baseline", action="store_true")
-    ap.add_argument("--tile-qubits", type=int, default=0)
-    ap.add_argument("--low-qubits", type=int, default=0)
-    ap.add_argument("--chunk-circuits", type=int, default=0)
-    args = ap.parse_args()
-
-    rank = int(os.environ.get("RANK", "0"))
-    world = int(os.environ.get("WORLD_SIZE", "1"))
-    local_rank = int(os.environ.get("LOCAL_RANK", "0"))
-    steps, warmup = args.steps, max(args.warmup, 0)
-
-    # ------------------------------------------------------------------ reference arm (CPU)
-    if args.impl == "reference":
-        if rank != 0:
-            return 0
-        t_all = time.perf_counter()
-        rates = []
-        for i in range(warmup + steps):
-            # each step = one bounded sample; budget so that the whole run ends within minutes
-            rate, cores, sample, _ = cpu_reference_rate(args.workload, budget_s=10.0)
-            if i >= warmup:
-                rates.append(rate)
-        value = float(np.mean(rates))
-        line = {
-            "impl": "reference", "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": args.gpus, "steps": steps,
-            "warmup": warmup, "ms_per_step": 1e3 * (time.perf_counter() - t_all) / max(1, warmup + steps),
-            "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f64", "data": "synthetic",
-            "config": {"workload": args.workload, "note": "Aer-style C++/OpenMP restatement (oracle/cpu_ref.cpp); "
-                       "qiskit-aer is not installable offline"},
-            "cpu_baseline": {"value": value, "unit": UNIT, "cores": cores, "kind": "port", "sample": sample},
-            "e2e": {"value": value, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
-            "gpu_launches": 0,
-        }
-        print(json.dumps(line))
-        return 0
-
-    # ------------------------------------------------------------------ our arm (B200)
+# density-matrix workloads (cfg1, cfg2, cfg3, cfg5-generation): circuit-sharded, weak scaling
+# ----------------------------------------------------------------------------------------------
+def bench_dm(ctx, name, steps, warmup, scale=1.0, cpu_budget=15.0, cpu_first=None, clocks=False):
     import torch
 
-    if not torch.cuda.is_available():
-        raise SystemExit("bench.py: no CUDA device -- the engine has no CPU fallback (use --impl reference for the CPU arm)")
-    torch.cuda.set_device(local_rank)
-    dist = None
-    if world > 1:
-        import torch.distributed as dist_mod
-
-        dist = dist_mod
-        dist.init_process_group("nccl", device_id=torch.device("cuda", local_rank))
     from ml_qem_b200 import engine, noise
 
-    if args.workload.startswith("tfim") and args.workload.endswith("_sv"):
-        return bench_sharded_sv(args, rank, world, local_rank, dist, steps, warmup)
-
-    wl = build_workload(args.workload, rank, args.scale)
+    args, rank, world, dist, eng = ctx.args, ctx.rank, ctx.world, ctx.dist, ctx.eng
+    wl = build_workload(name, rank, scale)
+    t_enc = time.perf_counter()
     batch = engine.encode_batch(wl["circuits"], wl["observables"])
+    t_enc = time.perf_counter() - t_enc
     n_circ = batch.n_circuits
-    eng = engine.Engine(local_rank)
     # lowering threads: the ranks of one box share its host cores
     eng.set_options(tile_qubits=args.tile_qubits, low_qubits=args.low_qubits, chunk_circuits=args.chunk_circuits,
-                    host_threads=max(1, (os.cpu_count() or 8) // world) if world > 1 else 0)
+                    host_threads=max(1, host_threads() // world) if world > 1 else 0, flags=args.flags)
     eng.set_noise(noise.from_backend(wl["backend"]))
-
-    def barrier():
-        if dist is not None:
-            dist.barrier()
-        torch.cuda.synchronize()
-
-    def max_over_ranks(x):
-        if dist is None:
-            return x
-        t = torch.tensor([x], dtype=torch.float64, device="cuda")
-        dist.all_reduce(t, op=dist.ReduceOp.MAX)
-        return float(t.item())
-
-    def sum_over_ranks(x):
-        if dist is None:
-            return x
-        t = torch.tensor([x], dtype=torch.float64, device="cuda")
-        dist.all_reduce(t, op=dist.ReduceOp.SUM)
-        return float(t.item())
 
     # ---- resident-program throughput (`value`)
     st = eng.prepare_dm(batch)
@@ -350,10 +393,10 @@ def main():
     for _ in range(warmup):
         noisy = eng.execute_dm()
         ideal = eng.execute_sv()
-    sampler = ClockSampler(local_rank)
-    if rank == 0:
+    sampler = ClockSampler(ctx.local_rank)
+    if rank == 0 and clocks:
         sampler.start()
-    barrier()
+    ctx.barrier()
     t0 = time.perf_counter()
     dev_ms = sweep_ms = 0.0
     launches = swept = sweeps = 0
@@ -368,13 +411,13 @@ def main():
         s = eng.stats()
         dev_ms += s["kernel_ms"]
         launches += s["n_other_launches"]
-    barrier()
+    ctx.barrier()
     wall_s = time.perf_counter() - t0
-    clocks = sampler.stop() if rank == 0 else None
+    clk = sampler.stop() if (rank == 0 and clocks) else None
     # device time (CUDA events on the engine's stream, summed over the K steps), max over ranks
-    t_dev = max_over_ranks(dev_ms / 1e3)
-    t_wall = max_over_ranks(wall_s)
-    total_circ = sum_over_ranks(float(n_circ)) * steps
+    t_dev = ctx.max(dev_ms / 1e3)
+    t_wall = ctx.max(wall_s)
+    total_circ = ctx.sum(float(n_circ)) * steps
     value = total_circ / t_dev
 
     # ---- end to end through the C ABI with host buffers (`e2e`)
@@ -384,14 +427,14 @@ def main():
     sv_io = eng.run_sv(batch) and eng.stats()  # program/value bytes of the statevector side (untimed probe)
     for _ in range(min(warmup, 2)):
         eng.run_meas_data(batch)
-    barrier()
+    ctx.barrier()
     t0 = time.perf_counter()
     h2d = d2h = 0
     for _ in range(steps):
         ideal_e, noisy_e, st2, st1 = eng.run_meas_data(batch)
         s = eng.stats(); h2d += s["h2d_bytes"] + sv_io["h2d_bytes"]; d2h += s["d2h_bytes"] + sv_io["d2h_bytes"]
-    barrier()
-    e2e_s = max_over_ranks(time.perf_counter() - t0)
+    ctx.barrier()
+    e2e_s = ctx.max(time.perf_counter() - t0)
     e2e_value = total_circ / e2e_s
     assert np.array_equal(noisy_e, noisy) and np.array_equal(ideal_e, ideal), "resident and host-buffer paths differ"
 
@@ -400,34 +443,30 @@ def main():
         mine = torch.from_numpy(np.stack([noisy, ideal])).cuda()
         parts = [torch.empty_like(mine) for _ in range(world)] if rank == 0 else None
         dist.gather(mine, parts, dst=0)
-
     if rank != 0:
-        if dist is not None:
-            dist.destroy_process_group()
-        return 0
+        return None
 
-    # ---- roofline of the dominant kernel (dm_sweep_kernel): algorithmic bytes = 2 x 8 B x 4^n per
-    # state sweep (one read + one write of every Pauli-basis element), time = CUDA events around
-    # the sweep launches (rank 0)
-    peaks_path = os.path.join(ROOT, "MEASURED_PEAKS.json")
-    if os.path.exists(peaks_path):
-        peak, peak_src = float(json.load(open(peaks_path))["hbm_gbs"]), "measured (MEASURED_PEAKS.json)"
-    else:
-        peak, peak_src = 6650.0, "fallback (B200_PROFILING.md)"
+    # ---- roofline of the dominant kernel (dm_sweep): algorithmic bytes = 2 x 8 B x 4^n per state
+    # sweep (one read + one write of every Pauli-basis element), time = CUDA events around the
+    # sweep launches (rank 0)
     achieved = swept / (sweep_ms / 1e3) / 1e9 if sweep_ms > 0 else 0.0
-    roofline = {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
-                "traffic": None, "kernel": "dm_sweep_kernel<6,false>", "peak_source": peak_src,
+    on_chip = wl["desc"]["n_qubits"] <= 6
+    roofline = {"bound": "hbm", "achieved": achieved, "peak": ctx.peak, "unit": "GB/s", "frac": achieved / ctx.peak,
+                "traffic": None, "kernel": "dm_sweep_kernel<%d,false>" % min(6, wl["desc"]["n_qubits"]),
+                "peak_source": ctx.peak_src,
                 "bytes_definition": "actual layout: 2 x 8 B x 4^n per state sweep (real Pauli-basis elements); "
                                     "SURVEY 8(d) counts the reference's complex128 layout, 2 x 16 B x 4^n",
-                "achieved_survey_units": 2.0 * achieved, "frac_survey_units": 2.0 * achieved / peak,
+                "achieved_survey_units": 2.0 * achieved, "frac_survey_units": 2.0 * achieved / ctx.peak,
                 "bytes_per_launch": swept / max(1, steps * n_sweep_launches),
                 "launches_per_step": n_sweep_launches, "state_sweeps_per_step": sweeps // steps,
                 "register_passes_per_step": n_passes,
                 "sweep_share_of_step": sweep_ms / dev_ms if dev_ms else None}
+    if on_chip:
+        roofline["note"] = "state of <= 6 qubits never leaves the SM (one launch per circuit batch): HBM fraction is not the bound here"
     traffic_path = os.path.join(ROOT, "profiles", "traffic.json")
     if os.path.exists(traffic_path):
         try:
-            ratio = json.load(open(traffic_path)).get(args.workload, {}).get("traffic_over_algorithmic")
+            ratio = json.load(open(traffic_path)).get(name, {}).get("traffic_over_algorithmic")
             if ratio is not None:  # dram bytes per launch, scaled from the ncu capture to this launch size
                 roofline["traffic"] = ratio * roofline["bytes_per_launch"]
                 roofline["traffic_source"] = "ncu --set full capture (profiles/traffic.json), scaled to this launch size"
@@ -435,33 +474,162 @@ def main():
             pass
 
     cpu = None
-    if not args.no_cpu_baseline and world == 1:
-        rate, cores, sample, (fb_s, v_dm, v_sv) = cpu_reference_rate(args.workload)
+    if cpu_budget > 0 and world == 1:
+        rate, cores, sample, (fb_s, v_dm, v_sv), kind = cpu_reference_rate(name, budget_s=cpu_budget, wl=wl if scale == 1.0 else None,
+                                                                           first=cpu_first)
         # the CPU sample doubles as a parity check of this very run
         k = fb_s.n_observables
         err = max(float(np.max(np.abs(noisy[:k] - v_dm))), float(np.max(np.abs(ideal[:k] - v_sv))))
-        cpu = {"value": rate, "unit": UNIT, "cores": cores, "kind": "port", "sample": sample,
+        cpu = {"value": rate, "unit": UNIT, "cores": cores, "kind": kind, "sample": sample,
                "max_abs_diff_vs_gpu": err}
 
-    line = {
-        "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": steps, "warmup": warmup,
-        "ms_per_step": 1e3 * t_dev / steps, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
-        "dtype": "f64", "data": "synthetic",
+    out = {
+        "value": value, "unit": UNIT, "ms_per_step": 1e3 * t_dev / steps, "scaling": "weak", "steps": steps, "warmup": warmup,
         "config": dict(wl["desc"], parallelism=f"circuit-sharded x{world}", state_layout="Pauli-basis density matrix, 8 B/element",
                        l2="per-rank working set %.1f GiB of resident states >> 126 MB L2 (no flush needed)" %
                           (wl["desc"].get("resident_state_bytes", n_circ * 8 * 4 ** wl["desc"]["n_qubits"]) / 2 ** 30),
                        timing="CUDA events on the engine stream summed over steps (max over ranks); wall %.1f ms/step" %
-                              (1e3 * t_wall / steps)),
+                              (1e3 * t_wall / steps),
+                       host_encode_ms=1e3 * t_enc),
         "e2e": {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": h2d // steps, "d2h_bytes_per_step": d2h // steps,
                 "ms_per_step": 1e3 * e2e_s / steps},
         "gpu_launches": int(launches),
         "roofline": roofline,
         "cpu_baseline": cpu,
-        "clocks": clocks,
+        "max_abs_diff_vs_cpu": cpu["max_abs_diff_vs_gpu"] if cpu else None,
     }
+    if clk is not None:
+        out["clocks"] = clk
+    return out
+
+
+# sub-workloads reported next to the headline line: the other BASELINE configs that fit the run
+# (name, steps, warmup, kwargs)
+SUB_WORKLOADS = [
+    ("tfim4_lima_zne", 3, 1, {"cpu_budget": 6.0}),
+    ("tfim14_dm", 2, 1, {"cpu_budget": 12.0, "cpu_first": 1}),
+    ("tfim30_sv", 3, 1, {"first_trotter": 3}),
+]
+
+
+def sub_summary(d):
+    """Compact form of a workload result for the `workloads` object of the headline line."""
+    if d is None:
+        return None
+    r = d["roofline"]
+    out = {"value": d["value"], "unit": d["unit"], "ms_per_step": d["ms_per_step"], "steps": d["steps"], "warmup": d["warmup"],
+           "scaling": d["scaling"], "e2e": d["e2e"]["value"],
+           "roofline": {"achieved": r["achieved"], "frac": r["frac"], "kernel": r["kernel"], "unit": r["unit"],
+                        "bytes_per_launch": r["bytes_per_launch"], "sweep_share_of_step": r.get("sweep_share_of_step")},
+           "max_abs_diff_vs_cpu": d.get("max_abs_diff_vs_cpu"), "gpu_launches": d["gpu_launches"],
+           "config": d["config"]}
+    if d.get("cpu_baseline"):
+        out["cpu_baseline"] = {k: d["cpu_baseline"][k] for k in ("value", "cores", "kind", "sample")}
+    for k in ("exchange", "max_abs_diff_vs_1rank"):
+        if k in d:
+            out[k] = d[k]
+    return out
+
+
+# ----------------------------------------------------------------------------------------------
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=5)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
+    ap.add_argument("--workload", default="brick10_guadalupe_twirl")
+    ap.add_argument("--scale", type=float, default=1.0, help="fraction of the named batch size (debug)")
+    ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--no-sub-workloads", action="store_true", help="only the headline workload (profiling runs)")
+    ap.add_argument("--tile-qubits", type=int, default=0)
+    ap.add_argument("--low-qubits", type=int, default=0)
+    ap.add_argument("--chunk-circuits", type=int, default=0)
+    ap.add_argument("--flags", type=int, default=0, help="BWQ_OPT_* bits (kernel experiments)")
+    args = ap.parse_args()
+
+    rank = int(os.environ.get("RANK", "0"))
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    steps, warmup = args.steps, max(args.warmup, 0)
+
+    # ------------------------------------------------------------------ reference arm (CPU)
+    if args.impl == "reference":
+        if rank != 0:
+            return 0
+        t_all = time.perf_counter()
+        aer = probe_qiskit_aer()
+        rates = []
+        for i in range(warmup + steps):
+            # each step = one bounded sample; budget so that the whole run ends within minutes
+            rate, cores, sample, _, kind = cpu_reference_rate(args.workload, budget_s=10.0)
+            if i >= warmup:
+                rates.append(rate)
+        value = float(np.mean(rates))
+        line = {
+            "impl": "reference", "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": args.gpus, "steps": steps,
+            "warmup": warmup, "ms_per_step": 1e3 * (time.perf_counter() - t_all) / max(1, warmup + steps),
+            "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f64", "data": "synthetic",
+            "config": {"workload": args.workload, "note": "real qiskit-aer" if kind == "reference" else
+                       "Aer-style C++/OpenMP restatement (oracle/cpu_ref.cpp); qiskit-aer is not installable offline",
+                       "qiskit_aer_probe": "found" if aer else "absent",
+                       "host_threads": cores, "env_OMP_NUM_THREADS_ignored": os.environ.get("OMP_NUM_THREADS")},
+            "cpu_baseline": {"value": value, "unit": UNIT, "cores": cores, "kind": kind, "sample": sample},
+            "e2e": {"value": value, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+            "gpu_launches": 0,
+        }
+        print(json.dumps(line))
+        return 0
+
+    # ------------------------------------------------------------------ our arm (B200)
+    import torch
+
+    if not torch.cuda.is_available():
+        raise SystemExit("bench.py: no CUDA device -- the engine has no CPU fallback (use --impl reference for the CPU arm)")
+    ctx = Ctx(args)
+    is_sv = args.workload.startswith("tfim") and args.workload.endswith("_sv")
+    cpu_budget = 0.0 if args.no_cpu_baseline else 15.0
+    if is_sv:
+        main_res = bench_sharded_sv(ctx, args.workload, steps, warmup, cpu_check=not args.no_cpu_baseline, clocks=True)
+    else:
+        main_res = bench_dm(ctx, args.workload, steps, warmup, args.scale, cpu_budget=cpu_budget, clocks=True)
+
+    subs = {}
+    if not args.no_sub_workloads and args.workload == "brick10_guadalupe_twirl" and args.scale == 1.0:
+        for name, s_steps, s_warm, kw in SUB_WORKLOADS:
+            t_sub = time.perf_counter()
+            try:
+                if name.endswith("_sv"):
+                    r = bench_sharded_sv(ctx, name, s_steps, s_warm, cpu_check=not args.no_cpu_baseline, **kw)
+                else:
+                    kw = dict(kw)
+                    if args.no_cpu_baseline:
+                        kw["cpu_budget"] = 0.0
+                    r = bench_dm(ctx, name, s_steps, s_warm, **kw)
+                if ctx.rank == 0:
+                    subs[name] = sub_summary(r)
+                    subs[name]["wall_s_incl_setup"] = time.perf_counter() - t_sub
+            except Exception as exc:  # noqa: BLE001 - a failing sub-workload must not void the headline line
+                if ctx.world > 1:
+                    raise
+                subs[name] = {"error": repr(exc)[:300]}
+
+    if ctx.rank != 0:
+        ctx.close()
+        return 0
+    line = {
+        "metric": METRIC, "value": main_res["value"], "unit": UNIT, "n_gpus": ctx.world, "steps": steps, "warmup": warmup,
+        "ms_per_step": main_res["ms_per_step"], "higher_is_better": True, "scaling": main_res["scaling"], "vs_baseline": None,
+        "dtype": "f64", "data": "synthetic", "config": main_res["config"], "e2e": main_res["e2e"],
+        "gpu_launches": main_res["gpu_launches"], "roofline": main_res["roofline"], "cpu_baseline": main_res.get("cpu_baseline"),
+        "clocks": main_res.get("clocks"),
+    }
+    for k in ("exchange", "max_abs_diff_vs_1rank", "last_values_head"):
+        if k in main_res:
+            line[k] = main_res[k]
+    if subs:
+        line["workloads"] = subs
     print(json.dumps(line))
-    if dist is not None:
-        dist.destroy_process_group()
+    ctx.close()
     return 0
 
 

@@ -48,14 +48,18 @@ constexpr uint32_t kLocalMat = 0x80000000u;
 //   block := BlockHdr | PassHdr[n_passes] | BlockOp[...] | parameters (16-byte aligned)
 struct BlockHdr {   // 16 B
   int32_t n_passes;
-  int32_t pad[3];
+  int32_t ext_q16;  // TMA layout: offset (16-byte units) of the per-pass corner tables, 64 B per pass
+  int32_t pad[2];
 };
 struct PassHdr {    // 16 B
   uint16_t ops_q16; // offset of the pass's first BlockOp, in 16-byte units from the block start
   uint16_t n_ops;
   uint8_t sa, sb;   // tile slots of digits a and b
   uint8_t flags;    // kPassLoadDirect (first pass; mirrored in SweepDesc::pos[7]) | kPassStoreDirect (last pass)
-  uint8_t pad[9];
+  uint8_t sig;      // TMA layout: PassSig -- straight-line body the kernel runs for this op list
+  uint8_t row;      // TMA layout: row of the thread-base table (slot pair index hi (hi - 1) / 2 + lo)
+  uint8_t pad[3];
+  uint32_t gofs;    // TMA layout: byte offset (XOR) of a thread's second register group
 };
 // Direct passes: the first pass of a sweep reads its register groups from global memory and the
 // last one writes them back, instead of staging the tile through shared memory.  Requested when
@@ -76,6 +80,86 @@ struct SweepDesc {  // 16 B
                         // pos[7] (density matrix): first-pass descriptor, see kFirstDirect
 };
 constexpr int kBlockBytes = 8192;  // shared-memory program buffer per CTA
+
+// ---- TMA tile layout (dm_sweep_tma_kernel; circuits wider than the 6-digit tile) ---------------
+// The tile is the box of a rank-5 tensor map: dim 0 = the 16 contiguous elements of digits 0 and 1
+// (128 bytes), dims 1..4 = the four other resident digits IN AN ORDER THE LOWERING CHOOSES (the
+// "box order"; slot 2 + k of a pass header = box dim 1 + k).  Element with tile-local index j
+// (2 bits per slot) lives at 8 * tswz(j) in shared memory -- CU_TENSOR_MAP_SWIZZLE_128B: byte
+// address bits 4..6 ^= bits 7..9, i.e. (D0hi, D1lo, D1hi) ^= (D2lo, D2hi, D3lo).
+// Lowering output: SweepDesc::pos[0..5] ascending positions, pos[6] = box order (2 bits per box
+// dim: index into the ascending list of the four upper positions), pos[7] = kTmaSweep; the batch
+// merge replaces pos[6..7] by the 16-bit index of the sweep's tensor map.
+constexpr uint8_t kTmaSweep = 0x40;
+constexpr int kTmaThreads = 128;
+constexpr uint32_t tswz(uint32_t j) { return j ^ (((j >> 4) & 7u) << 1); }
+
+// Register-pass work split of the TMA kernel: 128 threads x 32 elements.  A thread owns the 16
+// (da, db) corners of TWO register groups.  Slot 0 not a target: the groups differ in the low bit
+// of digit 0, i.e. one 16-byte shared-memory access brings corner i of both (beta = index bit 0).
+// Slot 0 a target: they differ in the highest free index bit.  tbit[k] = tile index bit driven by
+// thread-id bit k: a quarter warp (lane bits 0..2) must hit eight distinct 16-byte chunks, chunk
+// bits = index bits (1,2,3) ^ (4,5,6); lane bit k-1 drives bit k, or bit k+3 when bit k belongs
+// to a target digit -- impossible only for the slot pairs {0,2}, {1,2}, {1,3} (2-way conflict),
+// which the lowering avoids through the box order.
+struct TmaPassLayout {
+  int tbit[7];
+  int beta;
+};
+inline TmaPassLayout tma_pass_layout(int sa, int sb) {
+  TmaPassLayout L{};
+  bool is_target[12], used[12];
+  for (int b = 0; b < 12; ++b) { is_target[b] = (b >> 1) == sa || (b >> 1) == sb; used[b] = is_target[b]; }
+  const bool slot0 = sa == 0 || sb == 0;
+  if (!slot0) { L.beta = 0; used[0] = true; }
+  for (int k = 1; k <= 3; ++k) {
+    int pick = -1;
+    if (!used[k]) pick = k;
+    else if (!used[k + 3]) pick = k + 3;
+    L.tbit[k - 1] = pick;  // -1: no conflict-free choice, filled below
+    if (pick >= 0) used[pick] = true;
+  }
+  if (slot0) {  // beta = highest free bit
+    for (int b = 11; b >= 0; --b) if (!used[b]) { L.beta = b; used[b] = true; break; }
+  }
+  int next = 0;
+  auto take = [&]() { while (used[next]) ++next; used[next] = true; return next; };
+  for (int k = 0; k < 3; ++k) if (L.tbit[k] < 0) L.tbit[k] = take();
+  for (int k = 3; k < 7; ++k) L.tbit[k] = take();
+  return L;
+}
+inline int tma_pair_row(int sa, int sb) {
+  const int lo = sa < sb ? sa : sb, hi = sa < sb ? sb : sa;
+  return hi * (hi - 1) / 2 + lo;
+}
+constexpr int kTmaPairs = 15;
+// thread-base table: row (lo, hi) x thread -> swizzled byte offset of the thread's first element
+inline void fill_tma_a_table(uint32_t* t) {
+  for (int hi = 1; hi < 6; ++hi)
+    for (int lo = 0; lo < hi; ++lo) {
+      const TmaPassLayout L = tma_pass_layout(lo, hi);
+      for (int tid = 0; tid < kTmaThreads; ++tid) {
+        uint32_t j = 0;
+        for (int k = 0; k < 7; ++k) j |= uint32_t((tid >> k) & 1) << L.tbit[k];
+        t[tma_pair_row(lo, hi) * kTmaThreads + tid] = 8u * tswz(j);
+      }
+    }
+}
+
+// Pass signatures with a straight-line body in the TMA kernel (no op dispatch inside the pass, so
+// no register reconciliation at dispatch joins).  Macro-op (pre_a, pre_b, twoq) sequences:
+enum PassSig : uint8_t {
+  SIG_GENERIC = 0,
+  SIG_AAC = 1,       // (AFF, AFF, CXN_AB)
+  SIG_AAC_AA = 2,    // (AFF, AFF, CXN_AB) (AFF, AFF, -)
+  SIG_AAC_RC = 3,    // (AFF, AFF, CXN_AB) (-, ROT, CXN_AB)         TFIM bond, first Trotter step
+  SIG_C_RC = 4,      // (-, -, CXN_AB) (-, ROT, CXN_AB)             TFIM bond
+  SIG_RAC = 5,       // (ROT, AFF, CXN_AB)
+  SIG_0AC = 6,       // (-, AFF, CXN_AB)
+  SIG_AAC_A0 = 7,    // (AFF, AFF, CXN_AB) (AFF, -, -)
+  SIG_AAC_0A = 8,    // (AFF, AFF, CXN_AB) (-, AFF, -)
+  SIG_COUNT
+};
 
 constexpr int kMaxTileQubits = 7;
 constexpr int kMaxDmQubits = 16;   // 4^16 doubles = 34 GB
@@ -116,12 +200,14 @@ struct CircuitProgram {
   std::vector<double> term_coeff;
   int64_t n_gates = 0;
   bool needs_dense = false;             // uses P_DENSE / Q_DENSE* (selects the FULL kernel)
+  bool tma = false;                     // sweeps are in the TMA tile layout
 };
 
 struct LowerOptions {
   int tile_qubits = 6;
   int low_qubits = 2;
   int direct = kPassLoadDirect | kPassStoreDirect;  // which direct passes the planner may request
+  bool tma = false;  // emit the TMA tile layout for circuits wider than a 6-digit tile (tile_qubits 6, low_qubits 2)
 };
 
 // Lowers circuit c of the batch.  Never throws; sets status on per-circuit failure.
