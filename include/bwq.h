@@ -120,6 +120,11 @@ typedef struct {
 #define BWQ_OPT_NO_DIRECT_STORE 2
 #define BWQ_OPT_NO_PIPELINE 4   /* bwq_dm_run: lower the whole batch before the first launch */
 #define BWQ_OPT_FORCE_PIPELINE 8 /* bwq_dm_run: pipeline segments even when the sweeps look too short to matter */
+#define BWQ_OPT_PERSIST 32       /* density matrix: after the first sweep use the persistent double-buffered
+                                   dm_sweep_tma_persistent_kernel (two resident CTAs per SM, producer warp) instead of one
+                                   CTA per tile; measured slower (8 compute warps per SM), kept for A/B */
+#define BWQ_OPT_NO_TMA 16       /* density matrix: keep circuits wider than the tile on dm_sweep_kernel (LDG/STG tile
+                                   movement) instead of dm_sweep_tma_kernel (TMA tensor-map tiles); A/B and parity tests */
 
 /* Counters of the last *_run call (for the roofline: bytes = sweeps x 16 B x 4^n). */
 typedef struct {
@@ -135,6 +140,7 @@ typedef struct {
   int64_t h2d_bytes, d2h_bytes;/* program upload / value download of the last run          */
   int64_t sv_state_bytes_swept;/* statevector sweeps: sum of 2 * 16 B * 2^n (+ 16 B * 2^n per
                                   expectation pass) of the last bwq_sv_* call                  */
+  int64_t n_tma_sweep_launches;/* of n_sweep_launches: launches of dm_sweep_tma_kernel       */
 } bwq_stats;
 
 typedef struct bwq_ctx bwq_ctx;
@@ -185,6 +191,10 @@ typedef struct bwq_program bwq_program;
 /* Lowers batch circuit `circuit` to its sweep program.  tile_qubits/low_qubits as in options. */
 int bwq_lower_dm(const bwq_noise_table* table, const bwq_batch* batch, int32_t circuit,
                  int32_t tile_qubits, int32_t low_qubits, bwq_program** out);
+/* Same with planner flags: bit 0 = emit the TMA tile layout (what bwq_dm_run does by default for
+ * circuits wider than the tile; see ml_qem_b200/csrc/program.h). */
+int bwq_lower_dm_ex(const bwq_noise_table* table, const bwq_batch* batch, int32_t circuit,
+                    int32_t tile_qubits, int32_t low_qubits, int32_t flags, bwq_program** out);
 void bwq_program_free(bwq_program* p);
 /* Sizes: [0]=n_active, [1]=n_sweeps, [2]=n_passes, [3]=n_prog (8-byte words), [4]=needs_dense,
  * [5]=status, [6]=n_terms, [7]=n_gates */

@@ -5,13 +5,18 @@
 #include <chrono>
 #include <cstdarg>
 #include <cstdio>
+#include <cstdlib>
 #include <cstring>
 #include <numeric>
 #include <string>
 #include <thread>
 #include <vector>
 
+#include <cuda.h>
+#include <cudaTypedefs.h>
+
 #include "kernels.cuh"
+#include "kernels_tma.cuh"
 #include "sv_kernels.cuh"
 
 using namespace bwq;
@@ -77,6 +82,10 @@ struct Blob {
 struct DmChunk {
   int first = 0, count = 0, nd = 0, kq = 0;
   bool full = false;
+  bool tma = false;               // sweeps in the TMA tile layout: dm_sweep_tma_kernel
+  int window_log2 = 0, n_windows = 1;  // circuit slots per tensor map (dim 0 must stay below 2^31 elements)
+  size_t map_first = 0;           // first tensor map of the chunk in the plan's map array
+  std::vector<uint32_t> map_keys; // per map id: the four upper digit positions in box order, one byte each
   std::vector<int> live;  // circuits that still have a sweep s, per sweep index
   std::vector<int64_t> desc_off;  // per sweep index: first descriptor of the launch (sweep-major table)
   std::vector<int64_t> bytes;  // algorithmic bytes of launch s: tiles that are not provably zero
@@ -91,6 +100,8 @@ struct DmPlan {
   std::vector<std::pair<int64_t, double>> host_fix;
   int64_t max_chunk_bytes = 0, n_gates = 0, n_passes = 0;
   double lower_ms = 0, h2d_ms = 0;
+  size_t n_maps = 0;              // tensor maps of all TMA chunks
+  const void* maps_for = nullptr; // state buffer the uploaded maps were encoded for
 };
 
 struct SvGroup {
@@ -129,6 +140,8 @@ struct SvPlan {
   double lower_ms = 0, h2d_ms = 0;
 };
 
+constexpr int kMaxPersistLaunches = 16384;
+
 struct bwq_ctx {
   int device = 0;
   cudaStream_t stream = nullptr;
@@ -142,7 +155,10 @@ struct bwq_ctx {
   // density-matrix program slots: slot 0 is the prepared batch of bwq_dm_prepare / bwq_dm_execute;
   // bwq_dm_run alternates between both so that segment k+1 is lowered on the host threads while
   // the GPU executes segment k
-  struct DmSlot { DmPlan plan; PinBuf h_prog; DevBuf d_prog; cudaEvent_t h2d_done = nullptr; } dm[2];
+  struct DmSlot { DmPlan plan; PinBuf h_prog, h_maps; DevBuf d_prog, d_maps; cudaEvent_t h2d_done = nullptr; } dm[2];
+  DevBuf d_tma_a;                     // thread-base table of dm_sweep_tma_kernel
+  DevBuf d_counters;                  // tile counters of the persistent launches (one per launch of an execute)
+  PFN_cuTensorMapEncodeTiled encode_tiled = nullptr;  // driver entry point; null => no TMA path
   SvPlan sv_plan;
   std::vector<cudaEvent_t> chunk_ev;  // begin/end of each chunk's sweep launches
   bwq_ctx* companion = nullptr;       // statevector side of bwq_meas_data_run (created on first use)
@@ -220,6 +236,24 @@ extern "C" int bwq_create(int device, bwq_ctx** out) {
     if ((e = cudaMemcpy(ctx->d_b0.p, tab.data(), tab.size() * sizeof(uint32_t), cudaMemcpyHostToDevice)) != cudaSuccess)
       return bail(e, "cudaMemcpy(b0 table)");
   }
+  {
+    std::vector<uint32_t> tab((size_t)kTmaPairs * kTmaThreads);
+    fill_tma_a_table(tab.data());
+    if ((e = ctx->d_tma_a.reserve(tab.size() * sizeof(uint32_t))) != cudaSuccess) return bail(e, "cudaMalloc(tma table)");
+    if ((e = cudaMemcpy(ctx->d_tma_a.p, tab.data(), tab.size() * sizeof(uint32_t), cudaMemcpyHostToDevice)) != cudaSuccess)
+      return bail(e, "cudaMemcpy(tma table)");
+    if ((e = ctx->d_counters.reserve(sizeof(unsigned int) * kMaxPersistLaunches)) != cudaSuccess) return bail(e, "cudaMalloc(counters)");
+    if ((e = cudaFuncSetAttribute(dm_sweep_tma_persistent_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kTmaPersistSmem)) != cudaSuccess)
+      return bail(e, "cudaFuncSetAttribute(dm_sweep_tma_persistent_kernel)");
+    if ((e = cudaFuncSetAttribute(dm_sweep_tma_persistent_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kTmaPersistSmem)) != cudaSuccess)
+      return bail(e, "cudaFuncSetAttribute(dm_sweep_tma_persistent_kernel<full>)");
+    void* fn = nullptr;
+    cudaDriverEntryPointQueryResult q;
+    if (cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &fn, cudaEnableDefault, &q) == cudaSuccess && q == cudaDriverEntryPointSuccess)
+      ctx->encode_tiled = (PFN_cuTensorMapEncodeTiled)fn;
+    else
+      cudaGetLastError();
+  }
   *out = ctx;
   return BWQ_OK;
 }
@@ -229,7 +263,8 @@ extern "C" int bwq_destroy(bwq_ctx* ctx) {
   cudaSetDevice(ctx->device);
   cudaStreamSynchronize(ctx->stream);
   ctx->d_b0.release(); ctx->d_noise.release(); ctx->d_states.release(); ctx->d_out.release();
-  for (auto& sl : ctx->dm) { sl.d_prog.release(); sl.h_prog.release(); if (sl.h2d_done) cudaEventDestroy(sl.h2d_done); }
+  for (auto& sl : ctx->dm) { sl.d_prog.release(); sl.h_prog.release(); sl.d_maps.release(); sl.h_maps.release(); if (sl.h2d_done) cudaEventDestroy(sl.h2d_done); }
+  ctx->d_tma_a.release(); ctx->d_counters.release();
   ctx->d_scratch.release(); ctx->h_out.release();
   ctx->d_sv_prog.release(); ctx->h_sv_prog.release();
   ctx->d_wide_prog.release(); ctx->h_wide_prog.release(); ctx->d_partial.release();
@@ -356,6 +391,7 @@ static int dm_lower_impl(bwq_ctx* ctx, bwq_ctx::DmSlot& sl, const bwq_batch* b, 
   lo.tile_qubits = ctx->opt.tile_qubits ? ctx->opt.tile_qubits : 6;
   lo.low_qubits = ctx->opt.low_qubits > 0 ? ctx->opt.low_qubits : 2;
   lo.direct = (ctx->opt.flags & BWQ_OPT_NO_DIRECT_LOAD ? 0 : kPassLoadDirect) | (ctx->opt.flags & BWQ_OPT_NO_DIRECT_STORE ? 0 : kPassStoreDirect);
+  lo.tma = ctx->encode_tiled != nullptr && !(ctx->opt.flags & BWQ_OPT_NO_TMA);
   P.tile_qubits = lo.tile_qubits;
   std::vector<CircuitProgram> progs(N);  // progs[c] <-> batch circuit c0 + c
   parallel_for(N, host_threads(ctx), [&](int c) { lower_dm_circuit(ctx->noise, *b, c0 + c, lo, &progs[c]); });
@@ -450,6 +486,7 @@ static int dm_lower_impl(bwq_ctx* ctx, bwq_ctx::DmSlot& sl, const bwq_batch* b, 
       ch.live.push_back(live);
     }
     for (int k = i; k < j; ++k) ch.full = ch.full || progs[order[k]].needs_dense;
+    ch.tma = progs[order[i]].tma;  // a function of the options and the width: uniform inside a chunk
     // bytes per launch: a tile with X/Y on an outside digit no pass has touched yet is all zero
     // (kernels.cuh): the first sweep stores it (8 B/element, no read), later sweeps skip it
     ch.bytes.assign(max_sweeps, 0);
@@ -474,6 +511,28 @@ static int dm_lower_impl(bwq_ctx* ctx, bwq_ctx::DmSlot& sl, const bwq_batch* b, 
         ch.desc_off.push_back(off);
         for (int slot = 0; slot < ch.live[sidx]; ++slot) all[off++] = tmp[(sw_off[i + slot] - base) + (int64_t)sidx];
       }
+    }
+    if (ch.tma) {
+      // tensor maps: one per ordered tuple of upper digit positions (box order) and window of
+      // circuit slots; the sweep descriptors get the 16-bit map id in place of pos[6..7]
+      ch.window_log2 = std::max(0, 31 - 2 * nd);
+      if (const char* wenv = std::getenv("BWQ_TMA_WINDOW_LOG2"))  // tests: several windows at small widths
+        ch.window_log2 = std::max(0, std::min(ch.window_log2, std::atoi(wenv)));
+      ch.n_windows = (ch.count + (1 << ch.window_log2) - 1) >> ch.window_log2;
+      ch.map_first = P.n_maps;
+      SweepDesc* all = (SweepDesc*)(hb + P.o_sweeps);
+      for (int64_t d = sw_off[i]; d < sw_off[j]; ++d) {
+        SweepDesc& sd = all[d];
+        uint32_t key = 0;
+        for (int k = 0; k < 4; ++k) key |= uint32_t(sd.pos[2 + ((sd.pos[6] >> (2 * k)) & 3)]) << (8 * k);
+        size_t id = 0;
+        while (id < ch.map_keys.size() && ch.map_keys[id] != key) ++id;
+        if (id == ch.map_keys.size()) ch.map_keys.push_back(key);
+        sd.pos[6] = (uint8_t)(id & 0xff);
+        sd.pos[7] = (uint8_t)(id >> 8);
+      }
+      if (ch.map_keys.size() >= 65536) return fail(ctx, BWQ_ERR_ARG, "too many distinct tile layouts in one chunk");
+      P.n_maps += ch.map_keys.size() * (size_t)ch.n_windows;
     }
     P.chunks.push_back(std::move(ch));
     i = j;
@@ -504,6 +563,8 @@ static int dm_lower_impl(bwq_ctx* ctx, bwq_ctx::DmSlot& sl, const bwq_batch* b, 
   return BWQ_OK;
 }
 
+static int dm_encode_maps(bwq_ctx* ctx, bwq_ctx::DmSlot& sl);
+
 // Device part of the preparation: buffers + one H2D copy of the slot's program blob.
 // sync = false (pipelined run): the value buffers were sized for the whole batch by the caller and
 // the copy is only enqueued; sl.h2d_done tells the lowering thread when the pinned blob is free.
@@ -520,6 +581,12 @@ static int dm_upload_impl(bwq_ctx* ctx, bwq_ctx::DmSlot& sl, bool sync) {
   }
   cudaStream_t st = ctx->stream;
   if (sync) CK(cudaEventRecord(ctx->ev[0], st));
+  if (have) {
+    // the pinned map staging may still feed the copy of this slot's previous segment
+    if (!sync && P.n_maps) CK(cudaEventSynchronize(sl.h2d_done));
+    int rc = dm_encode_maps(ctx, sl);
+    if (rc) return rc;
+  }
   if (have) CK(cudaMemcpyAsync(sl.d_prog.p, hb, blob_total, cudaMemcpyHostToDevice, st));
   CK(cudaEventRecord(sync ? ctx->ev[1] : sl.h2d_done, st));
   if (sync) {
@@ -528,6 +595,39 @@ static int dm_upload_impl(bwq_ctx* ctx, bwq_ctx::DmSlot& sl, bool sync) {
     CK(cudaEventElapsedTime(&ms, ctx->ev[0], ctx->ev[1]));
     P.h2d_ms = ms;
   }
+  return BWQ_OK;
+}
+
+// Tensor maps of the slot's TMA chunks, encoded for the current state buffer: rank 5, dim 0 = the
+// whole window of states (stride 1: the tile's 128-byte runs start at any multiple of 16 elements),
+// dims 1..4 = one resident digit each (extent 4, stride 8 * 4^pos bytes), box 16 x 4 x 4 x 4 x 4,
+// 128-byte swizzle.  Uploaded on the engine stream (pinned staging).
+static int dm_encode_maps(bwq_ctx* ctx, bwq_ctx::DmSlot& sl) {
+  DmPlan& P = sl.plan;
+  if (P.n_maps == 0) return BWQ_OK;
+  if (!ctx->encode_tiled) return fail(ctx, BWQ_ERR_UNSUPPORTED, "TMA program without cuTensorMapEncodeTiled");
+  CK(sl.h_maps.reserve(P.n_maps * sizeof(CUtensorMap)));
+  CK(sl.d_maps.reserve(P.n_maps * sizeof(CUtensorMap)));
+  CUtensorMap* hm = (CUtensorMap*)sl.h_maps.p;
+  for (const DmChunk& ch : P.chunks) {
+    if (!ch.tma) continue;
+    const uint64_t state_elems = uint64_t(1) << (2 * ch.nd);
+    for (size_t id = 0; id < ch.map_keys.size(); ++id)
+      for (int w = 0; w < ch.n_windows; ++w) {
+        const uint32_t key = ch.map_keys[id];
+        cuuint64_t gdim[5] = {state_elems << ch.window_log2, 4, 4, 4, 4};
+        cuuint64_t gstr[4];
+        for (int k = 0; k < 4; ++k) gstr[k] = cuuint64_t(8) << (2 * ((key >> (8 * k)) & 0xffu));
+        cuuint32_t box[5] = {16, 4, 4, 4, 4}, estr[5] = {1, 1, 1, 1, 1};
+        void* base = (double*)ctx->d_states.p + (uint64_t(w) << ch.window_log2) * state_elems;
+        CUresult r = ctx->encode_tiled(&hm[ch.map_first + id * ch.n_windows + w], CU_TENSOR_MAP_DATA_TYPE_FLOAT64, 5, base, gdim, gstr, box,
+                                       estr, CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_128B,
+                                       CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+        if (r != CUDA_SUCCESS) return fail(ctx, BWQ_ERR_CUDA, "cuTensorMapEncodeTiled failed (%d)", (int)r);
+      }
+  }
+  CK(cudaMemcpyAsync(sl.d_maps.p, hm, P.n_maps * sizeof(CUtensorMap), cudaMemcpyHostToDevice, ctx->stream));
+  P.maps_for = ctx->d_states.p;
   return BWQ_OK;
 }
 
@@ -574,8 +674,17 @@ static int dm_execute_impl(bwq_ctx* ctx, bwq_ctx::DmSlot& sl, double* out_vals, 
   cudaStream_t st = ctx->stream;
   double* d_out = out_on_device ? out_vals : (double*)ctx->d_out.p + obs_off;
   const char* db = (const char*)sl.d_prog.p;
+  // the state buffer moved since the maps were encoded (another prepare grew it): encode again
+  if (P.n_maps && P.maps_for != ctx->d_states.p) {
+    CK(cudaStreamSynchronize(st));
+    int rc = dm_encode_maps(ctx, sl);
+    if (rc) return rc;
+  }
   if (!deferred) CK(cudaEventRecord(ctx->ev[1], st));
   if (P.n_obs > 0) CK(cudaMemsetAsync(d_out, 0, sizeof(double) * (size_t)P.n_obs, st));
+  int n_persist = 0;
+  const bool persist_ok = (ctx->opt.flags & BWQ_OPT_PERSIST) != 0;
+  if (P.n_maps && persist_ok) CK(cudaMemsetAsync(ctx->d_counters.p, 0, sizeof(unsigned int) * kMaxPersistLaunches, st));
   const size_t n_ev = deferred ? 0 : std::min(P.chunks.size(), ctx->chunk_ev.size() / 2);
   for (size_t ci = 0; ci < P.chunks.size(); ++ci) {
     const DmChunk& ch = P.chunks[ci];
@@ -593,8 +702,28 @@ static int dm_execute_impl(bwq_ctx* ctx, bwq_ctx::DmSlot& sl, double* out_vals, 
       const int live = ch.live[sidx];
       L.sweeps = (const SweepDesc*)(db + P.o_sweeps) + ch.desc_off[sidx];
       L.prefetch_dist = sidx == 0 ? 0 : pf_dist;  // the first sweep synthesises |0..0><0..0|, nothing to read
-      CK(ch.full ? launch_sweep_kq<true>(ch.kq, L, (int)sidx, tiles * live, st)
-                 : launch_sweep_kq<false>(ch.kq, L, (int)sidx, tiles * live, st));
+      if (ch.tma) {
+        DmTmaLaunch TL;
+        TL.states = L.states; TL.stride = L.stride; TL.n_digits = L.n_digits; TL.prefetch_dist = L.prefetch_dist;
+        TL.sweeps = L.sweeps; TL.prog = L.prog;
+        TL.a_table = (const uint32_t*)ctx->d_tma_a.p;
+        TL.maps = (const CUtensorMap*)sl.d_maps.p + ch.map_first;
+        TL.n_windows = ch.n_windows; TL.window_log2 = ch.window_log2;
+        if (sidx > 0 && persist_ok && n_persist < kMaxPersistLaunches) {
+          // resident CTAs (two per SM) pull tiles from this launch's counter; tile k+1 streams in while k is swept
+          const unsigned total = (unsigned)(tiles * live);
+          const unsigned grid = std::min<unsigned>(total, 2u * (unsigned)ctx->sm_count);
+          unsigned int* cnt = (unsigned int*)ctx->d_counters.p + n_persist++;
+          if (ch.full) dm_sweep_tma_persistent_kernel<true><<<grid, kTmaPersistThreads, kTmaPersistSmem, st>>>(TL, cnt, total);
+          else dm_sweep_tma_persistent_kernel<false><<<grid, kTmaPersistThreads, kTmaPersistSmem, st>>>(TL, cnt, total);
+        } else if (ch.full) dm_sweep_tma_kernel<true><<<(unsigned)(tiles * live), kTmaThreads, 0, st>>>(TL, (int)sidx);
+        else dm_sweep_tma_kernel<false><<<(unsigned)(tiles * live), kTmaThreads, 0, st>>>(TL, (int)sidx);
+        CK(cudaGetLastError());
+        S.n_tma_sweep_launches++;
+      } else {
+        CK(ch.full ? launch_sweep_kq<true>(ch.kq, L, (int)sidx, tiles * live, st)
+                   : launch_sweep_kq<false>(ch.kq, L, (int)sidx, tiles * live, st));
+      }
       S.n_sweep_launches++;
       S.n_state_sweeps += live;
       S.state_bytes_swept += ch.bytes[sidx];
@@ -726,6 +855,7 @@ static int dm_run_impl(bwq_ctx* ctx, const bwq_batch* b, double* out_vals, int32
     if (helper.joinable()) helper.join();
     if (rc || next_rc) { cudaStreamSynchronize(st); return rc ? rc : next_rc; }
     total.n_sweep_launches += S.n_sweep_launches; total.n_state_sweeps += S.n_state_sweeps;
+    total.n_tma_sweep_launches += S.n_tma_sweep_launches;
     total.n_passes += S.n_passes; total.n_gates += S.n_gates; total.state_bytes_swept += S.state_bytes_swept;
     total.n_other_launches += S.n_other_launches; total.lower_ms += seg_lower_ms;
     total.h2d_bytes += S.h2d_bytes; total.d2h_bytes += S.d2h_bytes;
@@ -1207,8 +1337,14 @@ extern "C" int bwq_meas_data_run(bwq_ctx* ctx, const bwq_batch* b, double* out_i
 // ------------------------------------------------------------------------------------------------
 // host-only lowering introspection
 // ------------------------------------------------------------------------------------------------
+extern "C" int bwq_lower_dm_ex(const bwq_noise_table* table, const bwq_batch* batch, int32_t circuit, int32_t tile_qubits,
+                               int32_t low_qubits, int32_t flags, bwq_program** out);
 extern "C" int bwq_lower_dm(const bwq_noise_table* table, const bwq_batch* batch, int32_t circuit,
                             int32_t tile_qubits, int32_t low_qubits, bwq_program** out) {
+  return bwq_lower_dm_ex(table, batch, circuit, tile_qubits, low_qubits, 0, out);
+}
+extern "C" int bwq_lower_dm_ex(const bwq_noise_table* table, const bwq_batch* batch, int32_t circuit, int32_t tile_qubits,
+                               int32_t low_qubits, int32_t flags, bwq_program** out) {
   if (!batch || !out || circuit < 0 || circuit >= batch->n_circuits) return BWQ_ERR_ARG;
   NoiseTable nt;
   char err[256];
@@ -1217,6 +1353,7 @@ extern "C" int bwq_lower_dm(const bwq_noise_table* table, const bwq_batch* batch
   LowerOptions lo;
   lo.tile_qubits = tile_qubits ? tile_qubits : 6;
   lo.low_qubits = low_qubits < 0 ? 0 : (low_qubits ? low_qubits : 2);
+  lo.tma = (flags & 1) != 0;
   bwq_program* p = new bwq_program();
   lower_dm_circuit(nt, *batch, circuit, lo, &p->p);
   *out = p;

@@ -348,6 +348,29 @@ static void lower_terms(const bwq_batch& b, int c, const std::vector<int>& digit
   }
 }
 
+// op list of a pass -> PassSig (straight-line kernel body) or SIG_GENERIC.  Only passes that do not
+// target slot 0 have fast bodies (their two register groups share every 16-byte access).
+static PassSig classify_pass(const std::vector<MacroOp>& ops, bool fast_layout) {
+  if (!fast_layout || ops.empty() || ops.size() > 2) return SIG_GENERIC;
+  auto is = [](const MacroOp& o, uint8_t a, uint8_t b, uint8_t q) { return o.pre_a == a && o.pre_b == b && o.twoq == q; };
+  const MacroOp& o0 = ops[0];
+  if (ops.size() == 1) {
+    if (is(o0, P_AFF, P_AFF, Q_CXN_AB)) return SIG_AAC;
+    if (is(o0, P_ROT, P_AFF, Q_CXN_AB)) return SIG_RAC;
+    if (is(o0, P_NONE, P_AFF, Q_CXN_AB)) return SIG_0AC;
+    return SIG_GENERIC;
+  }
+  const MacroOp& o1 = ops[1];
+  if (is(o0, P_AFF, P_AFF, Q_CXN_AB)) {
+    if (is(o1, P_AFF, P_AFF, Q_NONE)) return SIG_AAC_AA;
+    if (is(o1, P_NONE, P_ROT, Q_CXN_AB)) return SIG_AAC_RC;
+    if (is(o1, P_AFF, P_NONE, Q_NONE)) return SIG_AAC_A0;
+    if (is(o1, P_NONE, P_AFF, Q_NONE)) return SIG_AAC_0A;
+  }
+  if (is(o0, P_NONE, P_NONE, Q_CXN_AB) && is(o1, P_NONE, P_ROT, Q_CXN_AB)) return SIG_C_RC;
+  return SIG_GENERIC;
+}
+
 void lower_dm_circuit(const NoiseTable& noise, const bwq_batch& b, int c, const LowerOptions& opt,
                       CircuitProgram* out) {
   *out = CircuitProgram();
@@ -496,10 +519,14 @@ void lower_dm_circuit(const NoiseTable& noise, const bwq_batch& b, int c, const 
   auto src_ptr = [&](uint32_t off) -> const double* {
     return (off & kLocalMat) ? &out->mats[off & ~kLocalMat] : &noise.data[off];
   };
+  // TMA tile layout: circuits wider than the 6-digit tile, default tiling (see program.h)
+  const bool tma = opt.tma && nd > 6 && nd <= 15 && std::min(std::max(opt.tile_qubits, 3), std::min(nd, kMaxTileQubits)) == 6 &&
+                   std::min(std::max(opt.low_qubits, 1), 4) == 2;
+  out->tma = tma;
   // bytes a pass adds to a sweep block; parameters already present (same source) are shared
   struct Seen { uint32_t key; uint16_t off; };
   auto pass_bytes = [&](const HostPass& p, const std::vector<Seen>& seen) {
-    int bytes = (int)sizeof(PassHdr) + (int)sizeof(BlockOp) * (int)p.ops.size();
+    int bytes = (int)sizeof(PassHdr) + (int)sizeof(BlockOp) * (int)p.ops.size() + (tma ? 64 : 0);
     std::vector<uint32_t> mine;
     auto add = [&](uint32_t key, int words) {
       if (!words) return;
@@ -587,6 +614,26 @@ void lower_dm_circuit(const NoiseTable& noise, const bwq_batch& b, int c, const 
     SweepDesc sw{};
     int s = 0;
     for (int d = 0; d < nd; ++d) if (in_tile[d]) { sw.pos[s] = (uint8_t)d; slot_of[d] = s++; }
+    if (tma) {
+      // box order of the four upper digits: a digit that shares a pass with digit 1 (or 0) should not
+      // sit in slot 2 (3), where its bits feed the 128-byte swizzle of the chunk bits its partner
+      // occupies (2-way bank conflicts, program.h) -- such digits go to the last box dims
+      int key[4], ord[4] = {0, 1, 2, 3};
+      for (int k = 0; k < 4; ++k) {
+        const int d = sw.pos[2 + k];
+        key[k] = 0;
+        for (int i : sel) {
+          const int other = passes[i].qa == d ? passes[i].qb : passes[i].qb == d ? passes[i].qa : -1;
+          if (other == 1) key[k] = 2;
+          else if (other == 0 && key[k] < 1) key[k] = 1;
+        }
+      }
+      std::stable_sort(ord, ord + 4, [&](int a, int c) { return key[a] < key[c]; });
+      uint8_t code = 0;
+      for (int k = 0; k < 4; ++k) { slot_of[sw.pos[2 + ord[k]]] = 2 + k; code |= (uint8_t)(ord[k] << (2 * k)); }
+      sw.pos[6] = code;
+      sw.pos[7] = kTmaSweep;
+    }
 
     // ---- direct passes: passes on disjoint qubits commute, so an eligible pass (neither target in
     // the two lowest slots) with no predecessor / successor on its qubits inside this sweep is
@@ -596,7 +643,7 @@ void lower_dm_circuit(const NoiseTable& noise, const bwq_batch& b, int c, const 
       return passes[i].qa == passes[j].qa || passes[i].qa == passes[j].qb || passes[i].qb == passes[j].qa || passes[i].qb == passes[j].qb;
     };
     bool first_direct = false, last_direct = false;
-    if (opt.direct & kPassLoadDirect) {
+    if (!tma && (opt.direct & kPassLoadDirect)) {
       for (size_t k = 0; k < sel.size() && !first_direct; ++k) {
         if (!eligible(sel[k])) continue;
         bool free_ = true;
@@ -606,7 +653,7 @@ void lower_dm_circuit(const NoiseTable& noise, const bwq_batch& b, int c, const 
         first_direct = true;
       }
     }
-    if (opt.direct & kPassStoreDirect) {
+    if (!tma && (opt.direct & kPassStoreDirect)) {
       const size_t stop = (first_direct && sel.size() > 1) ? 1 : 0;  // the front pass stays in front
       for (size_t k = sel.size(); k-- > stop && !last_direct;) {
         if (!eligible(sel[k])) continue;
@@ -621,12 +668,15 @@ void lower_dm_circuit(const NoiseTable& noise, const bwq_batch& b, int c, const 
     // ---- emit the block
     size_t n_ops_total = 0;
     for (int i : sel) n_ops_total += passes[i].ops.size();
-    const size_t hdr_words = (sizeof(BlockHdr) + sizeof(PassHdr) * sel.size() + sizeof(BlockOp) * n_ops_total) / 8;
+    const size_t ext_words = tma ? 8 * sel.size() : 0;  // corner tables: 16 x u32 per pass
+    const size_t hdr_words = (sizeof(BlockHdr) + sizeof(PassHdr) * sel.size() + sizeof(BlockOp) * n_ops_total) / 8 + ext_words;
     const size_t blk_begin = out->prog.size();
     out->prog.resize(blk_begin + (size_t)bytes / 8, 0);
     uint64_t* blk = out->prog.data() + blk_begin;
     BlockHdr* bh = reinterpret_cast<BlockHdr*>(blk);
     bh->n_passes = (int32_t)sel.size();
+    bh->ext_q16 = tma ? (int32_t)((hdr_words - ext_words) / 2) : 0;
+    uint32_t* ext = reinterpret_cast<uint32_t*>(blk + (hdr_words - ext_words));
     PassHdr* ph = reinterpret_cast<PassHdr*>(blk + sizeof(BlockHdr) / 8);
     BlockOp* bo = reinterpret_cast<BlockOp*>(blk + (sizeof(BlockHdr) + sizeof(PassHdr) * sel.size()) / 8);
     size_t op_cursor = 0, par_cursor = hdr_words;
@@ -652,6 +702,14 @@ void lower_dm_circuit(const NoiseTable& noise, const bwq_batch& b, int c, const 
         sw.pos[7] = (uint8_t)(kFirstDirect | ph[k].sa | (ph[k].sb << 3));
       }
       if (k + 1 == sel.size() && last_direct) ph[k].flags |= kPassStoreDirect;
+      if (tma) {
+        const int sa = ph[k].sa, sb = ph[k].sb;
+        ph[k].row = (uint8_t)tma_pair_row(sa, sb);
+        ph[k].gofs = 8u * tswz(1u << tma_pass_layout(std::min(sa, sb), std::max(sa, sb)).beta);
+        for (int db = 0; db < 4; ++db)
+          for (int da = 0; da < 4; ++da) ext[16 * k + da + 4 * db] = 8u * tswz((uint32_t(da) << (2 * sa)) | (uint32_t(db) << (2 * sb)));
+        ph[k].sig = (uint8_t)classify_pass(p.ops, sa != 0 && sb != 0);
+      }
       for (const MacroOp& o : p.ops) {
         BlockOp& d = bo[op_cursor++];
         d.pre_a = o.pre_a; d.pre_b = o.pre_b; d.twoq = o.twoq;

@@ -92,7 +92,12 @@ constexpr int kBlockBytes = 8192;  // shared-memory program buffer per CTA
 // merge replaces pos[6..7] by the 16-bit index of the sweep's tensor map.
 constexpr uint8_t kTmaSweep = 0x40;
 constexpr int kTmaThreads = 128;
-constexpr uint32_t tswz(uint32_t j) { return j ^ (((j >> 4) & 7u) << 1); }
+#ifdef __CUDACC__
+#define BWQ_HD __host__ __device__
+#else
+#define BWQ_HD
+#endif
+BWQ_HD constexpr uint32_t tswz(uint32_t j) { return j ^ (((j >> 4) & 7u) << 1); }
 
 // Register-pass work split of the TMA kernel: 128 threads x 32 elements.  A thread owns the 16
 // (da, db) corners of TWO register groups.  Slot 0 not a target: the groups differ in the low bit
@@ -264,7 +269,16 @@ enum SvOpKind : uint8_t {
   SVO_U2 = 3,    // 4x4 on (a,b), local index i_a + 2 i_b       32 doubles
   SVO_SWAP = 4,  // exchange slots a and b
   SVO_D1 = 5,    // phases by physical bit qa                    4 doubles (p0, p1)
-  SVO_D2 = 6     // phases by physical bits (qa,qb), b_qa+2b_qb  8 doubles
+  SVO_D2 = 6,    // phases by physical bits (qa,qb), b_qa+2b_qb  8 doubles
+  // structured 1-qubit unitaries (global phase dropped -- it never reaches an expectation value):
+  SVO_R1 = 7,    // real 2x2 (ry, h, ...): {m00, m01, m10, m11}                          4 doubles
+  SVO_X1 = 8,    // real diagonal, imaginary off-diagonal (rx, sx, x): {d0, d1, o01, o10},
+                 // u = [[d0, i o01], [i o10, d1]]                                       4 doubles
+  // a whole layer of K commuting exp(-i t ZZ)-type bonds with ONE phase pair (p_even, p_odd): the
+  // phase of an amplitude is table[w], w = number of bonds with odd parity =
+  // sum_j popc((x ^ (x >> d_j)) & M_j) over the distinct bond distances d_j.
+  // params: {u32 n_d, u32 K}, n_d x {u32 d, u32 M}, pad to 16 B, (K + 1) complex table
+  SVO_DZZ = 9
 };
 enum : uint8_t { SVF_ON_B = 1, SVF_COND = 2, SVF_COND_VAL = 4 };
 struct SvBlockOp {   // 8 B

@@ -86,6 +86,30 @@ __device__ __forceinline__ void sv_op_1q(double2 (&v)[NG][4], const double2* __r
   }
 }
 
+// structured 2x2 (global phase dropped by the planner): XT = false: real matrix {m00, m01, m10, m11};
+// XT = true: [[d0, i o01], [i o10, d1]] as {d0, d1, o01, o10} -- 4 multiply-adds per amplitude
+// instead of the 8 of a complex 2x2 (rx / ry / sx / h layers of the Trotter circuits)
+template <int NG, bool ON_B, bool XT>
+__device__ __forceinline__ void sv_op_1s(double2 (&v)[NG][4], const double* __restrict__ m) {
+  constexpr int P0 = 0, P1 = ON_B ? 2 : 1, Q0 = ON_B ? 1 : 2, Q1 = 3;
+  const double2 m01 = *reinterpret_cast<const double2*>(m), m23 = *reinterpret_cast<const double2*>(m + 2);
+#pragma unroll
+  for (int k = 0; k < NG; ++k) {
+#pragma unroll
+    for (int h = 0; h < 2; ++h) {
+      const int A = h ? Q0 : P0, B = h ? Q1 : P1;
+      const double2 a = v[k][A], b = v[k][B];
+      if (XT) {
+        v[k][A] = make_double2(fma(-m23.x, b.y, m01.x * a.x), fma(m23.x, b.x, m01.x * a.y));
+        v[k][B] = make_double2(fma(-m23.y, a.y, m01.y * b.x), fma(m23.y, a.x, m01.y * b.y));
+      } else {
+        v[k][A] = make_double2(fma(m01.y, b.x, m01.x * a.x), fma(m01.y, b.y, m01.x * a.y));
+        v[k][B] = make_double2(fma(m23.y, b.x, m23.x * a.x), fma(m23.y, b.y, m23.x * a.y));
+      }
+    }
+  }
+}
+
 // 4x4, matrix index i_first + 2 i_second; ON_B: (first, second) = (slot b, slot a)
 template <int NG, bool ON_B>
 __device__ __forceinline__ void sv_op_u2(double2 (&v)[NG][4], const double2* __restrict__ m) {
@@ -149,6 +173,27 @@ __device__ __forceinline__ void sv_run_pass(double2* __restrict__ tile, const do
     const uint32_t kind = raw.x & 0xffu, flags = (raw.x >> 8) & 0xffu;
     const uint32_t qa = (raw.x >> 16) & 0xffu, qb = raw.x >> 24;
     const double2* m = reinterpret_cast<const double2*>(pbuf + (raw.y & 0xffffu));
+    if (kind == SVO_DZZ) {
+      // fused layer of ZZ-type bonds: phase = table[number of bonds with odd parity]
+      const uint2* hdr = reinterpret_cast<const uint2*>(m);
+      const uint32_t n_d = hdr[0].x;
+      const double2* tab = reinterpret_cast<const double2*>(hdr + ((n_d + 2u) & ~1u));
+#pragma unroll
+      for (int k = 0; k < NG; ++k) {
+        uint32_t w[4] = {0u, 0u, 0u, 0u};
+        for (uint32_t j = 0; j < n_d; ++j) {
+          const uint2 dm = hdr[1 + j];
+#pragma unroll
+          for (int c = 0; c < 4; ++c) {
+            const uint32_t x = gidx0[k] | ((c & 1) ? ca : 0u) | ((c & 2) ? cb : 0u);
+            w[c] += __popc((x ^ (x >> dm.x)) & dm.y);
+          }
+        }
+#pragma unroll
+        for (int c = 0; c < 4; ++c) v[k][c] = cmul_d(tab[w[c]], v[k][c]);
+      }
+      continue;
+    }
     if (kind == SVO_D2 || kind == SVO_D1) {
       // phase index b_qa (+ 2 b_qb); gidx0 has zeros at pa and pb, so the slot bits OR in
       const bool two = kind == SVO_D2;
@@ -178,6 +223,12 @@ __device__ __forceinline__ void sv_run_pass(double2* __restrict__ tile, const do
         if (on_b) sv_op_1q<NG, true, false>(v, m, isx, gidx0, cbit, want, po);
         else sv_op_1q<NG, false, false>(v, m, isx, gidx0, cbit, want, po);
       }
+    } else if (kind == SVO_X1) {
+      if (on_b) sv_op_1s<NG, true, true>(v, reinterpret_cast<const double*>(m));
+      else sv_op_1s<NG, false, true>(v, reinterpret_cast<const double*>(m));
+    } else if (kind == SVO_R1) {
+      if (on_b) sv_op_1s<NG, true, false>(v, reinterpret_cast<const double*>(m));
+      else sv_op_1s<NG, false, false>(v, reinterpret_cast<const double*>(m));
     } else if (kind == SVO_U2) {
       if (on_b) sv_op_u2<NG, true>(v, m);
       else sv_op_u2<NG, false>(v, m);

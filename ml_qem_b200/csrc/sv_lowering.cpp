@@ -38,6 +38,10 @@ struct HOp {
   uint8_t cond_val = 0;
   int32_t off = -1;            // into Planner::mats (doubles)
 };
+struct ZzLayer {               // bonds of one fused diagonal layer (logical qubits) and its phase pair
+  std::vector<std::pair<int, int>> pairs;
+  cd pe, po;
+};
 struct HPass {
   int qa = -1, qb = -1;        // logical slot qubits (-1: any resident slot)
   std::vector<HOp> ops;
@@ -62,6 +66,12 @@ struct Planner {
   struct Block { int a = -1, b = -1; cd m[16]; bool open = false; };
   std::vector<Block> blocks;           // open 2-qubit runs
   std::vector<int> open_of;            // qubit -> index into blocks or -1
+  // ZZ-type diagonal bonds waiting to be fused into one layer op (they commute with every other
+  // diagonal op; the layer is emitted before the next non-diagonal op on one of its qubits)
+  std::vector<ZzLayer> zz_layers;      // emitted layers (HOp::off of SVO_DZZ)
+  ZzLayer pending;
+  uint64_t pending_qubits = 0;
+  bool fuse_layers = true;
 
   int32_t push(const double* m, int nd) {
     while (mats.size() % 2) mats.push_back(0.0);
@@ -86,8 +96,51 @@ struct Planner {
 
   // ---- ops -> passes ---------------------------------------------------------------------
   // need: qubits that must own a slot of the pass; touch: every qubit the op reads or writes
+  void flush_zz() {
+    if (pending.pairs.empty()) return;
+    ZzLayer L;
+    L.pairs.swap(pending.pairs);
+    L.pe = pending.pe; L.po = pending.po;
+    const uint64_t touch = pending_qubits;
+    pending_qubits = 0;
+    HOp op;
+    if (L.pairs.size() == 1) {  // a single bond stays a plain 2-qubit diagonal
+      op.kind = SVO_D2; op.qa = (int8_t)L.pairs[0].first; op.qb = (int8_t)L.pairs[0].second;
+      const cd ph[4] = {L.pe, L.po, L.po, L.pe};
+      op.off = push_c(ph, 4);
+    } else {
+      op.kind = SVO_DZZ;
+      op.off = (int32_t)zz_layers.size();
+      zz_layers.push_back(std::move(L));
+    }
+    emit(op, 0, touch);
+  }
+  void add_zz(int a, int b, cd pe, cd po) {
+    bool dup = false;
+    for (auto& pr : pending.pairs) dup = dup || (pr.first == a && pr.second == b) || (pr.first == b && pr.second == a);
+    if (!pending.pairs.empty() && (dup || pending.pe != pe || pending.po != po || pending.pairs.size() >= 62)) flush_zz();
+    pending.pairs.push_back({a, b});
+    pending.pe = pe; pending.po = po;
+    pending_qubits |= (1ull << a) | (1ull << b);
+  }
+
   void emit(const HOp& op, uint64_t need, uint64_t touch) {
     touch |= need;
+    // a non-diagonal op (it owns slots) or a conditional one on a qubit of the pending layer:
+    // the layer goes first (diagonal ops commute with it and may overtake it)
+    if ((need || op.cond_q >= 0) && (touch & pending_qubits)) {
+      // open 2-qubit runs that are complete bonds of the same layer join it first (their qubits
+      // have seen no later op: a later non-diagonal op would have closed the run)
+      for (size_t bi = 0; bi < blocks.size(); ++bi) {
+        const Block& B = blocks[bi];
+        if (!B.open || ((touch >> B.a) & 1) || ((touch >> B.b) & 1)) continue;
+        bool diag = true;
+        for (int r = 0; r < 4 && diag; ++r)
+          for (int c = 0; c < 4; ++c) if (r != c && !is_zero(B.m[r * 4 + c])) { diag = false; break; }
+        if (diag && B.m[0] == B.m[15] && B.m[5] == B.m[10] && B.m[0] == pending.pe && B.m[5] == pending.po) close_block((int)bi);
+      }
+      flush_zz();
+    }
     int P = -1;
     for (int q = 0; q < n; ++q) if ((touch >> q) & 1) P = std::max(P, last[q]);
     bool ok = P >= 0;
@@ -99,7 +152,7 @@ struct Planner {
       else ok = false;
     }
     // keep one pass well inside the shared-memory program buffer
-    if (ok && pass_bytes(passes[P]) + 8 * op_words(op.kind) + 64 > kBlockBytes / 2) ok = false;
+    if (ok && pass_bytes(passes[P]) + 8 * op_words_max(op) + 64 > kBlockBytes / 2) ok = false;
     if (!ok) {
       P = (int)passes.size();
       passes.push_back(HPass());
@@ -138,9 +191,33 @@ struct Planner {
       return;
     }
     op.target = (int8_t)q;
+    double st[4];
+    int skind = 0;
     if (is_x(m)) op.kind = SVO_X;
+    else if (cond_q < 0 && structured && (skind = classify_u1(m, st)) != 0) { op.kind = (uint8_t)skind; op.off = push(st, 4); }
     else { op.kind = SVO_U1; op.off = push_c(m, 4); }
     emit(op, (1ull << q) | hint, touch);
+  }
+
+  // Unconditional 1-qubit unitary up to a global phase: all entries real (SVO_R1) or real diagonal
+  // with imaginary off-diagonal (SVO_X1) -- half the multiply-adds of the general complex 2x2.
+  bool structured = true;
+  static int classify_u1(const cd* m, double* out) {
+    int big = 0;
+    for (int i = 1; i < 4; ++i) if (std::abs(m[i]) > std::abs(m[big])) big = i;
+    const double a0 = std::arg(m[big]);
+    const double tol = 1e-14;
+    for (int shift = 0; shift < 2; ++shift) {
+      const cd rot = std::polar(1.0, -(a0 - shift * (M_PI / 2)));
+      cd r[4];
+      for (int i = 0; i < 4; ++i) r[i] = m[i] * rot;
+      bool real = true, xt = true;
+      for (int i = 0; i < 4; ++i) real = real && std::abs(r[i].imag()) <= tol;
+      xt = std::abs(r[0].imag()) <= tol && std::abs(r[3].imag()) <= tol && std::abs(r[1].real()) <= tol && std::abs(r[2].real()) <= tol;
+      if (real) { for (int i = 0; i < 4; ++i) out[i] = r[i].real(); return SVO_R1; }
+      if (xt) { out[0] = r[0].real(); out[1] = r[3].real(); out[2] = r[1].imag(); out[3] = r[2].imag(); return SVO_X1; }
+    }
+    return 0;
   }
 
   void flush1(int q, uint64_t hint) {
@@ -167,6 +244,7 @@ struct Planner {
       }
     if (diag) {
       if (is_one(m[0]) && is_one(m[5]) && is_one(m[10]) && is_one(m[15])) return;
+      if (fuse_layers && m[0] == m[15] && m[5] == m[10]) { add_zz(a, b, m[0], m[5]); return; }  // exp(-i t ZZ) type
       HOp op; op.kind = SVO_D2; op.qa = (int8_t)a; op.qb = (int8_t)b;
       const cd ph[4] = {m[0], m[5], m[10], m[15]};
       op.off = push_c(ph, 4);
@@ -265,14 +343,49 @@ struct Planner {
   void end_gates() {
     for (size_t i = 0; i < blocks.size(); ++i) close_block((int)i);
     for (int q = 0; q < n; ++q) flush1(q, 0);
+    flush_zz();
   }
 
   // ---- passes -> sweeps / exchanges --------------------------------------------------------
-  static int op_words(uint8_t k) { return k == SVO_U1 ? 8 : k == SVO_U2 ? 32 : k == SVO_D1 ? 4 : k == SVO_D2 ? 8 : 0; }
-  static int pass_bytes(const HPass& p) {
+  static int op_words(uint8_t k) {
+    return k == SVO_U1 ? 8 : k == SVO_U2 ? 32 : (k == SVO_D1 || k == SVO_R1 || k == SVO_X1) ? 4 : k == SVO_D2 ? 8 : 0;
+  }
+  // upper bound for the block budget: a fused layer's size depends on the physical mapping at emission
+  int op_words_max(const HOp& o) const {
+    if (o.kind != SVO_DZZ) return op_words(o.kind);
+    const int K = (int)zz_layers[o.off].pairs.size();
+    return 2 + K + 2 * (K + 1);
+  }
+  int pass_bytes(const HPass& p) const {
     int b = (int)sizeof(SvPassHdr) + (int)sizeof(SvBlockOp) * (int)p.ops.size();
-    for (const HOp& o : p.ops) b += 8 * op_words(o.kind);
+    for (const HOp& o : p.ops) b += 8 * op_words_max(o) + 8;
     return b;
+  }
+  // parameters of a fused layer under the current logical -> physical map (8-byte words)
+  std::vector<uint64_t> zz_params(const ZzLayer& L) const {
+    std::vector<std::pair<uint32_t, uint32_t>> dm;  // (distance, mask)
+    for (auto& pr : L.pairs) {
+      const uint32_t pa = (uint32_t)phys[pr.first], pb = (uint32_t)phys[pr.second];
+      const uint32_t lo = std::min(pa, pb), d = std::max(pa, pb) - lo;
+      size_t j = 0;
+      while (j < dm.size() && dm[j].first != d) ++j;
+      if (j == dm.size()) dm.push_back({d, 0u});
+      dm[j].second |= 1u << lo;
+    }
+    const uint32_t K = (uint32_t)L.pairs.size();
+    std::vector<uint64_t> w;
+    w.push_back((uint64_t)dm.size() | ((uint64_t)K << 32));
+    for (auto& e : dm) w.push_back((uint64_t)e.first | ((uint64_t)e.second << 32));
+    if (w.size() % 2) w.push_back(0);
+    const double ae = std::arg(L.pe), ao = std::arg(L.po);
+    for (uint32_t k = 0; k <= K; ++k) {
+      const cd t = std::polar(1.0, (double)(K - k) * ae + (double)k * ao);
+      double re = t.real(), im = t.imag();
+      uint64_t a, b;
+      std::memcpy(&a, &re, 8); std::memcpy(&b, &im, 8);
+      w.push_back(a); w.push_back(b);
+    }
+    return w;
   }
 
   void emit_sweep(const std::vector<int>& sel_in, std::vector<char>& in_tile) {
@@ -326,7 +439,9 @@ struct Planner {
     const size_t o_ops = al16(o_pass + sizeof(SvPassHdr) * sel.size());
     size_t o_par = al16(o_ops + sizeof(SvBlockOp) * n_ops);
     size_t bytes = o_par;
-    for (int i : sel) for (const HOp& o : passes[i].ops) bytes += al16(8 * (size_t)op_words(o.kind));
+    for (int i : sel)
+      for (const HOp& o : passes[i].ops)
+        bytes += o.kind == SVO_DZZ ? al16(8 * zz_params(zz_layers[o.off]).size()) : al16(8 * (size_t)op_words(o.kind));
     const size_t blk_begin = out->prog.size();
     out->prog.resize(blk_begin + bytes / 8, 0);
     uint64_t* blk = out->prog.data() + blk_begin;
@@ -348,7 +463,15 @@ struct Planner {
         d.kind = o.kind;
         d.flags = 0;
         d.qa = d.qb = 0;
-        if (o.kind == SVO_U1 || o.kind == SVO_X) {
+        if (o.kind == SVO_DZZ) {
+          const std::vector<uint64_t> w = zz_params(zz_layers[o.off]);
+          ph[k].needs_index = 1;
+          d.off = (uint16_t)(pc / 8);
+          std::memcpy(reinterpret_cast<char*>(blk) + pc, w.data(), 8 * w.size());
+          pc += al16(8 * w.size());
+          continue;
+        }
+        if (o.kind == SVO_U1 || o.kind == SVO_X || o.kind == SVO_R1 || o.kind == SVO_X1) {
           if (o.target == p.qb) d.flags |= SVF_ON_B;
         } else if (o.kind == SVO_U2 || o.kind == SVO_SWAP) {
           if (o.qa != p.qa) d.flags |= SVF_ON_B;  // operands arrive swapped: (qa,qb) = (slot b, slot a)
@@ -414,7 +537,6 @@ struct Planner {
           if (!in_tile[pp]) newpos[need++] = pp;
         }
         int add = pass_bytes(p);
-        for (const HOp& o : p.ops) if (op_words(o.kind) % 2) add += 8;
         if (!ok || nt + need > K || bytes + add > kBlockBytes) { blocked |= p.touch; continue; }
         for (int k = 0; k < need; ++k) { in_tile[newpos[k]] = 1; ++nt; }
         bytes += add;
@@ -548,6 +670,8 @@ void lower_svx_circuit(const bwq_batch& b, int c, const SvxOptions& opt, SvxProg
   Planner P;
   P.out = out;
   P.direct_passes = opt.direct != 0 && std::getenv("BWQ_SVX_NO_DIRECT") == nullptr;  // env: kernel experiments
+  P.fuse_layers = std::getenv("BWQ_SVX_NO_FUSE") == nullptr;
+  P.structured = std::getenv("BWQ_SVX_NO_STRUCT") == nullptr;
   P.n = n; P.g = gl; P.nl = n - gl;
   P.K = std::min(std::min(std::max(opt.tile_bits, 2), kSvTileBitsMax), P.nl);
   P.L = std::max(0, P.K - kSvFreeSlots);

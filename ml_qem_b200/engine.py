@@ -54,12 +54,12 @@ class _Stats(C.Structure):
                 ("n_gates", C.c_int64), ("state_bytes_swept", C.c_int64), ("n_other_launches", C.c_int64),
                 ("lower_ms", C.c_double), ("h2d_ms", C.c_double), ("kernel_ms", C.c_double), ("d2h_ms", C.c_double),
                 ("sweep_kernel_ms", C.c_double), ("h2d_bytes", C.c_int64), ("d2h_bytes", C.c_int64),
-                ("sv_state_bytes_swept", C.c_int64)]
+                ("sv_state_bytes_swept", C.c_int64), ("n_tma_sweep_launches", C.c_int64)]
 
 
 EXPORTS = [
     "bwq_version", "bwq_create", "bwq_destroy", "bwq_last_error", "bwq_set_options", "bwq_set_noise_table",
-    "bwq_dm_run", "bwq_sv_run", "bwq_meas_data_run", "bwq_dm_run_device_out", "bwq_dm_prepare", "bwq_dm_execute", "bwq_dm_execute_device_out", "bwq_sv_prepare", "bwq_sv_execute", "bwq_get_stats", "bwq_sync", "bwq_lower_dm",
+    "bwq_dm_run", "bwq_sv_run", "bwq_meas_data_run", "bwq_dm_run_device_out", "bwq_dm_prepare", "bwq_dm_execute", "bwq_dm_execute_device_out", "bwq_sv_prepare", "bwq_sv_execute", "bwq_get_stats", "bwq_sync", "bwq_lower_dm", "bwq_lower_dm_ex",
     "bwq_program_free", "bwq_program_sizes", "bwq_program_read",
     "bwq_svx_lower", "bwq_svx_free", "bwq_svx_sizes", "bwq_svx_read", "bwq_svx_upload", "bwq_svx_run_segment",
     "bwq_svx_bytes", "bwq_svx_exchange_pull", "bwq_svx_exchange_push",
@@ -95,6 +95,8 @@ def load_library(path=None):
     lib.bwq_sync.argtypes = [C.c_void_p]
     lib.bwq_lower_dm.argtypes = [C.POINTER(_NoiseTable), C.POINTER(_Batch), C.c_int32, C.c_int32, C.c_int32,
                                  C.POINTER(C.c_void_p)]
+    lib.bwq_lower_dm_ex.argtypes = [C.POINTER(_NoiseTable), C.POINTER(_Batch), C.c_int32, C.c_int32, C.c_int32, C.c_int32,
+                                    C.POINTER(C.c_void_p)]
     lib.bwq_program_free.argtypes = [C.c_void_p]
     lib.bwq_program_free.restype = None
     lib.bwq_program_sizes.argtypes = [C.c_void_p, C.c_void_p]
@@ -285,7 +287,8 @@ class Engine:
 
     def set_options(self, tile_qubits=0, low_qubits=0, max_state_bytes=0, chunk_circuits=0, host_threads=0,
                     sv_tile_bits=0, flags=0):
-        """flags: BWQ_OPT_* bits of include/bwq.h (1 = no direct load pass, 2 = no direct store pass)."""
+        """flags: BWQ_OPT_* bits of include/bwq.h (1 = no direct load pass, 2 = no direct store pass,
+        4 / 8 = never / always pipeline bwq_dm_run, 16 = no TMA kernel)."""
         o = _Options(tile_qubits, low_qubits, max_state_bytes, chunk_circuits, host_threads, sv_tile_bits, flags)
         self._check(self._lib.bwq_set_options(self._ctx, C.byref(o)), "bwq_set_options")
 
@@ -404,15 +407,16 @@ class Engine:
         self._check(self._lib.bwq_sync(self._ctx), "bwq_sync")
 
 
-def lower_dm(batch, circuit, noise_model=None, tile_qubits=0, low_qubits=0):
+def lower_dm(batch, circuit, noise_model=None, tile_qubits=0, low_qubits=0, tma=False):
     """Host-only view of the lowering stage (no GPU): returns the sweep program of one circuit as a
-    dict of numpy arrays (see bwq_program_read in include/bwq.h)."""
+    dict of numpy arrays (see bwq_program_read in include/bwq.h).  tma=True: the TMA tile layout
+    the engine uses by default for circuits wider than the tile."""
     lib = load_library()
     st, keep = _noise_struct(noise_model.to_table() if noise_model is not None else None)
     prog = C.c_void_p()
     bs = batch.c_struct()
-    rc = lib.bwq_lower_dm(C.byref(st) if st is not None else None, C.byref(bs), circuit, tile_qubits, low_qubits,
-                          C.byref(prog))
+    rc = lib.bwq_lower_dm_ex(C.byref(st) if st is not None else None, C.byref(bs), circuit, tile_qubits, low_qubits,
+                             1 if tma else 0, C.byref(prog))
     if rc != 0:
         raise EngineError(f"bwq_lower_dm failed ({rc}): {lib.bwq_last_error(None).decode()}")
     try:

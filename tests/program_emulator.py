@@ -86,10 +86,13 @@ def decode_block(prog, sw):
     b = blk.view(np.uint8)
     n_passes = int(blk[:1].view(np.int32)[0])
     passes = []
+    ext_q16 = int(blk[:1].view(np.int32)[1])
     for p in range(n_passes):
         h = b[16 * (1 + p): 16 * (2 + p)]
         ops_q16, n_ops = int(h[:2].view(np.uint16)[0]), int(h[2:4].view(np.uint16)[0])
         sa, sb = int(h[4]), int(h[5])
+        if ext_q16:
+            check_tma_pass(h, b[16 * ext_q16 + 64 * p: 16 * ext_q16 + 64 * (p + 1)].view(np.uint32), sa, sb)
         ops = []
         for o in range(n_ops):
             r = b[16 * (ops_q16 + o): 16 * (ops_q16 + o + 1)]
@@ -97,6 +100,64 @@ def decode_block(prog, sw):
             ops.append((int(r[0]), int(r[1]), int(r[2]), int(offs[0]), int(offs[1]), int(offs[2])))
         passes.append((sa, sb, ops))
     return passes, blk.view(np.float64)
+
+
+def tswz(j):
+    """CU_TENSOR_MAP_SWIZZLE_128B on 8-byte element indices (program.h)."""
+    return j ^ (((j >> 4) & 7) << 1)
+
+
+def tma_pass_layout(sa, sb):
+    """numpy restatement of program.h tma_pass_layout: thread-id bit -> tile index bit, beta bit."""
+    is_target = [(b >> 1) in (sa, sb) for b in range(12)]
+    used = list(is_target)
+    slot0 = sa == 0 or sb == 0
+    beta = 0
+    if not slot0:
+        used[0] = True
+    tbit = [-1] * 7
+    for k in (1, 2, 3):
+        pick = k if not used[k] else (k + 3 if not used[k + 3] else -1)
+        tbit[k - 1] = pick
+        if pick >= 0:
+            used[pick] = True
+    if slot0:
+        beta = max(b for b in range(12) if not used[b])
+        used[beta] = True
+    free = [b for b in range(12) if not used[b]]
+    for k in range(7):
+        if tbit[k] < 0:
+            tbit[k] = free.pop(0)
+    return tbit, beta
+
+
+def check_tma_pass(h, corners, sa, sb):
+    """The host-computed addressing of a TMA-layout pass must (1) cover every tile element exactly
+    once over 128 threads x 2 groups x 16 corners and (2) keep the 16-byte accesses of the fast
+    layout aligned; returns the worst quarter-warp bank-conflict degree of the gathers."""
+    row, gofs = int(h[8]), int(h[12:16].view(np.uint32)[0])
+    lo, hi = min(sa, sb), max(sa, sb)
+    assert row == hi * (hi - 1) // 2 + lo
+    tbit, beta = tma_pass_layout(lo, hi)
+    assert gofs == 8 * tswz(1 << beta)
+    tid = np.arange(128)
+    j = np.zeros(128, dtype=np.int64)
+    for k in range(7):
+        j |= ((tid >> k) & 1) << tbit[k]
+    base = 8 * tswz(j)
+    assert [int(c) for c in corners] == [8 * tswz((i & 3) << (2 * sa) | (i >> 2) << (2 * sb)) for i in range(16)]
+    seen = np.zeros(4096, dtype=np.int32)
+    worst = 1
+    for c in corners:
+        a0 = base ^ int(c)
+        for g in (0, 1):
+            np.add.at(seen, (a0 ^ (gofs if g else 0)) // 8, 1)
+        if gofs == 8:
+            assert not (a0 & 15).any()
+            for q in range(0, 128, 8):  # quarter warp: 8 lanes x 16 B must hit 8 distinct chunks
+                worst = max(worst, 8 // len(set(((a0[q:q + 8] >> 4) & 7).tolist())))
+    assert (seen == 1).all()
+    return worst
 
 
 def run_program(prog):
@@ -112,10 +173,13 @@ def run_program(prog):
     t = state.reshape((4,) * nd)  # axis k <-> digit nd-1-k
     for sw in prog["sweeps"]:
         pos = list(sw[1:9])
-        kq = 1
-        while kq < 7 and kq < nd and pos[kq] > pos[kq - 1]:  # pos[7] is the first-pass descriptor
-            kq += 1
-        pos = pos[:kq]
+        if pos[7] == 0x40:  # TMA tile layout (program.h): slots 2..5 follow the box order in pos[6]
+            pos = pos[:2] + [pos[2 + ((pos[6] >> (2 * k)) & 3)] for k in range(4)]
+        else:
+            kq = 1
+            while kq < 7 and kq < nd and pos[kq] > pos[kq - 1]:  # pos[7] is the first-pass descriptor
+                kq += 1
+            pos = pos[:kq]
         passes, mats = decode_block(prog, sw)
         for sa, sb, ops in passes:
             da, db = pos[sa], pos[sb]

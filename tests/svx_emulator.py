@@ -4,7 +4,7 @@ all-to-all between simulated ranks, Z-type expectation sums -- so the planner (h
 checked against the oracle on a CPU-only box, including the amplitude-sharded case."""
 import numpy as np
 
-SVO_U1, SVO_X, SVO_U2, SVO_SWAP, SVO_D1, SVO_D2 = 1, 2, 3, 4, 5, 6
+SVO_U1, SVO_X, SVO_U2, SVO_SWAP, SVO_D1, SVO_D2, SVO_R1, SVO_X1, SVO_DZZ = 1, 2, 3, 4, 5, 6, 7, 8, 9
 SVF_ON_B, SVF_COND, SVF_COND_VAL = 1, 2, 4
 
 
@@ -51,7 +51,22 @@ def apply_sweeps(info, psi, rank, first, count):
                     cond = ((gi >> op["cond_bit"]) & 1) == want
                 on_b = bool(op["flags"] & SVF_ON_B)
                 k = op["kind"]
-                if k in (SVO_U1, SVO_X):
+                if k == SVO_DZZ:
+                    assert needs_index
+                    hdr = mats[op["off"]:].view(np.uint32)
+                    n_d, kz = int(hdr[0]), int(hdr[1])
+                    w = np.zeros_like(gi)
+                    seen_pairs = 0
+                    for j in range(n_d):
+                        d, M = int(hdr[2 + 2 * j]), int(hdr[3 + 2 * j])
+                        y = (gi ^ (gi >> d)) & M
+                        seen_pairs += bin(M).count("1")
+                        for q in range(32):
+                            w += (y >> q) & 1
+                    assert seen_pairs == kz
+                    tab = _cplx(mats, op["off"] + ((n_d + 2) & ~1), kz + 1)
+                    psi *= tab[w]
+                elif k in (SVO_U1, SVO_X, SVO_R1, SVO_X1):
                     pt = pb if on_b else pa
                     assert not (op["flags"] & SVF_COND) or op["cond_bit"] != pt
                     i0 = idx[((idx >> pt) & 1) == 0]
@@ -60,6 +75,16 @@ def apply_sweeps(info, psi, rank, first, count):
                     a, b = psi[i0].copy(), psi[i1].copy()
                     if k == SVO_X:
                         psi[i0], psi[i1] = b, a
+                    elif k == SVO_R1:
+                        assert not (op["flags"] & SVF_COND)
+                        m = mats[op["off"]:op["off"] + 4]
+                        psi[i0] = m[0] * a + m[1] * b
+                        psi[i1] = m[2] * a + m[3] * b
+                    elif k == SVO_X1:
+                        assert not (op["flags"] & SVF_COND)
+                        m = mats[op["off"]:op["off"] + 4]
+                        psi[i0] = m[0] * a + 1j * m[2] * b
+                        psi[i1] = 1j * m[3] * a + m[1] * b
                     else:
                         u = _cplx(mats, op["off"], 4)
                         psi[i0] = u[0] * a + u[1] * b

@@ -275,3 +275,51 @@ def test_complex_coefficients_return_the_complex_sum(lib):
     res = est.run([c, c], [ob, "-IIIZI"]).result()
     assert np.iscomplexobj(res.values)
     assert abs(res.values[0] - ref) <= TOL and abs(res.values[1] - (-parts[1])) <= TOL
+
+
+def test_tma_kernel_vs_classic_kernel_and_oracle(engine_gpu, monkeypatch):
+    """dm_sweep_tma_kernel (default for circuits wider than the tile) against dm_sweep_kernel
+    (BWQ_OPT_NO_TMA) and the oracle: chain circuits (straight-line pass bodies), random circuits
+    (generic bodies, passes that target slot 0), coherent cx errors (dense ops: the FULL
+    instantiation), several circuits per launch with different tile layouts, gate-free circuit."""
+    from oracle import noise_model as onm
+
+    rng = np.random.default_rng(77)
+    n = 8
+    be = backends.synthetic_chain(n, seed=21)
+    nm, on = noise.from_backend(be), onm.from_backend(be.to_dict())
+    chain = [(i, i + 1) for i in range(n - 1)] + [(i + 1, i) for i in range(n - 1)]
+    circs = [F.tfim_circuit(n, 1 + k % 4, float(rng.uniform(0, 1)), basis="XYZ"[k % 3]) for k in range(6)]
+    circs += [F.brickwork_circuit(n, 1 + k % 3, np.random.default_rng(k), twirl_rng=rng) for k in range(5)]
+    circs += [F.random_basis_circuit(n, 120, rng, chain) for _ in range(5)]
+    circs += [F.tfim_circuit(7, 2, 0.3, num_physical=n), Circuit(n)]
+    obs = [[[(l, float(rng.normal()))] for l in _labels(rng, n, 5)] for _ in circs]
+    batch = engine.encode_batch(circs, obs)
+    ref = np.concatenate([helpers.oracle_dm_values(c, o, on) for c, o in zip(circs, obs)])
+    engine_gpu.set_options()
+    v_tma, st = engine_gpu.run_dm(batch, noise=nm)
+    s_tma = engine_gpu.stats()
+    assert not st.any() and s_tma["n_tma_sweep_launches"] > 0
+    engine_gpu.set_options(flags=16)
+    v_cls, st = engine_gpu.run_dm(batch, noise=nm)
+    assert not st.any() and engine_gpu.stats()["n_tma_sweep_launches"] == 0
+    engine_gpu.set_options()
+    assert np.max(np.abs(v_tma - ref)) <= TOL and np.max(np.abs(v_cls - ref)) <= TOL
+    assert np.max(np.abs(v_tma - v_cls)) <= 1e-13
+    # several tensor-map windows (forced: normally 2^31 elements per map) and prepared/resident reruns
+    monkeypatch.setenv("BWQ_TMA_WINDOW_LOG2", "1")
+    st = engine_gpu.prepare_dm(batch)
+    assert not st.any()
+    assert np.array_equal(engine_gpu.execute_dm(), v_tma) and np.array_equal(engine_gpu.execute_dm(), v_tma)
+    monkeypatch.delenv("BWQ_TMA_WINDOW_LOG2")
+    # dense two-qubit ops (coherent cx error, non-basis gates) in the TMA layout: FULL instantiation
+    lima7 = backends.synthetic_chain(7, seed=3)
+    nm2 = noise.modify_and_add_noise_to_model(lima7, theta=np.pi / 8)
+    on2 = onm.modify_and_add_noise_to_model(lima7.to_dict(), theta=np.pi / 8)
+    c = F.tfim_circuit(7, 2, 0.55, basis="Y")
+    c.rzz(0.4, 2, 3); c.ecr(5, 6); c.h(0); c.swap(0, 1)
+    ob = F.tfim_observables(list(range(7)), 7)
+    ref2 = helpers.oracle_dm_values(c, ob, on2)
+    v2, st = engine_gpu.run_dm(engine.encode_batch([c], [ob]), noise=nm2)
+    assert not st.any() and engine_gpu.stats()["n_tma_sweep_launches"] > 0
+    assert np.max(np.abs(v2 - ref2)) <= TOL

@@ -162,3 +162,64 @@ def test_direct_pass_flags_are_consistent(lib):
         if len(passes) > 1:
             assert not (flags[0] & 2) and not (flags[-1] & 1)
     assert n_first > 0 and n_last > 0
+
+
+def test_tma_tile_layout_programs(lib):
+    """Circuits wider than the 6-digit tile in the TMA tile layout (what the engine runs by default on
+    the GPU): same values as the oracle through the emulator; every pass's host-computed addressing
+    covers the tile exactly once (checked inside the emulator's decoder); the common op lists get a
+    straight-line signature; the box order keeps the chain circuits free of bank conflicts."""
+    import program_emulator as pe
+    from oracle import noise_model as onm
+
+    rng = np.random.default_rng(12)
+    n = 8
+    be = backends.synthetic_chain(n, seed=5)
+    nm, on = noise.from_backend(be), onm.from_backend(be.to_dict())
+    cases = [F.tfim_circuit(n, 3, 0.4, basis="Y"), F.brickwork_circuit(n, 2, rng, twirl_rng=np.random.default_rng(2)),
+             F.random_basis_circuit(n, 150, rng, [(i, i + 1) for i in range(n - 1)] + [(i + 1, i) for i in range(n - 1)])]
+    sig_hist = {}
+    for c in cases:
+        obs = [[(l, 1.0)] for l in _labels(rng, n, 6)]
+        fb = engine.encode_batch([c], [obs])
+        ref = helpers.oracle_dm_values(c, obs, on)
+        prog = engine.lower_dm(fb, 0, nm, tma=True)
+        assert prog["status"] == 0 and all(sw[8] == 0x40 for sw in prog["sweeps"])
+        got = expvals(prog, run_program(prog), [1] * len(obs))
+        assert np.max(np.abs(got - ref)) <= TOL
+        # same state as the classic layout (the direct passes of the classic planner reorder
+        # commuting passes, so the rounding differs in the last bits)
+        classic = engine.lower_dm(fb, 0, nm)
+        assert np.max(np.abs(run_program(classic) - run_program(prog))) <= 1e-14
+        for sw in prog["sweeps"]:
+            blk = prog["prog"][2 * int(sw[0]): 2 * (int(sw[0]) + int(sw[9]))]
+            b = blk.view(np.uint8)
+            for p in range(int(blk[:1].view(np.int32)[0])):
+                h = b[16 * (1 + p): 16 * (2 + p)]
+                sig_hist[int(h[7])] = sig_hist.get(int(h[7]), 0) + 1
+                ext = int(blk[:1].view(np.int32)[1])
+                worst = pe.check_tma_pass(h, b[16 * ext + 64 * p: 16 * ext + 64 * (p + 1)].view(np.uint32), int(h[4]), int(h[5]))
+                if c is not cases[2]:
+                    assert worst == 1, (int(h[4]), int(h[5]))  # chain circuits: conflict free by box order
+    assert sum(v for k, v in sig_hist.items() if k != 0) > sum(sig_hist.values()) // 2
+    # narrow circuits (one tile) keep the classic layout
+    c6 = F.tfim_circuit(6, 2, 0.3)
+    p6 = engine.lower_dm(engine.encode_batch([c6], [F.single_z_observables(list(range(6)), 6)]), 0, nm, tma=True)
+    assert all(sw[8] != 0x40 for sw in p6["sweeps"])
+
+
+def test_tma_pass_layout_is_conflict_free_except_three_pairs(lib):
+    import program_emulator as pe
+    for hi in range(1, 6):
+        for lo in range(hi):
+            tbit, beta = pe.tma_pass_layout(lo, hi)
+            assert sorted(tbit + [beta] + [2 * lo, 2 * lo + 1, 2 * hi, 2 * hi + 1]) == list(range(12))
+            if lo == 0:
+                continue
+            tid = np.arange(128)
+            j = np.zeros(128, dtype=np.int64)
+            for k in range(7):
+                j |= ((tid >> k) & 1) << tbit[k]
+            a = 8 * pe.tswz(j)
+            degree = max(8 // len(set(((a[q:q + 8] >> 4) & 7).tolist())) for q in range(0, 128, 8))
+            assert degree == (2 if (lo, hi) in ((1, 2), (1, 3)) else 1), (lo, hi, degree)

@@ -15,7 +15,7 @@ kq = int(sys.argv[3]) if len(sys.argv) > 3 else 0
 low = int(sys.argv[4]) if len(sys.argv) > 4 else 0
 reps = int(sys.argv[5]) if len(sys.argv) > 5 else 2
 eng = engine.Engine(0)
-eng.set_options(tile_qubits=kq, low_qubits=low)
+eng.set_options(tile_qubits=kq, low_qubits=low, flags=int(os.environ.get("BWQ_FLAGS", "0"), 0))
 if kind == "tfim":
     be = backends.synthetic_chain(n, seed=n)
     circs, obs = F.config_tfim_dm(n=n, n_circuits=2, max_steps=3)
