@@ -45,15 +45,18 @@ def build_workload(name, rank, scale=1.0):
     rank owns its own batch of the same shape)."""
     from ml_qem_b200 import backends, families as F
 
+    extra = {}  # base circuits + variants descriptor of the workloads that are variants of base circuits
     if name == "brick10_guadalupe_twirl":
         n_base = max(1, int(round(20 * scale)))
-        circs, _, obs = F.config_brick10_twirl(n_base=n_base, n_twirls=100, seed=1 + 1000 * rank)
+        circs, base, obs = F.config_brick10_twirl(n_base=n_base, n_twirls=100, seed=1 + 1000 * rank)
+        extra = {"base": base, "variants": {"twirls": 100, "seed": 1 + 1000 * rank}}
         be = backends.synthetic_chain(16, seed=2, name="synthetic_guadalupe_like_16q")
         desc = {"workload": name, "n_qubits": 10, "register": 16, "base_circuits": n_base, "twirls": 100,
                 "circuits_per_rank": len(circs), "observables_per_circuit": len(obs), "trotter_steps": "1..5"}
     elif name == "tfim4_lima_zne":
         n_base = max(1, int(round(2000 * scale)))
-        circs, _, obs = F.config_tfim4_lima_zne(n_base=n_base, seed=1000 * rank)
+        circs, base, obs = F.config_tfim4_lima_zne(n_base=n_base, seed=1000 * rank)
+        extra = {"base": base, "variants": {"folds": (1, 3, 5)}}
         be = backends.fake_lima()
         desc = {"workload": name, "n_qubits": 4, "register": 5, "base_circuits": n_base, "zne_factors": [1, 3, 5],
                 "circuits_per_rank": len(circs), "observables_per_circuit": len(obs)}
@@ -76,7 +79,7 @@ def build_workload(name, rank, scale=1.0):
         return {"circuits": circs, "observables": obs_each, "backend": be, "desc": desc}
     else:
         raise SystemExit(f"unknown workload {name!r}")
-    return {"circuits": circs, "observables": [obs] * len(circs), "backend": be, "desc": desc}
+    return dict({"circuits": circs, "observables": [obs] * len(circs), "backend": be, "desc": desc}, **extra)
 
 
 # ----------------------------------------------------------------------------------------------
@@ -438,6 +441,37 @@ def bench_dm(ctx, name, steps, warmup, scale=1.0, cpu_budget=15.0, cpu_first=Non
     e2e_value = total_circ / e2e_s
     assert np.array_equal(noisy_e, noisy) and np.array_equal(ideal_e, ideal), "resident and host-buffer paths differ"
 
+    # ---- the same work through the reference-facing API from BASE circuits: B200Estimator.run(circuits,
+    # observables, variants=...) -- Python normalisation, encoding of the base circuits, variant
+    # generation (folds / twirls) inside the library, kernels, values back; plus the ideal estimator
+    est_res = None
+    if wl.get("base") is not None:
+        from ml_qem_b200.engine import Variants
+        from ml_qem_b200.estimator import B200Estimator
+
+        V = Variants(**wl["variants"])
+        base_c, obs0 = wl["base"], wl["observables"][0]
+        pairs_c = [c for c in base_c for _ in obs0]
+        pairs_o = [o for _ in base_c for o in obs0]
+        est_n, est_i = B200Estimator(backend=wl["backend"], engine=eng), B200Estimator(engine=eng)
+        for _ in range(2):
+            rn = est_n.run(pairs_c, pairs_o, variants=V).result()
+            ri = est_i.run(pairs_c, pairs_o).result()
+        ctx.barrier()
+        t0 = time.perf_counter()
+        for _ in range(steps):
+            rn = est_n.run(pairs_c, pairs_o, variants=V).result()
+            ri = est_i.run(pairs_c, pairs_o).result()
+        ctx.barrier()
+        est_s = ctx.max(time.perf_counter() - t0)
+        n_var_circ = ctx.sum(float(len(base_c) * V.n_variants)) * steps
+        est_res = {"value": n_var_circ / est_s, "unit": UNIT, "ms_per_step": 1e3 * est_s / steps,
+                   "call": "B200Estimator(backend).run(base circuits x observables, variants=Variants(%s)) + B200Estimator().run(...) "
+                           "(ideal); variants generated inside the library (bwq_dm_run_variants)" % wl["variants"],
+                   "base_circuits": len(base_c), "variants_per_circuit": V.n_variants, "pairs_per_call": len(pairs_c),
+                   "values_head": [float(x) for x in rn.values[:2]], "ideal_head": [float(x) for x in ri.values[:2]]}
+        eng.set_noise(noise.from_backend(wl["backend"]))
+
     # ---- final gather of the labels (the only collective of the density-matrix path)
     if dist is not None:
         mine = torch.from_numpy(np.stack([noisy, ideal])).cuda()
@@ -498,6 +532,8 @@ def bench_dm(ctx, name, steps, warmup, scale=1.0, cpu_budget=15.0, cpu_first=Non
         "cpu_baseline": cpu,
         "max_abs_diff_vs_cpu": cpu["max_abs_diff_vs_gpu"] if cpu else None,
     }
+    if est_res is not None:
+        out["e2e_estimator"] = est_res
     if clk is not None:
         out["clocks"] = clk
     return out
@@ -525,7 +561,7 @@ def sub_summary(d):
            "config": d["config"]}
     if d.get("cpu_baseline"):
         out["cpu_baseline"] = {k: d["cpu_baseline"][k] for k in ("value", "cores", "kind", "sample")}
-    for k in ("exchange", "max_abs_diff_vs_1rank"):
+    for k in ("exchange", "max_abs_diff_vs_1rank", "e2e_estimator"):
         if k in d:
             out[k] = d[k]
     return out
@@ -623,7 +659,7 @@ def main():
         "gpu_launches": main_res["gpu_launches"], "roofline": main_res["roofline"], "cpu_baseline": main_res.get("cpu_baseline"),
         "clocks": main_res.get("clocks"),
     }
-    for k in ("exchange", "max_abs_diff_vs_1rank", "last_values_head"):
+    for k in ("exchange", "max_abs_diff_vs_1rank", "last_values_head", "e2e_estimator"):
         if k in main_res:
             line[k] = main_res[k]
     if subs:

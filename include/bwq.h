@@ -82,6 +82,18 @@ typedef struct {
   const double* term_coeff;   /* real coefficients                                           */
 } bwq_batch;
 
+/* Variants of every circuit of a batch, generated INSIDE the library (K0) from the base gate
+ * stream: ZNE local folding of the 2-qubit gates and Pauli twirling of the cx gates -- what the
+ * reference builds as new Python circuits per variant (docs/tutorials/zne_parallel.py:168-189,
+ * docs/tutorials/derek_files/phase_diagram.ipynb:776,960).  Base circuit c yields
+ * n_variants = max(1, n_folds) * max(1, n_twirls) circuits, variant index fold * n_twirls + twirl. */
+typedef struct {
+  int32_t n_folds;          /* 0 = no folding (factor 1)                                       */
+  const int32_t* folds;     /* [n_folds] odd noise factors, e.g. {1, 3, 5}                     */
+  int32_t n_twirls;         /* 0 = no twirling; else twirled instances per (circuit, fold)     */
+  uint64_t seed;            /* the Pauli pairs are a pure function of (seed, circuit, twirl, cx index) */
+} bwq_variants;
+
 /* Noise table: one error per (opcode, ordered physical qubits), the lookup Aer's
  * NoiseModel.from_backend uses (reached from blackwater/data/utils.py:427).  Errors are given in
  * the real Pauli-transfer-matrix form R[i][j] = Tr(P_i E(P_j)) / 2^k, P in {I,X,Y,Z}, index
@@ -123,6 +135,8 @@ typedef struct {
 #define BWQ_OPT_PERSIST 32       /* density matrix: after the first sweep use the persistent double-buffered
                                    dm_sweep_tma_persistent_kernel (two resident CTAs per SM, producer warp) instead of one
                                    CTA per tile; measured slower (8 compute warps per SM), kept for A/B */
+#define BWQ_OPT_TMA_DIRECT_STORE 64 /* TMA layout: the last pass of a sweep stores its register groups to global memory
+                                   with 16-byte stores instead of scatter + TMA store; measured slower (0.635 vs 0.676), A/B */
 #define BWQ_OPT_NO_TMA 16       /* density matrix: keep circuits wider than the tile on dm_sweep_kernel (LDG/STG tile
                                    movement) instead of dm_sweep_tma_kernel (TMA tensor-map tiles); A/B and parity tests */
 
@@ -183,6 +197,20 @@ int bwq_dm_run_device_out(bwq_ctx* ctx, const bwq_batch* batch, double* d_out_va
  * density-matrix side. */
 int bwq_meas_data_run(bwq_ctx* ctx, const bwq_batch* batch, double* out_ideal, double* out_noisy,
                       int32_t* status_ideal, int32_t* status_noisy);
+/* (ideal, noisy) values of every VARIANT of every circuit: the noisy side (density matrix) runs all
+ * n_circuits * n_variants circuits, the ideal side (statevector) the base circuits only -- folds
+ * and twirls leave the ideal circuit unchanged.  out_noisy[(observable of circuit c, variant v)] is
+ * laid out circuit-major, then variant, then the circuit's observables; out_ideal as bwq_sv_run.
+ * status_noisy[n_circuits] (per base circuit: first failing variant), status_ideal[n_circuits]. */
+int bwq_meas_data_run_variants(bwq_ctx* ctx, const bwq_batch* batch, const bwq_variants* variants, double* out_ideal,
+                               double* out_noisy, int32_t* status_ideal, int32_t* status_noisy);
+/* Noisy side alone: out_vals / out_status cover the n_circuits * n_variants expanded circuits
+ * (circuit-major, then variant; out_status[n_circuits * n_variants]). */
+int bwq_dm_run_variants(bwq_ctx* ctx, const bwq_batch* batch, const bwq_variants* variants, double* out_vals, int32_t* out_status);
+/* Host-only view of the expansion (no GPU): sizes[0..3] = {n circuits, n ops, n params, variants per
+ * circuit}; a second call with buffers copies op_offsets[n+1], ops[n_ops], params[n_params] out. */
+int bwq_expand_variants(const bwq_batch* batch, const bwq_variants* variants, int64_t sizes[4], int64_t* op_offsets,
+                        bwq_op* ops, double* params);
 int bwq_get_stats(const bwq_ctx* ctx, bwq_stats* out);
 int bwq_sync(bwq_ctx* ctx);
 
@@ -191,7 +219,7 @@ typedef struct bwq_program bwq_program;
 /* Lowers batch circuit `circuit` to its sweep program.  tile_qubits/low_qubits as in options. */
 int bwq_lower_dm(const bwq_noise_table* table, const bwq_batch* batch, int32_t circuit,
                  int32_t tile_qubits, int32_t low_qubits, bwq_program** out);
-/* Same with planner flags: bit 0 = emit the TMA tile layout (what bwq_dm_run does by default for
+/* Same with planner flags: bit 1 = direct last-pass stores in the TMA layout; bit 0 = emit the TMA tile layout (what bwq_dm_run does by default for
  * circuits wider than the tile; see ml_qem_b200/csrc/program.h). */
 int bwq_lower_dm_ex(const bwq_noise_table* table, const bwq_batch* batch, int32_t circuit,
                     int32_t tile_qubits, int32_t low_qubits, int32_t flags, bwq_program** out);

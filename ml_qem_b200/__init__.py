@@ -18,7 +18,7 @@ def __getattr__(name):  # lazy: the estimator pulls in ctypes + the CUDA library
         from . import estimator
 
         return getattr(estimator, name)
-    if name in ("Engine", "EngineError", "FlatBatch", "encode_batch"):
+    if name in ("Engine", "EngineError", "FlatBatch", "encode_batch", "Variants"):
         from . import engine
 
         return getattr(engine, name)

@@ -162,6 +162,35 @@ class Circuit:
             raise ValueError("mid-circuit measurement is not supported by the exact estimator")
         return ops
 
+    def flat(self):
+        """The gate stream as numpy arrays (opcode u16, q0 u8, q1 u8, parameters per op i32,
+        parameters f64), cached until the op list changes -- what encode_batch concatenates, so a
+        circuit object is walked gate by gate in Python once, not once per run."""
+        ops = self.ops
+        key = (len(ops), id(ops[-1]) if ops else 0)
+        cache = self.__dict__.get("_flat")
+        if cache is not None and cache[0] == key:
+            return cache[1]
+        gate_ops = self.gate_ops()
+        n = len(gate_ops)
+        opc = np.empty(n, dtype=np.uint16)
+        q0 = np.empty(n, dtype=np.uint8)
+        q1 = np.zeros(n, dtype=np.uint8)
+        npar = np.zeros(n, dtype=np.int32)
+        params = []
+        for i, (name, qubits, pr) in enumerate(gate_ops):
+            opc[i] = OPCODES[name]
+            q0[i] = qubits[0]
+            if len(qubits) > 1:
+                q1[i] = qubits[1]
+            k = NUM_PARAMS.get(name, 0)
+            if k:
+                npar[i] = k
+                params.extend(float(p) for p in pr)
+        out = (opc, q0, q1, npar, np.asarray(params, dtype=np.float64))
+        self.__dict__["_flat"] = (key, out)
+        return out
+
     def size(self):
         return len(self.ops)
 

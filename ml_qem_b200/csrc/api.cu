@@ -392,6 +392,7 @@ static int dm_lower_impl(bwq_ctx* ctx, bwq_ctx::DmSlot& sl, const bwq_batch* b, 
   lo.low_qubits = ctx->opt.low_qubits > 0 ? ctx->opt.low_qubits : 2;
   lo.direct = (ctx->opt.flags & BWQ_OPT_NO_DIRECT_LOAD ? 0 : kPassLoadDirect) | (ctx->opt.flags & BWQ_OPT_NO_DIRECT_STORE ? 0 : kPassStoreDirect);
   lo.tma = ctx->encode_tiled != nullptr && !(ctx->opt.flags & BWQ_OPT_NO_TMA);
+  lo.tma_direct_store = (ctx->opt.flags & BWQ_OPT_TMA_DIRECT_STORE) != 0;
   P.tile_qubits = lo.tile_qubits;
   std::vector<CircuitProgram> progs(N);  // progs[c] <-> batch circuit c0 + c
   parallel_for(N, host_threads(ctx), [&](int c) { lower_dm_circuit(ctx->noise, *b, c0 + c, lo, &progs[c]); });
@@ -1302,10 +1303,8 @@ extern "C" int bwq_sv_run(bwq_ctx* ctx, const bwq_batch* b, double* out_vals, in
   return rc ? rc : sv_execute_impl(ctx, out_vals);
 }
 
-extern "C" int bwq_meas_data_run(bwq_ctx* ctx, const bwq_batch* b, double* out_ideal, double* out_noisy,
-                                 int32_t* status_ideal, int32_t* status_noisy) {
-  if (!ctx) return BWQ_ERR_ARG;
-  if (!out_ideal || !out_noisy || !status_ideal || !status_noisy) return fail(ctx, BWQ_ERR_ARG, "null out/status");
+// statevector side of the (ideal, noisy) calls: a companion context with its own stream and buffers
+static int ensure_companion(bwq_ctx* ctx) {
   if (!ctx->companion) {
     int rc = bwq_create(ctx->device, &ctx->companion);
     if (rc) return fail(ctx, rc, "companion context: %s", bwq_last_error(nullptr));
@@ -1318,6 +1317,15 @@ extern "C" int bwq_meas_data_run(bwq_ctx* ctx, const bwq_batch* b, double* out_i
     cudaStreamDestroy(ctx->companion->stream);
     ctx->companion->stream = hp;
   }
+  return BWQ_OK;
+}
+
+extern "C" int bwq_meas_data_run(bwq_ctx* ctx, const bwq_batch* b, double* out_ideal, double* out_noisy,
+                                 int32_t* status_ideal, int32_t* status_noisy) {
+  if (!ctx) return BWQ_ERR_ARG;
+  if (!out_ideal || !out_noisy || !status_ideal || !status_noisy) return fail(ctx, BWQ_ERR_ARG, "null out/status");
+  int rc_c = ensure_companion(ctx);
+  if (rc_c) return rc_c;
   // both lowering stages run at once: split the host threads (statevector lowering is the cheaper
   // one) instead of oversubscribing the cores, which shows up as multi-millisecond join tails
   const int all_threads = host_threads(ctx), saved_threads = ctx->opt.host_threads;
@@ -1331,6 +1339,74 @@ extern "C" int bwq_meas_data_run(bwq_ctx* ctx, const bwq_batch* b, double* out_i
   ctx->opt.host_threads = saved_threads;
   if (rc_dm) return rc_dm;
   if (rc_sv) return fail(ctx, rc_sv, "statevector side: %s", bwq_last_error(ctx->companion));
+  return BWQ_OK;
+}
+
+// variants: expand on the host (K0), noisy side on every variant, ideal side on the base circuits
+extern "C" int bwq_meas_data_run_variants(bwq_ctx* ctx, const bwq_batch* b, const bwq_variants* v, double* out_ideal, double* out_noisy,
+                                          int32_t* status_ideal, int32_t* status_noisy) {
+  if (!ctx) return BWQ_ERR_ARG;
+  if (!b || !v || !out_ideal || !out_noisy || !status_ideal || !status_noisy) return fail(ctx, BWQ_ERR_ARG, "null argument");
+  int rc = check_batch(ctx, b, out_ideal, status_ideal);
+  if (rc) return rc;
+  if ((rc = ensure_companion(ctx))) return rc;
+  const double t0 = now_ms();
+  ExpandedBatch X;
+  if ((rc = expand_variants(*b, *v, &X))) return fail(ctx, rc, "bad variants descriptor (folds must be odd positive factors)");
+  const double expand_ms = now_ms() - t0;
+  std::vector<int32_t> st_var((size_t)X.view.n_circuits);
+  const int all_threads = host_threads(ctx), saved_threads = ctx->opt.host_threads;
+  ctx->companion->opt = ctx->opt;
+  ctx->companion->opt.host_threads = std::max(1, all_threads / 4);
+  ctx->opt.host_threads = std::max(1, all_threads - ctx->companion->opt.host_threads);
+  int rc_sv = BWQ_OK;
+  std::thread ideal([&] { rc_sv = bwq_sv_run(ctx->companion, b, out_ideal, status_ideal); });
+  const int rc_dm = bwq_dm_run(ctx, &X.view, out_noisy, st_var.data());
+  ideal.join();
+  ctx->opt.host_threads = saved_threads;
+  if (rc_dm) return rc_dm;
+  if (rc_sv) return fail(ctx, rc_sv, "statevector side: %s", bwq_last_error(ctx->companion));
+  for (int c = 0; c < b->n_circuits; ++c) {
+    status_noisy[c] = X.status[c];
+    for (int k = 0; k < X.n_variants && !status_noisy[c]; ++k) status_noisy[c] = st_var[(size_t)c * X.n_variants + k];
+    if (X.status[c])  // a gate without an inverse rule: the folded variants are not what was asked for
+      for (int64_t o = X.view.obs_offsets[(size_t)c * X.n_variants]; o < X.view.obs_offsets[(size_t)(c + 1) * X.n_variants]; ++o) out_noisy[o] = std::nan("");
+  }
+  ctx->stats.lower_ms += expand_ms;
+  return BWQ_OK;
+}
+
+extern "C" int bwq_dm_run_variants(bwq_ctx* ctx, const bwq_batch* b, const bwq_variants* v, double* out_vals, int32_t* out_status) {
+  if (!ctx) return BWQ_ERR_ARG;
+  if (!b || !v || !out_vals || !out_status) return fail(ctx, BWQ_ERR_ARG, "null argument");
+  int rc = check_batch(ctx, b, out_vals, out_status);
+  if (rc) return rc;
+  const double t0 = now_ms();
+  ExpandedBatch X;
+  if ((rc = expand_variants(*b, *v, &X))) return fail(ctx, rc, "bad variants descriptor (folds must be odd positive factors)");
+  const double expand_ms = now_ms() - t0;
+  if ((rc = bwq_dm_run(ctx, &X.view, out_vals, out_status))) return rc;
+  for (int c = 0; c < b->n_circuits; ++c)
+    if (X.status[c])
+      for (int k = 0; k < X.n_variants; ++k) {
+        const size_t vi = (size_t)c * X.n_variants + k;
+        out_status[vi] = X.status[c];
+        for (int64_t o = X.view.obs_offsets[vi]; o < X.view.obs_offsets[vi + 1]; ++o) out_vals[o] = std::nan("");
+      }
+  ctx->stats.lower_ms += expand_ms;
+  return BWQ_OK;
+}
+
+extern "C" int bwq_expand_variants(const bwq_batch* b, const bwq_variants* v, int64_t sizes[4], int64_t* op_offsets, bwq_op* ops,
+                                   double* params) {
+  if (!b || !v || !sizes) return BWQ_ERR_ARG;
+  ExpandedBatch X;
+  int rc = expand_variants(*b, *v, &X);
+  if (rc) return rc;
+  sizes[0] = X.view.n_circuits; sizes[1] = (int64_t)X.ops.size(); sizes[2] = (int64_t)X.params.size(); sizes[3] = X.n_variants;
+  if (op_offsets) std::memcpy(op_offsets, X.op_offsets.data(), sizeof(int64_t) * X.op_offsets.size());
+  if (ops && !X.ops.empty()) std::memcpy(ops, X.ops.data(), sizeof(bwq_op) * X.ops.size());
+  if (params && !X.params.empty()) std::memcpy(params, X.params.data(), sizeof(double) * X.params.size());
   return BWQ_OK;
 }
 
@@ -1354,6 +1430,7 @@ extern "C" int bwq_lower_dm_ex(const bwq_noise_table* table, const bwq_batch* ba
   lo.tile_qubits = tile_qubits ? tile_qubits : 6;
   lo.low_qubits = low_qubits < 0 ? 0 : (low_qubits ? low_qubits : 2);
   lo.tma = (flags & 1) != 0;
+  lo.tma_direct_store = (flags & 2) != 0;
   bwq_program* p = new bwq_program();
   lower_dm_circuit(nt, *batch, circuit, lo, &p->p);
   *out = p;

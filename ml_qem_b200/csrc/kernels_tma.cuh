@@ -86,9 +86,33 @@ __device__ __forceinline__ void macro_op(double (&v)[2][16], const double* __res
 
 // Straight-line pass body: 16-byte gathers (corner i of both register groups), the macro-ops of
 // the signature, 16-byte scatters.  base = thread offset ^ nothing else; cor = the pass's 16 corner offsets.
+// Destination of a pass's register groups: the shared-memory tile, or -- last pass of a sweep whose
+// targets are not slots 0/1 -- global memory directly: gdst = the thread's first element in the state,
+// gcor = the 16 corner offsets (elements); a quarter warp then writes one full 128-byte line per store
+// and the tile skips its last two shared-memory traversals (scatter + TMA read).
+struct PassDst {
+  double* gdst;        // nullptr: scatter to the tile
+  const uint4* gcor;
+};
+__device__ __forceinline__ void scatter_groups(const double (&v)[2][16], char* __restrict__ tile_b, const uint32_t (&off)[16], const PassDst& dst) {
+  if (dst.gdst != nullptr) {
+#pragma unroll
+    for (int q = 0; q < 4; ++q) {
+      const uint4 c = dst.gcor[q];
+      __stcg(reinterpret_cast<double2*>(dst.gdst + c.x), make_double2(v[0][4 * q], v[1][4 * q]));
+      __stcg(reinterpret_cast<double2*>(dst.gdst + c.y), make_double2(v[0][4 * q + 1], v[1][4 * q + 1]));
+      __stcg(reinterpret_cast<double2*>(dst.gdst + c.z), make_double2(v[0][4 * q + 2], v[1][4 * q + 2]));
+      __stcg(reinterpret_cast<double2*>(dst.gdst + c.w), make_double2(v[0][4 * q + 3], v[1][4 * q + 3]));
+    }
+  } else {
+#pragma unroll
+    for (int i = 0; i < 16; ++i) *reinterpret_cast<double2*>(tile_b + off[i]) = make_double2(v[0][i], v[1][i]);
+  }
+}
+
 template <int PA1, int PB1, int TQ1, bool TWO, int PA2, int PB2, int TQ2>
 __device__ __forceinline__ void pass_fast(char* __restrict__ tile_b, const double* __restrict__ pbuf, const uint32_t base,
-                                          const uint4* __restrict__ cor, const int ops_q16) {
+                                          const uint4* __restrict__ cor, const int ops_q16, const PassDst& dst) {
   double v[2][16];
   uint32_t off[16];
 #pragma unroll
@@ -105,15 +129,15 @@ __device__ __forceinline__ void pass_fast(char* __restrict__ tile_b, const doubl
   const uint4* ops = reinterpret_cast<const uint4*>(pbuf) + ops_q16;
   macro_op<PA1, PB1, TQ1>(v, pbuf, ops[0]);
   if constexpr (TWO) macro_op<PA2, PB2, TQ2>(v, pbuf, ops[1]);
-#pragma unroll
-  for (int i = 0; i < 16; ++i) *reinterpret_cast<double2*>(tile_b + off[i]) = make_double2(v[0][i], v[1][i]);
+  scatter_groups(v, tile_b, off, dst);
 }
 
 // Any op list.  gofs == 8: the second group is the other half of every 16-byte access; otherwise
 // (slot 0 is a target) the groups are separate 8-byte gathers at base and base ^ gofs.
 template <bool FULL>
 __device__ __forceinline__ void pass_generic(char* __restrict__ tile_b, const double* __restrict__ pbuf, const uint32_t base,
-                                             const uint4* __restrict__ cor, const int ops_q16, const int n_ops, const uint32_t gofs) {
+                                             const uint4* __restrict__ cor, const int ops_q16, const int n_ops, const uint32_t gofs,
+                                             const PassDst& dst) {
   double v[2][16];
   uint32_t off[16];
 #pragma unroll
@@ -138,8 +162,7 @@ __device__ __forceinline__ void pass_generic(char* __restrict__ tile_b, const do
   }
   run_ops<FULL, 2>(v, pbuf, ops_q16, n_ops);
   if (wide) {
-#pragma unroll
-    for (int i = 0; i < 16; ++i) *reinterpret_cast<double2*>(tile_b + off[i]) = make_double2(v[0][i], v[1][i]);
+    scatter_groups(v, tile_b, off, dst);  // direct stores are only requested for wide passes
   } else {
 #pragma unroll
     for (int i = 0; i < 16; ++i) {
@@ -161,11 +184,13 @@ template <bool NAMED> __device__ __forceinline__ void compute_sync() {
 }
 
 // all register passes of the sweep block in pbuf on the tile in tile_b
+// returns true when the last pass stored the tile to global memory itself (gtile = the tile's first element)
 template <bool FULL, bool NAMED>
-__device__ __forceinline__ void run_tma_passes(char* __restrict__ tile_b, const double* __restrict__ pbuf,
-                                               const uint32_t* __restrict__ a_table, const int tid) {
+__device__ __forceinline__ bool run_tma_passes(char* __restrict__ tile_b, const double* __restrict__ pbuf,
+                                               const uint32_t* __restrict__ a_table, const int tid, double* __restrict__ gtile) {
   constexpr int T = kTmaThreads;
   const int n_passes = reinterpret_cast<const int*>(pbuf)[0];
+  bool stored = false;
   const uint4* const ext = reinterpret_cast<const uint4*>(pbuf) + reinterpret_cast<const int*>(pbuf)[1];
   uint4 hraw = reinterpret_cast<const uint4*>(pbuf)[1];
   uint32_t a_next = __ldg(a_table + (hraw.z & 0xffu) * T + tid);
@@ -180,18 +205,32 @@ __device__ __forceinline__ void run_tma_passes(char* __restrict__ tile_b, const 
     const int ops_q16 = h.x & 0xffffu, n_ops = h.x >> 16;
     const uint32_t sig = h.y >> 24;
     const uint4* cor = ext + 4 * p;
+    PassDst dst{nullptr, ext + 4 * n_passes};
+    if ((h.y >> 16) & kPassStoreDirect) {
+      // the thread's first element in the state: its tile-local index (tswz is an involution) with
+      // every digit moved to the position of its slot
+      const uint32_t j = tswz(a_thr >> 3);
+      const uint2 sp = reinterpret_cast<const uint2*>(pbuf)[1];  // BlockHdr::slot_pos
+      const uint64_t spk = (uint64_t(sp.y) << 32) | sp.x;
+      uint32_t goff = 0;
+#pragma unroll
+      for (int s = 0; s < 6; ++s) goff |= ((j >> (2 * s)) & 3u) << (2u * (uint32_t(spk >> (8 * s)) & 0xffu));
+      dst.gdst = gtile + goff;
+      stored = true;
+    }
     switch (sig) {
-      case SIG_AAC: pass_fast<P_AFF, P_AFF, Q_CXN_AB, false, 0, 0, 0>(tile_b, pbuf, a_thr, cor, ops_q16); break;
-      case SIG_AAC_AA: pass_fast<P_AFF, P_AFF, Q_CXN_AB, true, P_AFF, P_AFF, Q_NONE>(tile_b, pbuf, a_thr, cor, ops_q16); break;
-      case SIG_AAC_RC: pass_fast<P_AFF, P_AFF, Q_CXN_AB, true, P_NONE, P_ROT, Q_CXN_AB>(tile_b, pbuf, a_thr, cor, ops_q16); break;
-      case SIG_C_RC: pass_fast<P_NONE, P_NONE, Q_CXN_AB, true, P_NONE, P_ROT, Q_CXN_AB>(tile_b, pbuf, a_thr, cor, ops_q16); break;
-      case SIG_RAC: pass_fast<P_ROT, P_AFF, Q_CXN_AB, false, 0, 0, 0>(tile_b, pbuf, a_thr, cor, ops_q16); break;
-      case SIG_0AC: pass_fast<P_NONE, P_AFF, Q_CXN_AB, false, 0, 0, 0>(tile_b, pbuf, a_thr, cor, ops_q16); break;
-      case SIG_AAC_A0: pass_fast<P_AFF, P_AFF, Q_CXN_AB, true, P_AFF, P_NONE, Q_NONE>(tile_b, pbuf, a_thr, cor, ops_q16); break;
-      case SIG_AAC_0A: pass_fast<P_AFF, P_AFF, Q_CXN_AB, true, P_NONE, P_AFF, Q_NONE>(tile_b, pbuf, a_thr, cor, ops_q16); break;
-      default: pass_generic<FULL>(tile_b, pbuf, a_thr, cor, ops_q16, n_ops, h.w); break;
+      case SIG_AAC: pass_fast<P_AFF, P_AFF, Q_CXN_AB, false, 0, 0, 0>(tile_b, pbuf, a_thr, cor, ops_q16, dst); break;
+      case SIG_AAC_AA: pass_fast<P_AFF, P_AFF, Q_CXN_AB, true, P_AFF, P_AFF, Q_NONE>(tile_b, pbuf, a_thr, cor, ops_q16, dst); break;
+      case SIG_AAC_RC: pass_fast<P_AFF, P_AFF, Q_CXN_AB, true, P_NONE, P_ROT, Q_CXN_AB>(tile_b, pbuf, a_thr, cor, ops_q16, dst); break;
+      case SIG_C_RC: pass_fast<P_NONE, P_NONE, Q_CXN_AB, true, P_NONE, P_ROT, Q_CXN_AB>(tile_b, pbuf, a_thr, cor, ops_q16, dst); break;
+      case SIG_RAC: pass_fast<P_ROT, P_AFF, Q_CXN_AB, false, 0, 0, 0>(tile_b, pbuf, a_thr, cor, ops_q16, dst); break;
+      case SIG_0AC: pass_fast<P_NONE, P_AFF, Q_CXN_AB, false, 0, 0, 0>(tile_b, pbuf, a_thr, cor, ops_q16, dst); break;
+      case SIG_AAC_A0: pass_fast<P_AFF, P_AFF, Q_CXN_AB, true, P_AFF, P_NONE, Q_NONE>(tile_b, pbuf, a_thr, cor, ops_q16, dst); break;
+      case SIG_AAC_0A: pass_fast<P_AFF, P_AFF, Q_CXN_AB, true, P_NONE, P_AFF, Q_NONE>(tile_b, pbuf, a_thr, cor, ops_q16, dst); break;
+      default: pass_generic<FULL>(tile_b, pbuf, a_thr, cor, ops_q16, n_ops, h.w, dst); break;
     }
   }
+  return stored;
 }
 
 template <bool FULL>
@@ -265,7 +304,7 @@ __global__ void __launch_bounds__(kTmaThreads, FULL ? 2 : BWQ_TMA_BLOCKS) dm_swe
   mbar_wait(&bar, 0);
   if (sweep_idx == 0) __syncthreads();
 
-  run_tma_passes<FULL, false>(tile_b, pbuf, L.a_table, tid);
+  if (run_tma_passes<FULL, false>(tile_b, pbuf, L.a_table, tid, L.states + int64_t(slot) * L.stride + base)) return;
   // generic-proxy writes -> async proxy, then one thread stores the tile and keeps the CTA (and
   // its shared memory) alive until the bulk store has read it
   asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
@@ -312,6 +351,8 @@ __global__ void __launch_bounds__(kTmaPersistThreads, 2) dm_sweep_tma_persistent
   uint64_t* const full = reinterpret_cast<uint64_t*>(pbufs + 2 * (kBlockBytes / 8));
   uint64_t* const done = full + 2;
   volatile int* const valid = reinterpret_cast<volatile int*>(done + 2);
+  volatile int* const stored_flag = valid + 2;                                   // the last pass stored the tile itself
+  volatile int64_t* const gt_off = reinterpret_cast<volatile int64_t*>(valid + 4);  // tile's first element in the chunk
   const int tid = threadIdx.x;
   if (tid == 0) {
     mbar_init_n(&full[0], 1); mbar_init_n(&full[1], 1);
@@ -362,6 +403,7 @@ __global__ void __launch_bounds__(kTmaPersistThreads, 2) dm_sweep_tma_persistent
           continue;
         }
         valid[b] = 1;
+        gt_off[b] = int64_t(t >> tiles_log2) * L.stride + int64_t(c0 & int((1u << (2 * L.n_digits)) - 1u));
         st_map[b] = map; st_c0[b] = c0;
         mbar_expect_tx(&full[b], blk_bytes + uint32_t(E * 8));
         bulk_load(pbufs + b * (kBlockBytes / 8), L.prog + blk_q16, blk_bytes, &full[b]);
@@ -372,8 +414,10 @@ __global__ void __launch_bounds__(kTmaPersistThreads, 2) dm_sweep_tma_persistent
       if (n_stored < n_real) {
         const int b = int(n_stored & 1u);
         mbar_wait(&done[b], (n_stored >> 1) & 1u);
-        tma_store_issue(st_map[b], tiles + b * E, st_c0[b]);
-        tma_store_wait_read();  // the buffer may be overwritten by the next load
+        if (!stored_flag[b]) {
+          tma_store_issue(st_map[b], tiles + b * E, st_c0[b]);
+          tma_store_wait_read();  // the buffer may be overwritten by the next load
+        }
         ++n_stored;
         continue;
       }
@@ -388,7 +432,9 @@ __global__ void __launch_bounds__(kTmaPersistThreads, 2) dm_sweep_tma_persistent
     const int b = int(k & 1u);
     mbar_wait(&full[b], (k >> 1) & 1u);
     if (!valid[b]) break;
-    run_tma_passes<FULL, true>(reinterpret_cast<char*>(tiles + b * E), pbufs + b * (kBlockBytes / 8), L.a_table, tid);
+    const bool stored = run_tma_passes<FULL, true>(reinterpret_cast<char*>(tiles + b * E), pbufs + b * (kBlockBytes / 8), L.a_table, tid,
+                                                   L.states + gt_off[b]);
+    if (tid == 0) stored_flag[b] = stored ? 1 : 0;
     asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
     compute_sync<true>();
     if (tid == 0) mbar_arrive(&done[b]);

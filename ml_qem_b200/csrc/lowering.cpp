@@ -582,7 +582,7 @@ void lower_dm_circuit(const NoiseTable& noise, const bwq_batch& b, int c, const 
     for (int d = 0; d < mlow; ++d) { in_tile[d] = 1; ++nt; }
     sel.clear();
     seen.clear();
-    int bytes = (int)sizeof(BlockHdr);
+    int bytes = (int)sizeof(BlockHdr) + (tma ? 64 : 0);  // TMA layout: room for the direct-store corner table
     while (first < np && done[first]) ++first;
     for (int i = first; i < np && nblocked < nd; ++i) {
       if (done[i]) continue;
@@ -653,7 +653,7 @@ void lower_dm_circuit(const NoiseTable& noise, const bwq_batch& b, int c, const 
         first_direct = true;
       }
     }
-    if (!tma && (opt.direct & kPassStoreDirect)) {
+    if ((opt.direct & kPassStoreDirect) && (!tma || opt.tma_direct_store)) {  // TMA layout: direct 16-byte stores on request
       const size_t stop = (first_direct && sel.size() > 1) ? 1 : 0;  // the front pass stays in front
       for (size_t k = sel.size(); k-- > stop && !last_direct;) {
         if (!eligible(sel[k])) continue;
@@ -668,7 +668,7 @@ void lower_dm_circuit(const NoiseTable& noise, const bwq_batch& b, int c, const 
     // ---- emit the block
     size_t n_ops_total = 0;
     for (int i : sel) n_ops_total += passes[i].ops.size();
-    const size_t ext_words = tma ? 8 * sel.size() : 0;  // corner tables: 16 x u32 per pass
+    const size_t ext_words = tma ? 8 * sel.size() + 8 : 0;  // corner tables: 16 x u32 per pass + the direct-store table
     const size_t hdr_words = (sizeof(BlockHdr) + sizeof(PassHdr) * sel.size() + sizeof(BlockOp) * n_ops_total) / 8 + ext_words;
     const size_t blk_begin = out->prog.size();
     out->prog.resize(blk_begin + (size_t)bytes / 8, 0);
@@ -677,6 +677,7 @@ void lower_dm_circuit(const NoiseTable& noise, const bwq_batch& b, int c, const 
     bh->n_passes = (int32_t)sel.size();
     bh->ext_q16 = tma ? (int32_t)((hdr_words - ext_words) / 2) : 0;
     uint32_t* ext = reinterpret_cast<uint32_t*>(blk + (hdr_words - ext_words));
+    if (tma) for (int d = 0; d < nd; ++d) if (in_tile[d]) bh->slot_pos[slot_of[d]] = (uint8_t)d;
     PassHdr* ph = reinterpret_cast<PassHdr*>(blk + sizeof(BlockHdr) / 8);
     BlockOp* bo = reinterpret_cast<BlockOp*>(blk + (sizeof(BlockHdr) + sizeof(PassHdr) * sel.size()) / 8);
     size_t op_cursor = 0, par_cursor = hdr_words;
@@ -709,6 +710,10 @@ void lower_dm_circuit(const NoiseTable& noise, const bwq_batch& b, int c, const 
         for (int db = 0; db < 4; ++db)
           for (int da = 0; da < 4; ++da) ext[16 * k + da + 4 * db] = 8u * tswz((uint32_t(da) << (2 * sa)) | (uint32_t(db) << (2 * sb)));
         ph[k].sig = (uint8_t)classify_pass(p.ops, sa != 0 && sb != 0);
+        if (ph[k].flags & kPassStoreDirect)
+          for (int db = 0; db < 4; ++db)
+            for (int da = 0; da < 4; ++da)
+              ext[16 * sel.size() + da + 4 * db] = (uint32_t(da) << (2 * p.qa)) | (uint32_t(db) << (2 * p.qb));
       }
       for (const MacroOp& o : p.ops) {
         BlockOp& d = bo[op_cursor++];

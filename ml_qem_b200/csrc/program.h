@@ -48,8 +48,10 @@ constexpr uint32_t kLocalMat = 0x80000000u;
 //   block := BlockHdr | PassHdr[n_passes] | BlockOp[...] | parameters (16-byte aligned)
 struct BlockHdr {   // 16 B
   int32_t n_passes;
-  int32_t ext_q16;  // TMA layout: offset (16-byte units) of the per-pass corner tables, 64 B per pass
-  int32_t pad[2];
+  int32_t ext_q16;  // TMA layout: offset (16-byte units) of the per-pass corner tables, 64 B per pass,
+                    // followed by one more 64 B table: the 16 corner offsets IN THE STATE (elements) of the
+                    // last pass when it stores its register groups straight to global memory (kPassStoreDirect)
+  uint8_t slot_pos[8];  // TMA layout: digit position of tile slot s (box order), s < 6
 };
 struct PassHdr {    // 16 B
   uint16_t ops_q16; // offset of the pass's first BlockOp, in 16-byte units from the block start
@@ -213,6 +215,7 @@ struct LowerOptions {
   int low_qubits = 2;
   int direct = kPassLoadDirect | kPassStoreDirect;  // which direct passes the planner may request
   bool tma = false;  // emit the TMA tile layout for circuits wider than a 6-digit tile (tile_qubits 6, low_qubits 2)
+  bool tma_direct_store = false;  // TMA layout: last pass stores to global memory itself (measured slower than the TMA store)
 };
 
 // Lowers circuit c of the batch.  Never throws; sets status on per-circuit failure.
@@ -240,6 +243,19 @@ struct SvProgram {
   int64_t n_gates = 0;
 };
 void lower_sv_circuit(const bwq_batch& b, int c, SvProgram* out);
+
+// ---- variant generation (variants.cpp): folds / twirls of a base batch on the flat gate stream
+struct ExpandedBatch {
+  int32_t n_variants = 1;               // variants per base circuit
+  std::vector<int32_t> n_qubits, status; // status: per BASE circuit (BWQ_CIRC_BAD_OP: a gate has no inverse rule)
+  std::vector<int64_t> op_offsets, obs_offsets, term_offsets;
+  std::vector<bwq_op> ops;
+  std::vector<double> params, term_coeff;
+  std::vector<uint64_t> term_x, term_z;
+  bwq_batch view{};                     // points into the vectors above
+};
+int expand_variants(const bwq_batch& base, const bwq_variants& v, ExpandedBatch* out);
+uint32_t twirl_draw(uint64_t seed, uint64_t circuit, uint64_t twirl, uint64_t cx_index);
 
 // gate library (host)
 bool gate_is_2q(uint16_t opcode);
@@ -280,21 +296,56 @@ enum SvOpKind : uint8_t {
   // params: {u32 n_d, u32 K}, n_d x {u32 d, u32 M}, pad to 16 B, (K + 1) complex table
   SVO_DZZ = 9
 };
-enum : uint8_t { SVF_ON_B = 1, SVF_COND = 2, SVF_COND_VAL = 4 };
+enum : uint8_t { SVF_COND = 2, SVF_COND_VAL = 4 };
 struct SvBlockOp {   // 8 B
   uint8_t kind, flags;
-  uint8_t qa, qb;    // D1/D2: physical bit positions
+  uint8_t qa, qb;    // U1/X/R1/X1: qa = pass slot (0..3) of the target; U2/SWAP: pass slots of the (first, second)
+                     // operand, matrix index i_first + 2 i_second; D1/D2: physical bit positions
   uint16_t off;      // parameter offset, 8-byte units from the block start
   uint8_t cond_bit;  // SVF_COND: physical bit tested against SVF_COND_VAL
   uint8_t pad;
 };
-struct SvPassHdr {   // 8 B
+// A register pass owns FOUR tile slots: every thread keeps the 16 amplitudes v[ia + 2 ib + 4 ic + 8 id]
+// of one group (256 threads x 16 = one 2^12 tile) and runs the pass's op list on them.
+// Fast passes (sig != SVS_GENERIC) have the shape  [diagonal ops] [one structured 1-qubit op of the
+// SAME kind on pass slots 0 .. n-1] [diagonal ops]  and run as straight-line bodies.
+enum SvSig : uint8_t {
+  SVS_GENERIC = 0,
+  SVS_X1 = 1,        // + (n - 1), n = 1..4 slot ops of kind SVO_X1
+  SVS_R1 = 5,        // SVO_R1
+  SVS_U1 = 9,        // SVO_U1 (unconditional)
+  SVS_DIAG = 13,     // diagonal ops only
+};
+struct SvPassHdr {   // 96 B
   uint16_t ops_q8;   // first SvBlockOp, 8-byte units from the block start
   uint16_t n_ops;
-  uint8_t sa, sb;    // tile slots
+  uint8_t s[4];      // tile slots of pass slots 0..3 (distinct)
+  uint8_t sig;       // SvSig
+  uint8_t n_pre;     // fast passes: diagonal ops before the slot ops (the rest follow them)
   uint8_t needs_index;  // some op reads the physical index (diagonal / conditional)
   uint8_t flags;     // kPassLoadDirect (first pass of the sweep) | kPassStoreDirect (last pass)
+  uint8_t pp[4];     // physical bit positions of pass slots 0..3
+  uint8_t tb[8];     // tile index bit driven by thread-id bit k (quarter warps hit 8 distinct 16-byte chunks)
+  uint8_t pad[8];
+  uint32_t cor[16];  // swizzled byte offsets of the 16 corners
 };
+static_assert(sizeof(SvPassHdr) == 96, "SvPassHdr layout");
+// shared-memory swizzle of the statevector tile (16-byte amplitudes): the low three index bits are
+// XOR-ed with bits 3..5, 6..8 and 9..11, so a lane bit may drive any of four index bits per chunk
+// bit -- with four pass slots there is always a free one: conflict free for every slot choice.
+BWQ_HD constexpr uint32_t svz12(uint32_t j) { return j ^ ((j >> 3) & 7u) ^ ((j >> 6) & 7u) ^ ((j >> 9) & 7u); }
+// thread-id bit -> tile index bit for a pass on tile slots sl[0..3] (K tile bits)
+inline void sv_thread_bits(const uint8_t sl[4], int K, uint8_t tb[8]) {
+  bool used[16] = {};
+  for (int i = 0; i < 4; ++i) used[sl[i]] = true;
+  int n = 0;
+  for (int k = 0; k < 3 && n < K - 4; ++k)
+    for (int b = k; b < K; b += 3)
+      if (!used[b]) { tb[n++] = (uint8_t)b; used[b] = true; break; }
+  for (int b = 0; b < K && n < K - 4; ++b)
+    if (!used[b]) { tb[n++] = (uint8_t)b; used[b] = true; }
+  for (; n < 8; ++n) tb[n] = 31;  // tiles smaller than 2^12 (tests): unused thread bits
+}
 // Statevector sweeps mirror the first-pass descriptor in the high half of SweepDesc::blk_len_q16:
 // kSvFirstDirect | sa | sb << 4 (the block length keeps the low 16 bits).  A pass is eligible when
 // both slots are free slots (>= the always-resident low bits): lanes then walk the contiguous low

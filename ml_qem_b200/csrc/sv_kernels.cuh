@@ -31,15 +31,10 @@ struct SvxLaunch {
 
 constexpr int kSvxThreads = 256;
 
-// shared-memory swizzle for 16-byte elements: LDS.128 is served per quarter-warp, so the eight
-// element indices of a quarter-warp must differ in their low 3 bits.  A register pass removes two
-// slots from the thread->index map, so bits 3 and 4 fold into the low bits (7 = 111b, 3 = 011b:
-// any three of {001, 010, 100, 111, 011} but {001,010,011} and {100,111,011} are independent;
-// those two cases -- passes on slots (2,3) and (0,1) -- pay a 2-way conflict).
-__device__ __forceinline__ uint32_t svz(uint32_t j) {
-  return j ^ (((j >> 3) & 1u) * 7u) ^ (((j >> 4) & 1u) * 3u);
-}
-
+// Shared-memory layout: amplitude with tile-local index j at 16 * svz12(j) (program.h): the low three
+// index bits are XOR-ed with three higher bit triples, so that the eight lanes of a quarter warp
+// (LDS.128 / STS.128 are served per quarter warp) hit eight distinct 16-byte chunks for every
+// choice of the four pass slots; the thread -> element map comes with the pass header (tb[]).
 __device__ __forceinline__ double2 cmul_d(double2 a, double2 b) {
   return make_double2(fma(a.x, b.x, -a.y * b.y), fma(a.x, b.y, a.y * b.x));
 }
@@ -56,201 +51,200 @@ __device__ __forceinline__ uint32_t svx_deposit_hi(uint32_t up, uint64_t pk) {
   return off;
 }
 
-// 2x2 (or X) on the target slot; pairs along it: indices (0,1),(2,3) for slot a, (0,2),(1,3) for b
-template <int NG, bool ON_B, bool COND>
-__device__ __forceinline__ void sv_op_1q(double2 (&v)[NG][4], const double2* __restrict__ m, const bool isx,
-                                         const uint32_t (&gidx0)[NG], const uint32_t cbit, const uint32_t want,
-                                         const uint32_t po) {
-  constexpr int P0 = 0, P1 = ON_B ? 2 : 1, Q0 = ON_B ? 1 : 2, Q1 = 3;
-  if (isx) {
+// ---- register-resident ops of the fast passes: v[ia + 2 ib + 4 ic + 8 id], pass slot S compile time
+// structured / general 2x2 on pass slot S: pairs (c, c | 1 << S)
+template <int S, int KIND>
+__device__ __forceinline__ void sv_slot_op(double2 (&v)[16], const double* __restrict__ m) {
+  if constexpr (KIND == SVO_U1) {
+    const double2* mc = reinterpret_cast<const double2*>(m);
+    const double2 u00 = mc[0], u01 = mc[1], u10 = mc[2], u11 = mc[3];
 #pragma unroll
-    for (int k = 0; k < NG; ++k) {
-      if (!COND || ((gidx0[k] >> cbit) & 1u) == want) { const double2 a = v[k][P0]; v[k][P0] = v[k][P1]; v[k][P1] = a; }
-      if (!COND || (((gidx0[k] | po) >> cbit) & 1u) == want) { const double2 a = v[k][Q0]; v[k][Q0] = v[k][Q1]; v[k][Q1] = a; }
+    for (int h = 0; h < 8; ++h) {
+      const int c0 = ((h >> S) << (S + 1)) | (h & ((1 << S) - 1)), c1 = c0 | (1 << S);
+      const double2 a = v[c0], b = v[c1];
+      v[c0] = cfma_d(u01, b, cmul_d(u00, a));
+      v[c1] = cfma_d(u11, b, cmul_d(u10, a));
     }
-    return;
-  }
-  const double2 u00 = m[0], u01 = m[1], u10 = m[2], u11 = m[3];
+  } else {
+    const double2 m01 = *reinterpret_cast<const double2*>(m), m23 = *reinterpret_cast<const double2*>(m + 2);
 #pragma unroll
-  for (int k = 0; k < NG; ++k) {
-    if (!COND || ((gidx0[k] >> cbit) & 1u) == want) {
-      const double2 a = v[k][P0], b = v[k][P1];
-      v[k][P0] = cfma_d(u01, b, cmul_d(u00, a));
-      v[k][P1] = cfma_d(u11, b, cmul_d(u10, a));
-    }
-    if (!COND || (((gidx0[k] | po) >> cbit) & 1u) == want) {
-      const double2 a = v[k][Q0], b = v[k][Q1];
-      v[k][Q0] = cfma_d(u01, b, cmul_d(u00, a));
-      v[k][Q1] = cfma_d(u11, b, cmul_d(u10, a));
-    }
-  }
-}
-
-// structured 2x2 (global phase dropped by the planner): XT = false: real matrix {m00, m01, m10, m11};
-// XT = true: [[d0, i o01], [i o10, d1]] as {d0, d1, o01, o10} -- 4 multiply-adds per amplitude
-// instead of the 8 of a complex 2x2 (rx / ry / sx / h layers of the Trotter circuits)
-template <int NG, bool ON_B, bool XT>
-__device__ __forceinline__ void sv_op_1s(double2 (&v)[NG][4], const double* __restrict__ m) {
-  constexpr int P0 = 0, P1 = ON_B ? 2 : 1, Q0 = ON_B ? 1 : 2, Q1 = 3;
-  const double2 m01 = *reinterpret_cast<const double2*>(m), m23 = *reinterpret_cast<const double2*>(m + 2);
-#pragma unroll
-  for (int k = 0; k < NG; ++k) {
-#pragma unroll
-    for (int h = 0; h < 2; ++h) {
-      const int A = h ? Q0 : P0, B = h ? Q1 : P1;
-      const double2 a = v[k][A], b = v[k][B];
-      if (XT) {
-        v[k][A] = make_double2(fma(-m23.x, b.y, m01.x * a.x), fma(m23.x, b.x, m01.x * a.y));
-        v[k][B] = make_double2(fma(-m23.y, a.y, m01.y * b.x), fma(m23.y, a.x, m01.y * b.y));
-      } else {
-        v[k][A] = make_double2(fma(m01.y, b.x, m01.x * a.x), fma(m01.y, b.y, m01.x * a.y));
-        v[k][B] = make_double2(fma(m23.y, b.x, m23.x * a.x), fma(m23.y, b.y, m23.x * a.y));
+    for (int h = 0; h < 8; ++h) {
+      const int c0 = ((h >> S) << (S + 1)) | (h & ((1 << S) - 1)), c1 = c0 | (1 << S);
+      const double2 a = v[c0], b = v[c1];
+      if constexpr (KIND == SVO_X1) {  // [[d0, i o01], [i o10, d1]] as {d0, d1, o01, o10}
+        v[c0] = make_double2(fma(-m23.x, b.y, m01.x * a.x), fma(m23.x, b.x, m01.x * a.y));
+        v[c1] = make_double2(fma(-m23.y, a.y, m01.y * b.x), fma(m23.y, a.x, m01.y * b.y));
+      } else {                         // real {m00, m01, m10, m11}
+        v[c0] = make_double2(fma(m01.y, b.x, m01.x * a.x), fma(m01.y, b.y, m01.x * a.y));
+        v[c1] = make_double2(fma(m23.y, b.x, m23.x * a.x), fma(m23.y, b.y, m23.x * a.y));
       }
     }
   }
 }
 
-// 4x4, matrix index i_first + 2 i_second; ON_B: (first, second) = (slot b, slot a)
-template <int NG, bool ON_B>
-__device__ __forceinline__ void sv_op_u2(double2 (&v)[NG][4], const double2* __restrict__ m) {
-  constexpr int I1 = ON_B ? 2 : 1, I2 = ON_B ? 1 : 2;
-  double2 y[NG][4];
-#pragma unroll
-  for (int r = 0; r < 4; ++r) {
-    const double2 m0 = m[4 * r], m1 = m[4 * r + 1], m2 = m[4 * r + 2], m3 = m[4 * r + 3];
-#pragma unroll
-    for (int k = 0; k < NG; ++k) {
-      double2 s = cmul_d(m0, v[k][0]);
-      s = cfma_d(m1, v[k][I1], s);
-      s = cfma_d(m2, v[k][I2], s);
-      y[k][r] = cfma_d(m3, v[k][3], s);
+// phase of one amplitude under a diagonal op; x = its full physical index
+__device__ __forceinline__ double2 sv_diag_phase(const uint32_t kind, const uint2 raw, const double* __restrict__ pbuf, const uint32_t x) {
+  const double* m = pbuf + (raw.y & 0xffffu);
+  if (kind == SVO_DZZ) {  // fused layer of ZZ-type bonds: table[number of bonds with odd parity]
+    const uint2* hdr = reinterpret_cast<const uint2*>(m);
+    const uint32_t n_d = hdr[0].x;
+    uint32_t w = 0;
+    for (uint32_t j = 0; j < n_d; ++j) {
+      const uint2 dm = hdr[1 + j];
+      w += __popc((x ^ (x >> dm.x)) & dm.y);
     }
+    return reinterpret_cast<const double2*>(hdr + ((n_d + 2u) & ~1u))[w];
   }
-#pragma unroll
-  for (int k = 0; k < NG; ++k) { v[k][0] = y[k][0]; v[k][I1] = y[k][1]; v[k][I2] = y[k][2]; v[k][3] = y[k][3]; }
+  const uint32_t qa = (raw.x >> 16) & 0xffu, qb = raw.x >> 24;
+  const uint32_t idx = ((x >> qa) & 1u) | (kind == SVO_D2 ? (((x >> qb) & 1u) << 1) : 0u);
+  return reinterpret_cast<const double2*>(m)[idx];
 }
 
-// One register pass on NG groups per thread (groups grp0 + k * kSvxThreads).  Every thread keeps
-// the 4 amplitudes v[k][ka + 2 kb] of its groups in registers and walks the op list once, so the
-// op decode and the (uniform) parameter loads are shared by the NG groups.
-// ld_g / st_g: direct pass -- the groups come from / go to global memory (gt = the tile's base in
-// the shard; the offset of a group is the deposit of its tile index, the 4 corners add the slot
-// bits 1 << pa, 1 << pb) instead of the shared-memory tile; synth: first sweep, |0...0> is generated.
-template <int NG>
-__device__ __forceinline__ void sv_run_pass(double2* __restrict__ tile, const double* __restrict__ pbuf,
-                                            const uint32_t* __restrict__ dep, const uint2* __restrict__ ops, const int n_ops,
-                                            const uint32_t grp0, const uint32_t n_grp, const int lo, const int hi,
-                                            const uint32_t ma, const uint32_t mb, const uint32_t pa, const uint32_t pb,
-                                            const uint32_t gbase, const int LB, const bool needs_index,
-                                            double2* __restrict__ gt, const bool ld_g, const bool st_g, const bool synth) {
-  uint32_t idx[NG][4], gidx0[NG], goff[NG];
-  double2 v[NG][4];
-  const uint32_t lowmask = (1u << LB) - 1u;
-  const uint32_t ca = 1u << pa, cb = 1u << pb;
+// Pass context (uniform per CTA except base / gidx0 / active)
+struct SvPassCtx {
+  char* tile_b;             // shared-memory tile
+  const double* pbuf;       // program block
+  const SvPassHdr* ph;      // this pass's header (shared memory)
+  const uint2* ops;
+  uint32_t base;            // thread's swizzled byte offset (corner 0)
+  uint32_t gidx0;           // full physical index of corner 0
+  uint32_t goff;            // local offset of corner 0 in the shard (direct passes)
+  double2* gt;              // tile base in the shard
+  bool ld_g, st_g, synth, active;
+};
+
+// diagonal ops [o0, o1) of a pass, applied to the thread's 16 amplitudes IN the shared-memory tile
+// (runtime loops: one small copy of this code serves every pass shape; a thread only touches its
+// own amplitudes, so no barrier separates this from the gather / scatter of the same pass)
+__device__ __forceinline__ void sv_diag_smem(const SvPassCtx& C, const int o0, const int o1) {
+  if (!C.active || o0 >= o1) return;
+  const SvPassHdr* ph = C.ph;
+  const uint32_t pbit[4] = {1u << ph->pp[0], 1u << ph->pp[1], 1u << ph->pp[2], 1u << ph->pp[3]};
+  for (uint32_t c = 0; c < 16; ++c) {
+    const uint32_t x = C.gidx0 | ((c & 1u) ? pbit[0] : 0u) | ((c & 2u) ? pbit[1] : 0u) | ((c & 4u) ? pbit[2] : 0u) | ((c & 8u) ? pbit[3] : 0u);
+    double2* a = reinterpret_cast<double2*>(C.tile_b + (C.base ^ ph->cor[c]));
+    double2 v = *a;
+    for (int o = o0; o < o1; ++o) {
+      const uint2 raw = C.ops[o];
+      v = cmul_d(sv_diag_phase(raw.x & 0xffu, raw, C.pbuf, x), v);
+    }
+    *a = v;
+  }
+}
+
+// Straight-line body of a fast pass: gather the 16 amplitudes (16-byte accesses, or global loads /
+// |0..0> synthesis on a direct first pass), N structured 1-qubit ops of one kind on pass slots
+// 0..N-1, scatter (or direct global stores on a direct last pass).
+template <int KIND, int N>
+__device__ __forceinline__ void sv_pass_fast(const SvPassCtx& C, const int first_op) {
+  if (!C.active) return;
+  const SvPassHdr* ph = C.ph;
+  double2 v[16];
+  if (C.ld_g) {
+    if (C.synth) {
 #pragma unroll
-  for (int k = 0; k < NG; ++k) {
-    const uint32_t grp = min(grp0 + k * kSvxThreads, n_grp - 1u);
-    uint32_t b0 = (grp & ((1u << lo) - 1u)) | ((grp >> lo) << (lo + 1));
-    b0 = (b0 & ((1u << hi) - 1u)) | ((b0 >> hi) << (hi + 1));
-    idx[k][0] = svz(b0); idx[k][1] = svz(b0 | ma); idx[k][2] = svz(b0 | mb); idx[k][3] = svz(b0 | ma | mb);
-    goff[k] = (needs_index || ld_g || st_g) ? ((b0 & lowmask) | dep[b0 >> LB]) : 0u;
-    gidx0[k] = gbase | goff[k];
-    if (ld_g) {
-      if (synth) {
-        v[k][0] = make_double2(gidx0[k] == 0u ? 1.0 : 0.0, 0.0);
-        v[k][1] = v[k][2] = v[k][3] = make_double2(0.0, 0.0);
-      } else {
-        const double2* __restrict__ src = gt + goff[k];
-        v[k][0] = __ldcg(src); v[k][1] = __ldcg(src + ca); v[k][2] = __ldcg(src + cb); v[k][3] = __ldcg(src + (ca | cb));
-      }
+      for (int c = 0; c < 16; ++c) v[c] = make_double2((c == 0 && C.gidx0 == 0u) ? 1.0 : 0.0, 0.0);
     } else {
+      const double2* __restrict__ src = C.gt + C.goff;
 #pragma unroll
-      for (int c = 0; c < 4; ++c) v[k][c] = tile[idx[k][c]];
+      for (int c = 0; c < 16; ++c)
+        v[c] = __ldcg(src + (((c & 1) ? 1u << ph->pp[0] : 0u) | ((c & 2) ? 1u << ph->pp[1] : 0u) | ((c & 4) ? 1u << ph->pp[2] : 0u) |
+                             ((c & 8) ? 1u << ph->pp[3] : 0u)));
+    }
+  } else {
+#pragma unroll
+    for (int q = 0; q < 4; ++q) {
+      const uint4 c4 = reinterpret_cast<const uint4*>(ph->cor)[q];
+      v[4 * q] = *reinterpret_cast<const double2*>(C.tile_b + (C.base ^ c4.x));
+      v[4 * q + 1] = *reinterpret_cast<const double2*>(C.tile_b + (C.base ^ c4.y));
+      v[4 * q + 2] = *reinterpret_cast<const double2*>(C.tile_b + (C.base ^ c4.z));
+      v[4 * q + 3] = *reinterpret_cast<const double2*>(C.tile_b + (C.base ^ c4.w));
     }
   }
-  for (int o = 0; o < n_ops; ++o) {
-    const uint2 raw = ops[o];
+  if constexpr (N >= 1) sv_slot_op<0, KIND>(v, C.pbuf + (C.ops[first_op].y & 0xffffu));
+  if constexpr (N >= 2) sv_slot_op<1, KIND>(v, C.pbuf + (C.ops[first_op + 1].y & 0xffffu));
+  if constexpr (N >= 3) sv_slot_op<2, KIND>(v, C.pbuf + (C.ops[first_op + 2].y & 0xffffu));
+  if constexpr (N >= 4) sv_slot_op<3, KIND>(v, C.pbuf + (C.ops[first_op + 3].y & 0xffffu));
+  if (C.st_g) {
+    double2* __restrict__ dst = C.gt + C.goff;
+#pragma unroll
+    for (int c = 0; c < 16; ++c)
+      dst[((c & 1) ? 1u << ph->pp[0] : 0u) | ((c & 2) ? 1u << ph->pp[1] : 0u) | ((c & 4) ? 1u << ph->pp[2] : 0u) |
+          ((c & 8) ? 1u << ph->pp[3] : 0u)] = v[c];
+  } else {
+#pragma unroll
+    for (int q = 0; q < 4; ++q) {
+      const uint4 c4 = reinterpret_cast<const uint4*>(ph->cor)[q];
+      *reinterpret_cast<double2*>(C.tile_b + (C.base ^ c4.x)) = v[4 * q];
+      *reinterpret_cast<double2*>(C.tile_b + (C.base ^ c4.y)) = v[4 * q + 1];
+      *reinterpret_cast<double2*>(C.tile_b + (C.base ^ c4.z)) = v[4 * q + 2];
+      *reinterpret_cast<double2*>(C.tile_b + (C.base ^ c4.w)) = v[4 * q + 3];
+    }
+  }
+}
+
+// Any op list: the ops run one after the other on the thread's 16 amplitudes IN the shared-memory
+// tile (runtime slots: no register-resident state, hence no register shuffling at the op dispatch).
+// Conditional / general 1-qubit ops, 4x4 unitaries and SWAPs take this path.
+__device__ __forceinline__ void sv_pass_generic(const SvPassCtx& C) {
+  if (!C.active) return;
+  const SvPassHdr* ph = C.ph;
+  const uint32_t pbit[4] = {1u << ph->pp[0], 1u << ph->pp[1], 1u << ph->pp[2], 1u << ph->pp[3]};
+  auto amp = [&](uint32_t c) { return reinterpret_cast<double2*>(C.tile_b + (C.base ^ ph->cor[c])); };
+  auto gidx = [&](uint32_t c) {
+    return C.gidx0 | ((c & 1u) ? pbit[0] : 0u) | ((c & 2u) ? pbit[1] : 0u) | ((c & 4u) ? pbit[2] : 0u) | ((c & 8u) ? pbit[3] : 0u);
+  };
+  for (int o = 0; o < ph->n_ops; ++o) {
+    const uint2 raw = C.ops[o];
     const uint32_t kind = raw.x & 0xffu, flags = (raw.x >> 8) & 0xffu;
-    const uint32_t qa = (raw.x >> 16) & 0xffu, qb = raw.x >> 24;
-    const double2* m = reinterpret_cast<const double2*>(pbuf + (raw.y & 0xffffu));
-    if (kind == SVO_DZZ) {
-      // fused layer of ZZ-type bonds: phase = table[number of bonds with odd parity]
-      const uint2* hdr = reinterpret_cast<const uint2*>(m);
-      const uint32_t n_d = hdr[0].x;
-      const double2* tab = reinterpret_cast<const double2*>(hdr + ((n_d + 2u) & ~1u));
+    const uint32_t sa = (raw.x >> 16) & 0xffu, sb = raw.x >> 24;
+    const double2* m = reinterpret_cast<const double2*>(C.pbuf + (raw.y & 0xffffu));
+    if (kind == SVO_D1 || kind == SVO_D2 || kind == SVO_DZZ) {
+      for (uint32_t c = 0; c < 16; ++c) {
+        double2* a = amp(c);
+        *a = cmul_d(sv_diag_phase(kind, raw, C.pbuf, gidx(c)), *a);
+      }
+    } else if (kind == SVO_U2 || kind == SVO_SWAP) {
+      const uint32_t ma = 1u << sa, mb = 1u << sb;
+      for (uint32_t c = 0; c < 16; ++c) {
+        if (c & (ma | mb)) continue;
+        double2 *a0 = amp(c), *a1 = amp(c | ma), *a2 = amp(c | mb), *a3 = amp(c | ma | mb);
+        const double2 x0 = *a0, x1 = *a1, x2 = *a2, x3 = *a3;
+        if (kind == SVO_SWAP) { *a1 = x2; *a2 = x1; continue; }
+        double2 y[4];
 #pragma unroll
-      for (int k = 0; k < NG; ++k) {
-        uint32_t w[4] = {0u, 0u, 0u, 0u};
-        for (uint32_t j = 0; j < n_d; ++j) {
-          const uint2 dm = hdr[1 + j];
-#pragma unroll
-          for (int c = 0; c < 4; ++c) {
-            const uint32_t x = gidx0[k] | ((c & 1) ? ca : 0u) | ((c & 2) ? cb : 0u);
-            w[c] += __popc((x ^ (x >> dm.x)) & dm.y);
+        for (int r = 0; r < 4; ++r) y[r] = cfma_d(m[4 * r + 3], x3, cfma_d(m[4 * r + 2], x2, cfma_d(m[4 * r + 1], x1, cmul_d(m[4 * r], x0))));
+        *a0 = y[0]; *a1 = y[1]; *a2 = y[2]; *a3 = y[3];
+      }
+    } else {  // 1-qubit op on pass slot sa, optionally conditional on a physical bit
+      const uint32_t ma = 1u << sa;
+      const uint32_t cbit = (raw.y >> 16) & 0xffu, want = (flags & SVF_COND_VAL) ? 1u : 0u;
+      for (uint32_t c = 0; c < 16; ++c) {
+        if (c & ma) continue;
+        if ((flags & SVF_COND) && ((gidx(c) >> cbit) & 1u) != want) continue;
+        double2 *pa = amp(c), *pb = amp(c | ma);
+        const double2 a = *pa, b = *pb;
+        if (kind == SVO_X) { *pa = b; *pb = a; }
+        else if (kind == SVO_U1) { *pa = cfma_d(m[1], b, cmul_d(m[0], a)); *pb = cfma_d(m[3], b, cmul_d(m[2], a)); }
+        else {
+          const double* r = reinterpret_cast<const double*>(m);
+          if (kind == SVO_X1) {
+            *pa = make_double2(fma(-r[2], b.y, r[0] * a.x), fma(r[2], b.x, r[0] * a.y));
+            *pb = make_double2(fma(-r[3], a.y, r[1] * b.x), fma(r[3], a.x, r[1] * b.y));
+          } else {
+            *pa = make_double2(fma(r[1], b.x, r[0] * a.x), fma(r[1], b.y, r[0] * a.y));
+            *pb = make_double2(fma(r[3], b.x, r[2] * a.x), fma(r[3], b.y, r[2] * a.y));
           }
         }
-#pragma unroll
-        for (int c = 0; c < 4; ++c) v[k][c] = cmul_d(tab[w[c]], v[k][c]);
       }
-      continue;
-    }
-    if (kind == SVO_D2 || kind == SVO_D1) {
-      // phase index b_qa (+ 2 b_qb); gidx0 has zeros at pa and pb, so the slot bits OR in
-      const bool two = kind == SVO_D2;
-      const uint32_t da = uint32_t(pa == qa) | (two ? (uint32_t(pa == qb) << 1) : 0u);
-      const uint32_t db = uint32_t(pb == qa) | (two ? (uint32_t(pb == qb) << 1) : 0u);
-#pragma unroll
-      for (int k = 0; k < NG; ++k) {
-        const uint32_t s0 = ((gidx0[k] >> qa) & 1u) | (two ? (((gidx0[k] >> qb) & 1u) << 1) : 0u);
-        v[k][0] = cmul_d(m[s0], v[k][0]);
-        v[k][1] = cmul_d(m[s0 | da], v[k][1]);
-        v[k][2] = cmul_d(m[s0 | db], v[k][2]);
-        v[k][3] = cmul_d(m[s0 | da | db], v[k][3]);
-      }
-      continue;
-    }
-    const bool on_b = (flags & SVF_ON_B) != 0u;
-    const uint32_t cbit = (raw.y >> 16) & 0xffu;
-    const uint32_t want = (flags & SVF_COND_VAL) ? 1u : 0u;
-    const uint32_t po = 1u << (on_b ? pa : pb);  // bit of the non-target slot
-    // uniform branches select straight-line variants (no per-element selects)
-    if (kind == SVO_U1 || kind == SVO_X) {
-      const bool isx = kind == SVO_X;
-      if (flags & SVF_COND) {
-        if (on_b) sv_op_1q<NG, true, true>(v, m, isx, gidx0, cbit, want, po);
-        else sv_op_1q<NG, false, true>(v, m, isx, gidx0, cbit, want, po);
-      } else {
-        if (on_b) sv_op_1q<NG, true, false>(v, m, isx, gidx0, cbit, want, po);
-        else sv_op_1q<NG, false, false>(v, m, isx, gidx0, cbit, want, po);
-      }
-    } else if (kind == SVO_X1) {
-      if (on_b) sv_op_1s<NG, true, true>(v, reinterpret_cast<const double*>(m));
-      else sv_op_1s<NG, false, true>(v, reinterpret_cast<const double*>(m));
-    } else if (kind == SVO_R1) {
-      if (on_b) sv_op_1s<NG, true, false>(v, reinterpret_cast<const double*>(m));
-      else sv_op_1s<NG, false, false>(v, reinterpret_cast<const double*>(m));
-    } else if (kind == SVO_U2) {
-      if (on_b) sv_op_u2<NG, true>(v, m);
-      else sv_op_u2<NG, false>(v, m);
-    } else if (kind == SVO_SWAP) {
-#pragma unroll
-      for (int k = 0; k < NG; ++k) { const double2 a = v[k][1]; v[k][1] = v[k][2]; v[k][2] = a; }
     }
   }
-#pragma unroll
-  for (int k = 0; k < NG; ++k)
-    if (NG == 1 ? (grp0 < n_grp) : true) {
-      if (st_g) {
-        double2* __restrict__ dst = gt + goff[k];
-        dst[0] = v[k][0]; dst[ca] = v[k][1]; dst[cb] = v[k][2]; dst[ca | cb] = v[k][3];
-      } else {
-#pragma unroll
-        for (int c = 0; c < 4; ++c) tile[idx[k][c]] = v[k][c];
-      }
-    }
 }
 
-__global__ void __launch_bounds__(kSvxThreads, 3) sv_sweep_kernel(const SvxLaunch L, const int sweep_idx) {
+#ifndef BWQ_SVX_BLOCKS
+#define BWQ_SVX_BLOCKS 2   // 128 registers: the 16 register-resident amplitudes are 64 of them
+#endif
+__global__ void __launch_bounds__(kSvxThreads, BWQ_SVX_BLOCKS) sv_sweep_kernel(const SvxLaunch L, const int sweep_idx) {
   extern __shared__ __align__(16) double2 sv_tile[];
   const int tid = threadIdx.x;
   const int K = L.tile_bits, LB = L.low_bits;
@@ -307,11 +301,11 @@ __global__ void __launch_bounds__(kSvxThreads, 3) sv_sweep_kernel(const SvxLaunc
     const int len = swraw.y & 0xffff;
     for (int i = tid; i < len; i += kSvxThreads) cp_async16(reinterpret_cast<uint4*>(pbuf) + i, src + i);
   }
-  // first pass direct (descriptor in the high half of blk_len): no staging of the tile; its lines
-  // are prefetched into L2 while the program block is in flight
+  // first pass direct (flag in the high half of blk_len): no staging of the tile; its lines are
+  // prefetched into L2 while the program block is in flight
   const bool first_direct = ((uint32_t(swraw.y) >> 16) & kSvFirstDirect) != 0u;
 
-  const uint32_t p_thr = svz(uint32_t(tid));
+  const uint32_t p_thr = svz12(uint32_t(tid));
   if (first_direct) {
     if (!first)
       for (uint32_t u = 8u * tid; u < E; u += 8u * kSvxThreads)   // one 128-byte line = 8 amplitudes
@@ -319,7 +313,7 @@ __global__ void __launch_bounds__(kSvxThreads, 3) sv_sweep_kernel(const SvxLaunc
   } else if (first) {
     for (uint32_t u0 = 0; u0 < E; u0 += kSvxThreads) {
       const uint32_t u = u0 + tid;
-      if (u < E) sv_tile[p_thr ^ svz(u0)] = make_double2((gbase == 0u && u == 0u) ? 1.0 : 0.0, 0.0);
+      if (u < E) sv_tile[p_thr ^ svz12(u0)] = make_double2((gbase == 0u && u == 0u) ? 1.0 : 0.0, 0.0);
     }
   } else {
     for (uint32_t u0 = 0; u0 < E; u0 += 4 * kSvxThreads) {
@@ -332,7 +326,7 @@ __global__ void __launch_bounds__(kSvxThreads, 3) sv_sweep_kernel(const SvxLaunc
 #pragma unroll
       for (int k = 0; k < 4; ++k) {
         const uint32_t uk = u0 + k * kSvxThreads;
-        if (uk + tid < E) sv_tile[p_thr ^ svz(uk)] = val[k];
+        if (uk + tid < E) sv_tile[p_thr ^ svz12(uk)] = val[k];
       }
     }
   }
@@ -340,39 +334,63 @@ __global__ void __launch_bounds__(kSvxThreads, 3) sv_sweep_kernel(const SvxLaunc
   __syncthreads();
 
   const int n_passes = reinterpret_cast<const int*>(pbuf)[0];
-  const uint2* phdr = reinterpret_cast<const uint2*>(pbuf + 2);
+  const SvPassHdr* phdr = reinterpret_cast<const SvPassHdr*>(pbuf + 2);
   bool stored = false;  // the last pass wrote the tile back itself
+  SvPassCtx C;
+  C.tile_b = reinterpret_cast<char*>(sv_tile);
+  C.pbuf = pbuf;
+  C.gt = g;
+  C.synth = first;
+  C.active = uint32_t(tid) < (E >> 4);
   for (int p = 0; p < n_passes; ++p) {
     if (p) __syncthreads();
-    const uint2 praw = phdr[p];
-    const int ops_q8 = praw.x & 0xffffu, n_ops = praw.x >> 16;
-    const int sa = praw.y & 0xffu, sb = (praw.y >> 8) & 0xffu;
-    const bool needs_index = ((praw.y >> 16) & 0xffu) != 0u;
-    const bool ld_g = p == 0 && first_direct;
-    const bool st_g = ((praw.y >> 24) & kPassStoreDirect) != 0u;
-    stored = st_g;
-    const int lo = min(sa, sb), hi = max(sa, sb);
-    const uint32_t ma = 1u << sa, mb = 1u << sb;
-    // physical positions of the two slots
-    const uint32_t pa = sa < LB ? uint32_t(sa) : (uint32_t(pk >> (8 * (sa - LB))) & 0xffu);
-    const uint32_t pb = sb < LB ? uint32_t(sb) : (uint32_t(pk >> (8 * (sb - LB))) & 0xffu);
-    const uint2* ops = reinterpret_cast<const uint2*>(pbuf) + ops_q8;
-    const uint32_t n_grp = E >> 2;
-    if (n_grp % (2u * kSvxThreads) == 0u)
-      for (uint32_t g0 = 0; g0 < n_grp; g0 += 2u * kSvxThreads)
-        sv_run_pass<2>(sv_tile, pbuf, dep, ops, n_ops, tid + g0, n_grp, lo, hi, ma, mb, pa, pb, gbase, LB, needs_index,
-                       g, ld_g, st_g, first);
-    else
-      for (uint32_t g0 = 0; g0 < n_grp; g0 += kSvxThreads)
-        sv_run_pass<1>(sv_tile, pbuf, dep, ops, n_ops, tid + g0, n_grp, lo, hi, ma, mb, pa, pb, gbase, LB, needs_index,
-                       g, ld_g, st_g, first);
+    const SvPassHdr* ph = phdr + p;
+    C.ph = ph;
+    C.ops = reinterpret_cast<const uint2*>(pbuf) + ph->ops_q8;
+    C.ld_g = p == 0 && first_direct;
+    C.st_g = (ph->flags & kPassStoreDirect) != 0u;
+    stored = C.st_g;
+    // thread -> tile-local index of its corner 0 (zeros at the four pass slots)
+    uint32_t j = 0;
+    {
+      const uint2 tbw = *reinterpret_cast<const uint2*>(ph->tb);
+      const uint64_t tbk = (uint64_t(tbw.y) << 32) | tbw.x;
+#pragma unroll
+      for (int k = 0; k < 8; ++k) j |= ((uint32_t(tid) >> k) & 1u) << (uint32_t(tbk >> (8 * k)) & 31u);
+      j &= E - 1u;  // tiles smaller than 2^12: unused thread bits point at bit 31
+    }
+    C.base = 16u * svz12(j);
+    C.goff = (ph->needs_index || C.ld_g || C.st_g) ? SVX_DEPOSIT(j) : 0u;
+    C.gidx0 = gbase | C.goff;
+    // fast passes: [diagonal ops on the tile] [register-resident slot ops] [diagonal ops on the tile]
+    // (the planner gives a direct first pass no leading and a direct last pass no trailing diagonal op)
+    const int n_pre = ph->n_pre, sig = ph->sig;
+    const int n_slot = sig == SVS_GENERIC ? 0 : (sig == SVS_DIAG ? 0 : ((sig - 1) & 3) + 1);
+    if (sig != SVS_GENERIC) sv_diag_smem(C, 0, n_pre);
+    switch (sig) {
+      case SVS_X1 + 0: sv_pass_fast<SVO_X1, 1>(C, n_pre); break;
+      case SVS_X1 + 1: sv_pass_fast<SVO_X1, 2>(C, n_pre); break;
+      case SVS_X1 + 2: sv_pass_fast<SVO_X1, 3>(C, n_pre); break;
+      case SVS_X1 + 3: sv_pass_fast<SVO_X1, 4>(C, n_pre); break;
+      case SVS_R1 + 0: sv_pass_fast<SVO_R1, 1>(C, n_pre); break;
+      case SVS_R1 + 1: sv_pass_fast<SVO_R1, 2>(C, n_pre); break;
+      case SVS_R1 + 2: sv_pass_fast<SVO_R1, 3>(C, n_pre); break;
+      case SVS_R1 + 3: sv_pass_fast<SVO_R1, 4>(C, n_pre); break;
+      case SVS_U1 + 0: sv_pass_fast<SVO_U1, 1>(C, n_pre); break;
+      case SVS_U1 + 1: sv_pass_fast<SVO_U1, 2>(C, n_pre); break;
+      case SVS_U1 + 2: sv_pass_fast<SVO_U1, 3>(C, n_pre); break;
+      case SVS_U1 + 3: sv_pass_fast<SVO_U1, 4>(C, n_pre); break;
+      case SVS_DIAG: break;
+      default: sv_pass_generic(C); break;
+    }
+    if (sig != SVS_GENERIC) sv_diag_smem(C, n_pre + n_slot, ph->n_ops);
   }
   if (stored) return;
   __syncthreads();
 
   for (uint32_t u0 = 0; u0 < E; u0 += kSvxThreads) {
     const uint32_t u = u0 + tid;
-    if (u < E) g[SVX_DEPOSIT(u)] = sv_tile[p_thr ^ svz(u0)];
+    if (u < E) g[SVX_DEPOSIT(u)] = sv_tile[p_thr ^ svz12(u0)];
   }
 #undef SVX_DEPOSIT
 }

@@ -43,10 +43,18 @@ struct ZzLayer {               // bonds of one fused diagonal layer (logical qub
   cd pe, po;
 };
 struct HPass {
-  int qa = -1, qb = -1;        // logical slot qubits (-1: any resident slot)
+  int q[4] = {-1, -1, -1, -1};  // logical qubits of pass slots 0..3 (-1: any other resident slot)
   std::vector<HOp> ops;
   uint64_t touch = 0;          // logical qubits this pass reads or writes (ordering)
+  // fast shape [diagonal ops][one structured 1-qubit op of one kind per slot 0..n-1][diagonal ops]:
+  bool fast = true;            // still has that shape
+  int n_pre = 0, n_slot = 0;   // diagonal ops before the slot ops, slot ops
+  uint8_t slot_kind = 0;       // their common kind
+  bool post = false;           // a diagonal op follows the slot ops
+  int slot_of(int lq) const { for (int i = 0; i < 4; ++i) if (q[i] == lq) return i; return -1; }
+  int n_q() const { int c = 0; for (int i = 0; i < 4; ++i) c += q[i] >= 0; return c; }
 };
+inline bool is_slot_kind(uint8_t k) { return k == SVO_U1 || k == SVO_R1 || k == SVO_X1; }
 
 inline bool is_zero(cd x) { return x.real() == 0.0 && x.imag() == 0.0; }
 inline bool is_one(cd x) { return x.real() == 1.0 && x.imag() == 0.0; }
@@ -143,24 +151,51 @@ struct Planner {
     }
     int P = -1;
     for (int q = 0; q < n; ++q) if ((touch >> q) & 1) P = std::max(P, last[q]);
-    bool ok = P >= 0;
-    int qa = ok ? passes[P].qa : -1, qb = ok ? passes[P].qb : -1;
-    for (int q = 0; q < n && ok; ++q) {
-      if (!((need >> q) & 1) || q == qa || q == qb) continue;
-      if (qa < 0) qa = q;
-      else if (qb < 0) qb = q;
-      else ok = false;
+    const bool slot_op = is_slot_kind(op.kind) && op.cond_q < 0;
+    const bool diag_op = need == 0;
+    // does the op fit pass c (index >= P: everything it depends on sits in passes <= P)?
+    auto fits = [&](const HPass& c) {
+      int free_slots = 4 - c.n_q();
+      for (int q = 0; q < n; ++q)
+        if (((need >> q) & 1) && c.slot_of(q) < 0 && --free_slots < 0) return false;
+      // keep a fast pass fast: its slot ops are one per slot, of one kind, no diagonal op between them
+      if (c.fast && slot_op) {
+        const int sl = c.slot_of(op.target);
+        if (c.post || c.n_slot >= 4 || (c.n_slot > 0 && c.slot_kind != op.kind)) return false;
+        if (sl >= 0 ? sl != c.n_slot : c.q[c.n_slot] >= 0) return false;  // its slot must be pass slot n_slot
+      }
+      // a pass stays well inside the shared-memory program buffer
+      return pass_bytes(c) + 8 * op_words_max(op) + 64 <= kBlockBytes / 2;
+    };
+    // diagonal ops go to the earliest legal pass (they must not delay later ops on their qubits),
+    // slot ops to the most recent pass with room (four slot ops share one gather / scatter)
+    int chosen = -1;
+    const int n_pass = (int)passes.size();
+    if (diag_op || !slot_op) {
+      for (int c = std::max(P, 0); c < n_pass && c < std::max(P, 0) + 4; ++c)
+        if ((P >= 0 || c == n_pass - 1) && fits(passes[c])) { chosen = c; break; }
+    } else {
+      for (int c = n_pass - 1; c >= std::max(P, 0) && c >= n_pass - 6; --c)
+        if (fits(passes[c])) { chosen = c; break; }
     }
-    // keep one pass well inside the shared-memory program buffer
-    if (ok && pass_bytes(passes[P]) + 8 * op_words_max(op) + 64 > kBlockBytes / 2) ok = false;
-    if (!ok) {
-      P = (int)passes.size();
+    if (chosen < 0) {
+      chosen = n_pass;
       passes.push_back(HPass());
-      qa = qb = -1;
-      for (int q = 0; q < n; ++q) if ((need >> q) & 1) { if (qa < 0) qa = q; else qb = q; }
     }
+    P = chosen;
     HPass& p = passes[P];
-    p.qa = qa; p.qb = qb;
+    if (p.fast && slot_op) {
+      p.q[p.n_slot] = op.target;  // (empty or already this qubit)
+      p.slot_kind = op.kind;
+      ++p.n_slot;
+    } else if (p.fast && diag_op) {
+      if (p.n_slot == 0) ++p.n_pre; else p.post = true;
+    } else {
+      p.fast = false;
+    }
+    for (int q = 0; q < n; ++q)
+      if (((need >> q) & 1) && p.slot_of(q) < 0)
+        for (int i = 0; i < 4; ++i) if (p.q[i] < 0) { p.q[i] = q; break; }
     p.ops.push_back(op);
     p.touch |= touch;
     for (int q = 0; q < n; ++q) if ((touch >> q) & 1) last[q] = P;
@@ -406,16 +441,34 @@ struct Planner {
     // direct passes: a pass that commutes with everything before / after it in this sweep (no
     // shared touched qubit) and whose slots are free slots moves to the front / back and exchanges
     // its register groups with global memory itself (sv_kernels.cuh)
-    auto slots_of = [&](const HPass& p, int& sa, int& sb) {
-      sa = p.qa >= 0 ? slot_of[phys[p.qa]] : -1; sb = p.qb >= 0 ? slot_of[phys[p.qb]] : -1;
-      if (sa < 0) sa = (sb == 0) ? 1 : 0;
-      if (sb < 0) sb = (sa == 0) ? 1 : 0;
+    // tile slots of the pass slots: real qubits first, then fillers (free slots preferred, so a
+    // pass on free slots stays eligible for direct global loads / stores)
+    auto slots_of = [&](const HPass& p, uint8_t (&ts)[4]) {
+      bool used[32] = {};
+      for (int i = 0; i < 4; ++i)
+        if (p.q[i] >= 0) { ts[i] = (uint8_t)slot_of[phys[p.q[i]]]; used[ts[i]] = true; }
+      for (int i = 0; i < 4; ++i) {
+        if (p.q[i] >= 0) continue;
+        int pick = -1;
+        for (int t = K - 1; t >= L && pick < 0; --t) if (!used[t]) pick = t;
+        for (int t = 0; t < L && pick < 0; ++t) if (!used[t]) pick = t;
+        ts[i] = (uint8_t)pick; used[pick] = true;
+      }
     };
-    auto eligible = [&](int i) { int sa, sb; slots_of(passes[i], sa, sb); return sa >= L && sb >= L && L >= 3; };
+    // only the register-resident part of a fast pass exchanges amplitudes with global memory:
+    // a direct first pass must not start with diagonal ops (they run on the tile), a direct last
+    // pass must not end with them
+    auto eligible = [&](int i, bool as_first) {
+      uint8_t ts[4];
+      slots_of(passes[i], ts);
+      const HPass& p = passes[i];
+      if (!p.fast || p.n_slot == 0 || (as_first ? p.n_pre > 0 : p.post)) return false;
+      return L >= 3 && ts[0] >= L && ts[1] >= L && ts[2] >= L && ts[3] >= L;
+    };
     bool first_direct = false, last_direct = false;
     if (direct_passes) {
       for (size_t k = 0; k < sel.size() && !first_direct; ++k) {
-        if (!eligible(sel[k])) continue;
+        if (!eligible(sel[k], true)) continue;
         bool free_ = true;
         for (size_t e = 0; e < k && free_; ++e) free_ = !(passes[sel[e]].touch & passes[sel[k]].touch);
         if (!free_) continue;
@@ -424,7 +477,7 @@ struct Planner {
       }
       const size_t stop = (first_direct && sel.size() > 1) ? 1 : 0;
       for (size_t k = sel.size(); k-- > stop && !last_direct;) {
-        if (!eligible(sel[k])) continue;
+        if (!eligible(sel[k], false)) continue;
         bool free_ = true;
         for (size_t l = k + 1; l < sel.size() && free_; ++l) free_ = !(passes[sel[l]].touch & passes[sel[k]].touch);
         if (!free_) continue;
@@ -451,13 +504,29 @@ struct Planner {
     size_t oc = 0, pc = o_par;
     for (size_t k = 0; k < sel.size(); ++k) {
       const HPass& p = passes[sel[k]];
-      int sa, sb;
-      slots_of(p, sa, sb);
+      uint8_t ts[4];
+      slots_of(p, ts);
       if (k == 0 && first_direct) ph[k].flags |= kPassLoadDirect;
       if (k + 1 == sel.size() && last_direct) ph[k].flags |= kPassStoreDirect;
       ph[k].ops_q8 = (uint16_t)((o_ops + sizeof(SvBlockOp) * oc) / 8);
       ph[k].n_ops = (uint16_t)p.ops.size();
-      ph[k].sa = (uint8_t)sa; ph[k].sb = (uint8_t)sb;
+      // slot -> physical position: low slots are their own position, free slots come from the sweep
+      for (int i = 0; i < 4; ++i) {
+        ph[k].s[i] = ts[i];
+        ph[k].pp[i] = ts[i] < L ? ts[i] : sw.pos[ts[i] - L];
+      }
+      sv_thread_bits(ph[k].s, K, ph[k].tb);
+      for (uint32_t c = 0; c < 16; ++c) {
+        uint32_t j = 0;
+        for (int i = 0; i < 4; ++i) j |= ((c >> i) & 1u) << ts[i];
+        ph[k].cor[c] = 16u * svz12(j);
+      }
+      ph[k].sig = SVS_GENERIC;
+      if (p.fast) {
+        ph[k].n_pre = (uint8_t)p.n_pre;
+        ph[k].sig = p.n_slot == 0 ? SVS_DIAG
+                  : (uint8_t)((p.slot_kind == SVO_X1 ? SVS_X1 : p.slot_kind == SVO_R1 ? SVS_R1 : SVS_U1) + (p.n_slot - 1));
+      }
       for (const HOp& o : p.ops) {
         SvBlockOp& d = bo[oc++];
         d.kind = o.kind;
@@ -472,9 +541,10 @@ struct Planner {
           continue;
         }
         if (o.kind == SVO_U1 || o.kind == SVO_X || o.kind == SVO_R1 || o.kind == SVO_X1) {
-          if (o.target == p.qb) d.flags |= SVF_ON_B;
+          d.qa = (uint8_t)p.slot_of(o.target);
         } else if (o.kind == SVO_U2 || o.kind == SVO_SWAP) {
-          if (o.qa != p.qa) d.flags |= SVF_ON_B;  // operands arrive swapped: (qa,qb) = (slot b, slot a)
+          d.qa = (uint8_t)p.slot_of(o.qa);
+          d.qb = (uint8_t)p.slot_of(o.qb);
         } else {
           d.qa = (uint8_t)phys[o.qa];
           d.qb = (uint8_t)(o.qb >= 0 ? phys[o.qb] : 0);
@@ -495,14 +565,12 @@ struct Planner {
     }
     sw.blk_q16 = (uint32_t)(blk_begin / 2);
     sw.blk_len_q16 = (uint32_t)(bytes / 16);
-    if (first_direct) sw.blk_len_q16 |= (kSvFirstDirect | (uint32_t)ph[0].sa | ((uint32_t)ph[0].sb << 4)) << 16;
+    if (first_direct) sw.blk_len_q16 |= kSvFirstDirect << 16;
     out->sweeps.push_back(sw);
     // a qubit only diagonal ops / control tests have seen is still |0>: amplitudes with a 1 on its
     // bit are zero, so tiles (or whole shards) with such an outside bit set can be skipped
-    for (int i : sel) {
-      if (passes[i].qa >= 0) touched |= 1ull << passes[i].qa;
-      if (passes[i].qb >= 0) touched |= 1ull << passes[i].qb;
-    }
+    for (int i : sel)
+      for (int k = 0; k < 4; ++k) if (passes[i].q[k] >= 0) touched |= 1ull << passes[i].q[k];
     uint32_t um = 0;
     for (int q = 0; q < n; ++q) if (!((touched >> q) & 1)) um |= 1u << phys[q];
     out->sweep_untouched.push_back(um);
@@ -529,8 +597,8 @@ struct Planner {
         if (p.touch & blocked) { blocked |= p.touch; continue; }
         bool ok = true;
         int need = 0;
-        int newpos[2];
-        for (int q : {p.qa, p.qb}) {
+        int newpos[4];
+        for (int q : p.q) {
           if (q < 0) continue;
           const int pp = phys[q];
           if (pp >= nl) { ok = false; break; }
@@ -590,9 +658,10 @@ struct Planner {
         if (!in_tile[pa]) { in_tile[pa] = 1; ++nt; }
         if (!in_tile[pb]) { in_tile[pb] = 1; ++nt; }
         HPass p;
-        p.qa = swaps[j].first; p.qb = swaps[j].second;
-        p.touch = (1ull << p.qa) | (1ull << p.qb);
-        HOp op; op.kind = SVO_SWAP; op.qa = (int8_t)p.qa; op.qb = (int8_t)p.qb;
+        p.q[0] = swaps[j].first; p.q[1] = swaps[j].second;
+        p.fast = false;
+        p.touch = (1ull << p.q[0]) | (1ull << p.q[1]);
+        HOp op; op.kind = SVO_SWAP; op.qa = (int8_t)p.q[0]; op.qb = (int8_t)p.q[1];
         p.ops.push_back(op);
         sel.push_back((int)passes.size());
         passes.push_back(p);
@@ -633,8 +702,7 @@ struct Planner {
       std::vector<int64_t> next_use(n, INT64_MAX);
       for (int i = np - 1; i >= 0; --i) {
         if (done[i]) continue;
-        if (passes[i].qa >= 0) next_use[passes[i].qa] = i;
-        if (passes[i].qb >= 0) next_use[passes[i].qb] = i;
+        for (int k = 0; k < 4; ++k) if (passes[i].q[k] >= 0) next_use[passes[i].q[k]] = i;
       }
       exchange(next_use);
     }
@@ -664,7 +732,9 @@ void lower_svx_circuit(const bwq_batch& b, int c, const SvxOptions& opt, SvxProg
     for (int q = 0; q < nq; ++q) if (used[q]) { bit_of[q] = (int)out->active.size(); out->active.push_back(q); }
   }
   const int gl = std::max(0, opt.n_global);
-  while ((int)out->active.size() < 2 * gl + 2) out->active.push_back(-1);
+  // a register pass owns four tile slots, and an exchange (the top g local bits leave) must be able
+  // to keep the up to four qubits of a pass local: n_local >= g + 4
+  while ((int)out->active.size() < 2 * gl + 4) out->active.push_back(-1);
   const int n = out->n_bits = (int)out->active.size();
   if (n > kMaxSvQubits + 1) { out->status = BWQ_CIRC_TOO_WIDE; return; }
   Planner P;
@@ -673,7 +743,7 @@ void lower_svx_circuit(const bwq_batch& b, int c, const SvxOptions& opt, SvxProg
   P.fuse_layers = std::getenv("BWQ_SVX_NO_FUSE") == nullptr;
   P.structured = std::getenv("BWQ_SVX_NO_STRUCT") == nullptr;
   P.n = n; P.g = gl; P.nl = n - gl;
-  P.K = std::min(std::min(std::max(opt.tile_bits, 2), kSvTileBitsMax), P.nl);
+  P.K = std::min(std::min(std::max(opt.tile_bits, 4), kSvTileBitsMax), P.nl);
   P.L = std::max(0, P.K - kSvFreeSlots);
   out->n_local = P.nl; out->n_global = gl; out->tile_bits = P.K;
   P.phys.resize(n); P.logical_at.resize(n);

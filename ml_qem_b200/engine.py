@@ -43,6 +43,30 @@ class _NoiseTable(C.Structure):
     ]
 
 
+class _Variants(C.Structure):
+    _fields_ = [("n_folds", C.c_int32), ("folds", C.c_void_p), ("n_twirls", C.c_int32), ("seed", C.c_uint64)]
+
+
+class Variants:
+    """ZNE folds / Pauli twirls generated inside the library from the base gate stream (bwq_variants):
+    base circuit c -> len(folds) * max(1, twirls) circuits, variant index fold * twirls + twirl."""
+
+    def __init__(self, folds=(1,), twirls=0, seed=0):
+        self.folds = tuple(int(f) for f in folds) or (1,)
+        if any(f < 1 or f % 2 == 0 for f in self.folds):
+            raise ValueError("noise factors of local folding must be odd positive integers")
+        self.twirls = int(twirls)
+        self.seed = int(seed)
+        self._folds_arr = np.asarray(self.folds, dtype=np.int32)
+
+    @property
+    def n_variants(self):
+        return len(self.folds) * max(1, self.twirls)
+
+    def c_struct(self):
+        return _Variants(len(self.folds), _ptr(self._folds_arr), self.twirls, self.seed)
+
+
 class _Options(C.Structure):
     _fields_ = [("tile_qubits", C.c_int32), ("low_qubits", C.c_int32), ("max_state_bytes", C.c_int64),
                 ("chunk_circuits", C.c_int32), ("host_threads", C.c_int32), ("sv_tile_bits", C.c_int32),
@@ -59,7 +83,7 @@ class _Stats(C.Structure):
 
 EXPORTS = [
     "bwq_version", "bwq_create", "bwq_destroy", "bwq_last_error", "bwq_set_options", "bwq_set_noise_table",
-    "bwq_dm_run", "bwq_sv_run", "bwq_meas_data_run", "bwq_dm_run_device_out", "bwq_dm_prepare", "bwq_dm_execute", "bwq_dm_execute_device_out", "bwq_sv_prepare", "bwq_sv_execute", "bwq_get_stats", "bwq_sync", "bwq_lower_dm", "bwq_lower_dm_ex",
+    "bwq_dm_run", "bwq_sv_run", "bwq_meas_data_run", "bwq_meas_data_run_variants", "bwq_dm_run_variants", "bwq_expand_variants", "bwq_dm_run_device_out", "bwq_dm_prepare", "bwq_dm_execute", "bwq_dm_execute_device_out", "bwq_sv_prepare", "bwq_sv_execute", "bwq_get_stats", "bwq_sync", "bwq_lower_dm", "bwq_lower_dm_ex",
     "bwq_program_free", "bwq_program_sizes", "bwq_program_read",
     "bwq_svx_lower", "bwq_svx_free", "bwq_svx_sizes", "bwq_svx_read", "bwq_svx_upload", "bwq_svx_run_segment",
     "bwq_svx_bytes", "bwq_svx_exchange_pull", "bwq_svx_exchange_push",
@@ -86,6 +110,10 @@ def load_library(path=None):
     for f in (lib.bwq_dm_run, lib.bwq_sv_run, lib.bwq_dm_run_device_out):
         f.argtypes = [C.c_void_p, C.POINTER(_Batch), C.c_void_p, C.c_void_p]
     lib.bwq_meas_data_run.argtypes = [C.c_void_p, C.POINTER(_Batch), C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p]
+    lib.bwq_meas_data_run_variants.argtypes = [C.c_void_p, C.POINTER(_Batch), C.POINTER(_Variants), C.c_void_p, C.c_void_p,
+                                               C.c_void_p, C.c_void_p]
+    lib.bwq_dm_run_variants.argtypes = [C.c_void_p, C.POINTER(_Batch), C.POINTER(_Variants), C.c_void_p, C.c_void_p]
+    lib.bwq_expand_variants.argtypes = [C.POINTER(_Batch), C.POINTER(_Variants), C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p]
     lib.bwq_dm_prepare.argtypes = [C.c_void_p, C.POINTER(_Batch), C.c_void_p]
     lib.bwq_dm_execute.argtypes = [C.c_void_p, C.c_void_p]
     lib.bwq_sv_prepare.argtypes = [C.c_void_p, C.POINTER(_Batch), C.c_void_p]
@@ -208,33 +236,45 @@ def encode_batch(circuits, observables):
 
     ``observables[i]`` is a list of Pauli observables evaluated on the SAME simulated state (the
     reference re-simulates the circuit once per observable, e.g. docs/tutorials/zne_parallel.py:259
-    passes ``[circ] * 4``; here one evolution serves them all)."""
-    n_qubits, op_off, obs_off, term_off = [], [0], [0], [0]
-    opc, q0s, q1s, pidx, params = [], [], [], [], []
-    tx, tz, tc = [], [], []
+    passes ``[circ] * 4``; here one evolution serves them all).  Vectorised: every circuit
+    contributes its cached flat arrays (Circuit.flat), every observable its cached masks; lists of
+    observables shared between circuits (``[obs] * n``) are converted once."""
+    n_qubits, op_cnt, obs_cnt = [], [], []
+    opc, q0s, q1s, npars, params = [], [], [], [], []
+    tx, tz, tc, term_cnt = [], [], [], []
+    obs_cache = {}
     for circ, obs_list in zip(circuits, observables):
         circ = circuit_mod.from_any(circ)
+        o, a, b, k, p = circ.flat()
         n_qubits.append(circ.num_qubits)
-        for name, qubits, pr in circ.gate_ops():
-            opc.append(OPCODES[name])
-            q0s.append(qubits[0])
-            q1s.append(qubits[1] if len(qubits) > 1 else 0)
-            pidx.append(len(params))
-            if NUM_PARAMS.get(name, 0):
-                params.extend(float(p) for p in pr)
-        op_off.append(len(opc))
-        for ob in obs_list:
-            ob = observable_mod.from_any(ob)
+        op_cnt.append(len(o))
+        opc.append(o); q0s.append(a); q1s.append(b); npars.append(k); params.append(p)
+        key = id(obs_list)
+        conv = obs_cache.get(key)
+        if conv is None or conv[0] is not obs_list:
+            obs_conv = [observable_mod.from_any(ob) for ob in obs_list]
+            masks = [ob.masks() for ob in obs_conv]
+            conv = (obs_list, obs_conv,
+                    np.concatenate([m[0] for m in masks]) if masks else np.zeros(0, dtype=np.uint64),
+                    np.concatenate([m[1] for m in masks]) if masks else np.zeros(0, dtype=np.uint64),
+                    np.concatenate([m[2] for m in masks]) if masks else np.zeros(0, dtype=np.float64),
+                    [len(m[2]) for m in masks])
+            obs_cache[key] = conv
+        for ob in conv[1]:
             if ob.num_qubits != circ.num_qubits and len(ob):
                 raise ValueError(f"observable acts on {ob.num_qubits} qubits, circuit has {circ.num_qubits}")
-            x, z, c = ob.masks()
-            tx.append(x); tz.append(z); tc.append(c)
-            term_off.append(term_off[-1] + len(c))
-        obs_off.append(obs_off[-1] + len(obs_list))
-    ops = np.zeros(len(opc), dtype=OP_DTYPE)
-    ops["opcode"], ops["q0"], ops["q1"], ops["param_idx"] = opc, q0s, q1s, pidx
-    cat = lambda xs, dt: np.concatenate(xs).astype(dt) if xs else np.zeros(0, dtype=dt)
-    return FlatBatch(n_qubits, op_off, ops, np.asarray(params, dtype=np.float64), obs_off, term_off,
+        tx.append(conv[2]); tz.append(conv[3]); tc.append(conv[4]); term_cnt.extend(conv[5])
+        obs_cnt.append(len(conv[1]))
+    cat = lambda xs, dt: np.concatenate(xs).astype(dt, copy=False) if xs else np.zeros(0, dtype=dt)
+    n_ops = int(sum(op_cnt))
+    ops = np.zeros(n_ops, dtype=OP_DTYPE)
+    if n_ops:
+        ops["opcode"], ops["q0"], ops["q1"] = cat(opc, np.uint16), cat(q0s, np.uint8), cat(q1s, np.uint8)
+        k = cat(npars, np.int64)
+        # param_idx = first parameter of the op (ops without parameters point at the running offset)
+        ops["param_idx"] = (np.cumsum(k) - k).astype(np.uint32)
+    off = lambda cnt: np.concatenate([[0], np.cumsum(np.asarray(cnt, dtype=np.int64))]) if len(cnt) else np.zeros(1, dtype=np.int64)
+    return FlatBatch(n_qubits, off(op_cnt), ops, cat(params, np.float64), off(obs_cnt), off(term_cnt),
                      cat(tx, np.uint64), cat(tz, np.uint64), cat(tc, np.float64))
 
 
@@ -379,6 +419,36 @@ class Engine:
                                                     st_n.ctypes.data_as(C.c_void_p)), "bwq_meas_data_run")
         return ideal, noisy, st_i, st_n
 
+    def run_dm_variants(self, batch, variants, noise=_KEEP_NOISE):
+        """Noisy values of every library-generated variant -> (values[n_observables * n_variants]
+        circuit-major then variant then the circuit's observables, status[n_circuits * n_variants])."""
+        vals = np.empty(batch.n_observables * variants.n_variants, dtype=np.float64)
+        status = np.zeros(batch.n_circuits * variants.n_variants, dtype=np.int32)
+        st, vs = batch.c_struct(), variants.c_struct()
+        with self._lock:
+            self._ensure_noise(noise)
+            self._check(self._lib.bwq_dm_run_variants(self._ctx, C.byref(st), C.byref(vs), vals.ctypes.data_as(C.c_void_p),
+                                                      status.ctypes.data_as(C.c_void_p)), "bwq_dm_run_variants")
+        return vals, status
+
+    def run_meas_data_variants(self, batch, variants, noise=_KEEP_NOISE):
+        """(ideal, noisy) values with the variants (ZNE folds, Pauli twirls) generated inside the
+        library: noisy[n_circuits, n_variants, obs...] flattened circuit-major, ideal as run_sv
+        (the base circuits: folds and twirls leave the ideal circuit unchanged).
+        -> (ideal, noisy, status_ideal, status_noisy)"""
+        ideal = np.empty(batch.n_observables, dtype=np.float64)
+        noisy = np.empty(batch.n_observables * variants.n_variants, dtype=np.float64)
+        st_i = np.zeros(batch.n_circuits, dtype=np.int32)
+        st_n = np.zeros(batch.n_circuits, dtype=np.int32)
+        st = batch.c_struct()
+        vs = variants.c_struct()
+        with self._lock:
+            self._ensure_noise(noise)
+            self._check(self._lib.bwq_meas_data_run_variants(self._ctx, C.byref(st), C.byref(vs), ideal.ctypes.data_as(C.c_void_p),
+                                                             noisy.ctypes.data_as(C.c_void_p), st_i.ctypes.data_as(C.c_void_p),
+                                                             st_n.ctypes.data_as(C.c_void_p)), "bwq_meas_data_run_variants")
+        return ideal, noisy, st_i, st_n
+
     def svx_exchange(self, local_ptr, peer_ptrs, rank, n_local_amps, stream=0, push=False):
         """EXCHANGE of the sharded statevector through peer memory: pull (local = new shard,
         peers = old shards) or push (local = old shard, peers = new shards)."""
@@ -407,7 +477,31 @@ class Engine:
         self._check(self._lib.bwq_sync(self._ctx), "bwq_sync")
 
 
-def lower_dm(batch, circuit, noise_model=None, tile_qubits=0, low_qubits=0, tma=False):
+def expand_variants(batch, variants):
+    """Host-only view of the library's variant generation (no GPU): the expanded FlatBatch
+    (observables replicated per variant), e.g. to compare with circuits built in Python."""
+    lib = load_library()
+    bs, vs = batch.c_struct(), variants.c_struct()
+    sizes = np.zeros(4, dtype=np.int64)
+    rc = lib.bwq_expand_variants(C.byref(bs), C.byref(vs), sizes.ctypes.data_as(C.c_void_p), None, None, None)
+    if rc != 0:
+        raise EngineError(f"bwq_expand_variants failed ({rc})")
+    n, n_ops, n_par, n_var = (int(x) for x in sizes)
+    op_off = np.zeros(n + 1, dtype=np.int64)
+    ops = np.zeros(n_ops, dtype=OP_DTYPE)
+    params = np.zeros(n_par, dtype=np.float64)
+    lib.bwq_expand_variants(C.byref(bs), C.byref(vs), sizes.ctypes.data_as(C.c_void_p), op_off.ctypes.data_as(C.c_void_p),
+                            ops.ctypes.data_as(C.c_void_p), params.ctypes.data_as(C.c_void_p))
+    rep = np.repeat(np.arange(batch.n_circuits), n_var)
+    obs_cnt = np.diff(batch.obs_offsets)[rep]
+    obs_src = _ranges(batch.obs_offsets[rep], batch.obs_offsets[rep + 1])
+    term_src = _ranges(batch.term_offsets[obs_src], batch.term_offsets[obs_src + 1])
+    return FlatBatch(batch.n_qubits[rep], op_off, ops, params, np.concatenate([[0], np.cumsum(obs_cnt)]),
+                     np.concatenate([[0], np.cumsum(np.diff(batch.term_offsets)[obs_src])]),
+                     batch.term_x[term_src], batch.term_z[term_src], batch.term_coeff[term_src])
+
+
+def lower_dm(batch, circuit, noise_model=None, tile_qubits=0, low_qubits=0, tma=False, tma_direct_store=False):
     """Host-only view of the lowering stage (no GPU): returns the sweep program of one circuit as a
     dict of numpy arrays (see bwq_program_read in include/bwq.h).  tma=True: the TMA tile layout
     the engine uses by default for circuits wider than the tile."""
@@ -416,7 +510,7 @@ def lower_dm(batch, circuit, noise_model=None, tile_qubits=0, low_qubits=0, tma=
     prog = C.c_void_p()
     bs = batch.c_struct()
     rc = lib.bwq_lower_dm_ex(C.byref(st) if st is not None else None, C.byref(bs), circuit, tile_qubits, low_qubits,
-                             1 if tma else 0, C.byref(prog))
+                             (1 if tma else 0) | (2 if tma_direct_store else 0), C.byref(prog))
     if rc != 0:
         raise EngineError(f"bwq_lower_dm failed ({rc}): {lib.bwq_last_error(None).decode()}")
     try:

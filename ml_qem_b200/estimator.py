@@ -223,6 +223,36 @@ class B200Estimator:
 
         meta = [{"simulator_metadata": {"method": method, "device": f"cuda:{self._device}"}} for _ in circuits]
         strategy = run_options.get("zne_strategy")
+        variants = run_options.get("variants")
+        if variants is not None:
+            # variants (ZNE folds x Pauli twirls) generated inside the library from the base gate stream
+            # (docs/tutorials/zne_parallel.py:168-189, docs/tutorials/derek_files/phase_diagram.ipynb:776):
+            # values[i] = twirl average at the first fold -- or its zero-noise extrapolation when an
+            # extrapolator comes with the strategy; metadata[i]["variants"] keeps every (fold, twirl) value
+            nf, nt = len(variants.folds), max(1, variants.twirls)
+            per = []  # per unique circuit: [n_var, n_obs_of_group]
+            if noisy:
+                vals, status = eng.run_dm_variants(batch, variants, noise=self._noise)
+                bad = np.nonzero(status)[0]
+                if len(bad):
+                    raise ValueError(f"circuit {groups[int(bad[0]) // (nf * nt)][0]}: {STATUS_TEXT.get(int(status[bad[0]]), 'error')}")
+                k = 0
+                for g in groups:
+                    per.append(vals[k:k + nf * nt * len(g)].reshape(nf * nt, len(g)))
+                    k += nf * nt * len(g)
+            else:  # folds and twirls leave the ideal circuit unchanged
+                base = evaluate(batch)
+                per = [np.repeat(base[g][None, :], nf * nt, axis=0) for g in (np.asarray(g) for g in groups)]
+            out = np.empty(len(circuits), dtype=float)
+            for g, v in zip(groups, per):
+                fold_means = v.reshape(nf, nt, len(g)).mean(axis=1)  # [fold, obs]
+                for j, i in enumerate(g):
+                    out[i] = fold_means[0, j]
+                    if strategy is not None and nf > 1:
+                        out[i] = strategy.extrapolator(fold_means[:, j], variants.folds)
+                    meta[i]["variants"] = {"folds": variants.folds, "twirls": variants.twirls, "seed": variants.seed,
+                                           "values": v[:, j].reshape(nf, nt)}
+            return EstimatorResult(out, meta)
         if strategy is None:
             return EstimatorResult(np.real_if_close(evaluate(batch)), meta)
         # digital ZNE (docs/tutorials/zne_parallel.py:168-189): every noise factor is the same

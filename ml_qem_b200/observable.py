@@ -39,6 +39,9 @@ class PauliObservable:
         that); calling this directly on a complex observable drops nothing silently -- it raises."""
         if self.is_complex() and not getattr(self, "_real_only_ok", False):
             raise ValueError("complex Pauli coefficients: evaluate real_part() and imag_part() separately")
+        cached = self.__dict__.get("_masks")
+        if cached is not None:
+            return cached
         n = len(self.terms)
         x = np.zeros(n, dtype=np.uint64)
         z = np.zeros(n, dtype=np.uint64)
@@ -53,6 +56,7 @@ class PauliObservable:
                 if ch in "ZY":
                     zm |= 1 << q
             x[k], z[k], c[k] = xm, zm, coeff.real
+        self.__dict__["_masks"] = (x, z, c)
         return x, z, c
 
     def real_part(self):

@@ -303,6 +303,10 @@ def test_tma_kernel_vs_classic_kernel_and_oracle(engine_gpu, monkeypatch):
     engine_gpu.set_options(flags=16)
     v_cls, st = engine_gpu.run_dm(batch, noise=nm)
     assert not st.any() and engine_gpu.stats()["n_tma_sweep_launches"] == 0
+    for fl in (64, 32, 32 | 64):  # direct last-pass stores; persistent double-buffered kernel; both
+        engine_gpu.set_options(flags=fl)
+        v_alt, st = engine_gpu.run_dm(batch, noise=nm)
+        assert not st.any() and np.max(np.abs(v_alt - v_tma)) <= 1e-13, fl
     engine_gpu.set_options()
     assert np.max(np.abs(v_tma - ref)) <= TOL and np.max(np.abs(v_cls - ref)) <= TOL
     assert np.max(np.abs(v_tma - v_cls)) <= 1e-13
@@ -323,3 +327,44 @@ def test_tma_kernel_vs_classic_kernel_and_oracle(engine_gpu, monkeypatch):
     v2, st = engine_gpu.run_dm(engine.encode_batch([c], [ob]), noise=nm2)
     assert not st.any() and engine_gpu.stats()["n_tma_sweep_launches"] > 0
     assert np.max(np.abs(v2 - ref2)) <= TOL
+
+
+def test_library_variants_on_gpu_match_python_built_variants(lib):
+    """bwq_dm_run_variants / bwq_meas_data_run_variants / B200Estimator(variants=...): the folds and
+    twirls generated inside the library give the values of the same variants built in Python (and
+    of the oracle on one of them); the ideal side runs the base circuits only."""
+    from test_variants import _Replay
+    from ml_qem_b200 import zne
+    from ml_qem_b200.engine import Engine, Variants
+
+    eng = Engine(0)
+    lima = backends.fake_lima()
+    nm = noise.from_backend(lima)
+    seed = 99
+    base = [F.tfim_circuit(4, s, 0.3 + 0.1 * s, layout=[0, 1, 3, 4], num_physical=5, basis="XYZ"[s % 3]) for s in (1, 2, 3)]
+    obs = [F.single_z_observables([0, 1, 3, 4], 5)] * 3
+    fb = engine.encode_batch(base, obs)
+    v = Variants(folds=(1, 3), twirls=4, seed=seed)
+    vals, st = eng.run_dm_variants(fb, v, noise=nm)
+    assert not st.any() and vals.shape == (3 * 8 * 4,)
+    ref_circs = [F.tfim_circuit(4, s, 0.3 + 0.1 * s, layout=[0, 1, 3, 4], num_physical=5, basis="XYZ"[s % 3], fold=fold,
+                                twirl_rng=_Replay(seed, c, t)) for c, s in enumerate((1, 2, 3)) for fold in (1, 3) for t in range(4)]
+    ref, st = eng.run_dm(engine.encode_batch(ref_circs, [obs[0]] * len(ref_circs)), noise=nm)
+    assert not st.any() and np.max(np.abs(vals - ref)) <= 1e-12
+    on = helpers.oracle_noise("fakelima")
+    assert np.max(np.abs(vals[5 * 4:6 * 4] - helpers.oracle_dm_values(ref_circs[5], obs[0], on))) <= TOL
+    ideal, noisy, st_i, st_n = eng.run_meas_data_variants(fb, v, noise=nm)
+    assert not st_i.any() and not st_n.any() and np.array_equal(noisy, vals)
+    assert np.max(np.abs(ideal - eng.run_sv(fb)[0])) == 0.0
+    # estimator: twirl averages, ZNE over the fold means, every (fold, twirl) value in the metadata
+    est = B200Estimator(backend=lima)
+    pairs_c = [c for c in base for _ in range(4)]
+    pairs_o = [o for _ in base for o in obs[0]]
+    res = est.run(pairs_c, pairs_o, variants=v).result()
+    grid = vals.reshape(3, 2, 4, 4)  # circuit, fold, twirl, observable
+    assert np.max(np.abs(res.values - grid[:, 0].mean(axis=1).reshape(-1))) <= 1e-12
+    assert np.allclose(res.metadata[5]["variants"]["values"], grid[1, :, :, 1])
+    res_z = est.run(pairs_c, pairs_o, variants=v, zne_strategy=zne.ZNEStrategy(noise_factors=(1, 3))).result()
+    m = grid.mean(axis=2)  # [circuit, fold, obs]
+    assert np.max(np.abs(res_z.values - (1.5 * m[:, 0] - 0.5 * m[:, 1]).reshape(-1))) <= 1e-10
+    eng.close()

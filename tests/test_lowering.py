@@ -179,11 +179,12 @@ def test_tma_tile_layout_programs(lib):
     cases = [F.tfim_circuit(n, 3, 0.4, basis="Y"), F.brickwork_circuit(n, 2, rng, twirl_rng=np.random.default_rng(2)),
              F.random_basis_circuit(n, 150, rng, [(i, i + 1) for i in range(n - 1)] + [(i + 1, i) for i in range(n - 1)])]
     sig_hist = {}
+    n_direct = [0]
     for c in cases:
         obs = [[(l, 1.0)] for l in _labels(rng, n, 6)]
         fb = engine.encode_batch([c], [obs])
         ref = helpers.oracle_dm_values(c, obs, on)
-        prog = engine.lower_dm(fb, 0, nm, tma=True)
+        prog = engine.lower_dm(fb, 0, nm, tma=True, tma_direct_store=True)
         assert prog["status"] == 0 and all(sw[8] == 0x40 for sw in prog["sweeps"])
         got = expvals(prog, run_program(prog), [1] * len(obs))
         assert np.max(np.abs(got - ref)) <= TOL
@@ -201,7 +202,19 @@ def test_tma_tile_layout_programs(lib):
                 worst = pe.check_tma_pass(h, b[16 * ext + 64 * p: 16 * ext + 64 * (p + 1)].view(np.uint32), int(h[4]), int(h[5]))
                 if c is not cases[2]:
                     assert worst == 1, (int(h[4]), int(h[5]))  # chain circuits: conflict free by box order
+                # slot positions in the block header = ascending positions permuted by the box order
+                pos = [int(x) for x in sw[1:9]]
+                slot_pos = pos[:2] + [pos[2 + ((pos[6] >> (2 * k)) & 3)] for k in range(4)]
+                assert [int(x) for x in b[8:14]] == slot_pos
+                if int(h[6]) & 2:  # last pass stores its groups directly: corner offsets in the state
+                    n_p = int(blk[:1].view(np.int32)[0])
+                    assert p == n_p - 1 and int(h[4]) >= 2 and int(h[5]) >= 2
+                    gcor = b[16 * ext + 64 * n_p: 16 * ext + 64 * (n_p + 1)].view(np.uint32)
+                    want = [((i & 3) << (2 * slot_pos[int(h[4])])) | ((i >> 2) << (2 * slot_pos[int(h[5])])) for i in range(16)]
+                    assert [int(x) for x in gcor] == want
+                    n_direct[0] += 1
     assert sum(v for k, v in sig_hist.items() if k != 0) > sum(sig_hist.values()) // 2
+    assert n_direct[0] > 0
     # narrow circuits (one tile) keep the classic layout
     c6 = F.tfim_circuit(6, 2, 0.3)
     p6 = engine.lower_dm(engine.encode_batch([c6], [F.single_z_observables(list(range(6)), 6)]), 0, nm, tma=True)

@@ -107,9 +107,8 @@ def test_exchange_count_tfim_chain_30q_plan(lib):
 
 def test_direct_pass_flags_of_statevector_sweeps(lib):
     """sv_sweep_kernel direct passes: the flagged first / last pass of a sweep uses free slots
-    only (>= the always-resident low bits) and the first-pass descriptor in the high half of the
-    sweep's block length repeats the first pass header.  (The reordered programs are run by the
-    emulator in the other tests of this file.)"""
+    only (>= the always-resident low bits) and the high half of the sweep's block length carries
+    the first-pass flag.  (The reordered programs are run by the emulator in the other tests.)"""
     from ml_qem_b200.engine import SvxProgram
     from svx_emulator import decode_block
 
@@ -122,16 +121,36 @@ def test_direct_pass_flags_of_statevector_sweeps(lib):
     for sw in info["sweeps"]:
         desc = (int(sw[9]) >> 16) & 0xffff
         passes, _ = decode_block(info, sw)
-        words = info["prog"][2 * int(sw[0]): 2 * (int(sw[0]) + (int(sw[9]) & 0xffff))].view(np.uint8)
-        flags = [int(words[16 + 8 * p + 7]) for p in range(len(passes))]
+        flags = [p["flags"] for p in passes]
         assert all(f == 0 for f in flags[1:-1])
         if flags[0] & 1:
-            sa, sb = passes[0][0], passes[0][1]
-            assert sa >= LB and sb >= LB and desc == (0x8000 | sa | (sb << 4))
+            assert all(x >= LB for x in passes[0]["s"]) and desc == 0x8000
             n_first += 1
         else:
             assert desc & 0x8000 == 0
         if flags[-1] & 2:
-            assert passes[-1][0] >= LB and passes[-1][1] >= LB
+            assert all(x >= LB for x in passes[-1]["s"])
             n_last += 1
     assert n_first > 0 and n_last > 0
+
+
+def test_four_slot_passes_and_fast_signatures(lib):
+    """Register passes own four tile slots; the rx / h layers of the Trotter circuits become fast
+    passes (straight-line kernel bodies) with up to four structured 1-qubit ops, the ZZ bonds of a
+    layer one fused diagonal op."""
+    from ml_qem_b200.engine import SvxProgram
+    from svx_emulator import SVO_DZZ, SVO_X1, SVS_GENERIC, decode_block
+
+    n = 24
+    circ = F.tfim_circuit(n, 4, 0.4, dt=0.25)
+    info = SvxProgram(engine.encode_batch([circ], [F.tfim_observables(list(range(n)), n)]), 0, 12, 0).info
+    n_pass = n_fast = n_x1 = n_dzz = 0
+    for sw in info["sweeps"]:
+        for ph in decode_block(info, sw)[0]:
+            n_pass += 1
+            n_fast += ph["sig"] != SVS_GENERIC
+            n_x1 += sum(o["kind"] == SVO_X1 for o in ph["ops"])
+            n_dzz += sum(o["kind"] == SVO_DZZ for o in ph["ops"])
+    assert n_x1 == 4 * n and n_dzz == 4
+    assert n_fast == n_pass                      # no generic pass in a TFIM circuit
+    assert n_pass <= (4 * n + n) / 4 + 8 + 4     # about four slot ops per pass
