@@ -470,7 +470,22 @@ def bench_dm(ctx, name, steps, warmup, scale=1.0, cpu_budget=15.0, cpu_first=Non
                            "(ideal); variants generated inside the library (bwq_dm_run_variants)" % wl["variants"],
                    "base_circuits": len(base_c), "variants_per_circuit": V.n_variants, "pairs_per_call": len(pairs_c),
                    "values_head": [float(x) for x in rn.values[:2]], "ideal_head": [float(x) for x in ri.values[:2]]}
-        eng.set_noise(noise.from_backend(wl["backend"]))
+        # the C ABI alone from the BASE batch (host buffers): bwq_meas_data_run_variants = variant generation in
+        # the library + lowering + H2D + kernels (noisy: every variant, ideal: base circuits) + D2H
+        nm_v = noise.from_backend(wl["backend"])
+        base_batch = engine.encode_batch(base_c, [obs0] * len(base_c))
+        for _ in range(2):
+            eng.run_meas_data_variants(base_batch, V, noise=nm_v)
+        ctx.barrier()
+        t0 = time.perf_counter()
+        for _ in range(steps):
+            eng.run_meas_data_variants(base_batch, V, noise=nm_v)
+        ctx.barrier()
+        var_s = ctx.max(time.perf_counter() - t0)
+        est_res["c_abi_variants"] = {"value": n_var_circ / var_s, "unit": UNIT, "ms_per_step": 1e3 * var_s / steps,
+                                     "call": "bwq_meas_data_run_variants(base batch, variants) from host buffers",
+                                     "h2d_base_batch_bytes": int(base_batch.nbytes())}
+        eng.set_noise(nm_v)
 
     # ---- final gather of the labels (the only collective of the density-matrix path)
     if dist is not None:

@@ -134,7 +134,13 @@ class Circuit:
 
     @property
     def num_parameters(self):
-        return len(self.parameters)
+        ops = self.ops
+        key = (len(ops), id(ops[-1]) if ops else 0)
+        cache = self.__dict__.get("_npar")
+        if cache is None or cache[0] != key:
+            cache = (key, len(self.parameters))
+            self.__dict__["_npar"] = cache
+        return cache[1]
 
     def bind_parameters(self, values):
         names = [p.name for p in self.parameters]

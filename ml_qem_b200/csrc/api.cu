@@ -227,8 +227,10 @@ extern "C" int bwq_create(int device, bwq_ctx** out) {
     return bail(e, "cudaFuncSetAttribute(dm_sweep_kernel<7, full>)");
   if ((e = cudaFuncSetAttribute(sv_circuit_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 16 << 12)) != cudaSuccess)
     return bail(e, "cudaFuncSetAttribute(sv_circuit_kernel)");
-  if ((e = cudaFuncSetAttribute(sv_sweep_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (16 << kSvTileBitsMax) + kBlockBytes + 1024)) != cudaSuccess)
+  if ((e = cudaFuncSetAttribute(sv_sweep_kernel<256>, cudaFuncAttributeMaxDynamicSharedMemorySize, (16 << kSvTileBitsMax) + kBlockBytes + 1024)) != cudaSuccess)
     return bail(e, "cudaFuncSetAttribute(sv_sweep_kernel)");
+  if ((e = cudaFuncSetAttribute(sv_sweep_kernel<128>, cudaFuncAttributeMaxDynamicSharedMemorySize, (16 << 11) + kBlockBytes + 1024)) != cudaSuccess)
+    return bail(e, "cudaFuncSetAttribute(sv_sweep_kernel<128>)");
   {
     std::vector<uint32_t> tab((size_t)kB0Pairs * kB0Groups);
     fill_b0_table(tab.data());
@@ -891,7 +893,8 @@ extern "C" int bwq_dm_run_device_out(bwq_ctx* ctx, const bwq_batch* b, double* d
 // ------------------------------------------------------------------------------------------------
 static cudaError_t launch_sv_sweep(const SvxLaunch& L, int sweep, int64_t n_cta, cudaStream_t s) {
   const size_t smem = (sizeof(double2) << L.tile_bits) + kBlockBytes + 1024;  // tile | program | deposit table
-  sv_sweep_kernel<<<(unsigned)n_cta, kSvxThreads, smem, s>>>(L, sweep);
+  if (L.tile_bits <= 11) sv_sweep_kernel<128><<<(unsigned)n_cta, 128, smem, s>>>(L, sweep);
+  else sv_sweep_kernel<256><<<(unsigned)n_cta, 256, smem, s>>>(L, sweep);
   return cudaGetLastError();
 }
 
@@ -1352,12 +1355,13 @@ extern "C" int bwq_meas_data_run_variants(bwq_ctx* ctx, const bwq_batch* b, cons
   if ((rc = ensure_companion(ctx))) return rc;
   const double t0 = now_ms();
   ExpandedBatch X;
-  if ((rc = expand_variants(*b, *v, &X))) return fail(ctx, rc, "bad variants descriptor (folds must be odd positive factors)");
+  if ((rc = expand_variants(*b, *v, &X, host_threads(ctx)))) return fail(ctx, rc, "bad variants descriptor (folds must be odd positive factors)");
   const double expand_ms = now_ms() - t0;
   std::vector<int32_t> st_var((size_t)X.view.n_circuits);
   const int all_threads = host_threads(ctx), saved_threads = ctx->opt.host_threads;
   ctx->companion->opt = ctx->opt;
-  ctx->companion->opt.host_threads = std::max(1, all_threads / 4);
+  // host threads in proportion to the circuits each side lowers (ideal: base circuits only)
+  ctx->companion->opt.host_threads = std::max(1, all_threads / (4 * std::max(1, X.n_variants)));
   ctx->opt.host_threads = std::max(1, all_threads - ctx->companion->opt.host_threads);
   int rc_sv = BWQ_OK;
   std::thread ideal([&] { rc_sv = bwq_sv_run(ctx->companion, b, out_ideal, status_ideal); });
@@ -1383,7 +1387,7 @@ extern "C" int bwq_dm_run_variants(bwq_ctx* ctx, const bwq_batch* b, const bwq_v
   if (rc) return rc;
   const double t0 = now_ms();
   ExpandedBatch X;
-  if ((rc = expand_variants(*b, *v, &X))) return fail(ctx, rc, "bad variants descriptor (folds must be odd positive factors)");
+  if ((rc = expand_variants(*b, *v, &X, host_threads(ctx)))) return fail(ctx, rc, "bad variants descriptor (folds must be odd positive factors)");
   const double expand_ms = now_ms() - t0;
   if ((rc = bwq_dm_run(ctx, &X.view, out_vals, out_status))) return rc;
   for (int c = 0; c < b->n_circuits; ++c)
@@ -1401,7 +1405,7 @@ extern "C" int bwq_expand_variants(const bwq_batch* b, const bwq_variants* v, in
                                    double* params) {
   if (!b || !v || !sizes) return BWQ_ERR_ARG;
   ExpandedBatch X;
-  int rc = expand_variants(*b, *v, &X);
+  int rc = expand_variants(*b, *v, &X, 4);
   if (rc) return rc;
   sizes[0] = X.view.n_circuits; sizes[1] = (int64_t)X.ops.size(); sizes[2] = (int64_t)X.params.size(); sizes[3] = X.n_variants;
   if (op_offsets) std::memcpy(op_offsets, X.op_offsets.data(), sizeof(int64_t) * X.op_offsets.size());

@@ -254,7 +254,7 @@ struct ExpandedBatch {
   std::vector<uint64_t> term_x, term_z;
   bwq_batch view{};                     // points into the vectors above
 };
-int expand_variants(const bwq_batch& base, const bwq_variants& v, ExpandedBatch* out);
+int expand_variants(const bwq_batch& base, const bwq_variants& v, ExpandedBatch* out, int threads = 1);
 uint32_t twirl_draw(uint64_t seed, uint64_t circuit, uint64_t twirl, uint64_t cx_index);
 
 // gate library (host)
@@ -351,7 +351,7 @@ inline void sv_thread_bits(const uint8_t sl[4], int K, uint8_t tb[8]) {
 // both slots are free slots (>= the always-resident low bits): lanes then walk the contiguous low
 // bits, i.e. whole 256-byte runs.
 constexpr uint32_t kSvFirstDirect = 0x8000u;
-constexpr int kSvTileBitsDefault = 12;  // 64 KiB tiles: 9 instead of 8 free slots' worth of passes per sweep, 7-9 % faster than 11
+constexpr int kSvTileBitsDefault = 11;  // 32 KiB tiles, 128-thread CTAs, four per SM: 6 % faster than 2^12 tiles (two 256-thread CTAs per SM)
 constexpr int kSvTileBitsMax = 12;
 constexpr int kSvFreeSlots = 8;       // SweepDesc::pos holds the positions of slots L..K-1
 constexpr int kSvSmallBits = 12;      // <= this: one CTA per circuit, state in shared memory

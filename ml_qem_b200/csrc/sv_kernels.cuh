@@ -120,6 +120,7 @@ __device__ __forceinline__ void sv_diag_smem(const SvPassCtx& C, const int o0, c
   if (!C.active || o0 >= o1) return;
   const SvPassHdr* ph = C.ph;
   const uint32_t pbit[4] = {1u << ph->pp[0], 1u << ph->pp[1], 1u << ph->pp[2], 1u << ph->pp[3]};
+#pragma unroll 4
   for (uint32_t c = 0; c < 16; ++c) {
     const uint32_t x = C.gidx0 | ((c & 1u) ? pbit[0] : 0u) | ((c & 2u) ? pbit[1] : 0u) | ((c & 4u) ? pbit[2] : 0u) | ((c & 8u) ? pbit[3] : 0u);
     double2* a = reinterpret_cast<double2*>(C.tile_b + (C.base ^ ph->cor[c]));
@@ -241,10 +242,11 @@ __device__ __forceinline__ void sv_pass_generic(const SvPassCtx& C) {
   }
 }
 
-#ifndef BWQ_SVX_BLOCKS
-#define BWQ_SVX_BLOCKS 2   // 128 registers: the 16 register-resident amplitudes are 64 of them
-#endif
-__global__ void __launch_bounds__(kSvxThreads, BWQ_SVX_BLOCKS) sv_sweep_kernel(const SvxLaunch L, const int sweep_idx) {
+// NT threads x 16 amplitudes: NT = 256 for 2^12-amplitude tiles (two CTAs per SM at 128 registers:
+// the 16 register-resident amplitudes are 64 of them), NT = 128 for tiles of 2^11 and fewer (four
+// smaller CTAs per SM: the same 16 warps, but a pass barrier only stalls four of them)
+template <int NT>
+__global__ void __launch_bounds__(NT, NT == 256 ? 2 : 4) sv_sweep_kernel(const SvxLaunch L, const int sweep_idx) {
   extern __shared__ __align__(16) double2 sv_tile[];
   const int tid = threadIdx.x;
   const int K = L.tile_bits, LB = L.low_bits;
@@ -288,18 +290,18 @@ __global__ void __launch_bounds__(kSvxThreads, BWQ_SVX_BLOCKS) sv_sweep_kernel(c
   if (dead && !first) return;
   // deposit table of the 8 free slots (one entry per thread), after the program block
   uint32_t* dep = reinterpret_cast<uint32_t*>(pbuf + kBlockBytes / 8);
-  dep[tid] = svx_deposit_hi(uint32_t(tid), pk);
+  for (int i = tid; i < 256; i += NT) dep[i] = svx_deposit_hi(uint32_t(i), pk);
   __syncthreads();
   const uint32_t lowmask = (1u << LB) - 1u;
 #define SVX_DEPOSIT(j) (((j) & lowmask) | dep[(j) >> LB])
   if (dead) {
-    for (uint32_t u = tid; u < E; u += kSvxThreads) __stcg(g + SVX_DEPOSIT(u), make_double2(0.0, 0.0));
+    for (uint32_t u = tid; u < E; u += NT) __stcg(g + SVX_DEPOSIT(u), make_double2(0.0, 0.0));
     return;
   }
   {
     const uint4* src = L.prog + uint32_t(swraw.x);
     const int len = swraw.y & 0xffff;
-    for (int i = tid; i < len; i += kSvxThreads) cp_async16(reinterpret_cast<uint4*>(pbuf) + i, src + i);
+    for (int i = tid; i < len; i += NT) cp_async16(reinterpret_cast<uint4*>(pbuf) + i, src + i);
   }
   // first pass direct (flag in the high half of blk_len): no staging of the tile; its lines are
   // prefetched into L2 while the program block is in flight
@@ -308,24 +310,24 @@ __global__ void __launch_bounds__(kSvxThreads, BWQ_SVX_BLOCKS) sv_sweep_kernel(c
   const uint32_t p_thr = svz12(uint32_t(tid));
   if (first_direct) {
     if (!first)
-      for (uint32_t u = 8u * tid; u < E; u += 8u * kSvxThreads)   // one 128-byte line = 8 amplitudes
+      for (uint32_t u = 8u * tid; u < E; u += 8u * NT)   // one 128-byte line = 8 amplitudes
         asm volatile("prefetch.global.L2 [%0];" ::"l"(g + SVX_DEPOSIT(u)));
   } else if (first) {
-    for (uint32_t u0 = 0; u0 < E; u0 += kSvxThreads) {
+    for (uint32_t u0 = 0; u0 < E; u0 += NT) {
       const uint32_t u = u0 + tid;
       if (u < E) sv_tile[p_thr ^ svz12(u0)] = make_double2((gbase == 0u && u == 0u) ? 1.0 : 0.0, 0.0);
     }
   } else {
-    for (uint32_t u0 = 0; u0 < E; u0 += 4 * kSvxThreads) {
+    for (uint32_t u0 = 0; u0 < E; u0 += 4 * NT) {
       double2 val[4];
 #pragma unroll
       for (int k = 0; k < 4; ++k) {
-        const uint32_t u = u0 + k * kSvxThreads + tid;
+        const uint32_t u = u0 + k * NT + tid;
         if (u < E) val[k] = __ldcg(g + SVX_DEPOSIT(u));
       }
 #pragma unroll
       for (int k = 0; k < 4; ++k) {
-        const uint32_t uk = u0 + k * kSvxThreads;
+        const uint32_t uk = u0 + k * NT;
         if (uk + tid < E) sv_tile[p_thr ^ svz12(uk)] = val[k];
       }
     }
@@ -388,7 +390,7 @@ __global__ void __launch_bounds__(kSvxThreads, BWQ_SVX_BLOCKS) sv_sweep_kernel(c
   if (stored) return;
   __syncthreads();
 
-  for (uint32_t u0 = 0; u0 < E; u0 += kSvxThreads) {
+  for (uint32_t u0 = 0; u0 < E; u0 += NT) {
     const uint32_t u = u0 + tid;
     if (u < E) g[SVX_DEPOSIT(u)] = sv_tile[p_thr ^ svz12(u0)];
   }

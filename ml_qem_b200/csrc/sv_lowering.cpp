@@ -423,6 +423,52 @@ struct Planner {
     return w;
   }
 
+  static bool is_diag_kind(uint8_t k) { return k == SVO_D1 || k == SVO_D2 || k == SVO_DZZ; }
+  std::vector<HOp> merge_diagonal_runs(const HPass& p, int* n_pre) {
+    std::vector<HOp> outv;
+    *n_pre = 0;
+    bool seen_non_diag = false;
+    for (size_t i = 0; i < p.ops.size();) {
+      if (!is_diag_kind(p.ops[i].kind) || p.ops[i].cond_q >= 0) { outv.push_back(p.ops[i++]); seen_non_diag = true; continue; }
+      size_t j = i;
+      while (j < p.ops.size() && is_diag_kind(p.ops[j].kind) && p.ops[j].cond_q < 0) ++j;
+      const size_t first = outv.size();
+      std::vector<ZzLayer> groups;
+      std::vector<HOp> singles;  // the original op of a group's first bond
+      for (size_t k = i; k < j; ++k) {
+        const HOp& o = p.ops[k];
+        bool zz = false;
+        if (o.kind == SVO_D2) {
+          const cd* ph = reinterpret_cast<const cd*>(&mats[o.off]);
+          zz = ph[0] == ph[3] && ph[1] == ph[2];
+          if (zz) {
+            size_t gi = 0;
+            for (; gi < groups.size(); ++gi) {
+              bool dup = false;
+              for (auto& pr : groups[gi].pairs) dup = dup || (pr.first == o.qa && pr.second == o.qb) || (pr.first == o.qb && pr.second == o.qa);
+              if (!dup && groups[gi].pe == ph[0] && groups[gi].po == ph[1] && groups[gi].pairs.size() < 62) break;
+            }
+            if (gi == groups.size()) { groups.push_back(ZzLayer()); groups[gi].pe = ph[0]; groups[gi].po = ph[1]; singles.push_back(o); }
+            groups[gi].pairs.push_back({o.qa, o.qb});
+          }
+        }
+        if (!zz) outv.push_back(o);
+      }
+      for (size_t gi = 0; gi < groups.size(); ++gi) {
+        if (groups[gi].pairs.size() == 1) { outv.push_back(singles[gi]); continue; }
+        HOp op;
+        op.kind = SVO_DZZ;
+        op.off = (int32_t)zz_layers.size();
+        zz_layers.push_back(groups[gi]);
+        outv.push_back(op);
+      }
+      if (!seen_non_diag) *n_pre = (int)outv.size();
+      (void)first;
+      i = j;
+    }
+    return outv;
+  }
+
   void emit_sweep(const std::vector<int>& sel_in, std::vector<char>& in_tile) {
     std::vector<int> sel(sel_in);
     int nt = 0;
@@ -485,15 +531,21 @@ struct Planner {
         last_direct = true;
       }
     }
+    // diagonal runs of a pass: ZZ-type bonds with one phase pair that landed in the same run become
+    // one fused-layer op (with n_global > 0 the planner keeps the bonds separate so that the light
+    // cone of a global qubit stays narrow; they are fused here, where they meet)
+    std::vector<std::vector<HOp>> mops(sel.size());
+    std::vector<int> m_pre(sel.size(), 0);
+    for (size_t k = 0; k < sel.size(); ++k) mops[k] = merge_diagonal_runs(passes[sel[k]], &m_pre[k]);
     size_t n_ops = 0;
-    for (int i : sel) n_ops += passes[i].ops.size();
+    for (size_t k = 0; k < sel.size(); ++k) n_ops += mops[k].size();
     auto al16 = [](size_t x) { return (x + 15) & ~size_t(15); };
     const size_t o_pass = sizeof(BlockHdr);
     const size_t o_ops = al16(o_pass + sizeof(SvPassHdr) * sel.size());
     size_t o_par = al16(o_ops + sizeof(SvBlockOp) * n_ops);
     size_t bytes = o_par;
-    for (int i : sel)
-      for (const HOp& o : passes[i].ops)
+    for (size_t k = 0; k < sel.size(); ++k)
+      for (const HOp& o : mops[k])
         bytes += o.kind == SVO_DZZ ? al16(8 * zz_params(zz_layers[o.off]).size()) : al16(8 * (size_t)op_words(o.kind));
     const size_t blk_begin = out->prog.size();
     out->prog.resize(blk_begin + bytes / 8, 0);
@@ -509,7 +561,7 @@ struct Planner {
       if (k == 0 && first_direct) ph[k].flags |= kPassLoadDirect;
       if (k + 1 == sel.size() && last_direct) ph[k].flags |= kPassStoreDirect;
       ph[k].ops_q8 = (uint16_t)((o_ops + sizeof(SvBlockOp) * oc) / 8);
-      ph[k].n_ops = (uint16_t)p.ops.size();
+      ph[k].n_ops = (uint16_t)mops[k].size();
       // slot -> physical position: low slots are their own position, free slots come from the sweep
       for (int i = 0; i < 4; ++i) {
         ph[k].s[i] = ts[i];
@@ -523,11 +575,11 @@ struct Planner {
       }
       ph[k].sig = SVS_GENERIC;
       if (p.fast) {
-        ph[k].n_pre = (uint8_t)p.n_pre;
+        ph[k].n_pre = (uint8_t)m_pre[k];
         ph[k].sig = p.n_slot == 0 ? SVS_DIAG
                   : (uint8_t)((p.slot_kind == SVO_X1 ? SVS_X1 : p.slot_kind == SVO_R1 ? SVS_R1 : SVS_U1) + (p.n_slot - 1));
       }
-      for (const HOp& o : p.ops) {
+      for (const HOp& o : mops[k]) {
         SvBlockOp& d = bo[oc++];
         d.kind = o.kind;
         d.flags = 0;
@@ -740,7 +792,11 @@ void lower_svx_circuit(const bwq_batch& b, int c, const SvxOptions& opt, SvxProg
   Planner P;
   P.out = out;
   P.direct_passes = opt.direct != 0 && std::getenv("BWQ_SVX_NO_DIRECT") == nullptr;  // env: kernel experiments
-  P.fuse_layers = std::getenv("BWQ_SVX_NO_FUSE") == nullptr;
+  // whole-layer fusion makes every qubit of the layer wait for the layer: right on one GPU (one
+  // table lookup per amplitude and layer), wrong when amplitudes are sharded -- a global qubit would
+  // need an exchange per Trotter layer instead of one per light cone; there the bonds stay separate
+  // and are fused pass by pass at emission (merge_diagonal_runs)
+  P.fuse_layers = std::getenv("BWQ_SVX_NO_FUSE") == nullptr && gl == 0;
   P.structured = std::getenv("BWQ_SVX_NO_STRUCT") == nullptr;
   P.n = n; P.g = gl; P.nl = n - gl;
   P.K = std::min(std::min(std::max(opt.tile_bits, 4), kSvTileBitsMax), P.nl);

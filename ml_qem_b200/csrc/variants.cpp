@@ -14,8 +14,11 @@
 //           twirl 0 of n_twirls == 0 means "no twirling"
 //   fold  : every 2-qubit gate G -> G (G^dagger G)^((f-1)/2) between the twirl Paulis; self-inverse
 //           gates repeat f times, rotations negate their angle, cu3 / unitary2 invert explicitly
+#include <algorithm>
+#include <atomic>
 #include <cmath>
 #include <cstring>
+#include <thread>
 
 #include "program.h"
 
@@ -42,13 +45,27 @@ static inline void cx_conjugate(int pc, int pt, int* qc, int* qt) {
   *qt = code[sx[pt] ^ sx[pc]][sz[pt]];
 }
 
-int expand_variants(const bwq_batch& b, const bwq_variants& v, ExpandedBatch* out) {
+// Two passes over the base circuits, both parallel over circuits (threads): (1) sizes of every
+// variant (ops, inverse parameters), (2) fill at the offsets the prefix sums give.
+template <class F> static void par_for(int n, int threads, F f) {
+  threads = std::max(1, std::min(threads, n));
+  if (threads == 1) { for (int i = 0; i < n; ++i) f(i); return; }
+  std::atomic<int> next(0);
+  std::vector<std::thread> pool;
+  for (int t = 0; t < threads; ++t)
+    pool.emplace_back([&] { for (;;) { int i = next.fetch_add(8); if (i >= n) break; for (int j = i; j < std::min(n, i + 8); ++j) f(j); } });
+  for (auto& th : pool) th.join();
+}
+
+int expand_variants(const bwq_batch& b, const bwq_variants& v, ExpandedBatch* out, int threads) {
   const int n_folds = v.n_folds > 0 ? v.n_folds : 1;
   const int n_tw = v.n_twirls > 0 ? v.n_twirls : 1;
   const bool twirl = v.n_twirls > 0;
+  int max_fac = 1;
   for (int f = 0; f < n_folds; ++f) {
     const int fac = v.n_folds > 0 ? v.folds[f] : 1;
     if (fac < 1 || fac % 2 == 0) return BWQ_ERR_ARG;  // local folding: odd factors
+    max_fac = std::max(max_fac, fac);
   }
   const int n_var = n_folds * n_tw;
   const int64_t N = (int64_t)b.n_circuits * n_var;
@@ -58,77 +75,144 @@ int expand_variants(const bwq_batch& b, const bwq_variants& v, ExpandedBatch* ou
   out->op_offsets.assign(N + 1, 0);
   out->obs_offsets.assign(N + 1, 0);
   out->status.assign(b.n_circuits, 0);
-  out->params.assign(b.params, b.params + b.n_params);
-  const uint32_t pi_idx = (uint32_t)out->params.size();
-  out->params.push_back(M_PI);
-  out->ops.clear();
-  out->term_offsets.assign(1, 0);
-  out->term_x.clear(); out->term_z.clear(); out->term_coeff.clear();
-  auto pauli = [&](int p, uint8_t q) {
-    if (p == 2 || p == 3) out->ops.push_back(bwq_op{BWQ_G_RZ, q, 0, pi_idx});
-    if (p == 1 || p == 2) out->ops.push_back(bwq_op{BWQ_G_X, q, 0, 0});
+  static const int pauli_ops[4] = {0, 1, 2, 1};  // gates a Pauli costs: I -, X x, Y rz x, Z rz
+  auto inverse_params = [](uint16_t opc) {       // parameters the inverse gate appends (-1: no rule)
+    switch (opc) {
+      case BWQ_G_CX: case BWQ_G_CY: case BWQ_G_CZ: case BWQ_G_CH: case BWQ_G_SWAP: case BWQ_G_ECR: return 0;
+      case BWQ_G_CRX: case BWQ_G_CRY: case BWQ_G_CRZ: case BWQ_G_CP:
+      case BWQ_G_RZZ: case BWQ_G_RXX: case BWQ_G_RYY: case BWQ_G_RZX: return 1;
+      case BWQ_G_CU3: return 3;
+      case BWQ_G_UNITARY2: return 32;
+      default: return -1;
+    }
   };
-  for (int c = 0; c < b.n_circuits; ++c) {
+  // ---- pass 1: ops per variant, inverse parameters per base circuit (shared by its variants)
+  std::vector<int64_t> inv_cnt(b.n_circuits + 1, 0);
+  par_for(b.n_circuits, threads, [&](int c) {
     const int64_t g0 = b.op_offsets[c], g1 = b.op_offsets[c + 1];
-    const int64_t o0 = b.obs_offsets[c], o1 = b.obs_offsets[c + 1];
+    int64_t n1 = 0, n2 = 0, ninv = 0;
+    for (int64_t g = g0; g < g1; ++g) {
+      const bwq_op& op = b.ops[g];
+      if (!gate_is_2q(op.opcode)) { ++n1; continue; }
+      ++n2;
+      if (max_fac > 1) {
+        const int k = inverse_params(op.opcode);
+        if (k < 0 || (int64_t)op.param_idx + k > b.n_params) out->status[c] = BWQ_CIRC_BAD_OP;
+        else ninv += k;
+      }
+    }
+    inv_cnt[c + 1] = ninv;
     for (int f = 0; f < n_folds; ++f) {
       const int fac = v.n_folds > 0 ? v.folds[f] : 1;
       for (int t = 0; t < n_tw; ++t) {
-        const int64_t vi = (int64_t)c * n_var + (int64_t)f * n_tw + t;
-        out->n_qubits[vi] = b.n_qubits[c];
-        uint64_t k_cx = 0;
-        for (int64_t g = g0; g < g1; ++g) {
-          const bwq_op op = b.ops[g];
-          if (!gate_is_2q(op.opcode)) { out->ops.push_back(op); continue; }
-          int pc = 0, pt = 0, qc = 0, qt = 0;
-          if (twirl && op.opcode == BWQ_G_CX) {
+        int64_t extra = 0;
+        if (twirl) {
+          uint64_t k_cx = 0;
+          for (int64_t g = g0; g < g1; ++g) {
+            if (b.ops[g].opcode != BWQ_G_CX) continue;
             const uint32_t d = twirl_draw(v.seed, (uint64_t)c, (uint64_t)t, k_cx++);
-            pc = (int)(d & 3u); pt = (int)(d >> 2);
-            cx_conjugate(pc, pt, &qc, &qt);
-            pauli(pc, op.q0); pauli(pt, op.q1);
+            int qc, qt;
+            cx_conjugate((int)(d & 3u), (int)(d >> 2), &qc, &qt);
+            extra += pauli_ops[d & 3u] + pauli_ops[d >> 2] + pauli_ops[qc] + pauli_ops[qt];
           }
-          // G (G^dagger G)^((fac-1)/2)
-          bwq_op inv = op;
-          if (fac > 1) {
-            switch (op.opcode) {
-              case BWQ_G_CX: case BWQ_G_CY: case BWQ_G_CZ: case BWQ_G_CH: case BWQ_G_SWAP: case BWQ_G_ECR: break;
-              case BWQ_G_CRX: case BWQ_G_CRY: case BWQ_G_CRZ: case BWQ_G_CP:
-              case BWQ_G_RZZ: case BWQ_G_RXX: case BWQ_G_RYY: case BWQ_G_RZX: {
-                if ((int64_t)op.param_idx + 1 > b.n_params) { out->status[c] = BWQ_CIRC_BAD_OP; break; }
-                inv.param_idx = (uint32_t)out->params.size();
-                out->params.push_back(-b.params[op.param_idx]);
-                break; }
-              case BWQ_G_CU3: {  // u3(t, p, l)^-1 = u3(-t, -l, -p)
-                if ((int64_t)op.param_idx + 3 > b.n_params) { out->status[c] = BWQ_CIRC_BAD_OP; break; }
-                inv.param_idx = (uint32_t)out->params.size();
-                const double* p = b.params + op.param_idx;
-                out->params.push_back(-p[0]); out->params.push_back(-p[2]); out->params.push_back(-p[1]);
-                break; }
-              case BWQ_G_UNITARY2: {
-                if ((int64_t)op.param_idx + 32 > b.n_params) { out->status[c] = BWQ_CIRC_BAD_OP; break; }
-                inv.param_idx = (uint32_t)out->params.size();
-                const double* p = b.params + op.param_idx;
-                for (int r = 0; r < 4; ++r)
-                  for (int cc = 0; cc < 4; ++cc) { out->params.push_back(p[2 * (cc * 4 + r)]); out->params.push_back(-p[2 * (cc * 4 + r) + 1]); }
-                break; }
-              default: out->status[c] = BWQ_CIRC_BAD_OP; break;  // no inverse rule (iswap)
-            }
-          }
-          for (int r = 0; r < fac; ++r) out->ops.push_back((r & 1) ? inv : op);
-          if (twirl && op.opcode == BWQ_G_CX) { pauli(qc, op.q0); pauli(qt, op.q1); }
         }
-        out->op_offsets[vi + 1] = (int64_t)out->ops.size();
-        // observables of the base circuit, replicated
-        for (int64_t o = o0; o < o1; ++o) {
-          for (int64_t tt = b.term_offsets[o]; tt < b.term_offsets[o + 1]; ++tt) {
-            out->term_x.push_back(b.term_x[tt]); out->term_z.push_back(b.term_z[tt]); out->term_coeff.push_back(b.term_coeff[tt]);
-          }
-          out->term_offsets.push_back((int64_t)out->term_x.size());
-        }
-        out->obs_offsets[vi + 1] = out->obs_offsets[vi] + (o1 - o0);
+        out->op_offsets[(int64_t)c * n_var + (int64_t)f * n_tw + t + 1] = n1 + n2 * fac + extra;
       }
     }
+  });
+  for (int64_t i = 0; i < N; ++i) out->op_offsets[i + 1] += out->op_offsets[i];
+  for (int c = 0; c < b.n_circuits; ++c) inv_cnt[c + 1] += inv_cnt[c];
+  const int64_t n_par_total = b.n_params + 1 + inv_cnt[b.n_circuits];
+  if (n_par_total >= (int64_t(1) << 32)) return BWQ_ERR_ARG;
+  out->params.resize((size_t)n_par_total);
+  if (b.n_params) std::memcpy(out->params.data(), b.params, sizeof(double) * (size_t)b.n_params);
+  const uint32_t pi_idx = (uint32_t)b.n_params;
+  out->params[pi_idx] = M_PI;
+  out->ops.resize((size_t)out->op_offsets[N]);
+  // observables replicated per variant
+  {
+    std::vector<int64_t> tcount(b.n_circuits + 1, 0);
+    for (int c = 0; c < b.n_circuits; ++c) {
+      const int64_t o0 = b.obs_offsets[c], o1 = b.obs_offsets[c + 1];
+      tcount[c + 1] = tcount[c] + (b.term_offsets[o1] - b.term_offsets[o0]) * n_var;
+      for (int k = 0; k < n_var; ++k) out->obs_offsets[(int64_t)c * n_var + k + 1] = o1 - o0;
+    }
+    for (int64_t i = 0; i < N; ++i) out->obs_offsets[i + 1] += out->obs_offsets[i];
+    out->term_offsets.assign((size_t)out->obs_offsets[N] + 1, 0);
+    out->term_x.resize((size_t)tcount[b.n_circuits]);
+    out->term_z.resize((size_t)tcount[b.n_circuits]);
+    out->term_coeff.resize((size_t)tcount[b.n_circuits]);
+    par_for(b.n_circuits, threads, [&](int c) {
+      const int64_t o0 = b.obs_offsets[c], o1 = b.obs_offsets[c + 1];
+      const int64_t t0 = b.term_offsets[o0], nt = b.term_offsets[o1] - t0;
+      for (int k = 0; k < n_var; ++k) {
+        const int64_t dst = tcount[c] + (int64_t)k * nt;
+        if (nt) {
+          std::memcpy(&out->term_x[dst], b.term_x + t0, sizeof(uint64_t) * nt);
+          std::memcpy(&out->term_z[dst], b.term_z + t0, sizeof(uint64_t) * nt);
+          std::memcpy(&out->term_coeff[dst], b.term_coeff + t0, sizeof(double) * nt);
+        }
+        const int64_t ob = out->obs_offsets[(int64_t)c * n_var + k];
+        for (int64_t o = o0; o < o1; ++o) out->term_offsets[ob + (o - o0) + 1] = dst + (b.term_offsets[o + 1] - t0);
+      }
+    });
   }
+  // ---- pass 2: fill
+  par_for(b.n_circuits, threads, [&](int c) {
+    const int64_t g0 = b.op_offsets[c], g1 = b.op_offsets[c + 1];
+    // inverse parameters of this circuit's parametrised 2-qubit gates (only when some factor > 1)
+    std::vector<uint32_t> inv_idx;
+    if (max_fac > 1 && !out->status[c]) {
+      int64_t cur = b.n_params + 1 + inv_cnt[c];
+      for (int64_t g = g0; g < g1; ++g) {
+        const bwq_op& op = b.ops[g];
+        if (!gate_is_2q(op.opcode)) continue;
+        const int k = inverse_params(op.opcode);
+        inv_idx.push_back(k > 0 ? (uint32_t)cur : op.param_idx);
+        const double* p = b.params + op.param_idx;
+        double* q = out->params.data() + cur;
+        if (k == 1) q[0] = -p[0];
+        else if (k == 3) { q[0] = -p[0]; q[1] = -p[2]; q[2] = -p[1]; }  // u3(t, p, l)^-1 = u3(-t, -l, -p)
+        else if (k == 32)
+          for (int r = 0; r < 4; ++r)
+            for (int cc = 0; cc < 4; ++cc) { q[2 * (r * 4 + cc)] = p[2 * (cc * 4 + r)]; q[2 * (r * 4 + cc) + 1] = -p[2 * (cc * 4 + r) + 1]; }
+        cur += std::max(k, 0);
+      }
+    }
+    for (int f = 0; f < n_folds; ++f) {
+      const int fac = out->status[c] ? 1 : (v.n_folds > 0 ? v.folds[f] : 1);
+      for (int t = 0; t < n_tw; ++t) {
+        const int64_t vi = (int64_t)c * n_var + (int64_t)f * n_tw + t;
+        out->n_qubits[vi] = b.n_qubits[c];
+        bwq_op* w = out->ops.data() + out->op_offsets[vi];
+        bwq_op* const w_end = out->ops.data() + out->op_offsets[vi + 1];
+        auto pauli = [&](int p, uint8_t q) {
+          if (p == 2 || p == 3) *w++ = bwq_op{BWQ_G_RZ, q, 0, pi_idx};
+          if (p == 1 || p == 2) *w++ = bwq_op{BWQ_G_X, q, 0, 0};
+        };
+        uint64_t k_cx = 0;
+        size_t k2 = 0;
+        for (int64_t g = g0; g < g1; ++g) {
+          const bwq_op op = b.ops[g];
+          if (!gate_is_2q(op.opcode)) { *w++ = op; continue; }
+          int qc = 0, qt = 0;
+          const bool tw = twirl && op.opcode == BWQ_G_CX;
+          if (tw) {
+            const uint32_t d = twirl_draw(v.seed, (uint64_t)c, (uint64_t)t, k_cx++);
+            cx_conjugate((int)(d & 3u), (int)(d >> 2), &qc, &qt);
+            pauli((int)(d & 3u), op.q0); pauli((int)(d >> 2), op.q1);
+          }
+          bwq_op inv = op;  // G (G^dagger G)^((fac-1)/2)
+          if (!inv_idx.empty()) inv.param_idx = inv_idx[k2];
+          ++k2;
+          for (int r = 0; r < fac; ++r) *w++ = (r & 1) ? inv : op;
+          if (tw) { pauli(qc, op.q0); pauli(qt, op.q1); }
+        }
+        // a circuit whose folds are impossible (status set) keeps factor 1; pad what pass 1 reserved
+        while (w < w_end) *w++ = bwq_op{BWQ_G_ID, 0, 0, 0};
+      }
+    }
+  });
   if (out->params.size() >= (size_t(1) << 32)) return BWQ_ERR_ARG;
   out->view.n_circuits = (int32_t)N;
   out->view.n_qubits = out->n_qubits.data();

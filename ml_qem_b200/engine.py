@@ -249,9 +249,9 @@ def encode_batch(circuits, observables):
         n_qubits.append(circ.num_qubits)
         op_cnt.append(len(o))
         opc.append(o); q0s.append(a); q1s.append(b); npars.append(k); params.append(p)
-        key = id(obs_list)
+        key = tuple(map(id, obs_list))  # the same observable objects in the same order
         conv = obs_cache.get(key)
-        if conv is None or conv[0] is not obs_list:
+        if conv is None:
             obs_conv = [observable_mod.from_any(ob) for ob in obs_list]
             masks = [ob.masks() for ob in obs_conv]
             conv = (obs_list, obs_conv,

@@ -136,7 +136,9 @@ class B200Estimator:
                 observables and isinstance(observables[0], tuple) and isinstance(observables[0][0], str)):
             observables = [observables]
         circuits = tuple(circuits)
-        observables = tuple(observable_mod.from_any(o) for o in observables)
+        # the same observable / circuit objects usually repeat over the pairs: convert and inspect once
+        conv = {}
+        observables = tuple(conv[id(o)] if id(o) in conv else conv.setdefault(id(o), observable_mod.from_any(o)) for o in observables)
         if parameter_values is None:
             parameter_values = [()] * len(circuits)
         else:
@@ -148,11 +150,14 @@ class B200Estimator:
             raise ValueError(f"The number of circuits ({len(circuits)}) does not match the number of observables ({len(observables)}).")
         if len(circuits) != len(parameter_values):
             raise ValueError(f"The number of circuits ({len(circuits)}) does not match the number of parameter value sets ({len(parameter_values)}).")
+        shape = {}  # id(circuit) -> (number of parameters, number of qubits)
         for i, (c, o, pv) in enumerate(zip(circuits, observables, parameter_values)):
-            npar = getattr(c, "num_parameters", 0) if not isinstance(c, str) else 0
+            if id(c) not in shape:
+                shape[id(c)] = ((getattr(c, "num_parameters", 0), c.num_qubits) if not isinstance(c, str)
+                                else (0, circuit_mod.from_any(c).num_qubits))
+            npar, nq = shape[id(c)]
             if len(pv) != npar:
                 raise ValueError(f"The number of values ({len(pv)}) does not match the number of parameters ({npar}) for the {i}-th circuit.")
-            nq = c.num_qubits if not isinstance(c, str) else circuit_mod.from_any(c).num_qubits
             if len(o) and o.num_qubits != nq:
                 raise ValueError(f"The number of qubits of the {i}-th circuit ({nq}) does not match the number of qubits of the {i}-th observable ({o.num_qubits}).")
         opts = dict(self._options)
@@ -194,9 +199,16 @@ class B200Estimator:
             groups[keys[key]].append(i)
         # complex coefficients (Aer returns np.real_if_close of the complex sum): the C ABI takes
         # real coefficients, so such an observable is evaluated as <Re O> + i <Im O>
-        cplx = [i for i, o in enumerate(observables) if o.is_complex()]
-        obs_lists = [[observables[i].real_part() if observables[i].is_complex() else observables[i] for i in g] +
-                     [observables[i].imag_part() for i in g if observables[i].is_complex()] for g in groups]
+        is_cplx = {}
+        for o in observables:
+            if id(o) not in is_cplx:
+                is_cplx[id(o)] = o.is_complex()
+        cplx = [i for i, o in enumerate(observables) if is_cplx[id(o)]]
+        if cplx:
+            obs_lists = [[observables[i].real_part() if is_cplx[id(observables[i])] else observables[i] for i in g] +
+                         [observables[i].imag_part() for i in g if is_cplx[id(observables[i])]] for g in groups]
+        else:
+            obs_lists = [[observables[i] for i in g] for g in groups]
         batch = encode_batch(bound, obs_lists)
         eng = self._engine_handle()
         noisy = self._noise is not None and not self._noise.is_ideal()
@@ -216,7 +228,7 @@ class B200Estimator:
                     out[i] = vals[k]
                     k += 1
                 for i in g:
-                    if observables[i].is_complex():
+                    if cplx and is_cplx[id(observables[i])]:
                         out[i] += 1j * vals[k]
                         k += 1
             return out

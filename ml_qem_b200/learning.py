@@ -71,6 +71,31 @@ class EmptyProcessor(LearningMethodEstimatorProcessor):
         return np.asarray(values)
 
 
+class ZNEProcessor(LearningMethodEstimatorProcessor):
+    """estimator.py:33-86: the post-processed value is the zero-noise extrapolation of the SAME circuit,
+    obtained from a second estimator call with a ``zne_strategy`` (the reference: ``zne(BackendEstimator)``
+    from prototype-zne; here any estimator of this package -- the folded variants run as one GPU batch).
+    The reference transpiles the circuit for the backend and pads the observable to its five physical
+    qubits for a 2-qubit measurement (estimator.py:52-80); circuits and observables are taken on the
+    register they are given on here (skip_transpile semantics), so that step is the caller's.
+    ``shots`` is accepted for signature compatibility: the engine is exact (shots=None)."""
+
+    def __init__(self, zne_estimator, zne_strategy, backend=None, shots=None):
+        self._zne_estimator = zne_estimator
+        self._zne_strategy = zne_strategy
+        self._backend = backend
+        self._shots = shots
+
+    def process(self, expectation_value, circuits, observables, parameter_values):
+        job = self._zne_estimator.run(_bind(circuits, parameter_values), observables, zne_strategy=self._zne_strategy)
+        return job.result().values[0]
+
+    def process_batch(self, expectation_values, circuits, observables, parameter_values):
+        """One estimator call for the whole job (the reference loops over the items, one ZNE job each)."""
+        bound = [_bind(c, p) for c, p in zip(circuits, parameter_values)]
+        return np.asarray(self._zne_estimator.run(bound, list(observables), zne_strategy=self._zne_strategy).result().values)
+
+
 class _ModelProcessor(LearningMethodEstimatorProcessor):
     """Feature row per (circuit, Pauli term): the observable's noisy value is the single
     expectation feature and the term (coefficient 1) the measurement basis; the prediction is

@@ -174,3 +174,59 @@ def test_twirled_batch_on_gpu_averages_to_the_untwirled_value_without_coherent_n
     avg = Z.average_twirls(v_tw, 16, 4)
     v0, _ = eng.run_dm(base)
     assert np.max(np.abs(avg - v0)) < 0.05
+
+
+def test_ngem_consumer_passes_metadata_through(lib):
+    """ngem(B200Estimator, model, backend) (blackwater/library/ngem/estimator.py:137-158): the wrapped
+    ``_run`` is called with keyword arguments, the job's values are the GNN's predictions on the
+    engine's noisy values, and ``result.metadata`` of the base estimator is passed through (:86)."""
+    import torch
+
+    from ml_qem_b200 import features as FT, gnn
+
+    lima, ideal, noisy = _pair(lib)
+    props = FT.backend_properties_v1(lima)
+    circs = [F.tfim_circuit(4, s, 0.2 * s, layout=[0, 1, 3, 4], num_physical=5) for s in (1, 2, 3)]
+    obs = ["IIIIZ", "ZIIII", [("IIIZI", 1.0)]]
+    nf = len(FT.circuit_to_graph_data_json(circs[0], props, use_qubit_features=True, use_gate_features=True)["nodes"]["DAGOpNode"][0])
+    torch.manual_seed(0)
+    model = gnn.ExpValCircuitGraphModel(num_node_features=nf, hidden_channels=6, exp_value_size=1, dropout=0.0)
+    NgemEstimator = gnn.ngem(B200Estimator, model, lima)
+    est = NgemEstimator(backend=lima)
+    job = est.run(circs, obs)
+    res = job.result()
+    base = noisy.run(circs, obs).result()
+    assert res.values.shape == (3,) and len(res.metadata) == 3
+    assert res.metadata == base.metadata and "NgemJob" in repr(job)
+    # the model saw the engine's noisy values: recompute the prediction of circuit 1 by hand
+    g = FT.circuit_to_graph_data_json(circs[1], props, use_qubit_features=True, use_gate_features=True)
+    e = FT.ExpValueEntry(circuit_graph=g, observable=[], ideal_exp_value=0.0, noisy_exp_values=[float(base.values[1])])
+    b = gnn.graph_batch([e])
+    model.eval()
+    with torch.no_grad():
+        want = float(model(b["noisy_0"], b["observable"], b["circuit_depth"], b["x"], b["edge_index"], b["batch"], 1)[0, 0])
+    assert abs(res.values[1] - want) < 1e-5
+
+
+def test_zne_processor_in_the_learning_decorator(lib):
+    """learning(B200Estimator, ZNEProcessor(zne estimator, strategy)) (blackwater/library/learning/
+    estimator.py:33-86, 300-328): values = zero-noise extrapolation of the folded circuits, metadata
+    keeps the unmitigated ``original_value``."""
+    from ml_qem_b200 import learning, zne
+
+    lima, ideal, noisy = _pair(lib)
+    strategy = zne.ZNEStrategy(noise_factors=(1, 3), extrapolator=zne.PolynomialExtrapolator(degree=1))
+    proc = learning.ZNEProcessor(zne.zne(B200Estimator)(backend=lima), strategy, backend=lima)
+    est = learning.learning(B200Estimator, proc, backend=lima)(backend=lima)
+    circs = [F.tfim_circuit(4, 2, 0.3, layout=[0, 1, 3, 4], num_physical=5), F.tfim_circuit(4, 3, 0.7, layout=[0, 1, 3, 4], num_physical=5, basis="X")]
+    obs = ["IIIIZ", [("ZIIIZ", 0.5), ("IIIZI", 1.0)]]
+    res = est.run(circs, obs).result()
+    on = helpers.oracle_noise("fakelima")
+    for k, (c, o) in enumerate(zip(circs, obs)):
+        ob = [(o, 1.0)] if isinstance(o, str) else o
+        v1 = helpers.oracle_dm_values(c, [ob], on)[0]
+        c3 = F.tfim_circuit(4, 2 + k, 0.3 if k == 0 else 0.7, layout=[0, 1, 3, 4], num_physical=5, basis="Z" if k == 0 else "X", fold=3)
+        v3 = helpers.oracle_dm_values(c3, [ob], on)[0]
+        assert abs(res.values[k] - (1.5 * v1 - 0.5 * v3)) <= 1e-9
+        assert abs(res.metadata[k]["original_value"] - v1) <= TOL
+    assert abs(proc.process(0.0, circs[0], obs[0], ()) - res.values[0]) <= 1e-12
