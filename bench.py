@@ -194,6 +194,7 @@ def cpu_reference_rate(workload_name, budget_s=15.0, max_circuits=512, wl=None, 
     cores = host_threads()
     # size the sample: time one circuit, then as many as fit the budget
     fb1 = engine.encode_batch(wl["circuits"][:1], wl["observables"][:1])
+    cpu_ref.prepare(fb1)  # gate matrices from oracle/gates.py: data preparation, not part of the timed simulation
     t = time.perf_counter()
     cpu_ref.run_dm(fb1, onoise, threads=cores)
     cpu_ref.run_sv(fb1, threads=cores)
@@ -205,6 +206,7 @@ def cpu_reference_rate(workload_name, budget_s=15.0, max_circuits=512, wl=None, 
     if first is not None:
         n = min(n, first)
     fb = engine.encode_batch(wl["circuits"][:n], wl["observables"][:n])
+    cpu_ref.prepare(fb)
     reps, dt = 0, 0.0
     while True:  # small circuits: repeat the sample until it amounts to ~10 s of CPU work
         t = time.perf_counter()
@@ -356,6 +358,7 @@ def bench_sharded_sv(ctx, name, steps, warmup, first_trotter=1, cpu_check=True, 
         m = 22
         c_small = [F.tfim_circuit(m, trot[i], Js[i], dt=0.25) for i in range(min(2, steps))]
         fb = engine.encode_batch(c_small, [F.tfim_observables(list(range(m)), m)] * len(c_small))
+        cpu_ref.prepare(fb)
         cores = host_threads()
         t = time.perf_counter()
         ref, st = cpu_ref.run_sv(fb, threads=cores)

@@ -295,3 +295,61 @@ def load_entries(path, num_samples=None):
 def save_entries(path, entries):
     with open(path, "w") as f:
         json.dump([e.to_dict() for e in entries], f)
+
+
+# ----------------------------------------------------------------------------- batched, from the flat gate stream
+def encode_data_flat(batch, properties, ideal_exp_vals, noisy_exp_vals, num_qubits, meas_bases=None, device=None):
+    """``encode_data`` for a whole FlatBatch at once, computed from the flat gate stream the engine
+    consumes (no per-circuit objects, no Python loop over gates): gate counts by a scatter-add over
+    (circuit, opcode), the 40 rotation-angle bins by one ``searchsorted``.  ``noisy_exp_vals`` /
+    ``ideal_exp_vals`` may be torch tensors that already live on ``device`` (the engine's
+    ``run_dm_into`` output): they are placed into X / y without a host round trip.  Same X, y as
+    ``encode_data`` on the same circuits (tests/test_features.py)."""
+    import torch
+
+    from .gateset import NAMES, OPCODES
+
+    gates_set = sorted(properties["gates_set"])
+    vec = [_mean_of(properties, t1, t2) for t1, t2 in (("cx", "gate_error"), ("id", "gate_error"), ("sx", "gate_error"),
+                                                       ("x", "gate_error"), ("rz", "gate_error"))]
+    vec += [_mean_of(properties, "", k) for k in ("readout_error", "t1", "t2")]
+    n = batch.n_circuits
+    nv, ng = len(vec), len(gates_set)
+    bin_size = 0.1 * np.pi
+    n_bins = int(np.ceil(4 * np.pi / bin_size))
+    edges = np.arange(-2 * np.pi, 2 * np.pi + bin_size, bin_size)
+    nb = meas_bases if meas_bases is not None else [[]]
+    width = nv + ng + n_bins + num_qubits + len(nb[0])
+    X = np.zeros((n, width), dtype=np.float32)
+    X[:, :nv] = (torch.tensor(vec) * 100).numpy()[None, :]
+    ops = batch.ops
+    circ_of = np.repeat(np.arange(n), np.diff(batch.op_offsets))
+    # gate counts: opcode -> column of the sorted gates_set (names the backend does not list are not counted)
+    col_of = np.full(max(NAMES) + 1, -1, dtype=np.int64)
+    for j, g in enumerate(gates_set):
+        code = OPCODES.get(canonical(g))
+        if code is not None:
+            col_of[code] = j
+    cols = col_of[ops["opcode"]]
+    keep = cols >= 0
+    counts = np.zeros((n, ng))
+    np.add.at(counts, (circ_of[keep], cols[keep]), 1.0)
+    X[:, nv:nv + ng] = (torch.tensor(counts) * 0.01).to(torch.float32).numpy()
+    # rotation angles of rx / ry / rz
+    rot = np.isin(ops["opcode"], [OPCODES["rx"], OPCODES["ry"], OPCODES["rz"]])
+    ang = batch.params[ops["param_idx"][rot].astype(np.int64)]
+    idx = np.searchsorted(edges, ang, side="right") - 1
+    idx[ang == edges[-1]] = len(edges) - 2           # numpy.histogram: the last bin is closed
+    ok = (idx >= 0) & (idx < min(n_bins, len(edges) - 1))
+    hist = np.zeros((n, n_bins))
+    np.add.at(hist, (circ_of[rot][ok], idx[ok]), 1.0)
+    X[:, nv + ng:nv + ng + n_bins] = (torch.tensor(hist) * 0.01).to(torch.float32).numpy()
+    Xt = torch.from_numpy(X)
+    if device is not None:
+        Xt = Xt.to(device)
+    noisy = noisy_exp_vals if torch.is_tensor(noisy_exp_vals) else torch.tensor(np.asarray(noisy_exp_vals, dtype=np.float64))
+    Xt[:, nv + ng + n_bins:nv + ng + n_bins + num_qubits] = noisy.reshape(n, num_qubits).to(Xt.device, torch.float32)
+    if meas_bases is not None:
+        Xt[:, nv + ng + n_bins + num_qubits:] = torch.tensor(meas_bases, dtype=torch.float32).to(Xt.device)
+    ideal = ideal_exp_vals if torch.is_tensor(ideal_exp_vals) else torch.tensor(np.asarray(ideal_exp_vals, dtype=np.float64))
+    return Xt, ideal.to(Xt.device, torch.float32)

@@ -42,80 +42,28 @@ namespace {
 
 bool is2q(uint16_t op) { return (op >= BWQ_G_CX && op <= BWQ_G_ECR) || op == BWQ_G_UNITARY2; }
 
-void u3m(double th, double ph, double la, cd* m) {
-  double c = std::cos(th / 2), s = std::sin(th / 2);
-  m[0] = c; m[1] = -std::exp(I_ * la) * s; m[2] = std::exp(I_ * ph) * s; m[3] = std::exp(I_ * (ph + la)) * c;
-}
+// Gate matrices are DATA here: oracle/cpu_ref.py evaluates oracle/gates.py (the numpy restatement of
+// Qiskit's standard gates) for every op of the batch and hands the table over, so this file shares
+// no gate library with the product (ml_qem_b200/csrc/lowering.cpp) -- a wrong matrix there cannot be
+// common-mode here.  Entry g: 4 (1-qubit) or 16 (2-qubit) complex numbers, row-major, local index
+// i_q0 + 2 i_q1; reset has no matrix (its superoperator is built below).
+struct GateTable {
+  const double* mats = nullptr;   // interleaved re/im
+  const int64_t* off = nullptr;   // per op of the batch: offset in complex numbers, -1 = unsupported
+};
+const GateTable* g_tab = nullptr;  // set for the duration of one cpuref_*_run call (calls are not re-entrant)
 
-bool unitary1(uint16_t op, const double* p, cd* m) {
-  const double r = std::sqrt(0.5);
-  switch (op) {
-    case BWQ_G_ID: m[0] = 1; m[1] = 0; m[2] = 0; m[3] = 1; return true;
-    case BWQ_G_X: m[0] = 0; m[1] = 1; m[2] = 1; m[3] = 0; return true;
-    case BWQ_G_Y: m[0] = 0; m[1] = -I_; m[2] = I_; m[3] = 0; return true;
-    case BWQ_G_Z: m[0] = 1; m[1] = 0; m[2] = 0; m[3] = -1; return true;
-    case BWQ_G_H: m[0] = r; m[1] = r; m[2] = r; m[3] = -r; return true;
-    case BWQ_G_S: m[0] = 1; m[1] = 0; m[2] = 0; m[3] = I_; return true;
-    case BWQ_G_SDG: m[0] = 1; m[1] = 0; m[2] = 0; m[3] = -I_; return true;
-    case BWQ_G_T: m[0] = 1; m[1] = 0; m[2] = 0; m[3] = std::exp(I_ * (M_PI / 4)); return true;
-    case BWQ_G_TDG: m[0] = 1; m[1] = 0; m[2] = 0; m[3] = std::exp(-I_ * (M_PI / 4)); return true;
-    case BWQ_G_SX: m[0] = cd(.5, .5); m[1] = cd(.5, -.5); m[2] = cd(.5, -.5); m[3] = cd(.5, .5); return true;
-    case BWQ_G_SXDG: m[0] = cd(.5, -.5); m[1] = cd(.5, .5); m[2] = cd(.5, .5); m[3] = cd(.5, -.5); return true;
-    case BWQ_G_RX: { double c = std::cos(p[0] / 2), s = std::sin(p[0] / 2); m[0] = c; m[1] = -I_ * s; m[2] = -I_ * s; m[3] = c; return true; }
-    case BWQ_G_RY: { double c = std::cos(p[0] / 2), s = std::sin(p[0] / 2); m[0] = c; m[1] = -s; m[2] = s; m[3] = c; return true; }
-    case BWQ_G_RZ: m[0] = std::exp(-I_ * (p[0] / 2)); m[1] = 0; m[2] = 0; m[3] = std::exp(I_ * (p[0] / 2)); return true;
-    case BWQ_G_P: m[0] = 1; m[1] = 0; m[2] = 0; m[3] = std::exp(I_ * p[0]); return true;
-    case BWQ_G_U2: u3m(M_PI / 2, p[0], p[1], m); return true;
-    case BWQ_G_U3: u3m(p[0], p[1], p[2], m); return true;
-    case BWQ_G_UNITARY1: for (int i = 0; i < 4; ++i) m[i] = cd(p[2 * i], p[2 * i + 1]); return true;
-    default: return false;
-  }
+bool unitary1(int64_t g, cd* m) {
+  if (!g_tab || !g_tab->off || g_tab->off[g] < 0) return false;
+  const double* p = g_tab->mats + 2 * g_tab->off[g];
+  for (int i = 0; i < 4; ++i) m[i] = cd(p[2 * i], p[2 * i + 1]);
+  return true;
 }
-
-void controlled(const cd* u, cd* m) {
-  for (int i = 0; i < 16; ++i) m[i] = 0;
-  m[0] = 1; m[10] = 1;
-  for (int tr = 0; tr < 2; ++tr) for (int tc = 0; tc < 2; ++tc) m[(1 + 2 * tr) * 4 + (1 + 2 * tc)] = u[tr * 2 + tc];
-}
-
-void pauli_rot2(int a, int b, double th, cd* m) {
-  static const cd P[4][4] = {{1, 0, 0, 1}, {0, 1, 1, 0}, {0, cd(0, -1), cd(0, 1), 0}, {1, 0, 0, -1}};
-  double c = std::cos(th / 2), s = std::sin(th / 2);
-  for (int r0 = 0; r0 < 2; ++r0) for (int r1 = 0; r1 < 2; ++r1) for (int c0 = 0; c0 < 2; ++c0) for (int c1 = 0; c1 < 2; ++c1) {
-    cd pp = P[a][r0 * 2 + c0] * P[b][r1 * 2 + c1];
-    cd id = (r0 == c0 && r1 == c1) ? 1.0 : 0.0;
-    m[(r0 + 2 * r1) * 4 + (c0 + 2 * c1)] = c * id - I_ * s * pp;
-  }
-}
-
-bool unitary2(uint16_t op, const double* p, cd* m) {
-  cd u[4];
-  static const uint16_t base[] = {BWQ_G_X, BWQ_G_Y, BWQ_G_Z, BWQ_G_H, BWQ_G_RX, BWQ_G_RY, BWQ_G_RZ, BWQ_G_P, BWQ_G_U3};
-  if (op >= BWQ_G_CX && op <= BWQ_G_CU3) { unitary1(base[op - BWQ_G_CX], p, u); controlled(u, m); return true; }
-  switch (op) {
-    case BWQ_G_SWAP: for (int i = 0; i < 16; ++i) m[i] = 0; m[0] = 1; m[6] = 1; m[9] = 1; m[15] = 1; return true;
-    case BWQ_G_ISWAP: for (int i = 0; i < 16; ++i) m[i] = 0; m[0] = 1; m[6] = I_; m[9] = I_; m[15] = 1; return true;
-    case BWQ_G_RZZ: pauli_rot2(3, 3, p[0], m); return true;
-    case BWQ_G_RXX: pauli_rot2(1, 1, p[0], m); return true;
-    case BWQ_G_RYY: pauli_rot2(2, 2, p[0], m); return true;
-    case BWQ_G_RZX: pauli_rot2(3, 1, p[0], m); return true;
-    case BWQ_G_ECR: { const double r = std::sqrt(0.5); const cd e[16] = {0, 1, 0, I_, 1, 0, -I_, 0, 0, I_, 0, 1, -I_, 0, 1, 0};
-      for (int i = 0; i < 16; ++i) m[i] = r * e[i]; return true; }
-    case BWQ_G_UNITARY2: for (int i = 0; i < 16; ++i) m[i] = cd(p[2 * i], p[2 * i + 1]); return true;
-    default: return false;
-  }
-}
-
-int nparams(uint16_t op) {
-  switch (op) {
-    case BWQ_G_RX: case BWQ_G_RY: case BWQ_G_RZ: case BWQ_G_P: case BWQ_G_CRX: case BWQ_G_CRY: case BWQ_G_CRZ:
-    case BWQ_G_CP: case BWQ_G_RZZ: case BWQ_G_RXX: case BWQ_G_RYY: case BWQ_G_RZX: return 1;
-    case BWQ_G_U2: return 2;
-    case BWQ_G_U3: case BWQ_G_CU3: return 3;
-    case BWQ_G_UNITARY1: return 8;
-    case BWQ_G_UNITARY2: return 32;
-    default: return 0;
-  }
+bool unitary2(int64_t g, cd* m) {
+  if (!g_tab || !g_tab->off || g_tab->off[g] < 0) return false;
+  const double* p = g_tab->mats + 2 * g_tab->off[g];
+  for (int i = 0; i < 16; ++i) m[i] = cd(p[2 * i], p[2 * i + 1]);
+  return true;
 }
 
 // ---- generic k-"bit" matrix application on a 2^N vector (bits ascending order in `bits`)
@@ -290,7 +238,6 @@ int dm_circuit(const bwq_batch& b, int c, const cpuref_noise* noise, double* out
   };
   for (int64_t g = b.op_offsets[c]; g < b.op_offsets[c + 1]; ++g) {
     const bwq_op& op = b.ops[g];
-    const double* par_p = nparams(op.opcode) ? b.params + op.param_idx : nullptr;
     if (!is2q(op.opcode)) {
       const int q = cq.pos[op.q0];
       cd s4[16];
@@ -300,7 +247,7 @@ int dm_circuit(const bwq_batch& b, int c, const cpuref_noise* noise, double* out
         s4[0] = 1; s4[3] = 1; have_s4 = true;
       }
       cd u[4];
-      if (!have_s4 && !unitary1(op.opcode, par_p, u)) return BWQ_CIRC_BAD_OP;
+      if (!have_s4 && !unitary1(g, u)) return BWQ_CIRC_BAD_OP;
       const cd* ns = nl.find(op.opcode, op.q0, 255);
       if (fuse && f.active && (q == f.a || q == f.b)) {
         if (!have_s4) superop_from_unitary(u, 2, s4);
@@ -326,7 +273,7 @@ int dm_circuit(const bwq_batch& b, int c, const cpuref_noise* noise, double* out
     const cd* ns = nl.find(op.opcode, op.q0, op.q1);
     if (fuse) {
       cd u[16], s[256];
-      if (!unitary2(op.opcode, par_p, u)) return BWQ_CIRC_BAD_OP;
+      if (!unitary2(g, u)) return BWQ_CIRC_BAD_OP;
       superop_from_unitary(u, 4, s);
       fuse_2q(q0, q1, s);
       if (ns) fuse_2q(q0, q1, ns);
@@ -337,7 +284,7 @@ int dm_circuit(const bwq_batch& b, int c, const cpuref_noise* noise, double* out
       apply_cx_bits(v.data(), nbits, q0 + n, q1 + n, par);
     } else {
       cd u[16], s[256];
-      if (!unitary2(op.opcode, par_p, u)) return BWQ_CIRC_BAD_OP;
+      if (!unitary2(g, u)) return BWQ_CIRC_BAD_OP;
       superop_from_unitary(u, 4, s);
       int bits[4] = {q0, q1, q0 + n, q1 + n};
       apply_matrix(v.data(), nbits, bits, 4, s, par);
@@ -386,10 +333,9 @@ int sv_circuit(const bwq_batch& b, int c, double* out, bool par) {
   v[0] = 1;
   for (int64_t g = b.op_offsets[c]; g < b.op_offsets[c + 1]; ++g) {
     const bwq_op& op = b.ops[g];
-    const double* par_p = nparams(op.opcode) ? b.params + op.param_idx : nullptr;
     if (!is2q(op.opcode)) {
       cd u[4];
-      if (op.opcode == BWQ_G_RESET || !unitary1(op.opcode, par_p, u)) return BWQ_CIRC_BAD_OP;
+      if (op.opcode == BWQ_G_RESET || !unitary1(g, u)) return BWQ_CIRC_BAD_OP;
       int bits[1] = {cq.pos[op.q0]};
       if (op.opcode == BWQ_G_X) apply_x_bit(v.data(), n, bits[0], par);
       else if (u[1] == cd(0) && u[2] == cd(0)) apply_diag1(v.data(), n, bits[0], u[0], u[3], par);
@@ -398,7 +344,7 @@ int sv_circuit(const bwq_batch& b, int c, double* out, bool par) {
       apply_cx_bits(v.data(), n, cq.pos[op.q0], cq.pos[op.q1], par);
     } else {
       cd u[16];
-      if (!unitary2(op.opcode, par_p, u)) return BWQ_CIRC_BAD_OP;
+      if (!unitary2(g, u)) return BWQ_CIRC_BAD_OP;
       int bits[2] = {cq.pos[op.q0], cq.pos[op.q1]};
       apply_matrix(v.data(), n, bits, 2, u, par);
     }
@@ -441,8 +387,10 @@ extern "C" {
 
 // threads <= 0 -> omp_get_max_threads().  amplitude_parallel_qubits: states with at least this many
 // active qubits are parallelised over amplitudes, smaller ones over circuits (Aer: experiments).
-int cpuref_dm_run(const bwq_batch* b, const cpuref_noise* noise, double* out, int32_t* status, int threads,
-                  int amplitude_parallel_qubits, int fusion_threshold) {
+int cpuref_dm_run(const bwq_batch* b, const cpuref_noise* noise, const double* gate_mats, const int64_t* gate_off, double* out,
+                  int32_t* status, int threads, int amplitude_parallel_qubits, int fusion_threshold) {
+  const GateTable tab{gate_mats, gate_off};
+  g_tab = &tab;
   if (threads <= 0) threads = omp_get_max_threads();
   omp_set_num_threads(threads);
   if (amplitude_parallel_qubits <= 0) amplitude_parallel_qubits = 7;
@@ -452,10 +400,14 @@ int cpuref_dm_run(const bwq_batch* b, const cpuref_noise* noise, double* out, in
 #pragma omp parallel for schedule(dynamic, 1)
   for (size_t i = 0; i < small.size(); ++i) status[small[i]] = dm_circuit(*b, small[i], noise, out, false, fusion_threshold);
   for (int c : big) status[c] = dm_circuit(*b, c, noise, out, true, fusion_threshold);
+  g_tab = nullptr;
   return 0;
 }
 
-int cpuref_sv_run(const bwq_batch* b, double* out, int32_t* status, int threads, int amplitude_parallel_qubits) {
+int cpuref_sv_run(const bwq_batch* b, const double* gate_mats, const int64_t* gate_off, double* out, int32_t* status, int threads,
+                  int amplitude_parallel_qubits) {
+  const GateTable tab{gate_mats, gate_off};
+  g_tab = &tab;
   if (threads <= 0) threads = omp_get_max_threads();
   omp_set_num_threads(threads);
   if (amplitude_parallel_qubits <= 0) amplitude_parallel_qubits = 14;
@@ -464,6 +416,7 @@ int cpuref_sv_run(const bwq_batch* b, double* out, int32_t* status, int threads,
 #pragma omp parallel for schedule(dynamic, 1)
   for (size_t i = 0; i < small.size(); ++i) status[small[i]] = sv_circuit(*b, small[i], out, false);
   for (int c : big) status[c] = sv_circuit(*b, c, out, true);
+  g_tab = nullptr;
   return 0;
 }
 

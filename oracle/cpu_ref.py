@@ -74,8 +74,66 @@ def noise_arrays(model, opcodes):
     return keep
 
 
+_NAMES = None
+_NPAR = None
+
+
+def gate_table(fb):
+    """Matrix of every op of the batch from oracle/gates.py (memoised per (gate, parameters)):
+    -> (mats complex128 [total], off int64 [n_ops], -1 for reset / unsupported).  This is the ONLY gate
+    library of the CPU restatement: the C++ side has none (no code shared with the product)."""
+    global _NAMES, _NPAR
+    from . import gates as G
+
+    if _NAMES is None:
+        from ml_qem_b200.gateset import NAMES, NUM_PARAMS  # opcode <-> name of the C ABI (include/bwq.h), data only
+
+        _NAMES = dict(NAMES)
+        _NPAR = {code: NUM_PARAMS.get(name, 0) for code, name in NAMES.items()}
+    ops = fb.ops
+    off = np.full(len(ops), -1, dtype=np.int64)
+    cache, chunks, pos = {}, [], 0
+    opcodes, pidx, params = ops["opcode"].tolist(), ops["param_idx"].tolist(), fb.params
+    for g, (code, pi) in enumerate(zip(opcodes, pidx)):
+        k = _NPAR.get(code, 0)
+        key = (code, params[pi:pi + k].tobytes() if k else b"")
+        hit = cache.get(key)
+        if hit is None:
+            name = _NAMES.get(code)
+            p = params[pi:pi + k]
+            if name is None or name == "reset":
+                hit = -1
+            else:
+                if name == "unitary1":
+                    m = (p[0::2] + 1j * p[1::2]).reshape(2, 2)
+                elif name == "unitary2":
+                    m = (p[0::2] + 1j * p[1::2]).reshape(4, 4)
+                else:
+                    m = G.gate_matrix(name, p)
+                chunks.append(np.ascontiguousarray(m, dtype=np.complex128).reshape(-1))
+                hit = pos
+                pos += m.size
+            cache[key] = hit
+        off[g] = hit
+    mats = np.concatenate(chunks) if chunks else np.zeros(0, dtype=np.complex128)
+    return mats, off
+
+
+def prepare(fb):
+    """gate_table(fb), cached on the batch object (the table is not part of the timed region)."""
+    tab = getattr(fb, "_cpuref_gates", None)
+    if tab is None:
+        tab = gate_table(fb)
+        try:
+            fb._cpuref_gates = tab
+        except AttributeError:
+            pass
+    return tab
+
+
 def run_dm(fb, noise_keep, threads=0, amplitude_parallel_qubits=0, fusion_threshold=0):
     lib = load()
+    mats, goff = prepare(fb)
     out = np.zeros(fb.n_observables, dtype=np.float64)
     status = np.zeros(fb.n_circuits, dtype=np.int32)
     bs = _batch_struct(fb)
@@ -83,7 +141,7 @@ def run_dm(fb, noise_keep, threads=0, amplitude_parallel_qubits=0, fusion_thresh
     if noise_keep is not None and len(noise_keep["opcode"]):
         ns = _Noise(len(noise_keep["opcode"]), _p(noise_keep["opcode"]), _p(noise_keep["q0"]), _p(noise_keep["q1"]),
                     _p(noise_keep["data_off"]), _p(noise_keep["data"]))
-    lib.cpuref_dm_run(C.byref(bs), C.byref(ns) if ns is not None else None, _p(out), _p(status), int(threads),
+    lib.cpuref_dm_run(C.byref(bs), C.byref(ns) if ns is not None else None, _p(mats), _p(goff), _p(out), _p(status), int(threads),
                       int(amplitude_parallel_qubits), int(fusion_threshold))
     return out, status
 
@@ -93,7 +151,8 @@ def run_sv(fb, threads=0, amplitude_parallel_qubits=0):
     out = np.zeros(fb.n_observables, dtype=np.float64)
     status = np.zeros(fb.n_circuits, dtype=np.int32)
     bs = _batch_struct(fb)
-    lib.cpuref_sv_run(C.byref(bs), _p(out), _p(status), int(threads), int(amplitude_parallel_qubits))
+    mats, goff = prepare(fb)
+    lib.cpuref_sv_run(C.byref(bs), _p(mats), _p(goff), _p(out), _p(status), int(threads), int(amplitude_parallel_qubits))
     return out, status
 
 

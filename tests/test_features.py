@@ -110,3 +110,61 @@ def test_exp_value_entry_round_trip(tmp_path):
     t = e.to_tensors()
     assert t["x"].shape[1] == 22 and t["edge_index"].shape[0] == 2 and t["edge_attr"].shape[1] == 3
     assert t["y"].shape == (1, 1) and float(t["noisy_1"]) == pytest.approx(0.3) and float(t["circuit_depth"]) == 7.0
+
+
+def test_encode_data_flat_equals_encode_data():
+    """Batched feature rows from the flat gate stream == the reference-pinned per-circuit encoder."""
+    from ml_qem_b200 import engine, families as F
+
+    lima = backends.fake_lima()
+    props = FT.backend_properties_v1(lima)
+    rng = np.random.default_rng(3)
+    circs = [F.tfim_circuit(4, 1 + i % 4, float(rng.uniform(0, 1)), layout=[0, 1, 3, 4], num_physical=5, basis="XYZ"[i % 3]) for i in range(7)]
+    circs.append(F.random_basis_circuit(5, 60, rng, lima.coupling_map))
+    c = Circuit(5); c.append("rz", (1,), (2 * np.pi,)); c.append("rz", (2,), (-2 * np.pi,)); c.append("rz", (0,), (7.0,)); c.append("reset", (3,))
+    circs.append(c)  # angles on the outer bin edges and outside the histogram range
+    n = len(circs)
+    ideal = rng.uniform(-1, 1, size=(n, 4)).tolist()
+    noisy = rng.uniform(-1, 1, size=(n, 4)).tolist()
+    bases = [[1, 0, 0, 0] * 4 for _ in range(n)]
+    obs = [F.single_z_observables([0, 1, 3, 4], 5)] * n
+    fb = engine.encode_batch(circs, obs)
+    X, y = FT.encode_data(circs, props, ideal, noisy, 4, meas_bases=bases)
+    Xf, yf = FT.encode_data_flat(fb, props, ideal, noisy, 4, meas_bases=bases)
+    assert Xf.shape == X.shape and torch.allclose(Xf, X, atol=1e-7) and torch.equal(yf, y)
+    X1, _ = FT.encode_data(circs, props, ideal, noisy, 4)
+    X1f, _ = FT.encode_data_flat(fb, props, torch.tensor(ideal), torch.tensor(noisy, dtype=torch.float64), 4)
+    assert torch.allclose(X1f, X1, atol=1e-7)
+
+
+def test_sharded_dataset_resume(tmp_path):
+    """Chunked generation: one binary shard per chunk, a crashed run resumes at the first missing chunk."""
+    from ml_qem_b200 import dataset, families as F
+
+    rng = np.random.default_rng(0)
+    circs = [F.tfim_circuit(3, 1 + i % 3, float(rng.uniform(0, 1))) for i in range(11)]
+    obs = [F.single_z_observables([0, 1, 2], 3)] * len(circs)
+    calls = []
+
+    def evaluate(fb):
+        calls.append(fb.n_circuits)
+        if len(calls) == 3 and crash[0]:
+            raise RuntimeError("simulated crash")
+        v = np.arange(fb.n_observables, dtype=float) + 100 * len(calls)
+        return v, -v
+
+    crash = [True]
+    out = str(tmp_path / "ds")
+    with pytest.raises(RuntimeError):
+        dataset.generate(circs, obs, evaluate, out, chunk_size=4)
+    assert sorted(f for f in os.listdir(out) if f.startswith("chunk_")) == ["chunk_00000.npz", "chunk_00001.npz"]
+    crash[0] = False
+    calls.clear()
+    m = dataset.generate(circs, obs, evaluate, out, chunk_size=4)
+    assert calls == [3] and [s["reused"] for s in m["shards"]] == [True, True, False]
+    d = dataset.load(out)
+    assert d["ideal"].shape == (33,) and np.array_equal(d["noisy"], -d["ideal"]) and d["obs_offsets"][-1] == 33
+    fb1 = dataset.shard_batch(out, 1)
+    assert fb1.n_circuits == 4 and fb1.n_observables == 12
+    t = dataset.load(out, as_torch=True)
+    assert t["ideal"].dtype == torch.float64
