@@ -219,7 +219,8 @@ typedef struct bwq_program bwq_program;
 /* Lowers batch circuit `circuit` to its sweep program.  tile_qubits/low_qubits as in options. */
 int bwq_lower_dm(const bwq_noise_table* table, const bwq_batch* batch, int32_t circuit,
                  int32_t tile_qubits, int32_t low_qubits, bwq_program** out);
-/* Same with planner flags: bit 1 = direct last-pass stores in the TMA layout; bit 0 = emit the TMA tile layout (what bwq_dm_run does by default for
+/* Same with planner flags: bits 8..15 = ZNE noise factor (the fold-aware lowering bwq_*_variants uses for
+ * cx-only circuits: gates lowered once, cx ops repeated); bit 1 = direct last-pass stores in the TMA layout; bit 0 = emit the TMA tile layout (what bwq_dm_run does by default for
  * circuits wider than the tile; see ml_qem_b200/csrc/program.h). */
 int bwq_lower_dm_ex(const bwq_noise_table* table, const bwq_batch* batch, int32_t circuit,
                     int32_t tile_qubits, int32_t low_qubits, int32_t flags, bwq_program** out);

@@ -6,6 +6,7 @@
 #include <cstdarg>
 #include <cstdio>
 #include <cstdlib>
+#include <cmath>
 #include <cstring>
 #include <numeric>
 #include <string>
@@ -376,8 +377,16 @@ template <bool FULL> static cudaError_t launch_sweep_kq(int kq, const DmLaunch& 
 // Host part: lowers circuits [c0, c1) of the batch into slot `sl` (program blob in pinned memory,
 // chunk plan).  Output indices are relative to the first observable of c0.  Touches only the slot,
 // so it may run on a helper thread while the GPU executes the other slot.
+// The batch is the expansion of `base` into n_folds fold variants per circuit (variant-major inside a
+// circuit, no twirls): circuit i of the batch = base circuit i / n_folds at factor folds[i % n_folds].
+struct FoldInfo {
+  const bwq_batch* base;
+  const int32_t* folds;
+  int n_folds;
+};
+
 static int dm_lower_impl(bwq_ctx* ctx, bwq_ctx::DmSlot& sl, const bwq_batch* b, int c0, int c1, int32_t* out_status,
-                         int64_t budget) {
+                         int64_t budget, const FoldInfo* fi = nullptr) {
   DmPlan& P = sl.plan;
   P = DmPlan();
   const int N = c1 - c0;
@@ -397,7 +406,17 @@ static int dm_lower_impl(bwq_ctx* ctx, bwq_ctx::DmSlot& sl, const bwq_batch* b, 
   lo.tma_direct_store = (ctx->opt.flags & BWQ_OPT_TMA_DIRECT_STORE) != 0;
   P.tile_qubits = lo.tile_qubits;
   std::vector<CircuitProgram> progs(N);  // progs[c] <-> batch circuit c0 + c
-  parallel_for(N, host_threads(ctx), [&](int c) { lower_dm_circuit(ctx->noise, *b, c0 + c, lo, &progs[c]); });
+  if (fi && fi->n_folds > 0 && c0 % fi->n_folds == 0 && N % fi->n_folds == 0) {
+    // fold variants: the gates of a base circuit are lowered once, every fold re-packs the passes
+    const int nf = fi->n_folds;
+    parallel_for(N / nf, host_threads(ctx), [&](int k) {
+      const int base = c0 / nf + k;
+      if (!lower_dm_circuit_folds(ctx->noise, *fi->base, base, lo, fi->folds, nf, &progs[(size_t)k * nf]))
+        for (int f = 0; f < nf; ++f) lower_dm_circuit(ctx->noise, *b, c0 + k * nf + f, lo, &progs[(size_t)k * nf + f]);
+    });
+  } else {
+    parallel_for(N, host_threads(ctx), [&](int c) { lower_dm_circuit(ctx->noise, *b, c0 + c, lo, &progs[c]); });
+  }
 
   std::vector<int> order;
   order.reserve(N);
@@ -789,7 +808,8 @@ extern "C" int bwq_dm_execute_device_out(bwq_ctx* ctx, double* d_out_vals) { ret
 // and software-pipelined over the two program slots: while the GPU sweeps segment k, the host
 // threads lower segment k+1 (K0 is otherwise 20-25 % of the call for 10-qubit circuits).  The
 // values do not depend on the segmentation (circuits are independent).
-static int dm_run_impl(bwq_ctx* ctx, const bwq_batch* b, double* out_vals, int32_t* out_status, bool out_on_device) {
+static int dm_run_impl(bwq_ctx* ctx, const bwq_batch* b, double* out_vals, int32_t* out_status, bool out_on_device,
+                       const FoldInfo* fi = nullptr) {
   if (!ctx) return BWQ_ERR_ARG;
   int rc = check_batch(ctx, b, out_status, out_status);
   if (rc) return rc;
@@ -819,9 +839,10 @@ static int dm_run_impl(bwq_ctx* ctx, const bwq_batch* b, double* out_vals, int32
     }
     if (est_bytes < 2e10) n_seg = 1;  // < ~5 ms of sweeps
   }
-  auto seg_begin = [&](int k) { return (int)((int64_t)N * k / n_seg); };
+  const int unit = fi && fi->n_folds > 0 && N % fi->n_folds == 0 ? fi->n_folds : 1;  // the variants of a circuit stay in one segment
+  auto seg_begin = [&](int k) { return (int)((int64_t)(N / unit) * k / n_seg) * unit; };
   if (n_seg == 1) {
-    if ((rc = dm_lower_impl(ctx, ctx->dm[0], b, 0, N, out_status, budget))) return rc;
+    if ((rc = dm_lower_impl(ctx, ctx->dm[0], b, 0, N, out_status, budget, fi))) return rc;
     if (N > 0 && (rc = dm_upload_impl(ctx, ctx->dm[0], true))) return rc;
     return dm_execute_impl(ctx, ctx->dm[0], out_vals, out_on_device);
   }
@@ -836,7 +857,7 @@ static int dm_run_impl(bwq_ctx* ctx, const bwq_batch* b, double* out_vals, int32
   }
   bwq_stats total{};
   std::vector<std::pair<int64_t, double>> fixes;
-  if ((rc = dm_lower_impl(ctx, ctx->dm[0], b, seg_begin(0), seg_begin(1), out_status, budget))) return rc;
+  if ((rc = dm_lower_impl(ctx, ctx->dm[0], b, seg_begin(0), seg_begin(1), out_status, budget, fi))) return rc;
   CK(cudaEventRecord(ctx->ev[1], st));
   for (int k = 0; k < n_seg; ++k) {
     bwq_ctx::DmSlot& cur = ctx->dm[k & 1];
@@ -847,7 +868,7 @@ static int dm_run_impl(bwq_ctx* ctx, const bwq_batch* b, double* out_vals, int32
         bwq_ctx::DmSlot& nxt = ctx->dm[(k + 1) & 1];
         cudaSetDevice(ctx->device);
         cudaEventSynchronize(nxt.h2d_done);  // the blob of segment k-1 has left the pinned buffer
-        next_rc = dm_lower_impl(ctx, nxt, b, seg_begin(k + 1), seg_begin(k + 2), out_status, budget);
+        next_rc = dm_lower_impl(ctx, nxt, b, seg_begin(k + 1), seg_begin(k + 2), out_status, budget, fi);
       });
     const int64_t obs0 = b->obs_offsets[seg_begin(k)];
     rc = dm_upload_impl(ctx, cur, false);
@@ -1360,12 +1381,18 @@ extern "C" int bwq_meas_data_run_variants(bwq_ctx* ctx, const bwq_batch* b, cons
   std::vector<int32_t> st_var((size_t)X.view.n_circuits);
   const int all_threads = host_threads(ctx), saved_threads = ctx->opt.host_threads;
   ctx->companion->opt = ctx->opt;
-  // host threads in proportion to the circuits each side lowers (ideal: base circuits only)
-  ctx->companion->opt.host_threads = std::max(1, all_threads / (4 * std::max(1, X.n_variants)));
+  // host threads in proportion to the lowering work of each side: the ideal side lowers the base
+  // circuits only; the noisy side every variant (about a third of that per extra fold of a base circuit)
+  {
+    const double sv_work = 16.0 * b->n_circuits;
+    const double dm_work = (v->n_twirls == 0 ? 19.0 + 6.0 * (X.n_variants - 1) : 19.0 * X.n_variants) * b->n_circuits;
+    ctx->companion->opt.host_threads = std::max(1, (int)std::lround(all_threads * sv_work / (sv_work + dm_work)));
+  }
   ctx->opt.host_threads = std::max(1, all_threads - ctx->companion->opt.host_threads);
   int rc_sv = BWQ_OK;
   std::thread ideal([&] { rc_sv = bwq_sv_run(ctx->companion, b, out_ideal, status_ideal); });
-  const int rc_dm = bwq_dm_run(ctx, &X.view, out_noisy, st_var.data());
+  const FoldInfo fi{b, v->folds, v->n_folds};
+  const int rc_dm = dm_run_impl(ctx, &X.view, out_noisy, st_var.data(), false, v->n_twirls == 0 && v->n_folds > 0 ? &fi : nullptr);
   ideal.join();
   ctx->opt.host_threads = saved_threads;
   if (rc_dm) return rc_dm;
@@ -1389,7 +1416,8 @@ extern "C" int bwq_dm_run_variants(bwq_ctx* ctx, const bwq_batch* b, const bwq_v
   ExpandedBatch X;
   if ((rc = expand_variants(*b, *v, &X, host_threads(ctx)))) return fail(ctx, rc, "bad variants descriptor (folds must be odd positive factors)");
   const double expand_ms = now_ms() - t0;
-  if ((rc = bwq_dm_run(ctx, &X.view, out_vals, out_status))) return rc;
+  const FoldInfo fi{b, v->folds, v->n_folds};
+  if ((rc = dm_run_impl(ctx, &X.view, out_vals, out_status, false, v->n_twirls == 0 && v->n_folds > 0 ? &fi : nullptr))) return rc;
   for (int c = 0; c < b->n_circuits; ++c)
     if (X.status[c])
       for (int k = 0; k < X.n_variants; ++k) {
@@ -1436,7 +1464,12 @@ extern "C" int bwq_lower_dm_ex(const bwq_noise_table* table, const bwq_batch* ba
   lo.tma = (flags & 1) != 0;
   lo.tma_direct_store = (flags & 2) != 0;
   bwq_program* p = new bwq_program();
-  lower_dm_circuit(nt, *batch, circuit, lo, &p->p);
+  const int32_t fold = (flags >> 8) & 0xff;  // ZNE noise factor: the fold-aware path of bwq_*_variants
+  if (fold > 1) {
+    if (!lower_dm_circuit_folds(nt, *batch, circuit, lo, &fold, 1, &p->p)) p->p.status = BWQ_CIRC_BAD_OP;
+  } else {
+    lower_dm_circuit(nt, *batch, circuit, lo, &p->p);
+  }
   *out = p;
   return BWQ_OK;
 }

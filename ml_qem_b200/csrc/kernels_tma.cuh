@@ -41,6 +41,9 @@ __device__ __forceinline__ void mbar_init(uint64_t* bar, int count) {
   asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(smem_u32(bar)), "r"(count));
   asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
 }
+__device__ __forceinline__ void mbar_init_n(uint64_t* bar, int count) {
+  asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(smem_u32(bar)), "r"(count));
+}
 __device__ __forceinline__ void mbar_expect_tx(uint64_t* bar, uint32_t bytes) {
   asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(smem_u32(bar)), "r"(bytes) : "memory");
 }
@@ -187,13 +190,15 @@ template <bool NAMED> __device__ __forceinline__ void compute_sync() {
 // returns true when the last pass stored the tile to global memory itself (gtile = the tile's first element)
 template <bool FULL, bool NAMED>
 __device__ __forceinline__ bool run_tma_passes(char* __restrict__ tile_b, const double* __restrict__ pbuf,
-                                               const uint32_t* __restrict__ a_table, const int tid, double* __restrict__ gtile) {
+                                               const uint32_t* __restrict__ a_table, const int tid, double* __restrict__ gtile,
+                                               uint64_t* tile_bar = nullptr) {
   constexpr int T = kTmaThreads;
   const int n_passes = reinterpret_cast<const int*>(pbuf)[0];
   bool stored = false;
   const uint4* const ext = reinterpret_cast<const uint4*>(pbuf) + reinterpret_cast<const int*>(pbuf)[1];
   uint4 hraw = reinterpret_cast<const uint4*>(pbuf)[1];
   uint32_t a_next = __ldg(a_table + (hraw.z & 0xffu) * T + tid);
+  if (tile_bar != nullptr) mbar_wait(tile_bar, 0);  // the tile: its flight covered the header / thread-base lookups
   for (int p = 0; p < n_passes; ++p) {
     if (p) compute_sync<NAMED>();
     const uint4 h = hraw;
@@ -238,7 +243,7 @@ __global__ void __launch_bounds__(kTmaThreads, FULL ? 2 : BWQ_TMA_BLOCKS) dm_swe
   constexpr int KQ = 6, E = 1 << (2 * KQ), T = kTmaThreads;
   __shared__ __align__(1024) double tile[E];
   __shared__ __align__(16) double pbuf[kBlockBytes / 8];
-  __shared__ __align__(8) uint64_t bar;
+  __shared__ __align__(8) uint64_t bar[2];  // [0]: program block landed, [1]: tile landed
   const int tid = threadIdx.x;
   const int tiles_log2 = 2 * (L.n_digits - KQ);
   const uint32_t tile_mask = (1u << tiles_log2) - 1u;
@@ -266,13 +271,20 @@ __global__ void __launch_bounds__(kTmaThreads, FULL ? 2 : BWQ_TMA_BLOCKS) dm_swe
 
   const CUtensorMap* const map = L.maps + map_id * uint32_t(L.n_windows) + (slot >> L.window_log2);
   const int c0 = int(((slot & ((1u << L.window_log2) - 1u)) << (2 * L.n_digits)) + base);
-  if (tid == 0) mbar_init(&bar, 1);
-  __syncthreads();
   if (tid == 0) {
+    // both copies are issued before the CTA-wide barrier that publishes the mbarriers: the loads are
+    // in flight while the other warps arrive; the (small) program block gets its own mbarrier so the
+    // first pass header and thread-base lookup overlap the tile's flight
+    mbar_init_n(&bar[0], 1);
+    mbar_init_n(&bar[1], 1);
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
     const uint32_t blk_bytes = uint32_t(swraw.y & 0xffff) * 16u;
-    mbar_expect_tx(&bar, blk_bytes + (sweep_idx > 0 ? uint32_t(E * 8) : 0u));
-    bulk_load(pbuf, L.prog + uint32_t(swraw.x), blk_bytes, &bar);
-    if (sweep_idx > 0) tma_load_tile(tile, map, &bar, c0);
+    mbar_expect_tx(&bar[0], blk_bytes);
+    bulk_load(pbuf, L.prog + uint32_t(swraw.x), blk_bytes, &bar[0]);
+    if (sweep_idx > 0) {
+      mbar_expect_tx(&bar[1], uint32_t(E * 8));
+      tma_load_tile(tile, map, &bar[1], c0);
+    }
     // L2 prefetch of the tile a later CTA will sweep (CTAs are dispatched in index order)
     if (L.prefetch_dist > 0 && sweep_idx > 0) {
       const uint32_t nb = blockIdx.x + uint32_t(L.prefetch_dist);
@@ -301,10 +313,11 @@ __global__ void __launch_bounds__(kTmaThreads, FULL ? 2 : BWQ_TMA_BLOCKS) dm_swe
       *reinterpret_cast<double2*>(tile_b + 8u * tswz(j)) = make_double2((hi_ok && !d0_is2) ? 1.0 : 0.0, (hi_ok && d0_is2) ? 1.0 : 0.0);
     }
   }
-  mbar_wait(&bar, 0);
-  if (sweep_idx == 0) __syncthreads();
+  __syncthreads();  // mbarrier inits visible; first sweep: the synthesised tile is complete
+  mbar_wait(&bar[0], 0);
 
-  if (run_tma_passes<FULL, false>(tile_b, pbuf, L.a_table, tid, L.states + int64_t(slot) * L.stride + base)) return;
+  if (run_tma_passes<FULL, false>(tile_b, pbuf, L.a_table, tid, L.states + int64_t(slot) * L.stride + base, sweep_idx > 0 ? &bar[1] : nullptr))
+    return;
   // generic-proxy writes -> async proxy, then one thread stores the tile and keeps the CTA (and
   // its shared memory) alive until the bulk store has read it
   asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
@@ -320,9 +333,6 @@ __global__ void __launch_bounds__(kTmaThreads, FULL ? 2 : BWQ_TMA_BLOCKS) dm_swe
 // buffer b have landed (producer arrive.expect_tx + TMA complete_tx); done[b]: the compute warps
 // are through with buffer b (their writes fenced to the async proxy).
 // ---------------------------------------------------------------------------------------------
-__device__ __forceinline__ void mbar_init_n(uint64_t* bar, int count) {
-  asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(smem_u32(bar)), "r"(count));
-}
 __device__ __forceinline__ void mbar_arrive(uint64_t* bar) {
   asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(smem_u32(bar)) : "memory");
 }

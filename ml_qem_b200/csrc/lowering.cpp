@@ -314,6 +314,14 @@ struct HostPass {
   int qa, qb;
   std::vector<MacroOp> ops;
 };
+// Result of the first lowering stage (gates + noise -> register passes), reusable for every ZNE
+// fold of the circuit: a fold only repeats the cx ops inside the passes.
+struct DmStageA {
+  bool valid = false;
+  bool cx_only = true;          // every 2-qubit gate is a cx (self-inverse: folding = repetition)
+  CircuitProgram head;          // active qubits, term indices, matrix scratch, status
+  std::vector<HostPass> passes;
+};
 }  // namespace
 
 static int64_t push_mat(std::vector<double>& mats, const double* m, int n) {
@@ -371,9 +379,77 @@ static PassSig classify_pass(const std::vector<MacroOp>& ops, bool fast_layout) 
   return SIG_GENERIC;
 }
 
+static void lower_dm_impl(const NoiseTable& noise, const bwq_batch& b, int c, const LowerOptions& opt, CircuitProgram* out,
+                          DmStageA* cache, int fold);
+static void lower_dm_gates(const NoiseTable& noise, const bwq_batch& b, int c, CircuitProgram* out, std::vector<HostPass>* passes_out);
+static void pack_dm_passes(const NoiseTable& noise, const LowerOptions& opt, const int nd, std::vector<HostPass>& passes, CircuitProgram* out);
+
 void lower_dm_circuit(const NoiseTable& noise, const bwq_batch& b, int c, const LowerOptions& opt,
                       CircuitProgram* out) {
+  lower_dm_impl(noise, b, c, opt, out, nullptr, 1);
+}
+
+// Programs of circuit c at the noise factors folds[0..n) (local folding of the 2-qubit gates, as
+// LocalFoldingAmplifier(gates_to_fold=2) of docs/tutorials/zne_parallel.py:172-183): the gates are
+// lowered ONCE, every fold re-packs the passes with its cx ops repeated.  Returns false when the
+// circuit has 2-qubit gates other than cx (their folds need inverse gates: lower the expanded
+// gate stream of bwq_variants instead).
+bool lower_dm_circuit_folds(const NoiseTable& noise, const bwq_batch& b, int c, const LowerOptions& opt, const int32_t* folds,
+                            int n_folds, CircuitProgram* outs) {
+  for (int64_t g = b.op_offsets[c]; g < b.op_offsets[c + 1]; ++g)
+    if (gate_is_2q(b.ops[g].opcode) && b.ops[g].opcode != BWQ_G_CX) return false;
+  DmStageA A;
+  for (int f = 0; f < n_folds; ++f) lower_dm_impl(noise, b, c, opt, &outs[f], &A, folds[f]);
+  return true;
+}
+
+static void lower_dm_impl(const NoiseTable& noise, const bwq_batch& b, int c, const LowerOptions& opt, CircuitProgram* out,
+                          DmStageA* cache, int fold) {
   *out = CircuitProgram();
+  std::vector<HostPass> passes;
+  if (cache && cache->valid) {
+    *out = cache->head;
+    passes = cache->passes;
+  } else {
+    lower_dm_gates(noise, b, c, out, &passes);
+    if (cache) { cache->valid = true; cache->head = *out; cache->passes = passes; }
+  }
+  if (out->status) return;
+  if (fold > 1) {  // G -> G (G^dagger G)^((fold-1)/2) = fold copies of the self-inverse cx, each with its error
+    for (HostPass& p : passes) {
+      std::vector<MacroOp> ops;
+      ops.reserve(p.ops.size() * fold);
+      for (size_t i = 0; i < p.ops.size(); ++i) {
+        const MacroOp& o = p.ops[i];
+        ops.push_back(o);
+        if (o.twoq == Q_CXN_AB || o.twoq == Q_CXN_BA) {  // cx fused with its relaxation error
+          MacroOp rep{};
+          rep.twoq = o.twoq; rep.off_2 = o.off_2;
+          for (int r = 1; r < fold; ++r) ops.push_back(rep);
+        } else if (o.twoq == Q_CX_AB || o.twoq == Q_CX_BA) {
+          // bare cx: its error, if any, is the next op (the circuit has no other 2-qubit gates) -- repeat the pair
+          MacroOp rep{};
+          rep.twoq = o.twoq;
+          const bool has_err = i + 1 < p.ops.size() && p.ops[i + 1].pre_a == P_NONE && p.ops[i + 1].pre_b == P_NONE &&
+                               p.ops[i + 1].twoq >= Q_RELAX;
+          if (has_err) ops.push_back(p.ops[i + 1]);
+          for (int r = 1; r < fold; ++r) { ops.push_back(rep); if (has_err) ops.push_back(p.ops[i + 1]); }
+          if (has_err) ++i;
+        }
+      }
+      p.ops.swap(ops);
+    }
+    int64_t n_cx = 0;
+    for (int64_t g = b.op_offsets[c]; g < b.op_offsets[c + 1]; ++g) n_cx += b.ops[g].opcode == BWQ_G_CX;
+    out->n_gates += n_cx * (fold - 1);
+  }
+  const int nd = out->n_digits;
+  pack_dm_passes(noise, opt, nd, passes, out);
+}
+
+// first stage: gates + attached errors -> register passes (and the circuit's digits / Pauli terms)
+static void lower_dm_gates(const NoiseTable& noise, const bwq_batch& b, int c, CircuitProgram* out, std::vector<HostPass>* passes_out) {
+  std::vector<HostPass>& passes = *passes_out;
   const int nq = b.n_qubits[c];
   const int64_t g0 = b.op_offsets[c], g1 = b.op_offsets[c + 1];
   out->n_gates = g1 - g0;
@@ -400,7 +476,6 @@ void lower_dm_circuit(const NoiseTable& noise, const bwq_batch& b, int c, const 
 
   // ---- gates -> passes
   out->mats.reserve((size_t)(g1 - g0) * 6 + 64);
-  std::vector<HostPass> passes;
   passes.reserve(64);
   std::vector<double> pend(16 * nd);
   std::vector<char> has(nd, 0);
@@ -511,6 +586,10 @@ void lower_dm_circuit(const NoiseTable& noise, const bwq_batch& b, int c, const 
     flush(d, passes[last[d]]);
   }
 
+}
+
+// second stage: passes -> sweeps, each one self-contained program block
+static void pack_dm_passes(const NoiseTable& noise, const LowerOptions& opt, const int nd, std::vector<HostPass>& passes, CircuitProgram* out) {
   // ---- parameter sizes (8-byte words) and sources
   auto pre_words = [](uint8_t k) { return k == P_ROT ? 4 : k == P_AFF ? 12 : k == P_DENSE ? 16 : 0; };
   auto two_words = [](uint8_t k) {

@@ -222,6 +222,11 @@ struct LowerOptions {
 void lower_dm_circuit(const NoiseTable& noise, const bwq_batch& b, int c, const LowerOptions& o,
                       CircuitProgram* out);
 
+// Programs of circuit c at the ZNE noise factors folds[0..n): the gates are lowered once.  False when
+// the circuit has 2-qubit gates other than cx (lower the expanded stream of bwq_variants instead).
+bool lower_dm_circuit_folds(const NoiseTable& noise, const bwq_batch& b, int c, const LowerOptions& o, const int32_t* folds,
+                            int n_folds, CircuitProgram* outs);
+
 // ---- statevector lowering --------------------------------------------------------------
 enum SvKind : int32_t { SV_U1 = 0, SV_CX = 1, SV_U2 = 2 };
 struct SvOp {       // 16 B

@@ -501,7 +501,7 @@ def expand_variants(batch, variants):
                      batch.term_x[term_src], batch.term_z[term_src], batch.term_coeff[term_src])
 
 
-def lower_dm(batch, circuit, noise_model=None, tile_qubits=0, low_qubits=0, tma=False, tma_direct_store=False):
+def lower_dm(batch, circuit, noise_model=None, tile_qubits=0, low_qubits=0, tma=False, tma_direct_store=False, fold=1):
     """Host-only view of the lowering stage (no GPU): returns the sweep program of one circuit as a
     dict of numpy arrays (see bwq_program_read in include/bwq.h).  tma=True: the TMA tile layout
     the engine uses by default for circuits wider than the tile."""
@@ -510,7 +510,7 @@ def lower_dm(batch, circuit, noise_model=None, tile_qubits=0, low_qubits=0, tma=
     prog = C.c_void_p()
     bs = batch.c_struct()
     rc = lib.bwq_lower_dm_ex(C.byref(st) if st is not None else None, C.byref(bs), circuit, tile_qubits, low_qubits,
-                             (1 if tma else 0) | (2 if tma_direct_store else 0), C.byref(prog))
+                             (1 if tma else 0) | (2 if tma_direct_store else 0) | (int(fold) << 8), C.byref(prog))
     if rc != 0:
         raise EngineError(f"bwq_lower_dm failed ({rc}): {lib.bwq_last_error(None).decode()}")
     try:

@@ -353,6 +353,11 @@ def test_library_variants_on_gpu_match_python_built_variants(lib):
     assert not st.any() and np.max(np.abs(vals - ref)) <= 1e-12
     on = helpers.oracle_noise("fakelima")
     assert np.max(np.abs(vals[5 * 4:6 * 4] - helpers.oracle_dm_values(ref_circs[5], obs[0], on))) <= TOL
+    # folds only: the fold-aware lowering (gates lowered once per base circuit) == the folded circuits
+    vf = Variants(folds=(1, 3, 5))
+    vals_f, st = eng.run_dm_variants(fb, vf, noise=nm)
+    ref_f = np.stack([eng.run_dm(zne.fold_batch(fb, f), noise=nm)[0].reshape(3, 4) for f in (1, 3, 5)], axis=1)
+    assert not st.any() and np.max(np.abs(vals_f.reshape(3, 3, 4) - ref_f)) <= 1e-13
     ideal, noisy, st_i, st_n = eng.run_meas_data_variants(fb, v, noise=nm)
     assert not st_i.any() and not st_n.any() and np.array_equal(noisy, vals)
     assert np.max(np.abs(ideal - eng.run_sv(fb)[0])) == 0.0

@@ -107,3 +107,34 @@ def test_folding_rules_for_parametrised_two_qubit_gates(lib):
     ex = engine.expand_variants(fb, Variants(folds=(3,)))
     ref = zne.fold_batch(fb, 3)
     assert _gates(ex, 0) == _gates(ref, 0)
+
+
+def test_fold_aware_lowering_equals_lowering_of_the_folded_circuit(lib):
+    """bwq_*_variants lower the gates of a cx-only circuit once and repeat the cx ops per fold: the
+    program must evolve the state exactly like the program of the explicitly folded circuit -- with the
+    fused cx + relaxation error (device model) and with a cx followed by a separate dense error
+    (coherent cx noise), on chip and tiled."""
+    import helpers
+    from program_emulator import run_program
+    from ml_qem_b200 import backends, noise
+
+    lima = backends.fake_lima()
+    models = [noise.from_backend(lima), noise.add_coherent_noise(lima, theta=0.04 * np.pi, seed=0)[0]]
+    c5 = F.tfim_circuit(4, 3, 0.37, basis="Y", layout=[0, 1, 3, 4], num_physical=5, random_init_prefix=True)
+    o5 = F.single_z_observables([0, 1, 3, 4], 5)
+    be8 = backends.synthetic_chain(8, seed=5)
+    c8 = F.brickwork_circuit(8, 2, np.random.default_rng(1), twirl_rng=np.random.default_rng(2))
+    o8 = F.single_z_observables(list(range(8)), 8)
+    for circ, obs, nms, kw in ((c5, o5, models, {}), (c8, o8, [noise.from_backend(be8)], {"tma": True}), (c8, o8, [noise.from_backend(be8)], {})):
+        fb = engine.encode_batch([circ], [obs])
+        for nm in nms:
+            for fold in (3, 5):
+                folded = zne.fold_batch(fb, fold)
+                ref = engine.lower_dm(folded, 0, nm, **kw)
+                got = engine.lower_dm(fb, 0, nm, fold=fold, **kw)
+                assert got["status"] == 0 and got["n_gates"] == ref["n_gates"]
+                assert np.max(np.abs(run_program(got) - run_program(ref))) <= 1e-14
+    # a circuit with another 2-qubit gate has no fold-aware program (the expanded stream is lowered)
+    from ml_qem_b200 import Circuit
+    c = Circuit(3); c.cx(0, 1); c.rzz(0.3, 1, 2)
+    assert engine.lower_dm(engine.encode_batch([c], [[[("ZZZ", 1.0)]]]), 0, None, fold=3)["status"] == 1
