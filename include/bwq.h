@@ -137,6 +137,8 @@ typedef struct {
                                    CTA per tile; measured slower (8 compute warps per SM), kept for A/B */
 #define BWQ_OPT_TMA_DIRECT_STORE 64 /* TMA layout: the last pass of a sweep stores its register groups to global memory
                                    with 16-byte stores instead of scatter + TMA store; measured slower (0.635 vs 0.676), A/B */
+#define BWQ_OPT_NO_ONCHIP 128   /* keep circuits of <= 5 active qubits on the lowering + tile-sweep path instead of
+                                   dm_onchip_kernel (one warp interprets the raw gate stream of a circuit); A/B and parity tests */
 #define BWQ_OPT_NO_TMA 16       /* density matrix: keep circuits wider than the tile on dm_sweep_kernel (LDG/STG tile
                                    movement) instead of dm_sweep_tma_kernel (TMA tensor-map tiles); A/B and parity tests */
 
@@ -155,6 +157,8 @@ typedef struct {
   int64_t sv_state_bytes_swept;/* statevector sweeps: sum of 2 * 16 B * 2^n (+ 16 B * 2^n per
                                   expectation pass) of the last bwq_sv_* call                  */
   int64_t n_tma_sweep_launches;/* of n_sweep_launches: launches of dm_sweep_tma_kernel       */
+  int64_t n_onchip_circuits;   /* (circuit, variant) pairs evolved by dm_onchip_kernel (no lowering,
+                                  no sweeps: n_sweep_launches = 0 then)                        */
 } bwq_stats;
 
 typedef struct bwq_ctx bwq_ctx;

@@ -6,7 +6,7 @@ import sys
 
 HERE = os.path.dirname(os.path.abspath(__file__))
 SRC = [os.path.join(HERE, "csrc", f) for f in ("api.cu", "lowering.cpp", "sv_lowering.cpp", "variants.cpp")]
-HDR = [os.path.join(HERE, "csrc", f) for f in ("kernels.cuh", "kernels_tma.cuh", "sv_kernels.cuh", "program.h")] + [os.path.join(HERE, "..", "include", "bwq.h")]
+HDR = [os.path.join(HERE, "csrc", f) for f in ("kernels.cuh", "kernels_tma.cuh", "onchip.cuh", "sv_kernels.cuh", "program.h")] + [os.path.join(HERE, "..", "include", "bwq.h")]
 OUT = os.path.join(HERE, "lib", "libbwq.so")
 
 

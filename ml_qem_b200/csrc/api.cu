@@ -19,6 +19,7 @@
 #include "kernels.cuh"
 #include "kernels_tma.cuh"
 #include "sv_kernels.cuh"
+#include "onchip.cuh"
 
 using namespace bwq;
 
@@ -163,6 +164,11 @@ struct bwq_ctx {
   SvPlan sv_plan;
   std::vector<cudaEvent_t> chunk_ev;  // begin/end of each chunk's sweep launches
   bwq_ctx* companion = nullptr;       // statevector side of bwq_meas_data_run (created on first use)
+  // dm_onchip_kernel: raw batch blob, result buffers, device copy of the noise lookup tables
+  DevBuf d_oc, d_oc_out, d_oc_noise;
+  PinBuf h_oc, h_oc_out;
+  OnchipNoise oc_noise{};
+  bool oc_noise_valid = false;
   size_t smem_optin = 0;
   int sm_count = 0;
 };
@@ -226,6 +232,8 @@ extern "C" int bwq_create(int device, bwq_ctx** out) {
     return bail(e, "cudaFuncSetAttribute(dm_sweep_kernel<7>) -- was the library built for this GPU (sm_100a)?");
   if ((e = cudaFuncSetAttribute(dm_sweep_kernel<7, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (8 << 14) + kBlockBytes)) != cudaSuccess)
     return bail(e, "cudaFuncSetAttribute(dm_sweep_kernel<7, full>)");
+  if ((e = cudaFuncSetAttribute(dm_onchip_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kOnchipSmem)) != cudaSuccess)
+    return bail(e, "cudaFuncSetAttribute(dm_onchip_kernel)");
   if ((e = cudaFuncSetAttribute(sv_circuit_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 16 << 12)) != cudaSuccess)
     return bail(e, "cudaFuncSetAttribute(sv_circuit_kernel)");
   if ((e = cudaFuncSetAttribute(sv_sweep_kernel<256>, cudaFuncAttributeMaxDynamicSharedMemorySize, (16 << kSvTileBitsMax) + kBlockBytes + 1024)) != cudaSuccess)
@@ -268,6 +276,8 @@ extern "C" int bwq_destroy(bwq_ctx* ctx) {
   ctx->d_b0.release(); ctx->d_noise.release(); ctx->d_states.release(); ctx->d_out.release();
   for (auto& sl : ctx->dm) { sl.d_prog.release(); sl.h_prog.release(); sl.d_maps.release(); sl.h_maps.release(); if (sl.h2d_done) cudaEventDestroy(sl.h2d_done); }
   ctx->d_tma_a.release(); ctx->d_counters.release();
+  ctx->d_oc.release(); ctx->d_oc_out.release(); ctx->d_oc_noise.release(); ctx->h_oc.release(); ctx->h_oc_out.release();
+  if (ctx->companion) bwq_destroy(ctx->companion);
   ctx->d_scratch.release(); ctx->h_out.release();
   ctx->d_sv_prog.release(); ctx->h_sv_prog.release();
   ctx->d_wide_prog.release(); ctx->h_wide_prog.release(); ctx->d_partial.release();
@@ -292,6 +302,7 @@ extern "C" int bwq_set_noise_table(bwq_ctx* ctx, const bwq_noise_table* table) {
   if (!ctx) return BWQ_ERR_ARG;
   char err[256] = {0};
   int rc = ctx->noise.set(table, err, sizeof err);
+  ctx->oc_noise_valid = false;
   if (rc) return fail(ctx, rc, "%s", err);
   CK(cudaSetDevice(ctx->device));
   if (!ctx->noise.data.empty()) {
@@ -808,11 +819,189 @@ extern "C" int bwq_dm_execute_device_out(bwq_ctx* ctx, double* d_out_vals) { ret
 // and software-pipelined over the two program slots: while the GPU sweeps segment k, the host
 // threads lower segment k+1 (K0 is otherwise 20-25 % of the call for 10-qubit circuits).  The
 // values do not depend on the segmentation (circuits are independent).
+// ------------------------------------------------------------------------------------------------
+// on-chip path (onchip.cuh): circuits of at most 5 active qubits whose 2-qubit gates are all cx --
+// one warp interprets the gate stream of one (circuit, variant); the upload is the raw base batch
+// ------------------------------------------------------------------------------------------------
+static int onchip_upload_noise(bwq_ctx* ctx) {
+  if (ctx->oc_noise_valid) return BWQ_OK;
+  ctx->oc_noise = OnchipNoise{};
+  const NoiseTable& nt = ctx->noise;
+  if (!nt.empty()) {
+    const size_t ne = nt.entries.size();
+    Blob blob;
+    const size_t o_g1 = blob.add(sizeof(int32_t) * 33 * 64), o_cx = blob.add(sizeof(int32_t) * 64 * 64);
+    const size_t o_ent = blob.add(sizeof(int2) * ne), o_ok = blob.add(32 * 64), o_fx = blob.add(sizeof(double) * 32 * 64 * 16);
+    std::vector<char> h(blob.total, 0);
+    int32_t* g1 = (int32_t*)(h.data() + o_g1);
+    int32_t* cx = (int32_t*)(h.data() + o_cx);
+    int2* ent = (int2*)(h.data() + o_ent);
+    auto index_of = [&](const NoiseEntry* e) -> int32_t {
+      if (!e) return -1;
+      return (int32_t)(((const char*)e - (const char*)&nt.entries[0].second) / (ptrdiff_t)sizeof(nt.entries[0]));
+    };
+    for (int op = 0; op <= 32; ++op)
+      for (int q = 0; q < 64; ++q) {
+        const uint16_t opc = op < 32 ? (uint16_t)op : (uint16_t)BWQ_G_UNITARY1;
+        const NoiseEntry* e = gate_is_2q(opc) ? nullptr : nt.find(opc, q, 255);
+        g1[op * 64 + q] = (e && e->kind == BWQ_NOISE_DENSE1) ? index_of(e) : -1;
+      }
+    for (int a = 0; a < 64; ++a)
+      for (int t = 0; t < 64; ++t) cx[a * 64 + t] = a == t ? -1 : index_of(nt.find(BWQ_G_CX, a, t));
+    for (size_t i = 0; i < ne; ++i) ent[i] = make_int2((int)nt.entries[i].second.kind, (int)nt.entries[i].second.off);
+    if (!nt.fixed_ok.empty()) {
+      std::memcpy(h.data() + o_ok, nt.fixed_ok.data(), std::min<size_t>(nt.fixed_ok.size(), 32 * 64));
+      std::memcpy(h.data() + o_fx, nt.fixed_ptm.data(), std::min<size_t>(nt.fixed_ptm.size(), (size_t)32 * 64 * 16) * sizeof(double));
+    }
+    CK(ctx->d_oc_noise.reserve(blob.total));
+    CK(cudaMemcpyAsync(ctx->d_oc_noise.p, h.data(), blob.total, cudaMemcpyHostToDevice, ctx->stream));
+    CK(cudaStreamSynchronize(ctx->stream));
+    const char* d = (const char*)ctx->d_oc_noise.p;
+    ctx->oc_noise.g1 = (const int32_t*)(d + o_g1);
+    ctx->oc_noise.cx = (const int32_t*)(d + o_cx);
+    ctx->oc_noise.ent = (const int2*)(d + o_ent);
+    ctx->oc_noise.fixed_ok = (const uint8_t*)(d + o_ok);
+    ctx->oc_noise.fixed_ptm = (const double*)(d + o_fx);
+    ctx->oc_noise.data = (const double*)ctx->d_noise.p;
+  }
+  ctx->oc_noise_valid = true;
+  return BWQ_OK;
+}
+
+// Runs the batch (times its variants) on dm_onchip_kernel when every circuit qualifies; *handled =
+// false leaves out_vals / out_status for the tile-sweep path.  out_status: one entry per variant
+// circuit (circuit-major), out_vals as bwq_dm_run_variants.
+static int onchip_run(bwq_ctx* ctx, const bwq_batch* b, const bwq_variants* v, bool noisy, double* out_vals, bool out_on_device,
+                      int32_t* out_status, bool* handled) {
+  *handled = false;
+  if (ctx->opt.flags & BWQ_OPT_NO_ONCHIP) return BWQ_OK;
+  const int N = b->n_circuits;
+  if (N <= 0) return BWQ_OK;
+  const int n_folds = v && v->n_folds > 0 ? v->n_folds : 1, n_tw = v && v->n_twirls > 0 ? v->n_twirls : 1;
+  if (v && v->n_folds > 0) {
+    if (!v->folds) return BWQ_OK;
+    for (int f = 0; f < n_folds; ++f)
+      if (v->folds[f] < 1 || v->folds[f] % 2 == 0) return BWQ_OK;  // the expansion path reports the error
+  }
+  const int64_t NV = (int64_t)N * n_folds * n_tw;
+  const int64_t g_lo = b->op_offsets[0], g_hi = b->op_offsets[N];
+  const int64_t ob_lo = b->obs_offsets[0], ob_hi = b->obs_offsets[N];
+  const int64_t t_lo = ob_hi > ob_lo ? b->term_offsets[ob_lo] : 0, t_hi = ob_hi > ob_lo ? b->term_offsets[ob_hi] : 0;
+  if (NV > INT32_MAX || b->n_params >= (int64_t(1) << 32)) return BWQ_OK;
+  // routing probe (the kernel decides per circuit): a few circuits must have at most 5 active qubits
+  for (int probe = 0; probe < 3; ++probe) {
+    const int c = probe == 0 ? 0 : probe == 1 ? N / 2 : N - 1;
+    uint64_t used = 0;
+    for (int64_t g = b->op_offsets[c]; g < b->op_offsets[c + 1]; ++g) {
+      const bwq_op& op = b->ops[g];
+      if (gate_is_2q(op.opcode)) {
+        if (op.opcode != BWQ_G_CX) return BWQ_OK;
+        used |= 1ull << (op.q1 & 63);
+      }
+      used |= 1ull << (op.q0 & 63);
+    }
+    if (__builtin_popcountll(used) > kOnchipMaxDigits) return BWQ_OK;
+  }
+  const double t0 = now_ms();
+  CK(cudaSetDevice(ctx->device));
+  int rc = noisy ? onchip_upload_noise(ctx) : BWQ_OK;
+  if (rc) return rc;
+  const int64_t n_obs = ob_hi - ob_lo, n_out = n_obs * n_folds * n_tw;
+  Blob blob;
+  const size_t o_nq = blob.add(sizeof(int32_t) * (size_t)N), o_go = blob.add(sizeof(int64_t) * (size_t)(N + 1));
+  const size_t o_ops = blob.add(sizeof(bwq_op) * (size_t)(g_hi - g_lo)), o_par = blob.add(sizeof(double) * (size_t)b->n_params);
+  const size_t o_oo = blob.add(sizeof(int64_t) * (size_t)(N + 1)), o_to = blob.add(sizeof(int64_t) * (size_t)(n_obs + 1));
+  const size_t o_tx = blob.add(sizeof(uint64_t) * (size_t)(t_hi - t_lo)), o_tz = blob.add(sizeof(uint64_t) * (size_t)(t_hi - t_lo));
+  const size_t o_tc = blob.add(sizeof(double) * (size_t)(t_hi - t_lo)), o_fd = blob.add(sizeof(int32_t) * (size_t)n_folds);
+  if (blob.total > (size_t(1) << 30)) return BWQ_OK;  // larger batches: the segmented tile-sweep pipeline
+  CK(ctx->h_oc.reserve(blob.total));
+  CK(ctx->d_oc.reserve(blob.total));
+  char* h = (char*)ctx->h_oc.p;
+  {
+    struct Piece { size_t off; const void* src; size_t bytes; };
+    const Piece pieces[] = {
+        {o_nq, b->n_qubits, sizeof(int32_t) * (size_t)N}, {o_go, b->op_offsets, sizeof(int64_t) * (size_t)(N + 1)},
+        {o_ops, b->ops ? b->ops + g_lo : nullptr, sizeof(bwq_op) * (size_t)(g_hi - g_lo)}, {o_par, b->params, sizeof(double) * (size_t)b->n_params},
+        {o_oo, b->obs_offsets, sizeof(int64_t) * (size_t)(N + 1)}, {o_to, b->term_offsets + ob_lo, sizeof(int64_t) * (size_t)(n_obs + 1)},
+        {o_tx, b->term_x ? b->term_x + t_lo : nullptr, sizeof(uint64_t) * (size_t)(t_hi - t_lo)},
+        {o_tz, b->term_z ? b->term_z + t_lo : nullptr, sizeof(uint64_t) * (size_t)(t_hi - t_lo)},
+        {o_tc, b->term_coeff ? b->term_coeff + t_lo : nullptr, sizeof(double) * (size_t)(t_hi - t_lo)},
+        {o_fd, v && v->n_folds > 0 ? v->folds : nullptr, sizeof(int32_t) * (size_t)n_folds}};
+    // staging copy into the pinned blob, 1 MiB slices over the host threads when it is large
+    struct Slice { char* dst; const char* src; size_t bytes; };
+    std::vector<Slice> slices;
+    for (const Piece& pc : pieces) {
+      if (!pc.src || !pc.bytes) continue;
+      for (size_t o = 0; o < pc.bytes; o += size_t(1) << 20)
+        slices.push_back({h + pc.off + o, (const char*)pc.src + o, std::min(pc.bytes - o, size_t(1) << 20)});
+    }
+    parallel_for((int)slices.size(), slices.size() >= 8 ? host_threads(ctx) : 1, [&](int i) { std::memcpy(slices[i].dst, slices[i].src, slices[i].bytes); });
+  }
+  // results: [status int32 x NV | values]; values straight into the caller's buffer when it is on the device
+  const size_t st_bytes = (sizeof(int32_t) * (size_t)NV + 255) & ~size_t(255);
+  const size_t res_bytes = st_bytes + (out_on_device ? 0 : sizeof(double) * (size_t)n_out);
+  CK(ctx->d_oc_out.reserve(res_bytes));
+  CK(ctx->h_oc_out.reserve(res_bytes));
+  const double staged_ms = now_ms() - t0;
+  cudaStream_t st = ctx->stream;
+  CK(cudaEventRecord(ctx->ev[0], st));
+  CK(cudaMemcpyAsync(ctx->d_oc.p, h, blob.total, cudaMemcpyHostToDevice, st));
+  CK(cudaEventRecord(ctx->ev[1], st));
+  const char* d = (const char*)ctx->d_oc.p;
+  OnchipLaunch L{};
+  L.n_circuits = N; L.n_folds = n_folds; L.n_twirls = n_tw; L.twirl = v && v->n_twirls > 0; L.seed = v ? v->seed : 0;
+  L.folds = v && v->n_folds > 0 ? (const int32_t*)(d + o_fd) : nullptr;
+  L.n_qubits = (const int32_t*)(d + o_nq);
+  L.op_offsets = (const int64_t*)(d + o_go);
+  L.ops = (const bwq_op*)(d + o_ops) - g_lo;  // indexed with the batch's absolute offsets
+  L.params = (const double*)(d + o_par);
+  L.n_params = b->n_params;
+  L.obs_offsets = (const int64_t*)(d + o_oo);
+  L.term_offsets = (const int64_t*)(d + o_to) - ob_lo;
+  L.term_x = (const uint64_t*)(d + o_tx) - t_lo;
+  L.term_z = (const uint64_t*)(d + o_tz) - t_lo;
+  L.term_coeff = (const double*)(d + o_tc) - t_lo;
+  if (noisy) L.noise = ctx->oc_noise;
+  double* d_vals = out_on_device ? out_vals : (double*)((char*)ctx->d_oc_out.p + st_bytes);
+  L.out = d_vals - ob_lo * (int64_t)(n_folds * n_tw);
+  L.status = (int32_t*)ctx->d_oc_out.p;
+  const unsigned grid = (unsigned)((NV + kOnchipWarps - 1) / kOnchipWarps);
+  dm_onchip_kernel<<<grid, 32 * kOnchipWarps, kOnchipSmem, st>>>(L);
+  CK(cudaGetLastError());
+  CK(cudaEventRecord(ctx->ev[2], st));
+  CK(cudaMemcpyAsync(ctx->h_oc_out.p, ctx->d_oc_out.p, res_bytes, cudaMemcpyDeviceToHost, st));
+  CK(cudaEventRecord(ctx->ev[3], st));
+  CK(cudaStreamSynchronize(st));
+  const int32_t* hs = (const int32_t*)ctx->h_oc_out.p;
+  for (int64_t i = 0; i < NV; ++i)
+    if (hs[i] == kOnchipNotHandled) return BWQ_OK;  // mixed batch: everything goes through the tile sweeps
+  std::memcpy(out_status, hs, sizeof(int32_t) * (size_t)NV);
+  if (!out_on_device && n_out > 0) std::memcpy(out_vals, (const char*)ctx->h_oc_out.p + st_bytes, sizeof(double) * (size_t)n_out);
+  bwq_stats S{};
+  float ms = 0.f;
+  CK(cudaEventElapsedTime(&ms, ctx->ev[0], ctx->ev[1])); S.h2d_ms = ms;
+  CK(cudaEventElapsedTime(&ms, ctx->ev[1], ctx->ev[2])); S.kernel_ms = ms;
+  CK(cudaEventElapsedTime(&ms, ctx->ev[2], ctx->ev[3])); S.d2h_ms = ms;
+  S.lower_ms = staged_ms;
+  S.h2d_bytes = (int64_t)blob.total; S.d2h_bytes = (int64_t)res_bytes;
+  S.n_other_launches = 1;
+  S.n_onchip_circuits = NV;
+  for (int c = 0; c < N; ++c) S.n_gates += b->op_offsets[c + 1] - b->op_offsets[c];
+  ctx->stats = S;
+  *handled = true;
+  return BWQ_OK;
+}
+
 static int dm_run_impl(bwq_ctx* ctx, const bwq_batch* b, double* out_vals, int32_t* out_status, bool out_on_device,
-                       const FoldInfo* fi = nullptr) {
+                       const FoldInfo* fi = nullptr, bool allow_onchip = true) {
   if (!ctx) return BWQ_ERR_ARG;
   int rc = check_batch(ctx, b, out_status, out_status);
   if (rc) return rc;
+  if (allow_onchip) {  // circuits that fit on chip: one launch on the raw gate stream, no lowering
+    bool handled = false;
+    if ((rc = onchip_run(ctx, b, nullptr, true, out_vals, out_on_device, out_status, &handled))) return rc;
+    if (handled) return BWQ_OK;
+  }
   ctx->stats = bwq_stats{};
   const int N = b->n_circuits;
   int64_t budget = 0;
@@ -1322,8 +1511,16 @@ extern "C" int bwq_sv_prepare(bwq_ctx* ctx, const bwq_batch* b, int32_t* out_sta
 }
 extern "C" int bwq_sv_execute(bwq_ctx* ctx, double* out_vals) { return sv_execute_impl(ctx, out_vals); }
 extern "C" int bwq_sv_run(bwq_ctx* ctx, const bwq_batch* b, double* out_vals, int32_t* out_status) {
+  if (!ctx) return BWQ_ERR_ARG;
   if (!out_vals || !out_status) return fail(ctx, BWQ_ERR_ARG, "null out/status");
-  int rc = sv_prepare_impl(ctx, b, out_status);
+  int rc = check_batch(ctx, b, out_vals, out_status);
+  if (rc) return rc;
+  {  // circuits that fit on chip: the noise-free Pauli-basis evolution gives the same <P> (onchip.cuh)
+    bool handled = false;
+    if ((rc = onchip_run(ctx, b, nullptr, false, out_vals, false, out_status, &handled))) return rc;
+    if (handled) return BWQ_OK;
+  }
+  rc = sv_prepare_impl(ctx, b, out_status);
   return rc ? rc : sv_execute_impl(ctx, out_vals);
 }
 
@@ -1348,6 +1545,22 @@ extern "C" int bwq_meas_data_run(bwq_ctx* ctx, const bwq_batch* b, double* out_i
                                  int32_t* status_ideal, int32_t* status_noisy) {
   if (!ctx) return BWQ_ERR_ARG;
   if (!out_ideal || !out_noisy || !status_ideal || !status_noisy) return fail(ctx, BWQ_ERR_ARG, "null out/status");
+  {
+    int rc = check_batch(ctx, b, out_ideal, status_ideal);
+    if (rc) return rc;
+    bool handled = false;
+    if ((rc = onchip_run(ctx, b, nullptr, true, out_noisy, false, status_noisy, &handled))) return rc;
+    if (handled) {  // small circuits: both sides on dm_onchip_kernel (ideal = without the noise table)
+      const bwq_stats noisy_stats = ctx->stats;
+      if ((rc = onchip_run(ctx, b, nullptr, false, out_ideal, false, status_ideal, &handled))) return rc;
+      if (!handled) return fail(ctx, BWQ_ERR_UNSUPPORTED, "on-chip path: ideal side rejected a batch the noisy side took");
+      bwq_stats S = noisy_stats;
+      S.lower_ms += ctx->stats.lower_ms; S.h2d_ms += ctx->stats.h2d_ms; S.kernel_ms += ctx->stats.kernel_ms; S.d2h_ms += ctx->stats.d2h_ms;
+      S.h2d_bytes += ctx->stats.h2d_bytes; S.d2h_bytes += ctx->stats.d2h_bytes; S.n_other_launches += ctx->stats.n_other_launches;
+      ctx->stats = S;
+      return BWQ_OK;
+    }
+  }
   int rc_c = ensure_companion(ctx);
   if (rc_c) return rc_c;
   // both lowering stages run at once: split the host threads (statevector lowering is the cheaper
@@ -1358,7 +1571,7 @@ extern "C" int bwq_meas_data_run(bwq_ctx* ctx, const bwq_batch* b, double* out_i
   ctx->opt.host_threads = std::max(1, all_threads - ctx->companion->opt.host_threads);
   int rc_sv = BWQ_OK;
   std::thread ideal([&] { rc_sv = bwq_sv_run(ctx->companion, b, out_ideal, status_ideal); });
-  const int rc_dm = bwq_dm_run(ctx, b, out_noisy, status_noisy);
+  const int rc_dm = dm_run_impl(ctx, b, out_noisy, status_noisy, false, nullptr, false);
   ideal.join();
   ctx->opt.host_threads = saved_threads;
   if (rc_dm) return rc_dm;
@@ -1373,6 +1586,26 @@ extern "C" int bwq_meas_data_run_variants(bwq_ctx* ctx, const bwq_batch* b, cons
   if (!b || !v || !out_ideal || !out_noisy || !status_ideal || !status_noisy) return fail(ctx, BWQ_ERR_ARG, "null argument");
   int rc = check_batch(ctx, b, out_ideal, status_ideal);
   if (rc) return rc;
+  {
+    bool handled = false;
+    const int64_t n_var = (int64_t)std::max(1, v->n_folds) * std::max(1, v->n_twirls);
+    std::vector<int32_t> st_all((size_t)std::max<int64_t>(1, b->n_circuits * n_var));
+    if ((rc = onchip_run(ctx, b, v, true, out_noisy, false, st_all.data(), &handled))) return rc;
+    if (handled) {
+      for (int c = 0; c < b->n_circuits; ++c) {
+        status_noisy[c] = 0;
+        for (int64_t k = 0; k < n_var && !status_noisy[c]; ++k) status_noisy[c] = st_all[(size_t)(c * n_var + k)];
+      }
+      const bwq_stats noisy_stats = ctx->stats;
+      if ((rc = onchip_run(ctx, b, nullptr, false, out_ideal, false, status_ideal, &handled))) return rc;
+      if (!handled) return fail(ctx, BWQ_ERR_UNSUPPORTED, "on-chip path: ideal side rejected a batch the noisy side took");
+      bwq_stats S = noisy_stats;
+      S.lower_ms += ctx->stats.lower_ms; S.h2d_ms += ctx->stats.h2d_ms; S.kernel_ms += ctx->stats.kernel_ms; S.d2h_ms += ctx->stats.d2h_ms;
+      S.h2d_bytes += ctx->stats.h2d_bytes; S.d2h_bytes += ctx->stats.d2h_bytes; S.n_other_launches += ctx->stats.n_other_launches;
+      ctx->stats = S;
+      return BWQ_OK;
+    }
+  }
   if ((rc = ensure_companion(ctx))) return rc;
   const double t0 = now_ms();
   ExpandedBatch X;
@@ -1392,7 +1625,7 @@ extern "C" int bwq_meas_data_run_variants(bwq_ctx* ctx, const bwq_batch* b, cons
   int rc_sv = BWQ_OK;
   std::thread ideal([&] { rc_sv = bwq_sv_run(ctx->companion, b, out_ideal, status_ideal); });
   const FoldInfo fi{b, v->folds, v->n_folds};
-  const int rc_dm = dm_run_impl(ctx, &X.view, out_noisy, st_var.data(), false, v->n_twirls == 0 && v->n_folds > 0 ? &fi : nullptr);
+  const int rc_dm = dm_run_impl(ctx, &X.view, out_noisy, st_var.data(), false, v->n_twirls == 0 && v->n_folds > 0 ? &fi : nullptr, false);
   ideal.join();
   ctx->opt.host_threads = saved_threads;
   if (rc_dm) return rc_dm;
@@ -1412,12 +1645,17 @@ extern "C" int bwq_dm_run_variants(bwq_ctx* ctx, const bwq_batch* b, const bwq_v
   if (!b || !v || !out_vals || !out_status) return fail(ctx, BWQ_ERR_ARG, "null argument");
   int rc = check_batch(ctx, b, out_vals, out_status);
   if (rc) return rc;
+  {
+    bool handled = false;
+    if ((rc = onchip_run(ctx, b, v, true, out_vals, false, out_status, &handled))) return rc;
+    if (handled) return BWQ_OK;
+  }
   const double t0 = now_ms();
   ExpandedBatch X;
   if ((rc = expand_variants(*b, *v, &X, host_threads(ctx)))) return fail(ctx, rc, "bad variants descriptor (folds must be odd positive factors)");
   const double expand_ms = now_ms() - t0;
   const FoldInfo fi{b, v->folds, v->n_folds};
-  if ((rc = dm_run_impl(ctx, &X.view, out_vals, out_status, false, v->n_twirls == 0 && v->n_folds > 0 ? &fi : nullptr))) return rc;
+  if ((rc = dm_run_impl(ctx, &X.view, out_vals, out_status, false, v->n_twirls == 0 && v->n_folds > 0 ? &fi : nullptr, false))) return rc;
   for (int c = 0; c < b->n_circuits; ++c)
     if (X.status[c])
       for (int k = 0; k < X.n_variants; ++k) {

@@ -51,6 +51,8 @@ int NoiseTable::set(const bwq_noise_table* t, char* err, size_t errlen) {
     entries.push_back({key, NoiseEntry{t->kind[i], (int64_t)data.size()}});
     data.insert(data.end(), t->data + t->data_off[i], t->data + t->data_off[i] + need);
   }
+  while (data.size() % 4) data.push_back(0.0);  // the kernels read a 25-double entry as 13 pairs
+  data.push_back(0.0);
   std::sort(entries.begin(), entries.end(),
             [](const auto& a, const auto& b) { return a.first < b.first; });
   one_q.clear();  // find() below searches while the table is being filled

@@ -47,6 +47,10 @@ def _kron2(b, a):
 def gate_matrix(name, params=()):
     n = name.lower()
     p = [float(x) for x in params]
+    if n in ("unitary1", "unitary2"):
+        # explicit matrix: row-major, (re, im) interleaved; 2-qubit index = i_q0 + 2 i_q1 (include/bwq.h:62-63)
+        d = 2 if n == "unitary1" else 4
+        return (np.array(p[0::2]) + 1j * np.array(p[1::2])).reshape(d, d)
     if n in ("id", "i"):
         return I2.copy()
     if n == "x":

@@ -281,18 +281,20 @@ def test_pipelined_run_and_meas_data_call(engine_gpu):
         obs.append([[(l, float(rng.normal()))] for l in _labels(rng, 5, int(rng.integers(1, 4)))])
     batch = engine.encode_batch(circs, obs)
     engine_gpu.set_noise(nm)
-    engine_gpu.set_options(flags=8)  # BWQ_OPT_FORCE_PIPELINE (5-qubit circuits are below the automatic threshold)
+    # 128 = BWQ_OPT_NO_ONCHIP: these 5-qubit circuits would otherwise run on dm_onchip_kernel (no segments)
+    engine_gpu.set_options(flags=8 | 128)  # BWQ_OPT_FORCE_PIPELINE (5-qubit circuits are below the automatic threshold)
     v_pipe, st_pipe = engine_gpu.run_dm(batch)
     assert engine_gpu.stats()["n_sweep_launches"] >= 4  # one launch per segment at least
-    engine_gpu.set_options(flags=4)  # BWQ_OPT_NO_PIPELINE
+    engine_gpu.set_options(flags=4 | 128)  # BWQ_OPT_NO_PIPELINE
     v_one, st_one = engine_gpu.run_dm(batch)
     engine_gpu.set_options()
     assert not st_pipe.any() and not st_one.any()
     assert np.array_equal(v_pipe, v_one)
     assert not engine_gpu.prepare_dm(batch).any()
     assert np.array_equal(engine_gpu.execute_dm(), v_pipe)
+    engine_gpu.set_options(flags=128)
     v_sv, st_sv = engine_gpu.run_sv(batch)
-    engine_gpu.set_options(flags=8)
+    engine_gpu.set_options(flags=8 | 128)
     ideal, noisy, st_i, st_n = engine_gpu.run_meas_data(batch)
     engine_gpu.set_options()
     assert not st_i.any() and not st_n.any()
