@@ -872,8 +872,9 @@ static int onchip_upload_noise(bwq_ctx* ctx) {
 // false leaves out_vals / out_status for the tile-sweep path.  out_status: one entry per variant
 // circuit (circuit-major), out_vals as bwq_dm_run_variants.
 static int onchip_run(bwq_ctx* ctx, const bwq_batch* b, const bwq_variants* v, bool noisy, double* out_vals, bool out_on_device,
-                      int32_t* out_status, bool* handled) {
+                      int32_t* out_status, bool* handled, double* out_ideal = nullptr, int32_t* status_ideal = nullptr) {
   *handled = false;
+  const bool with_ideal = out_ideal != nullptr;  // the same launch also evolves every base circuit without noise
   if (ctx->opt.flags & BWQ_OPT_NO_ONCHIP) return BWQ_OK;
   const int N = b->n_circuits;
   if (N <= 0) return BWQ_OK;
@@ -927,19 +928,21 @@ static int onchip_run(bwq_ctx* ctx, const bwq_batch* b, const bwq_variants* v, b
         {o_tz, b->term_z ? b->term_z + t_lo : nullptr, sizeof(uint64_t) * (size_t)(t_hi - t_lo)},
         {o_tc, b->term_coeff ? b->term_coeff + t_lo : nullptr, sizeof(double) * (size_t)(t_hi - t_lo)},
         {o_fd, v && v->n_folds > 0 ? v->folds : nullptr, sizeof(int32_t) * (size_t)n_folds}};
-    // staging copy into the pinned blob, 1 MiB slices over the host threads when it is large
+    // staging copy into the pinned blob, 256 KiB slices over a few host threads when it is large
     struct Slice { char* dst; const char* src; size_t bytes; };
     std::vector<Slice> slices;
     for (const Piece& pc : pieces) {
       if (!pc.src || !pc.bytes) continue;
-      for (size_t o = 0; o < pc.bytes; o += size_t(1) << 20)
-        slices.push_back({h + pc.off + o, (const char*)pc.src + o, std::min(pc.bytes - o, size_t(1) << 20)});
+      for (size_t o = 0; o < pc.bytes; o += size_t(1) << 18)
+        slices.push_back({h + pc.off + o, (const char*)pc.src + o, std::min(pc.bytes - o, size_t(1) << 18)});
     }
-    parallel_for((int)slices.size(), slices.size() >= 8 ? host_threads(ctx) : 1, [&](int i) { std::memcpy(slices[i].dst, slices[i].src, slices[i].bytes); });
+    parallel_for((int)slices.size(), std::min<int>({(int)slices.size() / 4, 8, host_threads(ctx)}), [&](int i) { std::memcpy(slices[i].dst, slices[i].src, slices[i].bytes); });
   }
-  // results: [status int32 x NV | values]; values straight into the caller's buffer when it is on the device
-  const size_t st_bytes = (sizeof(int32_t) * (size_t)NV + 255) & ~size_t(255);
-  const size_t res_bytes = st_bytes + (out_on_device ? 0 : sizeof(double) * (size_t)n_out);
+  // results: [status int32 x NV | status_ideal x N | values | ideal values]; values straight into the
+  // caller's buffer when it is on the device
+  const size_t st_bytes = (sizeof(int32_t) * (size_t)(NV + (with_ideal ? N : 0)) + 255) & ~size_t(255);
+  const size_t val_bytes = out_on_device ? 0 : ((sizeof(double) * (size_t)n_out + 255) & ~size_t(255));
+  const size_t res_bytes = st_bytes + val_bytes + (with_ideal ? sizeof(double) * (size_t)n_obs : 0);
   CK(ctx->d_oc_out.reserve(res_bytes));
   CK(ctx->h_oc_out.reserve(res_bytes));
   const double staged_ms = now_ms() - t0;
@@ -965,7 +968,11 @@ static int onchip_run(bwq_ctx* ctx, const bwq_batch* b, const bwq_variants* v, b
   double* d_vals = out_on_device ? out_vals : (double*)((char*)ctx->d_oc_out.p + st_bytes);
   L.out = d_vals - ob_lo * (int64_t)(n_folds * n_tw);
   L.status = (int32_t*)ctx->d_oc_out.p;
-  const unsigned grid = (unsigned)((NV + kOnchipWarps - 1) / kOnchipWarps);
+  L.with_ideal = with_ideal ? 1 : 0;
+  L.out_ideal = with_ideal ? (double*)((char*)ctx->d_oc_out.p + st_bytes + val_bytes) - ob_lo : nullptr;
+  L.status_ideal = L.status + NV;
+  const int64_t n_warps = NV + (with_ideal ? N : 0);
+  const unsigned grid = (unsigned)((n_warps + kOnchipWarps - 1) / kOnchipWarps);
   dm_onchip_kernel<<<grid, 32 * kOnchipWarps, kOnchipSmem, st>>>(L);
   CK(cudaGetLastError());
   CK(cudaEventRecord(ctx->ev[2], st));
@@ -973,10 +980,14 @@ static int onchip_run(bwq_ctx* ctx, const bwq_batch* b, const bwq_variants* v, b
   CK(cudaEventRecord(ctx->ev[3], st));
   CK(cudaStreamSynchronize(st));
   const int32_t* hs = (const int32_t*)ctx->h_oc_out.p;
-  for (int64_t i = 0; i < NV; ++i)
+  for (int64_t i = 0; i < n_warps; ++i)
     if (hs[i] == kOnchipNotHandled) return BWQ_OK;  // mixed batch: everything goes through the tile sweeps
   std::memcpy(out_status, hs, sizeof(int32_t) * (size_t)NV);
   if (!out_on_device && n_out > 0) std::memcpy(out_vals, (const char*)ctx->h_oc_out.p + st_bytes, sizeof(double) * (size_t)n_out);
+  if (with_ideal) {
+    std::memcpy(status_ideal, hs + NV, sizeof(int32_t) * (size_t)N);
+    if (n_obs > 0) std::memcpy(out_ideal, (const char*)ctx->h_oc_out.p + st_bytes + val_bytes, sizeof(double) * (size_t)n_obs);
+  }
   bwq_stats S{};
   float ms = 0.f;
   CK(cudaEventElapsedTime(&ms, ctx->ev[0], ctx->ev[1])); S.h2d_ms = ms;
@@ -985,7 +996,7 @@ static int onchip_run(bwq_ctx* ctx, const bwq_batch* b, const bwq_variants* v, b
   S.lower_ms = staged_ms;
   S.h2d_bytes = (int64_t)blob.total; S.d2h_bytes = (int64_t)res_bytes;
   S.n_other_launches = 1;
-  S.n_onchip_circuits = NV;
+  S.n_onchip_circuits = n_warps;
   for (int c = 0; c < N; ++c) S.n_gates += b->op_offsets[c + 1] - b->op_offsets[c];
   ctx->stats = S;
   *handled = true;
@@ -1549,17 +1560,9 @@ extern "C" int bwq_meas_data_run(bwq_ctx* ctx, const bwq_batch* b, double* out_i
     int rc = check_batch(ctx, b, out_ideal, status_ideal);
     if (rc) return rc;
     bool handled = false;
-    if ((rc = onchip_run(ctx, b, nullptr, true, out_noisy, false, status_noisy, &handled))) return rc;
-    if (handled) {  // small circuits: both sides on dm_onchip_kernel (ideal = without the noise table)
-      const bwq_stats noisy_stats = ctx->stats;
-      if ((rc = onchip_run(ctx, b, nullptr, false, out_ideal, false, status_ideal, &handled))) return rc;
-      if (!handled) return fail(ctx, BWQ_ERR_UNSUPPORTED, "on-chip path: ideal side rejected a batch the noisy side took");
-      bwq_stats S = noisy_stats;
-      S.lower_ms += ctx->stats.lower_ms; S.h2d_ms += ctx->stats.h2d_ms; S.kernel_ms += ctx->stats.kernel_ms; S.d2h_ms += ctx->stats.d2h_ms;
-      S.h2d_bytes += ctx->stats.h2d_bytes; S.d2h_bytes += ctx->stats.d2h_bytes; S.n_other_launches += ctx->stats.n_other_launches;
-      ctx->stats = S;
-      return BWQ_OK;
-    }
+    // small circuits: both sides in one launch of dm_onchip_kernel (ideal = without the noise table)
+    if ((rc = onchip_run(ctx, b, nullptr, true, out_noisy, false, status_noisy, &handled, out_ideal, status_ideal))) return rc;
+    if (handled) return BWQ_OK;
   }
   int rc_c = ensure_companion(ctx);
   if (rc_c) return rc_c;
@@ -1590,19 +1593,12 @@ extern "C" int bwq_meas_data_run_variants(bwq_ctx* ctx, const bwq_batch* b, cons
     bool handled = false;
     const int64_t n_var = (int64_t)std::max(1, v->n_folds) * std::max(1, v->n_twirls);
     std::vector<int32_t> st_all((size_t)std::max<int64_t>(1, b->n_circuits * n_var));
-    if ((rc = onchip_run(ctx, b, v, true, out_noisy, false, st_all.data(), &handled))) return rc;
+    if ((rc = onchip_run(ctx, b, v, true, out_noisy, false, st_all.data(), &handled, out_ideal, status_ideal))) return rc;
     if (handled) {
       for (int c = 0; c < b->n_circuits; ++c) {
         status_noisy[c] = 0;
         for (int64_t k = 0; k < n_var && !status_noisy[c]; ++k) status_noisy[c] = st_all[(size_t)(c * n_var + k)];
       }
-      const bwq_stats noisy_stats = ctx->stats;
-      if ((rc = onchip_run(ctx, b, nullptr, false, out_ideal, false, status_ideal, &handled))) return rc;
-      if (!handled) return fail(ctx, BWQ_ERR_UNSUPPORTED, "on-chip path: ideal side rejected a batch the noisy side took");
-      bwq_stats S = noisy_stats;
-      S.lower_ms += ctx->stats.lower_ms; S.h2d_ms += ctx->stats.h2d_ms; S.kernel_ms += ctx->stats.kernel_ms; S.d2h_ms += ctx->stats.d2h_ms;
-      S.h2d_bytes += ctx->stats.h2d_bytes; S.d2h_bytes += ctx->stats.d2h_bytes; S.n_other_launches += ctx->stats.n_other_launches;
-      ctx->stats = S;
       return BWQ_OK;
     }
   }

@@ -57,6 +57,11 @@ struct OnchipLaunch {
   OnchipNoise noise;
   double* out;                  // [(obs of circuit c) x variants]: circuit-major, variant, observable
   int32_t* status;              // [n_circuits * n_variants]
+  // with_ideal: one more warp per circuit evolves the base circuit WITHOUT the noise table (the
+  // ideal value of every variant: folds and twirls are identities) -> out_ideal [obs], status_ideal [n_circuits]
+  int32_t with_ideal;
+  double* out_ideal;
+  int32_t* status_ideal;
 };
 
 __device__ __forceinline__ int dev_num_params(uint32_t op) {
@@ -152,8 +157,37 @@ constexpr int kOnchipGRow = 18;  // doubles per staged gate matrix (16 + pad: co
 constexpr int kOnchipWarpDoubles = (1 << (2 * kOnchipMaxDigits)) + kOnchipMaxDigits * 16 + 32 * kOnchipGRow;
 constexpr size_t kOnchipSmem = sizeof(double) * kOnchipWarpDoubles * kOnchipWarps;
 
+// Bank swizzle of the warp's state: element idx (digits d0..d4) lives at idx ^ S(idx), where S folds
+// the upper digits into the low four index bits (= the 8-byte bank) through a spread of GF(2)^4:
+//   bits 0..1 ^= d2 ^ d3 ^ d4,   bits 2..3 ^= d2 ^ w(d3) ^ w(w(d4)),   w = multiplication by the GF(4) generator.
+// The five 2-bit subspaces are pairwise complementary, so the 16 register groups of ANY digit pair
+// (lanes enumerate the two other digits of a 4-qubit state) touch 16 distinct banks for each of
+// their 16 elements; S is linear over XOR, so address(x | a << 2da | b << 2db) = P(x) ^ P(a << 2da) ^ P(b << 2db).
+__host__ __device__ constexpr uint32_t oc_w(uint32_t x) { return ((x >> 1) & 1u) | (((x ^ (x >> 1)) & 1u) << 1); }
+__host__ __device__ constexpr uint32_t oc_nib(int d, uint32_t k) {  // S of digit d = k (d = 2, 3, 4)
+  return d == 2 ? (k | (k << 2)) : d == 3 ? (k | (oc_w(k) << 2)) : (k | ((k ^ oc_w(k)) << 2));
+}
+__host__ __device__ constexpr uint64_t oc_table() {  // nibble 4 * (d - 2) * 4 + k ... : 16 bits per digit
+  uint64_t t = 0;
+  for (int d = 2; d <= 4; ++d)
+    for (uint32_t k = 0; k < 4; ++k) t |= (uint64_t)oc_nib(d, k) << (16 * (d - 2) + 4 * k);
+  return t;
+}
+constexpr uint64_t kOcTable = oc_table();
+__device__ __forceinline__ uint32_t oc_phys(uint32_t idx) {
+  const uint32_t hi = idx >> 4;  // digits 2..4, 2 bits each -> nibble index 4 * (d - 2) + k: shift 16 (d - 2) + 4 k
+  const uint32_t s2 = (uint32_t)(kOcTable >> ((hi & 3u) << 2)), s3 = (uint32_t)(kOcTable >> (16u + (((hi >> 2) & 3u) << 2)));
+  const uint32_t s4 = (uint32_t)(kOcTable >> (32u + (((hi >> 4) & 3u) << 2)));
+  return idx ^ ((s2 ^ s3 ^ s4) & 15u);
+}
+// swizzled image of digit d = k alone (a basis vector of the XOR-linear map)
+__device__ __forceinline__ uint32_t oc_phys_digit(int d, uint32_t k) {
+  const uint32_t sw = d < 2 ? 0u : (uint32_t)(kOcTable >> (16 * (d - 2) + 4 * k)) & 15u;
+  return (k << (2 * d)) ^ sw;
+}
+
 struct OnchipWarp {
-  double* st;      // 4^n state of this warp
+  double* st;      // 4^n state of this warp (swizzled: oc_phys)
   double* pend;    // [kOnchipMaxDigits][16] pending 1-qubit maps
   double* gbuf;    // [32][kOnchipGRow] transfer matrices of the fetched ops
   uint32_t has;    // digits with a pending map (warp-uniform)
@@ -218,34 +252,45 @@ __device__ __forceinline__ void onchip_pauli(OnchipWarp& W, const OnchipNoise& N
   if (p == 1 || p == 2) onchip_gate1(W, N, scratch, BWQ_G_X, q, d, 0.0);
 }
 
-// register groups of the digit pair (da, db): pending maps, then `reps` copies of cx (+ its error
-// of `kind` at nm); reps = 0: only the pending map of da (end of circuit)
+// one cx (+ its error of `kind` at nm) on the register group
+__device__ __forceinline__ void onchip_cx(double (&v)[1][16], int kind, const double* __restrict__ nm) {
+  if (kind == BWQ_NOISE_RELAX2) op_relax2<false, true, 1>(v, nm);
+  else {
+    op_cx<false, 1>(v);
+    if (kind == BWQ_NOISE_DENSE2) op_dense2<false, 1>(v, nm);
+  }
+}
+
+// register groups of the digit pair (da, db): pending maps, then `reps` copies of cx (+ its error);
+// reps = 0: only the pending map of da (end of circuit)
 __device__ __forceinline__ void onchip_pair(OnchipWarp& W, int da, int db, int reps, int kind, const double* __restrict__ nm) {
   const int lo = min(da, db), hi = max(da, db);
   const int groups = 1 << (2 * (W.nd - 2));
   const bool pa = (W.has >> da) & 1u, pb = reps > 0 && ((W.has >> db) & 1u);
+  uint32_t oa[4], ob[4];  // byte offsets
+#pragma unroll
+  for (int k = 0; k < 4; ++k) { oa[k] = oc_phys_digit(da, (uint32_t)k) << 3; ob[k] = oc_phys_digit(db, (uint32_t)k) << 3; }
+  char* const base = reinterpret_cast<char*>(W.st);
   for (int g = W.lane; g < groups; g += 32) {
     uint32_t x = (uint32_t)g;
     x = ((x >> (2 * lo)) << (2 * lo + 2)) | (x & ((1u << (2 * lo)) - 1u));
     x = ((x >> (2 * hi)) << (2 * hi + 2)) | (x & ((1u << (2 * hi)) - 1u));
+    const uint32_t px = oc_phys(x) << 3;
     double v[1][16];
 #pragma unroll
     for (int b = 0; b < 4; ++b)
 #pragma unroll
-      for (int a = 0; a < 4; ++a) v[0][a + 4 * b] = W.st[x + (a << (2 * da)) + (b << (2 * db))];
+      for (int a = 0; a < 4; ++a) v[0][a + 4 * b] = *reinterpret_cast<const double*>(base + (px ^ oa[a] ^ ob[b]));
     if (pa) op_dense1<false, 1>(v, W.pend + 16 * da);
     if (pb) op_dense1<true, 1>(v, W.pend + 16 * db);
-    for (int r = 0; r < reps; ++r) {
-      if (kind == BWQ_NOISE_RELAX2) op_relax2<false, true, 1>(v, nm);
-      else {
-        op_cx<false, 1>(v);
-        if (kind == BWQ_NOISE_DENSE2) op_dense2<false, 1>(v, nm);
-      }
-    }
+    // folds are odd: one application, then pairs (the cx permutation is an involution, so a pair
+    // returns the register assignment to where it started: no moves at the loop edge)
+    if (reps & 1) onchip_cx(v, kind, nm);
+    for (int r = 0; r < (reps >> 1); ++r) { onchip_cx(v, kind, nm); onchip_cx(v, kind, nm); }
 #pragma unroll
     for (int b = 0; b < 4; ++b)
 #pragma unroll
-      for (int a = 0; a < 4; ++a) W.st[x + (a << (2 * da)) + (b << (2 * db))] = v[0][a + 4 * b];
+      for (int a = 0; a < 4; ++a) *reinterpret_cast<double*>(base + (px ^ oa[a] ^ ob[b])) = v[0][a + 4 * b];
   }
   W.has &= ~(1u << da);
   if (reps > 0) W.has &= ~(1u << db);
@@ -257,16 +302,22 @@ __global__ void __launch_bounds__(32 * kOnchipWarps, 16 / kOnchipWarps) dm_onchi
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const int n_var = L.n_folds * L.n_twirls;
   const int64_t w = (int64_t)blockIdx.x * kOnchipWarps + warp;
-  if (w >= (int64_t)L.n_circuits * n_var) return;
+  if (w >= (int64_t)L.n_circuits * (n_var + L.with_ideal)) return;
   // variant-major launch order, last variant first: the folds are ascending, so the longest
-  // circuits (highest noise factor) start first and the short ones fill the tail
-  const int c = (int)(w % L.n_circuits), vi = n_var - 1 - (int)(w / L.n_circuits);
-  const int fac = L.folds ? __ldg(L.folds + vi / L.n_twirls) : 1;
+  // circuits (highest noise factor) start first and the short ones (the ideal side last) fill the tail
+  const int c = (int)(w % L.n_circuits);
+  const int v_rev = (int)(w / L.n_circuits);
+  const bool ideal = v_rev == n_var;
+  const int vi = ideal ? 0 : n_var - 1 - v_rev;
+  const int fac = (L.folds && !ideal) ? __ldg(L.folds + vi / L.n_twirls) : 1;
   const int tw = vi % L.n_twirls;
+  const bool twirl = L.twirl && !ideal;
+  OnchipNoise NZ = L.noise;
+  if (ideal) NZ = OnchipNoise{};
   const int nq = __ldg(L.n_qubits + c);
   const int64_t g0 = __ldg(L.op_offsets + c), g1 = __ldg(L.op_offsets + c + 1);
   const int64_t o0 = __ldg(L.obs_offsets + c), o1 = __ldg(L.obs_offsets + c + 1);
-  double* out = L.out + o0 * n_var + (int64_t)vi * (o1 - o0);
+  double* out = ideal ? L.out_ideal + o0 : L.out + o0 * n_var + (int64_t)vi * (o1 - o0);
 
   // ---- scan: active qubits and validity (status precedence of lower_dm_circuit)
   uint64_t used = 0;
@@ -299,7 +350,7 @@ __global__ void __launch_bounds__(32 * kOnchipWarps, 16 / kOnchipWarps) dm_onchi
   if (bad & 1u) status = BWQ_CIRC_BAD_QUBIT;
   else if (n_active > kOnchipMaxDigits || (bad & 4u)) status = kOnchipNotHandled;
   else if (bad & 2u) status = BWQ_CIRC_BAD_OP;
-  if (lane == 0) L.status[(int64_t)c * n_var + vi] = status;
+  if (lane == 0) { if (ideal) L.status_ideal[c] = status; else L.status[(int64_t)c * n_var + vi] = status; }
   if (status) {
     for (int64_t o = lane; o < o1 - o0; o += 32) out[o] = __longlong_as_double(0x7ff8000000000000ll);
     return;
@@ -313,7 +364,7 @@ __global__ void __launch_bounds__(32 * kOnchipWarps, 16 / kOnchipWarps) dm_onchi
   auto digit_of = [&](int q) { return __popcll(used & ((1ull << q) - 1ull)); };
 
   // ---- |0..0><0..0|: 1 on the {I, Z} strings
-  for (int j = lane; j < (1 << (2 * W.nd)); j += 32) W.st[j] = ((j ^ (j >> 1)) & 0x55555555) == 0 ? 1.0 : 0.0;
+  for (int j = lane; j < (1 << (2 * W.nd)); j += 32) W.st[oc_phys((uint32_t)j)] = ((j ^ (j >> 1)) & 0x55555555) == 0 ? 1.0 : 0.0;
   __syncwarp();
 
   // ---- the gate stream, 32 ops per fetch: every lane prepares ITS op (transfer matrix x error of a
@@ -322,17 +373,19 @@ __global__ void __launch_bounds__(32 * kOnchipWarps, 16 / kOnchipWarps) dm_onchi
   uint64_t k_cx = 0;
   for (int64_t gb = g0; gb < g1; gb += 32) {
     unsigned long long my_raw = 0ull, my_aux = 0ull;
+    uint32_t my_dig = 0u;  // opcode | digit(q0) << 16 | digit(q1) << 24
     if (gb + lane < g1) {
       my_raw = __ldg(reinterpret_cast<const unsigned long long*>(L.ops) + gb + lane);
       const uint32_t opc = (uint32_t)(my_raw & 0xffffu);
       const int q0 = (int)((my_raw >> 16) & 0xffu), q1 = (int)((my_raw >> 24) & 0xffu);
+      my_dig = opc | ((uint32_t)digit_of(q0) << 16) | ((uint32_t)digit_of(q1 & 63) << 24);
       if (opc == BWQ_G_CX) {
-        const int e = L.noise.cx ? __ldg(L.noise.cx + q0 * 64 + q1) : -1;
-        if (e >= 0) { const int2 en = __ldg(&L.noise.ent[e]); my_aux = ((unsigned long long)(uint32_t)en.x << 32) | (uint32_t)en.y; }
+        const int e = NZ.cx ? __ldg(NZ.cx + q0 * 64 + q1) : -1;
+        if (e >= 0) { const int2 en = __ldg(&NZ.ent[e]); my_aux = ((unsigned long long)(uint32_t)en.x << 32) | (uint32_t)en.y; }
       } else {
         const double* pp = L.params + (uint32_t)(my_raw >> 32);
         double g[16];
-        onchip_gate_matrix(L.noise, opc, q0, dev_num_params(opc) > 0 ? __ldg(pp) : 0.0, pp, g);
+        onchip_gate_matrix(NZ, opc, q0, dev_num_params(opc) > 0 ? __ldg(pp) : 0.0, pp, g);
         double2* dst = reinterpret_cast<double2*>(W.gbuf + lane * kOnchipGRow);
 #pragma unroll
         for (int i = 0; i < 8; ++i) dst[i] = make_double2(g[2 * i], g[2 * i + 1]);
@@ -341,19 +394,22 @@ __global__ void __launch_bounds__(32 * kOnchipWarps, 16 / kOnchipWarps) dm_onchi
     __syncwarp();
     const int cnt = (int)min((int64_t)32, g1 - gb);
     for (int k = 0; k < cnt; ++k) {
-      const unsigned long long raw = __shfl_sync(0xffffffffu, my_raw, k);
-      const uint32_t opc = (uint32_t)(raw & 0xffffu);
-      const int q0 = (int)((raw >> 16) & 0xffu), q1 = (int)((raw >> 24) & 0xffu);
-      if (opc != BWQ_G_CX) {
-        onchip_push1(W, digit_of(q0), W.gbuf + k * kOnchipGRow);
+      const uint32_t dig = __shfl_sync(0xffffffffu, my_dig, k);
+      const int da = (int)((dig >> 16) & 0xffu), db = (int)(dig >> 24);
+      if ((dig & 0xffffu) != BWQ_G_CX) {
+        onchip_push1(W, da, W.gbuf + k * kOnchipGRow);
         continue;
       }
       const unsigned long long aux = __shfl_sync(0xffffffffu, my_aux, k);
-      const int da = digit_of(q0), db = digit_of(q1);
+      int q0 = 0, q1 = 0;
+      if (twirl) {
+        const unsigned long long raw = __shfl_sync(0xffffffffu, my_raw, k);
+        q0 = (int)((raw >> 16) & 0xffu); q1 = (int)((raw >> 24) & 0xffu);
+      }
       // twirl Paulis are staged in the gate-matrix row of the cx itself (a cx leaves its row unused)
       double* scratch = W.gbuf + k * kOnchipGRow;
       int qc = 0, qt = 0;
-      if (L.twirl) {
+      if (twirl) {
         const uint32_t d = (uint32_t)(dev_splitmix64(dev_splitmix64(dev_splitmix64(L.seed ^ (uint64_t)c) ^ (uint64_t)tw) ^ k_cx) & 15u);
         ++k_cx;
         const int pc = (int)(d & 3u), pt = (int)(d >> 2);
@@ -362,13 +418,13 @@ __global__ void __launch_bounds__(32 * kOnchipWarps, 16 / kOnchipWarps) dm_onchi
         const int zc2 = zc ^ zt, xt2 = xt ^ xc;
         qc = xc ? (zc2 ? 2 : 1) : (zc2 ? 3 : 0);
         qt = xt2 ? (zt ? 2 : 1) : (zt ? 3 : 0);
-        onchip_pauli(W, L.noise, scratch, pc, q0, da);
-        onchip_pauli(W, L.noise, scratch, pt, q1, db);
+        onchip_pauli(W, NZ, scratch, pc, q0, da);
+        onchip_pauli(W, NZ, scratch, pt, q1, db);
       }
-      onchip_pair(W, da, db, fac, (int)(aux >> 32), L.noise.data + (uint32_t)aux);
-      if (L.twirl) {
-        onchip_pauli(W, L.noise, scratch, qc, q0, da);
-        onchip_pauli(W, L.noise, scratch, qt, q1, db);
+      onchip_pair(W, da, db, fac, (int)(aux >> 32), NZ.data + (uint32_t)aux);
+      if (twirl) {
+        onchip_pauli(W, NZ, scratch, qc, q0, da);
+        onchip_pauli(W, NZ, scratch, qt, q1, db);
       }
     }
     __syncwarp();
@@ -392,7 +448,7 @@ __global__ void __launch_bounds__(32 * kOnchipWarps, 16 / kOnchipWarps) dm_onchi
         const int xb = (int)((x >> q) & 1ull), zb = (int)((z >> q) & 1ull);
         idx += (uint32_t)(xb ? (zb ? 2 : 1) : 3) << (2 * digit_of(q));
       }
-      if (!zero) acc += __ldg(L.term_coeff + t) * W.st[idx];
+      if (!zero) acc += __ldg(L.term_coeff + t) * W.st[oc_phys(idx)];
     }
 #pragma unroll
     for (int s = 16; s > 0; s >>= 1) acc += __shfl_xor_sync(0xffffffffu, acc, s);

@@ -143,7 +143,7 @@ def test_onchip_variants_match_python_built_variants(lib):
     # folds only (cfg1's shape) and the (ideal, noisy) call
     vf = Variants(folds=(1, 3, 5))
     ideal, noisy, st_i, st_n = eng.run_meas_data_variants(fb, vf, noise=nm)
-    assert eng.stats()["n_onchip_circuits"] == len(base) * 3 and not st_i.any() and not st_n.any()
+    assert eng.stats()["n_onchip_circuits"] == len(base) * (3 + 1) and not st_i.any() and not st_n.any()  # + the ideal warps
     eng.set_options(flags=NO_ONCHIP)
     ideal_t, noisy_t, _, _ = eng.run_meas_data_variants(fb, vf, noise=nm)
     eng.set_options()
