@@ -275,6 +275,16 @@ int bwq_svx_upload(bwq_ctx* ctx, bwq_svx_program* p);
 int bwq_svx_run_segment(bwq_ctx* ctx, const bwq_svx_program* p, int32_t segment, double* d_state,
                         int32_t rank, double* d_obs, void* stream);
 
+/* A SWEEPS segment that is followed by an EXCHANGE, with the exchange FUSED into the store of its
+ * last sweep: sv_sweep_kernel writes the swept tiles straight into the peers' NEW shards
+ * (peer_dst[w] = rank w's new shard as mapped into this process, peer_dst[rank] the local one) --
+ * the separate read + write of the whole shard by bwq_svx_exchange_* disappears and the NVLink
+ * traffic overlaps the sweep's arithmetic.  d_state (the old shard) is left as the input of the
+ * last sweep.  The caller skips the EXCHANGE segment and places the cross-rank barrier after this
+ * call (all tiles have landed before anyone sweeps its new shard); world = 2^n_global <= 16. */
+int bwq_svx_run_segment_push(bwq_ctx* ctx, const bwq_svx_program* p, int32_t segment, double* d_state, int32_t rank,
+                             const uint64_t* peer_dst, int32_t world, void* stream);
+
 /* EXCHANGE segment over NVLink peer memory (the engine's own replacement for the NCCL
  * all_to_all): the top log2(world) local index bits swap with the rank bits, so block b of the
  * new shard d_dst is block `rank` of rank b's old shard.  peer_src[w] = device pointer to rank

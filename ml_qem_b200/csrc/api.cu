@@ -1288,7 +1288,7 @@ static int sv_wide_execute(bwq_ctx* ctx, double* d_out) {
   cudaStream_t st = ctx->stream;
   const char* db = (const char*)ctx->d_wide_prog.p;
   for (const SvWideChunk& ch : W.chunks) {
-    SvxLaunch L;
+    SvxLaunch L{};
     L.states = (double2*)ctx->d_states.p;
     L.stride = int64_t(1) << ch.nb;
     L.n_local = ch.nb; L.tile_bits = ch.tile_bits; L.low_bits = ch.low_bits;
@@ -1899,8 +1899,26 @@ extern "C" int bwq_svx_exchange_push(bwq_ctx* ctx, const double* d_src, const ui
   return svx_exchange_impl(ctx, const_cast<double*>(d_src), peer_dst, world, rank, n_local_amps, stream, true);
 }
 
+static int svx_run_segment_impl(bwq_ctx* ctx, const bwq_svx_program* h, int32_t segment, double* d_state, int32_t rank, double* d_obs,
+                                void* stream, const uint64_t* peer_dst, int32_t world);
+
 extern "C" int bwq_svx_run_segment(bwq_ctx* ctx, const bwq_svx_program* h, int32_t segment, double* d_state,
                                    int32_t rank, double* d_obs, void* stream) {
+  return svx_run_segment_impl(ctx, h, segment, d_state, rank, d_obs, stream, nullptr, 0);
+}
+
+extern "C" int bwq_svx_run_segment_push(bwq_ctx* ctx, const bwq_svx_program* h, int32_t segment, double* d_state, int32_t rank,
+                                        const uint64_t* peer_dst, int32_t world, void* stream) {
+  if (!ctx || !h || !peer_dst) return BWQ_ERR_ARG;
+  const SvxProgram& p = h->p;
+  if (segment < 0 || segment + 1 >= (int)p.segs.size() || p.segs[segment].kind != SVSEG_SWEEPS || p.segs[segment + 1].kind != SVSEG_EXCHANGE)
+    return fail(ctx, BWQ_ERR_ARG, "bwq_svx_run_segment_push: segment must be a SWEEPS segment followed by an EXCHANGE");
+  if (world != (1 << p.n_global) || world > kSvxMaxWorld) return fail(ctx, BWQ_ERR_ARG, "bwq_svx_run_segment_push: world must be 2^n_global (<= %d)", kSvxMaxWorld);
+  return svx_run_segment_impl(ctx, h, segment, d_state, rank, nullptr, stream, peer_dst, world);
+}
+
+static int svx_run_segment_impl(bwq_ctx* ctx, const bwq_svx_program* h, int32_t segment, double* d_state, int32_t rank, double* d_obs,
+                                void* stream, const uint64_t* peer_dst, int32_t world) {
   if (!ctx || !h || !d_state) return BWQ_ERR_ARG;
   if (!h->uploaded) return fail(ctx, BWQ_ERR_ARG, "bwq_svx_run_segment: call bwq_svx_upload first");
   const SvxProgram& p = h->p;
@@ -1920,7 +1938,7 @@ extern "C" int bwq_svx_run_segment(bwq_ctx* ctx, const bwq_svx_program* h, int32
   if (sg.kind == SVSEG_EXCHANGE)
     return fail(ctx, BWQ_ERR_UNSUPPORTED, "EXCHANGE segments are executed by the caller (all-to-all of the top local bits)");
   if (sg.kind == SVSEG_SWEEPS) {
-    SvxLaunch L;
+    SvxLaunch L{};
     L.states = (double2*)d_state; L.stride = stride;
     L.n_local = p.n_local; L.tile_bits = p.tile_bits; L.low_bits = std::max(0, p.tile_bits - kSvFreeSlots);
     L.first_circuit = 0; L.sweep_range = nullptr;
@@ -1929,7 +1947,13 @@ extern "C" int bwq_svx_run_segment(bwq_ctx* ctx, const bwq_svx_program* h, int32
     L.prog = (const uint4*)(db + h->o_prog);
     L.hi_bits = hi; L.init = 1;
     const int64_t tiles = int64_t(1) << (p.n_local - p.tile_bits);
-    for (int s = sg.first; s < sg.first + sg.count; ++s) CK(launch_sv_sweep(L, s, tiles, st));
+    for (int s = sg.first; s < sg.first + sg.count; ++s) {
+      if (peer_dst && s + 1 == sg.first + sg.count) {  // last sweep: its store is the EXCHANGE (P2P stores)
+        L.push_g = p.n_global; L.push_rank = rank;
+        for (int w = 0; w < world; ++w) L.push_ptr[w] = (double2*)peer_dst[w];
+      }
+      CK(launch_sv_sweep(L, s, tiles, st));
+    }
     return BWQ_OK;
   }
   if (!d_obs) return fail(ctx, BWQ_ERR_ARG, "EXPVAL segment needs d_obs");

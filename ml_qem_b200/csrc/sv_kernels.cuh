@@ -27,6 +27,12 @@ struct SvxLaunch {
   const uint4* prog;
   uint32_t hi_bits;            // rank << n_local: the global part of the physical index
   int32_t init;                // sweep_idx == 0 synthesises |0...0> instead of reading
+  // EXCHANGE fused into this sweep's store (push_g > 0, amplitude-sharded runs): the swept tile is
+  // written straight into the NEW shards of the peers over NVLink -- the top push_g local index
+  // bits of an amplitude select the destination rank, this rank's id takes their place (what
+  // svx_exchange_kernel<PUSH> does as a separate read + write of the whole shard)
+  int32_t push_g, push_rank;
+  double2* push_ptr[16];       // rank w's NEW shard as mapped into this process (kSvxMaxWorld entries)
 };
 
 constexpr int kSvxThreads = 256;
@@ -287,15 +293,22 @@ __global__ void __launch_bounds__(NT, NT == 256 ? 2 : 4) sv_sweep_kernel(const S
   // zero and stays zero -- nothing to do, except that the very first sweep has to store the zeros
   const bool first = L.init && sweep_idx == 0;
   const bool dead = (gbase & untouched) != 0u;
-  if (dead && !first) return;
+  const bool push = L.push_g > 0;
+  if (dead && !first && !push) return;  // (a pushed sweep still has to deliver the zeros to the new shards)
+  const int push_sh = L.n_local - L.push_g;
+  const uint32_t push_low = (1u << push_sh) - 1u, push_me = uint32_t(L.push_rank) << push_sh;
+  const int64_t slot_off = slot * L.stride;
   // deposit table of the 8 free slots (one entry per thread), after the program block
   uint32_t* dep = reinterpret_cast<uint32_t*>(pbuf + kBlockBytes / 8);
   for (int i = tid; i < 256; i += NT) dep[i] = svx_deposit_hi(uint32_t(i), pk);
   __syncthreads();
   const uint32_t lowmask = (1u << LB) - 1u;
 #define SVX_DEPOSIT(j) (((j) & lowmask) | dep[(j) >> LB])
+// destination of the amplitude with local index i when the sweep pushes its output to the peers
+#define SVX_PUSH_DST(i) (L.push_ptr[(i) >> push_sh] + slot_off + (push_me | ((i) & push_low)))
   if (dead) {
-    for (uint32_t u = tid; u < E; u += NT) __stcg(g + SVX_DEPOSIT(u), make_double2(0.0, 0.0));
+    if (push) { for (uint32_t u = tid; u < E; u += NT) { const uint32_t i = base | SVX_DEPOSIT(u); __stcg(SVX_PUSH_DST(i), make_double2(0.0, 0.0)); } }
+    else for (uint32_t u = tid; u < E; u += NT) __stcg(g + SVX_DEPOSIT(u), make_double2(0.0, 0.0));
     return;
   }
   {
@@ -350,7 +363,7 @@ __global__ void __launch_bounds__(NT, NT == 256 ? 2 : 4) sv_sweep_kernel(const S
     C.ph = ph;
     C.ops = reinterpret_cast<const uint2*>(pbuf) + ph->ops_q8;
     C.ld_g = p == 0 && first_direct;
-    C.st_g = (ph->flags & kPassStoreDirect) != 0u;
+    C.st_g = (ph->flags & kPassStoreDirect) != 0u && !push;  // pushed sweeps store from the staged tile
     stored = C.st_g;
     // thread -> tile-local index of its corner 0 (zeros at the four pass slots)
     uint32_t j = 0;
@@ -390,10 +403,18 @@ __global__ void __launch_bounds__(NT, NT == 256 ? 2 : 4) sv_sweep_kernel(const S
   if (stored) return;
   __syncthreads();
 
+  if (push) {
+    for (uint32_t u0 = 0; u0 < E; u0 += NT) {
+      const uint32_t u = u0 + tid;
+      if (u < E) { const uint32_t i = base | SVX_DEPOSIT(u); *SVX_PUSH_DST(i) = sv_tile[p_thr ^ svz12(u0)]; }
+    }
+    return;
+  }
   for (uint32_t u0 = 0; u0 < E; u0 += NT) {
     const uint32_t u = u0 + tid;
     if (u < E) g[SVX_DEPOSIT(u)] = sv_tile[p_thr ^ svz12(u0)];
   }
+#undef SVX_PUSH_DST
 #undef SVX_DEPOSIT
 }
 

@@ -86,7 +86,7 @@ EXPORTS = [
     "bwq_dm_run", "bwq_sv_run", "bwq_meas_data_run", "bwq_meas_data_run_variants", "bwq_dm_run_variants", "bwq_expand_variants", "bwq_dm_run_device_out", "bwq_dm_prepare", "bwq_dm_execute", "bwq_dm_execute_device_out", "bwq_sv_prepare", "bwq_sv_execute", "bwq_get_stats", "bwq_sync", "bwq_lower_dm", "bwq_lower_dm_ex",
     "bwq_program_free", "bwq_program_sizes", "bwq_program_read",
     "bwq_svx_lower", "bwq_svx_free", "bwq_svx_sizes", "bwq_svx_read", "bwq_svx_upload", "bwq_svx_run_segment",
-    "bwq_svx_bytes", "bwq_svx_exchange_pull", "bwq_svx_exchange_push",
+    "bwq_svx_bytes", "bwq_svx_exchange_pull", "bwq_svx_exchange_push", "bwq_svx_run_segment_push",
 ]
 
 
@@ -138,6 +138,7 @@ def load_library(path=None):
     lib.bwq_svx_bytes.argtypes = [C.c_void_p, C.c_int32]
     lib.bwq_svx_bytes.restype = C.c_int64
     lib.bwq_svx_run_segment.argtypes = [C.c_void_p, C.c_void_p, C.c_int32, C.c_void_p, C.c_int32, C.c_void_p, C.c_void_p]
+    lib.bwq_svx_run_segment_push.argtypes = [C.c_void_p, C.c_void_p, C.c_int32, C.c_void_p, C.c_int32, C.c_void_p, C.c_int32, C.c_void_p]
     for f in (lib.bwq_svx_exchange_pull, lib.bwq_svx_exchange_push):
         f.argtypes = [C.c_void_p, C.c_void_p, C.c_void_p, C.c_int32, C.c_int32, C.c_int64, C.c_void_p]
     if path is None:
@@ -574,6 +575,14 @@ class SvxProgram:
 
     def upload(self, engine):
         engine._check(self._lib.bwq_svx_upload(engine._ctx, self._h), "bwq_svx_upload")
+
+    def run_segment_push(self, engine, segment, state_ptr, rank, peer_ptrs, stream=0):
+        """SWEEPS segment whose last sweep stores into the peers' new shards (the EXCHANGE that
+        follows it is skipped by the caller): bwq_svx_run_segment_push."""
+        peers = np.asarray(peer_ptrs, dtype=np.uint64)
+        engine._check(self._lib.bwq_svx_run_segment_push(engine._ctx, self._h, int(segment), C.c_void_p(int(state_ptr)), int(rank),
+                                                         peers.ctypes.data_as(C.c_void_p), len(peers),
+                                                         C.c_void_p(int(stream)) if stream else None), "bwq_svx_run_segment_push")
 
     def run_segment(self, engine, segment, state_ptr, rank=0, obs_ptr=0, stream=0):
         engine._check(self._lib.bwq_svx_run_segment(engine._ctx, self._h, int(segment), C.c_void_p(int(state_ptr)),

@@ -136,29 +136,40 @@ class B200Estimator:
                 observables and isinstance(observables[0], tuple) and isinstance(observables[0][0], str)):
             observables = [observables]
         circuits = tuple(circuits)
-        # the same observable / circuit objects usually repeat over the pairs: convert and inspect once
-        conv = {}
-        observables = tuple(conv[id(o)] if id(o) in conv else conv.setdefault(id(o), observable_mod.from_any(o)) for o in observables)
+        # the same observable / circuit objects usually repeat over the pairs (thousands of pairs for
+        # small circuits): everything below works on the UNIQUE objects, the per-pair work is C-level
+        # map/zip only
+        ids_o = list(map(id, observables))
+        conv = {i: observable_mod.from_any(o) for i, o in dict(zip(ids_o, observables)).items()}
+        observables = tuple(map(conv.__getitem__, ids_o))
         if parameter_values is None:
-            parameter_values = [()] * len(circuits)
+            parameter_values = ((),) * len(circuits)
         else:
             parameter_values = list(parameter_values)
             if parameter_values and not isinstance(parameter_values[0], (list, tuple, np.ndarray)):
                 parameter_values = [parameter_values]
-        parameter_values = tuple(tuple(float(v) for v in pv) for pv in parameter_values)
+            parameter_values = tuple(tuple(float(v) for v in pv) for pv in parameter_values)
         if len(circuits) != len(observables):
             raise ValueError(f"The number of circuits ({len(circuits)}) does not match the number of observables ({len(observables)}).")
         if len(circuits) != len(parameter_values):
             raise ValueError(f"The number of circuits ({len(circuits)}) does not match the number of parameter value sets ({len(parameter_values)}).")
+        ids_c = list(map(id, circuits))
+        cobj = dict(zip(ids_c, circuits))
+        oobj = {id(o): o for o in conv.values()}
         shape = {}  # id(circuit) -> (number of parameters, number of qubits)
-        for i, (c, o, pv) in enumerate(zip(circuits, observables, parameter_values)):
-            if id(c) not in shape:
-                shape[id(c)] = ((getattr(c, "num_parameters", 0), c.num_qubits) if not isinstance(c, str)
-                                else (0, circuit_mod.from_any(c).num_qubits))
-            npar, nq = shape[id(c)]
-            if len(pv) != npar:
-                raise ValueError(f"The number of values ({len(pv)}) does not match the number of parameters ({npar}) for the {i}-th circuit.")
-            if len(o) and o.num_qubits != nq:
+        for ic, io, npv in set(zip(ids_c, map(id, observables), map(len, parameter_values))):
+            if ic not in shape:
+                c = cobj[ic]
+                shape[ic] = ((getattr(c, "num_parameters", 0), c.num_qubits) if not isinstance(c, str)
+                             else (0, circuit_mod.from_any(c).num_qubits))
+            npar, nq = shape[ic]
+            o = oobj[io]
+            if npv != npar or (len(o) and o.num_qubits != nq):
+                # first offending pair, in pair order (the message names it)
+                i = next(k for k, (a, b, pv) in enumerate(zip(ids_c, observables, parameter_values))
+                         if a == ic and id(b) == io and len(pv) == npv)
+                if npv != npar:
+                    raise ValueError(f"The number of values ({npv}) does not match the number of parameters ({npar}) for the {i}-th circuit.")
                 raise ValueError(f"The number of qubits of the {i}-th circuit ({nq}) does not match the number of qubits of the {i}-th observable ({o.num_qubits}).")
         opts = dict(self._options)
         opts.update(run_options)
@@ -181,22 +192,22 @@ class B200Estimator:
         shots = run_options.get("shots")
         if shots not in (None, 0):
             raise ValueError("B200Estimator is exact: run with shots=None")
-        bound, keys = [], {}
-        groups = []  # unique (circuit, params) -> list of observable indices: one evolution serves all
-        for i, (c, pv) in enumerate(zip(circuits, parameter_values)):
-            key = (id(c), pv)
-            if key not in keys:
-                if pv:
-                    if hasattr(c, "assign_parameters"):
-                        b = c.assign_parameters(list(pv))
-                    else:
-                        b = c.bind_parameters(list(pv))
-                else:
-                    b = c
-                keys[key] = len(bound)
-                bound.append(circuit_mod.from_any(b))
-                groups.append([])
-            groups[keys[key]].append(i)
+        # unique (circuit, params) -> the pairs that use it: one evolution serves all its observables
+        first = {}
+        gidx = [first.setdefault(k, len(first)) for k in zip(map(id, circuits), parameter_values)]
+        bound = []
+        for (_, pv), i in zip(first, np.unique(np.asarray(gidx, dtype=np.int64), return_index=True)[1].tolist()):
+            c = circuits[i]
+            if pv:
+                c = c.assign_parameters(list(pv)) if hasattr(c, "assign_parameters") else c.bind_parameters(list(pv))
+            bound.append(circuit_mod.from_any(c))
+        g_arr = np.asarray(gidx, dtype=np.int64)
+        order = np.argsort(g_arr, kind="stable")
+        counts = np.bincount(g_arr, minlength=len(first))
+        if len(first) and counts.min() == counts.max():
+            groups = order.reshape(len(first), -1).tolist()
+        else:
+            groups = [g.tolist() for g in np.split(order, np.cumsum(counts)[:-1])] if len(first) else []
         # complex coefficients (Aer returns np.real_if_close of the complex sum): the C ABI takes
         # real coefficients, so such an observable is evaluated as <Re O> + i <Im O>
         is_cplx = {}
@@ -222,6 +233,9 @@ class B200Estimator:
                 c = int(bad[0])
                 raise ValueError(f"circuit {groups[c][0]}: {STATUS_TEXT.get(int(status[c]), 'error')}")
             out = np.empty(len(circuits), dtype=complex if cplx else float)
+            if not cplx:
+                out[order] = vals  # group-major value order == the stable order of the pairs by group
+                return out
             k = 0
             for g in groups:
                 for i in g:
@@ -233,7 +247,8 @@ class B200Estimator:
                         k += 1
             return out
 
-        meta = [{"simulator_metadata": {"method": method, "device": f"cuda:{self._device}"}} for _ in circuits]
+        sim_meta = {"method": method, "device": f"cuda:{self._device}"}
+        meta = [{"simulator_metadata": sim_meta} for _ in circuits]
         strategy = run_options.get("zne_strategy")
         variants = run_options.get("variants")
         if variants is not None:
@@ -256,6 +271,15 @@ class B200Estimator:
                 base = evaluate(batch)
                 per = [np.repeat(base[g][None, :], nf * nt, axis=0) for g in (np.asarray(g) for g in groups)]
             out = np.empty(len(circuits), dtype=float)
+            gs = len(groups[0]) if groups else 0
+            if groups and strategy is None and all(len(g) == gs for g in groups):
+                # equal group sizes (the usual [circuit] * k pairs): no per-pair arithmetic in Python
+                cube = np.stack(per).reshape(len(groups), nf, nt, gs)        # [group, fold, twirl, obs]
+                out[order] = cube[:, 0].mean(axis=1).reshape(-1)
+                views = list(np.ascontiguousarray(cube.transpose(0, 3, 1, 2)).reshape(-1, nf, nt))  # (group, obs) -> [fold, twirl]
+                for i, vw in zip(order.tolist(), views):
+                    meta[i]["variants"] = {"folds": variants.folds, "twirls": variants.twirls, "seed": variants.seed, "values": vw}
+                return EstimatorResult(out, meta)
             for g, v in zip(groups, per):
                 fold_means = v.reshape(nf, nt, len(g)).mean(axis=1)  # [fold, obs]
                 for j, i in enumerate(g):

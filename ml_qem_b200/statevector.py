@@ -80,6 +80,12 @@ class GpuExecutor:
             cache[n_amp] = None
         return cache[n_amp]
 
+    def run_segment_push(self, program, seg, src, dst, rank):
+        """SWEEPS segment + the EXCHANGE after it in one go: the last sweep of the segment writes its
+        tiles into the peers' new shards (P2P stores from sv_sweep_kernel), barrier after."""
+        program.run_segment_push(self.engine, seg, src[0].data_ptr(), rank, dst[2], self._stream())
+        dst[1].barrier(channel=0)
+
     def exchange(self, src, dst, rank, world):
         """src/dst: entries of exchange_buffers().  Cross-rank barrier (every peer has finished
         writing its old shard; it also fences the previous pull out of ``dst``), then the pull."""
@@ -145,7 +151,25 @@ class ShardedStatevector:
                 marks.append((kind, ev))
 
         mark("begin")
-        for seg, (kind, first, count, _) in enumerate(info["segs"]):
+        import os
+        fuse = xbuf is not None and hasattr(self.ex, "run_segment_push") and os.environ.get("BWQ_SVX_FUSED_EXCHANGE", "1") != "0"
+        segs = info["segs"]
+        fused = fused_sweeps = 0
+        skip = False
+        for seg, (kind, first, count, _) in enumerate(segs):
+            if skip:  # the EXCHANGE that the previous segment's last sweep already performed
+                skip = False
+                continue
+            if fuse and kind == SEG_SWEEPS and seg + 1 < len(segs) and segs[seg + 1][0] == SEG_EXCHANGE:
+                self.ex.run_segment_push(prog, seg, cur, other, self.rank)
+                cur, other = other, cur
+                state, spare = spare, state
+                exchanged_bytes += state.numel() * 16 * (self.world - 1) // self.world
+                fused += 1
+                fused_sweeps += int(count)
+                skip = True
+                mark("sweeps+exchange")
+                continue
             if kind == SEG_EXCHANGE:
                 # block v of rank s <-> block s of rank v: top g local bits swap with the rank bits
                 if xbuf is not None:
@@ -164,7 +188,7 @@ class ShardedStatevector:
             mark("allreduce")
         self.last_plan = {"n_bits": info["n_bits"], "n_local": info["n_local"], "n_sweeps": len(info["sweeps"]),
                           "n_passes": info["n_passes"], "n_exchanges": info["n_exchanges"],
-                          "exchanged_bytes_per_rank": exchanged_bytes,
+                          "exchanged_bytes_per_rank": exchanged_bytes, "fused_exchanges": fused, "n_sweeps_in_fused_segments": fused_sweeps,
                           "exchange_impl": "own P2P kernel over symmetric memory (bwq_svx_exchange_push/pull)" if xbuf is not None else "nccl all_to_all",
                           "kernel_bytes": prog.algorithmic_bytes(self.rank),
                           "n_expval_passes": int(sum(-(-int(c) // 32) for k, _, c, _ in info["segs"] if k == SEG_EXPVAL))}

@@ -244,21 +244,41 @@ def test_svx_simulated_ranks_on_one_gpu(engine_gpu, g):
         shards = [torch.empty(1 << nl, dtype=torch.complex128, device=dev) for _ in range(G)]
         vals = torch.zeros(info["n_observables"], dtype=torch.float64, device=dev)
         blk = 1 << (nl - g)
-        for seg, (kind, first, count, _) in enumerate(info["segs"]):
-            if kind == engine.SEG_EXCHANGE:
-                torch.cuda.synchronize()
-                new = [torch.empty_like(s) for s in shards]
-                for s in range(G):
-                    for v in range(G):
-                        new[v][s * blk:(s + 1) * blk] = shards[s][v * blk:(v + 1) * blk]
-                shards = new
-                torch.cuda.synchronize()
-            else:
-                for r in range(G):
-                    prog.run_segment(engine_gpu, seg, shards[r].data_ptr(), r, vals.data_ptr())
-                engine_gpu.sync()
         ref = helpers.oracle_sv_values(circ, obs)
-        assert np.max(np.abs(vals.cpu().numpy() - ref)) <= TOL
+        # fused = True: the EXCHANGE rides on the store of the preceding sweep (bwq_svx_run_segment_push:
+        # P2P stores into the peers' new shards -- here same-device "peers"); the new shards start as
+        # NaN so a tile the pushed sweep failed to deliver (e.g. a known-zero one) cannot go unnoticed
+        for fused in (False, True):
+            vals.zero_()
+            segs = info["segs"]
+            skip = False
+            n_fused = 0
+            for seg, (kind, first, count, _) in enumerate(segs):
+                if skip:
+                    skip = False
+                    continue
+                if fused and kind == engine.SEG_SWEEPS and seg + 1 < len(segs) and segs[seg + 1][0] == engine.SEG_EXCHANGE:
+                    new = [torch.full_like(s, float("nan")) for s in shards]
+                    for r in range(G):
+                        prog.run_segment_push(engine_gpu, seg, shards[r].data_ptr(), r, [t.data_ptr() for t in new])
+                    engine_gpu.sync()
+                    shards = new
+                    skip = True
+                    n_fused += 1
+                elif kind == engine.SEG_EXCHANGE:
+                    torch.cuda.synchronize()
+                    new = [torch.empty_like(s) for s in shards]
+                    for s in range(G):
+                        for v in range(G):
+                            new[v][s * blk:(s + 1) * blk] = shards[s][v * blk:(v + 1) * blk]
+                    shards = new
+                    torch.cuda.synchronize()
+                else:
+                    for r in range(G):
+                        prog.run_segment(engine_gpu, seg, shards[r].data_ptr(), r, vals.data_ptr())
+                    engine_gpu.sync()
+            assert np.max(np.abs(vals.cpu().numpy() - ref)) <= TOL, fused
+            assert not fused or n_fused >= 1
         prog.close()
 
 
