@@ -428,7 +428,7 @@ def bench_dm(ctx, name, steps, warmup, scale=1.0, cpu_budget=15.0, cpu_first=Non
         dev_ms += s["kernel_ms"]; sweep_ms += s["sweep_kernel_ms"]
         launches += s["n_sweep_launches"] + s["n_other_launches"]
         swept += s["state_bytes_swept"]; sweeps += s["n_state_sweeps"]
-        n_sweep_launches = s["n_sweep_launches"]; n_passes = s["n_passes"]
+        n_sweep_launches = s["n_sweep_launches"]; n_passes = s["n_passes"]; n_tma_launches = s["n_tma_sweep_launches"]
         ideal = eng.execute_sv()
         s = eng.stats()
         dev_ms += s["kernel_ms"]
@@ -535,7 +535,8 @@ def bench_dm(ctx, name, steps, warmup, scale=1.0, cpu_budget=15.0, cpu_first=Non
     achieved = swept / (sweep_ms / 1e3) / 1e9 if sweep_ms > 0 else 0.0
     on_chip = wl["desc"]["n_qubits"] <= 6
     roofline = {"bound": "hbm", "achieved": achieved, "peak": ctx.peak, "unit": "GB/s", "frac": achieved / ctx.peak,
-                "traffic": None, "kernel": "dm_sweep_kernel<%d,false>" % min(6, wl["desc"]["n_qubits"]),
+                "traffic": None, "kernel": ("dm_sweep_tma_kernel<false> (TMA tile load/store)" if n_tma_launches else
+                           "dm_sweep_kernel<%d,false>" % min(6, wl["desc"]["n_qubits"])),
                 "peak_source": ctx.peak_src,
                 "bytes_definition": "actual layout: 2 x 8 B x 4^n per state sweep (real Pauli-basis elements); "
                                     "SURVEY 8(d) counts the reference's complex128 layout, 2 x 16 B x 4^n",

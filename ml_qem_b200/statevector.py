@@ -152,7 +152,13 @@ class ShardedStatevector:
 
         mark("begin")
         import os
-        fuse = xbuf is not None and hasattr(self.ex, "run_segment_push") and os.environ.get("BWQ_SVX_FUSED_EXCHANGE", "1") != "0"
+        # the EXCHANGE fused into the store of the sweep before it (bwq_svx_run_segment_push).  Measured on
+        # tfim30 (profiles/r2/bench_n{2,8}_tfim30_sv_*): 2 GPUs 74.0 -> 68.1 ms per circuit (half of every tile
+        # stays local, the rest leaves in runs the sweep produces anyway); 8 GPUs 20.8 -> 22.3 ms (7/8 of the
+        # stores cross NVLink as 128-byte runs: 413 GB/s against 696 GB/s of the streaming exchange kernel) --
+        # so it is the default on 2 ranks only; BWQ_SVX_FUSED_EXCHANGE=1 / 0 forces it on / off
+        want = os.environ.get("BWQ_SVX_FUSED_EXCHANGE", "auto")
+        fuse = xbuf is not None and hasattr(self.ex, "run_segment_push") and (want == "1" or (want == "auto" and self.world == 2))
         segs = info["segs"]
         fused = fused_sweeps = 0
         skip = False
