@@ -13,7 +13,7 @@ to the simulator in the reference), plus the ZNE-folded and Pauli-twirled varian
 
 Basis decompositions (global phase dropped): rx(t) = rz(pi/2) sx rz(t+pi) sx rz(5pi/2);
 u3(t,p,l) = rz(l) sx rz(t+pi) sx rz(p+3pi); h = rz(pi/2) sx rz(pi/2); cz = h_t cx h_t;
-p(l) = rz(l); sdg = rz(-pi/2).  tests/test_families.py checks them against the oracle.
+p(l) = rz(l); sdg = rz(-pi/2).  tests/test_host_regressions.py checks them against the oracle gate table.
 """
 import math
 

@@ -136,8 +136,15 @@ class ShardedStatevector:
             cur, other = xbuf
             state, spare = cur[0], other[0]
         else:
-            state = torch.empty(n_amp, dtype=torch.complex128, device=dev)
-            spare = torch.empty(n_amp, dtype=torch.complex128, device=dev) if info["n_exchanges"] else None
+            # shard buffers are kept between calls (a 30-qubit shard is a 17 GB allocation)
+            cache = self.__dict__.setdefault("_shards", {})
+            key = (n_amp, str(dev))
+            if key not in cache:
+                cache.clear()
+                cache[key] = [torch.empty(n_amp, dtype=torch.complex128, device=dev), None]
+            if info["n_exchanges"] and cache[key][1] is None:
+                cache[key][1] = torch.empty(n_amp, dtype=torch.complex128, device=dev)
+            state, spare = cache[key]
         obs = torch.zeros(max(1, info["n_observables"]), dtype=torch.float64, device=dev)
         self.ex.init_state(state, self.rank)
         exchanged_bytes = 0

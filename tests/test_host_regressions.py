@@ -102,3 +102,30 @@ def test_learning_skip_transpile_false_warns_without_qiskit():
         import qiskit  # noqa: F401
     except Exception:  # noqa: BLE001
         assert any("no transpiler" in str(x.message) for x in w)
+
+
+def test_basis_decompositions_equal_their_gates_up_to_phase():
+    """families.BasisBuilder: rx / u3 / h / Paulis written in the backend basis (rz, sx, x) are the
+    named gates up to a global phase (matrices from the oracle's gate table)."""
+    from oracle import gates as G
+    from ml_qem_b200.families import BasisBuilder
+
+    def unitary(build):
+        b = BasisBuilder(1)
+        build(b)
+        u = np.eye(2, dtype=complex)
+        for name, _, params in b.done().gate_ops():
+            u = G.gate_matrix(name, params) @ u
+        return u
+
+    def same_up_to_phase(a, b):
+        k = np.argmax(np.abs(b))
+        ph = a.reshape(-1)[k] / b.reshape(-1)[k]
+        return abs(abs(ph) - 1) < 1e-12 and np.max(np.abs(a - ph * b)) < 1e-12
+
+    for t in (-2.7, 0.3, 1.9):
+        assert same_up_to_phase(unitary(lambda b: b.rx(t, 0)), G.gate_matrix("rx", (t,)))
+        assert same_up_to_phase(unitary(lambda b: b.u3(t, 0.4, -1.1, 0)), G.gate_matrix("u3", (t, 0.4, -1.1)))
+    assert same_up_to_phase(unitary(lambda b: b.h(0)), G.gate_matrix("h"))
+    for p, name in ((1, "x"), (2, "y"), (3, "z")):
+        assert same_up_to_phase(unitary(lambda b: b.pauli(p, 0)), G.gate_matrix(name))
