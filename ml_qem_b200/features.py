@@ -353,3 +353,88 @@ def encode_data_flat(batch, properties, ideal_exp_vals, noisy_exp_vals, num_qubi
         Xt[:, nv + ng + n_bins + num_qubits:] = torch.tensor(meas_bases, dtype=torch.float32).to(Xt.device)
     ideal = ideal_exp_vals if torch.is_tensor(ideal_exp_vals) else torch.tensor(np.asarray(ideal_exp_vals, dtype=np.float64))
     return Xt, ideal.to(Xt.device, torch.float32)
+
+
+def graph_tensors_flat(batch, properties, use_gate_features=False, use_qubit_features=False):
+    """``circuit_to_graph_data_json`` for a whole FlatBatch, computed from the flat gate stream (no
+    per-circuit dicts, no Python loop over gates): the DAGOpNode feature matrix of every gate of
+    every circuit and the DAGOpNode_wire_DAGOpNode edges (consecutive gates on a qubit wire), i.e.
+    exactly what the graph model consumes (loaders/exp_val.py:63-89 keeps only these).  The gate
+    stream carries no barriers / measurements (``Circuit.flat`` strips final measurements).
+
+    Returns a dict of numpy arrays: ``x`` [n_ops, n_features] float32, ``edge_src`` / ``edge_dst``
+    (global op indices, in the order circuit_to_graph_data_json emits them: by destination gate,
+    then by the gate's qubit order), ``op_offsets`` [n_circuits + 1] and ``edge_offsets``
+    [n_circuits + 1].  tests/test_features.py checks it against the per-circuit function."""
+    from .gateset import NAMES, NUM_PARAMS, OPCODES
+
+    types = [canonical(g) for g in properties["gates_set"]] + ["barrier", "measure"]
+    ops = batch.ops
+    n_ops = len(ops)
+    opc = ops["opcode"].astype(np.int64)
+    col_of = np.full(max(NAMES) + 1, -1, dtype=np.int64)
+    for j, g in enumerate(types):
+        if g in OPCODES:
+            col_of[OPCODES[g]] = j
+    cols = col_of[opc]
+    if n_ops and cols.min() < 0:
+        bad = NAMES[int(opc[np.argmin(cols)])]
+        raise ValueError(f"gate {bad!r} is not in the backend's gate set {properties['gates_set']}")
+    two = np.zeros(max(NAMES) + 1, dtype=bool)
+    npar_of = np.zeros(max(NAMES) + 1, dtype=np.int64)
+    for name, code in OPCODES.items():
+        two[code] = (32 <= code < 64) or name == "unitary2"
+        npar_of[code] = NUM_PARAMS.get(name, 0)
+    is2 = two[opc]
+    q0 = ops["q0"].astype(np.int64)
+    q1 = ops["q1"].astype(np.int64)
+    nt = len(types)
+    nf = 3 + nt + (9 if use_qubit_features else 0) + (2 if use_gate_features else 0)
+    x = np.zeros((n_ops, nf), dtype=np.float64)
+    # up to three gate parameters
+    npar = np.minimum(npar_of[opc], 3)
+    pidx = ops["param_idx"].astype(np.int64)
+    for k in range(3):
+        m = npar > k
+        x[m, k] = batch.params[pidx[m] + k]
+    x[np.arange(n_ops), 3 + cols] = 1.0
+    c = 3 + nt
+    if use_qubit_features:
+        qp = {int(k): v for k, v in properties["qubits_props"].items()}
+        nq = max(qp) + 1 if qp else 0
+        tab = np.zeros((nq + 1, 3))  # row nq = "no qubit"
+        for q, v in qp.items():
+            tab[q] = (v.get("t1", 0.0), v.get("t2", 0.0), v.get("readout_error", 0.0))
+        if n_ops and (q0.max() >= nq or (is2.any() and q1[is2].max() >= nq)):
+            raise KeyError("qubit without properties")
+        qb = np.where(is2, q1, nq)
+        for k in range(3):                       # layout: t1 x 3 qubits, t2 x 3, readout x 3 (third qubit never set)
+            x[:, c + 3 * k + 0] = tab[q0, k]
+            x[:, c + 3 * k + 1] = tab[qb, k]
+        c += 9
+    if use_gate_features:
+        key = opc * 65536 + q0 * 256 + np.where(is2, q1, 255)
+        uniq, inv = np.unique(key, return_inverse=True)
+        vals = np.zeros((len(uniq), 2))
+        for j, k in enumerate(uniq.tolist()):
+            name, a, b = NAMES[k >> 16], (k >> 8) & 255, k & 255
+            gp = properties["gate_props"].get(f"{name}_{a}" if b == 255 else f"{name}_{a}_{b}", {})
+            vals[j] = (gp.get("gate_error", 0.0), gp.get("gate_length", 0.0))
+        x[:, c:c + 2] = vals[inv]
+    # wire edges: incidences (op, qubit) sorted by (circuit, qubit, op); neighbours on the same wire are linked
+    n = batch.n_circuits
+    op_offsets = batch.op_offsets.astype(np.int64)
+    circ_of = np.repeat(np.arange(n, dtype=np.int64), np.diff(op_offsets))
+    op_idx = np.arange(n_ops, dtype=np.int64)
+    inc_op = np.concatenate([op_idx, op_idx[is2]])
+    inc_q = np.concatenate([q0, q1[is2]])
+    inc_slot = np.concatenate([np.zeros(n_ops, dtype=np.int64), np.ones(int(is2.sum()), dtype=np.int64)])
+    wire = circ_of[inc_op] * 256 + inc_q
+    order = np.lexsort((inc_op, wire))
+    w_s, o_s, s_s = wire[order], inc_op[order], inc_slot[order]
+    link = np.nonzero(w_s[1:] == w_s[:-1])[0]
+    src, dst, slot = o_s[link], o_s[link + 1], s_s[link + 1]
+    eorder = np.lexsort((slot, dst))
+    src, dst = src[eorder], dst[eorder]
+    edge_offsets = np.searchsorted(dst, op_offsets, side="left").astype(np.int64)
+    return {"x": x.astype(np.float32), "edge_src": src, "edge_dst": dst, "op_offsets": op_offsets, "edge_offsets": edge_offsets}

@@ -17,6 +17,7 @@ device tensors (e.g. filled by ``Engine.run_dm_into``) without a host round trip
 """
 import math
 
+import numpy as np
 import torch
 from torch import nn
 
@@ -120,20 +121,23 @@ class ASAPooling(nn.Module):
         rank = torch.arange(n, device=x.device) - start[sorted_batch]
         perm = order[rank < keep_n[sorted_batch]]
         x_out = xc[perm] * fitness[perm].unsqueeze(1)
-        # coarsened adjacency A' = S^T A S with S[j, cluster i] = score(j -> i), restricted to the kept clusters
+        # coarsened adjacency A' = S^T A S with S[j, cluster i] = score(j -> i), restricted to the kept
+        # clusters.  Only its sparsity pattern is used downstream (TransformerConv takes no edge
+        # weights), and PyG forms it with sparse products (structural non-zeros); here: two
+        # sparse x sparse products of 0/1 matrices -- the dense n x n form costs 2 TFLOP per pooling
+        # layer at 64 graphs x 200 nodes
         new_id = torch.full((n,), -1, dtype=torch.long, device=x.device)
         new_id[perm] = torch.arange(perm.numel(), device=x.device)
         m = perm.numel()
-        S = torch.zeros(n, m, dtype=x.dtype, device=x.device)
-        sel = new_id[dst] >= 0
-        S.index_put_((src[sel], new_id[dst][sel]), score[sel], accumulate=True)
-        A = torch.zeros(n, n, dtype=x.dtype, device=x.device)
-        A.index_put_((ei[0], ei[1]), torch.ones(ei.shape[1], dtype=x.dtype, device=x.device), accumulate=True)
-        Ac = S.t() @ A @ S
-        Ac.fill_diagonal_(0.0)
         new_batch = batch[perm]
-        same_graph = new_batch.unsqueeze(0) == new_batch.unsqueeze(1)
-        new_ei = torch.nonzero((Ac != 0) & same_graph, as_tuple=False).t().contiguous()
+        with torch.no_grad():
+            sel = new_id[dst] >= 0
+            one = lambda k: torch.ones(k, dtype=torch.float32, device=x.device)
+            S = torch.sparse_coo_tensor(torch.stack([src[sel], new_id[dst][sel]]), one(int(sel.sum())), (n, m)).coalesce()
+            A = torch.sparse_coo_tensor(ei, one(ei.shape[1]), (n, n)).coalesce()
+            Ac = torch.sparse.mm(S.t().coalesce(), torch.sparse.mm(A, S)).coalesce()
+            idx = Ac.indices()
+            new_ei = idx[:, idx[0] != idx[1]].contiguous()   # row-major order, as nonzero() of the dense form
         return x_out, new_ei, new_batch, perm
 
 
@@ -198,6 +202,44 @@ def graph_batch(entries, noisy=None, ideal=None, device="cpu"):
            "circuit_depth": torch.cat(deps).to(device), "observable": obs, "n_graphs": len(entries)}
     out["noisy_0"] = noisy.to(torch.float) if noisy is not None else torch.cat(n0).to(device)
     out["y"] = ideal.to(torch.float) if ideal is not None else torch.cat(ys).to(device)
+    return out
+
+
+def graph_batches_flat(flat, noisy, ideal, depth, batch_size, device="cpu", first=0, last=None, drop_last=True):
+    """Mini-batches in the layout of ``graph_batch`` straight from ``features.graph_tensors_flat``
+    (one vectorised pass over the gate stream of the whole dataset instead of a JSON graph, an
+    entry object and five tensors per circuit).  ``noisy`` / ``ideal``: [n_circuits, exp_value_size]
+    arrays or tensors (tensors on ``device`` are sliced in place -- the engine's zero-copy output);
+    ``depth``: [n_circuits].  Circuits ``first`` .. ``last`` in chunks of ``batch_size``; equal to
+    ``graph_batch`` on the same circuits (tests/test_gnn.py), self loops included."""
+    x_all = torch.from_numpy(flat["x"]).to(device)
+    oo, eo = flat["op_offsets"], flat["edge_offsets"]
+    src_all, dst_all = torch.from_numpy(flat["edge_src"]).to(device), torch.from_numpy(flat["edge_dst"]).to(device)
+    op_off = torch.from_numpy(oo).to(device)
+    n = len(oo) - 1
+    last = n if last is None else last
+    as_t = lambda a: a if torch.is_tensor(a) else torch.as_tensor(np.asarray(a), dtype=torch.float)
+    noisy, ideal, depth = as_t(noisy).to(device, torch.float), as_t(ideal).to(device, torch.float), as_t(depth).to(device, torch.float)
+    out = []
+    for a in range(first, last, batch_size):
+        b = min(a + batch_size, last)
+        if b - a < batch_size and drop_last:
+            break
+        o0, o1, e0, e1 = int(oo[a]), int(oo[b]), int(eo[a]), int(eo[b])
+        n_nodes = o1 - o0
+        sizes = op_off[a + 1:b + 1] - op_off[a:b]
+        batch = torch.repeat_interleave(torch.arange(b - a, device=device), sizes)
+        src, dst = src_all[e0:e1] - o0, dst_all[e0:e1] - o0
+        keep = src != dst
+        src, dst = src[keep], dst[keep]
+        loops = torch.arange(n_nodes, device=device)
+        # per graph: its wire edges, then its self loops (the order graph_batch produces)
+        ei = torch.stack([torch.cat([src, loops]), torch.cat([dst, loops])])
+        key = torch.cat([2 * batch[dst], 2 * batch + 1])
+        ei = ei[:, torch.argsort(key, stable=True)]
+        out.append({"x": x_all[o0:o1], "edge_index": ei, "batch": batch, "circuit_depth": depth[a:b].reshape(-1, 1),
+                    "observable": [torch.zeros(1, 0)] * (b - a), "n_graphs": b - a,
+                    "noisy_0": noisy[a:b].reshape(b - a, -1), "y": ideal[a:b].reshape(b - a, -1)})
     return out
 
 

@@ -5,6 +5,7 @@ training loop of gnn.py:282-378 on a tiny synthetic task."""
 import math
 
 import numpy as np
+import pytest
 import torch
 
 import helpers
@@ -62,6 +63,16 @@ def test_asapooling_keeps_half_of_every_graph_and_coarsens_inside_graphs():
         mine = torch.nonzero(batch == g).view(-1)
         top = mine[torch.argsort(fit[mine], descending=True)[:math.ceil(0.5 * len(mine))]]
         assert set(top.tolist()) == set(perm[bo == g].tolist())
+    # coarsened edges == the pattern of the dense S^T A S (S = assignment scores of the kept clusters)
+    n, m = x.shape[0], len(perm)
+    new_id = torch.full((n,), -1, dtype=torch.long)
+    new_id[perm] = torch.arange(m)
+    keep = new_id[ei_l[1]] >= 0
+    S = torch.zeros(n, m).index_put_((ei_l[0][keep], new_id[ei_l[1]][keep]), sc[keep].detach(), accumulate=True)
+    A = torch.zeros(n, n).index_put_((ei_l[0], ei_l[1]), torch.ones(ei_l.shape[1]), accumulate=True)
+    Ac = S.t() @ A @ S
+    Ac.fill_diagonal_(0.0)
+    assert torch.equal(eo, torch.nonzero(Ac != 0).t())
     xo.sum().backward()  # gradients reach the attention and the score network
     assert pool.att.weight.grad is not None and pool.gnn_score.lin1.weight.grad is not None
 
@@ -97,3 +108,34 @@ def test_model_forward_and_training_loop():
     noisy = torch.zeros(16, 4); ideal = torch.ones(16, 4)
     b = gnn.graph_batch(entries[:16], noisy=noisy, ideal=ideal)
     assert torch.equal(b["noisy_0"], noisy) and torch.equal(b["y"], ideal)
+
+
+def test_flat_graph_batches_equal_the_per_circuit_path():
+    """features.graph_tensors_flat + gnn.graph_batches_flat (one vectorised pass over the flat gate
+    stream) == circuit_to_graph_data_json + ExpValueEntry.to_tensors + graph_batch, tensor for tensor."""
+    from ml_qem_b200 import engine
+
+    rng = np.random.default_rng(5)
+    lima = backends.fake_lima()
+    props = FT.backend_properties_v1(lima)
+    circs = [F.tfim_circuit(4, 1 + i % 3, float(rng.uniform(0, 1)), layout=[0, 1, 3, 4], num_physical=5) for i in range(20)]
+    circs += [F.random_basis_circuit(5, int(rng.integers(12, 50)), rng, lima.coupling_map) for _ in range(12)]
+    ideal = rng.uniform(-1, 1, size=(len(circs), 4))
+    noisy = 0.8 * ideal
+    entries = [FT.ExpValueEntry(circuit_graph=FT.circuit_to_graph_data_json(c, props, use_qubit_features=True, use_gate_features=True),
+                                observable=[], ideal_exp_value=ideal[i].tolist(), noisy_exp_values=[noisy[i].tolist()],
+                                circuit_depth=c.size()) for i, c in enumerate(circs)]
+    fb = engine.encode_batch(circs, [[]] * len(circs))
+    flat = FT.graph_tensors_flat(fb, props, use_gate_features=True, use_qubit_features=True)
+    got = gnn.graph_batches_flat(flat, noisy, ideal, [c.size() for c in circs], batch_size=8)
+    assert len(got) == 4
+    for k, g in enumerate(got):
+        ref = gnn.graph_batch(entries[8 * k:8 * k + 8])
+        for key in ("x", "edge_index", "batch", "circuit_depth", "noisy_0", "y"):
+            assert torch.equal(g[key], ref[key]), (k, key)
+        assert g["n_graphs"] == ref["n_graphs"]
+    # a gate outside the backend's gate set is an error, as in the per-circuit function
+    from ml_qem_b200 import Circuit
+    c = Circuit(2); c.h(0)
+    with pytest.raises(ValueError):
+        FT.graph_tensors_flat(engine.encode_batch([c], [[]]), props)
