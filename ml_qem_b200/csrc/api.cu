@@ -965,6 +965,7 @@ static int onchip_run(bwq_ctx* ctx, const bwq_batch* b, const bwq_variants* v, b
   L.term_z = (const uint64_t*)(d + o_tz) - t_lo;
   L.term_coeff = (const double*)(d + o_tc) - t_lo;
   if (noisy) L.noise = ctx->oc_noise;
+  L.sv_mode = noisy ? 0 : 1;  // the ideal call keeps the statevector path's semantics (reset = unsupported op)
   double* d_vals = out_on_device ? out_vals : (double*)((char*)ctx->d_oc_out.p + st_bytes);
   L.out = d_vals - ob_lo * (int64_t)(n_folds * n_tw);
   L.status = (int32_t*)ctx->d_oc_out.p;

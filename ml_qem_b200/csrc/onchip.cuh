@@ -62,6 +62,9 @@ struct OnchipLaunch {
   int32_t with_ideal;
   double* out_ideal;
   int32_t* status_ideal;
+  // statevector semantics for the whole launch (bwq_sv_run): `reset` is not a unitary -- the
+  // statevector path reports BWQ_CIRC_BAD_OP for it (sv_lowering.cpp), and so do the ideal warps
+  int32_t sv_mode;
 };
 
 __device__ __forceinline__ int dev_num_params(uint32_t op) {
@@ -333,6 +336,7 @@ __global__ void __launch_bounds__(32 * kOnchipWarps, 16 / kOnchipWarps) dm_onchi
     if (two) used |= 1ull << op.q1;
     const int np = one ? dev_num_params(op.opcode) : 0;
     if (np && (int64_t)op.param_idx + np > L.n_params) bad |= 2u;
+    if (op.opcode == BWQ_G_RESET && (ideal || L.sv_mode)) bad |= 2u;
   }
   {
     const uint64_t valid = nq >= 64 ? ~0ull : ((1ull << max(nq, 0)) - 1ull);

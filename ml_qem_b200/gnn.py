@@ -133,8 +133,8 @@ class ASAPooling(nn.Module):
         with torch.no_grad():
             sel = new_id[dst] >= 0
             one = lambda k: torch.ones(k, dtype=torch.float32, device=x.device)
-            S = torch.sparse_coo_tensor(torch.stack([src[sel], new_id[dst][sel]]), one(int(sel.sum())), (n, m)).coalesce()
-            A = torch.sparse_coo_tensor(ei, one(ei.shape[1]), (n, n)).coalesce()
+            S = torch.sparse_coo_tensor(torch.stack([src[sel], new_id[dst][sel]]), one(int(sel.sum())), (n, m), check_invariants=False).coalesce()
+            A = torch.sparse_coo_tensor(ei, one(ei.shape[1]), (n, n), check_invariants=False).coalesce()
             Ac = torch.sparse.mm(S.t().coalesce(), torch.sparse.mm(A, S)).coalesce()
             idx = Ac.indices()
             new_ei = idx[:, idx[0] != idx[1]].contiguous()   # row-major order, as nonzero() of the dense form

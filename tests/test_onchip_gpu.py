@@ -63,14 +63,24 @@ def test_onchip_vs_oracle_and_tile_path_all_gates(engine_gpu):
     engine_gpu.set_options()
     assert not status_t.any() and np.max(np.abs(vals - vals_t)) <= 1e-12
     # ideal side: the same kernel without the noise table == the statevector oracle
+    # (a reset is not a unitary: status 1 and NaN, as on the statevector path proper)
     ideal, st = engine_gpu.run_sv(fb)
-    assert engine_gpu.stats()["n_onchip_circuits"] == len(circs) and not st.any()
-    keep = [i for i, c in enumerate(circs) if not any(g == "reset" for g, _, _ in c.gate_ops())]
+    assert engine_gpu.stats()["n_onchip_circuits"] == len(circs)
+    has_reset = [any(g == "reset" for g, _, _ in c.gate_ops()) for c in circs]
+    assert st.tolist() == [1 if r else 0 for r in has_reset] and any(has_reset) and not all(has_reset)
     off = np.cumsum([0] + [len(o) for o in obs])
-    for i in keep:
-        assert np.max(np.abs(ideal[off[i]:off[i + 1]] - helpers.oracle_sv_values(circs[i], obs[i]))) <= TOL, i
+    for i, r in enumerate(has_reset):
+        if r:
+            assert np.isnan(ideal[off[i]:off[i + 1]]).all()
+        else:
+            assert np.max(np.abs(ideal[off[i]:off[i + 1]] - helpers.oracle_sv_values(circs[i], obs[i]))) <= TOL, i
+    engine_gpu.set_options(flags=NO_ONCHIP)
+    ideal_t, st_t = engine_gpu.run_sv(fb)
+    engine_gpu.set_options()
+    assert st_t.tolist() == st.tolist() and np.nanmax(np.abs(ideal - ideal_t)) <= 1e-12
     both = engine_gpu.run_meas_data(fb, noise=nm)
-    assert np.array_equal(both[0], ideal) and np.array_equal(both[1], vals)
+    assert np.array_equal(both[0], ideal, equal_nan=True) and np.array_equal(both[1], vals)
+    assert both[2].tolist() == st.tolist() and not both[3].any()
 
 
 def test_onchip_status_codes_and_mixed_batches(engine_gpu):
