@@ -80,6 +80,7 @@ struct Planner {
   ZzLayer pending;
   uint64_t pending_qubits = 0;
   bool fuse_layers = true;
+  int zz_chunk = 62;                   // bonds per fused layer op (sharded runs use small chunks: see lower_svx_circuit)
 
   int32_t push(const double* m, int nd) {
     while (mats.size() % 2) mats.push_back(0.0);
@@ -126,7 +127,7 @@ struct Planner {
   void add_zz(int a, int b, cd pe, cd po) {
     bool dup = false;
     for (auto& pr : pending.pairs) dup = dup || (pr.first == a && pr.second == b) || (pr.first == b && pr.second == a);
-    if (!pending.pairs.empty() && (dup || pending.pe != pe || pending.po != po || pending.pairs.size() >= 62)) flush_zz();
+    if (!pending.pairs.empty() && (dup || pending.pe != pe || pending.po != po || (int)pending.pairs.size() >= zz_chunk)) flush_zz();
     pending.pairs.push_back({a, b});
     pending.pe = pe; pending.po = po;
     pending_qubits |= (1ull << a) | (1ull << b);
@@ -797,6 +798,10 @@ void lower_svx_circuit(const bwq_batch& b, int c, const SvxOptions& opt, SvxProg
   // need an exchange per Trotter layer instead of one per light cone; there the bonds stay separate
   // and are fused pass by pass at emission (merge_diagonal_runs)
   P.fuse_layers = std::getenv("BWQ_SVX_NO_FUSE") == nullptr && gl == 0;
+  if (const char* ce = std::getenv("BWQ_SVX_ZZ_CHUNK")) {  // experiment: chunked layer ops when sharded
+    const int c = std::atoi(ce);
+    if (c >= 2 && std::getenv("BWQ_SVX_NO_FUSE") == nullptr) { P.fuse_layers = true; P.zz_chunk = gl > 0 ? std::min(c, 62) : 62; }
+  }
   P.structured = std::getenv("BWQ_SVX_NO_STRUCT") == nullptr;
   P.n = n; P.g = gl; P.nl = n - gl;
   P.K = std::min(std::min(std::max(opt.tile_bits, 4), kSvTileBitsMax), P.nl);
