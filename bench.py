@@ -559,6 +559,13 @@ def bench_dm(ctx, name, steps, warmup, scale=1.0, cpu_budget=15.0, cpu_first=Non
                                  "HBM traffic is the 8-byte ops only"})
         roofline["frac"] = roofline["achieved"] / ctx.peak
         roofline.pop("achieved_survey_units", None); roofline.pop("frac_survey_units", None)
+        try:  # SURVEY 8(d), n <= 6 regime: report the FP64-pipe fraction (from the committed ncu capture of this kernel)
+            oc = json.load(open(os.path.join(ROOT, "profiles", "traffic.json"))).get(name, {})
+            if "fp64_pipe_pct" in oc:
+                roofline["on_chip_pipes_ncu"] = {k: oc[k] for k in ("fp64_pipe_pct", "issue_active_pct", "warps_active_pct") if k in oc}
+                roofline["on_chip_pipes_source"] = "profiles/r2/ncu_dm_onchip_cfg1.txt (ncu --set full of this kernel on this workload)"
+        except Exception:  # noqa: BLE001
+            pass
     traffic_path = os.path.join(ROOT, "profiles", "traffic.json")
     if os.path.exists(traffic_path):
         try:
@@ -618,7 +625,8 @@ def sub_summary(d):
     out = {"value": d["value"], "unit": d["unit"], "ms_per_step": d["ms_per_step"], "steps": d["steps"], "warmup": d["warmup"],
            "scaling": d["scaling"], "e2e": d["e2e"]["value"],
            "roofline": {"achieved": r["achieved"], "frac": r["frac"], "kernel": r["kernel"], "unit": r["unit"],
-                        "bytes_per_launch": r["bytes_per_launch"], "sweep_share_of_step": r.get("sweep_share_of_step")},
+                        "bytes_per_launch": r["bytes_per_launch"], "sweep_share_of_step": r.get("sweep_share_of_step"),
+                        **{k: r[k] for k in ("on_chip_pipes_ncu", "note", "tile_sweep_path") if k in r}},
            "max_abs_diff_vs_cpu": d.get("max_abs_diff_vs_cpu"), "gpu_launches": d["gpu_launches"],
            "config": d["config"]}
     if d.get("cpu_baseline"):
