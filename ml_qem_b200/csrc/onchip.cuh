@@ -87,6 +87,11 @@ __device__ __forceinline__ void dev_unitary1(uint32_t op, double p0, const doubl
   const double r = 0.70710678118654757;  // sqrt(0.5) as the host computes it
   u[0] = make_double2(1, 0); u[1] = make_double2(0, 0); u[2] = make_double2(0, 0); u[3] = make_double2(1, 0);
   switch (op) {
+    case BWQ_G_X: u[0].x = 0; u[1].x = 1; u[2].x = 1; u[3].x = 0; break;
+    case BWQ_G_Z: u[3].x = -1; break;
+    case BWQ_G_SX: u[0] = make_double2(.5, .5); u[1] = make_double2(.5, -.5); u[2] = make_double2(.5, -.5); u[3] = make_double2(.5, .5); break;
+    case BWQ_G_RZ: { double s, c; sincos(0.5 * p0, &s, &c); u[0] = make_double2(c, -s); u[3] = make_double2(c, s); break; }
+    case BWQ_G_P: { double s, c; sincos(p0, &s, &c); u[3] = make_double2(c, s); break; }
     case BWQ_G_Y: u[0].x = 0; u[1] = make_double2(0, -1); u[2] = make_double2(0, 1); u[3].x = 0; break;
     case BWQ_G_H: u[0].x = r; u[1].x = r; u[2].x = r; u[3].x = -r; break;
     case BWQ_G_S: u[3] = make_double2(0, 1); break;
@@ -300,6 +305,79 @@ __device__ __forceinline__ void onchip_pair(OnchipWarp& W, int da, int db, int r
   __syncwarp();
 }
 
+// Ideal side (and bwq_sv_run on small circuits): the noise-free state is pure, so the warp evolves
+// the 2^n <= 32 complex amplitudes instead of 4^n Pauli coefficients -- lane x owns amplitude x, a
+// 1-qubit gate is one butterfly through a shuffle, cx a conditional shuffle, <P> one partner
+// shuffle per Pauli term.  The 2x2 unitaries of a fetch of 32 ops are prepared 32 wide (one lane
+// per op) into the gate-matrix rows of shared memory, as on the noisy side.
+__device__ __forceinline__ void onchip_sv_warp(const OnchipLaunch& L, double* __restrict__ gbuf, int lane, uint64_t used,
+                                               int64_t g0, int64_t g1, int64_t o0, int64_t o1, double* __restrict__ out) {
+  auto digit_of = [&](int q) { return __popcll(used & ((1ull << q) - 1ull)); };
+  double2 psi = make_double2(lane == 0 ? 1.0 : 0.0, 0.0);
+  for (int64_t gb = g0; gb < g1; gb += 32) {
+    uint32_t my_dig = 0u;  // opcode | digit(q0) << 16 | digit(q1) << 24
+    if (gb + lane < g1) {
+      const unsigned long long raw = __ldg(reinterpret_cast<const unsigned long long*>(L.ops) + gb + lane);
+      const uint32_t opc = (uint32_t)(raw & 0xffffu);
+      const int q0 = (int)((raw >> 16) & 0xffu), q1 = (int)((raw >> 24) & 0xffu);
+      my_dig = opc | ((uint32_t)digit_of(q0) << 16) | ((uint32_t)digit_of(q1 & 63) << 24);
+      if (opc != BWQ_G_CX) {
+        const double* pp = L.params + (uint32_t)(raw >> 32);
+        double2 u[4];
+        dev_unitary1(opc, dev_num_params(opc) > 0 ? __ldg(pp) : 0.0, pp, u);
+        double2* dst = reinterpret_cast<double2*>(gbuf + lane * kOnchipGRow);
+#pragma unroll
+        for (int i = 0; i < 4; ++i) dst[i] = u[i];
+      }
+    }
+    __syncwarp();
+    const int cnt = (int)min((int64_t)32, g1 - gb);
+    for (int k = 0; k < cnt; ++k) {
+      const uint32_t dig = __shfl_sync(0xffffffffu, my_dig, k);
+      const int da = (int)((dig >> 16) & 0xffu), db = (int)(dig >> 24);
+      if ((dig & 0xffffu) == BWQ_G_CX) {  // control = q0: amplitudes with the control bit set swap along the target bit
+        const double vx = __shfl_xor_sync(0xffffffffu, psi.x, 1 << db), vy = __shfl_xor_sync(0xffffffffu, psi.y, 1 << db);
+        if ((lane >> da) & 1) psi = make_double2(vx, vy);
+        continue;
+      }
+      const double2* u = reinterpret_cast<const double2*>(gbuf + k * kOnchipGRow);
+      const double2 p = make_double2(__shfl_xor_sync(0xffffffffu, psi.x, 1 << da), __shfl_xor_sync(0xffffffffu, psi.y, 1 << da));
+      const bool hi = (lane >> da) & 1;
+      const double2 ua = hi ? u[3] : u[0], ub = hi ? u[2] : u[1];  // new = u[bit][bit] * mine + u[bit][1 - bit] * partner
+      psi = make_double2(ua.x * psi.x - ua.y * psi.y + ub.x * p.x - ub.y * p.y, ua.x * psi.y + ua.y * psi.x + ub.x * p.y + ub.y * p.x);
+    }
+    __syncwarp();
+  }
+  // <P> = sum_j conj(psi_j) phase(j ^ xm) psi_(j ^ xm), phase(k) = i^(#Y) (-1)^popc(k & zm)
+  for (int64_t o = o0; o < o1; ++o) {
+    const int64_t t0 = __ldg(L.term_offsets + o), t1 = __ldg(L.term_offsets + o + 1);
+    double acc = 0.0;
+    for (int64_t t = t0; t < t1; ++t) {
+      const uint64_t x = __ldg(L.term_x + t), z = __ldg(L.term_z + t);
+      uint32_t xm = 0, zm = 0;
+      uint64_t m = (x | z) & used;
+      while (m) {
+        const int q = __ffsll((long long)m) - 1;
+        m &= m - 1;
+        const int d = digit_of(q);
+        xm |= (uint32_t)((x >> q) & 1ull) << d;
+        zm |= (uint32_t)((z >> q) & 1ull) << d;
+      }
+      const double2 p = make_double2(__shfl_xor_sync(0xffffffffu, psi.x, xm), __shfl_xor_sync(0xffffffffu, psi.y, xm));
+      if ((x & ~used) != 0ull) continue;  // X / Y on an idle qubit (warp-uniform)
+      const int ny = __popc(xm & zm) & 3;
+      const double sgn = (__popc((uint32_t)(lane ^ xm) & zm) & 1) ? -1.0 : 1.0;
+      // conj(psi) * p = (re, im); times i^ny: real part is re, -im, -re, im for ny = 0..3
+      const double re = psi.x * p.x + psi.y * p.y, im = psi.x * p.y - psi.y * p.x;
+      const double v = ny == 0 ? re : ny == 1 ? -im : ny == 2 ? -re : im;
+      acc += __ldg(L.term_coeff + t) * sgn * v;
+    }
+#pragma unroll
+    for (int s = 16; s > 0; s >>= 1) acc += __shfl_xor_sync(0xffffffffu, acc, s);
+    if (lane == 0) out[o - o0] = acc;
+  }
+}
+
 __global__ void __launch_bounds__(32 * kOnchipWarps, 16 / kOnchipWarps) dm_onchip_kernel(const OnchipLaunch L) {
   extern __shared__ __align__(16) double s_dyn[];
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
@@ -357,6 +435,10 @@ __global__ void __launch_bounds__(32 * kOnchipWarps, 16 / kOnchipWarps) dm_onchi
   if (lane == 0) { if (ideal) L.status_ideal[c] = status; else L.status[(int64_t)c * n_var + vi] = status; }
   if (status) {
     for (int64_t o = lane; o < o1 - o0; o += 32) out[o] = __longlong_as_double(0x7ff8000000000000ll);
+    return;
+  }
+  if (ideal || L.sv_mode) {  // pure state: 2^n amplitudes in registers
+    onchip_sv_warp(L, s_dyn + warp * kOnchipWarpDoubles + (1 << (2 * kOnchipMaxDigits)) + kOnchipMaxDigits * 16, lane, used, g0, g1, o0, o1, out);
     return;
   }
   OnchipWarp W;
