@@ -24,7 +24,13 @@
 
 namespace bwq {
 
-constexpr int kOnchipMaxDigits = 5;
+#ifndef BWQ_ONCHIP_MAXD
+#define BWQ_ONCHIP_MAXD 5
+#endif
+#ifndef BWQ_ONCHIP_MINB
+#define BWQ_ONCHIP_MINB 16
+#endif
+constexpr int kOnchipMaxDigits = BWQ_ONCHIP_MAXD;
 #ifndef BWQ_ONCHIP_WARPS
 #define BWQ_ONCHIP_WARPS 1
 #endif
@@ -378,7 +384,7 @@ __device__ __forceinline__ void onchip_sv_warp(const OnchipLaunch& L, double* __
   }
 }
 
-__global__ void __launch_bounds__(32 * kOnchipWarps, 16 / kOnchipWarps) dm_onchip_kernel(const OnchipLaunch L) {
+__global__ void __launch_bounds__(32 * kOnchipWarps, BWQ_ONCHIP_MINB / kOnchipWarps) dm_onchip_kernel(const OnchipLaunch L) {
   extern __shared__ __align__(16) double s_dyn[];
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const int n_var = L.n_folds * L.n_twirls;
@@ -393,8 +399,6 @@ __global__ void __launch_bounds__(32 * kOnchipWarps, 16 / kOnchipWarps) dm_onchi
   const int fac = (L.folds && !ideal) ? __ldg(L.folds + vi / L.n_twirls) : 1;
   const int tw = vi % L.n_twirls;
   const bool twirl = L.twirl && !ideal;
-  OnchipNoise NZ = L.noise;
-  if (ideal) NZ = OnchipNoise{};
   const int nq = __ldg(L.n_qubits + c);
   const int64_t g0 = __ldg(L.op_offsets + c), g1 = __ldg(L.op_offsets + c + 1);
   const int64_t o0 = __ldg(L.obs_offsets + c), o1 = __ldg(L.obs_offsets + c + 1);
@@ -466,12 +470,12 @@ __global__ void __launch_bounds__(32 * kOnchipWarps, 16 / kOnchipWarps) dm_onchi
       const int q0 = (int)((my_raw >> 16) & 0xffu), q1 = (int)((my_raw >> 24) & 0xffu);
       my_dig = opc | ((uint32_t)digit_of(q0) << 16) | ((uint32_t)digit_of(q1 & 63) << 24);
       if (opc == BWQ_G_CX) {
-        const int e = NZ.cx ? __ldg(NZ.cx + q0 * 64 + q1) : -1;
-        if (e >= 0) { const int2 en = __ldg(&NZ.ent[e]); my_aux = ((unsigned long long)(uint32_t)en.x << 32) | (uint32_t)en.y; }
+        const int e = L.noise.cx ? __ldg(L.noise.cx + q0 * 64 + q1) : -1;
+        if (e >= 0) { const int2 en = __ldg(&L.noise.ent[e]); my_aux = ((unsigned long long)(uint32_t)en.x << 32) | (uint32_t)en.y; }
       } else {
         const double* pp = L.params + (uint32_t)(my_raw >> 32);
         double g[16];
-        onchip_gate_matrix(NZ, opc, q0, dev_num_params(opc) > 0 ? __ldg(pp) : 0.0, pp, g);
+        onchip_gate_matrix(L.noise, opc, q0, dev_num_params(opc) > 0 ? __ldg(pp) : 0.0, pp, g);
         double2* dst = reinterpret_cast<double2*>(W.gbuf + lane * kOnchipGRow);
 #pragma unroll
         for (int i = 0; i < 8; ++i) dst[i] = make_double2(g[2 * i], g[2 * i + 1]);
@@ -504,13 +508,13 @@ __global__ void __launch_bounds__(32 * kOnchipWarps, 16 / kOnchipWarps) dm_onchi
         const int zc2 = zc ^ zt, xt2 = xt ^ xc;
         qc = xc ? (zc2 ? 2 : 1) : (zc2 ? 3 : 0);
         qt = xt2 ? (zt ? 2 : 1) : (zt ? 3 : 0);
-        onchip_pauli(W, NZ, scratch, pc, q0, da);
-        onchip_pauli(W, NZ, scratch, pt, q1, db);
+        onchip_pauli(W, L.noise, scratch, pc, q0, da);
+        onchip_pauli(W, L.noise, scratch, pt, q1, db);
       }
-      onchip_pair(W, da, db, fac, (int)(aux >> 32), NZ.data + (uint32_t)aux);
+      onchip_pair(W, da, db, fac, (int)(aux >> 32), L.noise.data + (uint32_t)aux);
       if (twirl) {
-        onchip_pauli(W, NZ, scratch, qc, q0, da);
-        onchip_pauli(W, NZ, scratch, qt, q1, db);
+        onchip_pauli(W, L.noise, scratch, qc, q0, da);
+        onchip_pauli(W, L.noise, scratch, qt, q1, db);
       }
     }
     __syncwarp();
