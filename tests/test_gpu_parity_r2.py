@@ -373,3 +373,18 @@ def test_library_variants_on_gpu_match_python_built_variants(lib):
     m = grid.mean(axis=2)  # [circuit, fold, obs]
     assert np.max(np.abs(res_z.values - (1.5 * m[:, 0] - 0.5 * m[:, 1]).reshape(-1))) <= 1e-10
     eng.close()
+
+
+def test_random_circuits_reach_every_density_matrix_path(engine_gpu):
+    """tools/fuzz_parity.py: random circuits of 2..9 qubits (every gate kind, resets, idle qubits,
+    multi-Pauli observables) on random synthetic backends; dm_onchip_kernel, the single-tile kernel and
+    the TMA sweeps must each be exercised and agree with the oracle to 1e-10 (asserted inside)."""
+    import importlib.util
+    import os
+
+    spec = importlib.util.spec_from_file_location("fuzz_parity", os.path.join(os.path.dirname(__file__), "..", "tools", "fuzz_parity.py"))
+    mod = importlib.util.module_from_spec(spec)
+    spec.loader.exec_module(mod)
+    paths, worst = mod.run(n_cases=60, seed=11, eng=engine_gpu)
+    assert all(paths.get(k, 0) > 0 for k in ("onchip", "sweep", "tma")), paths
+    assert worst["dm"] <= TOL and worst["sv"] <= TOL
