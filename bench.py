@@ -17,6 +17,10 @@ resident in HBM (bwq_dm_execute + bwq_sv_execute), `e2e` through the C ABI with 
 (one bwq_meas_data_run per step = ideal + noisy values of the batch: lowering, H2D of the programs,
 kernels, D2H of the values; the density-matrix side is pipelined in segments, the statevector side
 runs concurrently on a companion context).
+`e2e_estimator` is the same work from the BASE circuit objects through B200Estimator.run(...,
+variants=...) (variants generated inside the library); `workloads` carries the other BASELINE configs
+(cfg1 tfim4_lima_zne -- runs on dm_onchip_kernel, `value` = that launch alone --, cfg3 tfim14_dm, cfg4
+tfim30_sv, amplitude-sharded with exchange figures when --gpus > 1) at reduced steps.
 `--impl reference` times the Aer-style CPU restatement (oracle/cpu_ref.cpp; qiskit-aer itself is
 not installable here) on the host cores, on a bounded sample of the same workload.
 """
