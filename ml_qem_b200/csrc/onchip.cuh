@@ -48,6 +48,7 @@ struct OnchipNoise {            // all null / 0 for the ideal evolution
 
 struct OnchipLaunch {
   int32_t n_circuits, n_folds, n_twirls, twirl;   // n_folds, n_twirls >= 1 here; twirl = draw Paulis
+  int32_t circuit_base;         // batch index of this launch's circuit 0 (a launch covers a range of the batch; twirl draws use the batch index)
   uint64_t seed;
   const int32_t* folds;         // [n_folds] or null (factor 1)
   const int32_t* n_qubits;
@@ -500,7 +501,7 @@ __global__ void __launch_bounds__(32 * kOnchipWarps, BWQ_ONCHIP_MINB / kOnchipWa
       double* scratch = W.gbuf + k * kOnchipGRow;
       int qc = 0, qt = 0;
       if (twirl) {
-        const uint32_t d = (uint32_t)(dev_splitmix64(dev_splitmix64(dev_splitmix64(L.seed ^ (uint64_t)c) ^ (uint64_t)tw) ^ k_cx) & 15u);
+        const uint32_t d = (uint32_t)(dev_splitmix64(dev_splitmix64(dev_splitmix64(L.seed ^ (uint64_t)(c + L.circuit_base)) ^ (uint64_t)tw) ^ k_cx) & 15u);
         ++k_cx;
         const int pc = (int)(d & 3u), pt = (int)(d >> 2);
         // CX conjugation (sign dropped): X_c -> X_c X_t, Z_t -> Z_c Z_t

@@ -159,3 +159,31 @@ def test_onchip_variants_match_python_built_variants(lib):
     eng.set_options()
     assert np.max(np.abs(noisy - noisy_t)) <= 1e-12 and np.max(np.abs(ideal - ideal_t)) <= 1e-12
     eng.close()
+
+
+def test_onchip_ranges_pipeline_gives_identical_values(lib, monkeypatch):
+    """Large batches are cut into ranges of circuits (range r+1 is staged and uploaded while the kernel
+    of range r runs); forced here on a small batch: values, statuses and twirl draws (a function of the
+    BATCH index of a circuit) do not depend on the number of ranges."""
+    lima = backends.fake_lima()
+    nm = noise.from_backend(lima)
+    rng = np.random.default_rng(21)
+    circs = [_random_circuit(rng, 5, int(rng.integers(5, 60)), lima.coupling_map) for _ in range(37)]
+    obs = [[[(l, 1.0)] for l in _labels(rng, 5, int(rng.integers(1, 4)))] for _ in circs]
+    fb = engine.encode_batch(circs, obs)
+    v = Variants(folds=(1, 3), twirls=3, seed=5)
+    ref = None
+    for ranges in ("1", "3", "8"):
+        monkeypatch.setenv("BWQ_ONCHIP_RANGES", ranges)
+        eng = Engine(0)
+        a = eng.run_meas_data_variants(fb, v, noise=nm)
+        assert eng.stats()["n_onchip_circuits"] == len(circs) * 7 and eng.stats()["n_other_launches"] == int(ranges)
+        b = eng.run_dm(fb, noise=nm)
+        c = eng.run_sv(fb)
+        eng.close()
+        got = [np.asarray(x) for x in (*a, *b, *c)]
+        if ref is None:
+            ref = got
+        else:
+            for x, y in zip(got, ref):
+                assert np.array_equal(x, y, equal_nan=True), ranges
