@@ -15,6 +15,7 @@
 
 #include <cuda.h>
 #include <cudaTypedefs.h>
+#include <nvtx3/nvToolsExt.h>
 
 #include "kernels.cuh"
 #include "kernels_tma.cuh"
@@ -35,6 +36,12 @@ double now_ms() {
   using namespace std::chrono;
   return duration<double, std::milli>(steady_clock::now().time_since_epoch()).count();
 }
+
+// NVTX range over a host-side stage (visible in ncu / nsys timelines; header-only, no cost without a tool attached)
+struct NvtxRange {
+  explicit NvtxRange(const char* name) { nvtxRangePushA(name); }
+  ~NvtxRange() { nvtxRangePop(); }
+};
 
 // grow-only device / pinned-host buffers
 struct DevBuf {
@@ -404,6 +411,7 @@ struct FoldInfo {
 
 static int dm_lower_impl(bwq_ctx* ctx, bwq_ctx::DmSlot& sl, const bwq_batch* b, int c0, int c1, int32_t* out_status,
                          int64_t budget, const FoldInfo* fi = nullptr) {
+  NvtxRange nvtx_range("bwq:dm_lower (K0)");
   DmPlan& P = sl.plan;
   P = DmPlan();
   const int N = c1 - c0;
@@ -608,6 +616,7 @@ static int dm_encode_maps(bwq_ctx* ctx, bwq_ctx::DmSlot& sl);
 // sync = false (pipelined run): the value buffers were sized for the whole batch by the caller and
 // the copy is only enqueued; sl.h2d_done tells the lowering thread when the pinned blob is free.
 static int dm_upload_impl(bwq_ctx* ctx, bwq_ctx::DmSlot& sl, bool sync) {
+  NvtxRange nvtx_range("bwq:dm_upload");
   DmPlan& P = sl.plan;
   const size_t blob_total = P.blob_bytes;
   const char* hb = (const char*)sl.h_prog.p;
@@ -702,6 +711,7 @@ static int dm_prepare_impl(bwq_ctx* ctx, const bwq_batch* b, int32_t* out_status
 // nothing is synchronised, timed or copied to the caller here (dm_run_impl does that once).
 static int dm_execute_impl(bwq_ctx* ctx, bwq_ctx::DmSlot& sl, double* out_vals, bool out_on_device, bool deferred = false,
                            int64_t obs_off = 0) {
+  NvtxRange nvtx_range("bwq:dm_execute (sweeps + expval)");
   if (!ctx || !out_vals) return BWQ_ERR_ARG;
   DmPlan& P = sl.plan;
   if (!P.valid) return fail(ctx, BWQ_ERR_ARG, "bwq_dm_execute: no prepared batch (call bwq_dm_prepare first)");
@@ -879,6 +889,7 @@ static int onchip_upload_noise(bwq_ctx* ctx) {
 // circuit (circuit-major), out_vals as bwq_dm_run_variants.
 static int onchip_run(bwq_ctx* ctx, const bwq_batch* b, const bwq_variants* v, bool noisy, double* out_vals, bool out_on_device,
                       int32_t* out_status, bool* handled, double* out_ideal = nullptr, int32_t* status_ideal = nullptr) {
+  NvtxRange nvtx_range("bwq:onchip");
   *handled = false;
   const bool with_ideal = out_ideal != nullptr;  // the same launch also evolves every base circuit without noise
   if (ctx->opt.flags & BWQ_OPT_NO_ONCHIP) return BWQ_OK;
@@ -1411,6 +1422,7 @@ static int sv_wide_execute(bwq_ctx* ctx, double* d_out) {
 // statevector run (ideal labels)
 // ------------------------------------------------------------------------------------------------
 static int sv_prepare_impl(bwq_ctx* ctx, const bwq_batch* b, int32_t* out_status) {
+  NvtxRange nvtx_range("bwq:sv_prepare (K0)");
   if (!ctx) return BWQ_ERR_ARG;
   int rc = check_batch(ctx, b, out_status, out_status);
   if (rc) return rc;
@@ -1534,6 +1546,7 @@ static int sv_prepare_impl(bwq_ctx* ctx, const bwq_batch* b, int32_t* out_status
 }
 
 static int sv_execute_impl(bwq_ctx* ctx, double* out_vals) {
+  NvtxRange nvtx_range("bwq:sv_execute");
   if (!ctx || !out_vals) return BWQ_ERR_ARG;
   SvPlan& P = ctx->sv_plan;
   if (!P.valid) return fail(ctx, BWQ_ERR_ARG, "bwq_sv_execute: no prepared batch (call bwq_sv_prepare first)");
