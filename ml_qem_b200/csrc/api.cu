@@ -8,6 +8,9 @@
 #include <cstdlib>
 #include <cmath>
 #include <cstring>
+#include <condition_variable>
+#include <functional>
+#include <mutex>
 #include <numeric>
 #include <string>
 #include <thread>
@@ -36,6 +39,19 @@ double now_ms() {
   using namespace std::chrono;
   return duration<double, std::milli>(steady_clock::now().time_since_epoch()).count();
 }
+
+// BWQ_TRACE=1: wall-clock phase marks of the *_run entry points on stderr (host-side tuning)
+struct Trace {
+  bool on;
+  double t0, last;
+  explicit Trace(const char* what) : on(std::getenv("BWQ_TRACE") != nullptr), t0(now_ms()), last(t0) { if (on) std::fprintf(stderr, "[bwq trace] %s\n", what); }
+  void mark(const char* what) {
+    if (!on) return;
+    const double t = now_ms();
+    std::fprintf(stderr, "[bwq trace]   %-34s +%7.3f ms  (at %7.3f)\n", what, t - last, t - t0);
+    last = t;
+  }
+};
 
 // NVTX range over a host-side stage (visible in ncu / nsys timelines; header-only, no cost without a tool attached)
 struct NvtxRange {
@@ -84,6 +100,66 @@ struct Blob {
     total += (bytes + 255) & ~size_t(255);
     return o;
   }
+};
+
+// Persistent host worker pool of a context.  The lowering stages call parallel_for two or three
+// times per segment; spawning 15 std::threads per call costs ~0.5 ms on an idle host and several
+// milliseconds on a loaded one -- the workers are created once and parked on a condition variable.
+class HostPool {
+ public:
+  ~HostPool() {
+    { std::lock_guard<std::mutex> lk(m_); stop_ = true; }
+    cv_.notify_all();
+    for (auto& t : workers_) t.join();
+  }
+  // f(i) for i in [0, n) on `threads` threads (the caller is one of them); one job at a time per pool
+  template <class F> void run(int n, int threads, F& f) {
+    threads = std::max(1, std::min(threads, n));
+    if (threads == 1) { for (int i = 0; i < n; ++i) f(i); return; }
+    std::lock_guard<std::mutex> job_guard(job_m_);
+    {
+      std::unique_lock<std::mutex> lk(m_);
+      while ((int)workers_.size() < threads - 1) workers_.emplace_back([this] { worker(); });
+      body_ = [&f](int i) { f(i); };
+      n_ = n; next_.store(0); slots_ = running_ = threads - 1; ++gen_;
+    }
+    cv_.notify_all();
+    work();
+    std::unique_lock<std::mutex> lk(m_);
+    done_.wait(lk, [&] { return running_ == 0; });
+    body_ = nullptr;
+  }
+
+ private:
+  void work() {
+    for (;;) {
+      const int i = next_.fetch_add(16);
+      if (i >= n_) break;
+      for (int j = i; j < std::min(n_, i + 16); ++j) body_(j);
+    }
+  }
+  void worker() {
+    int seen = 0;
+    std::unique_lock<std::mutex> lk(m_);
+    for (;;) {
+      cv_.wait(lk, [&] { return stop_ || gen_ != seen; });
+      if (stop_) return;
+      seen = gen_;
+      if (slots_ <= 0) continue;  // this job already has its workers
+      --slots_;
+      lk.unlock();
+      work();
+      lk.lock();
+      if (--running_ == 0) done_.notify_one();
+    }
+  }
+  std::mutex job_m_, m_;
+  std::condition_variable cv_, done_;
+  std::vector<std::thread> workers_;
+  std::function<void(int)> body_;
+  std::atomic<int> next_{0};
+  int n_ = 0, slots_ = 0, running_ = 0, gen_ = 0;
+  bool stop_ = false;
 };
 
 }  // namespace
@@ -176,6 +252,7 @@ struct bwq_ctx {
   PinBuf h_oc, h_oc_out;
   OnchipNoise oc_noise{};
   bool oc_noise_valid = false;
+  HostPool pool;                                  // lowering / staging workers (persistent)
   cudaStream_t oc_copy_stream = nullptr;          // uploads of range r+1 overlap the kernel of range r
   cudaEvent_t oc_copied[8] = {}, oc_k0[8] = {}, oc_k1[8] = {};
   size_t smem_optin = 0;
@@ -359,15 +436,7 @@ static int check_batch(bwq_ctx* ctx, const bwq_batch* b, const void* out, const 
   return BWQ_OK;
 }
 
-template <class F> static void parallel_for(int n, int threads, F f) {
-  threads = std::max(1, std::min(threads, n));
-  if (threads == 1) { for (int i = 0; i < n; ++i) f(i); return; }
-  std::atomic<int> next(0);
-  std::vector<std::thread> pool;
-  for (int t = 0; t < threads; ++t)
-    pool.emplace_back([&] { for (;;) { int i = next.fetch_add(16); if (i >= n) break; for (int j = i; j < std::min(n, i + 16); ++j) f(j); } });
-  for (auto& th : pool) th.join();
-}
+template <class F> static void parallel_for(bwq_ctx* ctx, int n, int threads, F f) { ctx->pool.run(n, threads, f); }
 
 static int host_threads(const bwq_ctx* ctx) {
   if (ctx->opt.host_threads > 0) return ctx->opt.host_threads;
@@ -434,13 +503,13 @@ static int dm_lower_impl(bwq_ctx* ctx, bwq_ctx::DmSlot& sl, const bwq_batch* b, 
   if (fi && fi->n_folds > 0 && c0 % fi->n_folds == 0 && N % fi->n_folds == 0) {
     // fold variants: the gates of a base circuit are lowered once, every fold re-packs the passes
     const int nf = fi->n_folds;
-    parallel_for(N / nf, host_threads(ctx), [&](int k) {
+    parallel_for(ctx, N / nf, host_threads(ctx), [&](int k) {
       const int base = c0 / nf + k;
       if (!lower_dm_circuit_folds(ctx->noise, *fi->base, base, lo, fi->folds, nf, &progs[(size_t)k * nf]))
         for (int f = 0; f < nf; ++f) lower_dm_circuit(ctx->noise, *b, c0 + k * nf + f, lo, &progs[(size_t)k * nf + f]);
     });
   } else {
-    parallel_for(N, host_threads(ctx), [&](int c) { lower_dm_circuit(ctx->noise, *b, c0 + c, lo, &progs[c]); });
+    parallel_for(ctx, N, host_threads(ctx), [&](int c) { lower_dm_circuit(ctx->noise, *b, c0 + c, lo, &progs[c]); });
   }
 
   std::vector<int> order;
@@ -478,7 +547,7 @@ static int dm_lower_impl(bwq_ctx* ctx, bwq_ctx::DmSlot& sl, const bwq_batch* b, 
   P.blob_bytes = blob.total;
   if (M > 0) CK(sl.h_prog.reserve(blob.total));
   char* hb = (char*)sl.h_prog.p;
-  parallel_for(M, host_threads(ctx), [&](int i) {
+  parallel_for(ctx, M, host_threads(ctx), [&](int i) {
     const int c = order[i];
     const CircuitProgram& p = progs[c];
     SweepDesc* sw = (SweepDesc*)(hb + P.o_sweeps) + sw_off[i];
@@ -605,7 +674,7 @@ static int dm_lower_impl(bwq_ctx* ctx, bwq_ctx::DmSlot& sl, const bwq_batch* b, 
     }
   }
   // thousands of small circuits leave ~10 heap blocks each: release them on the host threads too
-  if (N >= 1024) parallel_for(N, host_threads(ctx), [&](int c) { progs[c] = CircuitProgram(); });
+  if (N >= 1024) parallel_for(ctx, N, host_threads(ctx), [&](int c) { progs[c] = CircuitProgram(); });
   P.lower_ms = now_ms() - t0;
   return BWQ_OK;
 }
@@ -973,7 +1042,7 @@ static int onchip_run(bwq_ctx* ctx, const bwq_batch* b, const bwq_variants* v, b
       for (size_t o = 0; o < pc.bytes; o += size_t(1) << 18)
         slices.push_back({h + pc.off + o, (const char*)pc.src + o, std::min(pc.bytes - o, size_t(1) << 18)});
     }
-    parallel_for((int)slices.size(), std::min<int>({(int)slices.size() / 4, 8, host_threads(ctx)}), [&](int i) { std::memcpy(slices[i].dst, slices[i].src, slices[i].bytes); });
+    parallel_for(ctx, (int)slices.size(), std::min<int>({(int)slices.size() / 4, 8, host_threads(ctx)}), [&](int i) { std::memcpy(slices[i].dst, slices[i].src, slices[i].bytes); });
   };
   auto stage_range = [&](int r) {
     const int c0 = rc0[r], nc = rc0[r + 1] - c0;
@@ -1088,8 +1157,10 @@ static int onchip_run(bwq_ctx* ctx, const bwq_batch* b, const bwq_variants* v, b
 static int dm_run_impl(bwq_ctx* ctx, const bwq_batch* b, double* out_vals, int32_t* out_status, bool out_on_device,
                        const FoldInfo* fi = nullptr, bool allow_onchip = true) {
   if (!ctx) return BWQ_ERR_ARG;
+  Trace tr("dm_run");
   int rc = check_batch(ctx, b, out_status, out_status);
   if (rc) return rc;
+  tr.mark("check_batch");
   if (allow_onchip) {  // circuits that fit on chip: one launch on the raw gate stream, no lowering
     bool handled = false;
     if ((rc = onchip_run(ctx, b, nullptr, true, out_vals, out_on_device, out_status, &handled))) return rc;
@@ -1107,8 +1178,11 @@ static int dm_run_impl(bwq_ctx* ctx, const bwq_batch* b, double* out_vals, int32
   constexpr int kMinSeg = 128, kMaxSegs = 8;
   int n_seg = (ctx->opt.flags & BWQ_OPT_NO_PIPELINE) ? 1 : std::max(1, std::min(kMaxSegs, N / kMinSeg));
   if (n_seg > 1 && !(ctx->opt.flags & BWQ_OPT_FORCE_PIPELINE)) {
+    // (a sample of at most 64 evenly spaced circuits, scaled: the scan is serial and sits in front of
+    // the first segment's lowering)
     double est_bytes = 0.0;
-    for (int c = 0; c < N && est_bytes < 2e10; ++c) {
+    const int stride = std::max(1, N / 64);
+    for (int c = 0; c < N && est_bytes < 2e10; c += stride) {
       uint64_t used = 0;
       int64_t n2 = 0;
       for (int64_t g = b->op_offsets[c]; g < b->op_offsets[c + 1]; ++g) {
@@ -1117,10 +1191,11 @@ static int dm_run_impl(bwq_ctx* ctx, const bwq_batch* b, double* out_vals, int32
         if (gate_is_2q(op.opcode)) { used |= 1ull << (op.q1 & 63); ++n2; }
       }
       const int na = std::min(__builtin_popcountll(used), kMaxDmQubits);
-      if (na > 6) est_bytes += 16.0 * std::ldexp(1.0, 2 * na) * (1.0 + 0.25 * (double)n2);
+      if (na > 6) est_bytes += (double)stride * 16.0 * std::ldexp(1.0, 2 * na) * (1.0 + 0.25 * (double)n2);
     }
     if (est_bytes < 2e10) n_seg = 1;  // < ~5 ms of sweeps
   }
+  tr.mark("budget + traffic estimate");
   const int unit = fi && fi->n_folds > 0 && N % fi->n_folds == 0 ? fi->n_folds : 1;  // the variants of a circuit stay in one segment
   auto seg_begin = [&](int k) { return (int)((int64_t)(N / unit) * k / n_seg) * unit; };
   if (n_seg == 1) {
@@ -1140,6 +1215,7 @@ static int dm_run_impl(bwq_ctx* ctx, const bwq_batch* b, double* out_vals, int32
   bwq_stats total{};
   std::vector<std::pair<int64_t, double>> fixes;
   if ((rc = dm_lower_impl(ctx, ctx->dm[0], b, seg_begin(0), seg_begin(1), out_status, budget, fi))) return rc;
+  tr.mark("lower segment 0 (exposed)");
   CK(cudaEventRecord(ctx->ev[1], st));
   for (int k = 0; k < n_seg; ++k) {
     bwq_ctx::DmSlot& cur = ctx->dm[k & 1];
@@ -1158,7 +1234,9 @@ static int dm_run_impl(bwq_ctx* ctx, const bwq_batch* b, double* out_vals, int32
     for (auto& f : cur.plan.host_fix) fixes.push_back({obs0 + f.first, f.second});
     const bwq_stats S = ctx->stats;
     const double seg_lower_ms = cur.plan.lower_ms;
+    tr.mark("  upload + launches enqueued");
     if (helper.joinable()) helper.join();
+    tr.mark("  next segment lowered (join)");
     if (rc || next_rc) { cudaStreamSynchronize(st); return rc ? rc : next_rc; }
     total.n_sweep_launches += S.n_sweep_launches; total.n_state_sweeps += S.n_state_sweeps;
     total.n_tma_sweep_launches += S.n_tma_sweep_launches;
@@ -1168,6 +1246,7 @@ static int dm_run_impl(bwq_ctx* ctx, const bwq_batch* b, double* out_vals, int32
   }
   CK(cudaEventRecord(ctx->ev[2], st));
   CK(cudaStreamSynchronize(st));
+  tr.mark("stream synchronised");
   float ms = 0.f;
   CK(cudaEventElapsedTime(&ms, ctx->ev[1], ctx->ev[2]));
   total.kernel_ms = total.sweep_kernel_ms = ms;  // uploads and value copies of the segments included
@@ -1215,7 +1294,7 @@ static int sv_wide_prepare(bwq_ctx* ctx, const bwq_batch* b, const std::vector<i
   std::vector<SvxProgram> progs(NW);
   SvxOptions so;
   so.tile_bits = ctx->opt.sv_tile_bits > 0 ? ctx->opt.sv_tile_bits : kSvTileBitsDefault;
-  parallel_for(NW, host_threads(ctx), [&](int i) { lower_svx_circuit(*b, wide[i], so, &progs[i]); });
+  parallel_for(ctx, NW, host_threads(ctx), [&](int i) { lower_svx_circuit(*b, wide[i], so, &progs[i]); });
   size_t free_b = 0, total_b = 0;
   CK(cudaMemGetInfo(&free_b, &total_b));
   const int64_t budget = ctx->opt.max_state_bytes > 0 ? ctx->opt.max_state_bytes
@@ -1339,7 +1418,7 @@ static int sv_wide_prepare(bwq_ctx* ctx, const bwq_batch* b, const std::vector<i
   if (!gdesc.empty()) std::memcpy(hb + W.o_gdesc, gdesc.data(), sizeof(int32_t) * gdesc.size());
   if (!cdesc.empty()) std::memcpy(hb + W.o_cdesc, cdesc.data(), sizeof(int32_t) * cdesc.size());
   if (!inits.empty()) std::memcpy(hb + W.o_init, inits.data(), sizeof(int32_t) * inits.size());
-  parallel_for(M, host_threads(ctx), [&](int i) {
+  parallel_for(ctx, M, host_threads(ctx), [&](int i) {
     const SvxProgram& p = progs[order[i]];
     SweepDesc* sw = (SweepDesc*)(hb + W.o_sweeps) + sw_off[i];
     for (size_t k = 0; k < p.sweeps.size(); ++k) { sw[k] = p.sweeps[k]; sw[k].blk_q16 += (uint32_t)(pg_off[i] / 2); }
@@ -1436,7 +1515,7 @@ static int sv_prepare_impl(bwq_ctx* ctx, const bwq_batch* b, int32_t* out_status
   CK(cudaSetDevice(ctx->device));
   double t0 = now_ms();
   std::vector<SvProgram> progs(N);
-  parallel_for(N, host_threads(ctx), [&](int c) { lower_sv_circuit(*b, c, &progs[c]); });
+  parallel_for(ctx, N, host_threads(ctx), [&](int c) { lower_sv_circuit(*b, c, &progs[c]); });
   // <= kSvSmallBits active qubits: one CTA per circuit, state in shared memory; wider: tile sweeps
   std::vector<int> order, wide;
   for (int c = 0; c < N; ++c) {
@@ -1479,7 +1558,7 @@ static int sv_prepare_impl(bwq_ctx* ctx, const bwq_batch* b, int32_t* out_status
     CK(ctx->d_sv_prog.reserve(blob.total));
   }
   char* hb = (char*)ctx->h_sv_prog.p;
-  parallel_for(M, host_threads(ctx), [&](int i) {
+  parallel_for(ctx, M, host_threads(ctx), [&](int i) {
     const int c = order[i];
     const SvProgram& p = progs[c];
     int32_t* cd = (int32_t*)(hb + P.o_cd) + 8 * i;
@@ -1657,9 +1736,12 @@ extern "C" int bwq_meas_data_run(bwq_ctx* ctx, const bwq_batch* b, double* out_i
   ctx->companion->opt.host_threads = std::max(1, all_threads / 4);
   ctx->opt.host_threads = std::max(1, all_threads - ctx->companion->opt.host_threads);
   int rc_sv = BWQ_OK;
+  Trace tr("meas_data_run");
   std::thread ideal([&] { rc_sv = bwq_sv_run(ctx->companion, b, out_ideal, status_ideal); });
   const int rc_dm = dm_run_impl(ctx, b, out_noisy, status_noisy, false, nullptr, false);
+  tr.mark("density-matrix side returned");
   ideal.join();
+  tr.mark("statevector side joined");
   ctx->opt.host_threads = saved_threads;
   if (rc_dm) return rc_dm;
   if (rc_sv) return fail(ctx, rc_sv, "statevector side: %s", bwq_last_error(ctx->companion));
@@ -1689,7 +1771,8 @@ extern "C" int bwq_meas_data_run_variants(bwq_ctx* ctx, const bwq_batch* b, cons
   if ((rc = ensure_companion(ctx))) return rc;
   const double t0 = now_ms();
   ExpandedBatch X;
-  if ((rc = expand_variants(*b, *v, &X, host_threads(ctx)))) return fail(ctx, rc, "bad variants descriptor (folds must be odd positive factors)");
+  const ParallelRunner pool_runner = [ctx](int n, const std::function<void(int)>& f) { ctx->pool.run(n, host_threads(ctx), f); };
+  if ((rc = expand_variants(*b, *v, &X, host_threads(ctx), &pool_runner))) return fail(ctx, rc, "bad variants descriptor (folds must be odd positive factors)");
   const double expand_ms = now_ms() - t0;
   std::vector<int32_t> st_var((size_t)X.view.n_circuits);
   const int all_threads = host_threads(ctx), saved_threads = ctx->opt.host_threads;
@@ -1732,7 +1815,8 @@ extern "C" int bwq_dm_run_variants(bwq_ctx* ctx, const bwq_batch* b, const bwq_v
   }
   const double t0 = now_ms();
   ExpandedBatch X;
-  if ((rc = expand_variants(*b, *v, &X, host_threads(ctx)))) return fail(ctx, rc, "bad variants descriptor (folds must be odd positive factors)");
+  const ParallelRunner pool_runner = [ctx](int n, const std::function<void(int)>& f) { ctx->pool.run(n, host_threads(ctx), f); };
+  if ((rc = expand_variants(*b, *v, &X, host_threads(ctx), &pool_runner))) return fail(ctx, rc, "bad variants descriptor (folds must be odd positive factors)");
   const double expand_ms = now_ms() - t0;
   const FoldInfo fi{b, v->folds, v->n_folds};
   if ((rc = dm_run_impl(ctx, &X.view, out_vals, out_status, false, v->n_twirls == 0 && v->n_folds > 0 ? &fi : nullptr, false))) return rc;

@@ -7,6 +7,7 @@
 // column-stacked complex vec(rho) in half the bytes, and Tr(rho P) is a lookup.
 #pragma once
 #include <cstdint>
+#include <functional>
 #include <vector>
 
 #include "../../include/bwq.h"
@@ -259,7 +260,9 @@ struct ExpandedBatch {
   std::vector<uint64_t> term_x, term_z;
   bwq_batch view{};                     // points into the vectors above
 };
-int expand_variants(const bwq_batch& base, const bwq_variants& v, ExpandedBatch* out, int threads = 1);
+// runner(n, body): executes body(i) for i in [0, n) (in parallel); null = std::threads spawned per call
+using ParallelRunner = std::function<void(int, const std::function<void(int)>&)>;
+int expand_variants(const bwq_batch& base, const bwq_variants& v, ExpandedBatch* out, int threads = 1, const ParallelRunner* runner = nullptr);
 uint32_t twirl_draw(uint64_t seed, uint64_t circuit, uint64_t twirl, uint64_t cx_index);
 
 // gate library (host)

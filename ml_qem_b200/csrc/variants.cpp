@@ -57,7 +57,12 @@ template <class F> static void par_for(int n, int threads, F f) {
   for (auto& th : pool) th.join();
 }
 
-int expand_variants(const bwq_batch& b, const bwq_variants& v, ExpandedBatch* out, int threads) {
+int expand_variants(const bwq_batch& b, const bwq_variants& v, ExpandedBatch* out, int threads, const ParallelRunner* runner) {
+  // the context's persistent worker pool when the caller has one, else threads spawned per call
+  auto par_for = [&](int n, int thr, const std::function<void(int)>& f) {
+    if (runner && *runner) (*runner)(n, f);
+    else bwq::par_for(n, thr, f);
+  };
   const int n_folds = v.n_folds > 0 ? v.n_folds : 1;
   const int n_tw = v.n_twirls > 0 ? v.n_twirls : 1;
   const bool twirl = v.n_twirls > 0;
