@@ -10,6 +10,7 @@
 #include <cstring>
 #include <condition_variable>
 #include <functional>
+#include <memory>
 #include <mutex>
 #include <numeric>
 #include <string>
@@ -102,66 +103,6 @@ struct Blob {
   }
 };
 
-// Persistent host worker pool of a context.  The lowering stages call parallel_for two or three
-// times per segment; spawning 15 std::threads per call costs ~0.5 ms on an idle host and several
-// milliseconds on a loaded one -- the workers are created once and parked on a condition variable.
-class HostPool {
- public:
-  ~HostPool() {
-    { std::lock_guard<std::mutex> lk(m_); stop_ = true; }
-    cv_.notify_all();
-    for (auto& t : workers_) t.join();
-  }
-  // f(i) for i in [0, n) on `threads` threads (the caller is one of them); one job at a time per pool
-  template <class F> void run(int n, int threads, F& f) {
-    threads = std::max(1, std::min(threads, n));
-    if (threads == 1) { for (int i = 0; i < n; ++i) f(i); return; }
-    std::lock_guard<std::mutex> job_guard(job_m_);
-    {
-      std::unique_lock<std::mutex> lk(m_);
-      while ((int)workers_.size() < threads - 1) workers_.emplace_back([this] { worker(); });
-      body_ = [&f](int i) { f(i); };
-      n_ = n; next_.store(0); slots_ = running_ = threads - 1; ++gen_;
-    }
-    cv_.notify_all();
-    work();
-    std::unique_lock<std::mutex> lk(m_);
-    done_.wait(lk, [&] { return running_ == 0; });
-    body_ = nullptr;
-  }
-
- private:
-  void work() {
-    for (;;) {
-      const int i = next_.fetch_add(16);
-      if (i >= n_) break;
-      for (int j = i; j < std::min(n_, i + 16); ++j) body_(j);
-    }
-  }
-  void worker() {
-    int seen = 0;
-    std::unique_lock<std::mutex> lk(m_);
-    for (;;) {
-      cv_.wait(lk, [&] { return stop_ || gen_ != seen; });
-      if (stop_) return;
-      seen = gen_;
-      if (slots_ <= 0) continue;  // this job already has its workers
-      --slots_;
-      lk.unlock();
-      work();
-      lk.lock();
-      if (--running_ == 0) done_.notify_one();
-    }
-  }
-  std::mutex job_m_, m_;
-  std::condition_variable cv_, done_;
-  std::vector<std::thread> workers_;
-  std::function<void(int)> body_;
-  std::atomic<int> next_{0};
-  int n_ = 0, slots_ = 0, running_ = 0, gen_ = 0;
-  bool stop_ = false;
-};
-
 }  // namespace
 
 struct DmChunk {
@@ -252,7 +193,6 @@ struct bwq_ctx {
   PinBuf h_oc, h_oc_out;
   OnchipNoise oc_noise{};
   bool oc_noise_valid = false;
-  HostPool pool;                                  // lowering / staging workers (persistent)
   cudaStream_t oc_copy_stream = nullptr;          // uploads of range r+1 overlap the kernel of range r
   cudaEvent_t oc_copied[8] = {}, oc_k0[8] = {}, oc_k1[8] = {};
   size_t smem_optin = 0;
@@ -436,7 +376,19 @@ static int check_batch(bwq_ctx* ctx, const bwq_batch* b, const void* out, const 
   return BWQ_OK;
 }
 
-template <class F> static void parallel_for(bwq_ctx* ctx, int n, int threads, F f) { ctx->pool.run(n, threads, f); }
+// Threads are spawned per call.  A persistent pool parked on a condition variable was measured and
+// dropped: it saves ~3 ms of lowering per cfg2 call on a quiet host (6.5 vs 9.5 ms, hidden behind the
+// sweeps anyway) but on two ranks sharing 16 cores one run in three fell into an 81 ms-per-call mode
+// (47 ms with spawned threads, tools/gpu_r2_poolab.sh).
+template <class F> static void parallel_for(bwq_ctx* /*ctx*/, int n, int threads, F f) {
+  threads = std::max(1, std::min(threads, n));
+  if (threads == 1) { for (int i = 0; i < n; ++i) f(i); return; }
+  std::atomic<int> next(0);
+  std::vector<std::thread> pool;
+  for (int t = 0; t < threads; ++t)
+    pool.emplace_back([&] { for (;;) { int i = next.fetch_add(16); if (i >= n) break; for (int j = i; j < std::min(n, i + 16); ++j) f(j); } });
+  for (auto& th : pool) th.join();
+}
 
 static int host_threads(const bwq_ctx* ctx) {
   if (ctx->opt.host_threads > 0) return ctx->opt.host_threads;
@@ -1771,8 +1723,7 @@ extern "C" int bwq_meas_data_run_variants(bwq_ctx* ctx, const bwq_batch* b, cons
   if ((rc = ensure_companion(ctx))) return rc;
   const double t0 = now_ms();
   ExpandedBatch X;
-  const ParallelRunner pool_runner = [ctx](int n, const std::function<void(int)>& f) { ctx->pool.run(n, host_threads(ctx), f); };
-  if ((rc = expand_variants(*b, *v, &X, host_threads(ctx), &pool_runner))) return fail(ctx, rc, "bad variants descriptor (folds must be odd positive factors)");
+  if ((rc = expand_variants(*b, *v, &X, host_threads(ctx)))) return fail(ctx, rc, "bad variants descriptor (folds must be odd positive factors)");
   const double expand_ms = now_ms() - t0;
   std::vector<int32_t> st_var((size_t)X.view.n_circuits);
   const int all_threads = host_threads(ctx), saved_threads = ctx->opt.host_threads;
@@ -1815,8 +1766,7 @@ extern "C" int bwq_dm_run_variants(bwq_ctx* ctx, const bwq_batch* b, const bwq_v
   }
   const double t0 = now_ms();
   ExpandedBatch X;
-  const ParallelRunner pool_runner = [ctx](int n, const std::function<void(int)>& f) { ctx->pool.run(n, host_threads(ctx), f); };
-  if ((rc = expand_variants(*b, *v, &X, host_threads(ctx), &pool_runner))) return fail(ctx, rc, "bad variants descriptor (folds must be odd positive factors)");
+  if ((rc = expand_variants(*b, *v, &X, host_threads(ctx)))) return fail(ctx, rc, "bad variants descriptor (folds must be odd positive factors)");
   const double expand_ms = now_ms() - t0;
   const FoldInfo fi{b, v->folds, v->n_folds};
   if ((rc = dm_run_impl(ctx, &X.view, out_vals, out_status, false, v->n_twirls == 0 && v->n_folds > 0 ? &fi : nullptr, false))) return rc;
