@@ -379,7 +379,7 @@ static int check_batch(bwq_ctx* ctx, const bwq_batch* b, const void* out, const 
 // Threads are spawned per call.  A persistent pool parked on a condition variable was measured and
 // dropped: it saves ~3 ms of lowering per cfg2 call on a quiet host (6.5 vs 9.5 ms, hidden behind the
 // sweeps anyway) but on two ranks sharing 16 cores one run in three fell into an 81 ms-per-call mode
-// (47 ms with spawned threads, tools/gpu_r2_poolab.sh).
+// (47 ms with spawned threads; same box, alternating runs of both builds, commit 676d3d0 has the pool).
 template <class F> static void parallel_for(bwq_ctx* /*ctx*/, int n, int threads, F f) {
   threads = std::max(1, std::min(threads, n));
   if (threads == 1) { for (int i = 0; i < n; ++i) f(i); return; }
