@@ -2,7 +2,7 @@
 # sharded tfim30_sv: chunked ZZ-layer fusion (BWQ_SVX_ZZ_CHUNK) vs per-pass merging
 mkdir -p gpurun_out
 N=${1:-2}
-for c in 0 3 4 62; do
+for c in ${CHUNKS:-0 3 4 62}; do
 BWQ_SVX_ZZ_CHUNK=$c timeout 600 python -m torch.distributed.run --nnodes=1 --nproc-per-node=$N --master-addr 127.0.0.1 --master-port 2957$((c%10)) bench.py --gpus $N --workload tfim30_sv --steps 3 --warmup 1 --no-cpu-baseline > gpurun_out/zz_$c.json 2> gpurun_out/zz_$c.err
 python - <<PY
 import json
