@@ -197,6 +197,50 @@ class Circuit:
         self.__dict__["_flat"] = (key, out)
         return out
 
+    def flat_template(self):
+        """``flat()`` of a PARAMETRISED circuit, once for all parameter sets: the arrays of ``flat()``
+        with zeros at the parametric positions, plus (position, parameter index, scale, shift) of every
+        ``a * theta + b`` entry -- a parameter set then binds with one numpy expression instead of a
+        Python walk over the gates (VQE-style ``run(batch * [ansatz], batch * [op], parameter_values)``,
+        reference: docs/tutorials/vqe_to_substitute*.py:260-269)."""
+        ops = self.ops
+        key = (len(ops), id(ops[-1]) if ops else 0)
+        cache = self.__dict__.get("_flat_tpl")
+        if cache is not None and cache[0] == key:
+            return cache[1]
+        names = [p.name for p in self.parameters]
+        index = {n: i for i, n in enumerate(names)}
+        gate_ops = self.gate_ops()
+        n = len(gate_ops)
+        opc = np.empty(n, dtype=np.uint16)
+        q0 = np.empty(n, dtype=np.uint8)
+        q1 = np.zeros(n, dtype=np.uint8)
+        npar = np.zeros(n, dtype=np.int32)
+        const, pos, idx, scale, shift = [], [], [], [], []
+        for i, (name, qubits, pr) in enumerate(gate_ops):
+            opc[i] = OPCODES[name]
+            q0[i] = qubits[0]
+            if len(qubits) > 1:
+                q1[i] = qubits[1]
+            k = NUM_PARAMS.get(name, 0)
+            if k:
+                npar[i] = k
+                for p in pr:
+                    if isinstance(p, Parameter):
+                        pos.append(len(const)); idx.append(index[p.name]); scale.append(p.scale); shift.append(p.shift)
+                        const.append(0.0)
+                    else:
+                        const.append(float(p))
+        out = (opc, q0, q1, npar, np.asarray(const, dtype=np.float64), np.asarray(pos, dtype=np.int64),
+               np.asarray(idx, dtype=np.int64), np.asarray(scale, dtype=np.float64), np.asarray(shift, dtype=np.float64), len(names))
+        self.__dict__["_flat_tpl"] = (key, out)
+        return out
+
+    def bound_view(self, values):
+        """This circuit with its parameters (name order, as ``bind_parameters``) set to ``values``, as
+        a view that shares the template: ``flat()`` costs one numpy expression."""
+        return _BoundCircuit(self, values)
+
     def size(self):
         return len(self.ops)
 
@@ -209,6 +253,39 @@ class Circuit:
     @staticmethod
     def from_qasm(text):
         return parse_qasm(text)
+
+
+class _BoundCircuit(Circuit):
+    """``Circuit.bound_view``: behaves like ``template.bind_parameters(values)``; the gate list is only
+    materialised if somebody asks for ``ops``-based views (``gate_ops``, ``size`` ...)."""
+
+    def __init__(self, template, values):
+        tpl = template.flat_template()
+        values = np.asarray(values, dtype=np.float64).reshape(-1)
+        if len(values) != tpl[9]:
+            raise ValueError(f"circuit has {tpl[9]} parameters, got {len(values)} values")
+        self.num_qubits = template.num_qubits
+        self.name = template.name
+        self.metadata = template.metadata
+        self._template, self._values = template, values
+
+    @property
+    def ops(self):
+        bound = self.__dict__.get("_bound")
+        if bound is None:
+            bound = self.__dict__["_bound"] = self._template.bind_parameters(list(self._values))
+        return bound.ops
+
+    def flat(self):
+        opc, q0, q1, npar, const, pos, idx, scale, shift, _ = self._template.flat_template()
+        params = const.copy()
+        if len(pos):
+            params[pos] = scale * self._values[idx] + shift
+        return opc, q0, q1, npar, params
+
+    @property
+    def num_parameters(self):
+        return 0
 
 
 def _param_sort_key(name):

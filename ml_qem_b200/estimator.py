@@ -199,7 +199,10 @@ class B200Estimator:
         for (_, pv), i in zip(first, np.unique(np.asarray(gidx, dtype=np.int64), return_index=True)[1].tolist()):
             c = circuits[i]
             if pv:
-                c = c.assign_parameters(list(pv)) if hasattr(c, "assign_parameters") else c.bind_parameters(list(pv))
+                if isinstance(c, circuit_mod.Circuit):
+                    c = c.bound_view(pv)  # the template is walked once for all parameter sets of the ansatz
+                else:
+                    c = c.assign_parameters(list(pv)) if hasattr(c, "assign_parameters") else c.bind_parameters(list(pv))
             bound.append(circuit_mod.from_any(c))
         g_arr = np.asarray(gidx, dtype=np.int64)
         order = np.argsort(g_arr, kind="stable")

@@ -129,3 +129,30 @@ def test_basis_decompositions_equal_their_gates_up_to_phase():
     assert same_up_to_phase(unitary(lambda b: b.h(0)), G.gate_matrix("h"))
     for p, name in ((1, "x"), (2, "y"), (3, "z")):
         assert same_up_to_phase(unitary(lambda b: b.pauli(p, 0)), G.gate_matrix(name))
+
+
+def test_bound_view_encodes_like_bind_parameters():
+    """Circuit.bound_view (what B200Estimator uses for run(batch * [ansatz], ..., parameter_values)):
+    the parametrised circuit is walked once, every parameter set binds with one numpy expression;
+    the encoded batch is identical to binding circuit by circuit."""
+    from ml_qem_b200 import Circuit, engine
+    from ml_qem_b200.circuit import Parameter
+
+    th = [Parameter(f"t[{i}]") for i in range(11)]  # t[10] sorts after t[9], as ParameterVector does
+    c = Circuit(3)
+    for i, t in enumerate(th):
+        c.ry(t, i % 3)
+        if i % 3 == 2:
+            c.cx(0, 1); c.cx(1, 2)
+    c.rz(2 * th[0] + 0.5, 1); c.rx(-th[10], 2); c.u3(th[3] / 2, 0.1, th[4] - 1.0, 0); c.p(0.3, 0)
+    rng = np.random.default_rng(3)
+    vals = rng.uniform(-3, 3, size=(40, 11))
+    obs = [[("ZZI", 1.0), ("XIX", 0.5)], [("IIY", 1.0)]]
+    a = engine.encode_batch([c.bind_parameters(list(v)) for v in vals], [obs] * len(vals))
+    b = engine.encode_batch([c.bound_view(v) for v in vals], [obs] * len(vals))
+    for f in ("n_qubits", "op_offsets", "ops", "params", "obs_offsets", "term_offsets", "term_x", "term_z", "term_coeff"):
+        assert np.array_equal(getattr(a, f), getattr(b, f)), f
+    v = c.bound_view(vals[0])
+    assert v.gate_ops() == c.bind_parameters(list(vals[0])).gate_ops() and v.num_parameters == 0 and v.size() == c.size()
+    with pytest.raises(ValueError):
+        c.bound_view(vals[0][:5])
