@@ -230,3 +230,30 @@ def test_zne_processor_in_the_learning_decorator(lib):
         assert abs(res.values[k] - (1.5 * v1 - 0.5 * v3)) <= 1e-9
         assert abs(res.metadata[k]["original_value"] - v1) <= TOL
     assert abs(proc.process(0.0, circs[0], obs[0], ()) - res.values[0]) <= 1e-12
+
+
+def test_vqe_style_parameter_sweep_of_one_ansatz(lib):
+    """run(batch * [ansatz], batch * [op], parameter_values) as the (patched) VQE of the reference
+    calls it (docs/tutorials/vqe_to_substitute*.py:260-269): 64 parameter sets of one parametrised
+    ansatz with a multi-Pauli Hamiltonian, noisy and ideal, against the oracle (sample) and against
+    circuits bound one by one."""
+    lima, ideal, noisy = _pair(lib)
+    th = [Parameter(f"t[{i}]") for i in range(8)]
+    a = Circuit(5)
+    for i, q in enumerate((0, 1, 3, 4)):
+        a.ry(th[i], q)
+    a.cx(0, 1); a.cx(1, 3); a.cx(3, 4)
+    for i, q in enumerate((0, 1, 3, 4)):
+        a.rz(2 * th[4 + i] - 0.25, q); a.sx(q)
+    ham = [("ZZIII", -1.05), ("IZIZI", 0.39), ("XIIXI", 0.18), ("YYIII", -0.01), ("IIIII", 0.7)]
+    rng = np.random.default_rng(8)
+    vals = rng.uniform(-np.pi, np.pi, size=(64, 8))
+    rn = noisy.run([a] * 64, [ham] * 64, vals).result()
+    ri = ideal.run([a] * 64, [ham] * 64, [tuple(v) for v in vals]).result()
+    bound = [a.bind_parameters(list(v)) for v in vals]
+    rb = noisy.run(bound, [ham] * 64).result()
+    assert np.array_equal(rn.values, rb.values)
+    on = helpers.oracle_noise("fakelima")
+    for k in (0, 31, 63):
+        assert abs(rn.values[k] - helpers.oracle_dm_values(bound[k], [ham], on)[0]) <= TOL
+        assert abs(ri.values[k] - helpers.oracle_sv_values(bound[k], [ham])[0]) <= TOL
