@@ -37,6 +37,19 @@ import numpy as np
 ROOT = os.path.dirname(os.path.abspath(__file__))
 sys.path.insert(0, ROOT)
 
+import gc
+
+
+def _park_setup_objects():
+    """The synthetic workloads are millions of small Python objects (2000 circuits x 484 gate tuples);
+    a generation-2 garbage collection that rescans them costs 50-100 ms and fires at random inside the
+    timed host-buffer calls (seen as sporadic 100 ms calls next to 47 ms ones).  gc.freeze() moves
+    everything built during setup into the permanent generation: the collector stays on, it just no
+    longer rescans the workload."""
+    gc.collect()
+    gc.freeze()
+
+
 METRIC = "noisy+ideal circuits/sec (exact <O>)"
 UNIT = "circuits/s"
 
@@ -301,6 +314,7 @@ def bench_sharded_sv(ctx, name, steps, warmup, first_trotter=1, cpu_check=True, 
 
     for c in circs[:warmup]:
         sv.estimate(c, obs)
+    _park_setup_objects()
     sampler = ClockSampler(ctx.local_rank)
     if rank == 0 and clocks:
         sampler.start()
@@ -411,6 +425,7 @@ def bench_dm(ctx, name, steps, warmup, scale=1.0, cpu_budget=15.0, cpu_first=Non
                     host_threads=max(1, host_threads() // world) if world > 1 else 0, flags=args.flags)
     eng.set_noise(noise.from_backend(wl["backend"]))
 
+    _park_setup_objects()
     # ---- resident-program throughput (`value`)
     st = eng.prepare_dm(batch)
     assert not st.any(), "lowering failed"
