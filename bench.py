@@ -471,10 +471,11 @@ def bench_dm(ctx, name, steps, warmup, scale=1.0, cpu_budget=15.0, cpu_first=Non
     ctx.barrier()
     t0 = time.perf_counter()
     h2d = d2h = 0
-    oc_kernel_ms = 0.0
+    oc_kernel_ms = pre_ms = call_ms = 0.0
     for _ in range(steps):
         ideal_e, noisy_e, st2, st1 = eng.run_meas_data(batch)
         s = eng.stats()
+        pre_ms += s["host_pre_ms"]; call_ms += s["call_wall_ms"]
         onchip = s["n_onchip_circuits"] > 0   # dm_onchip_kernel took the batch: one launch, both sides, no lowering
         oc_kernel_ms += s["kernel_ms"]
         h2d += s["h2d_bytes"] + (0 if onchip else sv_io["h2d_bytes"]); d2h += s["d2h_bytes"] + (0 if onchip else sv_io["d2h_bytes"])
@@ -614,7 +615,11 @@ def bench_dm(ctx, name, steps, warmup, scale=1.0, cpu_budget=15.0, cpu_first=Non
                               (1e3 * t_wall / steps),
                        host_encode_ms=1e3 * t_enc),
         "e2e": {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": h2d // steps, "d2h_bytes_per_step": d2h // steps,
-                "ms_per_step": 1e3 * e2e_s / steps},
+                "ms_per_step": 1e3 * e2e_s / steps,
+                # of which the GPU was busy (CUDA events inside the call, first launch to last value copy): the rest is host
+                "device_ms_per_step": oc_kernel_ms / steps,
+                # density-matrix side inside the library: entry -> first enqueue, and the whole C call (pipelined runs only)
+                "host_pre_ms_per_step": pre_ms / steps, "c_call_ms_per_step": call_ms / steps},
         "gpu_launches": int(launches),
         "roofline": roofline,
         "cpu_baseline": cpu,

@@ -159,6 +159,10 @@ typedef struct {
   int64_t n_tma_sweep_launches;/* of n_sweep_launches: launches of dm_sweep_tma_kernel       */
   int64_t n_onchip_circuits;   /* (circuit, variant) pairs evolved by dm_onchip_kernel (no lowering,
                                   no sweeps: n_sweep_launches = 0 then)                        */
+  double host_pre_ms;          /* pipelined bwq_dm_run / bwq_meas_data_run: wall time from entry to the first
+                                  enqueue (checks, budget, lowering of the first segment)      */
+  double call_wall_ms;         /* wall time of the whole call; call_wall_ms - host_pre_ms - kernel_ms is
+                                  what the host adds after the last device event               */
 } bwq_stats;
 
 typedef struct bwq_ctx bwq_ctx;

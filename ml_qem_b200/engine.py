@@ -78,7 +78,8 @@ class _Stats(C.Structure):
                 ("n_gates", C.c_int64), ("state_bytes_swept", C.c_int64), ("n_other_launches", C.c_int64),
                 ("lower_ms", C.c_double), ("h2d_ms", C.c_double), ("kernel_ms", C.c_double), ("d2h_ms", C.c_double),
                 ("sweep_kernel_ms", C.c_double), ("h2d_bytes", C.c_int64), ("d2h_bytes", C.c_int64),
-                ("sv_state_bytes_swept", C.c_int64), ("n_tma_sweep_launches", C.c_int64), ("n_onchip_circuits", C.c_int64)]
+                ("sv_state_bytes_swept", C.c_int64), ("n_tma_sweep_launches", C.c_int64), ("n_onchip_circuits", C.c_int64), ("host_pre_ms", C.c_double),
+                ("call_wall_ms", C.c_double)]
 
 
 EXPORTS = [
